@@ -1,0 +1,211 @@
+/*
+ * snn_b200.h — C ABI of libsnn_b200.so: the B200-native (sm_100a) replacement for the
+ * per-millisecond spiking-neuron step + dopamine-modulated STDP update of SuReLI/RL-STDP.
+ *
+ * The reference has no FFI layer: its boundary is the Julia-level `Network` API
+ * (constructor, step!/step_LIF!/learn!, public mutable fields).  Every entry point below
+ * cites the reference interface it replaces (paths relative to the reference repo root).
+ * A Julia `ccall` wrapper (julia/RLSTDPB200.jl) and a Python `ctypes` mirror
+ * (rl_stdp_b200/) bind exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns int32 status: 0 = OK, <0 = error; text via snn_last_error()
+ *     (thread-local).  No exception or abort crosses the boundary.
+ *   - neuron / synapse ids are 0-based here (the Julia wrapper adds 1).
+ *   - host buffers are caller-owned and only touched during the call.
+ *   - there is NO CPU backend in this library: without a CUDA device snn_create fails.
+ */
+#ifndef SNN_B200_H
+#define SNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNN_ABI_VERSION 1
+
+/* status codes */
+enum {
+  SNN_OK = 0,
+  SNN_ERR_INVALID = -1,   /* bad argument / config */
+  SNN_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  SNN_ERR_NODEVICE = -3,  /* no usable CUDA device: the library never falls back to CPU */
+  SNN_ERR_STATE = -4,     /* call order violated (e.g. step before synapses were set) */
+  SNN_ERR_CAPACITY = -5   /* an output buffer was too small (results truncated) */
+};
+
+enum { SNN_F32 = 0, SNN_F64 = 1 };
+
+/* propagation mode */
+enum {
+  SNN_MODE_FAST = 0,  /* push: atomic scatter-add of weights into the current array */
+  SNN_MODE_EXACT = 1  /* pull: every target sums its spiking sources in ascending presynaptic
+                         id, the accumulation order of new_net.jl:116-118 — bit-reproducible */
+};
+
+enum { SNN_NOISE_NONE = 0, SNN_NOISE_REPLAY = 1, SNN_NOISE_PHILOX = 2 };
+
+/* when the eligibility trace sd is decayed (SURVEY §8a switch list) */
+enum {
+  SNN_SD_DECAY_ON_LEARN = 0, /* new_net.jl:141  sd .*= 0.99 inside learn!            */
+  SNN_SD_DECAY_EVERY_STEP = 1, /* net_arch.jl:207-209 de[l] .*= tde every ms (LIF)   */
+  SNN_SD_DECAY_NEVER = 2     /* net_arch.jl:328-379 Izhikevich layered path          */
+};
+
+/* learn-rate form: w += rate * sd */
+enum {
+  SNN_RATE_BASE_PLUS_DA = 0, /* (learn_base + da)   new_net.jl:137, net_res.jl:213 */
+  SNN_RATE_DA = 1,           /* da                  net_arch.jl:217                */
+  SNN_RATE_ETA_DA = 2        /* eta*da              net_arch.jl:226                */
+};
+
+/* Plain-old-data configuration of one (possibly batched) sparse Izhikevich DA-STDP network.
+ * Replaces: `Network(n_neurons, connectivity, n_exc)` Old_net/new_net.jl:80-98 and the
+ * hard-coded constants of spike!/learn! (new_net.jl:109-142); the YAML `param` Dict of
+ * net_res.jl / net_arch.jl (Modules/cfg.yml) maps onto the same fields. */
+typedef struct snn_config {
+  int32_t struct_size;     /* = sizeof(snn_config), checked */
+  int32_t dtype;           /* SNN_F32 | SNN_F64 : arithmetic + storage type of state */
+  int32_t mode;            /* SNN_MODE_FAST | SNN_MODE_EXACT */
+  int32_t device;          /* CUDA device ordinal */
+  int64_t n_neurons;       /* total neurons = n_instances * n_per_instance */
+  int64_t n_per_instance;  /* neurons of one independent network instance */
+  int64_t n_exc;           /* per instance: local ids [0,n_exc) excitatory, rest inhibitory */
+  int32_t max_delay;       /* axonal delays are 1..max_delay steps (1 = reference semantics) */
+  int32_t threshold_ge;    /* 0: spike iff v-ho >  vthresh (new_net.jl:112)
+                              1: spike iff v-ho >= vthresh (NeuronModel.jl / Julia_DA_STDPv2.jl:75) */
+  double vthresh;          /* 30   new_net.jl:112 */
+  double v_reset;          /* -65  new_net.jl:113 (param "c") */
+  double a_exc, a_inh;     /* 0.02 / 0.1  new_net.jl:84 */
+  double d_exc, d_inh;     /* 8 / 2       new_net.jl:83 */
+  double trace_set;        /* 0.1   new_net.jl:123 */
+  double trace_decay;      /* 0.95  new_net.jl:130 */
+  double apost;            /* 1.0   LTP amplitude new_net.jl:126 */
+  double apre;             /* 1.5   LTD amplitude new_net.jl:127 */
+  double da_decay;         /* 0.995 new_net.jl:131 */
+  double learn_base;       /* 0.002 new_net.jl:137 */
+  double eta;              /* only for SNN_RATE_ETA_DA */
+  double wmin, wmax;       /* clamp bounds 0 / 4  new_net.jl:138 */
+  double sd_decay;         /* 0.99  new_net.jl:141 */
+  int32_t sd_decay_mode;   /* SNN_SD_DECAY_* */
+  int32_t rate_mode;       /* SNN_RATE_* */
+  int32_t noise_mode;      /* SNN_NOISE_* ; REPLAY = caller passes the recorded 13*(rand-0.5) */
+  int32_t plastic_ei;      /* 1: exc->inh synapses are plastic too (variant A / net_res arch==[0]);
+                              0: only exc->exc (net_res.jl layered) */
+  double noise_amp;        /* 13.0 (PHILOX mode: I = noise_amp*(U-0.5))  new_net.jl:111 */
+  uint64_t noise_seed;     /* PHILOX key */
+  double theta;            /* homeostasis increment (0 = off)  net_res.jl:171 */
+  double ttheta;           /* homeostasis decay                net_res.jl:204 */
+  int64_t ho_from;         /* local ids >= ho_from (and < n_exc) get homeostasis (arch[1]) */
+  int32_t reserved[8];
+} snn_config;
+
+typedef struct snn_net snn_net;
+
+/* dopamine injection event: after step `step` (0-based inside the window) of instance
+ * `instance`, da += amount.  Replaces `n.da += 0.5` newnet_DASTDP.jl:54-56 (which runs after
+ * step! returns) and Latencysim_rewardv0.jl:141-145. */
+typedef struct snn_da_event {
+  int32_t step;
+  int32_t instance;
+  double amount;
+} snn_da_event;
+
+/* forced-spike input: before step `step`, v[neuron] = 40.0.
+ * Replaces input!(net, ::Array{Int64}) new_net.jl:104-106. */
+typedef struct snn_force_event {
+  int32_t step;
+  int32_t neuron;
+} snn_force_event;
+
+/* fields for snn_get_array / snn_set_array */
+enum {
+  SNN_FIELD_V = 0,       /* [n_neurons] real  — Network.v  new_net.jl:9  */
+  SNN_FIELD_U = 1,       /* [n_neurons] real  — Network.u  new_net.jl:10 */
+  SNN_FIELD_TRACE = 2,   /* [n_neurons] real  — Network.STDP new_net.jl:17 (post-decay value) */
+  SNN_FIELD_HO = 3,      /* [n_neurons] real  — Network.ho net_res.jl:27 */
+  SNN_FIELD_W = 4,       /* [n_synapses] real, caller's CSR order — Network.s  new_net.jl:15 */
+  SNN_FIELD_SD = 5,      /* [n_synapses] real, caller's CSR order — Network.sd new_net.jl:16
+                            (only plastic synapses are maintained; others read 0) */
+  SNN_FIELD_DA = 6,      /* [n_instances] real — Network.da new_net.jl:23 */
+  SNN_FIELD_I = 7        /* [n_neurons] real — Network.I new_net.jl:22 (input current used by
+                            the last Euler update) */
+};
+
+/* per-window statistics filled by snn_step */
+typedef struct snn_step_stats {
+  int64_t n_spikes;          /* spikes emitted in the window */
+  int64_t n_syn_events;      /* spike deliveries (one spike across one synapse) */
+  int64_t n_ltp_events;      /* incoming plastic synapses visited for LTP */
+  double device_ms;          /* CUDA-event time of the window on the net's stream */
+  double learn_ms;           /* summed CUDA-event time of the learn kernel launches (profiling on) */
+  double neuron_ms;          /* same for the neuron kernel */
+  double synapse_ms;         /* same for the propagate+STDP kernel */
+  int32_t learn_launches, neuron_launches, synapse_launches;
+  int32_t reserved;
+} snn_step_stats;
+
+const char* snn_last_error(void);
+int32_t snn_abi_version(void);
+
+/* Fill `cfg` with the constants of variant A (Old_net/new_net.jl:80-142). */
+int32_t snn_config_default(snn_config* cfg);
+
+/* Replaces the Network constructors (new_net.jl:58-98): allocates all device state,
+ * v = v_reset, u = 0.2*v (new_net.jl:81-82), traces/sd/da = 0. */
+int32_t snn_create(const snn_config* cfg, snn_net** out);
+int32_t snn_destroy(snn_net* net);
+
+/* Synapses in CSR by presynaptic neuron.  rowptr[n_neurons+1], post[E] (global 0-based ids, must
+ * stay inside the presynaptic neuron's instance), w[E] (float64), delay[E] in 1..max_delay or
+ * NULL (= all 1).  Replaces `s`/`connection` of new_net.jl:14-15,27-56 and post/delays of
+ * Old_net/DASTDP.jl:32-49.  The library re-sorts each row by (delay, given order) and builds
+ * the incoming-synapse index on the device. */
+int32_t snn_set_synapses_csr(snn_net* net, const int64_t* rowptr, const int32_t* post,
+                             const double* w, const uint8_t* delay);
+
+/* Exactly what variant A holds: s[pre,post] and connection[pre,post], column-major N x N
+ * (new_net.jl:14-15, 86-91); single instance only. */
+int32_t snn_set_synapses_dense(snn_net* net, const double* s_colmajor,
+                               const int64_t* connection_colmajor);
+
+/* Run n_steps calls of step!(net[, input_spikes], train) (new_net.jl:146-161) on the device
+ * with no host round trip.
+ *   noise       [n_steps][n_neurons] float64 (REPLAY mode) or NULL
+ *   train_flags [n_steps] or NULL (= never learn); train_flags[k]!=0 -> learn! after step k
+ *   force       forced spikes (input!), sorted by step, may be NULL
+ *   da          dopamine events sorted by step, may be NULL
+ *   spikes_out  ids of spiking neurons, ascending inside each step, concatenated; NULL = not
+ *               recorded.  spike_offsets[n_steps+1] delimits the steps.
+ * Returns SNN_ERR_CAPACITY (after finishing the window) if more than spikes_cap spikes occurred. */
+int32_t snn_step(snn_net* net, int32_t n_steps, const double* noise, const uint8_t* train_flags,
+                 const snn_force_event* force, int32_t n_force, const snn_da_event* da,
+                 int32_t n_da, int32_t* spikes_out, int64_t* spike_offsets, int64_t spikes_cap,
+                 snn_step_stats* stats);
+
+/* `net.da += x` (newnet_DASTDP.jl:55, teacher_sim.jl:133, critic_sim.jl:69) */
+int32_t snn_add_dopamine(snn_net* net, int32_t instance, double amount);
+/* `net.v .= c` (cartpole_fitness.jl:71) */
+int32_t snn_reset_v(snn_net* net);
+
+/* Field access (`net.s[n1,n2] = 0.0` newnet_DASTDP.jl:19, reads at :58-59).  Host buffers are
+ * always float64 regardless of dtype; count = number of elements. */
+int32_t snn_get_array(snn_net* net, int32_t field, double* host, int64_t count);
+int32_t snn_set_array(snn_net* net, int32_t field, const double* host, int64_t count);
+
+int64_t snn_n_synapses(const snn_net* net);
+int64_t snn_step_index(const snn_net* net);
+
+/* 1: record CUDA events around every kernel launch so snn_step_stats carries per-kernel
+ * times (used by bench.py for the roofline); 0 (default): only the window events. */
+int32_t snn_set_profiling(snn_net* net, int32_t enable);
+/* Use an externally owned CUDA stream (cudaStream_t) instead of the net's own. */
+int32_t snn_set_stream(snn_net* net, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNN_B200_H */

@@ -1,0 +1,174 @@
+// capi.cu — the extern "C" boundary of libsnn_b200.so (declared in include/snn_b200.h).
+// Plain pointers and sizes only; every error becomes a status code + thread-local message.
+#include <string.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "snn_common.h"
+
+struct snn_net {
+  snn_config cfg;
+  std::unique_ptr<snn::IEngine> eng;
+};
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+int validate(const snn_config& c, std::string& err) {
+  if (c.struct_size != (int32_t)sizeof(snn_config)) { err = "snn_config.struct_size mismatch (ABI)"; return SNN_ERR_INVALID; }
+  if (c.dtype != SNN_F32 && c.dtype != SNN_F64) { err = "dtype must be SNN_F32 or SNN_F64"; return SNN_ERR_INVALID; }
+  if (c.mode != SNN_MODE_FAST && c.mode != SNN_MODE_EXACT) { err = "bad mode"; return SNN_ERR_INVALID; }
+  if (c.n_neurons <= 0 || c.n_per_instance <= 0 || c.n_neurons % c.n_per_instance != 0) {
+    err = "n_neurons must be a positive multiple of n_per_instance"; return SNN_ERR_INVALID;
+  }
+  if (c.n_exc < 0 || c.n_exc > c.n_per_instance) { err = "0 <= n_exc <= n_per_instance"; return SNN_ERR_INVALID; }
+  if (c.max_delay < 1 || c.max_delay > snn::kMaxDelay) { err = "max_delay must be in 1..63"; return SNN_ERR_INVALID; }
+  if (c.n_neurons > (1ll << snn::kPreBits)) { err = "n_neurons must be <= 2^26"; return SNN_ERR_INVALID; }
+  if (c.noise_mode < SNN_NOISE_NONE || c.noise_mode > SNN_NOISE_PHILOX) { err = "bad noise_mode"; return SNN_ERR_INVALID; }
+  if (c.sd_decay_mode < 0 || c.sd_decay_mode > 2 || c.rate_mode < 0 || c.rate_mode > 2) { err = "bad sd_decay_mode / rate_mode"; return SNN_ERR_INVALID; }
+  if (!(c.wmin <= c.wmax)) { err = "wmin must be <= wmax"; return SNN_ERR_INVALID; }
+  return SNN_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* snn_last_error(void) { return g_err.c_str(); }
+int32_t snn_abi_version(void) { return SNN_ABI_VERSION; }
+
+int32_t snn_config_default(snn_config* c) {
+  if (!c) return fail(SNN_ERR_INVALID, "null config");
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(snn_config);
+  c->dtype = SNN_F32; c->mode = SNN_MODE_FAST; c->device = 0;
+  c->n_neurons = 1000; c->n_per_instance = 1000; c->n_exc = 800; c->max_delay = 1;
+  c->threshold_ge = 0; c->vthresh = 30.0; c->v_reset = -65.0;
+  c->a_exc = 0.02; c->a_inh = 0.1; c->d_exc = 8.0; c->d_inh = 2.0;
+  c->trace_set = 0.1; c->trace_decay = 0.95; c->apost = 1.0; c->apre = 1.5;
+  c->da_decay = 0.995; c->learn_base = 0.002; c->eta = 0.0; c->wmin = 0.0; c->wmax = 4.0;
+  c->sd_decay = 0.99; c->sd_decay_mode = SNN_SD_DECAY_ON_LEARN; c->rate_mode = SNN_RATE_BASE_PLUS_DA;
+  c->noise_mode = SNN_NOISE_REPLAY; c->plastic_ei = 1; c->noise_amp = 13.0; c->noise_seed = 0;
+  c->theta = 0.0; c->ttheta = 1.0; c->ho_from = 0;
+  return SNN_OK;
+}
+
+int32_t snn_create(const snn_config* cfg, snn_net** out) {
+  if (!cfg || !out) return fail(SNN_ERR_INVALID, "null argument");
+  *out = nullptr;
+  std::string err;
+  int rc = validate(*cfg, err);
+  if (rc) return fail(rc, err);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0)
+    return fail(SNN_ERR_NODEVICE, std::string("no CUDA device (libsnn_b200 has no CPU fallback): ") +
+                                      (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0"));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SNN_ERR_INVALID, "device ordinal out of range");
+  snn_net* n = new (std::nothrow) snn_net;
+  if (!n) return fail(SNN_ERR_INVALID, "out of host memory");
+  n->cfg = *cfg;
+  n->eng.reset(cfg->dtype == SNN_F64 ? snn::make_engine_f64(*cfg) : snn::make_engine_f32(*cfg));
+  rc = n->eng->init(err);
+  if (rc) { delete n; return fail(rc, err); }
+  *out = n;
+  return SNN_OK;
+}
+
+int32_t snn_destroy(snn_net* net) {
+  if (!net) return SNN_OK;
+  cudaSetDevice(net->cfg.device);
+  delete net;
+  return SNN_OK;
+}
+
+int32_t snn_set_synapses_csr(snn_net* net, const int64_t* rowptr, const int32_t* post, const double* w,
+                             const uint8_t* delay) {
+  if (!net || !rowptr) return fail(SNN_ERR_INVALID, "null argument");
+  const int64_t E = rowptr[net->cfg.n_neurons];
+  if (E > 0 && (!post || !w)) return fail(SNN_ERR_INVALID, "null post / w");
+  std::string err;
+  cudaSetDevice(net->cfg.device);
+  snn::Topo topo;
+  int rc = snn::build_topology(net->cfg, rowptr, post, delay, &topo, net->eng->stream(), err);
+  if (rc) return fail(rc, err);
+  rc = net->eng->set_topology(std::move(topo), w, err);
+  if (rc) return fail(rc, err);
+  return SNN_OK;
+}
+
+int32_t snn_set_synapses_dense(snn_net* net, const double* s, const int64_t* connection) {
+  if (!net || !s || !connection) return fail(SNN_ERR_INVALID, "null argument");
+  const int64_t N = net->cfg.n_neurons;
+  if (net->cfg.n_per_instance != N) return fail(SNN_ERR_INVALID, "dense synapses: single instance only");
+  if (net->cfg.max_delay != 1) return fail(SNN_ERR_INVALID, "dense synapses carry no delays: max_delay must be 1");
+  std::vector<int64_t> rowptr(N + 1, 0);
+  std::vector<int32_t> post;
+  std::vector<double> w;
+  for (int64_t i = 0; i < N; ++i) {
+    for (int64_t j = 0; j < N; ++j)
+      if (connection[i + N * j] != 0) { post.push_back((int32_t)j); w.push_back(s[i + N * j]); }
+    rowptr[i + 1] = (int64_t)post.size();
+  }
+  return snn_set_synapses_csr(net, rowptr.data(), post.data(), w.data(), nullptr);
+}
+
+int32_t snn_step(snn_net* net, int32_t n_steps, const double* noise, const uint8_t* train_flags,
+                 const snn_force_event* force, int32_t n_force, const snn_da_event* da, int32_t n_da,
+                 int32_t* spikes_out, int64_t* spike_offsets, int64_t spikes_cap, snn_step_stats* stats) {
+  if (!net) return fail(SNN_ERR_INVALID, "null net");
+  if ((n_force > 0 && !force) || (n_da > 0 && !da) || n_force < 0 || n_da < 0)
+    return fail(SNN_ERR_INVALID, "event list pointer / count mismatch");
+  snn::StepArgs a{n_steps, noise, train_flags, force, n_force, da, n_da, spikes_out, spike_offsets, spikes_cap, stats};
+  std::string err;
+  int rc = net->eng->step(a, err);
+  if (rc) return fail(rc, err);
+  return SNN_OK;
+}
+
+int32_t snn_add_dopamine(snn_net* net, int32_t instance, double amount) {
+  if (!net) return fail(SNN_ERR_INVALID, "null net");
+  std::string err;
+  int rc = net->eng->add_dopamine(instance, amount, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_reset_v(snn_net* net) {
+  if (!net) return fail(SNN_ERR_INVALID, "null net");
+  std::string err;
+  int rc = net->eng->reset_v(err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_get_array(snn_net* net, int32_t field, double* host, int64_t count) {
+  if (!net || !host) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->get_array(field, host, count, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_set_array(snn_net* net, int32_t field, const double* host, int64_t count) {
+  if (!net || !host) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->set_array(field, host, count, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int64_t snn_n_synapses(const snn_net* net) { return net ? net->eng->n_synapses() : -1; }
+int64_t snn_step_index(const snn_net* net) { return net ? net->eng->step_index() : -1; }
+
+int32_t snn_set_profiling(snn_net* net, int32_t enable) {
+  if (!net) return fail(SNN_ERR_INVALID, "null net");
+  net->eng->set_profiling(enable != 0);
+  return SNN_OK;
+}
+
+int32_t snn_set_stream(snn_net* net, void* cuda_stream) {
+  if (!net) return fail(SNN_ERR_INVALID, "null net");
+  net->eng->set_stream((cudaStream_t)cuda_stream);
+  return SNN_OK;
+}
+
+}  // extern "C"

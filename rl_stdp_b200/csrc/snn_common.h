@@ -1,0 +1,82 @@
+// snn_common.h — host-side types shared by the translation units of libsnn_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/snn_b200.h"
+
+namespace snn {
+
+constexpr int kMaxDelay = 63;        // delay-1 is packed into 6 bits of in_pre
+constexpr int kPreBits = 26;         // neuron ids < 2^26 in the packed incoming entry
+constexpr uint32_t kPreMask = (1u << kPreBits) - 1u;
+
+#define SNN_CUDA_OK(expr)                                                        \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) {                                                     \
+      err = std::string(#expr) + ": " + cudaGetErrorString(_e);                  \
+      return SNN_ERR_CUDA;                                                       \
+    }                                                                            \
+  } while (0)
+
+// Type-independent synapse topology, built once on the device (snn_build.cu).
+// Internal synapse order: ascending (pre, delay, caller position).
+struct Topo {
+  int64_t N = 0, E = 0, Nper = 0, Ne = 0;
+  int32_t Dmax = 1, R = 2, B = 1;
+  uint32_t* seg = nullptr;      // [N*(Dmax+1)] seg[i*(Dmax+1)+a] = first synapse of row i with delay a+1
+  int32_t* post = nullptr;      // [E]
+  uint32_t* perm = nullptr;     // [E] internal position -> caller position
+  uint32_t* colptr = nullptr;   // [N+1] incoming lists, ascending (pre, internal position)
+  uint32_t* col_npl = nullptr;  // [N] length of the plastic prefix of each incoming list
+  uint32_t* in_syn = nullptr;   // [E] internal synapse position
+  uint32_t* in_pre = nullptr;   // [E] (delay-1) << 26 | pre
+  void release();
+};
+
+int build_topology(const snn_config& cfg, const int64_t* h_rowptr, const int32_t* h_post,
+                   const uint8_t* h_delay, Topo* out, cudaStream_t stream, std::string& err);
+
+// Sort every [off[k], off[k+1]) segment of keys ascending (spike record formatting).
+int sort_segments(int32_t* d_keys, int64_t n_items, const int32_t* d_offsets, int32_t n_segments,
+                  cudaStream_t stream, std::string& err);
+
+struct StepArgs {
+  int32_t n_steps;
+  const double* noise;
+  const uint8_t* train_flags;
+  const snn_force_event* force;
+  int32_t n_force;
+  const snn_da_event* da;
+  int32_t n_da;
+  int32_t* spikes_out;
+  int64_t* spike_offsets;
+  int64_t spikes_cap;
+  snn_step_stats* stats;
+};
+
+class IEngine {
+ public:
+  virtual ~IEngine() {}
+  virtual int init(std::string& err) = 0;
+  virtual int set_topology(Topo&& topo, const double* h_w_caller, std::string& err) = 0;
+  virtual int step(const StepArgs& a, std::string& err) = 0;
+  virtual int get_array(int field, double* host, int64_t count, std::string& err) = 0;
+  virtual int set_array(int field, const double* host, int64_t count, std::string& err) = 0;
+  virtual int add_dopamine(int instance, double amount, std::string& err) = 0;
+  virtual int reset_v(std::string& err) = 0;
+  virtual int64_t n_synapses() const = 0;
+  virtual int64_t step_index() const = 0;
+  virtual void set_profiling(bool on) = 0;
+  virtual void set_stream(cudaStream_t s) = 0;
+  virtual cudaStream_t stream() const = 0;
+};
+
+IEngine* make_engine_f32(const snn_config& cfg);
+IEngine* make_engine_f64(const snn_config& cfg);
+
+}  // namespace snn

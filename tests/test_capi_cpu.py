@@ -1,0 +1,80 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/snn_b200.h
+declares, validates configs, and — with no CUDA device — refuses to run instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from rl_stdp_b200 import build, _lib as L
+    build.build()
+    return L
+
+
+def test_header_symbols_all_exported():
+    L = _lib()
+    lib = L.load()
+    hdr = open(os.path.join(ROOT, "include", "snn_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(snn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/snn_b200.h but not exported"
+    assert names == set(L.SYMBOLS), names ^ set(L.SYMBOLS)
+    assert lib.snn_abi_version() == 1
+
+
+def test_config_struct_matches_header():
+    L = _lib()
+    cfg = L.SnnConfig()
+    L.check(L.load().snn_config_default(C.byref(cfg)))
+    assert cfg.struct_size == C.sizeof(L.SnnConfig)
+    # variant A constants (Old_net/new_net.jl:80-142)
+    assert (cfg.vthresh, cfg.v_reset, cfg.a_exc, cfg.a_inh, cfg.d_exc, cfg.d_inh) == (30.0, -65.0, 0.02, 0.1, 8.0, 2.0)
+    assert (cfg.trace_set, cfg.trace_decay, cfg.apost, cfg.apre) == (0.1, 0.95, 1.0, 1.5)
+    assert (cfg.da_decay, cfg.learn_base, cfg.wmin, cfg.wmax, cfg.sd_decay) == (0.995, 0.002, 0.0, 4.0, 0.99)
+    assert cfg.noise_amp == 13.0 and cfg.plastic_ei == 1
+
+
+def test_invalid_configs_rejected():
+    L = _lib()
+    lib = L.load()
+    for field, val, word in [("max_delay", 0, b"max_delay"), ("max_delay", 64, b"max_delay"), ("dtype", 7, b"dtype"),
+                             ("n_per_instance", 333, b"multiple"), ("n_exc", 5000, b"n_exc"),
+                             ("struct_size", 8, b"struct_size")]:
+        cfg = L.SnnConfig()
+        lib.snn_config_default(C.byref(cfg))
+        setattr(cfg, field, val)
+        h = C.c_void_p()
+        assert lib.snn_create(C.byref(cfg), C.byref(h)) == -1
+        assert word in lib.snn_last_error(), (field, lib.snn_last_error())
+        assert not h.value
+    assert lib.snn_step(None, 1, None, None, None, 0, None, 0, None, None, 0, None) == -1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path fails loudly (SNN_ERR_NODEVICE)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = _lib()
+    lib = L.load()
+    cfg = L.SnnConfig()
+    lib.snn_config_default(C.byref(cfg))
+    h = C.c_void_p()
+    rc = lib.snn_create(C.byref(cfg), C.byref(h))
+    assert rc == -3 and b"no CPU fallback" in lib.snn_last_error()
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under rl_stdp_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "rl_stdp_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/_" not in txt, f

@@ -1,0 +1,274 @@
+"""GPU parity: the CUDA hot path (through the C ABI) against the CPU oracle on identical,
+replayed inputs.  fp64 exact mode: spike times identical, state within 1e-9 relative
+(BASELINE.json north_star).  fp32 / atomic mode: statistics within stated tolerances.
+
+The oracle is a restatement of the Julia reference (oracle/snn_oracle.c cites the lines), not
+the Julia binary: the reference ships no golden vectors for this path.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import c1_inputs, rel_err, run_oracle_sparse
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9  # north_star: "weights and traces within 1e-9 relative error"
+
+
+def _lib():
+    from rl_stdp_b200 import _lib as L
+    return L
+
+
+def test_c1_variant_a_fp64_exact_1000ms():
+    """Config C1 (Izhikevich 2007 net, N=1000, 800/200, p=0.1) against the LITERAL dense
+    restatement of new_net.jl:109-161, 1000 ms, learn every 10 ms, dopamine +0.5 injected twice."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200.network import Network
+    L = _lib()
+    n, ne, t = 1000, 800, 1000
+    conn, noise, train = c1_inputs(n, ne, 0.1, t)
+    ora = po.DenseA(n, ne, conn)
+    net = Network(n, 0.1, ne, connection=conn, dtype="f64", mode="exact")
+    # n.s[n1,n2] = 0.0 (newnet_DASTDP.jl:15-19)
+    n1 = 1
+    n2 = int(net.post(n1)[0])
+    ora.s[n1, n2] = 0.0
+    net.s[n1, n2] = 0.0
+    da_events = [(299, 0, 0.5), (650, 0, 0.5)]
+    ref = []
+    for k in range(t):
+        ref.append(ora.step(noise[k], bool(train[k])))
+        for s, _, a in da_events:
+            if s == k:
+                ora.da += a
+    spikes, stats = net.run(noise, train, da_events=da_events)
+    for k in range(t):
+        assert np.array_equal(spikes[k], ref[k]), f"spike mismatch at ms {k}"
+    assert stats.n_spikes == sum(len(r) for r in ref)
+    pre, post = np.nonzero(conn)
+    exc = pre < ne
+    w = net._sparse.get(L.FIELD_W)
+    sd = net._sparse.get(L.FIELD_SD)
+    assert rel_err(w, ora.s[pre, post]) <= RTOL
+    assert rel_err(sd[exc], ora.sd[pre, post][exc]) <= RTOL
+    assert rel_err(net.v, ora.v) <= RTOL
+    assert rel_err(net.u, ora.u) <= RTOL
+    assert rel_err(net.STDP, ora.STDP) <= RTOL
+    assert rel_err([net.da], [ora.da]) <= RTOL
+    assert rel_err(net.I, ora.I) <= RTOL
+    # expected synaptic events = sum over spikes of the spiker's fan-out
+    fan = conn.sum(axis=1)
+    assert stats.n_syn_events == int(sum(fan[r].sum() for r in ref))
+
+
+@pytest.mark.parametrize("dmax", [1, 5, 20])
+def test_sparse_delays_fp64_exact(dmax):
+    """CSR + axonal delays (the generalisation) against the sparse oracle, with learning,
+    dopamine events and forced spikes."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    n, ne, fan, t = 2000, 1600, 60, 400
+    rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=11 + dmax)
+    noise = synth.thalamic_noise(t, n, seed=5)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    da_events = [(57, 0, 0.5), (57, 0, 0.25), (203, 0, 0.5)]
+    force = [(0, 3), (0, 4), (100, 7), (101, 1999)]
+    ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax)
+    ref = run_oracle_sparse(ora, noise, train, da_events, force)
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="exact", max_delay=dmax)
+    spikes, stats = net.run(t, noise, train, da_events=da_events, force=force)
+    for k in range(t):
+        assert np.array_equal(spikes[k], ref[k]), f"spike mismatch at ms {k}"
+    assert sum(len(r) for r in ref) > 500
+    plastic = np.repeat(np.arange(n), np.diff(rowptr)) < ne
+    assert rel_err(net.get(L.FIELD_W), ora.get(4)) <= RTOL
+    assert rel_err(net.get(L.FIELD_SD)[plastic], ora.get(5)[plastic]) <= RTOL
+    for f in (L.FIELD_V, L.FIELD_U, L.FIELD_TRACE, L.FIELD_DA):
+        assert rel_err(net.get(f), ora.get(f)) <= RTOL
+    ev, ltp = ora.counters()
+    assert stats.n_syn_events == ev
+    assert stats.n_ltp_events == ltp
+
+
+def test_windows_compose():
+    """Two windows of 150 ms == one window of 300 ms (state carried on the device)."""
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    n, ne, fan, dmax, t = 1000, 800, 50, 7, 300
+    rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=3)
+    noise = synth.thalamic_noise(t, n, seed=6)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    a = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="exact", max_delay=dmax)
+    b = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="exact", max_delay=dmax)
+    sa, _ = a.run(t, noise, train, da_events=[(149, 0, 0.5)])
+    sb1, _ = b.run(150, noise[:150], train[:150])
+    b.add_dopamine(0.5)
+    sb2, _ = b.run(150, noise[150:], train[150:])
+    sb = sb1 + sb2
+    for k in range(t):
+        assert np.array_equal(sa[k], sb[k])
+    for f in (L.FIELD_W, L.FIELD_SD, L.FIELD_V, L.FIELD_U, L.FIELD_TRACE, L.FIELD_DA):
+        assert np.array_equal(a.get(f), b.get(f))
+
+
+def test_philox_noise_matches_oracle():
+    """On-device Philox4x32-10 thalamic noise == the oracle's, so throughput runs (no replayed
+    noise array) are still checkable."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    n, ne, fan, dmax, t, seed = 1500, 1200, 40, 3, 200, 0xDEADBEEF12345
+    rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=21)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax)
+    ref = [ora.step(po.philox_noise(seed, k, n), bool(train[k])) for k in range(t)]
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="exact", noise="philox",
+                        max_delay=dmax, noise_seed=seed)
+    spikes, _ = net.run(t, None, train)
+    for k in range(t):
+        assert np.array_equal(spikes[k], ref[k]), k
+    assert rel_err(net.get(L.FIELD_W), ora.get(4)) <= RTOL
+    assert sum(len(r) for r in ref) > 100
+
+
+def test_batched_instances_equal_singles():
+    """B independent instances in one handle == B single-instance runs (block-diagonal net)."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    nper, ne, fan, dmax, t, B = 400, 320, 40, 4, 250, 3
+    rowptr, post, w, delay = synth.fixed_fanout(nper, ne, fan, dmax, seed=31, n_instances=B)
+    noise = synth.thalamic_noise(t, nper * B, seed=8)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    da_events = [(40, 1, 0.5), (120, 2, 0.3)]
+    ora = po.Sparse(nper * B, ne, rowptr, post, w, delay, max_delay=dmax, n_per_instance=nper)
+    ref = run_oracle_sparse(ora, noise, train, da_events)
+    net = SparseNetwork(nper, ne, rowptr, post, w, delay, n_instances=B, dtype="f64", mode="exact",
+                        max_delay=dmax)
+    spikes, _ = net.run(t, noise, train, da_events=da_events)
+    for k in range(t):
+        assert np.array_equal(spikes[k], ref[k]), k
+    assert rel_err(net.get(L.FIELD_W), ora.get(4)) <= RTOL
+    assert rel_err(net.get(L.FIELD_DA), ora.get(6)) <= RTOL
+    # and instance 1 alone reproduces its block
+    sl = slice(rowptr[nper], rowptr[2 * nper])
+    rp1 = rowptr[nper:2 * nper + 1] - rowptr[nper]
+    one = SparseNetwork(nper, ne, rp1, post[sl] - nper, w[sl], delay[sl], dtype="f64", mode="exact",
+                        max_delay=dmax)
+    s1, _ = one.run(t, noise[:, nper:2 * nper], train, da_events=[(40, 0, 0.5)])
+    for k in range(t):
+        blk = spikes[k][(spikes[k] >= nper) & (spikes[k] < 2 * nper)] - nper
+        assert np.array_equal(s1[k], blk), k
+
+
+def test_homeostasis_and_ge_threshold():
+    """threshold on v-ho with `>=`, theta/ttheta homeostasis beyond ho_from (net_res.jl:167-171,204),
+    exc->exc-only plasticity (net_res.jl:213-216)."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    n, ne, fan, t = 800, 640, 50, 300
+    rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, 1, seed=41)
+    noise = synth.thalamic_noise(t, n, seed=9, amp=16.0)
+    train = np.ones(t, np.uint8)
+    kw = dict(threshold_ge=1, theta=2.0, ttheta=0.9999, ho_from=100, plastic_ei=0, wmax=3.0,
+              apost=0.8, apre=1.1)
+    ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=1, **kw)
+    ref = run_oracle_sparse(ora, noise, train, [(10, 0, 0.5)])
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="exact", max_delay=1, **kw)
+    spikes, _ = net.run(t, noise, train, da_events=[(10, 0, 0.5)])
+    for k in range(t):
+        assert np.array_equal(spikes[k], ref[k]), k
+    assert rel_err(net.get(L.FIELD_W), ora.get(4)) <= RTOL
+    assert rel_err(net.get(L.FIELD_HO), ora.get(3)) <= RTOL
+    pre = np.repeat(np.arange(n), np.diff(rowptr))
+    plastic = (pre < ne) & (post < ne)
+    assert rel_err(net.get(L.FIELD_SD)[plastic], ora.get(5)[plastic]) <= RTOL
+    assert sum(len(r) for r in ref) > 200
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_fast_mode_statistics(dtype):
+    """Production mode (atomic scatter; fp32): the dynamics are chaotic, so parity is statistical
+    (SURVEY §8d gates): mean rate within 2 %, exc/inh rates within 5 %, mean plastic weight within
+    1 %, and the early spike trains (before divergence) identical for fp64."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    n, ne, fan, dmax, t = 4000, 3200, 100, 10, 1500
+    rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=51)
+    noise = synth.thalamic_noise(t, n, seed=10)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    da_events = [(500, 0, 0.5), (1000, 0, 0.5)]
+    ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax)
+    ref = run_oracle_sparse(ora, noise, train, da_events)
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype=dtype, mode="fast", max_delay=dmax)
+    spikes, stats = net.run(t, noise, train, da_events=da_events)
+    nr = np.array([len(r) for r in ref], float)
+    ng = np.array([len(s) for s in spikes], float)
+    assert nr.sum() > 5000
+    assert abs(ng.sum() - nr.sum()) / nr.sum() < 0.02
+    re = sum(int((r < ne).sum()) for r in ref)
+    ge = sum(int((s < ne).sum()) for s in spikes)
+    assert abs(ge - re) / re < 0.05
+    ri, gi = nr.sum() - re, ng.sum() - ge
+    assert abs(gi - ri) / max(ri, 1) < 0.05
+    plastic = np.repeat(np.arange(n), np.diff(rowptr)) < ne
+    wr, wg = ora.get(4)[plastic], net.get(L.FIELD_W)[plastic]
+    assert abs(wg.mean() - wr.mean()) / wr.mean() < 0.01
+    # two-sample KS distance of the plastic weight distributions
+    grid = np.linspace(0, 4, 401)
+    ks = np.abs(np.searchsorted(np.sort(wr), grid) / wr.size - np.searchsorted(np.sort(wg), grid) / wg.size).max()
+    assert ks < 0.02
+    if dtype == "f64":
+        for k in range(50):  # weights are still +-1 (exactly summable) before the first learn!
+            assert np.array_equal(spikes[k], ref[k]), k
+    for s in spikes:
+        assert np.all(np.diff(s) > 0)  # ascending ids inside every step
+    assert stats.n_syn_events == sum(int(np.diff(rowptr)[s].sum()) for s in spikes)
+
+
+def test_errors_and_field_roundtrip():
+    from rl_stdp_b200 import _lib as L
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork, default_config
+    import ctypes as C
+    lib = L.load()
+    cfg = default_config(max_delay=0)
+    h = C.c_void_p()
+    assert lib.snn_create(C.byref(cfg), C.byref(h)) == -1
+    assert b"max_delay" in lib.snn_last_error()
+    n, ne = 300, 240
+    rowptr, post, w, delay = synth.fixed_fanout(n, ne, 20, 3, seed=61)
+    bad = delay.copy()
+    bad[5] = 9
+    with pytest.raises(L.SnnError):
+        SparseNetwork(n, ne, rowptr, post, w, bad, max_delay=3)
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="exact", max_delay=3)
+    x = np.linspace(-70, -50, n)
+    net.set(L.FIELD_V, x)
+    assert np.array_equal(net.get(L.FIELD_V), x)
+    w2 = np.linspace(0, 1, len(w))
+    net.set(L.FIELD_W, w2)
+    assert np.array_equal(net.get(L.FIELD_W), w2)
+    assert np.array_equal(net.get(L.FIELD_SD), np.zeros(len(w)))
+    net.reset_v()
+    assert np.all(net.get(L.FIELD_V) == -65.0)
+    # capacity error: result truncated, status SNN_ERR_CAPACITY
+    noise = synth.thalamic_noise(50, n, seed=1, amp=60.0)
+    with pytest.raises(L.SnnError) as ei:
+        net.run(50, noise, None, spikes_cap=4)
+    assert ei.value.code == L.SNN_ERR_CAPACITY
+    # empty network (no synapses) still steps
+    e = SparseNetwork(64, 48, np.zeros(65, np.int64), np.zeros(0, np.int32), np.zeros(0), None, dtype="f64",
+                      mode="exact")
+    sp, st = e.run(20, synth.thalamic_noise(20, 64, seed=2, amp=80.0), np.ones(20, np.uint8))
+    assert st.n_syn_events == 0 and st.n_spikes == sum(len(s) for s in sp) > 0

@@ -1,0 +1,110 @@
+"""CPU tests of the oracle itself: the C restatement, the independent numpy restatement and the
+sparse generalisation must agree BIT FOR BIT (the reference has no golden vectors, so the two
+restatements written from the cited Julia lines pin each other), and both must reproduce the
+committed fixtures under tests/golden/."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import np_restate as nr
+from oracle import py_oracle as po
+from rl_stdp_b200 import synth
+from tests.helpers import run_oracle_sparse
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _drive_a(N, Ne, T, seed):
+    conn = synth.dense_connection(N, 0.1, seed)
+    noise = synth.thalamic_noise(T, N, seed + 1)
+    return conn, noise
+
+
+def test_dense_c_equals_numpy_equals_sparse():
+    N, Ne, T = 300, 240, 500
+    conn, noise = _drive_a(N, Ne, T, 1)
+    A = po.DenseA(N, Ne, conn)
+    B = nr.NetA(N, Ne, conn)
+    s0 = synth.variant_a_weights(N, Ne, conn)
+    rowptr, post, w = synth.dense_to_csr(s0, conn)
+    S = po.Sparse(N, Ne, rowptr, post, w)
+    total = 0
+    for t in range(T):
+        train = (t + 1) % 10 == 0
+        force = [5, 17] if t == 250 else None
+        a = A.step(noise[t], train, force)
+        b = B.step(noise[t], train, force)
+        c = S.step(noise[t], train, force)
+        assert np.array_equal(a, b) and np.array_equal(a, c), t
+        total += len(a)
+        if t in (120, 300):
+            A.da += 0.5; B.da += 0.5; S.add_da(0, 0.5)
+    assert total > 100
+    assert np.array_equal(A.s, B.s) and np.array_equal(A.sd, B.sd)
+    assert np.array_equal(A.v, B.v) and np.array_equal(A.u, B.u) and np.array_equal(A.STDP, B.STDP)
+    assert A.da == B.da
+    pre, pst = np.nonzero(conn)
+    exc = pre < Ne
+    assert np.array_equal(A.s[pre, pst], S.get(4))
+    assert np.array_equal(A.sd[pre, pst][exc], S.get(5)[exc])
+    assert np.array_equal(A.v, S.get(0)) and np.array_equal(A.STDP, S.get(2))
+    assert A.da == S.get(6)[0]
+    assert np.abs(A.sd).max() > 0 and np.abs(A.s - s0).max() > 0  # learning happened
+
+
+def test_golden_variant_a():
+    g = np.load(os.path.join(GOLD, "variant_a_n150_t300.npz"))
+    N, Ne, T = int(g["N"]), int(g["Ne"]), int(g["T"])
+    conn, noise = g["connection"], g["noise"]
+    A = po.DenseA(N, Ne, conn)
+    ids, offs = [], [0]
+    for t in range(T):
+        s = A.step(noise[t], (t + 1) % 10 == 0)
+        ids.extend(s.tolist()); offs.append(len(ids))
+        if t in g["da_steps"]:
+            A.da += 0.5
+    assert np.array_equal(np.array(ids, np.int32), g["spike_ids"])
+    assert np.array_equal(np.array(offs, np.int64), g["spike_offsets"])
+    assert np.array_equal(A.s, g["s_final"]) and np.array_equal(A.sd, g["sd_final"])
+    assert np.array_equal(A.v, g["v_final"]) and A.da == float(g["da_final"])
+
+
+def test_sparse_delay1_equals_delayD_with_shifted_semantics():
+    """Sanity of the delay ring: with every delay = d the network is the delay-1 network whose
+    arrivals (current + LTD) come d-1 calls later; with no recurrent spikes inside d calls the
+    first spikes are identical."""
+    N, Ne, T = 200, 160, 60
+    rowptr, post, w, _ = synth.fixed_fanout(N, Ne, 30, 1, seed=3)
+    noise = synth.thalamic_noise(T, N, seed=4)
+    a = po.Sparse(N, Ne, rowptr, post, w, np.ones(len(post), np.uint8), max_delay=1)
+    b = po.Sparse(N, Ne, rowptr, post, w, np.full(len(post), 4, np.uint8), max_delay=4)
+    first = None
+    for t in range(T):
+        sa, sb = a.step(noise[t]), b.step(noise[t])
+        if first is None and (len(sa) or len(sb)):
+            first = t
+            assert np.array_equal(sa, sb)
+    assert first is not None
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors): pins the shared noise generator."""
+    out = np.zeros(4, np.uint32)
+    L = po.lib()
+    L.ora_philox4x32(0, 0, 0, 0, 0, 0, out.ctypes.data)
+    assert [hex(x) for x in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    L.ora_philox4x32(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, out.ctypes.data)
+    assert [hex(x) for x in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    L.ora_philox4x32(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0, out.ctypes.data)
+    assert [hex(x) for x in out] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+    x = po.philox_noise(7, 3, 1000)
+    assert x.min() >= -6.5 and x.max() <= 6.5 and abs(x.mean()) < 0.5
+
+
+def test_run_helper_da_after_step():
+    N, Ne = 100, 80
+    rowptr, post, w, d = synth.fixed_fanout(N, Ne, 10, 2, seed=5)
+    o = po.Sparse(N, Ne, rowptr, post, w, d, max_delay=2)
+    run_oracle_sparse(o, synth.thalamic_noise(3, N, seed=6), [0, 0, 0], [(0, 0, 1.0)])
+    assert o.get(6)[0] == 1.0 * 0.995 * 0.995
