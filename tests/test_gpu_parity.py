@@ -198,7 +198,7 @@ def test_homeostasis_and_ge_threshold():
 def test_fast_mode_statistics(dtype):
     """Production mode (atomic scatter; fp32): the dynamics are chaotic, so parity is statistical
     (SURVEY §8d gates): mean rate within 2 %, exc/inh rates within 5 %, mean plastic weight within
-    1 %, and the early spike trains (before divergence) identical for fp64."""
+    1 %, weight quantiles within 5e-3, and the early spike trains (before divergence) identical for fp64."""
     from oracle import py_oracle as po
     from rl_stdp_b200 import synth
     from rl_stdp_b200.network import SparseNetwork
@@ -224,16 +224,24 @@ def test_fast_mode_statistics(dtype):
     plastic = np.repeat(np.arange(n), np.diff(rowptr)) < ne
     wr, wg = ora.get(4)[plastic], net.get(L.FIELD_W)[plastic]
     assert abs(wg.mean() - wr.mean()) / wr.mean() < 0.01
-    # two-sample KS distance of the plastic weight distributions
-    grid = np.linspace(0, 4, 401)
-    ks = np.abs(np.searchsorted(np.sort(wr), grid) / wr.size - np.searchsorted(np.sort(wg), grid) / wg.size).max()
-    assert ks < 0.02
+    # weight distributions: the quantile functions agree to 5e-3 (weights live in [0, 4]).  A plain
+    # KS statistic is meaningless here: most weights sit within 1e-6 of 1.0, an atom that fp32
+    # rounding moves across any fixed grid point.
+    qs = np.linspace(0.001, 0.999, 999)
+    assert np.abs(np.quantile(wr, qs) - np.quantile(wg, qs)).max() < 5e-3
+    assert abs(wg.std() - wr.std()) / wr.std() < 0.05
     if dtype == "f64":
         for k in range(50):  # weights are still +-1 (exactly summable) before the first learn!
             assert np.array_equal(spikes[k], ref[k]), k
     for s in spikes:
         assert np.all(np.diff(s) > 0)  # ascending ids inside every step
-    assert stats.n_syn_events == sum(int(np.diff(rowptr)[s].sum()) for s in spikes)
+    # a synaptic event is a DELIVERY: a spike at step k through a delay-d synapse arrives at k+d-1
+    pre = np.repeat(np.arange(n), np.diff(rowptr))
+    cnt = np.zeros((n, dmax + 1), np.int64)
+    np.add.at(cnt, (pre, delay), 1)
+    cum = np.cumsum(cnt, axis=1)  # cum[i, d] = synapses of i with delay <= d
+    expect = sum(int(cum[s, min(dmax, t - k)].sum()) for k, s in enumerate(spikes))
+    assert stats.n_syn_events == expect
 
 
 def test_errors_and_field_roundtrip():
