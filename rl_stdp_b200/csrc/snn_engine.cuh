@@ -74,7 +74,7 @@ __device__ __forceinline__ double philox_noise(uint64_t seed, int64_t t, int64_t
 template <typename T>
 struct DevNet {
   typedef typename Real2<T>::type T2;
-  int64_t N, Npad, Nper, Ne, E;
+  int64_t N, Nld, Nper, Ne, E;  // Nld = N rounded up to 128: leading dimension of ring slots
   int32_t Dmax, R, B, W;  // W = bitmap words per slot
   // neuron state
   T *v, *u, *ho, *Iacc;
@@ -88,8 +88,9 @@ struct DevNet {
   const int32_t* post;
   T2* wsd;           // [E] (w, sd) interleaved: one 8/16-byte access serves propagate + LTD
   const uint32_t *colptr, *col_npl, *in_syn, *in_pre;
-  // counters: [0]=spikes [1]=synaptic events [2]=ltp events
+  // counters: [0]=spikes [1]=synaptic events (exact mode) ; blk_counters[2*block+{0,1}] = events / ltp
   unsigned long long* counters;
+  unsigned long long* blk_counters;
   // spike record
   int32_t* rec_ids; int32_t* rec_off; int64_t rec_cap;
   // parameters
@@ -99,6 +100,8 @@ struct DevNet {
   int64_t ho_from;
   int32_t threshold_ge, sd_decay_mode, rate_mode, plastic_ei, noise_mode, exact, homeostasis;
 };
+
+constexpr int kMaxSynBlocks = 148 * 16 * 2;
 
 struct DaEvents {  // CSR by window step
   const int32_t* off; const int32_t* inst; const double* amt;
@@ -113,21 +116,42 @@ __device__ __forceinline__ int slot_of(int64_t t, int R) {
 // K1 neuron_kernel: [Euler(t-1)] + [detect(t)]   (new_net.jl:111-114,120-123,130-131;
 // homeostasis net_res.jl:167-171,204)
 //   EULER : I = noise(t-1) + Iacc ; two half-steps of v ; u update ; Iacc cleared
-//   DETECT: spike test, reset, homeostasis, trace set/decay into ring slot t, ballot bitmap,
+//   DETECT: spike test, reset, homeostasis, trace set/decay into ring slot t, spike bitmap,
 //           spike list append, dopamine events of step t-1 + decay (block 0)
-// One thread per neuron, a warp covers 32 consecutive neurons = one bitmap word.
+// Each thread owns 4 consecutive neurons: every array is read/written with one 16-byte (fp32)
+// access, all loads are issued before the first use (the kernel is latency-bound otherwise: ncu
+// r1a showed 1 x 128 B in flight per warp = 0.5 TB/s), and one Philox4x32 call yields the four
+// noise values.  A warp covers 128 neurons = 4 bitmap words.  Arrays are padded to Nld.
 // ---------------------------------------------------------------------------------------------
+template <typename T> struct Vec4 { T x[4]; };
+__device__ __forceinline__ Vec4<float> ld4(const float* p) {
+  float4 r = *reinterpret_cast<const float4*>(p);
+  Vec4<float> o; o.x[0] = r.x; o.x[1] = r.y; o.x[2] = r.z; o.x[3] = r.w; return o;
+}
+__device__ __forceinline__ Vec4<double> ld4(const double* p) {
+  double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  Vec4<double> o; o.x[0] = a.x; o.x[1] = a.y; o.x[2] = b.x; o.x[3] = b.y; return o;
+}
+__device__ __forceinline__ void st4(float* p, const Vec4<float>& v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v.x[0], v.x[1], v.x[2], v.x[3]);
+}
+__device__ __forceinline__ void st4(double* p, const Vec4<double>& v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v.x[0], v.x[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v.x[2], v.x[3]);
+}
+
 template <typename T, bool EULER, bool DETECT>
 __global__ void __launch_bounds__(256)
-neuron_kernel(DevNet<T> p, int64_t t, int32_t k_rel, const T* __restrict__ noise_prev, DaEvents ev) {
+neuron_kernel(DevNet<T> p, int64_t t, int32_t k_rel, int slot, int prev, const T* __restrict__ noise_prev,
+              DaEvents ev) {
   typedef Ops<T> O;
   const int lane = threadIdx.x & 31;
-  const int slot = slot_of(t, p.R), prev = slot_of(t - 1, p.R);
-  T* __restrict__ tr = p.trace + (size_t)slot * p.N;
-  const T* __restrict__ trp = p.trace + (size_t)prev * p.N;
+  T* __restrict__ tr = p.trace + (size_t)slot * p.Nld;
+  const T* __restrict__ trp = p.trace + (size_t)prev * p.Nld;
   uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
-  int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.N;
+  int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.Nld;
   const int32_t rec_base = (DETECT && p.rec_ids) ? p.rec_off[k_rel] : 0;
+  const uint32_t N = (uint32_t)p.N, Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
 
   // dopamine: da += events(step k_rel-1) ; da *= decay (new_net.jl:131, newnet_DASTDP.jl:54-56)
   if (blockIdx.x == 0) {
@@ -139,67 +163,112 @@ neuron_kernel(DevNet<T> p, int64_t t, int32_t k_rel, const T* __restrict__ noise
       for (int b = threadIdx.x; b < p.B; b += blockDim.x) p.da[b] = O::mul(p.da[b], p.da_decay);
   }
 
-  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.Npad;
-       j += (int64_t)gridDim.x * blockDim.x) {
-    const bool act = j < p.N;
-    T v = 0, u = 0;
-    bool exc = false;
-    int64_t l = 0;
-    if (act) {
-      v = p.v[j]; u = p.u[j];
-      l = j % p.Nper;
-      exc = l < p.Ne;
+  const uint32_t nquad = (uint32_t)(p.Nld >> 2);
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += gridDim.x * blockDim.x) {
+    const uint32_t j0 = q << 2;
+    // ---- all loads first
+    Vec4<T> v = ld4(p.v + j0), u = ld4(p.u + j0), I, tp, ho;
+    if (EULER) I = ld4(p.Iacc + j0);
+    if (DETECT) {
+      tp = ld4(trp + j0);
+      if (p.homeostasis) ho = ld4(p.ho + j0);
     }
-    if (EULER && act) {
-      T I = p.Iacc[j];
-      if (!p.exact) {
-        p.Iacc[j] = (T)0;
-        if (p.noise_mode == SNN_NOISE_REPLAY) I = O::add(noise_prev[j], I);
-        else if (p.noise_mode == SNN_NOISE_PHILOX)
-          I = O::add((T)philox_noise(p.noise_seed, t - 1, j, p.noise_amp), I);
-      }
-      // v = v + 0.5*((0.04*v+5)*v + 140 - u + I), twice (new_net.jl:120-121)
+    uint32_t l0 = p.B == 1 ? j0 : j0 % Nper;
+    bool exc[4], act[4];
 #pragma unroll
-      for (int rep = 0; rep < 2; ++rep) {
-        T x = O::add(O::mul((T)0.04, v), (T)5);
-        x = O::add(O::mul(x, v), (T)140);
-        x = O::add(O::sub(x, u), I);
-        v = O::add(v, O::mul((T)0.5, x));
+    for (int c = 0; c < 4; ++c) {
+      uint32_t l = l0 + c;
+      if (l >= Nper) l -= Nper;
+      exc[c] = l < Ne;
+      act[c] = j0 + c < N;
+    }
+    if (EULER) {
+      if (!p.exact) {
+        if (p.noise_mode == SNN_NOISE_REPLAY) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (act[c]) I.x[c] = O::add(noise_prev[j0 + c], I.x[c]);
+        } else if (p.noise_mode == SNN_NOISE_PHILOX) {
+          const int64_t tn = t - 1;
+          uint4 o = philox4x32_10(make_uint4(q, 0u, (uint32_t)tn, (uint32_t)((uint64_t)tn >> 32)),
+                                  make_uint2((uint32_t)p.noise_seed, (uint32_t)(p.noise_seed >> 32)));
+          const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            double U = __dmul_rn(__dadd_rn((double)w[c], 0.5), 1.0 / 4294967296.0);
+            I.x[c] = O::add((T)__dmul_rn(p.noise_amp, __dsub_rn(U, 0.5)), I.x[c]);
+          }
+        }
+        Vec4<T> z; z.x[0] = z.x[1] = z.x[2] = z.x[3] = (T)0;
+        st4(p.Iacc + j0, z);
       }
-      // u = u + a*(0.2*v - u) (new_net.jl:122)
-      u = O::add(u, O::mul(exc ? p.a_exc : p.a_inh, O::sub(O::mul((T)0.2, v), u)));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (!act[c]) continue;
+        T vv = v.x[c];
+        // v = v + 0.5*((0.04*v+5)*v + 140 - u + I), twice (new_net.jl:120-121)
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+          T x = O::add(O::mul((T)0.04, vv), (T)5);
+          x = O::add(O::mul(x, vv), (T)140);
+          x = O::add(O::sub(x, u.x[c]), I.x[c]);
+          vv = O::add(vv, O::mul((T)0.5, x));
+        }
+        v.x[c] = vv;
+        // u = u + a*(0.2*v - u) (new_net.jl:122)
+        u.x[c] = O::add(u.x[c], O::mul(exc[c] ? p.a_exc : p.a_inh, O::sub(O::mul((T)0.2, vv), u.x[c])));
+      }
     }
     if (DETECT) {
-      bool s = false;
-      if (act) {
-        T x = v;
-        T ho = 0;
-        if (p.homeostasis) { ho = p.ho[j]; x = O::sub(v, ho); }
-        s = p.threshold_ge ? (x >= p.vthresh) : (x > p.vthresh);
-        if (s) {
-          v = p.v_reset;
-          u = O::add(u, exc ? p.d_exc : p.d_inh);
+      unsigned nib = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        bool s = false;
+        if (act[c]) {
+          T x = p.homeostasis ? O::sub(v.x[c], ho.x[c]) : v.x[c];
+          s = p.threshold_ge ? (x >= p.vthresh) : (x > p.vthresh);
+          if (s) {
+            v.x[c] = p.v_reset;
+            u.x[c] = O::add(u.x[c], exc[c] ? p.d_exc : p.d_inh);
+          }
         }
         if (p.homeostasis) {
-          if (s && exc && l >= p.ho_from) ho = O::add(ho, p.theta);
-          p.ho[j] = O::mul(ho, p.ttheta);
+          uint32_t l = l0 + c;
+          if (l >= Nper) l -= Nper;
+          T h = ho.x[c];
+          if (s && exc[c] && (int64_t)l >= p.ho_from) h = O::add(h, p.theta);
+          ho.x[c] = O::mul(h, p.ttheta);
         }
-        tr[j] = s ? p.trace_set : (t > 0 ? O::mul(trp[j], p.trace_decay) : (T)0);
+        tp.x[c] = s ? p.trace_set : (t > 0 ? O::mul(tp.x[c], p.trace_decay) : (T)0);
+        nib |= (s ? 1u : 0u) << c;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, s);
-      if (lane == 0) bits[j >> 5] = m;
-      if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&p.spk_cnt[slot], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (s) {
-          int pos = base + __popc(m & ((1u << lane) - 1u));
-          list[pos] = (int32_t)j;
-          if (p.rec_ids && (int64_t)rec_base + pos < p.rec_cap) p.rec_ids[rec_base + pos] = (int32_t)j;
+      st4(tr + j0, tp);
+      if (p.homeostasis) st4(p.ho + j0, ho);
+      // 8 lanes x 4 neurons = one 32-bit bitmap word
+      unsigned word = nib << ((lane & 7) << 2);
+      word |= __shfl_xor_sync(0xffffffffu, word, 1);
+      word |= __shfl_xor_sync(0xffffffffu, word, 2);
+      word |= __shfl_xor_sync(0xffffffffu, word, 4);
+      if ((lane & 7) == 0) bits[j0 >> 5] = word;
+      if (__any_sync(0xffffffffu, nib != 0)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool s = (nib >> c) & 1u;
+          const unsigned m = __ballot_sync(0xffffffffu, s);
+          if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&p.spk_cnt[slot], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (s) {
+              const int pos = base + __popc(m & ((1u << lane) - 1u));
+              list[pos] = (int32_t)(j0 + c);
+              if (p.rec_ids && (int64_t)rec_base + pos < p.rec_cap) p.rec_ids[rec_base + pos] = (int32_t)(j0 + c);
+            }
+          }
         }
       }
     }
-    if (act && (EULER || DETECT)) { p.v[j] = v; p.u[j] = u; }
+    st4(p.v + j0, v);
+    st4(p.u + j0, u);
   }
 }
 
@@ -250,54 +319,108 @@ gather_kernel(DevNet<T> p, int64_t t, const T* __restrict__ noise) {
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool PUSH>
 __global__ void __launch_bounds__(256)
-synapse_kernel(DevNet<T> p, int64_t t, int32_t k_rel, int g_arr_log2, int g_ltp_log2) {
+synapse_kernel(DevNet<T> p, int64_t t, int32_t k_rel, int slot, int g_arr_log2, int g_ltp_log2) {
   typedef Ops<T> O;
   __shared__ int cum[kMaxDelay + 2];
-  const int slot = slot_of(t, p.R);
+  __shared__ int slots[kMaxDelay + 1];
+  __shared__ unsigned long long blk_ev, blk_ltp;
+  // prologue: the Dmax list lengths are loaded in parallel (one round trip), scanned in smem
+  if (threadIdx.x < (unsigned)p.Dmax) {
+    int sl = slot - (int)threadIdx.x;
+    if (sl < 0) sl += p.R;
+    slots[threadIdx.x] = sl;
+    cum[threadIdx.x + 1] = p.spk_cnt[sl];
+  }
+  if (threadIdx.x == 0) { blk_ev = 0ull; blk_ltp = 0ull; }
+  __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int a = 0; a < p.Dmax; ++a) {
-      cum[a] = acc;
-      acc += p.spk_cnt[slot_of(t - a, p.R)];
-    }
+    for (int a = 0; a < p.Dmax; ++a) { int c = cum[a + 1]; cum[a] = acc; acc += c; }
     cum[p.Dmax] = acc;
     if (blockIdx.x == 0) {
-      const int c0 = p.spk_cnt[slot];
-      atomicAdd(&p.counters[0], (unsigned long long)c0);
+      const int c0 = cum[p.Dmax > 1 ? 1 : p.Dmax];
+      p.counters[0] += (unsigned long long)c0;  // single writer
       if (p.rec_ids) {
         int64_t nxt = (int64_t)p.rec_off[k_rel] + c0;
         p.rec_off[k_rel + 1] = (int32_t)(nxt < p.rec_cap ? nxt : p.rec_cap);
       }
-      p.spk_cnt[slot_of(t + 1, p.R)] = 0;  // next call's list; not read by this launch (R = Dmax+1)
+      int nx = slot + 1; if (nx >= p.R) nx -= p.R;
+      p.spk_cnt[nx] = 0;  // next call's list; not read by this launch (R = Dmax+1)
     }
   }
   __syncthreads();
   const int total_arr = cum[p.Dmax];
-  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  const T* __restrict__ tr_now = p.trace + (size_t)slot * p.N;
+  const int n_now = p.Dmax > 1 ? cum[1] : total_arr;  // = spk_cnt[slot]
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const uint32_t Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
+  const size_t Nld = (size_t)p.Nld;
+  const T* __restrict__ tr_now = p.trace + (size_t)slot * Nld;
   const uint32_t* __restrict__ bits_now = p.bits + (size_t)slot * p.W;
   unsigned long long n_ev = 0, n_ltp = 0;
 
-  {  // phase 1: arrivals
-    const int G = 1 << g_arr_log2;
-    const int gl = (int)(gtid & (G - 1));
-    for (int64_t item = gtid >> g_arr_log2; item < total_arr; item += nthreads >> g_arr_log2) {
+  {  // LTP over the incoming index of this call's spikers.  Items are handed out from the LAST
+     // group downwards so they run concurrently with the arrivals of the low groups.
+    const uint32_t G = 1u << g_ltp_log2;
+    const uint32_t gl = gtid & (G - 1);
+    const uint32_t ngroups = nthreads >> g_ltp_log2;
+    const int32_t* __restrict__ list = p.spk_list + (size_t)slot * Nld;
+    for (uint32_t item = ngroups - 1 - (gtid >> g_ltp_log2); item < (uint32_t)n_now; item += ngroups) {
+      const int32_t j = list[item];
+      const uint32_t c0 = p.colptr[j], c1 = c0 + p.col_npl[j];
+      if (gl == 0) n_ltp += (c1 - c0);
+      for (uint32_t kb = c0 + gl; kb < c1; kb += 3 * G) {
+        uint32_t pk[3], e[3]; bool ok[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const uint32_t k = kb + q * G;
+          ok[q] = k < c1;
+          pk[q] = ok[q] ? p.in_pre[k] : 0u;
+          e[q] = ok[q] ? p.in_syn[k] : 0u;
+        }
+        size_t toff[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const uint32_t i = pk[q] & kPreMask;
+          const int sl = slots[pk[q] >> kPreBits];
+          toff[q] = (size_t)sl * Nld + i;
+          if (ok[q]) {
+            const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
+            ok[q] = !((word >> (i & 31)) & 1u);  // else the spike arrives now: arrivals own the synapse
+          }
+        }
+        T trv[3], sdv[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          trv[q] = ok[q] ? p.trace[toff[q]] : (T)0;
+          sdv[q] = ok[q] ? p.wsd[e[q]].y : (T)0;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (ok[q]) p.wsd[e[q]].y = O::add(sdv[q], O::mul(p.apost, trv[q]));
+      }
+    }
+  }
+  {  // arrivals
+    const uint32_t G = 1u << g_arr_log2;
+    const uint32_t gl = gtid & (G - 1);
+    const uint32_t ngroups = nthreads >> g_arr_log2;
+    for (uint32_t item = gtid >> g_arr_log2; item < (uint32_t)total_arr; item += ngroups) {
       int a = 0;
-      while (a + 1 < p.Dmax && cum[a + 1] <= item) ++a;
-      const int sl = slot_of(t - a, p.R);
-      const int32_t i = p.spk_list[(size_t)sl * p.N + (item - cum[a])];
+      while (a + 1 < p.Dmax && cum[a + 1] <= (int)item) ++a;
+      const int sl = slots[a];
+      const uint32_t i = (uint32_t)p.spk_list[(size_t)sl * Nld + (item - cum[a])];
       const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1) + a];
       const uint32_t s1 = p.seg[(size_t)i * (p.Dmax + 1) + a + 1];
-      const int64_t ibase = ((int64_t)i / p.Nper) * p.Nper;
-      const bool row_plastic = ((int64_t)i - ibase) < p.Ne;
-      const T pre_up = row_plastic ? O::mul(p.apost, p.trace[(size_t)sl * p.N + i]) : (T)0;
+      const uint32_t ibase = p.B == 1 ? 0u : (i / Nper) * Nper;
+      const bool row_plastic = (i - ibase) < Ne;
+      const T pre_up = row_plastic ? O::mul(p.apost, p.trace[(size_t)sl * Nld + i]) : (T)0;
       if (gl == 0) n_ev += (s1 - s0);
       for (uint32_t e = s0 + gl; e < s1; e += G) {
-        const int32_t j = p.post[e];
+        const uint32_t j = (uint32_t)p.post[e];
         typename DevNet<T>::T2 ws = p.wsd[e];
         if (PUSH) atomicAdd(&p.Iacc[j], ws.x);
-        if (row_plastic && (p.plastic_ei || ((int64_t)j - ibase) < p.Ne)) {
+        if (row_plastic && (p.plastic_ei || (j - ibase) < Ne)) {
           const T dn = O::mul(p.apre, tr_now[j]);
           const bool jsp = (bits_now[j >> 5] >> (j & 31)) & 1u;
           T sd = ws.y;
@@ -308,35 +431,19 @@ synapse_kernel(DevNet<T> p, int64_t t, int32_t k_rel, int g_arr_log2, int g_ltp_
       }
     }
   }
-  {  // phase 2: LTP over the incoming index of this call's spikers
-    const int G = 1 << g_ltp_log2;
-    const int gl = (int)(gtid & (G - 1));
-    const int n_now = cum[1];  // = spk_cnt[slot] (Dmax >= 1)
-    const int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.N;
-    for (int64_t item = gtid >> g_ltp_log2; item < n_now; item += nthreads >> g_ltp_log2) {
-      const int32_t j = list[item];
-      const uint32_t c0 = p.colptr[j], c1 = c0 + p.col_npl[j];
-      if (gl == 0) n_ltp += (c1 - c0);
-      for (uint32_t k = c0 + gl; k < c1; k += G) {
-        const uint32_t pk = p.in_pre[k];
-        const uint32_t i = pk & kPreMask;
-        const int sl = slot_of(t - (int)(pk >> kPreBits), p.R);
-        const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
-        if ((word >> (i & 31)) & 1u) continue;  // this spike arrives now: phase 1 owns the synapse
-        const T up = O::mul(p.apost, p.trace[(size_t)sl * p.N + i]);
-        const uint32_t e = p.in_syn[k];
-        p.wsd[e].y = O::add(p.wsd[e].y, up);
-      }
-    }
-  }
-  // one atomic per warp
+  // block-local reduction, then one plain RMW on this block's own counter slot (no contended atomics)
   for (int o = 16; o > 0; o >>= 1) {
     n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
     n_ltp += __shfl_down_sync(0xffffffffu, n_ltp, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    if (n_ev && PUSH) atomicAdd(&p.counters[1], n_ev);
-    if (n_ltp) atomicAdd(&p.counters[2], n_ltp);
+    if (n_ev) atomicAdd(&blk_ev, n_ev);
+    if (n_ltp) atomicAdd(&blk_ltp, n_ltp);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (PUSH) p.blk_counters[2 * blockIdx.x] += blk_ev;
+    p.blk_counters[2 * blockIdx.x + 1] += blk_ltp;
   }
 }
 
@@ -437,7 +544,7 @@ learn_kernel(DevNet<T> p, int do_learn, int do_decay) {
 // ----------------------------------------------------------------------------- small helpers
 template <typename T>
 __global__ void init_state_kernel(DevNet<T> p) {
-  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.N; j += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.Nld; j += (int64_t)gridDim.x * blockDim.x) {
     p.v[j] = p.v_reset;
     p.u[j] = Ops<T>::mul((T)0.2, p.v_reset);
   }
@@ -489,9 +596,9 @@ class Engine : public IEngine {
     n_sm_ = sms;
     DevNet<T>& p = p_;
     memset(&p, 0, sizeof(p));
-    p.N = cfg_.n_neurons; p.Npad = (p.N + 31) / 32 * 32; p.Nper = cfg_.n_per_instance; p.Ne = cfg_.n_exc;
-    p.Dmax = cfg_.max_delay; p.R = p.Dmax + 1; p.B = (int32_t)(p.N / p.Nper); p.W = (int32_t)(p.Npad / 32);
-    const size_t N = (size_t)p.N;
+    p.N = cfg_.n_neurons; p.Nld = (p.N + 127) / 128 * 128; p.Nper = cfg_.n_per_instance; p.Ne = cfg_.n_exc;
+    p.Dmax = cfg_.max_delay; p.R = p.Dmax + 1; p.B = (int32_t)(p.N / p.Nper); p.W = (int32_t)(p.Nld / 32);
+    const size_t N = (size_t)p.Nld;  // padded: vector accesses never leave the allocation
     SNN_CUDA_OK(cudaMalloc(&p.v, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.u, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.ho, N * sizeof(T)));
@@ -502,6 +609,8 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMalloc(&p.spk_cnt, (size_t)p.R * sizeof(int32_t)));
     SNN_CUDA_OK(cudaMalloc(&p.da, (size_t)p.B * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.counters, 4 * sizeof(unsigned long long)));
+    SNN_CUDA_OK(cudaMalloc(&p.blk_counters, 2 * kMaxSynBlocks * sizeof(unsigned long long)));
+    SNN_CUDA_OK(cudaMemsetAsync(p.blk_counters, 0, 2 * kMaxSynBlocks * sizeof(unsigned long long), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.ho, 0, N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.Iacc, 0, N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.trace, 0, (size_t)p.R * N * sizeof(T), stream_));
@@ -519,7 +628,7 @@ class Engine : public IEngine {
     p.rate_mode = cfg_.rate_mode; p.plastic_ei = cfg_.plastic_ei; p.noise_mode = cfg_.noise_mode;
     p.exact = cfg_.mode == SNN_MODE_EXACT;
     p.homeostasis = !(cfg_.theta == 0.0 && cfg_.ttheta == 1.0);
-    init_state_kernel<T><<<grid_for(p.N), 256, 0, stream_>>>(p);
+    init_state_kernel<T><<<grid_for(p.Nld), 256, 0, stream_>>>(p);
     SNN_CUDA_OK(cudaGetLastError());
     SNN_CUDA_OK(cudaStreamSynchronize(stream_));
     return SNN_OK;
@@ -560,7 +669,7 @@ class Engine : public IEngine {
       case SNN_FIELD_HO: src = p.ho; break;
       case SNN_FIELD_TRACE:
         if (t_ == 0) { if (count != p.N) { err = "count mismatch"; return SNN_ERR_INVALID; } std::fill(host, host + count, 0.0); return SNN_OK; }
-        src = p.trace + (size_t)slot_host(t_ - 1) * p.N; scale = cfg_.trace_decay; break;
+        src = p.trace + (size_t)slot_host(t_ - 1) * p.Nld; scale = cfg_.trace_decay; break;
       case SNN_FIELD_DA: src = p.da; n = p.B; break;
       case SNN_FIELD_I:
         if (!p.exact) { err = "FIELD_I is only kept in SNN_MODE_EXACT"; return SNN_ERR_INVALID; }
@@ -669,7 +778,7 @@ class Engine : public IEngine {
   void release() {
     DevNet<T>& p = p_;
     cudaFree(p.v); cudaFree(p.u); cudaFree(p.ho); cudaFree(p.Iacc); cudaFree(p.trace); cudaFree(p.bits);
-    cudaFree(p.spk_list); cudaFree(p.spk_cnt); cudaFree(p.da); cudaFree(p.counters); cudaFree(p.wsd);
+    cudaFree(p.spk_list); cudaFree(p.spk_cnt); cudaFree(p.da); cudaFree(p.counters); cudaFree(p.blk_counters); cudaFree(p.wsd);
     topo_.release();
     if (ev_begin_) cudaEventDestroy(ev_begin_);
     if (ev_end_) cudaEventDestroy(ev_end_);
@@ -702,7 +811,7 @@ class Engine : public IEngine {
   Topo topo_;
   bool have_topo_ = false, profiling_ = false;
   int64_t t_ = 0;
-  int n_sm_ = 148, g_arr_log2_ = 5, g_ltp_log2_ = 5;
+  int n_sm_ = 148, g_arr_log2_ = 5, g_ltp_log2_ = 5, gS_ = 0;
   cudaStream_t own_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev_begin_ = nullptr, ev_end_ = nullptr;
   std::vector<cudaEvent_t> prof_events_;
@@ -801,10 +910,18 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   }
   unsigned long long c_before[4];
   STEP_OK(cudaMemcpyAsync(c_before, p.counters, sizeof(c_before), cudaMemcpyDeviceToHost, stream_));
+  STEP_OK(cudaMemsetAsync(p.blk_counters, 0, 2 * kMaxSynBlocks * sizeof(unsigned long long), stream_));
 
   prof_used_ = 0; prof_cls_.clear();
-  const int gN = grid_for(p.Npad);
-  const int gS = n_sm_ * 8;
+  // one quad of neurons per thread; persistent synapse grid sized to what is resident
+  const int gN = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 + 255) / 256, (int64_t)n_sm_ * 8));
+  if (gS_ == 0) {
+    int per_sm = 0;
+    if (p.exact) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synapse_kernel<T, false>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synapse_kernel<T, true>, 256, 0);
+    gS_ = std::min(kMaxSynBlocks, n_sm_ * std::max(1, per_sm));
+  }
+  const int gS = gS_;
   // learn grid: x blocks per instance
   int64_t plastic_per_inst = p.B ? (p.E / p.B) : 0;
   int gLx = (int)std::max<int64_t>(1, std::min<int64_t>((plastic_per_inst / 2 + 256 * 4 - 1) / (256 * 4),
@@ -813,21 +930,22 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
 
   for (int k = 0; k <= n; ++k) {
     const int64_t t = t_ + k;
+    const int slot = slot_host(t), prev = slot_host(t - 1);
     const T* noise_prev = (d_noise && k > 0) ? d_noise + (size_t)(k - 1) * N : nullptr;
     const bool forced = k < n && force_off[k + 1] > force_off[k];
     prof_begin(0);
     if (k == 0) {
       if (forced) force_kernel<T><<<(force_off[1] - force_off[0] + 255) / 256, 256, 0, stream_>>>(p, d_force + force_off[0], force_off[1] - force_off[0]);
-      neuron_kernel<T, false, true><<<gN, 256, 0, stream_>>>(p, t, k, noise_prev, ev);
+      neuron_kernel<T, false, true><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, ev);
     } else if (k == n) {
-      neuron_kernel<T, true, false><<<gN, 256, 0, stream_>>>(p, t, k, noise_prev, ev);
+      neuron_kernel<T, true, false><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, ev);
     } else if (forced) {
-      neuron_kernel<T, true, false><<<gN, 256, 0, stream_>>>(p, t, k, noise_prev, ev);
+      neuron_kernel<T, true, false><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, ev);
       const int nf = force_off[k + 1] - force_off[k];
       force_kernel<T><<<(nf + 255) / 256, 256, 0, stream_>>>(p, d_force + force_off[k], nf);
-      neuron_kernel<T, false, true><<<gN, 256, 0, stream_>>>(p, t, k, noise_prev, DaEvents{nullptr, nullptr, nullptr});
+      neuron_kernel<T, false, true><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, DaEvents{nullptr, nullptr, nullptr});
     } else {
-      neuron_kernel<T, true, true><<<gN, 256, 0, stream_>>>(p, t, k, noise_prev, ev);
+      neuron_kernel<T, true, true><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, ev);
     }
     prof_end();
     if (k == n) break;
@@ -835,9 +953,9 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     if (p.exact) {
       const T* noise_now = d_noise ? d_noise + (size_t)k * N : nullptr;
       gather_kernel<T><<<grid_for(N), 256, 0, stream_>>>(p, t, noise_now);
-      synapse_kernel<T, false><<<gS, 256, 0, stream_>>>(p, t, k, g_arr_log2_, g_ltp_log2_);
+      synapse_kernel<T, false><<<gS, 256, 0, stream_>>>(p, t, k, slot, g_arr_log2_, g_ltp_log2_);
     } else {
-      synapse_kernel<T, true><<<gS, 256, 0, stream_>>>(p, t, k, g_arr_log2_, g_ltp_log2_);
+      synapse_kernel<T, true><<<gS, 256, 0, stream_>>>(p, t, k, slot, g_arr_log2_, g_ltp_log2_);
     }
     prof_end();
     const bool train = a.train_flags && a.train_flags[k];
@@ -867,6 +985,8 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   }
   unsigned long long c_after[4];
   STEP_OK(cudaMemcpyAsync(c_after, p.counters, sizeof(c_after), cudaMemcpyDeviceToHost, stream_));
+  std::vector<unsigned long long> h_blk(2 * (size_t)gS);
+  STEP_OK(cudaMemcpyAsync(h_blk.data(), p.blk_counters, h_blk.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
   STEP_OK(cudaEventRecord(ev_end_, stream_));
   STEP_OK(cudaStreamSynchronize(stream_));
   if (a.spikes_out && (int64_t)(c_after[0] - c_before[0]) > a.spikes_cap) {
@@ -877,7 +997,7 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     memset(&s, 0, sizeof(s));
     s.n_spikes = (int64_t)(c_after[0] - c_before[0]);
     s.n_syn_events = (int64_t)(c_after[1] - c_before[1]);
-    s.n_ltp_events = (int64_t)(c_after[2] - c_before[2]);
+    for (int b = 0; b < gS; ++b) { s.n_syn_events += (int64_t)h_blk[2 * b]; s.n_ltp_events += (int64_t)h_blk[2 * b + 1]; }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev_begin_, ev_end_);
     s.device_ms = ms;
