@@ -100,7 +100,7 @@ typedef struct snn_config {
   double theta;            /* homeostasis increment (0 = off)  net_res.jl:171 */
   double ttheta;           /* homeostasis decay                net_res.jl:204 */
   int64_t ho_from;         /* local ids >= ho_from (and < n_exc) get homeostasis (arch[1]) */
-  int32_t reserved[8];
+  int32_t reserved[8];     /* reserved[0] = 1 disables the CUDA-graph scheduler (A/B testing) */
 } snn_config;
 
 typedef struct snn_net snn_net;
@@ -199,8 +199,9 @@ int32_t snn_set_array(snn_net* net, int32_t field, const double* host, int64_t c
 int64_t snn_n_synapses(const snn_net* net);
 int64_t snn_step_index(const snn_net* net);
 
-/* 1: record CUDA events around every kernel launch so snn_step_stats carries per-kernel
- * times (used by bench.py for the roofline); 0 (default): only the window events. */
+/* 0 (default): only the window events; the window runs as one CUDA graph when possible.
+ * 1: CUDA events around every kernel class, plain stream-ordered launches (diagnostics).
+ * 2: the CUDA-graph path with events around the learn_kernel launches only (bench.py roofline). */
 int32_t snn_set_profiling(snn_net* net, int32_t enable);
 /* Use an externally owned CUDA stream (cudaStream_t) instead of the net's own. */
 int32_t snn_set_stream(snn_net* net, void* cuda_stream);

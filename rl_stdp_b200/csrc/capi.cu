@@ -161,7 +161,7 @@ int64_t snn_step_index(const snn_net* net) { return net ? net->eng->step_index()
 
 int32_t snn_set_profiling(snn_net* net, int32_t enable) {
   if (!net) return fail(SNN_ERR_INVALID, "null net");
-  net->eng->set_profiling(enable != 0);
+  net->eng->set_profiling(enable);
   return SNN_OK;
 }
 

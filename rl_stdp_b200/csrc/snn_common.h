@@ -71,7 +71,7 @@ class IEngine {
   virtual int reset_v(std::string& err) = 0;
   virtual int64_t n_synapses() const = 0;
   virtual int64_t step_index() const = 0;
-  virtual void set_profiling(bool on) = 0;
+  virtual void set_profiling(int mode) = 0;
   virtual void set_stream(cudaStream_t s) = 0;
   virtual cudaStream_t stream() const = 0;
 };

@@ -9,21 +9,31 @@
 //
 //   reference order (new_net.jl:109-142)          kernels here
 //   ------------------------------------------    ------------------------------------------
-//   I = noise                          :111       neuron_kernel<DETECT>(t):  [Euler(t-1) first]
-//   spiked = v > 30 ; v=-65 ; u+=d     :112-114     threshold/reset, trace set/decay, ballot
-//   for n in spiked: I += s[n,:]       :116-118     bitmap + spike list, dopamine decay
-//   v,v,u Euler                        :120-122   synapse_kernel(t): arrivals (I += w, LTD) and
-//   STDP[spiked]=0.1                   :123         LTP over the incoming index
-//   sd[:,n]+=STDP ; sd[n,:]-=1.5STDP   :125-128   [exact mode: gather_kernel(t) pulls I in
-//   STDP*=0.95 ; da*=0.995             :130-131     ascending presynaptic order]
-//   learn! (if train)                  :135-142   learn_kernel(t): w=clamp(w+(b+da)*sd), sd*=.99
+//   I = noise                          :111       neuron_kernel(t):  Euler(t-1) then detect(t):
+//   spiked = v > 30 ; v=-65 ; u+=d     :112-114     threshold/reset, trace set/decay, bitmap,
+//   for n in spiked: I += s[n,:]       :116-118     spike list, dopamine decay
+//   v,v,u Euler                        :120-122   arrival_kernel(t): I += w and LTD for every spike
+//   STDP[spiked]=0.1                   :123         arriving now (delay ring of spike lists)
+//   sd[:,n]+=STDP ; sd[n,:]-=1.5STDP   :125-128   ltp_kernel(t): LTP over the incoming index
+//   STDP*=0.95 ; da*=0.995             :130-131   [exact mode: gather_kernel(t) pulls I in
+//   learn! (if train)                  :135-142     ascending presynaptic order]
+//                                                 learn_kernel(t): w=clamp(w+(b+da)*sd), sd*=.99
 //
 // Detection at t only needs the Euler result of t-1, so Euler(t-1) and detect(t) are one pass
 // over the neuron arrays (36 B/neuron fp32).  Trace values do not enter the Euler update, so the
 // result is identical to the reference order.
+//
+// Scheduling: a whole window of steps is captured once as a CUDA graph (two captured streams):
+//   s1: neuron(k) -> arrival(k) -> neuron(k+1) -> ...
+//   s2:    \-> ltp(k) -------\-> learn(k) --------/ (joined before arrival(k+1))
+// so ltp(k) runs beside arrival(k) (disjoint synapse ownership) and the bandwidth-bound learn(k)
+// runs beside the latency-bound neuron(k+1).  All step-dependent values (absolute step, ring
+// slot, input pointers) come from a device-side WindowCtx, so one instantiated graph serves every
+// window with the same length and train-flag pattern.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <algorithm>
 #include <string>
@@ -62,37 +72,41 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   }
   return c;
 }
+__device__ __forceinline__ double philox_to_noise(uint32_t x, double amp) {
+  double U = __dmul_rn(__dadd_rn((double)x, 0.5), 1.0 / 4294967296.0);
+  return __dmul_rn(amp, __dsub_rn(U, 0.5));
+}
 __device__ __forceinline__ double philox_noise(uint64_t seed, int64_t t, int64_t j, double amp) {
   uint4 o = philox4x32_10(make_uint4((uint32_t)(j >> 2), 0u, (uint32_t)t, (uint32_t)((uint64_t)t >> 32)),
                           make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   uint32_t x = (j & 3) == 0 ? o.x : ((j & 3) == 1 ? o.y : ((j & 3) == 2 ? o.z : o.w));
-  double U = __dmul_rn(__dadd_rn((double)x, 0.5), 1.0 / 4294967296.0);
-  return __dmul_rn(amp, __dsub_rn(U, 0.5));
+  return philox_to_noise(x, amp);
 }
 
-// Everything the kernels need, passed by value.
+constexpr int kMaxSynBlocks = 148 * 16 * 2;
+
+// Network state + parameters, passed to the kernels by value.
 template <typename T>
 struct DevNet {
   typedef typename Real2<T>::type T2;
   int64_t N, Nld, Nper, Ne, E;  // Nld = N rounded up to 128: leading dimension of ring slots
-  int32_t Dmax, R, B, W;  // W = bitmap words per slot
+  int32_t Dmax, R, B, W;        // R = Dmax+1 ring slots ; W = bitmap words per slot
   // neuron state
   T *v, *u, *ho, *Iacc;
-  T* trace;          // [R][N]
-  uint32_t* bits;    // [R][W]
-  int32_t* spk_list; // [R][N]
+  T* trace;          // [R][Nld]  trace after the set of that step (pre-decay)
+  uint32_t* bits;    // [R][W]    spike bitmap per step
+  int32_t* spk_list; // [R][Nld]  spike list per step (unordered)
   int32_t* spk_cnt;  // [R]
-  T* da;             // [B]
-  // synapses
-  const uint32_t* seg;
-  const int32_t* post;
-  T2* wsd;           // [E] (w, sd) interleaved: one 8/16-byte access serves propagate + LTD
+  T* da;             // [2][B]    da[t&1] = dopamine after the decay of step t-1
+  // synapses (internal order: ascending pre, delay, caller position)
+  const uint32_t* seg;   // [N][Dmax+1] delay-segment table
+  const int32_t* post;   // [E]
+  T2* wsd;               // [E] (w, sd) interleaved: one 8-byte access serves propagate + LTD
   const uint32_t *colptr, *col_npl, *in_syn, *in_pre;
-  // counters: [0]=spikes [1]=synaptic events (exact mode) ; blk_counters[2*block+{0,1}] = events / ltp
+  // counters[0] = spikes, [1] = synaptic events (exact mode); per-block partial sums otherwise
   unsigned long long* counters;
-  unsigned long long* blk_counters;
-  // spike record
-  int32_t* rec_ids; int32_t* rec_off; int64_t rec_cap;
+  unsigned long long* blk_ev;   // [kMaxSynBlocks] synaptic events (arrival_kernel)
+  unsigned long long* blk_ltp;  // [kMaxSynBlocks] LTP visits (ltp_kernel)
   // parameters
   T vthresh, v_reset, a_exc, a_inh, d_exc, d_inh, trace_set, trace_decay, apost, apre, da_decay,
       learn_base, eta, wmin, wmax, sd_decay, theta, ttheta;
@@ -101,28 +115,18 @@ struct DevNet {
   int32_t threshold_ge, sd_decay_mode, rate_mode, plastic_ei, noise_mode, exact, homeostasis;
 };
 
-constexpr int kMaxSynBlocks = 148 * 16 * 2;
-
-struct DaEvents {  // CSR by window step
-  const int32_t* off; const int32_t* inst; const double* amt;
+// Per-window inputs/outputs.  Lives in device memory so that a captured graph never has to be
+// re-parameterised: kernels receive (net, ctx pointer, k) and derive everything else.
+template <typename T>
+struct WindowCtx {
+  int64_t t0;        // absolute step of window step 0
+  int32_t slot0;     // t0 mod R
+  int32_t n_steps;
+  const T* noise;    // [n_steps][N] replayed thalamic input, or null
+  const int32_t* ev_off; const int32_t* ev_inst; const double* ev_amt;  // dopamine events, CSR by step
+  int32_t* rec_ids; int32_t* rec_off; int64_t rec_cap;                  // spike record
 };
 
-__device__ __forceinline__ int slot_of(int64_t t, int R) {
-  int64_t m = t % R;
-  return (int)(m < 0 ? m + R : m);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1 neuron_kernel: [Euler(t-1)] + [detect(t)]   (new_net.jl:111-114,120-123,130-131;
-// homeostasis net_res.jl:167-171,204)
-//   EULER : I = noise(t-1) + Iacc ; two half-steps of v ; u update ; Iacc cleared
-//   DETECT: spike test, reset, homeostasis, trace set/decay into ring slot t, spike bitmap,
-//           spike list append, dopamine events of step t-1 + decay (block 0)
-// Each thread owns 4 consecutive neurons: every array is read/written with one 16-byte (fp32)
-// access, all loads are issued before the first use (the kernel is latency-bound otherwise: ncu
-// r1a showed 1 x 128 B in flight per warp = 0.5 TB/s), and one Philox4x32 call yields the four
-// noise values.  A warp covers 128 neurons = 4 bitmap words.  Arrays are padded to Nld.
-// ---------------------------------------------------------------------------------------------
 template <typename T> struct Vec4 { T x[4]; };
 __device__ __forceinline__ Vec4<float> ld4(const float* p) {
   float4 r = *reinterpret_cast<const float4*>(p);
@@ -139,28 +143,49 @@ __device__ __forceinline__ void st4(double* p, const Vec4<double>& v) {
   *reinterpret_cast<double2*>(p) = make_double2(v.x[0], v.x[1]);
   *reinterpret_cast<double2*>(p + 2) = make_double2(v.x[2], v.x[3]);
 }
+__device__ __forceinline__ int wrap_slot(int s, int R) { return s >= R ? s - R : (s < 0 ? s + R : s); }
 
+// ---------------------------------------------------------------------------------------------
+// K1 neuron_kernel: [Euler(t-1)] + [detect(t)]   (new_net.jl:111-114,120-123,130-131;
+// homeostasis net_res.jl:167-171,204)
+//   EULER : I = noise(t-1) + Iacc ; two half-steps of v ; u update ; Iacc cleared
+//   DETECT: spike test, reset, homeostasis, trace set/decay into ring slot t, spike bitmap,
+//           spike list append; block 0: da[(t+1)&1] = (da[t&1] + events(t-1)) * decay
+// Each thread owns 4 consecutive neurons: every array is read/written with one 16-byte (fp32)
+// access, all loads are issued before the first use (the scalar version had one 128-B request in
+// flight per warp and ran at 0.5 TB/s — profiles/r1a), one Philox4x32 call yields the four noise
+// values.  A warp covers 128 neurons = 4 bitmap words.  Arrays are padded to Nld.
+// ---------------------------------------------------------------------------------------------
 template <typename T, bool EULER, bool DETECT>
 __global__ void __launch_bounds__(256)
-neuron_kernel(DevNet<T> p, int64_t t, int32_t k_rel, int slot, int prev, const T* __restrict__ noise_prev,
-              DaEvents ev) {
+neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev) {
   typedef Ops<T> O;
   const int lane = threadIdx.x & 31;
+  const int64_t t = cx->t0 + k;
+  const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
   T* __restrict__ tr = p.trace + (size_t)slot * p.Nld;
   const T* __restrict__ trp = p.trace + (size_t)prev * p.Nld;
   uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
   int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.Nld;
-  const int32_t rec_base = (DETECT && p.rec_ids) ? p.rec_off[k_rel] : 0;
+  int32_t* __restrict__ rec_ids = DETECT ? cx->rec_ids : nullptr;
+  const int32_t rec_base = rec_ids ? cx->rec_off[k] : 0;
+  const int64_t rec_cap = cx->rec_cap;
+  const T* __restrict__ noise_prev = (EULER && cx->noise) ? cx->noise + (size_t)(k - 1) * p.N : nullptr;
   const uint32_t N = (uint32_t)p.N, Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
 
-  // dopamine: da += events(step k_rel-1) ; da *= decay (new_net.jl:131, newnet_DASTDP.jl:54-56)
+  // dopamine (new_net.jl:131 da *= 0.995 ; newnet_DASTDP.jl:54-56 da += 0.5 after step!)
   if (blockIdx.x == 0) {
-    if (ev.off && k_rel > 0 && threadIdx.x == 0)
-      for (int q = ev.off[k_rel - 1]; q < ev.off[k_rel]; ++q)
-        p.da[ev.inst[q]] = O::add(p.da[ev.inst[q]], (T)ev.amt[q]);
-    __syncthreads();
-    if (DETECT)
-      for (int b = threadIdx.x; b < p.B; b += blockDim.x) p.da[b] = O::mul(p.da[b], p.da_decay);
+    const T* __restrict__ din = p.da + (size_t)(t & 1) * p.B;
+    T* __restrict__ dout = p.da + (size_t)((t + 1) & 1) * p.B;
+    const bool evs = apply_ev && cx->ev_off && k > 0;
+    const int q0 = evs ? cx->ev_off[k - 1] : 0, q1 = evs ? cx->ev_off[k] : 0;
+    for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+      T d = din[b];
+      for (int q = q0; q < q1; ++q)
+        if (cx->ev_inst[q] == b) d = O::add(d, (T)cx->ev_amt[q]);
+      if (DETECT) dout[b] = O::mul(d, p.da_decay);
+      else if (q1 > q0) p.da[(size_t)(t & 1) * p.B + b] = d;  // Euler-only launch: events only, in place
+    }
   }
 
   const uint32_t nquad = (uint32_t)(p.Nld >> 2);
@@ -173,7 +198,7 @@ neuron_kernel(DevNet<T> p, int64_t t, int32_t k_rel, int slot, int prev, const T
       tp = ld4(trp + j0);
       if (p.homeostasis) ho = ld4(p.ho + j0);
     }
-    uint32_t l0 = p.B == 1 ? j0 : j0 % Nper;
+    const uint32_t l0 = p.B == 1 ? j0 : j0 % Nper;
     bool exc[4], act[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -193,10 +218,7 @@ neuron_kernel(DevNet<T> p, int64_t t, int32_t k_rel, int slot, int prev, const T
                                   make_uint2((uint32_t)p.noise_seed, (uint32_t)(p.noise_seed >> 32)));
           const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            double U = __dmul_rn(__dadd_rn((double)w[c], 0.5), 1.0 / 4294967296.0);
-            I.x[c] = O::add((T)__dmul_rn(p.noise_amp, __dsub_rn(U, 0.5)), I.x[c]);
-          }
+          for (int c = 0; c < 4; ++c) I.x[c] = O::add((T)philox_to_noise(w[c], p.noise_amp), I.x[c]);
         }
         Vec4<T> z; z.x[0] = z.x[1] = z.x[2] = z.x[3] = (T)0;
         st4(p.Iacc + j0, z);
@@ -261,7 +283,7 @@ neuron_kernel(DevNet<T> p, int64_t t, int32_t k_rel, int slot, int prev, const T
             if (s) {
               const int pos = base + __popc(m & ((1u << lane) - 1u));
               list[pos] = (int32_t)(j0 + c);
-              if (p.rec_ids && (int64_t)rec_base + pos < p.rec_cap) p.rec_ids[rec_base + pos] = (int32_t)(j0 + c);
+              if (rec_ids && (int64_t)rec_base + pos < rec_cap) rec_ids[rec_base + pos] = (int32_t)(j0 + c);
             }
           }
         }
@@ -285,8 +307,11 @@ __global__ void force_kernel(DevNet<T> p, const int32_t* __restrict__ idx, int n
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-gather_kernel(DevNet<T> p, int64_t t, const T* __restrict__ noise) {
+gather_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
   typedef Ops<T> O;
+  const int64_t t = cx->t0 + k;
+  const int slot = (cx->slot0 + k) % p.R;
+  const T* __restrict__ noise = cx->noise ? cx->noise + (size_t)k * p.N : nullptr;
   unsigned long long ev = 0;
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.N;
        j += (int64_t)gridDim.x * blockDim.x) {
@@ -294,12 +319,12 @@ gather_kernel(DevNet<T> p, int64_t t, const T* __restrict__ noise) {
     if (p.noise_mode == SNN_NOISE_REPLAY) acc = noise[j];
     else if (p.noise_mode == SNN_NOISE_PHILOX) acc = (T)philox_noise(p.noise_seed, t, j, p.noise_amp);
     const uint32_t c0 = p.colptr[j], c1 = p.colptr[j + 1];
-    for (uint32_t k = c0; k < c1; ++k) {
-      const uint32_t pk = p.in_pre[k];
+    for (uint32_t q = c0; q < c1; ++q) {
+      const uint32_t pk = p.in_pre[q];
       const uint32_t i = pk & kPreMask;
-      const int a = (int)(pk >> kPreBits);
-      const uint32_t word = p.bits[(size_t)slot_of(t - a, p.R) * p.W + (i >> 5)];
-      if ((word >> (i & 31)) & 1u) { acc = O::add(acc, p.wsd[p.in_syn[k]].x); ++ev; }
+      const int sl = wrap_slot(slot - (int)(pk >> kPreBits), p.R);
+      const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
+      if ((word >> (i & 31)) & 1u) { acc = O::add(acc, p.wsd[p.in_syn[q]].x); ++ev; }
     }
     p.Iacc[j] = acc;
   }
@@ -307,151 +332,159 @@ gather_kernel(DevNet<T> p, int64_t t, const T* __restrict__ noise) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2+K3 synapse_kernel(t): persistent grid, sub-warp groups of G lanes per work item.
-//   phase 1, arrivals: for every age a=0..Dmax-1 and every neuron i that spiked at t-a, walk the
-//     delay-(a+1) segment of row i:  I[post] += w (PUSH), and for plastic rows LTD with the post
-//     trace of this call (new_net.jl:127 `sd[n,:] .-= 1.5 .* STDP`).  If the target also spiked
-//     at t the same thread applies its LTP too, in the reference's loop order
-//     (post<=pre: + then -, else - then +; new_net.jl:125-128).
-//   phase 2, LTP: for every neuron j that spiked at t walk the plastic prefix of its incoming
-//     list (new_net.jl:126 `sd[:,n] .+= STDP`), skipping synapses owned by phase 1.
-// Every synapse is written by exactly one thread per call: no atomics on sd, bit-reproducible.
+// K2 arrival_kernel(t): persistent grid, sub-warp groups of G lanes per work item.  For every age
+// a=0..Dmax-1 and every neuron i that spiked at t-a, walk the delay-(a+1) segment of row i:
+// I[post] += w (PUSH), and for plastic rows LTD with the post trace of this call
+// (new_net.jl:127 `sd[n,:] .-= 1.5 .* STDP`).  If the target also spiked at t the same thread
+// applies its LTP too, in the reference's loop order (post<=pre: + then -, else - then +;
+// new_net.jl:125-128).  ltp_kernel skips those synapses, so every synapse is written by exactly
+// one thread per call: no atomics on sd, bit-reproducible, and the two kernels may overlap.
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool PUSH>
 __global__ void __launch_bounds__(256)
-synapse_kernel(DevNet<T> p, int64_t t, int32_t k_rel, int slot, int g_arr_log2, int g_ltp_log2) {
+arrival_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
   typedef Ops<T> O;
   __shared__ int cum[kMaxDelay + 2];
   __shared__ int slots[kMaxDelay + 1];
-  __shared__ unsigned long long blk_ev, blk_ltp;
+  __shared__ unsigned long long blk_ev;
+  const int slot = (cx->slot0 + k) % p.R;
   // prologue: the Dmax list lengths are loaded in parallel (one round trip), scanned in smem
   if (threadIdx.x < (unsigned)p.Dmax) {
-    int sl = slot - (int)threadIdx.x;
-    if (sl < 0) sl += p.R;
+    const int sl = wrap_slot(slot - (int)threadIdx.x, p.R);
     slots[threadIdx.x] = sl;
     cum[threadIdx.x + 1] = p.spk_cnt[sl];
   }
-  if (threadIdx.x == 0) { blk_ev = 0ull; blk_ltp = 0ull; }
+  if (threadIdx.x == 0) blk_ev = 0ull;
   __syncthreads();
   if (threadIdx.x == 0) {
+    const int c0 = cum[1];
     int acc = 0;
     for (int a = 0; a < p.Dmax; ++a) { int c = cum[a + 1]; cum[a] = acc; acc += c; }
     cum[p.Dmax] = acc;
     if (blockIdx.x == 0) {
-      const int c0 = cum[p.Dmax > 1 ? 1 : p.Dmax];
       p.counters[0] += (unsigned long long)c0;  // single writer
-      if (p.rec_ids) {
-        int64_t nxt = (int64_t)p.rec_off[k_rel] + c0;
-        p.rec_off[k_rel + 1] = (int32_t)(nxt < p.rec_cap ? nxt : p.rec_cap);
+      if (cx->rec_ids) {
+        int64_t nxt = (int64_t)cx->rec_off[k] + c0;
+        cx->rec_off[k + 1] = (int32_t)(nxt < cx->rec_cap ? nxt : cx->rec_cap);
       }
-      int nx = slot + 1; if (nx >= p.R) nx -= p.R;
-      p.spk_cnt[nx] = 0;  // next call's list; not read by this launch (R = Dmax+1)
+      p.spk_cnt[wrap_slot(slot + 1, p.R)] = 0;  // next call's list; nobody reads it now (R = Dmax+1)
     }
   }
   __syncthreads();
   const int total_arr = cum[p.Dmax];
-  const int n_now = p.Dmax > 1 ? cum[1] : total_arr;  // = spk_cnt[slot]
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
   const uint32_t Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
   const size_t Nld = (size_t)p.Nld;
   const T* __restrict__ tr_now = p.trace + (size_t)slot * Nld;
   const uint32_t* __restrict__ bits_now = p.bits + (size_t)slot * p.W;
-  unsigned long long n_ev = 0, n_ltp = 0;
-
-  {  // LTP over the incoming index of this call's spikers.  Items are handed out from the LAST
-     // group downwards so they run concurrently with the arrivals of the low groups.
-    const uint32_t G = 1u << g_ltp_log2;
-    const uint32_t gl = gtid & (G - 1);
-    const uint32_t ngroups = nthreads >> g_ltp_log2;
-    const int32_t* __restrict__ list = p.spk_list + (size_t)slot * Nld;
-    for (uint32_t item = ngroups - 1 - (gtid >> g_ltp_log2); item < (uint32_t)n_now; item += ngroups) {
-      const int32_t j = list[item];
-      const uint32_t c0 = p.colptr[j], c1 = c0 + p.col_npl[j];
-      if (gl == 0) n_ltp += (c1 - c0);
-      for (uint32_t kb = c0 + gl; kb < c1; kb += 3 * G) {
-        uint32_t pk[3], e[3]; bool ok[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const uint32_t k = kb + q * G;
-          ok[q] = k < c1;
-          pk[q] = ok[q] ? p.in_pre[k] : 0u;
-          e[q] = ok[q] ? p.in_syn[k] : 0u;
-        }
-        size_t toff[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const uint32_t i = pk[q] & kPreMask;
-          const int sl = slots[pk[q] >> kPreBits];
-          toff[q] = (size_t)sl * Nld + i;
-          if (ok[q]) {
-            const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
-            ok[q] = !((word >> (i & 31)) & 1u);  // else the spike arrives now: arrivals own the synapse
-          }
-        }
-        T trv[3], sdv[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          trv[q] = ok[q] ? p.trace[toff[q]] : (T)0;
-          sdv[q] = ok[q] ? p.wsd[e[q]].y : (T)0;
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-          if (ok[q]) p.wsd[e[q]].y = O::add(sdv[q], O::mul(p.apost, trv[q]));
+  unsigned long long n_ev = 0;
+  const uint32_t G = 1u << g_log2;
+  const uint32_t gl = gtid & (G - 1);
+  const uint32_t ngroups = nthreads >> g_log2;
+  for (uint32_t item = gtid >> g_log2; item < (uint32_t)total_arr; item += ngroups) {
+    int a = 0;
+    while (a + 1 < p.Dmax && cum[a + 1] <= (int)item) ++a;
+    const int sl = slots[a];
+    const uint32_t i = (uint32_t)p.spk_list[(size_t)sl * Nld + (item - cum[a])];
+    const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1) + a];
+    const uint32_t s1 = p.seg[(size_t)i * (p.Dmax + 1) + a + 1];
+    const uint32_t ibase = p.B == 1 ? 0u : (i / Nper) * Nper;
+    const bool row_plastic = (i - ibase) < Ne;
+    const T pre_up = row_plastic ? O::mul(p.apost, p.trace[(size_t)sl * Nld + i]) : (T)0;
+    if (gl == 0) n_ev += (s1 - s0);
+    for (uint32_t e = s0 + gl; e < s1; e += G) {
+      const uint32_t j = (uint32_t)p.post[e];
+      typename DevNet<T>::T2 ws = p.wsd[e];
+      if (PUSH) atomicAdd(&p.Iacc[j], ws.x);
+      if (row_plastic && (p.plastic_ei || (j - ibase) < Ne)) {
+        const T dn = O::mul(p.apre, tr_now[j]);
+        const bool jsp = (bits_now[j >> 5] >> (j & 31)) & 1u;
+        T sd = ws.y;
+        if (jsp) sd = (j <= i) ? O::sub(O::add(sd, pre_up), dn) : O::add(O::sub(sd, dn), pre_up);
+        else sd = O::sub(sd, dn);
+        p.wsd[e].y = sd;
       }
     }
   }
-  {  // arrivals
-    const uint32_t G = 1u << g_arr_log2;
-    const uint32_t gl = gtid & (G - 1);
-    const uint32_t ngroups = nthreads >> g_arr_log2;
-    for (uint32_t item = gtid >> g_arr_log2; item < (uint32_t)total_arr; item += ngroups) {
-      int a = 0;
-      while (a + 1 < p.Dmax && cum[a + 1] <= (int)item) ++a;
-      const int sl = slots[a];
-      const uint32_t i = (uint32_t)p.spk_list[(size_t)sl * Nld + (item - cum[a])];
-      const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1) + a];
-      const uint32_t s1 = p.seg[(size_t)i * (p.Dmax + 1) + a + 1];
-      const uint32_t ibase = p.B == 1 ? 0u : (i / Nper) * Nper;
-      const bool row_plastic = (i - ibase) < Ne;
-      const T pre_up = row_plastic ? O::mul(p.apost, p.trace[(size_t)sl * Nld + i]) : (T)0;
-      if (gl == 0) n_ev += (s1 - s0);
-      for (uint32_t e = s0 + gl; e < s1; e += G) {
-        const uint32_t j = (uint32_t)p.post[e];
-        typename DevNet<T>::T2 ws = p.wsd[e];
-        if (PUSH) atomicAdd(&p.Iacc[j], ws.x);
-        if (row_plastic && (p.plastic_ei || (j - ibase) < Ne)) {
-          const T dn = O::mul(p.apre, tr_now[j]);
-          const bool jsp = (bits_now[j >> 5] >> (j & 31)) & 1u;
-          T sd = ws.y;
-          if (jsp) sd = (j <= i) ? O::sub(O::add(sd, pre_up), dn) : O::add(O::sub(sd, dn), pre_up);
-          else sd = O::sub(sd, dn);
-          p.wsd[e].y = sd;
-        }
-      }
-    }
-  }
-  // block-local reduction, then one plain RMW on this block's own counter slot (no contended atomics)
-  for (int o = 16; o > 0; o >>= 1) {
-    n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
-    n_ltp += __shfl_down_sync(0xffffffffu, n_ltp, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (n_ev) atomicAdd(&blk_ev, n_ev);
-    if (n_ltp) atomicAdd(&blk_ltp, n_ltp);
-  }
+  // block-local reduction, then one plain RMW on this block's own slot (no contended atomics)
+  for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
+  if ((threadIdx.x & 31) == 0 && n_ev) atomicAdd(&blk_ev, n_ev);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    if (PUSH) p.blk_counters[2 * blockIdx.x] += blk_ev;
-    p.blk_counters[2 * blockIdx.x + 1] += blk_ltp;
+  if (threadIdx.x == 0 && PUSH && blk_ev) p.blk_ev[blockIdx.x] += blk_ev;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 ltp_kernel(t): for every neuron j that spiked at t walk the plastic prefix of its incoming
+// list (new_net.jl:126 `sd[:,n] .+= STDP`): sd += apost * trace_pre as seen at the synapse
+// (trace of step t-(d-1), Old_net/DASTDP.jl:62-68).  Synapses whose presynaptic spike arrives
+// at this very call are owned by arrival_kernel (see there).  Three gathers are kept in flight
+// per lane.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
+  typedef Ops<T> O;
+  __shared__ unsigned long long blk_ltp;
+  const int slot = (cx->slot0 + k) % p.R;
+  const int n_now = p.spk_cnt[slot];
+  if (threadIdx.x == 0) blk_ltp = 0ull;
+  __syncthreads();
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const size_t Nld = (size_t)p.Nld;
+  const uint32_t G = 1u << g_log2;
+  const uint32_t gl = gtid & (G - 1);
+  const uint32_t ngroups = nthreads >> g_log2;
+  const int32_t* __restrict__ list = p.spk_list + (size_t)slot * Nld;
+  unsigned long long n_ltp = 0;
+  for (uint32_t item = gtid >> g_log2; item < (uint32_t)n_now; item += ngroups) {
+    const int32_t j = list[item];
+    const uint32_t c0 = p.colptr[j], c1 = c0 + p.col_npl[j];
+    if (gl == 0) n_ltp += (c1 - c0);
+    for (uint32_t kb = c0 + gl; kb < c1; kb += 3 * G) {
+      uint32_t pk[3], e[3]; bool ok[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const uint32_t kk = kb + q * G;
+        ok[q] = kk < c1;
+        pk[q] = ok[q] ? p.in_pre[kk] : 0u;
+        e[q] = ok[q] ? p.in_syn[kk] : 0u;
+      }
+      size_t toff[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const uint32_t i = pk[q] & kPreMask;
+        const int sl = wrap_slot(slot - (int)(pk[q] >> kPreBits), p.R);
+        toff[q] = (size_t)sl * Nld + i;
+        if (ok[q]) {
+          const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
+          ok[q] = !((word >> (i & 31)) & 1u);
+        }
+      }
+      T trv[3], sdv[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        trv[q] = ok[q] ? p.trace[toff[q]] : (T)0;
+        sdv[q] = ok[q] ? p.wsd[e[q]].y : (T)0;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (ok[q]) p.wsd[e[q]].y = O::add(sdv[q], O::mul(p.apost, trv[q]));
+    }
   }
+  for (int o = 16; o > 0; o >>= 1) n_ltp += __shfl_down_sync(0xffffffffu, n_ltp, o);
+  if ((threadIdx.x & 31) == 0 && n_ltp) atomicAdd(&blk_ltp, n_ltp);
+  __syncthreads();
+  if (threadIdx.x == 0 && blk_ltp) p.blk_ltp[blockIdx.x] += blk_ltp;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K4 learn_kernel: one streaming pass over the plastic synapses of every instance
 //   w = clamp(w + rate*sd, wmin, wmax) ; sd *= sd_decay      (new_net.jl:135-142)
-// rate = (learn_base+da) | da | eta*da.  16 B/synapse fp32 (read w,sd; write w,sd).
-// blockIdx.y = instance; exc rows of an instance are contiguous in the CSR.
+// rate = (learn_base+da) | da | eta*da with da as decayed by this step (new_net.jl:131 runs
+// before learn!).  16 B/synapse fp32 (read w,sd; write w,sd); four 16-byte loads in flight per
+// thread.  blockIdx.y = instance; exc rows of an instance are contiguous in the CSR.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void learn_one(typename Real2<T>::type& ws, T g, T wmin, T wmax, T sdk,
@@ -466,14 +499,15 @@ __device__ __forceinline__ void learn_one(typename Real2<T>::type& ws, T g, T wm
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-learn_kernel(DevNet<T> p, int do_learn, int do_decay) {
+learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int do_learn, int do_decay) {
   typedef Ops<T> O;
   typedef typename DevNet<T>::T2 T2;
   const int b = blockIdx.y;
+  const int64_t t = cx->t0 + k;
   const int64_t r0 = (int64_t)b * p.Nper;
   const uint32_t lo = p.seg[(size_t)r0 * (p.Dmax + 1)];
   const uint32_t hi = p.seg[(size_t)(r0 + p.Ne - 1) * (p.Dmax + 1) + p.Dmax];
-  const T da = p.da[b];
+  const T da = p.da[(size_t)((t + 1) & 1) * p.B + b];
   const T g = p.rate_mode == SNN_RATE_BASE_PLUS_DA ? O::add(p.learn_base, da)
               : (p.rate_mode == SNN_RATE_DA ? da : O::mul(p.eta, da));
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -578,6 +612,22 @@ __global__ void wsd_to_caller(const typename Real2<T>::type* __restrict__ wsd, c
     out[perm[e]] = (double)(comp == 0 ? wsd[e].x : wsd[e].y);
 }
 
+// grow-only device buffer
+struct DevBuf {
+  void* ptr = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+  template <typename U> U* as() const { return reinterpret_cast<U*>(ptr); }
+};
+
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 class Engine : public IEngine {
@@ -588,12 +638,15 @@ class Engine : public IEngine {
   int init(std::string& err) override {
     SNN_CUDA_OK(cudaSetDevice(cfg_.device));
     SNN_CUDA_OK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    SNN_CUDA_OK(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
     stream_ = own_stream_;
     SNN_CUDA_OK(cudaEventCreate(&ev_begin_));
     SNN_CUDA_OK(cudaEventCreate(&ev_end_));
+    for (auto& e : dep_ev_) SNN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device);
     n_sm_ = sms;
+    use_graph_ = cfg_.reserved[0] == 0;
     DevNet<T>& p = p_;
     memset(&p, 0, sizeof(p));
     p.N = cfg_.n_neurons; p.Nld = (p.N + 127) / 128 * 128; p.Nper = cfg_.n_per_instance; p.Ne = cfg_.n_exc;
@@ -607,16 +660,19 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMalloc(&p.bits, (size_t)p.R * p.W * sizeof(uint32_t)));
     SNN_CUDA_OK(cudaMalloc(&p.spk_list, (size_t)p.R * N * sizeof(int32_t)));
     SNN_CUDA_OK(cudaMalloc(&p.spk_cnt, (size_t)p.R * sizeof(int32_t)));
-    SNN_CUDA_OK(cudaMalloc(&p.da, (size_t)p.B * sizeof(T)));
+    SNN_CUDA_OK(cudaMalloc(&p.da, 2 * (size_t)p.B * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.counters, 4 * sizeof(unsigned long long)));
-    SNN_CUDA_OK(cudaMalloc(&p.blk_counters, 2 * kMaxSynBlocks * sizeof(unsigned long long)));
-    SNN_CUDA_OK(cudaMemsetAsync(p.blk_counters, 0, 2 * kMaxSynBlocks * sizeof(unsigned long long), stream_));
+    SNN_CUDA_OK(cudaMalloc(&p.blk_ev, kMaxSynBlocks * sizeof(unsigned long long)));
+    SNN_CUDA_OK(cudaMalloc(&p.blk_ltp, kMaxSynBlocks * sizeof(unsigned long long)));
+    SNN_CUDA_OK(cudaMalloc(&d_ctx_, sizeof(WindowCtx<T>)));
+    SNN_CUDA_OK(cudaMallocHost(&h_ctx_, sizeof(WindowCtx<T>)));
+    SNN_CUDA_OK(cudaMallocHost(&h_blk_, 2 * kMaxSynBlocks * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMemsetAsync(p.ho, 0, N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.Iacc, 0, N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.trace, 0, (size_t)p.R * N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.bits, 0, (size_t)p.R * p.W * sizeof(uint32_t), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.spk_cnt, 0, (size_t)p.R * sizeof(int32_t), stream_));
-    SNN_CUDA_OK(cudaMemsetAsync(p.da, 0, (size_t)p.B * sizeof(T), stream_));
+    SNN_CUDA_OK(cudaMemsetAsync(p.da, 0, 2 * (size_t)p.B * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.counters, 0, 4 * sizeof(unsigned long long), stream_));
     p.vthresh = (T)cfg_.vthresh; p.v_reset = (T)cfg_.v_reset; p.a_exc = (T)cfg_.a_exc; p.a_inh = (T)cfg_.a_inh;
     p.d_exc = (T)cfg_.d_exc; p.d_inh = (T)cfg_.d_inh; p.trace_set = (T)cfg_.trace_set;
@@ -636,6 +692,7 @@ class Engine : public IEngine {
 
   int set_topology(Topo&& topo, const double* h_w, std::string& err) override {
     SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    drop_graph();
     topo_.release();
     topo_ = topo;
     DevNet<T>& p = p_;
@@ -647,11 +704,9 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMalloc(&p.wsd, Ea * sizeof(typename DevNet<T>::T2)));
     int rc = upload_wsd(h_w, 0, 1, err);
     if (rc) return rc;
-    // group sizes from the mean work-item length
+    // lanes per work item from the mean item length
     const double mean_row = p.N ? (double)p.E / (double)p.N : 0.0;
-    int n_delays = p.Dmax;
-    double mean_seg = mean_row / (n_delays > 0 ? n_delays : 1);
-    g_arr_log2_ = pick_group(mean_seg);
+    g_arr_log2_ = pick_group(mean_row / p.Dmax);
     g_ltp_log2_ = pick_group(mean_row);
     have_topo_ = true;
     return SNN_OK;
@@ -670,7 +725,7 @@ class Engine : public IEngine {
       case SNN_FIELD_TRACE:
         if (t_ == 0) { if (count != p.N) { err = "count mismatch"; return SNN_ERR_INVALID; } std::fill(host, host + count, 0.0); return SNN_OK; }
         src = p.trace + (size_t)slot_host(t_ - 1) * p.Nld; scale = cfg_.trace_decay; break;
-      case SNN_FIELD_DA: src = p.da; n = p.B; break;
+      case SNN_FIELD_DA: src = p.da + (size_t)(t_ & 1) * p.B; n = p.B; break;
       case SNN_FIELD_I:
         if (!p.exact) { err = "FIELD_I is only kept in SNN_MODE_EXACT"; return SNN_ERR_INVALID; }
         src = p.Iacc; break;
@@ -708,7 +763,7 @@ class Engine : public IEngine {
       case SNN_FIELD_V: dst = p.v; break;
       case SNN_FIELD_U: dst = p.u; break;
       case SNN_FIELD_HO: dst = p.ho; break;
-      case SNN_FIELD_DA: dst = p.da; n = p.B; break;
+      case SNN_FIELD_DA: dst = p.da + (size_t)(t_ & 1) * p.B; n = p.B; break;
       case SNN_FIELD_W: case SNN_FIELD_SD:
         if (!have_topo_) { err = "synapses not set"; return SNN_ERR_STATE; }
         if (count != p.E) { err = "count mismatch"; return SNN_ERR_INVALID; }
@@ -746,8 +801,12 @@ class Engine : public IEngine {
 
   int64_t n_synapses() const override { return p_.E; }
   int64_t step_index() const override { return t_; }
-  void set_profiling(bool on) override { profiling_ = on; }
-  void set_stream(cudaStream_t s) override { stream_ = s ? s : own_stream_; }
+  void set_profiling(int mode) override { profiling_ = mode; }
+  void set_stream(cudaStream_t s) override {
+    cudaStream_t ns = s ? s : own_stream_;
+    if (ns != stream_) drop_graph();
+    stream_ = ns;
+  }
   cudaStream_t stream() const override { return stream_; }
 
  private:
@@ -775,49 +834,204 @@ class Engine : public IEngine {
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return SNN_ERR_CUDA; }
     return SNN_OK;
   }
+  void drop_graph() {
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    graph_exec_ = nullptr; graph_key_.clear();
+  }
   void release() {
     DevNet<T>& p = p_;
+    drop_graph();
     cudaFree(p.v); cudaFree(p.u); cudaFree(p.ho); cudaFree(p.Iacc); cudaFree(p.trace); cudaFree(p.bits);
-    cudaFree(p.spk_list); cudaFree(p.spk_cnt); cudaFree(p.da); cudaFree(p.counters); cudaFree(p.blk_counters); cudaFree(p.wsd);
+    cudaFree(p.spk_list); cudaFree(p.spk_cnt); cudaFree(p.da); cudaFree(p.counters); cudaFree(p.blk_ev);
+    cudaFree(p.blk_ltp); cudaFree(p.wsd); cudaFree(d_ctx_);
+    if (h_ctx_) cudaFreeHost(h_ctx_);
+    if (h_blk_) cudaFreeHost(h_blk_);
+    b_noise_.release(); b_noise64_.release(); b_ev_off_.release(); b_ev_inst_.release(); b_ev_amt_.release();
+    b_force_.release(); b_rec_.release(); b_rec_off_.release();
     topo_.release();
     if (ev_begin_) cudaEventDestroy(ev_begin_);
     if (ev_end_) cudaEventDestroy(ev_end_);
+    for (auto& e : dep_ev_) if (e) cudaEventDestroy(e);
     for (auto& e : prof_events_) cudaEventDestroy(e);
     prof_events_.clear();
     if (own_stream_) cudaStreamDestroy(own_stream_);
+    if (side_stream_) cudaStreamDestroy(side_stream_);
     memset(&p, 0, sizeof(p));
-    own_stream_ = nullptr; ev_begin_ = ev_end_ = nullptr;
+    own_stream_ = side_stream_ = nullptr; ev_begin_ = ev_end_ = nullptr; d_ctx_ = nullptr; h_ctx_ = nullptr; h_blk_ = nullptr;
   }
 
-  // profiling: event pairs around launches, tagged by kernel class
-  void prof_begin(int cls) {
-    if (!profiling_) return;
-    if (prof_used_ + 2 > prof_events_.size()) {
+  // event pairs around launches, tagged by kernel class (0 neuron, 1 synapse, 2 learn)
+  void prof_reserve(size_t n_events) {
+    if (n_events > prof_events_.size()) {
       size_t old = prof_events_.size();
-      prof_events_.resize(old + 256);
+      prof_events_.resize(n_events);
       for (size_t q = old; q < prof_events_.size(); ++q) cudaEventCreate(&prof_events_[q]);
     }
-    cudaEventRecord(prof_events_[prof_used_], stream_);
+  }
+  // `captured`: inside stream capture an event only becomes a real record node with the
+  // External flag (otherwise it is just a dependency edge and carries no timestamp)
+  void prof_begin(int cls, cudaStream_t s, bool captured = false) {
+    prof_reserve(prof_used_ + 2);
+    if (captured) cudaEventRecordWithFlags(prof_events_[prof_used_], s, cudaEventRecordExternal);
+    else cudaEventRecord(prof_events_[prof_used_], s);
     prof_cls_.push_back(cls);
   }
-  void prof_end() {
-    if (!profiling_) return;
-    cudaEventRecord(prof_events_[prof_used_ + 1], stream_);
+  void prof_end(cudaStream_t s, bool captured = false) {
+    if (captured) cudaEventRecordWithFlags(prof_events_[prof_used_ + 1], s, cudaEventRecordExternal);
+    else cudaEventRecord(prof_events_[prof_used_ + 1], s);
     prof_used_ += 2;
   }
+
+  struct Launch {
+    int gN, gA, gP; dim3 gL;
+  };
+  Launch grids() {
+    DevNet<T>& p = p_;
+    Launch l;
+    l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 + 255) / 256, (int64_t)n_sm_ * 8));
+    if (gA_ == 0) {
+      int per_sm = 0;
+      if (p.exact) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, arrival_kernel<T, false>, 256, 0);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, arrival_kernel<T, true>, 256, 0);
+      gA_ = std::min(kMaxSynBlocks, n_sm_ * std::max(1, per_sm));
+    }
+    l.gA = gA_;
+    l.gP = std::min(kMaxSynBlocks, n_sm_ * 4);
+    int64_t plastic_per_inst = p.B ? (p.E / p.B) : 0;
+    int gLx = (int)std::max<int64_t>(1, std::min<int64_t>((plastic_per_inst / 2 + 256 * 4 - 1) / (256 * 4),
+                                                           std::max<int64_t>(1, (int64_t)n_sm_ * 8 / p.B)));
+    l.gL = dim3(gLx, p.B);
+    return l;
+  }
+  bool wants_learn(const StepArgs& a, int k, int* do_learn, int* do_decay) const {
+    const bool train = a.train_flags && a.train_flags[k];
+    const bool decay_step = cfg_.sd_decay_mode == SNN_SD_DECAY_EVERY_STEP;
+    *do_learn = train ? 1 : 0;
+    *do_decay = (decay_step || (train && cfg_.sd_decay_mode == SNN_SD_DECAY_ON_LEARN)) ? 1 : 0;
+    return (train || decay_step) && p_.E > 0 && p_.Ne > 0;
+  }
+  void launch_serial(const StepArgs& a, const std::vector<int32_t>& force_off, const int32_t* d_force, bool prof);
+  int launch_graph(const StepArgs& a, bool prof, std::string& err);
 
   snn_config cfg_;
   DevNet<T> p_;
   Topo topo_;
-  bool have_topo_ = false, profiling_ = false;
+  bool have_topo_ = false, use_graph_ = true;
+  int profiling_ = 0;
   int64_t t_ = 0;
-  int n_sm_ = 148, g_arr_log2_ = 5, g_ltp_log2_ = 5, gS_ = 0;
-  cudaStream_t own_stream_ = nullptr, stream_ = nullptr;
+  int n_sm_ = 148, g_arr_log2_ = 5, g_ltp_log2_ = 5, gA_ = 0;
+  cudaStream_t own_stream_ = nullptr, side_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev_begin_ = nullptr, ev_end_ = nullptr;
+  cudaEvent_t dep_ev_[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> prof_events_;
-  std::vector<int> prof_cls_;
-  size_t prof_used_ = 0;
+  std::vector<int> prof_cls_, graph_prof_cls_;
+  size_t prof_used_ = 0, graph_prof_used_ = 0;
+  WindowCtx<T>* d_ctx_ = nullptr; WindowCtx<T>* h_ctx_ = nullptr;
+  unsigned long long* h_blk_ = nullptr;
+  DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  std::string graph_key_;
 };
+
+// Plain stream-ordered launches: exact mode, forced spikes, per-kernel profiling.
+template <typename T>
+void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& force_off, const int32_t* d_force,
+                              bool prof) {
+  DevNet<T>& p = p_;
+  const int n = a.n_steps;
+  const Launch g = grids();
+  cudaStream_t s = stream_;
+  for (int k = 0; k <= n; ++k) {
+    const bool forced = k < n && force_off[k + 1] > force_off[k];
+    if (prof) prof_begin(0, s);
+    if (k == 0) {
+      if (forced) force_kernel<T><<<(force_off[1] - force_off[0] + 255) / 256, 256, 0, s>>>(p, d_force + force_off[0], force_off[1] - force_off[0]);
+      neuron_kernel<T, false, true><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 1);
+    } else if (k == n) {
+      neuron_kernel<T, true, false><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 1);
+    } else if (forced) {
+      // events of step k-1 must enter before the decay of step k: fold them into da[t&1] in
+      // place (no learn kernel is in flight on this serial path), then detect with decay only
+      neuron_kernel<T, true, false><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 1);
+      const int nf = force_off[k + 1] - force_off[k];
+      force_kernel<T><<<(nf + 255) / 256, 256, 0, s>>>(p, d_force + force_off[k], nf);
+      neuron_kernel<T, false, true><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 0);
+    } else {
+      neuron_kernel<T, true, true><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 1);
+    }
+    if (prof) prof_end(s);
+    if (k == n) break;
+    if (prof) prof_begin(1, s);
+    if (p.exact) {
+      gather_kernel<T><<<grid_for(p.N), 256, 0, s>>>(p, d_ctx_, k);
+      arrival_kernel<T, false><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
+    } else {
+      arrival_kernel<T, true><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
+    }
+    ltp_kernel<T><<<g.gP, 256, 0, s>>>(p, d_ctx_, k, g_ltp_log2_);
+    if (prof) prof_end(s);
+    int dl, dd;
+    if (wants_learn(a, k, &dl, &dd)) {
+      if (prof) prof_begin(2, s);
+      learn_kernel<T><<<g.gL, 256, 0, s>>>(p, d_ctx_, k, dl, dd);
+      if (prof) prof_end(s);
+    }
+  }
+}
+
+// Whole window as one CUDA graph (captured once per (length, train pattern)), two streams.
+template <typename T>
+int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
+  DevNet<T>& p = p_;
+  const int n = a.n_steps;
+  std::string key(reinterpret_cast<const char*>(&n), sizeof(n));
+  key.push_back(prof ? 'p' : '-');
+  if (a.train_flags) key.append(reinterpret_cast<const char*>(a.train_flags), n);
+  if (!graph_exec_ || key != graph_key_) {
+    drop_graph();
+    const Launch g = grids();
+    cudaStream_t s1 = stream_, s2 = side_stream_;
+    cudaGraph_t graph = nullptr;
+    prof_used_ = 0; prof_cls_.clear();
+    if (prof) prof_reserve(2 * (size_t)n + 2);  // no allocation while capturing
+    SNN_CUDA_OK(cudaStreamBeginCapture(s1, cudaStreamCaptureModeThreadLocal));
+    bool side_pending = false;
+    for (int k = 0; k < n; ++k) {
+      if (k == 0) neuron_kernel<T, false, true><<<g.gN, 256, 0, s1>>>(p, d_ctx_, k, 1);
+      else neuron_kernel<T, true, true><<<g.gN, 256, 0, s1>>>(p, d_ctx_, k, 1);
+      cudaEventRecord(dep_ev_[0], s1);
+      cudaStreamWaitEvent(s2, dep_ev_[0], 0);           // ltp(k) needs trace/bitmap/list of step k
+      ltp_kernel<T><<<g.gP, 256, 0, s2>>>(p, d_ctx_, k, g_ltp_log2_);
+      if (side_pending) cudaStreamWaitEvent(s1, dep_ev_[2], 0);  // arrival(k) needs ltp/learn(k-1)
+      arrival_kernel<T, true><<<g.gA, 256, 0, s1>>>(p, d_ctx_, k, g_arr_log2_);
+      int dl, dd;
+      if (wants_learn(a, k, &dl, &dd)) {
+        cudaEventRecord(dep_ev_[1], s1);
+        cudaStreamWaitEvent(s2, dep_ev_[1], 0);         // learn(k) needs arrival(k) (LTD) and ltp(k)
+        if (prof) prof_begin(2, s2, true);
+        learn_kernel<T><<<g.gL, 256, 0, s2>>>(p, d_ctx_, k, dl, dd);
+        if (prof) prof_end(s2, true);
+      }
+      cudaEventRecord(dep_ev_[2], s2);
+      side_pending = true;
+    }
+    if (side_pending) cudaStreamWaitEvent(s1, dep_ev_[2], 0);
+    neuron_kernel<T, true, false><<<g.gN, 256, 0, s1>>>(p, d_ctx_, n, 1);
+    cudaError_t e = cudaStreamEndCapture(s1, &graph);
+    if (e != cudaSuccess || !graph) { err = std::string("graph capture: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
+    e = cudaGraphInstantiate(&graph_exec_, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { graph_exec_ = nullptr; err = std::string("graph instantiate: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
+    graph_key_ = key;
+    graph_prof_used_ = prof_used_;
+    graph_prof_cls_ = prof_cls_;
+  } else {
+    prof_used_ = graph_prof_used_;
+    prof_cls_ = graph_prof_cls_;
+  }
+  SNN_CUDA_OK(cudaGraphLaunch(graph_exec_, stream_));
+  return SNN_OK;
+}
 
 template <typename T>
 int Engine<T>::step(const StepArgs& a, std::string& err) {
@@ -832,142 +1046,84 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   const int n = a.n_steps;
   const int64_t N = p.N;
 
-  // ---- stage the window's inputs on the device
-  T* d_noise = nullptr; double* d_noise64 = nullptr;
-  int32_t *d_ev_off = nullptr, *d_ev_inst = nullptr, *d_force = nullptr, *d_rec = nullptr, *d_rec_off = nullptr;
-  double* d_ev_amt = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_noise); cudaFree(d_noise64); cudaFree(d_ev_off); cudaFree(d_ev_inst); cudaFree(d_ev_amt);
-    cudaFree(d_force); cudaFree(d_rec); cudaFree(d_rec_off);
-    p.rec_ids = nullptr; p.rec_off = nullptr; p.rec_cap = 0;
-  };
-#define STEP_OK(expr)                                              \
-  do {                                                             \
-    cudaError_t _e = (expr);                                       \
-    if (_e != cudaSuccess) {                                       \
-      err = std::string(#expr) + ": " + cudaGetErrorString(_e);    \
-      cleanup();                                                   \
-      return SNN_ERR_CUDA;                                         \
-    }                                                              \
-  } while (0)
-
-  STEP_OK(cudaEventRecord(ev_begin_, stream_));
-  if (cfg_.noise_mode == SNN_NOISE_REPLAY) {
-    const size_t cnt = (size_t)n * N;
-    if (sizeof(T) == 8) {
-      STEP_OK(cudaMalloc(&d_noise, cnt * sizeof(T)));
-      STEP_OK(cudaMemcpyAsync(d_noise, a.noise, cnt * sizeof(double), cudaMemcpyHostToDevice, stream_));
-    } else {
-      STEP_OK(cudaMalloc(&d_noise64, cnt * sizeof(double)));
-      STEP_OK(cudaMalloc(&d_noise, cnt * sizeof(T)));
-      STEP_OK(cudaMemcpyAsync(d_noise64, a.noise, cnt * sizeof(double), cudaMemcpyHostToDevice, stream_));
-      from_double_kernel<T><<<grid_for((int64_t)cnt), 256, 0, stream_>>>(d_noise64, d_noise, (int64_t)cnt);
-    }
-  }
-  DaEvents ev{nullptr, nullptr, nullptr};
+  // ---- validate + stage the window's inputs (persistent grow-only buffers)
+  std::vector<int32_t> ev_off, ev_inst, force_off(n + 1, 0), force_ids;
+  std::vector<double> ev_amt;
   if (a.n_da > 0) {
-    std::vector<int32_t> off(n + 1, 0), inst(a.n_da);
-    std::vector<double> amt(a.n_da);
+    ev_off.assign(n + 1, 0); ev_inst.resize(a.n_da); ev_amt.resize(a.n_da);
     int prev = -1;
     for (int q = 0; q < a.n_da; ++q) {
       const snn_da_event& e = a.da[q];
       if (e.step < 0 || e.step >= n || e.step < prev || e.instance < 0 || e.instance >= p.B) {
-        err = "da events must be sorted by step, inside the window, instance in range"; cleanup(); return SNN_ERR_INVALID;
+        err = "da events must be sorted by step, inside the window, instance in range"; return SNN_ERR_INVALID;
       }
-      prev = e.step; off[e.step + 1]++; inst[q] = e.instance; amt[q] = e.amount;
+      prev = e.step; ev_off[e.step + 1]++; ev_inst[q] = e.instance; ev_amt[q] = e.amount;
     }
-    for (int k = 0; k < n; ++k) off[k + 1] += off[k];
-    STEP_OK(cudaMalloc(&d_ev_off, (n + 1) * sizeof(int32_t)));
-    STEP_OK(cudaMalloc(&d_ev_inst, a.n_da * sizeof(int32_t)));
-    STEP_OK(cudaMalloc(&d_ev_amt, a.n_da * sizeof(double)));
-    STEP_OK(cudaMemcpyAsync(d_ev_off, off.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
-    STEP_OK(cudaMemcpyAsync(d_ev_inst, inst.data(), a.n_da * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
-    STEP_OK(cudaMemcpyAsync(d_ev_amt, amt.data(), a.n_da * sizeof(double), cudaMemcpyHostToDevice, stream_));
-    STEP_OK(cudaStreamSynchronize(stream_));  // host vectors go out of scope
-    ev = DaEvents{d_ev_off, d_ev_inst, d_ev_amt};
+    for (int k = 0; k < n; ++k) ev_off[k + 1] += ev_off[k];
   }
-  std::vector<int32_t> force_off(n + 1, 0);
   if (a.n_force > 0) {
-    std::vector<int32_t> ids(a.n_force);
+    force_ids.resize(a.n_force);
     int prev = -1;
     for (int q = 0; q < a.n_force; ++q) {
       const snn_force_event& e = a.force[q];
       if (e.step < 0 || e.step >= n || e.step < prev || e.neuron < 0 || e.neuron >= N) {
-        err = "force events must be sorted by step, inside the window, neuron in range"; cleanup(); return SNN_ERR_INVALID;
+        err = "force events must be sorted by step, inside the window, neuron in range"; return SNN_ERR_INVALID;
       }
-      prev = e.step; force_off[e.step + 1]++; ids[q] = e.neuron;
+      prev = e.step; force_off[e.step + 1]++; force_ids[q] = e.neuron;
     }
     for (int k = 0; k < n; ++k) force_off[k + 1] += force_off[k];
-    STEP_OK(cudaMalloc(&d_force, a.n_force * sizeof(int32_t)));
-    STEP_OK(cudaMemcpyAsync(d_force, ids.data(), a.n_force * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
-    STEP_OK(cudaStreamSynchronize(stream_));
+  }
+  SNN_CUDA_OK(cudaEventRecord(ev_begin_, stream_));
+  WindowCtx<T>& cx = *h_ctx_;
+  memset(&cx, 0, sizeof(cx));
+  cx.t0 = t_; cx.slot0 = slot_host(t_); cx.n_steps = n;
+  if (cfg_.noise_mode == SNN_NOISE_REPLAY) {
+    const size_t cnt = (size_t)n * N;
+    SNN_CUDA_OK(b_noise_.reserve(cnt * sizeof(T)));
+    if (sizeof(T) == 8) {
+      SNN_CUDA_OK(cudaMemcpyAsync(b_noise_.ptr, a.noise, cnt * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    } else {
+      SNN_CUDA_OK(b_noise64_.reserve(cnt * sizeof(double)));
+      SNN_CUDA_OK(cudaMemcpyAsync(b_noise64_.ptr, a.noise, cnt * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      from_double_kernel<T><<<grid_for((int64_t)cnt), 256, 0, stream_>>>(b_noise64_.as<double>(), b_noise_.as<T>(), (int64_t)cnt);
+    }
+    cx.noise = b_noise_.as<T>();
+  }
+  if (a.n_da > 0) {
+    SNN_CUDA_OK(b_ev_off_.reserve((n + 1) * sizeof(int32_t)));
+    SNN_CUDA_OK(b_ev_inst_.reserve(a.n_da * sizeof(int32_t)));
+    SNN_CUDA_OK(b_ev_amt_.reserve(a.n_da * sizeof(double)));
+    SNN_CUDA_OK(cudaMemcpyAsync(b_ev_off_.ptr, ev_off.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    SNN_CUDA_OK(cudaMemcpyAsync(b_ev_inst_.ptr, ev_inst.data(), a.n_da * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    SNN_CUDA_OK(cudaMemcpyAsync(b_ev_amt_.ptr, ev_amt.data(), a.n_da * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    cx.ev_off = b_ev_off_.as<int32_t>(); cx.ev_inst = b_ev_inst_.as<int32_t>(); cx.ev_amt = b_ev_amt_.as<double>();
+  }
+  if (a.n_force > 0) {
+    SNN_CUDA_OK(b_force_.reserve(a.n_force * sizeof(int32_t)));
+    SNN_CUDA_OK(cudaMemcpyAsync(b_force_.ptr, force_ids.data(), a.n_force * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
   }
   if (a.spikes_out) {
-    STEP_OK(cudaMalloc(&d_rec, a.spikes_cap * sizeof(int32_t)));
-    STEP_OK(cudaMalloc(&d_rec_off, (n + 1) * sizeof(int32_t)));
-    STEP_OK(cudaMemsetAsync(d_rec_off, 0, (n + 1) * sizeof(int32_t), stream_));
-    p.rec_ids = d_rec; p.rec_off = d_rec_off; p.rec_cap = a.spikes_cap;
+    SNN_CUDA_OK(b_rec_.reserve(a.spikes_cap * sizeof(int32_t)));
+    SNN_CUDA_OK(b_rec_off_.reserve((n + 1) * sizeof(int32_t)));
+    SNN_CUDA_OK(cudaMemsetAsync(b_rec_off_.ptr, 0, (n + 1) * sizeof(int32_t), stream_));
+    cx.rec_ids = b_rec_.as<int32_t>(); cx.rec_off = b_rec_off_.as<int32_t>(); cx.rec_cap = a.spikes_cap;
   }
-  unsigned long long c_before[4];
-  STEP_OK(cudaMemcpyAsync(c_before, p.counters, sizeof(c_before), cudaMemcpyDeviceToHost, stream_));
-  STEP_OK(cudaMemsetAsync(p.blk_counters, 0, 2 * kMaxSynBlocks * sizeof(unsigned long long), stream_));
+  SNN_CUDA_OK(cudaMemcpyAsync(d_ctx_, h_ctx_, sizeof(cx), cudaMemcpyHostToDevice, stream_));
+  unsigned long long c_before[4], c_after[4];
+  SNN_CUDA_OK(cudaMemcpyAsync(c_before, p.counters, sizeof(c_before), cudaMemcpyDeviceToHost, stream_));
+  SNN_CUDA_OK(cudaMemsetAsync(p.blk_ev, 0, kMaxSynBlocks * sizeof(unsigned long long), stream_));
+  SNN_CUDA_OK(cudaMemsetAsync(p.blk_ltp, 0, kMaxSynBlocks * sizeof(unsigned long long), stream_));
 
-  prof_used_ = 0; prof_cls_.clear();
-  // one quad of neurons per thread; persistent synapse grid sized to what is resident
-  const int gN = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 + 255) / 256, (int64_t)n_sm_ * 8));
-  if (gS_ == 0) {
-    int per_sm = 0;
-    if (p.exact) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synapse_kernel<T, false>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synapse_kernel<T, true>, 256, 0);
-    gS_ = std::min(kMaxSynBlocks, n_sm_ * std::max(1, per_sm));
+  // ---- the window
+  const bool graphable = use_graph_ && !p.exact && a.n_force == 0 && profiling_ != 1;
+  if (graphable) {
+    int rc = launch_graph(a, profiling_ == 2, err);
+    if (rc) return rc;
+  } else {
+    prof_used_ = 0; prof_cls_.clear();
+    launch_serial(a, force_off, b_force_.as<int32_t>(), profiling_ == 1);
   }
-  const int gS = gS_;
-  // learn grid: x blocks per instance
-  int64_t plastic_per_inst = p.B ? (p.E / p.B) : 0;
-  int gLx = (int)std::max<int64_t>(1, std::min<int64_t>((plastic_per_inst / 2 + 256 * 4 - 1) / (256 * 4),
-                                                         std::max<int64_t>(1, (int64_t)n_sm_ * 8 / p.B)));
-  dim3 gL(gLx, p.B);
-
-  for (int k = 0; k <= n; ++k) {
-    const int64_t t = t_ + k;
-    const int slot = slot_host(t), prev = slot_host(t - 1);
-    const T* noise_prev = (d_noise && k > 0) ? d_noise + (size_t)(k - 1) * N : nullptr;
-    const bool forced = k < n && force_off[k + 1] > force_off[k];
-    prof_begin(0);
-    if (k == 0) {
-      if (forced) force_kernel<T><<<(force_off[1] - force_off[0] + 255) / 256, 256, 0, stream_>>>(p, d_force + force_off[0], force_off[1] - force_off[0]);
-      neuron_kernel<T, false, true><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, ev);
-    } else if (k == n) {
-      neuron_kernel<T, true, false><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, ev);
-    } else if (forced) {
-      neuron_kernel<T, true, false><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, ev);
-      const int nf = force_off[k + 1] - force_off[k];
-      force_kernel<T><<<(nf + 255) / 256, 256, 0, stream_>>>(p, d_force + force_off[k], nf);
-      neuron_kernel<T, false, true><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, DaEvents{nullptr, nullptr, nullptr});
-    } else {
-      neuron_kernel<T, true, true><<<gN, 256, 0, stream_>>>(p, t, k, slot, prev, noise_prev, ev);
-    }
-    prof_end();
-    if (k == n) break;
-    prof_begin(1);
-    if (p.exact) {
-      const T* noise_now = d_noise ? d_noise + (size_t)k * N : nullptr;
-      gather_kernel<T><<<grid_for(N), 256, 0, stream_>>>(p, t, noise_now);
-      synapse_kernel<T, false><<<gS, 256, 0, stream_>>>(p, t, k, slot, g_arr_log2_, g_ltp_log2_);
-    } else {
-      synapse_kernel<T, true><<<gS, 256, 0, stream_>>>(p, t, k, slot, g_arr_log2_, g_ltp_log2_);
-    }
-    prof_end();
-    const bool train = a.train_flags && a.train_flags[k];
-    const bool decay_step = cfg_.sd_decay_mode == SNN_SD_DECAY_EVERY_STEP;
-    if ((train || decay_step) && p.E > 0 && p.Ne > 0) {
-      prof_begin(2);
-      learn_kernel<T><<<gL, 256, 0, stream_>>>(p, train ? 1 : 0,
-                                                (decay_step || (train && cfg_.sd_decay_mode == SNN_SD_DECAY_ON_LEARN)) ? 1 : 0);
-      prof_end();
-    }
-  }
-  STEP_OK(cudaGetLastError());
+  SNN_CUDA_OK(cudaGetLastError());
   t_ += n;
 
   // ---- results
@@ -975,20 +1131,19 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   std::vector<int32_t> h_off;
   if (a.spikes_out) {
     h_off.resize(n + 1);
-    STEP_OK(cudaMemcpyAsync(h_off.data(), d_rec_off, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-    STEP_OK(cudaStreamSynchronize(stream_));
+    SNN_CUDA_OK(cudaMemcpyAsync(h_off.data(), b_rec_off_.ptr, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
     const int64_t total = h_off[n];
-    int src = sort_segments(d_rec, total, d_rec_off, n, stream_, err);
-    if (src) { cleanup(); return src; }
-    if (total > 0) STEP_OK(cudaMemcpyAsync(a.spikes_out, d_rec, total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    int src = sort_segments(b_rec_.as<int32_t>(), total, b_rec_off_.as<int32_t>(), n, stream_, err);
+    if (src) return src;
+    if (total > 0) SNN_CUDA_OK(cudaMemcpyAsync(a.spikes_out, b_rec_.ptr, total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     for (int k = 0; k <= n; ++k) a.spike_offsets[k] = h_off[k];
   }
-  unsigned long long c_after[4];
-  STEP_OK(cudaMemcpyAsync(c_after, p.counters, sizeof(c_after), cudaMemcpyDeviceToHost, stream_));
-  std::vector<unsigned long long> h_blk(2 * (size_t)gS);
-  STEP_OK(cudaMemcpyAsync(h_blk.data(), p.blk_counters, h_blk.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
-  STEP_OK(cudaEventRecord(ev_end_, stream_));
-  STEP_OK(cudaStreamSynchronize(stream_));
+  SNN_CUDA_OK(cudaMemcpyAsync(c_after, p.counters, sizeof(c_after), cudaMemcpyDeviceToHost, stream_));
+  SNN_CUDA_OK(cudaMemcpyAsync(h_blk_, p.blk_ev, kMaxSynBlocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+  SNN_CUDA_OK(cudaMemcpyAsync(h_blk_ + kMaxSynBlocks, p.blk_ltp, kMaxSynBlocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+  SNN_CUDA_OK(cudaEventRecord(ev_end_, stream_));
+  SNN_CUDA_OK(cudaStreamSynchronize(stream_));
   if (a.spikes_out && (int64_t)(c_after[0] - c_before[0]) > a.spikes_cap) {
     err = "spikes_cap too small: record truncated"; rc = SNN_ERR_CAPACITY;
   }
@@ -997,21 +1152,32 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     memset(&s, 0, sizeof(s));
     s.n_spikes = (int64_t)(c_after[0] - c_before[0]);
     s.n_syn_events = (int64_t)(c_after[1] - c_before[1]);
-    for (int b = 0; b < gS; ++b) { s.n_syn_events += (int64_t)h_blk[2 * b]; s.n_ltp_events += (int64_t)h_blk[2 * b + 1]; }
+    for (int b = 0; b < kMaxSynBlocks; ++b) { s.n_syn_events += (int64_t)h_blk_[b]; s.n_ltp_events += (int64_t)h_blk_[kMaxSynBlocks + b]; }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev_begin_, ev_end_);
     s.device_ms = ms;
-    for (size_t q = 0; q + 1 < prof_used_ + 1 && q / 2 < prof_cls_.size(); q += 2) {
+    for (size_t q = 0; q < prof_used_ && q / 2 < prof_cls_.size(); q += 2) {
       float m = 0.f;
-      cudaEventElapsedTime(&m, prof_events_[q], prof_events_[q + 1]);
+      if (cudaEventElapsedTime(&m, prof_events_[q], prof_events_[q + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
       int cls = prof_cls_[q / 2];
       if (cls == 0) { s.neuron_ms += m; s.neuron_launches++; }
       else if (cls == 1) { s.synapse_ms += m; s.synapse_launches++; }
       else { s.learn_ms += m; s.learn_launches++; }
     }
+    if (graphable) {  // launches inside the graph (events exist only around learn, if at all)
+      s.neuron_launches = n + 1; s.synapse_launches = 2 * n;
+      if (profiling_ != 2) {
+        int nl = 0, dl, dd;
+        for (int k = 0; k < n; ++k) nl += wants_learn(a, k, &dl, &dd) ? 1 : 0;
+        s.learn_launches = nl;
+      }
+    } else if (profiling_ != 1) {
+      s.neuron_launches = n + 1; s.synapse_launches = (p.exact ? 3 : 2) * n;
+      int nl = 0, dl, dd;
+      for (int k = 0; k < n; ++k) nl += wants_learn(a, k, &dl, &dd) ? 1 : 0;
+      s.learn_launches = nl;
+    }
   }
-  cleanup();
-#undef STEP_OK
   return rc;
 }
 

@@ -54,6 +54,7 @@ class SparseNetwork:
         lib = L.load()
         n_per = int(n_neurons)
         max_delay = int(params.pop("max_delay", int(delay.max()) if delay is not None and len(delay) else 1))
+        use_graph = bool(params.pop("graph", True))
         cfg = default_config(
             dtype=L.SNN_F64 if dtype == "f64" else L.SNN_F32,
             mode=L.SNN_MODE_EXACT if mode == "exact" else L.SNN_MODE_FAST,
@@ -61,6 +62,8 @@ class SparseNetwork:
             max_delay=max_delay,
             noise_mode={"none": L.SNN_NOISE_NONE, "replay": L.SNN_NOISE_REPLAY, "philox": L.SNN_NOISE_PHILOX}[noise],
             **params)
+        if not use_graph:
+            cfg.reserved[0] = 1  # plain stream-ordered launches instead of the captured window graph
         self.cfg = cfg
         self.n_neurons = int(cfg.n_neurons)
         self.n_instances = int(n_instances)
@@ -116,7 +119,8 @@ class SparseNetwork:
             out = np.empty(cap, np.int32)
             offs = np.zeros(n_steps + 1, np.int64)
         st = L.SnnStepStats()
-        lib.snn_set_profiling(self._h, 1 if profile else 0)
+        # profile: False | 'kernels' (events around every kernel class, serial launches) | 'learn'
+        lib.snn_set_profiling(self._h, {False: 0, None: 0, True: 1, 'kernels': 1, 'learn': 2}[profile])
         rc = lib.snn_step(self._h, n_steps, _ptr(noise), _ptr(tf), fe, n_force, ev, n_da, _ptr(out), _ptr(offs),
                           cap, C.byref(st))
         L.check(rc)

@@ -280,3 +280,36 @@ def test_errors_and_field_roundtrip():
                       mode="exact")
     sp, st = e.run(20, synth.thalamic_noise(20, 64, seed=2, amp=80.0), np.ones(20, np.uint8))
     assert st.n_syn_events == 0 and st.n_spikes == sum(len(s) for s in sp) > 0
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_fast_scheduler_bitexact_with_frozen_weights(graph):
+    """With learn_base = 0 and no dopamine the weights stay +-1, so the atomic scatter sums are
+    exact in any order and the production scheduler (CUDA graph, ltp/learn overlapped on a second
+    stream) must reproduce the oracle bit for bit — spikes, eligibility traces (their LTP/LTD
+    order is fixed by synapse ownership) and the learn-pass decay.  A missing dependency between
+    the overlapped kernels would show up here."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    n, ne, fan, dmax, t = 3000, 2400, 80, 12, 600
+    rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=71)
+    noise = synth.thalamic_noise(t, n, seed=12)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax, learn_base=0.0)
+    ref = run_oracle_sparse(ora, noise, train)
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="fast", max_delay=dmax,
+                        learn_base=0.0, graph=graph)
+    got = []
+    for lo in range(0, t, 200):  # three windows: the second and third reuse the cached graph
+        sp, _ = net.run(200, noise[lo:lo + 200], train[lo:lo + 200])
+        got += sp
+    for k in range(t):
+        assert np.array_equal(got[k], ref[k]), k
+    assert sum(len(r) for r in ref) > 2000
+    plastic = np.repeat(np.arange(n), np.diff(rowptr)) < ne
+    assert np.array_equal(net.get(L.FIELD_W), ora.get(4))
+    assert np.array_equal(net.get(L.FIELD_SD)[plastic], ora.get(5)[plastic])
+    assert np.array_equal(net.get(L.FIELD_V), ora.get(0))
+    assert np.array_equal(net.get(L.FIELD_TRACE), ora.get(2))
