@@ -206,6 +206,62 @@ int32_t snn_set_profiling(snn_net* net, int32_t enable);
 /* Use an externally owned CUDA stream (cudaStream_t) instead of the net's own. */
 int32_t snn_set_stream(snn_net* net, void* cuda_stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Batched layered LIF actors (variant F) — thousands of independent tiny networks, one warp each.
+ * Replaces, for a whole population, Julia/Modules/Networks/net_arch.jl: Network(arch, param)
+ * :98-128, input_LIF! :142-152, spike_LIF! :154-211, learn! :213-220, learn_critic! :222-235,
+ * step_LIF! / step_LIF_critic! :256-272, and the decision/episode loop of
+ * Julia/Actors/cartpole_fitness.jl:51-114 (with a restated CartPole-v1: gym is not part of the
+ * reference).  Arrays carry a leading agent dimension; matrices are column-major per agent,
+ * exactly the layout of the Julia `e[l]`.  fp64 only (bit-identical to the oracle). */
+typedef struct snn_actor_config {
+  int32_t struct_size;   /* = sizeof(snn_actor_config) */
+  int32_t device;
+  int32_t n_agents;
+  int32_t n_layers;      /* length(arch) */
+  int32_t arch[8];       /* e.g. {8,8,8}: sum(arch) + sum(arch[2:end-1]) must be <= 32 */
+  double vthresh, c;     /* cartpole_cfglif.yml:7-41 keys */
+  double wei, wie, wmax;
+  double theta, ttheta;
+  double imin;
+  double apost, apre;
+  double tde, ttrace;
+  double taulif;
+  double eta, winh;      /* learn_critic! only */
+  double da_inc;         /* teacher_sim.jl:133 */
+  int32_t reserved[8];
+} snn_actor_config;
+
+typedef struct snn_actor snn_actor;
+
+/* defaults = Julia/Actors/cartpole_cfglif.yml, arch [8,8,8], 1 agent */
+int32_t snn_actor_config_default(snn_actor_config* cfg);
+int32_t snn_actor_create(const snn_actor_config* cfg, snn_actor** out);
+int32_t snn_actor_destroy(snn_actor* a);
+/* field: SNN_FIELD_V|HO [n_agents][n_neurons], TRACE [n_agents][n_exc], DA [n_agents],
+ * W|SD with `layer` l: e[l] / de[l] as [n_agents][arch[l]*arch[l+1]] column-major
+ * (`net.s.e[l][idx] = w` cartpole_fitness.jl:147). */
+int32_t snn_actor_get_array(snn_actor* a, int32_t field, int32_t layer, double* host, int64_t count);
+int32_t snn_actor_set_array(snn_actor* a, int32_t field, int32_t layer, const double* host, int64_t count);
+/* n_steps calls of step_LIF!(net, spikes, train) (critic: step_LIF_critic!) with the constant
+ * input spikes = [(i, intensity[agent][i]) for i in 1:arch[1]] (int_spikes,
+ * PoissonStateSpike.jl:62-68).  reset_v: `net.v .= c` first (cartpole_fitness.jl:71).
+ * counts [n_agents][arch[end]]: last-layer spike counts from msec >= length(arch)-1 (:76-78), may
+ * be NULL.  spike_masks [n_agents][n_steps]: bit j = neuron j spiked at that step, may be NULL. */
+int32_t snn_actor_window(snn_actor* a, int32_t n_steps, const double* intensity, int32_t train, int32_t critic,
+                         int32_t reset_v, int32_t* counts, int32_t* spike_masks, double* device_ms);
+/* play_episode (cartpole_fitness.jl:51-114) for every agent, environment on the device.
+ * matalpha [n_agents][arch[1]*4] column-major, state0 [n_agents][4] (the env.reset() observation),
+ * tie_actions [n_agents][n_decisions_max]: replayed rand(rng_action, 0:1) stream (:89),
+ * teach_actions: NULL or [n_agents][n_decisions_max] replayed rand(0:1) of teacher_sim.jl:132 —
+ * with train != 0, da += (action == draw ? 1 : -200) * da_inc after every decision.
+ * Outputs: rewards [n_agents] (tot_reward), n_decisions, n_rand, final state — any may be NULL
+ * except rewards. */
+int32_t snn_actor_episodes(snn_actor* a, const double* matalpha, const double* state0, const int32_t* tie_actions,
+                           const int32_t* teach_actions, int32_t n_decisions_max, int32_t win_size, int32_t train,
+                           double* rewards, int32_t* n_decisions, int32_t* n_rand, double* state_out,
+                           double* device_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -226,13 +226,31 @@ int ora_lay_spike_izh(ora_lay* o, int32_t* spiked) {
   return k;
 }
 
-/* ---- CartPole-v1, restated (NOT pinned by the reference; gym classic_control/cartpole.py) */
+/* ---- CartPole-v1, restated (NOT pinned by the reference; gym classic_control/cartpole.py).
+ * sin/cos are the fdlibm kernel polynomials (|x| <= pi/4; the pole angle never leaves +-0.21 rad
+ * before termination) written in plain IEEE operations, so the device implementation
+ * (rl_stdp_b200/csrc/actor.cu) can reproduce them bit for bit; libm results may differ in the last
+ * ulp between glibc and CUDA. */
+static double k_sin(double x) {
+  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+               S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+  double z = x * x, v = z * x;
+  double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+  return x + v * (S1 + z * r);
+}
+static double k_cos(double x) {
+  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+               C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+  double z = x * x;
+  double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+  return (1.0 - 0.5 * z) + z * r;
+}
 int ora_cartpole_step(double s[4], int action) {
   const double gravity = 9.8, masscart = 1.0, masspole = 0.1, length = 0.5, force_mag = 10.0, tau = 0.02;
   const double total_mass = masspole + masscart, polemass_length = masspole * length;
   double x = s[0], x_dot = s[1], theta = s[2], theta_dot = s[3];
   double force = action == 1 ? force_mag : -force_mag;
-  double costheta = cos(theta), sintheta = sin(theta);
+  double costheta = k_cos(theta), sintheta = k_sin(theta);
   double temp = (force + polemass_length * (theta_dot * theta_dot) * sintheta) / total_mass;
   double thetaacc = (gravity * sintheta - costheta * temp) /
                     (length * (4.0 / 3.0 - masspole * (costheta * costheta) / total_mass));
@@ -240,9 +258,11 @@ int ora_cartpole_step(double s[4], int action) {
   x = x + tau * x_dot; x_dot = x_dot + tau * xacc;
   theta = theta + tau * theta_dot; theta_dot = theta_dot + tau * thetaacc;
   s[0] = x; s[1] = x_dot; s[2] = theta; s[3] = theta_dot;
-  const double th = 12 * 2 * M_PI / 360;
+  const double th = 12 * 2 * 3.14159265358979323846 / 360;
   return x < -2.4 || x > 2.4 || theta < -th || theta > th;
 }
+double ora_ksin(double x) { return k_sin(x); }
+double ora_kcos(double x) { return k_cos(x); }
 
 /* norm_cartpole cartpole_fitness.jl:14-24 */
 void ora_norm_cartpole(const double obs[4], double out[4]) {
@@ -263,8 +283,8 @@ void ora_norm_cartpole(const double obs[4], double out[4]) {
  * matalpha: arch[0] x 4 column-major.  tie_actions: replayed stream of the rand(rng_action,0:1)
  * draws (:89).  state0: the env.reset() observation.  Returns tot_reward; n_decisions out. */
 double ora_play_episode(ora_lay* o, const double* matalpha, const double state0[4],
-                        const int32_t* tie_actions, int n_steps, int train, int32_t* n_dec_out,
-                        int32_t* n_rand_out) {
+                        const int32_t* tie_actions, const int32_t* teach_actions, double da_inc, int n_steps,
+                        int train, int32_t* n_dec_out, int32_t* n_rand_out, double* state_out) {
   const int win_size = 40;
   double tot_reward = 0;
   double st[4] = {state0[0], state0[1], state0[2], state0[3]};
@@ -296,11 +316,16 @@ double ora_play_episode(ora_lay* o, const double* matalpha, const double state0[
     int action = (sl >= sr) ? 0 : 1; /* :36-41 */
     if (sl == sr) { action = tie_actions[n_rand]; tot_reward -= 0.9; n_rand++; } /* :87-95 */
     n_tot++;
+    if (train && teach_actions) { /* teacher_sim.jl:92-99,132-133 */
+      double inc = (action == teach_actions[j]) ? 1.0 : -200.0;
+      o->da += inc * da_inc;
+    }
     int done = ora_cartpole_step(st, action);
     tot_reward += 1;
     if (done) break;
   }
   if (n_dec_out) *n_dec_out = n_tot;
   if (n_rand_out) *n_rand_out = n_rand;
+  if (state_out) for (int q = 0; q < 4; ++q) state_out[q] = st[q];
   return tot_reward;
 }

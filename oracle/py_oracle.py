@@ -93,7 +93,11 @@ def lib() -> C.CDLL:
         L.ora_cartpole_step.argtypes = [vp, C.c_int]
         L.ora_norm_cartpole.argtypes = [vp, vp]
         L.ora_play_episode.restype = dbl
-        L.ora_play_episode.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
+        L.ora_play_episode.argtypes = [vp, vp, vp, vp, vp, dbl, C.c_int, C.c_int, vp, vp, vp]
+        L.ora_ksin.restype = dbl
+        L.ora_ksin.argtypes = [dbl]
+        L.ora_kcos.restype = dbl
+        L.ora_kcos.argtypes = [dbl]
         _lib = L
     return _lib
 
@@ -263,13 +267,16 @@ class Layered:
             lib().ora_lay_learn(self._h)
         return self._spk[:k].copy()
 
-    def play_episode(self, matalpha, state0, tie_actions, n_steps=200, train=False):
+    def play_episode(self, matalpha, state0, tie_actions, n_steps=200, train=False, teach_actions=None, da_inc=0.0):
         ma = np.asfortranarray(matalpha, np.float64)
         s0 = np.ascontiguousarray(state0, np.float64)
         ta = np.ascontiguousarray(tie_actions, np.int32)
+        te = None if teach_actions is None else np.ascontiguousarray(teach_actions, np.int32)
         nd, nr = C.c_int32(0), C.c_int32(0)
-        r = lib().ora_play_episode(self._h, _p(ma), _p(s0), _p(ta), int(n_steps), int(train), C.byref(nd), C.byref(nr))
-        return float(r), nd.value, nr.value
+        so = np.zeros(4, np.float64)
+        r = lib().ora_play_episode(self._h, _p(ma), _p(s0), _p(ta), _p(te), float(da_inc), int(n_steps), int(train),
+                                   C.byref(nd), C.byref(nr), _p(so))
+        return float(r), nd.value, nr.value, so
 
 
 def cartpole_step(state, action):

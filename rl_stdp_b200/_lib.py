@@ -38,6 +38,17 @@ class SnnConfig(C.Structure):
     ]
 
 
+class SnnActorConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32), ("n_agents", C.c_int32), ("n_layers", C.c_int32),
+        ("arch", C.c_int32 * 8),
+        ("vthresh", C.c_double), ("c", C.c_double), ("wei", C.c_double), ("wie", C.c_double), ("wmax", C.c_double),
+        ("theta", C.c_double), ("ttheta", C.c_double), ("imin", C.c_double), ("apost", C.c_double),
+        ("apre", C.c_double), ("tde", C.c_double), ("ttrace", C.c_double), ("taulif", C.c_double),
+        ("eta", C.c_double), ("winh", C.c_double), ("da_inc", C.c_double), ("reserved", C.c_int32 * 8),
+    ]
+
+
 class SnnDaEvent(C.Structure):
     _fields_ = [("step", C.c_int32), ("instance", C.c_int32), ("amount", C.c_double)]
 
@@ -75,6 +86,15 @@ SYMBOLS = {
     "snn_step_index": (C.c_int64, [_VP]),
     "snn_set_profiling": (C.c_int32, [_VP, C.c_int32]),
     "snn_set_stream": (C.c_int32, [_VP, _VP]),
+    # batched LIF actors
+    "snn_actor_config_default": (C.c_int32, [C.POINTER(SnnActorConfig)]),
+    "snn_actor_create": (C.c_int32, [C.POINTER(SnnActorConfig), C.POINTER(_VP)]),
+    "snn_actor_destroy": (C.c_int32, [_VP]),
+    "snn_actor_get_array": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
+    "snn_actor_set_array": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
+    "snn_actor_window": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP]),
+    "snn_actor_episodes": (C.c_int32, [_VP, _VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP,
+                                       _VP]),
 }
 
 _lib = None

@@ -1,0 +1,503 @@
+// actor.cu — batched layered LIF actors (variant F): thousands of tiny networks, one warp each.
+//
+// Replaces, for a whole population at once, Julia/Modules/Networks/net_arch.jl
+//   input_LIF! :142-152, spike_LIF! :154-211, learn! :213-220, learn_critic! :222-235,
+//   step_LIF! :256-263, step_LIF_critic! :265-272
+// and the decision / episode loop of Julia/Actors/cartpole_fitness.jl:14-114 (norm_cartpole,
+// 40-ms spike-count window, left_right, tie -> replayed random action with -0.9 reward) with a
+// RESTATED CartPole-v1 (the reference calls OpenAI gym through PyCall; not in the reference).
+//
+// Mapping: lane j of a warp IS neuron j (n_neurons <= 32: the [8,8,8] actor has 24 exc + 8 inh).
+// Weights e[l] and eligibility de[l] of the agent live in shared memory for the whole window /
+// episode; state is read from and written back to HBM once per launch.  fp64 with explicit
+// round-to-nearest mul/add (never contracted) so results are bit-identical to the oracle
+// (oracle/lif_oracle.c); compiled with -fmad=false as well.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "actor.h"
+
+namespace snn {
+namespace {
+
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DADD(a, b) __dadd_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+
+struct ActorDev {
+  int32_t n_agents, L, n_exc, n_inh, n, w_tot;
+  int32_t arch[kActorMaxLayers], off[kActorMaxLayers + 1], ioff[kActorMaxLayers], woff[kActorMaxLayers];
+  double vthresh, c, wei, wie, wmax, theta, ttheta, imin, apost, apre, tde, ttrace, taulif, eta, winh, da_inc;
+  double *v, *ho, *trace, *e, *de, *da;  // [A][n], [A][n], [A][n_exc], [A][w_tot], [A][w_tot], [A]
+};
+
+struct Lane {          // per-lane view of "its" neuron
+  int layer;           // exc layer index, or -1
+  int ilayer;          // hidden layer whose inh partner this lane is, or -1
+  int local;           // index inside the layer
+};
+
+__device__ __forceinline__ Lane lane_info(const ActorDev& p, int j) {
+  Lane li; li.layer = -1; li.ilayer = -1; li.local = 0;
+  for (int l = 0; l < p.L; ++l) {
+    if (j >= p.off[l] && j < p.off[l + 1]) { li.layer = l; li.local = j - p.off[l]; }
+    if (p.ioff[l] >= 0 && j >= p.ioff[l] && j < p.ioff[l] + p.arch[l]) { li.ilayer = l; li.local = j - p.ioff[l]; }
+  }
+  return li;
+}
+
+// One call of step_LIF!(net, spikes, train) / step_LIF_critic! for the agent owned by this warp.
+// se/sde: the agent's weights in shared memory, str: trace_e in shared memory.
+// Returns the spike mask (bit j = neuron j spiked).
+__device__ __forceinline__ unsigned lif_step(const ActorDev& p, const Lane& li, int lane, double intensity,
+                                             double& v, double& ho, double& da, double* se, double* sde,
+                                             double* str, int train, int critic) {
+  const unsigned FULL = 0xffffffffu;
+  const bool alive = lane < p.n;
+  const double kk = 1.0 / p.taulif;  // (1/taulif) :151,:181
+  // input_LIF! :142-152 — I = (max-min)*intensity + min with max = imin + 1.0 computed literally
+  if (alive && li.layer == 0) {
+    const double gain = DSUB(DADD(p.imin, 1.0), p.imin);
+    const double I = DADD(0.0, DADD(DMUL(gain, intensity), p.imin));
+    v = DADD(v, DMUL(kk, DADD(DADD(-v, I), p.c)));
+  }
+  // spike_LIF! :154-211
+  const bool s = alive && (DSUB(v, ho) > p.vthresh);
+  const unsigned mask = __ballot_sync(FULL, s);
+  const bool is_exc = alive && lane < p.n_exc;
+  if (s && is_exc) ho = DADD(ho, p.theta);  // :160 (every layer)
+  if (s) v = p.c;
+  // propagate :164-176 — ascending spiker id: exc sources first, then inh partners
+  double I = 0.0;
+  if (alive) {
+    if (li.layer >= 1) {
+      const int l = li.layer - 1;  // source layer
+      unsigned m = (mask >> p.off[l]) & ((1u << p.arch[l]) - 1u);
+      while (m) {
+        const int np = __ffs(m) - 1; m &= m - 1;
+        I = DADD(I, se[p.woff[l] + np + p.arch[l] * li.local]);
+      }
+      if (p.ioff[li.layer] >= 0) {  // ie[l] = wie .* (ones - I) :29
+        unsigned mi = (mask >> p.ioff[li.layer]) & ((1u << p.arch[li.layer]) - 1u);
+        while (mi) {
+          const int np = __ffs(mi) - 1; mi &= mi - 1;
+          I = DADD(I, DMUL(p.wie, DSUB(1.0, np == li.local ? 1.0 : 0.0)));
+        }
+      }
+    } else if (li.ilayer >= 0) {    // ei[l] = wei .* I(arch[l]) :30
+      unsigned m = (mask >> p.off[li.ilayer]) & ((1u << p.arch[li.ilayer]) - 1u);
+      while (m) {
+        const int np = __ffs(m) - 1; m &= m - 1;
+        I = DADD(I, DMUL(p.wei, np == li.local ? 1.0 : 0.0));
+      }
+    }
+  }
+  // lr = arch[1]+1 : n_exc  :179-182 (inhibitory neurons are never integrated in LIF mode)
+  if (alive && li.layer >= 1) {
+    double x = DADD(v, I);
+    x = DADD(x, DMUL(kk, DADD(-x, p.c)));
+    v = fmax(x, 0.);
+  }
+  // trace_e[spiked_e] = 1.0 :185, then STDP :188-200 with the new traces
+  if (is_exc) { if (s) str[lane] = 1.0; }
+  __syncwarp();
+  if (mask & ((p.n_exc >= 32) ? FULL : ((1u << p.n_exc) - 1u))) {
+    for (int l = 0; l < p.L - 1; ++l) {
+      const int nr = p.arch[l], nc = p.arch[l + 1];
+      const unsigned mr = (mask >> p.off[l]) & ((1u << nr) - 1u);
+      const unsigned mc = (mask >> p.off[l + 1]) & ((1u << nc) - 1u);
+      if (!(mr | mc)) continue;
+      for (int q = lane; q < nr * nc; q += 32) {
+        const int i = q % nr, jj = q / nr;  // column-major [i + nr*jj]
+        double x = sde[p.woff[l] + q];
+        // pre id < post id always, so the reference loop applies LTD (row of i) before LTP (column of j)
+        if ((mr >> i) & 1u) x = DSUB(x, DMUL(p.apre, str[p.off[l + 1] + jj]));
+        if ((mc >> jj) & 1u) x = DADD(x, DMUL(p.apost, str[p.off[l] + i]));
+        sde[p.woff[l] + q] = x;
+      }
+    }
+  }
+  __syncwarp();
+  // time decay :204-209
+  if (alive) ho = DMUL(ho, p.ttheta);
+  if (is_exc) str[lane] = DMUL(str[lane], p.ttrace);
+  da = DMUL(da, p.tde);  // (tde, not tda)
+  for (int q = lane; q < p.w_tot; q += 32) sde[q] = DMUL(sde[q], p.tde);
+  __syncwarp();
+  if (train) {
+    const double g = critic ? DMUL(p.eta, da) : da;  // learn_critic! :226 / learn! :217
+    for (int q = lane; q < p.w_tot; q += 32) {
+      const double x = DADD(se[q], DMUL(g, sde[q]));
+      se[q] = x > p.wmax ? p.wmax : (x < 0.0 ? 0.0 : x);
+    }
+    if (critic) {  // :229-234 last div(arch[l],4) rows of hidden e[l] <- winh
+      __syncwarp();
+      for (int l = 1; l < p.L - 1; ++l) {
+        const int n_inh = p.arch[l] / 4, nr = p.arch[l], nc = p.arch[l + 1];
+        for (int q = lane; q < n_inh * nc; q += 32) {
+          const int i = nr - 1 - (q % n_inh), jj = q / n_inh;
+          se[p.woff[l] + i + nr * jj] = p.winh;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  return mask;
+}
+
+__device__ __forceinline__ void load_agent(const ActorDev& p, int a, int lane, double& v, double& ho, double& da,
+                                           double* se, double* sde, double* str) {
+  v = lane < p.n ? p.v[(size_t)a * p.n + lane] : 0.0;
+  ho = lane < p.n ? p.ho[(size_t)a * p.n + lane] : 0.0;
+  da = p.da[a];
+  if (lane < p.n_exc) str[lane] = p.trace[(size_t)a * p.n_exc + lane];
+  for (int q = lane; q < p.w_tot; q += 32) {
+    se[q] = p.e[(size_t)a * p.w_tot + q];
+    sde[q] = p.de[(size_t)a * p.w_tot + q];
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void store_agent(const ActorDev& p, int a, int lane, double v, double ho, double da,
+                                            const double* se, const double* sde, const double* str) {
+  __syncwarp();
+  if (lane < p.n) { p.v[(size_t)a * p.n + lane] = v; p.ho[(size_t)a * p.n + lane] = ho; }
+  if (lane == 0) p.da[a] = da;
+  if (lane < p.n_exc) p.trace[(size_t)a * p.n_exc + lane] = str[lane];
+  for (int q = lane; q < p.w_tot; q += 32) {
+    p.e[(size_t)a * p.w_tot + q] = se[q];
+    p.de[(size_t)a * p.w_tot + q] = sde[q];
+  }
+}
+
+// n_steps calls of step_LIF! with a constant input (cartpole_fitness.jl:70-79): optional v .= c
+// first, last-layer spike counts accumulated from step index >= L-1 (1-based msec >= L-1).
+__global__ void __launch_bounds__(128)
+actor_window_kernel(ActorDev p, const double* __restrict__ intensity, int n_steps, int train, int critic,
+                    int reset_v, int32_t* __restrict__ counts, int32_t* __restrict__ spikes, int64_t spikes_stride) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int a = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (a >= p.n_agents) return;
+  double* se = smem + (size_t)wib * (2 * p.w_tot + 32);
+  double* sde = se + p.w_tot;
+  double* str = sde + p.w_tot;
+  double v, ho, da;
+  load_agent(p, a, lane, v, ho, da, se, sde, str);
+  const Lane li = lane_info(p, lane);
+  const double inten = (li.layer == 0 && lane < p.n) ? intensity[(size_t)a * p.arch[0] + li.local] : 0.0;
+  if (reset_v && lane < p.n) v = p.c;  // net.v .= c  cartpole_fitness.jl:71
+  int cnt = 0;
+  for (int msec = 1; msec <= n_steps; ++msec) {
+    const unsigned m = lif_step(p, li, lane, inten, v, ho, da, se, sde, str, train, critic);
+    if (msec >= p.L - 1 && li.layer == p.L - 1 && ((m >> lane) & 1u)) ++cnt;
+    if (spikes && lane == 0) spikes[(size_t)a * spikes_stride + (msec - 1)] = (int32_t)m;
+  }
+  if (counts && li.layer == p.L - 1 && lane < p.n) counts[(size_t)a * p.arch[p.L - 1] + li.local] = cnt;
+  store_agent(p, a, lane, v, ho, da, se, sde, str);
+}
+
+// sin/cos restated with the fdlibm kernel polynomials (|x| <= pi/4 — the pole angle never leaves
+// +-0.21 rad before termination), in plain IEEE operations so that host oracle and device agree
+// bit for bit (libm results may differ in the last ulp between glibc and CUDA).
+__device__ __forceinline__ double k_sin(double x) {
+  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+               S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+  const double z = DMUL(x, x), vv = DMUL(z, x);
+  const double r = DADD(S2, DMUL(z, DADD(S3, DMUL(z, DADD(S4, DMUL(z, DADD(S5, DMUL(z, S6))))))));
+  return DADD(x, DMUL(vv, DADD(S1, DMUL(z, r))));
+}
+__device__ __forceinline__ double k_cos(double x) {
+  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+               C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+  const double z = DMUL(x, x);
+  const double r = DMUL(z, DADD(C1, DMUL(z, DADD(C2, DMUL(z, DADD(C3, DMUL(z, DADD(C4, DMUL(z, DADD(C5, DMUL(z, C6)))))))))));
+  return DADD(DSUB(1.0, DMUL(0.5, z)), DMUL(z, r));
+}
+
+// CartPole-v1 step, restated (gym classic_control/cartpole.py, Euler integrator)
+__device__ __forceinline__ int cartpole_step(double s[4], int action) {
+  const double gravity = 9.8, masscart = 1.0, masspole = 0.1, length = 0.5, force_mag = 10.0, tau = 0.02;
+  const double total_mass = DADD(masspole, masscart), polemass_length = DMUL(masspole, length);
+  double x = s[0], x_dot = s[1], theta = s[2], theta_dot = s[3];
+  const double force = action == 1 ? force_mag : -force_mag;
+  const double costheta = k_cos(theta), sintheta = k_sin(theta);
+  const double temp = __ddiv_rn(DADD(force, DMUL(DMUL(polemass_length, DMUL(theta_dot, theta_dot)), sintheta)), total_mass);
+  const double thetaacc = __ddiv_rn(
+      DSUB(DMUL(gravity, sintheta), DMUL(costheta, temp)),
+      DMUL(length, DSUB(__ddiv_rn(4.0, 3.0), __ddiv_rn(DMUL(masspole, DMUL(costheta, costheta)), total_mass))));
+  const double xacc = DSUB(temp, __ddiv_rn(DMUL(DMUL(polemass_length, thetaacc), costheta), total_mass));
+  x = DADD(x, DMUL(tau, x_dot)); x_dot = DADD(x_dot, DMUL(tau, xacc));
+  theta = DADD(theta, DMUL(tau, theta_dot)); theta_dot = DADD(theta_dot, DMUL(tau, thetaacc));
+  s[0] = x; s[1] = x_dot; s[2] = theta; s[3] = theta_dot;
+  const double th = __ddiv_rn(DMUL(DMUL(12.0, 2.0), 3.14159265358979323846), 360.0);
+  return x < -2.4 || x > 2.4 || theta < -th || theta > th;
+}
+
+// play_episode (cartpole_fitness.jl:51-114) for every agent; optional teacher-style dopamine
+// (CartPole/Teacher/teacher_sim.jl:61-80,132-133: da += (action==draw ? 1 : -200) * da_inc).
+__global__ void __launch_bounds__(128)
+actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const double* __restrict__ state0,
+                     const int32_t* __restrict__ tie_actions, const int32_t* __restrict__ teach_actions,
+                     int n_decisions_max, int win_size, int train, double* __restrict__ rewards,
+                     int32_t* __restrict__ n_dec, int32_t* __restrict__ n_rand_out, double* __restrict__ state_out) {
+  extern __shared__ double smem[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int a = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (a >= p.n_agents) return;
+  double* se = smem + (size_t)wib * (2 * p.w_tot + 32);
+  double* sde = se + p.w_tot;
+  double* str = sde + p.w_tot;
+  double v, ho, da;
+  load_agent(p, a, lane, v, ho, da, se, sde, str);
+  const Lane li = lane_info(p, lane);
+  const int A0 = p.arch[0], Lout = p.arch[p.L - 1], n_left = Lout / 2;
+  double st[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) st[c] = state0[(size_t)a * 4 + c];
+  double ma[4] = {0, 0, 0, 0};  // row `local` of matalpha (arch[0] x 4, column-major)
+  if (li.layer == 0 && lane < p.n)
+    for (int c = 0; c < 4; ++c) ma[c] = matalpha[(size_t)a * A0 * 4 + li.local + A0 * c];
+  double tot_reward = 0.0;
+  int n_rand = 0, n_tot = 0;
+  const double pi = 3.14159265358979323846;
+  for (int jdec = 0; jdec < n_decisions_max; ++jdec) {
+    // norm_cartpole :14-24
+    double r = fmod(DADD(st[2], pi), DMUL(2.0, pi));
+    if (r == 0) r = copysign(r, DMUL(2.0, pi)); else if (r < 0) r = DADD(r, DMUL(2.0, pi));
+    const double theta = DSUB(r, pi);
+    const double cone = __ddiv_rn(DMUL(12.0, pi), 180.0);
+    double on[4];
+    on[0] = __ddiv_rn(DADD(st[0], 2.4), 4.8);
+    on[1] = __ddiv_rn(DADD(st[1], 7.5), 15.0);
+    on[2] = __ddiv_rn(DADD(theta, cone), DMUL(2.0, cone));
+    on[3] = __ddiv_rn(DADD(st[3], 7.5), 15.0);
+    double inten = 0.0;  // matalpha*norm_cartpole(obs) :67
+#pragma unroll
+    for (int c = 0; c < 4; ++c) inten = DADD(inten, DMUL(ma[c], on[c]));
+    if (lane < p.n) v = p.c;  // :71
+    int cnt = 0;
+    for (int msec = 1; msec <= win_size; ++msec) {
+      const unsigned m = lif_step(p, li, lane, inten, v, ho, da, se, sde, str, train, 0);
+      if (msec >= p.L - 1 && li.layer == p.L - 1 && ((m >> lane) & 1u)) ++cnt;
+    }
+    // left_right :36-41 — counts are small integers: any summation order is exact
+    const bool outl = li.layer == p.L - 1 && lane < p.n;
+    int sl = (outl && li.local < n_left) ? cnt : 0, sr = (outl && li.local >= n_left) ? cnt : 0;
+    for (int o = 16; o > 0; o >>= 1) { sl += __shfl_xor_sync(FULL, sl, o); sr += __shfl_xor_sync(FULL, sr, o); }
+    int action = (sl >= sr) ? 0 : 1;
+    if (sl == sr) {  // :87-95
+      action = tie_actions[(size_t)a * n_decisions_max + n_rand];
+      tot_reward = DSUB(tot_reward, 0.9);
+      ++n_rand;
+    }
+    ++n_tot;
+    if (train && teach_actions) {  // teacher_sim.jl:92-99,132-133
+      const double inc = (action == teach_actions[(size_t)a * n_decisions_max + jdec]) ? 1.0 : -200.0;
+      da = DADD(da, DMUL(inc, p.da_inc));
+    }
+    const int done = cartpole_step(st, action);
+    tot_reward = DADD(tot_reward, 1.0);
+    if (done) break;
+  }
+  if (lane == 0) {
+    rewards[a] = tot_reward;
+    if (n_dec) n_dec[a] = n_tot;
+    if (n_rand_out) n_rand_out[a] = n_rand;
+    if (state_out) for (int c = 0; c < 4; ++c) state_out[(size_t)a * 4 + c] = st[c];
+  }
+  store_agent(p, a, lane, v, ho, da, se, sde, str);
+}
+
+__global__ void fill_d(double* a, int64_t n, double x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = x;
+}
+
+}  // namespace
+
+struct Actor::Impl {
+  ActorDev d;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+#define ACT_OK(expr)                                                       \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    if (_e != cudaSuccess) {                                               \
+      err = std::string(#expr) + ": " + cudaGetErrorString(_e);            \
+      return SNN_ERR_CUDA;                                                 \
+    }                                                                      \
+  } while (0)
+
+Actor::Actor() : impl_(new Impl) { memset(&impl_->d, 0, sizeof(impl_->d)); }
+Actor::~Actor() {
+  ActorDev& d = impl_->d;
+  cudaSetDevice(impl_->device);
+  cudaFree(d.v); cudaFree(d.ho); cudaFree(d.trace); cudaFree(d.e); cudaFree(d.de); cudaFree(d.da);
+  if (impl_->e0) cudaEventDestroy(impl_->e0);
+  if (impl_->e1) cudaEventDestroy(impl_->e1);
+  if (impl_->stream) cudaStreamDestroy(impl_->stream);
+  delete impl_;
+}
+
+int Actor::init(const snn_actor_config& c, std::string& err) {
+  ActorDev& d = impl_->d;
+  impl_->device = c.device;
+  cfg_ = c;
+  d.n_agents = c.n_agents; d.L = c.n_layers;
+  int acc = 0;
+  for (int l = 0; l < d.L; ++l) { d.arch[l] = c.arch[l]; d.off[l] = acc; acc += c.arch[l]; }
+  d.off[d.L] = acc; d.n_exc = acc;
+  int iacc = acc, wacc = 0;
+  for (int l = 0; l < d.L; ++l) {
+    if (l > 0 && l < d.L - 1) { d.ioff[l] = iacc; iacc += c.arch[l]; } else d.ioff[l] = -1;  // Ind :58-65
+    if (l < d.L - 1) { d.woff[l] = wacc; wacc += c.arch[l] * c.arch[l + 1]; }
+  }
+  d.n = iacc; d.n_inh = iacc - acc; d.w_tot = wacc;
+  if (d.n > 32) { err = "actor kernel maps one neuron per lane: n_exc + n_inh must be <= 32 (use the sparse engine for larger nets)"; return SNN_ERR_INVALID; }
+  for (int l = 0; l < d.L; ++l) if (c.arch[l] < 1 || c.arch[l] > 31) { err = "layer sizes must be in 1..31"; return SNN_ERR_INVALID; }
+  d.vthresh = c.vthresh; d.c = c.c; d.wei = c.wei; d.wie = c.wie; d.wmax = c.wmax; d.theta = c.theta; d.ttheta = c.ttheta;
+  d.imin = c.imin; d.apost = c.apost; d.apre = c.apre; d.tde = c.tde; d.ttrace = c.ttrace; d.taulif = c.taulif;
+  d.eta = c.eta; d.winh = c.winh; d.da_inc = c.da_inc;
+  ACT_OK(cudaSetDevice(c.device));
+  ACT_OK(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking));
+  ACT_OK(cudaEventCreate(&impl_->e0));
+  ACT_OK(cudaEventCreate(&impl_->e1));
+  const size_t A = (size_t)d.n_agents;
+  ACT_OK(cudaMalloc(&d.v, A * d.n * sizeof(double)));
+  ACT_OK(cudaMalloc(&d.ho, A * d.n * sizeof(double)));
+  ACT_OK(cudaMalloc(&d.trace, A * d.n_exc * sizeof(double)));
+  ACT_OK(cudaMalloc(&d.e, A * d.w_tot * sizeof(double)));
+  ACT_OK(cudaMalloc(&d.de, A * d.w_tot * sizeof(double)));
+  ACT_OK(cudaMalloc(&d.da, A * sizeof(double)));
+  fill_d<<<256, 256, 0, impl_->stream>>>(d.v, (int64_t)(A * d.n), c.c);  // v = c*ones :105
+  ACT_OK(cudaMemsetAsync(d.ho, 0, A * d.n * sizeof(double), impl_->stream));
+  ACT_OK(cudaMemsetAsync(d.trace, 0, A * d.n_exc * sizeof(double), impl_->stream));
+  ACT_OK(cudaMemsetAsync(d.e, 0, A * d.w_tot * sizeof(double), impl_->stream));
+  ACT_OK(cudaMemsetAsync(d.de, 0, A * d.w_tot * sizeof(double), impl_->stream));
+  ACT_OK(cudaMemsetAsync(d.da, 0, A * sizeof(double), impl_->stream));
+  ACT_OK(cudaStreamSynchronize(impl_->stream));
+  return SNN_OK;
+}
+
+int Actor::field_ptr(int field, int layer, double** ptr, int64_t* per_agent, int64_t* stride, std::string& err) {
+  ActorDev& d = impl_->d;
+  switch (field) {
+    case SNN_FIELD_V: *ptr = d.v; *per_agent = d.n; *stride = d.n; return SNN_OK;
+    case SNN_FIELD_HO: *ptr = d.ho; *per_agent = d.n; *stride = d.n; return SNN_OK;
+    case SNN_FIELD_TRACE: *ptr = d.trace; *per_agent = d.n_exc; *stride = d.n_exc; return SNN_OK;
+    case SNN_FIELD_DA: *ptr = d.da; *per_agent = 1; *stride = 1; return SNN_OK;
+    case SNN_FIELD_W: case SNN_FIELD_SD:
+      if (layer < 0 || layer >= d.L - 1) { err = "layer out of range"; return SNN_ERR_INVALID; }
+      *ptr = (field == SNN_FIELD_W ? d.e : d.de) + d.woff[layer];
+      *per_agent = (int64_t)d.arch[layer] * d.arch[layer + 1]; *stride = d.w_tot; return SNN_OK;
+    default: err = "unknown actor field"; return SNN_ERR_INVALID;
+  }
+}
+
+int Actor::get_array(int field, int layer, double* host, int64_t count, std::string& err) {
+  double* p; int64_t per, stride;
+  int rc = field_ptr(field, layer, &p, &per, &stride, err);
+  if (rc) return rc;
+  if (count != per * impl_->d.n_agents) { err = "count mismatch"; return SNN_ERR_INVALID; }
+  ACT_OK(cudaSetDevice(impl_->device));
+  ACT_OK(cudaMemcpy2DAsync(host, per * sizeof(double), p, stride * sizeof(double), per * sizeof(double),
+                           impl_->d.n_agents, cudaMemcpyDeviceToHost, impl_->stream));
+  ACT_OK(cudaStreamSynchronize(impl_->stream));
+  return SNN_OK;
+}
+int Actor::set_array(int field, int layer, const double* host, int64_t count, std::string& err) {
+  double* p; int64_t per, stride;
+  int rc = field_ptr(field, layer, &p, &per, &stride, err);
+  if (rc) return rc;
+  if (count != per * impl_->d.n_agents) { err = "count mismatch"; return SNN_ERR_INVALID; }
+  ACT_OK(cudaSetDevice(impl_->device));
+  ACT_OK(cudaMemcpy2DAsync(p, stride * sizeof(double), host, per * sizeof(double), per * sizeof(double),
+                           impl_->d.n_agents, cudaMemcpyHostToDevice, impl_->stream));
+  ACT_OK(cudaStreamSynchronize(impl_->stream));
+  return SNN_OK;
+}
+
+static inline size_t actor_smem(const ActorDev& d, int warps) { return (size_t)warps * (2 * d.w_tot + 32) * sizeof(double); }
+
+int Actor::window(int n_steps, const double* intensity, int train, int critic, int reset_v, int32_t* counts,
+                  int32_t* spike_masks, double* device_ms, std::string& err) {
+  ActorDev& d = impl_->d;
+  if (n_steps <= 0 || !intensity) { err = "n_steps must be > 0 and intensity non-null"; return SNN_ERR_INVALID; }
+  ACT_OK(cudaSetDevice(impl_->device));
+  const size_t A = (size_t)d.n_agents;
+  double* d_int = nullptr; int32_t *d_cnt = nullptr, *d_spk = nullptr;
+  const int Lout = d.arch[d.L - 1];
+  cudaError_t e = cudaMalloc(&d_int, A * d.arch[0] * sizeof(double));
+  if (e == cudaSuccess && counts) e = cudaMalloc(&d_cnt, A * Lout * sizeof(int32_t));
+  if (e == cudaSuccess && spike_masks) e = cudaMalloc(&d_spk, A * n_steps * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_int, intensity, A * d.arch[0] * sizeof(double), cudaMemcpyHostToDevice, impl_->stream);
+  if (e == cudaSuccess) {
+    const int warps = 4, blocks = (int)((A + warps - 1) / warps);
+    cudaEventRecord(impl_->e0, impl_->stream);
+    actor_window_kernel<<<blocks, warps * 32, actor_smem(d, warps), impl_->stream>>>(d, d_int, n_steps, train, critic, reset_v,
+                                                                                      d_cnt, d_spk, n_steps);
+    cudaEventRecord(impl_->e1, impl_->stream);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts, d_cnt, A * Lout * sizeof(int32_t), cudaMemcpyDeviceToHost, impl_->stream);
+  if (e == cudaSuccess && spike_masks) e = cudaMemcpyAsync(spike_masks, d_spk, A * n_steps * sizeof(int32_t), cudaMemcpyDeviceToHost, impl_->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(impl_->stream);
+  if (e == cudaSuccess && device_ms) { float ms = 0; cudaEventElapsedTime(&ms, impl_->e0, impl_->e1); *device_ms = ms; }
+  cudaFree(d_int); cudaFree(d_cnt); cudaFree(d_spk);
+  if (e != cudaSuccess) { err = std::string("actor window: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
+  return SNN_OK;
+}
+
+int Actor::episodes(const double* matalpha, const double* state0, const int32_t* tie_actions,
+                    const int32_t* teach_actions, int n_decisions_max, int win_size, int train, double* rewards,
+                    int32_t* n_dec, int32_t* n_rand, double* state_out, double* device_ms, std::string& err) {
+  ActorDev& d = impl_->d;
+  if (!matalpha || !state0 || !tie_actions || !rewards || n_decisions_max <= 0 || win_size <= 0) {
+    err = "episodes: null argument / non-positive sizes"; return SNN_ERR_INVALID;
+  }
+  ACT_OK(cudaSetDevice(impl_->device));
+  const size_t A = (size_t)d.n_agents;
+  double *d_ma = nullptr, *d_s0 = nullptr, *d_rw = nullptr, *d_so = nullptr;
+  int32_t *d_tie = nullptr, *d_teach = nullptr, *d_nd = nullptr, *d_nr = nullptr;
+  cudaStream_t s = impl_->stream;
+  cudaError_t e = cudaMalloc(&d_ma, A * d.arch[0] * 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_s0, A * 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_so, A * 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_rw, A * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_tie, A * n_decisions_max * sizeof(int32_t));
+  if (e == cudaSuccess && teach_actions) e = cudaMalloc(&d_teach, A * n_decisions_max * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_nd, A * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_nr, A * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ma, matalpha, A * d.arch[0] * 4 * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_s0, state0, A * 4 * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_tie, tie_actions, A * n_decisions_max * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && teach_actions)
+    e = cudaMemcpyAsync(d_teach, teach_actions, A * n_decisions_max * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    const int warps = 4, blocks = (int)((A + warps - 1) / warps);
+    cudaEventRecord(impl_->e0, s);
+    actor_episode_kernel<<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, d_teach, n_decisions_max,
+                                                                           win_size, train, d_rw, d_nd, d_nr, d_so);
+    cudaEventRecord(impl_->e1, s);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(rewards, d_rw, A * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && n_dec) e = cudaMemcpyAsync(n_dec, d_nd, A * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && n_rand) e = cudaMemcpyAsync(n_rand, d_nr, A * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && state_out) e = cudaMemcpyAsync(state_out, d_so, A * 4 * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess && device_ms) { float ms = 0; cudaEventElapsedTime(&ms, impl_->e0, impl_->e1); *device_ms = ms; }
+  cudaFree(d_ma); cudaFree(d_s0); cudaFree(d_so); cudaFree(d_rw); cudaFree(d_tie); cudaFree(d_teach); cudaFree(d_nd); cudaFree(d_nr);
+  if (e != cudaSuccess) { err = std::string("actor episodes: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
+  return SNN_OK;
+}
+
+}  // namespace snn

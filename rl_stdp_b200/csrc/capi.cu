@@ -6,7 +6,12 @@
 #include <string>
 #include <vector>
 
+#include "actor.h"
 #include "snn_common.h"
+
+struct snn_actor {
+  snn::Actor impl;
+};
 
 struct snn_net {
   snn_config cfg;
@@ -169,6 +174,74 @@ int32_t snn_set_stream(snn_net* net, void* cuda_stream) {
   if (!net) return fail(SNN_ERR_INVALID, "null net");
   net->eng->set_stream((cudaStream_t)cuda_stream);
   return SNN_OK;
+}
+
+int32_t snn_actor_config_default(snn_actor_config* c) {
+  if (!c) return fail(SNN_ERR_INVALID, "null config");
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(snn_actor_config);
+  c->device = 0; c->n_agents = 1; c->n_layers = 3; c->arch[0] = c->arch[1] = c->arch[2] = 8;
+  c->vthresh = 1.0; c->c = 0.0; c->wei = 0.0; c->wie = 0.0; c->wmax = 1.1; c->theta = 0.0; c->ttheta = 0.998;
+  c->imin = 1.0; c->apost = 0.1; c->apre = 0.15; c->tde = 0.99; c->ttrace = 0.9; c->taulif = 5.0;
+  c->eta = 0.001; c->winh = 0.0; c->da_inc = 0.01;
+  return SNN_OK;
+}
+
+int32_t snn_actor_create(const snn_actor_config* cfg, snn_actor** out) {
+  if (!cfg || !out) return fail(SNN_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(snn_actor_config)) return fail(SNN_ERR_INVALID, "snn_actor_config.struct_size mismatch (ABI)");
+  if (cfg->n_agents <= 0) return fail(SNN_ERR_INVALID, "n_agents must be > 0");
+  if (cfg->n_layers < 2 || cfg->n_layers > snn::kActorMaxLayers) return fail(SNN_ERR_INVALID, "n_layers must be in 2..8");
+  if (!(cfg->taulif != 0.0)) return fail(SNN_ERR_INVALID, "taulif must be non-zero");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0)
+    return fail(SNN_ERR_NODEVICE, std::string("no CUDA device (libsnn_b200 has no CPU fallback): ") +
+                                      (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0"));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SNN_ERR_INVALID, "device ordinal out of range");
+  snn_actor* a = new (std::nothrow) snn_actor;
+  if (!a) return fail(SNN_ERR_INVALID, "out of host memory");
+  std::string err;
+  int rc = a->impl.init(*cfg, err);
+  if (rc) { delete a; return fail(rc, err); }
+  *out = a;
+  return SNN_OK;
+}
+
+int32_t snn_actor_destroy(snn_actor* a) { delete a; return SNN_OK; }
+
+int32_t snn_actor_get_array(snn_actor* a, int32_t field, int32_t layer, double* host, int64_t count) {
+  if (!a || !host) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = a->impl.get_array(field, layer, host, count, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_actor_set_array(snn_actor* a, int32_t field, int32_t layer, const double* host, int64_t count) {
+  if (!a || !host) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = a->impl.set_array(field, layer, host, count, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_actor_window(snn_actor* a, int32_t n_steps, const double* intensity, int32_t train, int32_t critic,
+                         int32_t reset_v, int32_t* counts, int32_t* spike_masks, double* device_ms) {
+  if (!a) return fail(SNN_ERR_INVALID, "null actor");
+  std::string err;
+  int rc = a->impl.window(n_steps, intensity, train, critic, reset_v, counts, spike_masks, device_ms, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_actor_episodes(snn_actor* a, const double* matalpha, const double* state0, const int32_t* tie_actions,
+                           const int32_t* teach_actions, int32_t n_decisions_max, int32_t win_size, int32_t train,
+                           double* rewards, int32_t* n_decisions, int32_t* n_rand, double* state_out,
+                           double* device_ms) {
+  if (!a) return fail(SNN_ERR_INVALID, "null actor");
+  std::string err;
+  int rc = a->impl.episodes(matalpha, state0, tie_actions, teach_actions, n_decisions_max, win_size, train, rewards,
+                            n_decisions, n_rand, state_out, device_ms, err);
+  return rc ? fail(rc, err) : SNN_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,118 @@
+"""GPU parity of the batched LIF actor kernels (variant F, configs 2 and 4) against the oracle
+(oracle/lif_oracle.c), through the C ABI.  fp64, bit-exact: spike masks, counts, weights, traces,
+episode returns and final CartPole states."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(n_agents, arch, seed, **param):
+    from oracle import py_oracle as po
+    from rl_stdp_b200.lif import ActorPopulation
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    pop = ActorPopulation(arch, n_agents, **param)
+    oparam = {("de" if k == "de_" else k): v for k, v in param.items() if k != "da_inc"}
+    oras = [po.Layered(arch, "lif", **oparam) for _ in range(n_agents)]
+    # Weights(arch, param) :21 — clamp.(randn .* std .+ m, 0, wmax), recorded
+    wmax = param.get("wmax", 1.1)
+    for l in range(len(arch) - 1):
+        e = np.clip(rng.standard_normal((n_agents, arch[l], arch[l + 1])) * 0.3 + 0.8, 0, wmax)
+        pop.set_weights(l, e)
+        for a, o in enumerate(oras):
+            o.e(l)[:, :] = e[a]
+    return pop, oras, rng
+
+
+@pytest.mark.parametrize("train,critic", [(False, False), (True, False), (True, True)])
+def test_decision_window_bitexact(train, critic):
+    from rl_stdp_b200 import _lib as L
+    arch, A, T = [8, 8, 8], 37, 40
+    param = dict(theta=0.05, wei=0.3, wie=-0.2, apost=0.014, apre=0.019, ttrace=0.95, imin=0.9, eta=0.5, winh=-0.1)
+    pop, oras, rng = _mk(A, arch, 5, **param)
+    idx = np.arange(arch[0], dtype=np.int32)
+    for rep in range(3):  # three consecutive decisions: ho / trace / de / da carry over, v is reset
+        inten = rng.random((A, arch[0])) * 1.2
+        da0 = rng.random(A) * 0.02 - 0.005
+        pop.set(L.FIELD_DA, pop.get(L.FIELD_DA)[:, 0] + da0)
+        counts, masks, _ = pop.decision_window(inten, T, train=train, critic=critic, reset_v=True, spikes=True)
+        for a, o in enumerate(oras):
+            o.da = o.da + da0[a]
+            o.v[:] = o.params["c"]
+            cnt = np.zeros(arch[-1], np.int32)
+            for msec in range(1, T + 1):
+                sp = o.step_lif(idx, inten[a], train, critic)
+                m = 0
+                for j in sp:
+                    m |= 1 << int(j)
+                assert (int(masks[a, msec - 1]) & 0xFFFFFFFF) == m, (rep, a, msec)
+                if msec >= len(arch) - 1:
+                    for j in sp:
+                        if j >= sum(arch[:-1]) and j < sum(arch):
+                            cnt[j - sum(arch[:-1])] += 1
+            assert np.array_equal(counts[a], cnt)
+    v, ho, tr, da = pop.get(L.FIELD_V), pop.get(L.FIELD_HO), pop.get(L.FIELD_TRACE), pop.get(L.FIELD_DA)
+    tot = 0
+    for a, o in enumerate(oras):
+        assert np.array_equal(v[a], o.v) and np.array_equal(ho[a], o.ho) and np.array_equal(tr[a], o.trace_e)
+        assert da[a, 0] == o.da
+        for l in range(len(arch) - 1):
+            assert np.array_equal(pop.weights(l)[a], o.e(l)), (a, l)
+            assert np.array_equal(pop.weights(l, L.FIELD_SD)[a], o.de(l)), (a, l)
+            tot += np.abs(o.de(l)).sum()
+    assert tot > 0
+
+
+def test_episodes_bitexact_and_ragged():
+    """play_episode for 64 agents (different weights, M_alpha, reset states, tie streams): returns,
+    decision counts, tie counts and final env states identical to the oracle; episodes end at
+    different lengths (ragged), some hit the 200-decision cap."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200.lif import borne
+    arch, A, n_steps = [8, 8, 8], 64, 200
+    pop, oras, rng = _mk(A, arch, 9)
+    matalpha = borne(rng.random((A, arch[0], 4)) * 20 - 10, -1.0, 1.0)
+    state0 = rng.random((A, 4)) * 0.1 - 0.05  # env.reset(): U(-0.05, 0.05)^4
+    ties = rng.integers(0, 2, size=(A, n_steps), dtype=np.int32)
+    out = pop.play_episodes(matalpha, state0, ties, n_steps=n_steps)
+    lens = set()
+    for a, o in enumerate(oras):
+        r, nd, nr, so = o.play_episode(matalpha[a], state0[a], ties[a], n_steps, train=False)
+        assert out["rewards"][a] == r, a
+        assert out["n_decisions"][a] == nd and out["n_rand"][a] == nr
+        assert np.array_equal(out["state"][a], so)
+        lens.add(nd)
+    assert len(lens) > 3
+
+
+def test_teacher_style_learning_episode():
+    """train=true episodes with dopamine +-da_inc per decision (teacher_sim.jl:61-80,132-133)."""
+    from rl_stdp_b200 import _lib as L
+    arch, A, n_steps = [8, 8, 8], 16, 60
+    param = dict(apost=0.014, apre=0.019, ttrace=0.95, imin=0.5, da_inc=0.0001)
+    pop, oras, rng = _mk(A, arch, 13, **param)
+    matalpha = rng.random((A, arch[0], 4)) * 2 - 1
+    state0 = rng.random((A, 4)) * 0.1 - 0.05
+    ties = rng.integers(0, 2, size=(A, n_steps), dtype=np.int32)
+    teach = rng.integers(0, 2, size=(A, n_steps), dtype=np.int32)
+    out = pop.play_episodes(matalpha, state0, ties, n_steps=n_steps, train=True, teach_actions=teach)
+    changed = 0
+    for a, o in enumerate(oras):
+        e_before = [o.e(l).copy() for l in range(2)]
+        r, nd, nr, so = o.play_episode(matalpha[a], state0[a], ties[a], n_steps, train=True, teach_actions=teach[a],
+                                       da_inc=param["da_inc"])
+        assert out["rewards"][a] == r and out["n_decisions"][a] == nd
+        for l in range(2):
+            assert np.array_equal(pop.weights(l)[a], o.e(l))
+            changed += int(np.any(o.e(l) != e_before[l]))
+        assert pop.get(L.FIELD_DA)[a, 0] == o.da
+    assert changed > 0
+
+
+def test_actor_config_errors():
+    from rl_stdp_b200 import _lib as L
+    from rl_stdp_b200.lif import ActorPopulation
+    with pytest.raises(L.SnnError):
+        ActorPopulation([16, 16, 16], 4)  # 48 exc + 16 inh > 32 lanes
+    with pytest.raises(L.SnnError):
+        ActorPopulation([8, 8, 8], 0)

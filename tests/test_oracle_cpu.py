@@ -108,3 +108,83 @@ def test_run_helper_da_after_step():
     o = po.Sparse(N, Ne, rowptr, post, w, d, max_delay=2)
     run_oracle_sparse(o, synth.thalamic_noise(3, N, seed=6), [0, 0, 0], [(0, 0, 1.0)])
     assert o.get(6)[0] == 1.0 * 0.995 * 0.995
+
+
+def test_layered_c_equals_numpy_lif_and_izh():
+    """Variants F (LIF) and E (Izhikevich layered): C oracle == numpy restatement, bit for bit."""
+    rng = np.random.Generator(np.random.Philox(key=77))
+    arch = [6, 8, 4]
+    param = dict(po.CARTPOLE_CFGLIF)
+    param.update(theta=0.05, wei=0.3, wie=-0.2, apost=0.014, apre=0.019, ttrace=0.95, imin=0.9, imax=1.5, eta=0.5,
+                 winh=-0.1)
+    e0 = [np.clip(rng.standard_normal((arch[l], arch[l + 1])) * 0.3 + 0.8, 0, 1.1) for l in range(2)]
+    for critic in (False, True):
+        c = po.Layered(arch, "lif", **param)
+        n = nr.NetArch(arch, param, e0)
+        for l in range(2):
+            c.e(l)[:, :] = e0[l]
+        tot = 0
+        for t in range(120):
+            inten = rng.random(arch[0]) * 1.3
+            if t % 7 == 0:
+                c.da = c.da + 0.01; n.da += 0.01
+            a = c.step_lif(np.arange(arch[0]), inten, True, critic)
+            spikes = [(i, inten[i]) for i in range(arch[0])]
+            b = n.step_LIF_critic(spikes, True) if critic else n.step_LIF(spikes, True)
+            assert np.array_equal(a, b), (critic, t)
+            tot += len(a)
+        assert tot > 50
+        assert np.array_equal(c.v, n.v) and np.array_equal(c.ho, n.ho) and np.array_equal(c.trace_e, n.trace_e)
+        for l in range(2):
+            assert np.array_equal(c.e(l), n.e[l]) and np.array_equal(c.de(l), n.de[l])
+        assert c.da == n.da
+    # Izhikevich layered (variant E)
+    pe = dict(param)
+    pe.update(vthresh=30.0, c=-65.0, theta=2.0, ttheta=0.9999, wei=3.0, wie=-2.0, wmax=20.0, imin=0.0, imax=20.0,
+              apost=1.0, apre=1.5, ttrace=0.95, tda=0.995)
+    e0 = [np.clip(rng.standard_normal((arch[l], arch[l + 1])) * 2 + 8, 0, 20.0) for l in range(2)]
+    c = po.Layered(arch, "izh", **pe)
+    n = nr.NetArch(arch, pe, e0)
+    for l in range(2):
+        c.e(l)[:, :] = e0[l]
+    tot = 0
+    for t in range(300):
+        if t % 3 == 0:
+            idx = rng.choice(arch[0], size=2, replace=False)
+            inten = rng.random(2)
+            a = c.step_izh(idx, inten, train=(t % 10 == 9))
+            b = n.step([(int(i), float(x)) for i, x in zip(idx, inten)], train=(t % 10 == 9))
+        elif t % 3 == 1:
+            idx = rng.choice(arch[0], size=1)
+            a = c.step_izh(idx, None, train=False)
+            b = n.step([int(idx[0])], train=False)
+        else:
+            a = c.step_izh(None, None, train=False)
+            b = n.step(None, train=False)
+        if t % 50 == 0:
+            c.da = c.da + 0.1; n.da += 0.1
+        assert np.array_equal(a, b), t
+        tot += len(a)
+    assert tot > 30
+    assert np.array_equal(c.v, n.v) and np.array_equal(c.u, n.u) and np.array_equal(c.ho, n.ho)
+    for l in range(2):
+        assert np.array_equal(c.e(l), n.e[l]) and np.array_equal(c.de(l), n.de[l])
+
+
+def test_cartpole_restated_physics():
+    """The restated CartPole-v1 step: polynomial sin/cos within 1 ulp of libm on the reachable angle
+    range, a falling pole terminates at |theta| > 12 deg, and play_episode caps at n_steps."""
+    import math
+    L = po.lib()
+    for x in np.linspace(-0.78, 0.78, 401):
+        assert abs(L.ora_ksin(float(x)) - math.sin(x)) <= 1.2e-16
+        assert abs(L.ora_kcos(float(x)) - math.cos(x)) <= 1.2e-16
+    s = np.array([0.0, 0.0, 0.02, 0.0])
+    steps, done = 0, False
+    while not done and steps < 500:
+        s, done = po.cartpole_step(s, 1)
+        steps += 1
+    assert done and steps < 200 and (abs(s[2]) > 12 * 2 * math.pi / 360 or abs(s[0]) > 2.4)
+    s2, d2 = po.cartpole_step(np.array([0.0, 0.0, 0.0, 0.0]), 1)
+    # one Euler step from rest with +10 N: xacc = temp - pml*thetaacc/total ; theta_dot < 0
+    assert s2[1] > 0 and s2[3] < 0 and not d2
