@@ -38,6 +38,7 @@ WORKLOADS = {
     "c5_1M_100M": (1_000_000, 800_000, 100, 20),
     "c3_10k_1M": (10_000, 8_000, 100, 1),
     "tiny": (20_000, 16_000, 100, 20),
+    "c4_actors": None,  # 4096 x LIF [8,8,8] CartPole actors, whole episodes on the device (per GPU: 4096/N)
 }
 LEARN_PERIOD = 10
 DA_PERIOD = 1000
@@ -68,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -129,7 +130,7 @@ def run_b200(args):
     t_build = time.perf_counter()
     rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9 + rank)
     net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f32", mode="fast", noise="philox", device=local,
-                        max_delay=dmax, noise_seed=10 + rank)
+                        max_delay=dmax, noise_seed=10 + rank, exp_flags=args.exp_flags, graph=not args.no_graph)
     n_plastic = int(rowptr[ne])
     del post, w, delay
     t_build = time.perf_counter() - t_build
@@ -148,7 +149,7 @@ def run_b200(args):
     kw = 0
     for _ in range(args.warmup):
         tr, da = window_inputs(kw, W)
-        net.run(W, None, tr, da_events=da, record=False)
+        net.run(W, None, tr, da_events=da, record=False, profile='learn')  # same graph as the timed region
         kw += 1
 
     # ---- timed region 1: inputs resident, no spike record -> `value`
@@ -253,6 +254,77 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_actors(args):
+    """Config 4: 4096 independent CartPole LIF actors (cartpole_fitness.jl play_episode), sharded by
+    instance over the ranks; a bench step = one full episode of every agent (<= 200 decisions x 40 ms)."""
+    import torch
+    import torch.distributed as dist
+    from rl_stdp_b200.lif import ActorPopulation, borne
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    arch, total = [8, 8, 8], 4096
+    A = total // world
+    rng = np.random.Generator(np.random.Philox(key=4 + rank))
+    pop = ActorPopulation(arch, A, device=local)
+    for l in range(2):
+        pop.set_weights(l, np.clip(rng.standard_normal((A, 8, 8)) * 0.3 + 0.8, 0, 1.1))
+    matalpha = borne(rng.random((A, 8, 4)) * 20 - 10, -1.0, 1.0)
+
+    def episode():
+        s0 = rng.random((A, 4)) * 0.1 - 0.05
+        ties = rng.integers(0, 2, size=(A, 200), dtype=np.int32)
+        return pop.play_episodes(matalpha, s0, ties, n_steps=200), s0.nbytes + ties.nbytes + matalpha.nbytes
+
+    for _ in range(args.warmup):
+        episode()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0; sim_ms = 0; h2d = 0
+    for _ in range(args.steps):
+        out, nb = episode()
+        dev_ms += out["device_ms"]; sim_ms += int(out["n_decisions"].sum()) * 40; h2d += nb
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    vals = torch.tensor([dev_ms, wall * 1e3, float(sim_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, wall_ms, sim_all = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        wall_ms, sim_all = wall * 1e3, float(sim_ms)
+    if rank == 0:
+        line = {"metric": "simulated agent-ms per wall-s", "value": sim_all / (dev_ms * 1e-3), "unit": "agent-ms/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "c4_actors", "agents": total, "arch": arch, "window_ms": 40, "max_decisions": 200,
+                           "env": "CartPole-v1 restated, on device"},
+                "e2e": {"value": sim_all / (wall_ms * 1e-3), "unit": "agent-ms/s", "h2d_bytes_per_step": h2d // args.steps,
+                        "d2h_bytes_per_step": A * (8 + 4 + 4 + 32)},
+                "gpu_launches": args.steps}
+        if world == 1 and not args.no_cpu:
+            from oracle import py_oracle as po
+            o = po.Layered(arch, "lif")
+            for l in range(2):
+                o.e(l)[:, :] = np.clip(rng.standard_normal((8, 8)) * 0.3 + 0.8, 0, 1.1)
+            t1 = time.perf_counter(); ms = 0
+            while time.perf_counter() - t1 < min(args.cpu_seconds, 5.0):
+                _, nd, _, _ = o.play_episode(matalpha[0], rng.random(4) * 0.1 - 0.05, rng.integers(0, 2, 200), 200)
+                ms += nd * 40
+            dt = time.perf_counter() - t1
+            line["cpu_baseline"] = {"value": ms / dt, "unit": "agent-ms/s", "cores": 1, "kind": "port",
+                                    "sample": f"one agent, sequential episodes for {dt:.1f} s (oracle/lif_oracle.c)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(budget_s: float = 12.0, n=50_000, ne=40_000, fan=100, dmax=20):
     """The oracle port (oracle/snn_oracle.c sparse restatement, fp64, 1 thread — the reference is
     single-threaded Julia) on a 1/20-scale sample of the same workload.  Its cost is per synapse
@@ -286,7 +358,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n, ne, fan, dmax = WORKLOADS[args.workload]
+    n, ne, fan, dmax = WORKLOADS[args.workload if args.workload != "c4_actors" else "c5_1M_100M"]
     from oracle import py_oracle as po
     from rl_stdp_b200 import synth
     ns = min(n, 50_000)
@@ -330,7 +402,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5_1M_100M", choices=sorted(WORKLOADS))
@@ -338,9 +410,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-ms-per-step", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exp-flags", type=int, default=0, help="kernel experiments (wrong numerics), never for reported numbers")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4_actors":
+        run_actors(args)
     else:
         run_b200(args)
 

@@ -12,8 +12,8 @@
 //   I = noise                          :111       neuron_kernel(t):  Euler(t-1) then detect(t):
 //   spiked = v > 30 ; v=-65 ; u+=d     :112-114     threshold/reset, trace set/decay, bitmap,
 //   for n in spiked: I += s[n,:]       :116-118     spike list, dopamine decay
-//   v,v,u Euler                        :120-122   arrival_kernel(t): I += w and LTD for every spike
-//   STDP[spiked]=0.1                   :123         arriving now (delay ring of spike lists)
+//   v,v,u Euler                        :120-122   synapse_kernel(t): LTD for every spike arriving now
+//   STDP[spiked]=0.1                   :123         + I += w for the arrivals of t+1 (delay ring of lists)
 //   sd[:,n]+=STDP ; sd[n,:]-=1.5STDP   :125-128   ltp_kernel(t): LTP over the incoming index
 //   STDP*=0.95 ; da*=0.995             :130-131   [exact mode: gather_kernel(t) pulls I in
 //   learn! (if train)                  :135-142     ascending presynaptic order]
@@ -23,13 +23,20 @@
 // over the neuron arrays (36 B/neuron fp32).  Trace values do not enter the Euler update, so the
 // result is identical to the reference order.
 //
-// Scheduling: a whole window of steps is captured once as a CUDA graph (two captured streams):
-//   s1: neuron(k) -> arrival(k) -> neuron(k+1) -> ...
-//   s2:    \-> ltp(k) -------\-> learn(k) --------/ (joined before arrival(k+1))
-// so ltp(k) runs beside arrival(k) (disjoint synapse ownership) and the bandwidth-bound learn(k)
-// runs beside the latency-bound neuron(k+1).  All step-dependent values (absolute step, ring
-// slot, input pointers) come from a device-side WindowCtx, so one instantiated graph serves every
-// window with the same length and train-flag pattern.
+// Scheduling (production mode): only neuron(k) -> neuron(k+1) is a true serial chain.  The
+// currents consumed by Euler(k) are pushed ahead of time into a parity-double-buffered Iacc:
+//   - delay-1 synapses of step-k spikers: inside neuron_kernel(k), right after detection;
+//   - every other arrival of step k+1 (spikes of steps <= k): by synapse_kernel(k), which walks
+//     the delay-(a+1) segment for LTD (arrival now) and the adjacent delay-(a+2) segment for the
+//     push (arrival at k+1) in one pass.
+// sd updates (LTD in synapse_kernel, LTP in ltp_kernel) never feed the neuron update, so they run
+// on side streams.  A window is captured once as a CUDA graph over three streams:
+//   s1: neuron(0) -> neuron(1) -> neuron(2) ...           (waits synapse(k-2), learn(k-1))
+//   s2: synapse(k) after neuron(k), ltp(k-1)              [learn steps: LTD | learn | push]
+//   s3: ltp(k) after neuron(k), synapse(k-1) ; learn(k) after synapse(k)
+// All step-dependent values (absolute step, ring slot, input pointers) come from a device-side
+// WindowCtx, so one instantiated graph serves every window with the same length and train-flag
+// pattern.  Exact mode, forced spikes and per-kernel profiling use plain stream-ordered launches.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -90,9 +97,10 @@ template <typename T>
 struct DevNet {
   typedef typename Real2<T>::type T2;
   int64_t N, Nld, Nper, Ne, E;  // Nld = N rounded up to 128: leading dimension of ring slots
-  int32_t Dmax, R, B, W;        // R = Dmax+1 ring slots ; W = bitmap words per slot
+  int32_t Dmax, R, B, W;        // R = Dmax+2 ring slots ; W = bitmap words per slot
   // neuron state
-  T *v, *u, *ho, *Iacc;
+  T *v, *u, *ho;
+  T* Iacc;           // [2][Nld]  Iacc[t&1] = currents consumed by the Euler update of step t
   T* trace;          // [R][Nld]  trace after the set of that step (pre-decay)
   uint32_t* bits;    // [R][W]    spike bitmap per step
   int32_t* spk_list; // [R][Nld]  spike list per step (unordered)
@@ -105,7 +113,7 @@ struct DevNet {
   const uint32_t *colptr, *col_npl, *in_syn, *in_pre;
   // counters[0] = spikes, [1] = synaptic events (exact mode); per-block partial sums otherwise
   unsigned long long* counters;
-  unsigned long long* blk_ev;   // [kMaxSynBlocks] synaptic events (arrival_kernel)
+  unsigned long long* blk_ev;   // [kMaxSynBlocks] synaptic events (synapse_kernel)
   unsigned long long* blk_ltp;  // [kMaxSynBlocks] LTP visits (ltp_kernel)
   // parameters
   T vthresh, v_reset, a_exc, a_inh, d_exc, d_inh, trace_set, trace_decay, apost, apre, da_decay,
@@ -113,6 +121,7 @@ struct DevNet {
   double noise_amp; uint64_t noise_seed;
   int64_t ho_from;
   int32_t threshold_ge, sd_decay_mode, rate_mode, plastic_ei, noise_mode, exact, homeostasis;
+  int32_t exp_flags;  // experiments only (snn_config.reserved[1]); 0 in production
 };
 
 // Per-window inputs/outputs.  Lives in device memory so that a captured graph never has to be
@@ -167,14 +176,30 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
   const T* __restrict__ trp = p.trace + (size_t)prev * p.Nld;
   uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
   int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.Nld;
-  int32_t* __restrict__ rec_ids = DETECT ? cx->rec_ids : nullptr;
-  const int32_t rec_base = rec_ids ? cx->rec_off[k] : 0;
+  int32_t* __restrict__ rec_ids = cx->rec_ids;
   const int64_t rec_cap = cx->rec_cap;
+  // spike-record offset of this step = offset of the previous step + its (final) spike count
+  int32_t rec_base = 0;
+  const int n_prev = (k > 0 && (rec_ids || blockIdx.x == 0)) ? p.spk_cnt[prev] : 0;
+  if (rec_ids && k > 0) {
+    int64_t nxt = (int64_t)cx->rec_off[k - 1] + n_prev;
+    rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
+  }
+  T* __restrict__ I_prev = p.Iacc + (size_t)((t - 1) & 1) * p.Nld;  // consumed by Euler(t-1)
+  T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;         // receives the pushes of step t
   const T* __restrict__ noise_prev = (EULER && cx->noise) ? cx->noise + (size_t)(k - 1) * p.N : nullptr;
   const uint32_t N = (uint32_t)p.N, Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
 
   // dopamine (new_net.jl:131 da *= 0.995 ; newnet_DASTDP.jl:54-56 da += 0.5 after step!)
   if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      if (EULER && k > 0) {  // exactly one EULER launch per step k >= 1 (and the window-end launch)
+        p.counters[0] += (unsigned long long)n_prev;
+        if (rec_ids) cx->rec_off[k] = rec_base;
+      }
+      // next step's list; R = Dmax+2 so no kernel still in flight reads that slot
+      if (DETECT) p.spk_cnt[wrap_slot(slot + 1, p.R)] = 0;
+    }
     const T* __restrict__ din = p.da + (size_t)(t & 1) * p.B;
     T* __restrict__ dout = p.da + (size_t)((t + 1) & 1) * p.B;
     const bool evs = apply_ev && cx->ev_off && k > 0;
@@ -193,7 +218,7 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
     const uint32_t j0 = q << 2;
     // ---- all loads first
     Vec4<T> v = ld4(p.v + j0), u = ld4(p.u + j0), I, tp, ho;
-    if (EULER) I = ld4(p.Iacc + j0);
+    if (EULER) I = ld4(I_prev + j0);
     if (DETECT) {
       tp = ld4(trp + j0);
       if (p.homeostasis) ho = ld4(p.ho + j0);
@@ -221,7 +246,7 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
           for (int c = 0; c < 4; ++c) I.x[c] = O::add((T)philox_to_noise(w[c], p.noise_amp), I.x[c]);
         }
         Vec4<T> z; z.x[0] = z.x[1] = z.x[2] = z.x[3] = (T)0;
-        st4(p.Iacc + j0, z);
+        st4(I_prev + j0, z);
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -285,6 +310,29 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
               list[pos] = (int32_t)(j0 + c);
               if (rec_ids && (int64_t)rec_base + pos < rec_cap) rec_ids[rec_base + pos] = (int32_t)(j0 + c);
             }
+            if (!p.exact && !(p.exp_flags & 1)) {
+              // delay-1 synapses of this step's spikers feed the Euler update of this very step
+              // (new_net.jl:116-121): push them now, warp-cooperatively, into Iacc[t&1]
+              unsigned mm = m;
+              while (mm) {
+                const int src = __ffs(mm) - 1; mm &= mm - 1;
+                const uint32_t i = __shfl_sync(0xffffffffu, j0, src) + c;
+                const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1)], s1 = p.seg[(size_t)i * (p.Dmax + 1) + 1];
+                // four loads in flight per lane before the first reduction (an inhibitory row has
+                // ~100 delay-1 synapses; one round trip instead of four)
+                for (uint32_t e0 = s0 + lane; e0 < s1; e0 += 128) {
+                  int32_t pj[4]; T pw[4];
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint32_t e = e0 + 32 * q4;
+                    pj[q4] = e < s1 ? p.post[e] : -1;
+                    pw[q4] = e < s1 ? p.wsd[e].x : (T)0;
+                  }
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) if (pj[q4] >= 0) atomicAdd(&I_now[pj[q4]], pw[q4]);
+                }
+              }
+            }
           }
         }
       }
@@ -312,7 +360,6 @@ gather_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
   const int64_t t = cx->t0 + k;
   const int slot = (cx->slot0 + k) % p.R;
   const T* __restrict__ noise = cx->noise ? cx->noise + (size_t)k * p.N : nullptr;
-  unsigned long long ev = 0;
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.N;
        j += (int64_t)gridDim.x * blockDim.x) {
     T acc = (T)0;
@@ -324,30 +371,36 @@ gather_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
       const uint32_t i = pk & kPreMask;
       const int sl = wrap_slot(slot - (int)(pk >> kPreBits), p.R);
       const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
-      if ((word >> (i & 31)) & 1u) { acc = O::add(acc, p.wsd[p.in_syn[q]].x); ++ev; }
+      if ((word >> (i & 31)) & 1u) acc = O::add(acc, p.wsd[p.in_syn[q]].x);
     }
-    p.Iacc[j] = acc;
+    p.Iacc[(size_t)(t & 1) * p.Nld + j] = acc;
   }
-  if (ev) atomicAdd(&p.counters[1], ev);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2 arrival_kernel(t): persistent grid, sub-warp groups of G lanes per work item.  For every age
-// a=0..Dmax-1 and every neuron i that spiked at t-a, walk the delay-(a+1) segment of row i:
-// I[post] += w (PUSH), and for plastic rows LTD with the post trace of this call
-// (new_net.jl:127 `sd[n,:] .-= 1.5 .* STDP`).  If the target also spiked at t the same thread
-// applies its LTP too, in the reference's loop order (post<=pre: + then -, else - then +;
-// new_net.jl:125-128).  ltp_kernel skips those synapses, so every synapse is written by exactly
-// one thread per call: no atomics on sd, bit-reproducible, and the two kernels may overlap.
+// K2 synapse_kernel(k): persistent grid, sub-warp groups of G lanes per work item.  A work item is
+// (age a, neuron i that spiked at step k-a), a = 0..Dmax-1; its CSR row is sorted by delay, so the
+// delay-(a+1) segment (arriving NOW) and the delay-(a+2) segment (arriving at k+1) are adjacent:
+//   LTD      on the first: sd -= apre*trace_post(k) (new_net.jl:127 `sd[n,:] .-= 1.5 .* STDP`); if
+//            the target also spiked at k the same thread applies its LTP too, in the reference's
+//            loop order (post<=pre: + then -, else - then +; new_net.jl:125-128).  ltp_kernel skips
+//            those synapses, so every synapse is written by exactly one thread per step: no
+//            atomics on sd, bit-reproducible (exact mode).  Production mode (ATOMIC) uses
+//            red.global.add on sd instead: no load of sd, no ordering between the LTD and LTP
+//            kernels of neighbouring steps, so they pipeline freely on their side streams.
+//   PUSHNEXT on the second: Iacc[(k+1)&1][post] += w — the currents of step k+1 are complete one
+//            step early, which takes propagation off the neuron(k)->neuron(k+1) critical path.
+// (delay-1 pushes of step-k spikers happen inside neuron_kernel(k).)
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool PUSH>
+template <typename T, bool LTD, bool PUSHNEXT, bool ATOMIC>
 __global__ void __launch_bounds__(256)
-arrival_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
+synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
   typedef Ops<T> O;
   __shared__ int cum[kMaxDelay + 2];
   __shared__ int slots[kMaxDelay + 1];
   __shared__ unsigned long long blk_ev;
-  const int slot = (cx->slot0 + k) % p.R;
+  const int64_t t = cx->t0 + k;
+  const int slot = (int)(((int64_t)cx->slot0 + k + p.R) % p.R);  // k may be -1 (window-start push)
   // prologue: the Dmax list lengths are loaded in parallel (one round trip), scanned in smem
   if (threadIdx.x < (unsigned)p.Dmax) {
     const int sl = wrap_slot(slot - (int)threadIdx.x, p.R);
@@ -357,71 +410,70 @@ arrival_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
   if (threadIdx.x == 0) blk_ev = 0ull;
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int c0 = cum[1];
     int acc = 0;
     for (int a = 0; a < p.Dmax; ++a) { int c = cum[a + 1]; cum[a] = acc; acc += c; }
     cum[p.Dmax] = acc;
-    if (blockIdx.x == 0) {
-      p.counters[0] += (unsigned long long)c0;  // single writer
-      if (cx->rec_ids) {
-        int64_t nxt = (int64_t)cx->rec_off[k] + c0;
-        cx->rec_off[k + 1] = (int32_t)(nxt < cx->rec_cap ? nxt : cx->rec_cap);
-      }
-      p.spk_cnt[wrap_slot(slot + 1, p.R)] = 0;  // next call's list; nobody reads it now (R = Dmax+1)
-    }
   }
   __syncthreads();
-  const int total_arr = cum[p.Dmax];
+  const int total = cum[p.Dmax];
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
   const uint32_t Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
   const size_t Nld = (size_t)p.Nld;
   const T* __restrict__ tr_now = p.trace + (size_t)slot * Nld;
   const uint32_t* __restrict__ bits_now = p.bits + (size_t)slot * p.W;
+  T* __restrict__ I_next = p.Iacc + (size_t)((t + 1) & 1) * Nld;
   unsigned long long n_ev = 0;
   const uint32_t G = 1u << g_log2;
   const uint32_t gl = gtid & (G - 1);
   const uint32_t ngroups = nthreads >> g_log2;
-  for (uint32_t item = gtid >> g_log2; item < (uint32_t)total_arr; item += ngroups) {
+  for (uint32_t item = gtid >> g_log2; item < (uint32_t)total; item += ngroups) {
     int a = 0;
     while (a + 1 < p.Dmax && cum[a + 1] <= (int)item) ++a;
     const int sl = slots[a];
     const uint32_t i = (uint32_t)p.spk_list[(size_t)sl * Nld + (item - cum[a])];
-    const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1) + a];
-    const uint32_t s1 = p.seg[(size_t)i * (p.Dmax + 1) + a + 1];
+    const uint32_t* __restrict__ sg = p.seg + (size_t)i * (p.Dmax + 1) + a;
+    const uint32_t s0 = sg[0], s1 = sg[1];
+    const uint32_t s2 = (PUSHNEXT && a + 1 < p.Dmax) ? sg[2] : s1;
     const uint32_t ibase = p.B == 1 ? 0u : (i / Nper) * Nper;
-    const bool row_plastic = (i - ibase) < Ne;
-    const T pre_up = row_plastic ? O::mul(p.apost, p.trace[(size_t)sl * Nld + i]) : (T)0;
-    if (gl == 0) n_ev += (s1 - s0);
-    for (uint32_t e = s0 + gl; e < s1; e += G) {
+    const bool row_plastic = LTD && (i - ibase) < Ne;
+    const T pre_up = (row_plastic && !ATOMIC) ? O::mul(p.apost, p.trace[(size_t)sl * Nld + i]) : (T)0;
+    if (LTD && gl == 0) n_ev += (s1 - s0);
+    for (uint32_t e = (LTD ? s0 : s1) + gl; e < s2; e += G) {
       const uint32_t j = (uint32_t)p.post[e];
-      typename DevNet<T>::T2 ws = p.wsd[e];
-      if (PUSH) atomicAdd(&p.Iacc[j], ws.x);
-      if (row_plastic && (p.plastic_ei || (j - ibase) < Ne)) {
+      if (e >= s1) {                       // arrives at k+1: push only
+        atomicAdd(&I_next[j], p.wsd[e].x);
+      } else if (row_plastic && (p.plastic_ei || (j - ibase) < Ne)) {
         const T dn = O::mul(p.apre, tr_now[j]);
+        if (ATOMIC) {  // production: fire-and-forget reduction, LTP of this step comes from ltp_kernel
+          atomicAdd(&p.wsd[e].y, -dn);
+          continue;
+        }
         const bool jsp = (bits_now[j >> 5] >> (j & 31)) & 1u;
-        T sd = ws.y;
+        T sd = p.wsd[e].y;
         if (jsp) sd = (j <= i) ? O::sub(O::add(sd, pre_up), dn) : O::add(O::sub(sd, dn), pre_up);
         else sd = O::sub(sd, dn);
         p.wsd[e].y = sd;
       }
     }
   }
-  // block-local reduction, then one plain RMW on this block's own slot (no contended atomics)
-  for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
-  if ((threadIdx.x & 31) == 0 && n_ev) atomicAdd(&blk_ev, n_ev);
-  __syncthreads();
-  if (threadIdx.x == 0 && PUSH && blk_ev) p.blk_ev[blockIdx.x] += blk_ev;
+  if (LTD) {
+    // block-local reduction, then one plain RMW on this block's own slot (no contended atomics)
+    for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
+    if ((threadIdx.x & 31) == 0 && n_ev) atomicAdd(&blk_ev, n_ev);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk_ev) p.blk_ev[blockIdx.x] += blk_ev;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3 ltp_kernel(t): for every neuron j that spiked at t walk the plastic prefix of its incoming
 // list (new_net.jl:126 `sd[:,n] .+= STDP`): sd += apost * trace_pre as seen at the synapse
 // (trace of step t-(d-1), Old_net/DASTDP.jl:62-68).  Synapses whose presynaptic spike arrives
-// at this very call are owned by arrival_kernel (see there).  Three gathers are kept in flight
+// at this very call are owned by synapse_kernel (see there).  Three gathers are kept in flight
 // per lane.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool ATOMIC>
 __global__ void __launch_bounds__(256)
 ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
   typedef Ops<T> O;
@@ -457,7 +509,7 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
         const uint32_t i = pk[q] & kPreMask;
         const int sl = wrap_slot(slot - (int)(pk[q] >> kPreBits), p.R);
         toff[q] = (size_t)sl * Nld + i;
-        if (ok[q]) {
+        if (!ATOMIC && ok[q]) {
           const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
           ok[q] = !((word >> (i & 31)) & 1u);
         }
@@ -466,11 +518,14 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         trv[q] = ok[q] ? p.trace[toff[q]] : (T)0;
-        sdv[q] = ok[q] ? p.wsd[e[q]].y : (T)0;
+        sdv[q] = (!ATOMIC && ok[q]) ? p.wsd[e[q]].y : (T)0;
       }
 #pragma unroll
-      for (int q = 0; q < 3; ++q)
-        if (ok[q]) p.wsd[e[q]].y = O::add(sdv[q], O::mul(p.apost, trv[q]));
+      for (int q = 0; q < 3; ++q) {
+        if (!ok[q]) continue;
+        if (ATOMIC) atomicAdd(&p.wsd[e[q]].y, O::mul(p.apost, trv[q]));
+        else p.wsd[e[q]].y = O::add(sdv[q], O::mul(p.apost, trv[q]));
+      }
     }
   }
   for (int o = 16; o > 0; o >>= 1) n_ltp += __shfl_down_sync(0xffffffffu, n_ltp, o);
@@ -643,6 +698,7 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaEventCreate(&ev_begin_));
     SNN_CUDA_OK(cudaEventCreate(&ev_end_));
     for (auto& e : dep_ev_) SNN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    SNN_CUDA_OK(cudaStreamCreateWithFlags(&side2_stream_, cudaStreamNonBlocking));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device);
     n_sm_ = sms;
@@ -650,12 +706,12 @@ class Engine : public IEngine {
     DevNet<T>& p = p_;
     memset(&p, 0, sizeof(p));
     p.N = cfg_.n_neurons; p.Nld = (p.N + 127) / 128 * 128; p.Nper = cfg_.n_per_instance; p.Ne = cfg_.n_exc;
-    p.Dmax = cfg_.max_delay; p.R = p.Dmax + 1; p.B = (int32_t)(p.N / p.Nper); p.W = (int32_t)(p.Nld / 32);
+    p.Dmax = cfg_.max_delay; p.R = p.Dmax + 2; p.B = (int32_t)(p.N / p.Nper); p.W = (int32_t)(p.Nld / 32);
     const size_t N = (size_t)p.Nld;  // padded: vector accesses never leave the allocation
     SNN_CUDA_OK(cudaMalloc(&p.v, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.u, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.ho, N * sizeof(T)));
-    SNN_CUDA_OK(cudaMalloc(&p.Iacc, N * sizeof(T)));
+    SNN_CUDA_OK(cudaMalloc(&p.Iacc, 2 * N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.trace, (size_t)p.R * N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.bits, (size_t)p.R * p.W * sizeof(uint32_t)));
     SNN_CUDA_OK(cudaMalloc(&p.spk_list, (size_t)p.R * N * sizeof(int32_t)));
@@ -668,7 +724,7 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMallocHost(&h_ctx_, sizeof(WindowCtx<T>)));
     SNN_CUDA_OK(cudaMallocHost(&h_blk_, 2 * kMaxSynBlocks * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMemsetAsync(p.ho, 0, N * sizeof(T), stream_));
-    SNN_CUDA_OK(cudaMemsetAsync(p.Iacc, 0, N * sizeof(T), stream_));
+    SNN_CUDA_OK(cudaMemsetAsync(p.Iacc, 0, 2 * N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.trace, 0, (size_t)p.R * N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.bits, 0, (size_t)p.R * p.W * sizeof(uint32_t), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.spk_cnt, 0, (size_t)p.R * sizeof(int32_t), stream_));
@@ -683,6 +739,7 @@ class Engine : public IEngine {
     p.ho_from = cfg_.ho_from; p.threshold_ge = cfg_.threshold_ge; p.sd_decay_mode = cfg_.sd_decay_mode;
     p.rate_mode = cfg_.rate_mode; p.plastic_ei = cfg_.plastic_ei; p.noise_mode = cfg_.noise_mode;
     p.exact = cfg_.mode == SNN_MODE_EXACT;
+    p.exp_flags = cfg_.reserved[1];
     p.homeostasis = !(cfg_.theta == 0.0 && cfg_.ttheta == 1.0);
     init_state_kernel<T><<<grid_for(p.Nld), 256, 0, stream_>>>(p);
     SNN_CUDA_OK(cudaGetLastError());
@@ -728,7 +785,7 @@ class Engine : public IEngine {
       case SNN_FIELD_DA: src = p.da + (size_t)(t_ & 1) * p.B; n = p.B; break;
       case SNN_FIELD_I:
         if (!p.exact) { err = "FIELD_I is only kept in SNN_MODE_EXACT"; return SNN_ERR_INVALID; }
-        src = p.Iacc; break;
+        src = p.Iacc + (size_t)((t_ - 1) & 1) * p.Nld; break;
       case SNN_FIELD_W: case SNN_FIELD_SD: {
         if (!have_topo_) { err = "synapses not set"; return SNN_ERR_STATE; }
         if (count != p.E) { err = "count mismatch"; return SNN_ERR_INVALID; }
@@ -834,9 +891,16 @@ class Engine : public IEngine {
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return SNN_ERR_CUDA; }
     return SNN_OK;
   }
+  struct CachedGraph {
+    std::string key; cudaGraphExec_t exec = nullptr; size_t prof_used = 0; std::vector<int> prof_cls;
+    std::vector<cudaEvent_t> prof_events;  // event record nodes are baked into the graph
+  };
   void drop_graph() {
-    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
-    graph_exec_ = nullptr; graph_key_.clear();
+    for (auto& g : graphs_) {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      for (auto& e : g.prof_events) cudaEventDestroy(e);
+    }
+    graphs_.clear();
   }
   void release() {
     DevNet<T>& p = p_;
@@ -856,6 +920,8 @@ class Engine : public IEngine {
     prof_events_.clear();
     if (own_stream_) cudaStreamDestroy(own_stream_);
     if (side_stream_) cudaStreamDestroy(side_stream_);
+    if (side2_stream_) cudaStreamDestroy(side2_stream_);
+    side2_stream_ = nullptr;
     memset(&p, 0, sizeof(p));
     own_stream_ = side_stream_ = nullptr; ev_begin_ = ev_end_ = nullptr; d_ctx_ = nullptr; h_ctx_ = nullptr; h_blk_ = nullptr;
   }
@@ -891,8 +957,7 @@ class Engine : public IEngine {
     l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 + 255) / 256, (int64_t)n_sm_ * 8));
     if (gA_ == 0) {
       int per_sm = 0;
-      if (p.exact) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, arrival_kernel<T, false>, 256, 0);
-      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, arrival_kernel<T, true>, 256, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synapse_kernel<T, true, true, true>, 256, 0);
       gA_ = std::min(kMaxSynBlocks, n_sm_ * std::max(1, per_sm));
     }
     l.gA = gA_;
@@ -922,15 +987,16 @@ class Engine : public IEngine {
   int n_sm_ = 148, g_arr_log2_ = 5, g_ltp_log2_ = 5, gA_ = 0;
   cudaStream_t own_stream_ = nullptr, side_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev_begin_ = nullptr, ev_end_ = nullptr;
-  cudaEvent_t dep_ev_[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t dep_ev_[12] = {};
+  cudaStream_t side2_stream_ = nullptr;
   std::vector<cudaEvent_t> prof_events_;
-  std::vector<int> prof_cls_, graph_prof_cls_;
-  size_t prof_used_ = 0, graph_prof_used_ = 0;
+  std::vector<int> prof_cls_;
+  size_t prof_used_ = 0;
   WindowCtx<T>* d_ctx_ = nullptr; WindowCtx<T>* h_ctx_ = nullptr;
   unsigned long long* h_blk_ = nullptr;
   DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_;
-  cudaGraphExec_t graph_exec_ = nullptr;
-  std::string graph_key_;
+  const std::vector<cudaEvent_t>* graph_prof_events_ = nullptr;
+  std::vector<CachedGraph> graphs_;  // a few (length, train pattern, profiling) variants
 };
 
 // Plain stream-ordered launches: exact mode, forced spikes, per-kernel profiling.
@@ -941,6 +1007,8 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
   const int n = a.n_steps;
   const Launch g = grids();
   cudaStream_t s = stream_;
+  // production mode: arrivals of window step 0 that are already in flight (spikes of earlier windows)
+  if (!p.exact) synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s>>>(p, d_ctx_, -1, g_arr_log2_);
   for (int k = 0; k <= n; ++k) {
     const bool forced = k < n && force_off[k + 1] > force_off[k];
     if (prof) prof_begin(0, s);
@@ -961,25 +1029,37 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
     }
     if (prof) prof_end(s);
     if (k == n) break;
+    int dl, dd;
+    const bool learn = wants_learn(a, k, &dl, &dd);
+    const bool push_next = !p.exact && k + 1 < n;  // the last step leaves its pushes to the next window
     if (prof) prof_begin(1, s);
     if (p.exact) {
       gather_kernel<T><<<grid_for(p.N), 256, 0, s>>>(p, d_ctx_, k);
-      arrival_kernel<T, false><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
+      synapse_kernel<T, true, false, false><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
+      ltp_kernel<T, false><<<g.gP, 256, 0, s>>>(p, d_ctx_, k, g_ltp_log2_);
     } else {
-      arrival_kernel<T, true><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
+      if (push_next && !learn) synapse_kernel<T, true, true, true><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
+      else synapse_kernel<T, true, false, true><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
+      ltp_kernel<T, true><<<g.gP, 256, 0, s>>>(p, d_ctx_, k, g_ltp_log2_);
     }
-    ltp_kernel<T><<<g.gP, 256, 0, s>>>(p, d_ctx_, k, g_ltp_log2_);
     if (prof) prof_end(s);
-    int dl, dd;
-    if (wants_learn(a, k, &dl, &dd)) {
+    if (learn) {
       if (prof) prof_begin(2, s);
       learn_kernel<T><<<g.gL, 256, 0, s>>>(p, d_ctx_, k, dl, dd);
       if (prof) prof_end(s);
+      // the pushes of step k+1 must see the weights after learn!(k)
+      if (push_next) synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
     }
   }
 }
 
-// Whole window as one CUDA graph (captured once per (length, train pattern)), two streams.
+// Whole window as one CUDA graph (captured once per (length, train pattern)), three streams.
+//   needs(neuron(k))  : neuron(k-1) [stream], pushes for step k-1 = synapse(k-2) | push(k-2),
+//                       learn(k-1) (its delay-1 pushes read w)
+//   needs(synapse(k)) : neuron(k), learn(k-1), synapse(k-1) [stream]   (sd updates are reductions:
+//   needs(ltp(k))     : neuron(k), learn(k-1) [stream], ltp(k-1) [stream]  no LTD/LTP ordering)
+//   needs(learn(k))   : synapse(k) LTD, ltp(k) [stream]
+//   needs(push(k))    : learn(k)            (learn steps only; otherwise fused into synapse(k))
 template <typename T>
 int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
   DevNet<T>& p = p_;
@@ -987,49 +1067,101 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
   std::string key(reinterpret_cast<const char*>(&n), sizeof(n));
   key.push_back(prof ? 'p' : '-');
   if (a.train_flags) key.append(reinterpret_cast<const char*>(a.train_flags), n);
-  if (!graph_exec_ || key != graph_key_) {
-    drop_graph();
+  CachedGraph* hit = nullptr;
+  for (auto& cg : graphs_) if (cg.key == key) hit = &cg;
+  if (!hit) {
+    if (graphs_.size() >= 6) {  // evict the oldest
+      if (graphs_.front().exec) cudaGraphExecDestroy(graphs_.front().exec);
+      for (auto& e : graphs_.front().prof_events) cudaEventDestroy(e);
+      graphs_.erase(graphs_.begin());
+    }
+    // profiling events of a captured graph are baked into it: give this graph its own set
+    std::vector<cudaEvent_t> saved_events;
+    saved_events.swap(prof_events_);
     const Launch g = grids();
-    cudaStream_t s1 = stream_, s2 = side_stream_;
+    cudaStream_t s1 = stream_, s2 = side_stream_, s3 = side2_stream_;
     cudaGraph_t graph = nullptr;
     prof_used_ = 0; prof_cls_.clear();
     if (prof) prof_reserve(2 * (size_t)n + 2);  // no allocation while capturing
+    // events: [0] neuron done, [1..3] pushes-for-step ready (ring of 3), [4..5] synapse LTD done
+    // (ring of 2), [6..7] ltp done (ring of 2), [8] learn done
+    cudaEvent_t evN = dep_ev_[0], evL = dep_ev_[8];
+    auto evPush = [&](int step) { return dep_ev_[1 + ((step % 3) + 3) % 3]; };  // pushes consumed by Euler(step)
+    auto evS = [&](int step) { return dep_ev_[4 + (step & 1)]; };
+    auto evP = [&](int step) { return dep_ev_[6 + (step & 1)]; };
     SNN_CUDA_OK(cudaStreamBeginCapture(s1, cudaStreamCaptureModeThreadLocal));
-    bool side_pending = false;
+    cudaEventRecord(evN, s1);                      // fork point
+    cudaStreamWaitEvent(s2, evN, 0);
+    synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, -1, g_arr_log2_);  // pushes for step 0
+    cudaEventRecord(evPush(0), s2);
+    bool learn_prev = false, s3_used = false;
     for (int k = 0; k < n; ++k) {
+      int dl, dd;
+      const bool learn = wants_learn(a, k, &dl, &dd);
+      const bool push_next = k + 1 < n;
+      if (k >= 1) cudaStreamWaitEvent(s1, evPush(k - 1), 0);  // Euler(k-1) consumes them
+      if (learn_prev) cudaStreamWaitEvent(s1, evL, 0);
       if (k == 0) neuron_kernel<T, false, true><<<g.gN, 256, 0, s1>>>(p, d_ctx_, k, 1);
       else neuron_kernel<T, true, true><<<g.gN, 256, 0, s1>>>(p, d_ctx_, k, 1);
-      cudaEventRecord(dep_ev_[0], s1);
-      cudaStreamWaitEvent(s2, dep_ev_[0], 0);           // ltp(k) needs trace/bitmap/list of step k
-      ltp_kernel<T><<<g.gP, 256, 0, s2>>>(p, d_ctx_, k, g_ltp_log2_);
-      if (side_pending) cudaStreamWaitEvent(s1, dep_ev_[2], 0);  // arrival(k) needs ltp/learn(k-1)
-      arrival_kernel<T, true><<<g.gA, 256, 0, s1>>>(p, d_ctx_, k, g_arr_log2_);
-      int dl, dd;
-      if (wants_learn(a, k, &dl, &dd)) {
-        cudaEventRecord(dep_ev_[1], s1);
-        cudaStreamWaitEvent(s2, dep_ev_[1], 0);         // learn(k) needs arrival(k) (LTD) and ltp(k)
-        if (prof) prof_begin(2, s2, true);
-        learn_kernel<T><<<g.gL, 256, 0, s2>>>(p, d_ctx_, k, dl, dd);
-        if (prof) prof_end(s2, true);
+      cudaEventRecord(evN, s1);
+      // s2: synapse(k)
+      cudaStreamWaitEvent(s2, evN, 0);
+      if (learn_prev) cudaStreamWaitEvent(s2, evL, 0);  // sd reductions must not race the learn pass
+      if (push_next && !learn) {
+        synapse_kernel<T, true, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
+        cudaEventRecord(evPush(k + 1), s2);
+      } else {
+        synapse_kernel<T, true, false, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
       }
-      cudaEventRecord(dep_ev_[2], s2);
-      side_pending = true;
+      cudaEventRecord(evS(k), s2);
+      // s3: ltp(k) [-> learn(k)]
+      cudaStreamWaitEvent(s3, evN, 0);
+      ltp_kernel<T, true><<<g.gP, 256, 0, s3>>>(p, d_ctx_, k, g_ltp_log2_);
+      s3_used = true;
+      if (learn) {
+        cudaStreamWaitEvent(s3, evS(k), 0);
+        if (prof) prof_begin(2, s3, true);
+        learn_kernel<T><<<g.gL, 256, 0, s3>>>(p, d_ctx_, k, dl, dd);
+        if (prof) prof_end(s3, true);
+        cudaEventRecord(evL, s3);
+        if (push_next) {
+          cudaStreamWaitEvent(s2, evL, 0);
+          synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
+          cudaEventRecord(evPush(k + 1), s2);
+        }
+      }
+      cudaEventRecord(evP(k), s3);
+      learn_prev = learn;
     }
-    if (side_pending) cudaStreamWaitEvent(s1, dep_ev_[2], 0);
+    // join everything, then the window-end Euler
+    cudaEventRecord(evS(n), s2);
+    cudaStreamWaitEvent(s1, evS(n), 0);
+    if (s3_used) { cudaEventRecord(evP(n), s3); cudaStreamWaitEvent(s1, evP(n), 0); }
     neuron_kernel<T, true, false><<<g.gN, 256, 0, s1>>>(p, d_ctx_, n, 1);
     cudaError_t e = cudaStreamEndCapture(s1, &graph);
-    if (e != cudaSuccess || !graph) { err = std::string("graph capture: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
-    e = cudaGraphInstantiate(&graph_exec_, graph, 0);
+    if (e != cudaSuccess || !graph) {
+      for (auto& ev : prof_events_) cudaEventDestroy(ev);
+      prof_events_.clear();
+      prof_events_.swap(saved_events);
+      err = std::string("graph capture: ") + cudaGetErrorString(e); return SNN_ERR_CUDA;
+    }
+    CachedGraph cg;
+    cg.key = key; cg.prof_used = prof_used_; cg.prof_cls = prof_cls_;
+    cg.prof_events.swap(prof_events_);
+    prof_events_.swap(saved_events);
+    e = cudaGraphInstantiate(&cg.exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { graph_exec_ = nullptr; err = std::string("graph instantiate: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
-    graph_key_ = key;
-    graph_prof_used_ = prof_used_;
-    graph_prof_cls_ = prof_cls_;
-  } else {
-    prof_used_ = graph_prof_used_;
-    prof_cls_ = graph_prof_cls_;
+    if (e != cudaSuccess) {
+      for (auto& ev : cg.prof_events) cudaEventDestroy(ev);
+      err = std::string("graph instantiate: ") + cudaGetErrorString(e); return SNN_ERR_CUDA;
+    }
+    graphs_.push_back(std::move(cg));
+    hit = &graphs_.back();
   }
-  SNN_CUDA_OK(cudaGraphLaunch(graph_exec_, stream_));
+  prof_used_ = hit->prof_used;
+  prof_cls_ = hit->prof_cls;
+  graph_prof_events_ = &hit->prof_events;
+  SNN_CUDA_OK(cudaGraphLaunch(hit->exec, stream_));
   return SNN_OK;
 }
 
@@ -1156,16 +1288,17 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev_begin_, ev_end_);
     s.device_ms = ms;
-    for (size_t q = 0; q < prof_used_ && q / 2 < prof_cls_.size(); q += 2) {
+    const std::vector<cudaEvent_t>& pev = (graphable && graph_prof_events_) ? *graph_prof_events_ : prof_events_;
+    for (size_t q = 0; q + 1 < pev.size() && q < prof_used_ && q / 2 < prof_cls_.size(); q += 2) {
       float m = 0.f;
-      if (cudaEventElapsedTime(&m, prof_events_[q], prof_events_[q + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (cudaEventElapsedTime(&m, pev[q], pev[q + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
       int cls = prof_cls_[q / 2];
       if (cls == 0) { s.neuron_ms += m; s.neuron_launches++; }
       else if (cls == 1) { s.synapse_ms += m; s.synapse_launches++; }
       else { s.learn_ms += m; s.learn_launches++; }
     }
     if (graphable) {  // launches inside the graph (events exist only around learn, if at all)
-      s.neuron_launches = n + 1; s.synapse_launches = 2 * n;
+      s.neuron_launches = n + 1; s.synapse_launches = 2 * n + 1;
       if (profiling_ != 2) {
         int nl = 0, dl, dd;
         for (int k = 0; k < n; ++k) nl += wants_learn(a, k, &dl, &dd) ? 1 : 0;

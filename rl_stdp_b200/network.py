@@ -55,6 +55,7 @@ class SparseNetwork:
         n_per = int(n_neurons)
         max_delay = int(params.pop("max_delay", int(delay.max()) if delay is not None and len(delay) else 1))
         use_graph = bool(params.pop("graph", True))
+        exp_flags = int(params.pop("exp_flags", 0))
         cfg = default_config(
             dtype=L.SNN_F64 if dtype == "f64" else L.SNN_F32,
             mode=L.SNN_MODE_EXACT if mode == "exact" else L.SNN_MODE_FAST,
@@ -64,6 +65,7 @@ class SparseNetwork:
             **params)
         if not use_graph:
             cfg.reserved[0] = 1  # plain stream-ordered launches instead of the captured window graph
+        cfg.reserved[1] = exp_flags
         self.cfg = cfg
         self.n_neurons = int(cfg.n_neurons)
         self.n_instances = int(n_instances)
