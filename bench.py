@@ -128,10 +128,19 @@ def run_b200(args):
     n, ne, fan, dmax = WORKLOADS[args.workload]
     W = args.window_ms
     t_build = time.perf_counter()
-    rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9 + rank)
-    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f32", mode="fast", noise="philox", device=local,
-                        max_delay=dmax, noise_seed=10 + rank, exp_flags=args.exp_flags, graph=not args.no_graph)
-    n_plastic = int(rowptr[ne])
+    if args.partition and world > 1:
+        # ONE network, neuron-partitioned over the ranks, spike bitmap all-gathered per ms (NCCL)
+        from rl_stdp_b200.partition import PartitionedRank, TorchDistExchange, plan
+        rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9)
+        lo, hi = plan(n, world)[rank]
+        net = PartitionedRank(n, ne, rowptr, post, w, delay, lo, hi, TorchDistExchange().callback(), dtype="f32",
+                              mode="fast", noise="philox", device=local, max_delay=dmax, noise_seed=10)
+        n_plastic = int(np.count_nonzero(np.repeat(np.arange(n), np.diff(rowptr))[net.local_index] < ne))
+    else:
+        rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9 + rank)
+        net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f32", mode="fast", noise="philox", device=local,
+                            max_delay=dmax, noise_seed=10 + rank, exp_flags=args.exp_flags, graph=not args.no_graph)
+        n_plastic = int(rowptr[ne])
     del post, w, delay
     t_build = time.perf_counter() - t_build
     lib = L.load()
@@ -219,13 +228,17 @@ def run_b200(args):
         path_bytes = (sim_ms * n * B_NEURON + tot["ev"] * B_EVENT + tot["ltp"] * B_LTP + tot["nl"] * learn_bytes)
         line = {
             "metric": "synaptic events/s", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if (args.partition and world > 1) else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "neurons": n, "synapses": int(rowptr[-1]), "max_delay_ms": dmax,
                        "window_ms_per_step": W, "learn_period_ms": LEARN_PERIOD, "noise": "on-device Philox4x32-10",
-                       "instances": world, "sharding": "one independent instance per GPU, no collective",
+                       "instances": 1 if (args.partition and world > 1) else world,
+                       "sharding": ("one network, neurons partitioned over the ranks, NCCL all-gather of the spike "
+                                    "bitmap per ms") if (args.partition and world > 1) else
+                                   "one independent instance per GPU, no collective",
                        "l2": "working set 2.2 GB per instance >> 126 MB L2 (no flush needed)"},
-            "sim_ms_per_wall_s": sim_ms * world / (dev_ms * 1e-3),
+            "sim_ms_per_wall_s": sim_ms * (1 if (args.partition and world > 1) else world) / (dev_ms * 1e-3),
             "x_realtime_per_instance": sim_ms / dev_ms,
             "firing_rate_hz": spikes_all / world / n / (sim_ms * 1e-3),
             "e2e": {"value": e2e_ev_all / (e2e_ms * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d // args.steps,
@@ -412,6 +425,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exp-flags", type=int, default=0, help="kernel experiments (wrong numerics), never for reported numbers")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--partition", action="store_true", help="N>1: one network neuron-partitioned over the ranks (strong scaling) instead of one instance per rank")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -199,6 +199,19 @@ int32_t snn_set_array(snn_net* net, int32_t field, const double* host, int64_t c
 int64_t snn_n_synapses(const snn_net* net);
 int64_t snn_step_index(const snn_net* net);
 
+/* Neuron partitioning of ONE network over several GPUs: this handle integrates
+ * neurons [neuron_lo, neuron_hi) (multiples of 128) and must be given, through
+ * snn_set_synapses_csr, exactly the synapses whose POST is in that range (rowptr still spans all
+ * presynaptic neurons).  After every step's local detection the library calls `fn`, which must
+ * all-gather the spike bitmap of the step: `words` points to the device bitmap (uint32[total_words]),
+ * this rank owns [word_lo, word_lo+n_words), the other ranks' words must be valid when work
+ * enqueued on `cuda_stream` after the call runs (e.g. ncclAllGather / torch.distributed on that
+ * stream).  Traces of remote neurons, the spike list and `da` are replicated, so the union of the
+ * ranks reproduces the single-GPU run.  Call before the first step. */
+typedef int32_t (*snn_exchange_fn)(void* user, void* words, int64_t word_lo, int64_t n_words, int64_t total_words,
+                                   void* cuda_stream);
+int32_t snn_set_partition(snn_net* net, int64_t neuron_lo, int64_t neuron_hi, snn_exchange_fn fn, void* user);
+
 /* 0 (default): only the window events; the window runs as one CUDA graph when possible.
  * 1: CUDA events around every kernel class, plain stream-ordered launches (diagnostics).
  * 2: the CUDA-graph path with events around the learn_kernel launches only (bench.py roofline). */

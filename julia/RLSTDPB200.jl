@@ -1,0 +1,185 @@
+# RLSTDPB200.jl — thin `ccall` layer over libsnn_b200.so that keeps the reference's L1 API
+# (Julia/Izhikevic_dastdp/Old_net/new_net.jl: Network, step!, input!; field access net.da, net.v,
+#  net.s[pre,post]; Julia/Modules/Networks/net_arch.jl: step_LIF! for a population).
+#
+# NOT EXECUTED IN THE BUILD IMAGE (Julia is not installed there): the Python ctypes mirror
+# rl_stdp_b200/_lib.py + network.py binds the identical symbols and is what the tests drive.
+# Usage inside the reference repo:
+#     include("/path/to/julia/RLSTDPB200.jl"); using .RLSTDPB200
+#     n = RLSTDPB200.Network(1000, 0.1, 800; connection = conn)      # instead of Old_net/new_net.jl
+#     spiked = step!(n, noise_row, train)                              # noise_row = 13 .* (rand(N) .- 0.5)
+module RLSTDPB200
+
+export Network, step!, run_window!, add_dopamine!, reset_v!, weights, eligibility
+
+const LIB = get(ENV, "SNN_B200_LIB", joinpath(@__DIR__, "..", "rl_stdp_b200", "libsnn_b200.so"))
+
+# mirrors `struct snn_config` of include/snn_b200.h (field order and types must match)
+mutable struct SnnConfig
+    struct_size::Int32; dtype::Int32; mode::Int32; device::Int32
+    n_neurons::Int64; n_per_instance::Int64; n_exc::Int64
+    max_delay::Int32; threshold_ge::Int32
+    vthresh::Float64; v_reset::Float64
+    a_exc::Float64; a_inh::Float64; d_exc::Float64; d_inh::Float64
+    trace_set::Float64; trace_decay::Float64; apost::Float64; apre::Float64
+    da_decay::Float64; learn_base::Float64; eta::Float64
+    wmin::Float64; wmax::Float64; sd_decay::Float64
+    sd_decay_mode::Int32; rate_mode::Int32; noise_mode::Int32; plastic_ei::Int32
+    noise_amp::Float64; noise_seed::UInt64
+    theta::Float64; ttheta::Float64; ho_from::Int64
+    reserved::NTuple{8,Int32}
+    SnnConfig() = new()
+end
+
+struct SnnDaEvent
+    step::Int32; instance::Int32; amount::Float64
+end
+struct SnnForceEvent
+    step::Int32; neuron::Int32
+end
+mutable struct SnnStepStats
+    n_spikes::Int64; n_syn_events::Int64; n_ltp_events::Int64
+    device_ms::Float64; learn_ms::Float64; neuron_ms::Float64; synapse_ms::Float64
+    learn_launches::Int32; neuron_launches::Int32; synapse_launches::Int32; reserved::Int32
+    SnnStepStats() = new(0, 0, 0, 0.0, 0.0, 0.0, 0.0, 0, 0, 0, 0)
+end
+
+const FIELD_V, FIELD_U, FIELD_TRACE, FIELD_HO, FIELD_W, FIELD_SD, FIELD_DA, FIELD_I = Int32.(0:7)
+
+function check(rc::Integer)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:snn_last_error, LIB), Cstring, ()))
+    error("libsnn_b200 error $rc: $msg")
+end
+
+"""
+    Network(n_neurons, connectivity, n_exc; connection, dtype=:f64, mode=:exact)
+
+Drop-in for `Network(n_neurons::Int64, connectivity::Float64, n_exc::Int64)`
+(Old_net/new_net.jl:80-98).  `connection[pre,post]` defaults to `rand(N,N) .< connectivity`.
+"""
+mutable struct Network
+    handle::Ptr{Cvoid}
+    n_neurons::Int64
+    n_exc::Int64
+    connection::Matrix{Int64}
+    rowptr::Vector{Int64}     # CSR of `connection` (0-based post ids), caller order of W / SD
+    post::Vector{Int32}
+    exc::Vector{Int64}
+    inh::Vector{Int64}
+end
+
+function Network(n_neurons::Int64, connectivity::Float64, n_exc::Int64;
+                 connection::AbstractMatrix = (rand(n_neurons, n_neurons) .< connectivity),
+                 dtype::Symbol = :f64, mode::Symbol = :exact, device::Integer = 0)
+    conn = Matrix{Int64}(connection)
+    s = zeros(n_neurons, n_neurons)                        # new_net.jl:87-91
+    s[1:n_exc, :] .= 1.0
+    s[n_exc+1:end, :] .= -1.0
+    s .*= conn
+    cfg = SnnConfig()
+    check(ccall((:snn_config_default, LIB), Int32, (Ref{SnnConfig},), cfg))
+    cfg.dtype = dtype == :f64 ? 1 : 0
+    cfg.mode = mode == :exact ? 1 : 0
+    cfg.device = device
+    cfg.n_neurons = n_neurons; cfg.n_per_instance = n_neurons; cfg.n_exc = n_exc
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:snn_create, LIB), Int32, (Ref{SnnConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+    # snn_set_synapses_dense takes exactly what variant A holds (column-major s, connection)
+    check(ccall((:snn_set_synapses_dense, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}), h[], s, conn))
+    rowptr = zeros(Int64, n_neurons + 1); post = Int32[]
+    for i in 1:n_neurons
+        for j in 1:n_neurons
+            conn[i, j] != 0 && push!(post, Int32(j - 1))
+        end
+        rowptr[i+1] = length(post)
+    end
+    net = Network(h[], n_neurons, n_exc, conn, rowptr, post, collect(1:n_exc), collect(n_exc+1:n_neurons))
+    finalizer(n -> (n.handle != C_NULL && ccall((:snn_destroy, LIB), Int32, (Ptr{Cvoid},), n.handle); n.handle = C_NULL), net)
+    return net
+end
+
+function get_array(net::Network, field::Int32, n::Integer)
+    out = zeros(Float64, n)
+    check(ccall((:snn_get_array, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), net.handle, field, out, n))
+    out
+end
+set_array!(net::Network, field::Int32, a::Vector{Float64}) =
+    check(ccall((:snn_set_array, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), net.handle, field, a, length(a)))
+
+# `net.da`, `net.v`, `net.u`, `net.STDP`, `net.I` read through; `net.da = x` / `net.da += x` write through
+function Base.getproperty(net::Network, f::Symbol)
+    f === :da && return get_array(net, FIELD_DA, 1)[1]
+    f === :v && return get_array(net, FIELD_V, getfield(net, :n_neurons))
+    f === :u && return get_array(net, FIELD_U, getfield(net, :n_neurons))
+    f === :STDP && return get_array(net, FIELD_TRACE, getfield(net, :n_neurons))
+    f === :I && return get_array(net, FIELD_I, getfield(net, :n_neurons))
+    f === :s && return weights(net)
+    f === :sd && return eligibility(net)
+    return getfield(net, f)
+end
+function Base.setproperty!(net::Network, f::Symbol, x)
+    f === :da && return set_array!(net, FIELD_DA, [Float64(x)])
+    f === :v && return set_array!(net, FIELD_V, Vector{Float64}(x))
+    return setfield!(net, f, x)
+end
+
+"dense s[pre,post] (new_net.jl:15); write back with `set_weights!(net, s)` — `n.s[n1,n2] = 0.0` (newnet_DASTDP.jl:19)"
+function dense_from_csr(net::Network, field::Int32)
+    vals = get_array(net, field, length(getfield(net, :post)))
+    N = getfield(net, :n_neurons); m = zeros(N, N)
+    rp = getfield(net, :rowptr); po = getfield(net, :post)
+    for i in 1:N, e in rp[i]+1:rp[i+1]
+        m[i, po[e]+1] = vals[e]
+    end
+    m
+end
+weights(net::Network) = dense_from_csr(net, FIELD_W)
+eligibility(net::Network) = dense_from_csr(net, FIELD_SD)
+function set_weights!(net::Network, s::AbstractMatrix)
+    rp = getfield(net, :rowptr); po = getfield(net, :post)
+    vals = zeros(Float64, length(po))
+    for i in 1:getfield(net, :n_neurons), e in rp[i]+1:rp[i+1]
+        vals[e] = s[i, po[e]+1]
+    end
+    set_array!(net, FIELD_W, vals)
+end
+
+"""
+    run_window!(net, noise, train; da_events, force) -> Vector{Vector{Int64}}
+
+`noise` is N x T (column t = the recorded `13 .* (rand(N) .- 0.5)` of step t), `train` a Bool vector.
+Runs T calls of step! on the device without a host round trip and returns the 1-based spike ids
+of every step (ascending, like `findall`).
+"""
+function run_window!(net::Network, noise::Matrix{Float64}, train::AbstractVector{Bool};
+                     da_events::Vector{SnnDaEvent} = SnnDaEvent[], force::Vector{SnnForceEvent} = SnnForceEvent[])
+    T = length(train); N = getfield(net, :n_neurons)
+    @assert size(noise) == (N, T)           # column-major N x T == row-major [T][N] of the C ABI
+    flags = UInt8.(train)
+    cap = max(1024, N * T)
+    out = Vector{Int32}(undef, cap); offs = zeros(Int64, T + 1)
+    st = SnnStepStats()
+    GC.@preserve noise flags da_events force out offs begin
+        check(ccall((:snn_step, LIB), Int32,
+                    (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{UInt8}, Ptr{SnnForceEvent}, Int32, Ptr{SnnDaEvent}, Int32,
+                     Ptr{Int32}, Ptr{Int64}, Int64, Ref{SnnStepStats}),
+                    net.handle, T, noise, flags, force, length(force), da_events, length(da_events), out, offs, cap, st))
+    end
+    [Int64.(out[offs[k]+1:offs[k+1]]) .+ 1 for k in 1:T]
+end
+
+"step!(net, train) / step!(net, input_spikes, train)  (new_net.jl:146-161); `noise` replaces the internal rand"
+function step!(net::Network, noise::Vector{Float64}, train::Bool = false)
+    run_window!(net, reshape(noise, :, 1), [train])[1]
+end
+function step!(net::Network, input_spikes::Array{Int64}, noise::Vector{Float64}, train::Bool = false)
+    force = [SnnForceEvent(0, Int32(j - 1)) for j in input_spikes]   # input! new_net.jl:104-106
+    run_window!(net, reshape(noise, :, 1), [train]; force = force)[1]
+end
+
+add_dopamine!(net::Network, x::Real; instance::Integer = 0) =
+    check(ccall((:snn_add_dopamine, LIB), Int32, (Ptr{Cvoid}, Int32, Float64), net.handle, instance, x))
+reset_v!(net::Network) = check(ccall((:snn_reset_v, LIB), Int32, (Ptr{Cvoid},), net.handle))
+
+end # module

@@ -66,6 +66,8 @@ class SnnStepStats(C.Structure):
     ]
 
 
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p)
+
 # every symbol of include/snn_b200.h: name -> (restype, argtypes)
 _VP = C.c_void_p
 SYMBOLS = {
@@ -86,6 +88,7 @@ SYMBOLS = {
     "snn_step_index": (C.c_int64, [_VP]),
     "snn_set_profiling": (C.c_int32, [_VP, C.c_int32]),
     "snn_set_stream": (C.c_int32, [_VP, _VP]),
+    "snn_set_partition": (C.c_int32, [_VP, C.c_int64, C.c_int64, _VP, _VP]),
     # batched LIF actors
     "snn_actor_config_default": (C.c_int32, [C.POINTER(SnnActorConfig)]),
     "snn_actor_create": (C.c_int32, [C.POINTER(SnnActorConfig), C.POINTER(_VP)]),

@@ -140,6 +140,13 @@ int32_t snn_add_dopamine(snn_net* net, int32_t instance, double amount) {
   return rc ? fail(rc, err) : SNN_OK;
 }
 
+int32_t snn_set_partition(snn_net* net, int64_t neuron_lo, int64_t neuron_hi, snn_exchange_fn fn, void* user) {
+  if (!net) return fail(SNN_ERR_INVALID, "null net");
+  std::string err;
+  int rc = net->eng->set_partition(neuron_lo, neuron_hi, fn, user, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
 int32_t snn_reset_v(snn_net* net) {
   if (!net) return fail(SNN_ERR_INVALID, "null net");
   std::string err;

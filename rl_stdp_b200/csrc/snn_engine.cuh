@@ -122,6 +122,9 @@ struct DevNet {
   int64_t ho_from;
   int32_t threshold_ge, sd_decay_mode, rate_mode, plastic_ei, noise_mode, exact, homeostasis;
   int32_t exp_flags;  // experiments only (snn_config.reserved[1]); 0 in production
+  // neuron partition (multi-GPU): this rank integrates neurons [part_lo, part_hi)
+  // and holds every synapse whose POST is in that range; spike bitmaps are exchanged per step
+  int64_t part_lo, part_hi;
 };
 
 // Per-window inputs/outputs.  Lives in device memory so that a captured graph never has to be
@@ -213,8 +216,8 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
     }
   }
 
-  const uint32_t nquad = (uint32_t)(p.Nld >> 2);
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += gridDim.x * blockDim.x) {
+  const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi + 3) >> 2);
+  for (uint32_t q = q_lo + blockIdx.x * blockDim.x + threadIdx.x; q < q_hi; q += gridDim.x * blockDim.x) {
     const uint32_t j0 = q << 2;
     // ---- all loads first
     Vec4<T> v = ld4(p.v + j0), u = ld4(p.u + j0), I, tp, ho;
@@ -342,6 +345,74 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// remote_kernel(k) — neuron-partitioned runs only.  After the spike bitmap of step k has been
+// all-gathered, every rank replays detect(k) for the neurons it does NOT own: trace set/decay
+// (the replicated pre-trace ring that LTP gathers from), spike-list append, spike record and the
+// delay-1 current push of remote spikers into local targets.  Same quad/warp mapping as
+// neuron_kernel; no v/u traffic (16 B/neuron).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
+  typedef Ops<T> O;
+  const int lane = threadIdx.x & 31;
+  const int64_t t = cx->t0 + k;
+  const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
+  T* __restrict__ tr = p.trace + (size_t)slot * p.Nld;
+  const T* __restrict__ trp = p.trace + (size_t)prev * p.Nld;
+  const uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
+  int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.Nld;
+  int32_t* __restrict__ rec_ids = cx->rec_ids;
+  const int64_t rec_cap = cx->rec_cap;
+  int32_t rec_base = 0;
+  if (rec_ids && k > 0) {
+    int64_t nxt = (int64_t)cx->rec_off[k - 1] + p.spk_cnt[prev];
+    rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
+  }
+  T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;
+  const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi + 3) >> 2);
+  const uint32_t nquad = (uint32_t)(p.Nld >> 2), n_remote = nquad - (q_hi - q_lo);
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_remote; r += gridDim.x * blockDim.x) {
+    const uint32_t q = r < q_lo ? r : r + (q_hi - q_lo);  // part bounds are multiples of 128: warps stay whole
+    const uint32_t j0 = q << 2;
+    Vec4<T> tp = ld4(trp + j0);
+    const unsigned nib = (bits[j0 >> 5] >> (j0 & 31)) & 0xFu;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool s = (nib >> c) & 1u;
+      tp.x[c] = s ? p.trace_set : (t > 0 ? O::mul(tp.x[c], p.trace_decay) : (T)0);
+    }
+    st4(tr + j0, tp);
+    if (__any_sync(0xffffffffu, nib != 0)) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool s = (nib >> c) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, s);
+        if (m) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&p.spk_cnt[slot], __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (s) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            list[pos] = (int32_t)(j0 + c);
+            if (rec_ids && (int64_t)rec_base + pos < rec_cap) rec_ids[rec_base + pos] = (int32_t)(j0 + c);
+          }
+          if (!p.exact) {
+            unsigned mm = m;
+            while (mm) {
+              const int src = __ffs(mm) - 1; mm &= mm - 1;
+              const uint32_t i = __shfl_sync(0xffffffffu, j0, src) + c;
+              const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1)], s1 = p.seg[(size_t)i * (p.Dmax + 1) + 1];
+              for (uint32_t e = s0 + lane; e < s1; e += 32) atomicAdd(&I_now[p.post[e]], p.wsd[e].x);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // v[idx] = 40 (input! new_net.jl:104-106)
 template <typename T>
 __global__ void force_kernel(DevNet<T> p, const int32_t* __restrict__ idx, int n) {
@@ -360,7 +431,8 @@ gather_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
   const int64_t t = cx->t0 + k;
   const int slot = (cx->slot0 + k) % p.R;
   const T* __restrict__ noise = cx->noise ? cx->noise + (size_t)k * p.N : nullptr;
-  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.N;
+  const int64_t j_hi = p.part_hi < p.N ? p.part_hi : p.N;
+  for (int64_t j = p.part_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < j_hi;
        j += (int64_t)gridDim.x * blockDim.x) {
     T acc = (T)0;
     if (p.noise_mode == SNN_NOISE_REPLAY) acc = noise[j];
@@ -740,6 +812,7 @@ class Engine : public IEngine {
     p.rate_mode = cfg_.rate_mode; p.plastic_ei = cfg_.plastic_ei; p.noise_mode = cfg_.noise_mode;
     p.exact = cfg_.mode == SNN_MODE_EXACT;
     p.exp_flags = cfg_.reserved[1];
+    p.part_lo = 0; p.part_hi = p.N;
     p.homeostasis = !(cfg_.theta == 0.0 && cfg_.ttheta == 1.0);
     init_state_kernel<T><<<grid_for(p.Nld), 256, 0, stream_>>>(p);
     SNN_CUDA_OK(cudaGetLastError());
@@ -856,6 +929,21 @@ class Engine : public IEngine {
     return SNN_OK;
   }
 
+  int set_partition(int64_t lo, int64_t hi, snn_exchange_fn fn, void* user, std::string& err) override {
+    if (lo < 0 || hi > p_.N || lo >= hi || (lo % 128) != 0 || (hi % 128 != 0 && hi != p_.N)) {
+      err = "partition bounds must satisfy 0 <= lo < hi <= n_neurons, lo and hi multiples of 128 (hi may be n_neurons)";
+      return SNN_ERR_INVALID;
+    }
+    if (p_.B != 1) { err = "neuron partitioning applies to a single network instance"; return SNN_ERR_INVALID; }
+    const bool whole = lo == 0 && hi == p_.N;
+    if (!whole && !fn) { err = "a partial partition needs an exchange function"; return SNN_ERR_INVALID; }
+    if (t_ != 0) { err = "set the partition before the first step"; return SNN_ERR_STATE; }
+    drop_graph();
+    p_.part_lo = lo; p_.part_hi = hi;
+    exchange_ = whole ? nullptr : fn; exchange_user_ = user;
+    return SNN_OK;
+  }
+
   int64_t n_synapses() const override { return p_.E; }
   int64_t step_index() const override { return t_; }
   void set_profiling(int mode) override { profiling_ = mode; }
@@ -949,12 +1037,14 @@ class Engine : public IEngine {
   }
 
   struct Launch {
-    int gN, gA, gP; dim3 gL;
+    int gN, gA, gP, gR; dim3 gL;
   };
   Launch grids() {
     DevNet<T>& p = p_;
     Launch l;
-    l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 + 255) / 256, (int64_t)n_sm_ * 8));
+    const int64_t local_quads = ((p.part_hi + 3) >> 2) - (p.part_lo >> 2);
+    l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((local_quads + 255) / 256, (int64_t)n_sm_ * 8));
+    l.gR = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 - local_quads + 255) / 256, (int64_t)n_sm_ * 8));
     if (gA_ == 0) {
       int per_sm = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synapse_kernel<T, true, true, true>, 256, 0);
@@ -995,6 +1085,7 @@ class Engine : public IEngine {
   WindowCtx<T>* d_ctx_ = nullptr; WindowCtx<T>* h_ctx_ = nullptr;
   unsigned long long* h_blk_ = nullptr;
   DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_;
+  snn_exchange_fn exchange_ = nullptr; void* exchange_user_ = nullptr; int exchange_failed_ = 0;
   const std::vector<cudaEvent_t>* graph_prof_events_ = nullptr;
   std::vector<CachedGraph> graphs_;  // a few (length, train pattern, profiling) variants
 };
@@ -1026,6 +1117,14 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
       neuron_kernel<T, false, true><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 0);
     } else {
       neuron_kernel<T, true, true><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 1);
+    }
+    if (k < n && exchange_) {
+      // neuron-partitioned run: all-gather this step's spike bitmap, then replay detection for
+      // the neurons owned by the other ranks (traces, spike list, delay-1 pushes)
+      uint32_t* slot_bits = p.bits + (size_t)slot_host(t_ + k) * p.W;
+      const int rc = exchange_(exchange_user_, slot_bits, p.part_lo / 32, (p.part_hi - p.part_lo + 31) / 32, p.W, (void*)s);
+      if (rc != 0) { exchange_failed_ = rc; return; }
+      remote_kernel<T><<<g.gR, 256, 0, s>>>(p, d_ctx_, k);
     }
     if (prof) prof_end(s);
     if (k == n) break;
@@ -1247,13 +1346,19 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   SNN_CUDA_OK(cudaMemsetAsync(p.blk_ltp, 0, kMaxSynBlocks * sizeof(unsigned long long), stream_));
 
   // ---- the window
-  const bool graphable = use_graph_ && !p.exact && a.n_force == 0 && profiling_ != 1;
+  const bool graphable = use_graph_ && !p.exact && a.n_force == 0 && profiling_ != 1 && !exchange_;
   if (graphable) {
     int rc = launch_graph(a, profiling_ == 2, err);
     if (rc) return rc;
   } else {
     prof_used_ = 0; prof_cls_.clear();
+    exchange_failed_ = 0;
     launch_serial(a, force_off, b_force_.as<int32_t>(), profiling_ == 1);
+    if (exchange_failed_) {
+      cudaStreamSynchronize(stream_);
+      err = "bitmap exchange callback failed with code " + std::to_string(exchange_failed_);
+      return SNN_ERR_STATE;
+    }
   }
   SNN_CUDA_OK(cudaGetLastError());
   t_ += n;
