@@ -216,7 +216,8 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
     }
   }
 
-  const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi + 3) >> 2);
+  // whole warps only: the last rank's range is padded up to Nld (padding neurons are inactive)
+  const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2);
   for (uint32_t q = q_lo + blockIdx.x * blockDim.x + threadIdx.x; q < q_hi; q += gridDim.x * blockDim.x) {
     const uint32_t j0 = q << 2;
     // ---- all loads first
@@ -371,7 +372,8 @@ remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
     rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
   }
   T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;
-  const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi + 3) >> 2);
+  // whole warps only: the last rank's range is padded up to Nld (padding neurons are inactive)
+  const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2);
   const uint32_t nquad = (uint32_t)(p.Nld >> 2), n_remote = nquad - (q_hi - q_lo);
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_remote; r += gridDim.x * blockDim.x) {
     const uint32_t q = r < q_lo ? r : r + (q_hi - q_lo);  // part bounds are multiples of 128: warps stay whole
@@ -1042,7 +1044,7 @@ class Engine : public IEngine {
   Launch grids() {
     DevNet<T>& p = p_;
     Launch l;
-    const int64_t local_quads = ((p.part_hi + 3) >> 2) - (p.part_lo >> 2);
+    const int64_t local_quads = ((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2) - (p.part_lo >> 2);
     l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((local_quads + 255) / 256, (int64_t)n_sm_ * 8));
     l.gR = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 - local_quads + 255) / 256, (int64_t)n_sm_ * 8));
     if (gA_ == 0) {
