@@ -40,6 +40,9 @@ WORKLOADS = {
     # name: (neurons, n_exc, fanout, max_delay)
     "c5_1M_100M": (1_000_000, 800_000, 100, 20),
     "c3_10k_1M": (10_000, 8_000, 100, 1),
+    # batched small nets: (neurons per instance, n_exc, fanout, max_delay, instances)
+    "c1_x1024": (1_000, 800, 100, 1, 1024),
+    "c3_x64": (10_000, 8_000, 100, 1, 64),
     "tiny": (20_000, 16_000, 100, 20),
     "c4_actors": None,  # 4096 x LIF [8,8,8] CartPole actors, whole episodes on the device (per GPU: 4096/N)
 }
@@ -50,6 +53,18 @@ B_NEURON = 36      # per neuron per ms
 B_EVENT = 17 + 12  # per synaptic event: propagate 17 + LTD 12
 B_LTP = 20         # per incoming plastic synapse of a spiker
 B_LEARN = 16       # per plastic synapse per learn pass
+
+
+def learn_traffic(workload):
+    """DRAM bytes per learn_kernel launch from the committed `ncu --set full` capture (same workload)."""
+    if workload != "c5_1M_100M":
+        return None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1g_learn_kernel_ncu_full.json")))
+        v = [(float(x["dram__bytes_read.sum"]) + float(x["dram__bytes_write.sum"])) * 1e6 for x in d["launches"]]
+        return sum(v) / len(v)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -128,7 +143,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, ne, fan, dmax = WORKLOADS[args.workload]
+    wl = WORKLOADS[args.workload]
+    n, ne, fan, dmax = wl[:4]
+    n_inst = wl[4] if len(wl) > 4 else 1
     W = args.window_ms
     t_build = time.perf_counter()
     if args.partition and world > 1:
@@ -140,10 +157,11 @@ def run_b200(args):
                               mode="fast", noise="philox", device=local, max_delay=dmax, noise_seed=10)
         n_plastic = int(np.count_nonzero(np.repeat(np.arange(n), np.diff(rowptr))[net.local_index] < ne))
     else:
-        rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9 + rank)
-        net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f32", mode="fast", noise="philox", device=local,
-                            max_delay=dmax, noise_seed=10 + rank, exp_flags=args.exp_flags, graph=not args.no_graph)
-        n_plastic = int(rowptr[ne])
+        rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9 + rank, n_instances=n_inst)
+        net = SparseNetwork(n, ne, rowptr, post, w, delay, n_instances=n_inst, dtype="f32", mode="fast", noise="philox",
+                            device=local, max_delay=dmax, noise_seed=10 + rank, exp_flags=args.exp_flags,
+                            graph=not args.no_graph)
+        n_plastic = int(rowptr[ne]) * n_inst
     del post, w, delay
     t_build = time.perf_counter() - t_build
     lib = L.load()
@@ -228,28 +246,29 @@ def run_b200(args):
         learn_bytes = B_LEARN * n_plastic
         learn_avg_ms = tot["learn_ms"] / max(1, tot["nl"])
         learn_gbs = learn_bytes / (learn_avg_ms * 1e-3) / 1e9 if learn_avg_ms > 0 else 0.0
-        path_bytes = (sim_ms * n * B_NEURON + tot["ev"] * B_EVENT + tot["ltp"] * B_LTP + tot["nl"] * learn_bytes)
+        path_bytes = (sim_ms * n * n_inst * B_NEURON + tot["ev"] * B_EVENT + tot["ltp"] * B_LTP + tot["nl"] * learn_bytes)
         line = {
             "metric": "synaptic events/s", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if (args.partition and world > 1) else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "neurons": n, "synapses": int(rowptr[-1]), "max_delay_ms": dmax,
+            "config": {"workload": args.workload, "neurons": n * n_inst, "synapses": int(rowptr[-1]), "max_delay_ms": dmax,
+                       "instances_per_gpu": n_inst,
                        "window_ms_per_step": W, "learn_period_ms": LEARN_PERIOD, "noise": "on-device Philox4x32-10",
                        "instances": 1 if (args.partition and world > 1) else world,
                        "sharding": ("one network, neurons partitioned over the ranks, NCCL all-gather of the spike "
                                     "bitmap per ms") if (args.partition and world > 1) else
                                    "one independent instance per GPU, no collective",
                        "l2": "working set 2.2 GB per instance >> 126 MB L2 (no flush needed)"},
-            "sim_ms_per_wall_s": sim_ms * (1 if (args.partition and world > 1) else world) / (dev_ms * 1e-3),
+            "sim_ms_per_wall_s": sim_ms * n_inst * (1 if (args.partition and world > 1) else world) / (dev_ms * 1e-3),
             "x_realtime_per_instance": sim_ms / dev_ms,
-            "firing_rate_hz": spikes_all / world / n / (sim_ms * 1e-3),
+            "firing_rate_hz": spikes_all / world / (n * n_inst) / (sim_ms * 1e-3),
             "e2e": {"value": e2e_ev_all / (e2e_ms * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps,
                     "note": "snn_step() with host buffers: train flags + dopamine events in, sorted spike record out"},
             "gpu_launches": tot["nl"] + tot["nn"] + tot["ns"],
             "roofline": {"bound": "hbm", "kernel": "learn_kernel<float>", "achieved": learn_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": learn_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": learn_gbs / peak, "traffic": learn_traffic(args.workload), "peak_source": peak_src,
                          "bytes_per_launch": learn_bytes, "avg_launch_ms": learn_avg_ms,
                          "share_of_step_time": tot["learn_ms"] / dev_ms if dev_ms else None},
             "roofline_path": {"algorithmic_bytes": path_bytes, "achieved": path_bytes / (dev_ms * 1e-3) / 1e9,
@@ -374,7 +393,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n, ne, fan, dmax = WORKLOADS[args.workload if args.workload != "c4_actors" else "c5_1M_100M"]
+    n, ne, fan, dmax = WORKLOADS[args.workload if args.workload != "c4_actors" else "c5_1M_100M"][:4]
     from oracle import py_oracle as po
     from rl_stdp_b200 import synth
     ns = min(n, 50_000)
