@@ -121,6 +121,15 @@ typedef struct snn_force_event {
   int32_t neuron;
 } snn_force_event;
 
+/* injected-current input: before step `step`, neuron `neuron` integrates two Euler half-steps
+ * with the external current `current` (= (imax-imin)*intensity+imin, formed by the caller).
+ * Replaces input!(net, ::Array{Tuple{Int64,Float64}}) net_arch.jl:316-326 / net_res.jl:150-160. */
+typedef struct snn_current_event {
+  int32_t step;
+  int32_t neuron;
+  double current;
+} snn_current_event;
+
 /* fields for snn_get_array / snn_set_array */
 enum {
   SNN_FIELD_V = 0,       /* [n_neurons] real  — Network.v  new_net.jl:9  */
@@ -185,6 +194,24 @@ int32_t snn_step(snn_net* net, int32_t n_steps, const double* noise, const uint8
                  const snn_force_event* force, int32_t n_force, const snn_da_event* da,
                  int32_t n_da, int32_t* spikes_out, int64_t* spike_offsets, int64_t spikes_cap,
                  snn_step_stats* stats);
+
+/* Extensible form of snn_step: every input/output of a window in one struct (zero-initialise,
+ * set struct_size).  Adds injected-current events to what snn_step takes. */
+typedef struct snn_step_io {
+  int32_t struct_size;
+  int32_t n_steps;
+  const double* noise;
+  const uint8_t* train_flags;
+  const snn_force_event* force;
+  const snn_da_event* da;
+  const snn_current_event* currents;  /* sorted by step */
+  int32_t n_force, n_da, n_currents, reserved;
+  int32_t* spikes_out;
+  int64_t* spike_offsets;
+  int64_t spikes_cap;
+  snn_step_stats* stats;
+} snn_step_io;
+int32_t snn_step_ex(snn_net* net, const snn_step_io* io);
 
 /* `net.da += x` (newnet_DASTDP.jl:55, teacher_sim.jl:133, critic_sim.jl:69) */
 int32_t snn_add_dopamine(snn_net* net, int32_t instance, double amount);

@@ -57,6 +57,10 @@ class SnnForceEvent(C.Structure):
     _fields_ = [("step", C.c_int32), ("neuron", C.c_int32)]
 
 
+class SnnCurrentEvent(C.Structure):
+    _fields_ = [("step", C.c_int32), ("neuron", C.c_int32), ("current", C.c_double)]
+
+
 class SnnStepStats(C.Structure):
     _fields_ = [
         ("n_spikes", C.c_int64), ("n_syn_events", C.c_int64), ("n_ltp_events", C.c_int64),
@@ -67,6 +71,16 @@ class SnnStepStats(C.Structure):
 
 
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p)
+
+class SnnStepIO(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("n_steps", C.c_int32), ("noise", C.c_void_p), ("train_flags", C.c_void_p),
+        ("force", C.c_void_p), ("da", C.c_void_p), ("currents", C.c_void_p),
+        ("n_force", C.c_int32), ("n_da", C.c_int32), ("n_currents", C.c_int32), ("reserved", C.c_int32),
+        ("spikes_out", C.c_void_p), ("spike_offsets", C.c_void_p), ("spikes_cap", C.c_int64),
+        ("stats", C.POINTER(SnnStepStats)),
+    ]
+
 
 # every symbol of include/snn_b200.h: name -> (restype, argtypes)
 _VP = C.c_void_p
@@ -80,6 +94,7 @@ SYMBOLS = {
     "snn_set_synapses_dense": (C.c_int32, [_VP, _VP, _VP]),
     "snn_step": (C.c_int32, [_VP, C.c_int32, _VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP, _VP, C.c_int64,
                              C.POINTER(SnnStepStats)]),
+    "snn_step_ex": (C.c_int32, [_VP, C.POINTER(SnnStepIO)]),
     "snn_add_dopamine": (C.c_int32, [_VP, C.c_int32, C.c_double]),
     "snn_reset_v": (C.c_int32, [_VP]),
     "snn_get_array": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int64]),

@@ -126,11 +126,29 @@ int32_t snn_step(snn_net* net, int32_t n_steps, const double* noise, const uint8
   if (!net) return fail(SNN_ERR_INVALID, "null net");
   if ((n_force > 0 && !force) || (n_da > 0 && !da) || n_force < 0 || n_da < 0)
     return fail(SNN_ERR_INVALID, "event list pointer / count mismatch");
-  snn::StepArgs a{n_steps, noise, train_flags, force, n_force, da, n_da, spikes_out, spike_offsets, spikes_cap, stats};
+  snn::StepArgs a;
+  a.n_steps = n_steps; a.noise = noise; a.train_flags = train_flags; a.force = force; a.n_force = n_force;
+  a.da = da; a.n_da = n_da; a.spikes_out = spikes_out; a.spike_offsets = spike_offsets; a.spikes_cap = spikes_cap;
+  a.stats = stats;
   std::string err;
   int rc = net->eng->step(a, err);
   if (rc) return fail(rc, err);
   return SNN_OK;
+}
+
+int32_t snn_step_ex(snn_net* net, const snn_step_io* io) {
+  if (!net || !io) return fail(SNN_ERR_INVALID, "null argument");
+  if (io->struct_size != (int32_t)sizeof(snn_step_io)) return fail(SNN_ERR_INVALID, "snn_step_io.struct_size mismatch (ABI)");
+  if ((io->n_force > 0 && !io->force) || (io->n_da > 0 && !io->da) || (io->n_currents > 0 && !io->currents) ||
+      io->n_force < 0 || io->n_da < 0 || io->n_currents < 0)
+    return fail(SNN_ERR_INVALID, "event list pointer / count mismatch");
+  snn::StepArgs a;
+  a.n_steps = io->n_steps; a.noise = io->noise; a.train_flags = io->train_flags; a.force = io->force;
+  a.n_force = io->n_force; a.da = io->da; a.n_da = io->n_da; a.cur = io->currents; a.n_cur = io->n_currents;
+  a.spikes_out = io->spikes_out; a.spike_offsets = io->spike_offsets; a.spikes_cap = io->spikes_cap; a.stats = io->stats;
+  std::string err;
+  int rc = net->eng->step(a, err);
+  return rc ? fail(rc, err) : SNN_OK;
 }
 
 int32_t snn_add_dopamine(snn_net* net, int32_t instance, double amount) {

@@ -53,6 +53,8 @@ struct StepArgs {
   int32_t n_force;
   const snn_da_event* da;
   int32_t n_da;
+  const snn_current_event* cur = nullptr;
+  int32_t n_cur = 0;
   int32_t* spikes_out;
   int64_t* spike_offsets;
   int64_t spikes_cap;

@@ -422,6 +422,26 @@ __global__ void force_kernel(DevNet<T> p, const int32_t* __restrict__ idx, int n
   if (q < n) p.v[idx[q]] = (T)40.0;
 }
 
+// input!(net, ::Array{Tuple{Int64,Float64}}) net_arch.jl:316-326: two Euler half-steps of v[idx]
+// with the injected current only (I is zeroed again by spike!, :330)
+template <typename T>
+__global__ void current_kernel(DevNet<T> p, const int32_t* __restrict__ idx, const double* __restrict__ cur, int n) {
+  typedef Ops<T> O;
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int32_t j = idx[q];
+  const T I = (T)cur[q], u = p.u[j];
+  T v = p.v[j];
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    T x = O::add(O::mul((T)0.04, v), (T)5);
+    x = O::add(O::mul(x, v), (T)140);
+    x = O::add(O::sub(x, u), I);
+    v = O::add(v, O::mul((T)0.5, x));
+  }
+  p.v[j] = v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // exact mode: I[j] = noise[j] + sum over spiking sources in ascending presynaptic id — the
 // accumulation order of `for neuron in spiked: I .+= s[neuron,:]` (new_net.jl:116-118).
@@ -1001,7 +1021,7 @@ class Engine : public IEngine {
     if (h_ctx_) cudaFreeHost(h_ctx_);
     if (h_blk_) cudaFreeHost(h_blk_);
     b_noise_.release(); b_noise64_.release(); b_ev_off_.release(); b_ev_inst_.release(); b_ev_amt_.release();
-    b_force_.release(); b_rec_.release(); b_rec_off_.release();
+    b_force_.release(); b_rec_.release(); b_rec_off_.release(); b_cur_idx_.release(); b_cur_val_.release();
     topo_.release();
     if (ev_begin_) cudaEventDestroy(ev_begin_);
     if (ev_end_) cudaEventDestroy(ev_end_);
@@ -1067,7 +1087,8 @@ class Engine : public IEngine {
     *do_decay = (decay_step || (train && cfg_.sd_decay_mode == SNN_SD_DECAY_ON_LEARN)) ? 1 : 0;
     return (train || decay_step) && p_.E > 0 && p_.Ne > 0;
   }
-  void launch_serial(const StepArgs& a, const std::vector<int32_t>& force_off, const int32_t* d_force, bool prof);
+  void launch_serial(const StepArgs& a, const std::vector<int32_t>& force_off, const int32_t* d_force,
+                     const std::vector<int32_t>& cur_off, const int32_t* d_cur_idx, const double* d_cur_val, bool prof);
   int launch_graph(const StepArgs& a, bool prof, std::string& err);
 
   snn_config cfg_;
@@ -1086,7 +1107,7 @@ class Engine : public IEngine {
   size_t prof_used_ = 0;
   WindowCtx<T>* d_ctx_ = nullptr; WindowCtx<T>* h_ctx_ = nullptr;
   unsigned long long* h_blk_ = nullptr;
-  DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_;
+  DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_, b_cur_idx_, b_cur_val_;
   snn_exchange_fn exchange_ = nullptr; void* exchange_user_ = nullptr; int exchange_failed_ = 0;
   const std::vector<cudaEvent_t>* graph_prof_events_ = nullptr;
   std::vector<CachedGraph> graphs_;  // a few (length, train pattern, profiling) variants
@@ -1095,6 +1116,7 @@ class Engine : public IEngine {
 // Plain stream-ordered launches: exact mode, forced spikes, per-kernel profiling.
 template <typename T>
 void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& force_off, const int32_t* d_force,
+                              const std::vector<int32_t>& cur_off, const int32_t* d_cur_idx, const double* d_cur_val,
                               bool prof) {
   DevNet<T>& p = p_;
   const int n = a.n_steps;
@@ -1103,10 +1125,15 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
   // production mode: arrivals of window step 0 that are already in flight (spikes of earlier windows)
   if (!p.exact) synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s>>>(p, d_ctx_, -1, g_arr_log2_);
   for (int k = 0; k <= n; ++k) {
-    const bool forced = k < n && force_off[k + 1] > force_off[k];
+    const int nf = k < n ? force_off[k + 1] - force_off[k] : 0, nc = k < n ? cur_off[k + 1] - cur_off[k] : 0;
+    const bool forced = nf > 0 || nc > 0;
+    auto inputs = [&]() {  // input! of this step: forced spikes, then injected currents
+      if (nf > 0) force_kernel<T><<<(nf + 255) / 256, 256, 0, s>>>(p, d_force + force_off[k], nf);
+      if (nc > 0) current_kernel<T><<<(nc + 255) / 256, 256, 0, s>>>(p, d_cur_idx + cur_off[k], d_cur_val + cur_off[k], nc);
+    };
     if (prof) prof_begin(0, s);
     if (k == 0) {
-      if (forced) force_kernel<T><<<(force_off[1] - force_off[0] + 255) / 256, 256, 0, s>>>(p, d_force + force_off[0], force_off[1] - force_off[0]);
+      if (forced) inputs();
       neuron_kernel<T, false, true><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 1);
     } else if (k == n) {
       neuron_kernel<T, true, false><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 1);
@@ -1114,8 +1141,7 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
       // events of step k-1 must enter before the decay of step k: fold them into da[t&1] in
       // place (no learn kernel is in flight on this serial path), then detect with decay only
       neuron_kernel<T, true, false><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 1);
-      const int nf = force_off[k + 1] - force_off[k];
-      force_kernel<T><<<(nf + 255) / 256, 256, 0, s>>>(p, d_force + force_off[k], nf);
+      inputs();
       neuron_kernel<T, false, true><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 0);
     } else {
       neuron_kernel<T, true, true><<<g.gN, 256, 0, s>>>(p, d_ctx_, k, 1);
@@ -1306,6 +1332,20 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     }
     for (int k = 0; k < n; ++k) force_off[k + 1] += force_off[k];
   }
+  std::vector<int32_t> cur_off(n + 1, 0), cur_ids;
+  std::vector<double> cur_val;
+  if (a.n_cur > 0) {
+    cur_ids.resize(a.n_cur); cur_val.resize(a.n_cur);
+    int prev = -1;
+    for (int q = 0; q < a.n_cur; ++q) {
+      const snn_current_event& e = a.cur[q];
+      if (e.step < 0 || e.step >= n || e.step < prev || e.neuron < 0 || e.neuron >= N) {
+        err = "current events must be sorted by step, inside the window, neuron in range"; return SNN_ERR_INVALID;
+      }
+      prev = e.step; cur_off[e.step + 1]++; cur_ids[q] = e.neuron; cur_val[q] = e.current;
+    }
+    for (int k = 0; k < n; ++k) cur_off[k + 1] += cur_off[k];
+  }
   SNN_CUDA_OK(cudaEventRecord(ev_begin_, stream_));
   WindowCtx<T>& cx = *h_ctx_;
   memset(&cx, 0, sizeof(cx));
@@ -1335,6 +1375,12 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     SNN_CUDA_OK(b_force_.reserve(a.n_force * sizeof(int32_t)));
     SNN_CUDA_OK(cudaMemcpyAsync(b_force_.ptr, force_ids.data(), a.n_force * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
   }
+  if (a.n_cur > 0) {
+    SNN_CUDA_OK(b_cur_idx_.reserve(a.n_cur * sizeof(int32_t)));
+    SNN_CUDA_OK(b_cur_val_.reserve(a.n_cur * sizeof(double)));
+    SNN_CUDA_OK(cudaMemcpyAsync(b_cur_idx_.ptr, cur_ids.data(), a.n_cur * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    SNN_CUDA_OK(cudaMemcpyAsync(b_cur_val_.ptr, cur_val.data(), a.n_cur * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  }
   if (a.spikes_out) {
     SNN_CUDA_OK(b_rec_.reserve(a.spikes_cap * sizeof(int32_t)));
     SNN_CUDA_OK(b_rec_off_.reserve((n + 1) * sizeof(int32_t)));
@@ -1348,14 +1394,15 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   SNN_CUDA_OK(cudaMemsetAsync(p.blk_ltp, 0, kMaxSynBlocks * sizeof(unsigned long long), stream_));
 
   // ---- the window
-  const bool graphable = use_graph_ && !p.exact && a.n_force == 0 && profiling_ != 1 && !exchange_;
+  const bool graphable = use_graph_ && !p.exact && a.n_force == 0 && a.n_cur == 0 && profiling_ != 1 && !exchange_;
   if (graphable) {
     int rc = launch_graph(a, profiling_ == 2, err);
     if (rc) return rc;
   } else {
     prof_used_ = 0; prof_cls_.clear();
     exchange_failed_ = 0;
-    launch_serial(a, force_off, b_force_.as<int32_t>(), profiling_ == 1);
+    launch_serial(a, force_off, b_force_.as<int32_t>(), cur_off, b_cur_idx_.as<int32_t>(), b_cur_val_.as<double>(),
+                  profiling_ == 1);
     if (exchange_failed_) {
       cudaStreamSynchronize(stream_);
       err = "bitmap exchange callback failed with code " + std::to_string(exchange_failed_);

@@ -93,10 +93,11 @@ class SparseNetwork:
 
     # -- step!(net[, input_spikes], train) for a whole window
     def run(self, n_steps, noise=None, train=None, da_events=None, force=None, record=True,
-            spikes_cap=None, profile=False):
+            spikes_cap=None, profile=False, currents=None):
         """Runs n_steps milliseconds on the device.  noise: [n_steps, n_neurons] float64 or None;
         train: bool array [n_steps] (learn! after that step); da_events: [(step, instance,
-        amount)]; force: [(step, neuron)].  Returns (list of ascending spike-id arrays, stats)."""
+        amount)]; force: [(step, neuron)]; currents: [(step, neuron, current)] (injected-current
+        input!).  Returns (list of ascending spike-id arrays, stats)."""
         lib = L.load()
         n_steps = int(n_steps)
         if noise is not None:
@@ -123,8 +124,26 @@ class SparseNetwork:
         st = L.SnnStepStats()
         # profile: False | 'kernels' (events around every kernel class, serial launches) | 'learn'
         lib.snn_set_profiling(self._h, {False: 0, None: 0, True: 1, 'kernels': 1, 'learn': 2}[profile])
-        rc = lib.snn_step(self._h, n_steps, _ptr(noise), _ptr(tf), fe, n_force, ev, n_da, _ptr(out), _ptr(offs),
-                          cap, C.byref(st))
+        if currents:
+            n_cur = len(currents)
+            ce = (L.SnnCurrentEvent * n_cur)(*[L.SnnCurrentEvent(int(s_), int(j), float(c)) for s_, j, c in currents])
+            io = L.SnnStepIO()
+            io.struct_size = C.sizeof(L.SnnStepIO)
+            io.n_steps = n_steps
+            io.noise = None if noise is None else noise.ctypes.data
+            io.train_flags = None if tf is None else tf.ctypes.data
+            io.force = C.cast(fe, C.c_void_p) if fe is not None else None
+            io.da = C.cast(ev, C.c_void_p) if ev is not None else None
+            io.currents = C.cast(ce, C.c_void_p)
+            io.n_force, io.n_da, io.n_currents = n_force, n_da, n_cur
+            io.spikes_out = None if out is None else out.ctypes.data
+            io.spike_offsets = None if offs is None else offs.ctypes.data
+            io.spikes_cap = cap
+            io.stats = C.pointer(st)
+            rc = lib.snn_step_ex(self._h, C.byref(io))
+        else:
+            rc = lib.snn_step(self._h, n_steps, _ptr(noise), _ptr(tf), fe, n_force, ev, n_da, _ptr(out), _ptr(offs),
+                              cap, C.byref(st))
         L.check(rc)
         stats = StepStats(st.n_spikes, st.n_syn_events, st.n_ltp_events, st.device_ms, st.learn_ms, st.neuron_ms,
                           st.synapse_ms, st.learn_launches, st.neuron_launches, st.synapse_launches)

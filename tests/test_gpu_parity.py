@@ -316,3 +316,50 @@ def test_fast_scheduler_bitexact_with_frozen_weights(graph):
     assert np.count_nonzero(sd_o) > 1000
     assert np.array_equal(net.get(L.FIELD_V), ora.get(0))
     assert np.array_equal(net.get(L.FIELD_TRACE), ora.get(2))
+
+
+def test_variant_e_layered_izhikevich_exact():
+    """Variant E (net_arch.jl:316-379): layered Izhikevich net with forced-spike and injected-current
+    inputs, homeostasis beyond layer 1, lateral inhibition partners, `e += da*de` learning with an
+    undecayed `de` — on the sparse CUDA engine, bit-exact against the layered oracle."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200.layered import LayeredNetwork
+    rng = np.random.Generator(np.random.Philox(key=101))
+    arch = [12, 10, 6]
+    param = dict(po.CARTPOLE_CFGLIF)
+    param.update(vthresh=30.0, c=-65.0, theta=2.0, ttheta=0.9999, wei=3.0, wie=-2.0, wmax=20.0, imin=0.0, imax=20.0,
+                 apost=1.0, apre=1.5, ttrace=0.95, tda=0.995)
+    e0 = [np.clip(rng.standard_normal((arch[l], arch[l + 1])) * 2 + 8, 0, 20.0) for l in range(2)]
+    ora = po.Layered(arch, "izh", **param)
+    for l in range(2):
+        ora.e(l)[:, :] = e0[l]
+    net = LayeredNetwork(arch, param, e0)
+    tot = 0
+    for t in range(400):
+        train = t % 10 == 9
+        if t % 3 == 0:
+            idx = rng.choice(arch[0], size=3, replace=False)
+            inten = rng.random(3)
+            a = ora.step_izh(idx, inten, train=train)
+            b = net.step([(int(i), float(x)) for i, x in zip(idx, inten)], train)
+        elif t % 3 == 1:
+            idx = rng.choice(arch[0], size=2, replace=False)
+            a = ora.step_izh(idx, None, train=train)
+            b = net.step([int(i) for i in idx], train)
+        else:
+            a = ora.step_izh(None, None, train=train)
+            b = net.step(None, train)
+        assert np.array_equal(a, b), t
+        tot += len(a)
+        if t % 40 == 0:
+            ora.da = ora.da + 0.1
+            net.da = net.da + 0.1
+    assert tot > 100
+    assert np.array_equal(net.v, ora.v) and np.array_equal(net.u, ora.u) and np.array_equal(net.ho, ora.ho)
+    assert np.array_equal(net.trace_e, ora.trace_e) and net.da == ora.da
+    changed = 0
+    for l in range(2):
+        assert np.array_equal(net.e(l), ora.e(l)), l
+        assert np.array_equal(net.de(l), ora.de(l)), l
+        changed += int(np.any(ora.e(l) != e0[l]))
+    assert changed == 2
