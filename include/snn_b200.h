@@ -100,7 +100,13 @@ typedef struct snn_config {
   double theta;            /* homeostasis increment (0 = off)  net_res.jl:171 */
   double ttheta;           /* homeostasis decay                net_res.jl:204 */
   int64_t ho_from;         /* local ids >= ho_from (and < n_exc) get homeostasis (arch[1]) */
-  int32_t reserved[8];     /* reserved[0] = 1 disables the CUDA-graph scheduler (A/B testing) */
+  int32_t reserved[8];     /* tuning / A-B switches, 0 = default:
+                              [0] = 1 disables the CUDA-graph scheduler (plain launches)
+                              [1] experiment flags (bit 1: kernel timeline for snn_debug_timeline)
+                              [2] asynchronous learn pass: resident blocks per SM
+                              [4] learn pass: 0 auto (asynchronous on large nets), 1 always in place,
+                                  2 always asynchronous
+                              [5] asynchronous learn pass: total entries of the sd-update log */
 } snn_config;
 
 typedef struct snn_net snn_net;
@@ -243,6 +249,12 @@ int32_t snn_set_partition(snn_net* net, int64_t neuron_lo, int64_t neuron_hi, sn
  * 1: CUDA events around every kernel class, plain stream-ordered launches (diagnostics).
  * 2: the CUDA-graph path with events around the learn_kernel launches only (bench.py roofline). */
 int32_t snn_set_profiling(snn_net* net, int32_t enable);
+/* Diagnostics (snn_config.reserved[1] & 2): %globaltimer stamps (ns) of the last window's kernels,
+ * out[2][SNN_TL_CLASSES][SNN_TL_STEPS]: [0] = first block start, [1] = last block end; class
+ * 0 neuron, 1 synapse, 2 ltp, 3 learn, 4 remote, 5 push-only synapse; index = window step + 1. */
+#define SNN_TL_CLASSES 6
+#define SNN_TL_STEPS 258
+int32_t snn_debug_timeline(snn_net* net, uint64_t* out, int64_t count);
 /* Use an externally owned CUDA stream (cudaStream_t) instead of the net's own. */
 int32_t snn_set_stream(snn_net* net, void* cuda_stream);
 

@@ -19,6 +19,7 @@ SNN_SD_DECAY_ON_LEARN, SNN_SD_DECAY_EVERY_STEP, SNN_SD_DECAY_NEVER = 0, 1, 2
 SNN_RATE_BASE_PLUS_DA, SNN_RATE_DA, SNN_RATE_ETA_DA = 0, 1, 2
 (FIELD_V, FIELD_U, FIELD_TRACE, FIELD_HO, FIELD_W, FIELD_SD, FIELD_DA, FIELD_I) = range(8)
 SNN_ERR_CAPACITY = -5
+SNN_TL_CLASSES, SNN_TL_STEPS = 6, 258
 
 
 class SnnConfig(C.Structure):
@@ -103,6 +104,7 @@ SYMBOLS = {
     "snn_step_index": (C.c_int64, [_VP]),
     "snn_set_profiling": (C.c_int32, [_VP, C.c_int32]),
     "snn_set_stream": (C.c_int32, [_VP, _VP]),
+    "snn_debug_timeline": (C.c_int32, [_VP, _VP, C.c_int64]),
     "snn_set_partition": (C.c_int32, [_VP, C.c_int64, C.c_int64, _VP, _VP]),
     # batched LIF actors
     "snn_actor_config_default": (C.c_int32, [C.POINTER(SnnActorConfig)]),

@@ -195,6 +195,13 @@ int32_t snn_set_profiling(snn_net* net, int32_t enable) {
   return SNN_OK;
 }
 
+int32_t snn_debug_timeline(snn_net* net, uint64_t* out, int64_t count) {
+  if (!net || !out) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->get_timeline((unsigned long long*)out, count, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
 int32_t snn_set_stream(snn_net* net, void* cuda_stream) {
   if (!net) return fail(SNN_ERR_INVALID, "null net");
   net->eng->set_stream((cudaStream_t)cuda_stream);

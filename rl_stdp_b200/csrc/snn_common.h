@@ -72,6 +72,7 @@ class IEngine {
   virtual int add_dopamine(int instance, double amount, std::string& err) = 0;
   virtual int reset_v(std::string& err) = 0;
   virtual int set_partition(int64_t lo, int64_t hi, snn_exchange_fn fn, void* user, std::string& err) = 0;
+  virtual int get_timeline(unsigned long long* host, int64_t count, std::string& err) = 0;
   virtual int64_t n_synapses() const = 0;
   virtual int64_t step_index() const = 0;
   virtual void set_profiling(int mode) = 0;

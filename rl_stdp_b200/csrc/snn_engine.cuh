@@ -38,6 +38,7 @@
 // WindowCtx, so one instantiated graph serves every window with the same length and train-flag
 // pattern.  Exact mode, forced spikes and per-kernel profiling use plain stream-ordered launches.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -50,6 +51,7 @@
 
 namespace snn {
 
+template <typename T> struct LogEntry { uint32_t e; T d; };
 template <typename T> struct Real2;
 template <> struct Real2<float> { typedef float2 type; };
 template <> struct Real2<double> { typedef double2 type; };
@@ -92,6 +94,20 @@ __device__ __forceinline__ double philox_noise(uint64_t seed, int64_t t, int64_t
 
 constexpr int kMaxSynBlocks = 148 * 16 * 2;
 
+// State of the asynchronous learn pass.  `state` packs (cur << 31) | frontier, frontier in units
+// of 32 synapses: synapses with (e >> 5) < frontier have been processed by the pass in flight
+// (their post-learn (w, sd) is in wsdX[cur]); the others are still only valid in wsdX[cur^1],
+// which stays frozen until the pass and its log replay are over.  kFrontAll = no pass in flight.
+struct LearnCtl {
+  uint32_t state;
+  uint32_t epoch;      // pass counter: tile_done[t] == epoch <=> tile t of the pass in flight is written
+  uint32_t next_tile;  // tile dispenser of the persistent pass kernel
+  uint32_t spilled;    // some sd update went to the dense spill (a log region was full)
+};
+constexpr uint32_t kFrontAll = 0x7fffffffu;
+constexpr uint32_t kTileSyn = 32768;   // default synapses per tile of the learn pass (multiple of 1024)
+constexpr uint32_t kLogStride = 32;    // log counters are 128 B apart (per-block addresses, no contention)
+
 // Network state + parameters, passed to the kernels by value.
 template <typename T>
 struct DevNet {
@@ -109,7 +125,21 @@ struct DevNet {
   // synapses (internal order: ascending pre, delay, caller position)
   const uint32_t* seg;   // [N][Dmax+1] delay-segment table
   const int32_t* post;   // [E]
-  T2* wsd;               // [E] (w, sd) interleaved: one 8-byte access serves propagate + LTD
+  T2* wsd;               // = wsdX[0]; [E] (w, sd) interleaved: one 8-byte access serves propagate + LTD
+  // asynchronous learn pass (production mode): the pass reads wsdX[cur^1] (frozen) and writes
+  // wsdX[cur] while the following steps keep running; see LearnCtl
+  T2* wsdX[2];
+  LearnCtl* lc;          // device-side pass state
+  T* lg;                 // [B] learn rate (base+da | da | eta*da) of the pass in flight
+  // sd updates that hit not-yet-processed synapses while a pass is in flight: one private log
+  // region per (kernel, block) — a single shared append counter serialises in L2 at ~1 atomic/clk
+  LogEntry<T>* dlog;     // [log_regions][log_region_cap]
+  uint32_t* log_cnt;     // [log_regions * kLogStride]
+  T* dsd;                // [E] dense spill of the same when a region is full (never in practice)
+  uint32_t log_regions, log_region_cap, log_ltp_base;
+  uint32_t* tile_done;   // [n_tiles]
+  const uint32_t *inst_lo, *inst_hi;  // [B] plastic synapse range of every instance
+  uint32_t n_tiles, tile_syn;
   const uint32_t *colptr, *col_npl, *in_syn, *in_pre;
   // counters[0] = spikes, [1] = synaptic events (exact mode); per-block partial sums otherwise
   unsigned long long* counters;
@@ -125,7 +155,24 @@ struct DevNet {
   // neuron partition (multi-GPU): this rank integrates neurons [part_lo, part_hi)
   // and holds every synapse whose POST is in that range; spike bitmaps are exchanged per step
   int64_t part_lo, part_hi;
+  // diagnostics (exp_flags & 2): per-node first-block-start / last-block-end %globaltimer stamps
+  unsigned long long* tl;
 };
+
+// timeline classes: 0 neuron, 1 synapse, 2 ltp, 3 learn, 4 remote, 5 other
+constexpr int kTlSteps = 258, kTlClasses = 6;
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_begin(unsigned long long* tl, int cls, int k) {
+  if (tl && threadIdx.x == 0 && k + 1 >= 0 && k + 1 < kTlSteps) atomicMin(&tl[cls * kTlSteps + k + 1], gtime_ns());
+}
+__device__ __forceinline__ void tl_end(unsigned long long* tl, int cls, int k) {
+  if (tl && threadIdx.x == 0 && k + 1 >= 0 && k + 1 < kTlSteps)
+    atomicMax(&tl[kTlClasses * kTlSteps + cls * kTlSteps + k + 1], gtime_ns());
+}
 
 // Per-window inputs/outputs.  Lives in device memory so that a captured graph never has to be
 // re-parameterised: kernels receive (net, ctx pointer, k) and derive everything else.
@@ -158,6 +205,71 @@ __device__ __forceinline__ void st4(double* p, const Vec4<double>& v) {
 __device__ __forceinline__ int wrap_slot(int s, int R) { return s >= R ? s - R : (s < 0 ? s + R : s); }
 
 // ---------------------------------------------------------------------------------------------
+// View of the (w, sd) storage while a learn pass may be in flight.  Read ONCE per kernel: a stale
+// (smaller) frontier is always safe — the synapse is then simply treated as not yet processed.
+// All accesses go to L2 (ld.cg / red): the L1 of this SM may not see another kernel's writes.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct WView {
+  typename Real2<T>::type* cur;        // post-learn values of processed synapses; all non-plastic ones
+  const typename Real2<T>::type* old;  // frozen pre-learn values (valid for every synapse)
+  uint32_t front;                      // in units of 32 synapses
+};
+template <typename T>
+__device__ __forceinline__ WView<T> wview(const DevNet<T>& p) {
+  const uint32_t s = *reinterpret_cast<const volatile uint32_t*>(&p.lc->state);
+  WView<T> v;
+  v.cur = p.wsdX[s >> 31];
+  v.old = p.wsdX[(s >> 31) ^ 1u];
+  v.front = (p.exp_flags & 16) ? kFrontAll : (s & kFrontAll);  // experiment 16: ignore the frontier (wrong numerics)
+  return v;
+}
+__device__ __forceinline__ float ldcg_x(const float2* q) { return __ldcg(reinterpret_cast<const float*>(q)); }
+__device__ __forceinline__ double ldcg_x(const double2* q) { return __ldcg(reinterpret_cast<const double*>(q)); }
+// weight of synapse e as learn! leaves it: already written by the pass, or formed on the fly from
+// the frozen (w, sd) with the pass's rate (new_net.jl:137-138).  Two phases so that callers can
+// keep several independent loads in flight: w_fetch issues the load, w_resolve finishes.
+// `row_exc`: the presynaptic neuron is excitatory (only those rows can be plastic).
+template <typename T>
+__device__ __forceinline__ typename Real2<T>::type w_fetch(const WView<T>& vw, uint32_t e, bool row_exc, bool& fly) {
+  fly = row_exc && (e >> 5) >= vw.front;
+  typename Real2<T>::type ws;
+  if (fly) ws = __ldcg(vw.old + e);
+  else { ws.x = ldcg_x(vw.cur + e); ws.y = (T)0; }
+  return ws;
+}
+template <typename T>
+__device__ __forceinline__ T w_resolve(const DevNet<T>& p, const typename Real2<T>::type& ws, bool fly, bool plastic,
+                                       uint32_t inst) {
+  if (!(fly && plastic)) return ws.x;  // non-plastic weights never change: both buffers hold them
+  const T x = Ops<T>::add(ws.x, Ops<T>::mul(p.lg[inst], ws.y));
+  return x > p.wmax ? p.wmax : (x < p.wmin ? p.wmin : x);
+}
+// sd[e] += delta (production mode: unordered reductions).  A synapse the pass in flight has not
+// reached keeps its frozen sd: the update is logged (region = this block's private log) and
+// replayed onto the post-learn value.
+template <typename T>
+__device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, uint32_t e, T delta, uint32_t region) {
+  if ((e >> 5) < vw.front) {
+    atomicAdd(&vw.cur[e].y, delta);
+    return;
+  }
+  namespace cg = cooperative_groups;
+  cg::coalesced_group g = cg::coalesced_threads();
+  uint32_t base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(&p.log_cnt[(size_t)region * kLogStride], (uint32_t)g.size());
+  base = g.shfl(base, 0);
+  const uint32_t pos = base + g.thread_rank();
+  if (pos < p.log_region_cap) {
+    LogEntry<T> le; le.e = e; le.d = delta;
+    p.dlog[(size_t)region * p.log_region_cap + pos] = le;
+  } else {
+    atomicAdd(&p.dsd[e], delta);
+    p.lc->spilled = 1u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1 neuron_kernel: [Euler(t-1)] + [detect(t)]   (new_net.jl:111-114,120-123,130-131;
 // homeostasis net_res.jl:167-171,204)
 //   EULER : I = noise(t-1) + Iacc ; two half-steps of v ; u update ; Iacc cleared
@@ -172,6 +284,11 @@ template <typename T, bool EULER, bool DETECT>
 __global__ void __launch_bounds__(256)
 neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev) {
   typedef Ops<T> O;
+  // programmatic dependent launch (no-ops unless the launch carries the attribute): let the next
+  // kernel of the chain be launched now, and wait here for the previous one to complete and flush
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  tl_begin(p.tl, 0, k);
   const int lane = threadIdx.x & 31;
   const int64_t t = cx->t0 + k;
   const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
@@ -192,6 +309,8 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
   T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;         // receives the pushes of step t
   const T* __restrict__ noise_prev = (EULER && cx->noise) ? cx->noise + (size_t)(k - 1) * p.N : nullptr;
   const uint32_t N = (uint32_t)p.N, Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
+  WView<T> vw;
+  if (DETECT) vw = wview(p);
 
   // dopamine (new_net.jl:131 da *= 0.995 ; newnet_DASTDP.jl:54-56 da += 0.5 after step!)
   if (blockIdx.x == 0) {
@@ -322,18 +441,24 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
                 const int src = __ffs(mm) - 1; mm &= mm - 1;
                 const uint32_t i = __shfl_sync(0xffffffffu, j0, src) + c;
                 const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1)], s1 = p.seg[(size_t)i * (p.Dmax + 1) + 1];
+                const uint32_t inst = p.B == 1 ? 0u : i / Nper, ibase = inst * Nper;
+                const bool row_exc = (i - ibase) < Ne;
                 // four loads in flight per lane before the first reduction (an inhibitory row has
                 // ~100 delay-1 synapses; one round trip instead of four)
                 for (uint32_t e0 = s0 + lane; e0 < s1; e0 += 128) {
-                  int32_t pj[4]; T pw[4];
+                  int32_t pj[4]; typename DevNet<T>::T2 pw[4]; bool fly[4];
 #pragma unroll
                   for (int q4 = 0; q4 < 4; ++q4) {
                     const uint32_t e = e0 + 32 * q4;
                     pj[q4] = e < s1 ? p.post[e] : -1;
-                    pw[q4] = e < s1 ? p.wsd[e].x : (T)0;
+                    fly[q4] = false;
+                    if (e < s1) pw[q4] = w_fetch<T>(vw, e, row_exc, fly[q4]);
                   }
 #pragma unroll
-                  for (int q4 = 0; q4 < 4; ++q4) if (pj[q4] >= 0) atomicAdd(&I_now[pj[q4]], pw[q4]);
+                  for (int q4 = 0; q4 < 4; ++q4)
+                    if (pj[q4] >= 0)
+                      atomicAdd(&I_now[pj[q4]],
+                                w_resolve<T>(p, pw[q4], fly[q4], p.plastic_ei || ((uint32_t)pj[q4] - ibase) < Ne, inst));
                 }
               }
             }
@@ -344,6 +469,7 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
     st4(p.v + j0, v);
     st4(p.u + j0, u);
   }
+  tl_end(p.tl, 0, k);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -357,6 +483,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
   typedef Ops<T> O;
+  tl_begin(p.tl, 4, k);
   const int lane = threadIdx.x & 31;
   const int64_t t = cx->t0 + k;
   const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
@@ -372,6 +499,7 @@ remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
     rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
   }
   T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;
+  const WView<T> vw = wview(p);
   // whole warps only: the last rank's range is padded up to Nld (padding neurons are inactive)
   const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2);
   const uint32_t nquad = (uint32_t)(p.Nld >> 2), n_remote = nquad - (q_hi - q_lo);
@@ -406,13 +534,20 @@ remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
               const int src = __ffs(mm) - 1; mm &= mm - 1;
               const uint32_t i = __shfl_sync(0xffffffffu, j0, src) + c;
               const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1)], s1 = p.seg[(size_t)i * (p.Dmax + 1) + 1];
-              for (uint32_t e = s0 + lane; e < s1; e += 32) atomicAdd(&I_now[p.post[e]], p.wsd[e].x);
+              const bool row_exc = i < (uint32_t)p.Ne;  // partitioned runs are single-instance
+              for (uint32_t e = s0 + lane; e < s1; e += 32) {
+                const uint32_t j = (uint32_t)p.post[e];
+                bool fly;
+                const typename DevNet<T>::T2 ws = w_fetch<T>(vw, e, row_exc, fly);
+                atomicAdd(&I_now[j], w_resolve<T>(p, ws, fly, p.plastic_ei || j < (uint32_t)p.Ne, 0u));
+              }
             }
           }
         }
       }
     }
   }
+  tl_end(p.tl, 4, k);
 }
 
 // v[idx] = 40 (input! new_net.jl:104-106)
@@ -453,6 +588,7 @@ gather_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
   const int64_t t = cx->t0 + k;
   const int slot = (cx->slot0 + k) % p.R;
   const T* __restrict__ noise = cx->noise ? cx->noise + (size_t)k * p.N : nullptr;
+  const typename DevNet<T>::T2* __restrict__ wsd = wview(p).cur;
   const int64_t j_hi = p.part_hi < p.N ? p.part_hi : p.N;
   for (int64_t j = p.part_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < j_hi;
        j += (int64_t)gridDim.x * blockDim.x) {
@@ -465,7 +601,7 @@ gather_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
       const uint32_t i = pk & kPreMask;
       const int sl = wrap_slot(slot - (int)(pk >> kPreBits), p.R);
       const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
-      if ((word >> (i & 31)) & 1u) acc = O::add(acc, p.wsd[p.in_syn[q]].x);
+      if ((word >> (i & 31)) & 1u) acc = O::add(acc, wsd[p.in_syn[q]].x);
     }
     p.Iacc[(size_t)(t & 1) * p.Nld + j] = acc;
   }
@@ -493,6 +629,7 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
   __shared__ int cum[kMaxDelay + 2];
   __shared__ int slots[kMaxDelay + 1];
   __shared__ unsigned long long blk_ev;
+  tl_begin(p.tl, LTD ? 1 : 5, k);
   const int64_t t = cx->t0 + k;
   const int slot = (int)(((int64_t)cx->slot0 + k + p.R) % p.R);  // k may be -1 (window-start push)
   // prologue: the Dmax list lengths are loaded in parallel (one round trip), scanned in smem
@@ -518,6 +655,7 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
   const uint32_t* __restrict__ bits_now = p.bits + (size_t)slot * p.W;
   T* __restrict__ I_next = p.Iacc + (size_t)((t + 1) & 1) * Nld;
   unsigned long long n_ev = 0;
+  const WView<T> vw = wview(p);
   const uint32_t G = 1u << g_log2;
   const uint32_t gl = gtid & (G - 1);
   const uint32_t ngroups = nthreads >> g_log2;
@@ -529,25 +667,28 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
     const uint32_t* __restrict__ sg = p.seg + (size_t)i * (p.Dmax + 1) + a;
     const uint32_t s0 = sg[0], s1 = sg[1];
     const uint32_t s2 = (PUSHNEXT && a + 1 < p.Dmax) ? sg[2] : s1;
-    const uint32_t ibase = p.B == 1 ? 0u : (i / Nper) * Nper;
-    const bool row_plastic = LTD && (i - ibase) < Ne;
+    const uint32_t inst = p.B == 1 ? 0u : i / Nper, ibase = inst * Nper;
+    const bool row_exc = (i - ibase) < Ne;
+    const bool row_plastic = LTD && row_exc;
     const T pre_up = (row_plastic && !ATOMIC) ? O::mul(p.apost, p.trace[(size_t)sl * Nld + i]) : (T)0;
     if (LTD && gl == 0) n_ev += (s1 - s0);
     for (uint32_t e = (LTD ? s0 : s1) + gl; e < s2; e += G) {
       const uint32_t j = (uint32_t)p.post[e];
       if (e >= s1) {                       // arrives at k+1: push only
-        atomicAdd(&I_next[j], p.wsd[e].x);
+        bool fly;
+        const typename DevNet<T>::T2 ws = w_fetch<T>(vw, e, row_exc, fly);
+        atomicAdd(&I_next[j], w_resolve<T>(p, ws, fly, p.plastic_ei || (j - ibase) < Ne, inst));
       } else if (row_plastic && (p.plastic_ei || (j - ibase) < Ne)) {
         const T dn = O::mul(p.apre, tr_now[j]);
         if (ATOMIC) {  // production: fire-and-forget reduction, LTP of this step comes from ltp_kernel
-          atomicAdd(&p.wsd[e].y, -dn);
+          sd_add<T>(p, vw, e, -dn, blockIdx.x);
           continue;
         }
         const bool jsp = (bits_now[j >> 5] >> (j & 31)) & 1u;
-        T sd = p.wsd[e].y;
+        T sd = vw.cur[e].y;
         if (jsp) sd = (j <= i) ? O::sub(O::add(sd, pre_up), dn) : O::add(O::sub(sd, dn), pre_up);
         else sd = O::sub(sd, dn);
-        p.wsd[e].y = sd;
+        vw.cur[e].y = sd;
       }
     }
   }
@@ -558,6 +699,7 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
     __syncthreads();
     if (threadIdx.x == 0 && blk_ev) p.blk_ev[blockIdx.x] += blk_ev;
   }
+  tl_end(p.tl, LTD ? 1 : 5, k);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -572,6 +714,7 @@ __global__ void __launch_bounds__(256)
 ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
   typedef Ops<T> O;
   __shared__ unsigned long long blk_ltp;
+  tl_begin(p.tl, 2, k);
   const int slot = (cx->slot0 + k) % p.R;
   const int n_now = p.spk_cnt[slot];
   if (threadIdx.x == 0) blk_ltp = 0ull;
@@ -583,6 +726,7 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
   const uint32_t gl = gtid & (G - 1);
   const uint32_t ngroups = nthreads >> g_log2;
   const int32_t* __restrict__ list = p.spk_list + (size_t)slot * Nld;
+  const WView<T> vw = wview(p);
   unsigned long long n_ltp = 0;
   for (uint32_t item = gtid >> g_log2; item < (uint32_t)n_now; item += ngroups) {
     const int32_t j = list[item];
@@ -612,13 +756,13 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         trv[q] = ok[q] ? p.trace[toff[q]] : (T)0;
-        sdv[q] = (!ATOMIC && ok[q]) ? p.wsd[e[q]].y : (T)0;
+        sdv[q] = (!ATOMIC && ok[q]) ? vw.cur[e[q]].y : (T)0;
       }
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         if (!ok[q]) continue;
-        if (ATOMIC) atomicAdd(&p.wsd[e[q]].y, O::mul(p.apost, trv[q]));
-        else p.wsd[e[q]].y = O::add(sdv[q], O::mul(p.apost, trv[q]));
+        if (ATOMIC) sd_add<T>(p, vw, e[q], O::mul(p.apost, trv[q]), p.log_ltp_base + blockIdx.x);
+        else vw.cur[e[q]].y = O::add(sdv[q], O::mul(p.apost, trv[q]));
       }
     }
   }
@@ -626,6 +770,7 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
   if ((threadIdx.x & 31) == 0 && n_ltp) atomicAdd(&blk_ltp, n_ltp);
   __syncthreads();
   if (threadIdx.x == 0 && blk_ltp) p.blk_ltp[blockIdx.x] += blk_ltp;
+  tl_end(p.tl, 2, k);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -646,83 +791,439 @@ __device__ __forceinline__ void learn_one(typename Real2<T>::type& ws, T g, T wm
   if (do_decay) ws.y = O::mul(ws.y, sdk);
 }
 
+// synapses [lo, hi) of one instance (first neuron r0): dst = learn(src); src == dst for the in-place pass
+template <typename T, int UNR>
+__device__ __forceinline__ void learn_range(const DevNet<T>& p, const typename Real2<T>::type* src,
+                                            typename Real2<T>::type* dst, int64_t lo, int64_t hi, int64_t r0, T g,
+                                            int do_learn, int do_decay, int64_t tid, int64_t nth) {
+  typedef typename DevNet<T>::T2 T2;
+  if (hi <= lo) return;
+  if (p.plastic_ei) {
+    if constexpr (sizeof(T) == 4) {
+      // 16-byte accesses: two synapses per load
+      const int64_t lo2 = (lo + 1) & ~(int64_t)1, hi2 = hi & ~(int64_t)1;
+      if (tid == 0 && lo < lo2) {
+        T2 ws = src[lo]; learn_one<T>(ws, g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay); dst[lo] = ws;
+      }
+      if (tid == 1 % nth && hi2 < hi && hi2 >= lo2) {
+        T2 ws = src[hi2]; learn_one<T>(ws, g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay); dst[hi2] = ws;
+      }
+      if (hi2 > lo2) {
+        const float4* __restrict__ qs = reinterpret_cast<const float4*>(src + lo2);
+        float4* __restrict__ qd = reinterpret_cast<float4*>(dst + lo2);
+        const int64_t n4 = (hi2 - lo2) >> 1;
+        int64_t x = tid;
+        for (; x + (UNR - 1) * nth < n4; x += UNR * nth) {
+          float4 r[UNR];
+#pragma unroll
+          for (int c = 0; c < UNR; ++c) r[c] = __ldcs(qs + x + c * nth);
+#pragma unroll
+          for (int c = 0; c < UNR; ++c) {
+            float2 s0 = make_float2(r[c].x, r[c].y), s1 = make_float2(r[c].z, r[c].w);
+            learn_one<float>(s0, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
+            learn_one<float>(s1, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
+            __stcs(qd + x + c * nth, make_float4(s0.x, s0.y, s1.x, s1.y));
+          }
+        }
+        for (; x < n4; x += nth) {
+          float4 r = __ldcs(qs + x);
+          float2 s0 = make_float2(r.x, r.y), s1 = make_float2(r.z, r.w);
+          learn_one<float>(s0, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
+          learn_one<float>(s1, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
+          __stcs(qd + x, make_float4(s0.x, s0.y, s1.x, s1.y));
+        }
+      }
+    } else {
+      int64_t e = lo + tid;
+      for (; e + (UNR - 1) * nth < hi; e += UNR * nth) {
+        T2 r[UNR];
+#pragma unroll
+        for (int c = 0; c < UNR; ++c) r[c] = src[e + c * nth];
+#pragma unroll
+        for (int c = 0; c < UNR; ++c) {
+          learn_one<T>(r[c], g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay);
+          dst[e + c * nth] = r[c];
+        }
+      }
+      for (; e < hi; e += nth) {
+        T2 ws = src[e];
+        learn_one<T>(ws, g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay);
+        dst[e] = ws;
+      }
+    }
+  } else {
+    // only exc->exc synapses are plastic (net_res.jl:213-216): needs the post id
+    for (int64_t e = lo + tid; e < hi; e += nth) {
+      if (((int64_t)p.post[e] - r0) >= p.Ne) continue;
+      T2 ws = src[e];
+      learn_one<T>(ws, g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay);
+      dst[e] = ws;
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T learn_rate(const DevNet<T>& p, T da) {
+  typedef Ops<T> O;
+  return p.rate_mode == SNN_RATE_BASE_PLUS_DA ? O::add(p.learn_base, da)
+         : (p.rate_mode == SNN_RATE_DA ? da : O::mul(p.eta, da));
+}
+
+// in-place pass (exact mode, serial launches, windows whose learn steps are too dense to overlap)
 template <typename T>
 __global__ void __launch_bounds__(256)
 learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int do_learn, int do_decay) {
-  typedef Ops<T> O;
-  typedef typename DevNet<T>::T2 T2;
+  tl_begin(p.tl, 3, k);
   const int b = blockIdx.y;
   const int64_t t = cx->t0 + k;
   const int64_t r0 = (int64_t)b * p.Nper;
   const uint32_t lo = p.seg[(size_t)r0 * (p.Dmax + 1)];
   const uint32_t hi = p.seg[(size_t)(r0 + p.Ne - 1) * (p.Dmax + 1) + p.Dmax];
-  const T da = p.da[(size_t)((t + 1) & 1) * p.B + b];
-  const T g = p.rate_mode == SNN_RATE_BASE_PLUS_DA ? O::add(p.learn_base, da)
-              : (p.rate_mode == SNN_RATE_DA ? da : O::mul(p.eta, da));
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-  if (p.plastic_ei) {
+  const T g = learn_rate<T>(p, p.da[(size_t)((t + 1) & 1) * p.B + b]);
+  typename DevNet<T>::T2* w = wview(p).cur;
+  learn_range<T, 4>(p, w, w, lo, hi, r0, g, do_learn, do_decay, blockIdx.x * (int64_t)blockDim.x + threadIdx.x,
+                    (int64_t)gridDim.x * blockDim.x);
+  tl_end(p.tl, 3, k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Asynchronous learn pass (production mode).  learn!(k) runs as ONE persistent kernel on a
+// low-priority stream while the neuron/synapse/ltp kernels of steps k+1.. run beside it.
+//   learn_ctl(begin)  : g[b] from da as decayed by step k, flip cur, frontier = 0, new epoch
+//   learn_pass        : blocks take 32K-synapse tiles in ascending order: wsdX[cur] =
+//                       learn(wsdX[cur^1]); a finished tile is flagged and the frontier (the
+//                       contiguous prefix of finished tiles) advanced with a CAS on `state`
+//   learn_ctl(all)    : frontier = all
+//   learn_replay      : (before the next begin / at the window end) sd[e] += logged deltas
+// Readers (w_fetch/w_resolve, sd_add) never wait: an unprocessed synapse's post-learn weight is
+// formed on the fly from the frozen buffer, its sd updates are logged.
+// ---------------------------------------------------------------------------------------------
+// <= 64 registers: two resident blocks must leave half of the SM's register file to the step kernels
+// (at 128 registers two blocks owned the whole file and nothing ran beside the pass)
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+learn_pass_kernel(DevNet<T> p, int32_t k, int do_decay) {
+  tl_begin(p.tl, 3, k);
+  __shared__ uint32_t s_tile;
+  const uint32_t st0 = *reinterpret_cast<const volatile uint32_t*>(&p.lc->state);
+  const uint32_t cur = st0 >> 31, curbit = st0 & 0x80000000u;
+  const uint32_t epoch = p.lc->epoch;
+  const typename DevNet<T>::T2* __restrict__ src = p.wsdX[cur ^ 1u];
+  typename DevNet<T>::T2* __restrict__ dst = p.wsdX[cur];
+  const uint32_t TS = p.tile_syn, U = TS >> 5;  // frontier units per tile
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = (p.exp_flags & 32) ? p.n_tiles : atomicAdd(&p.lc->next_tile, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    __syncthreads();
+    if (tile >= p.n_tiles) break;
+    const int64_t a = (int64_t)tile * TS, z = a + TS;
+    // instances whose plastic range meets [a, z): first b with inst_hi[b] > a
+    int b = 0;
+    if (p.B > 1) {
+      int lo = 0, hi = p.B;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)p.inst_hi[mid] > a) hi = mid; else lo = mid + 1; }
+      b = lo;
+    }
+    bool done = false;
     if constexpr (sizeof(T) == 4) {
-      // 16-byte accesses: two synapses per load
-      const uint32_t lo2 = (lo + 1u) & ~1u, hi2 = hi & ~1u;
-      if (tid == 0 && lo < lo2 && lo < hi) {
-        T2 ws = p.wsd[lo]; learn_one<T>(ws, g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay); p.wsd[lo] = ws;
-      }
-      if (tid == 1 && hi2 < hi && hi2 >= lo2) {
-        T2 ws = p.wsd[hi2]; learn_one<T>(ws, g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay); p.wsd[hi2] = ws;
-      }
-      if (hi2 > lo2) {
-        float4* __restrict__ q = reinterpret_cast<float4*>(p.wsd + lo2);
-        const int64_t n4 = (hi2 - lo2) >> 1;
-        int64_t x = tid;
-        for (; x + 3 * nth < n4; x += 4 * nth) {
-          float4 r[4];
+      // whole tile inside one instance's plastic range: 16-byte accesses, 8 in flight per thread.
+      // The blocks run in lockstep through tiles that are TS*8 bytes apart; starting every tile at
+      // its own offset keeps them from all hitting the same HBM channels at the same time.
+      if (p.plastic_ei && b < p.B && (int64_t)p.inst_lo[b] <= a && (int64_t)p.inst_hi[b] >= z) {
+        const float4* __restrict__ qs = reinterpret_cast<const float4*>(src + a);
+        float4* __restrict__ qd = reinterpret_cast<float4*>(dst + a);
+        const uint32_t n4 = TS >> 1;  // multiple of 512
+        const uint32_t rot = (p.exp_flags & 256) ? 0u : ((tile * 2654435761u) >> 8) % (n4 >> 5) << 5;
+        const float g = p.lg[b];
+        for (uint32_t x0 = threadIdx.x; x0 < n4; x0 += 8 * 256) {
+          float4 r[8]; uint32_t ix[8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) r[c] = q[x + c * nth];
+          for (int c = 0; c < 8; ++c) {
+            uint32_t x = x0 + c * 256 + rot;
+            if (x >= n4) x -= n4;
+            ix[c] = x;
+            if (x0 + c * 256 < n4) r[c] = __ldcs(qs + x);
+          }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 8; ++c) {
+            if (x0 + c * 256 >= n4) continue;
             float2 s0 = make_float2(r[c].x, r[c].y), s1 = make_float2(r[c].z, r[c].w);
-            learn_one<float>(s0, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
-            learn_one<float>(s1, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
-            q[x + c * nth] = make_float4(s0.x, s0.y, s1.x, s1.y);
+            learn_one<float>(s0, g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, 1, do_decay);
+            learn_one<float>(s1, g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, 1, do_decay);
+            __stcs(qd + ix[c], make_float4(s0.x, s0.y, s1.x, s1.y));
           }
         }
-        for (; x < n4; x += nth) {
-          float4 r = q[x];
-          float2 s0 = make_float2(r.x, r.y), s1 = make_float2(r.z, r.w);
-          learn_one<float>(s0, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
-          learn_one<float>(s1, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
-          q[x] = make_float4(s0.x, s0.y, s1.x, s1.y);
-        }
-      }
-    } else {
-      int64_t e = (int64_t)lo + tid;
-      for (; e + 3 * nth < hi; e += 4 * nth) {
-        T2 r[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) r[c] = p.wsd[e + c * nth];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          learn_one<T>(r[c], g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay);
-          p.wsd[e + c * nth] = r[c];
-        }
-      }
-      for (; e < hi; e += nth) {
-        T2 ws = p.wsd[e];
-        learn_one<T>(ws, g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay);
-        p.wsd[e] = ws;
+        done = true;
       }
     }
-  } else {
-    // only exc->exc synapses are plastic (net_res.jl:213-216): needs the post id
-    for (int64_t e = (int64_t)lo + tid; e < hi; e += nth) {
-      if (((int64_t)p.post[e] - r0) >= p.Ne) continue;
-      T2 ws = p.wsd[e];
-      learn_one<T>(ws, g, p.wmin, p.wmax, p.sd_decay, do_learn, do_decay);
-      p.wsd[e] = ws;
+    if (!done) {
+      for (; b < p.B && (int64_t)p.inst_lo[b] < z; ++b) {
+        const int64_t lo = max((int64_t)p.inst_lo[b], a), hi = min((int64_t)p.inst_hi[b], z);
+        learn_range<T, 8>(p, src, dst, lo, hi, (int64_t)b * p.Nper, p.lg[b], 1, do_decay, threadIdx.x, blockDim.x);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const uint32_t lane = threadIdx.x;
+      if (lane == 0) {
+        __threadfence();  // the tile's stores are visible before its flag
+        *reinterpret_cast<volatile uint32_t*>(&p.tile_done[tile]) = epoch;
+        __threadfence();
+      }
+      __syncwarp();
+      // advance the frontier over the contiguous prefix of finished tiles: the warp scans 32 flags
+      // per round trip, then ONE atomicMax (the cur bit is constant during a pass, so the packed
+      // word is monotonic).  A serial CAS per tile would bound the whole pass by n_tiles L2 round
+      // trips.  Losing a race only leaves the frontier behind until the next tile finishes.
+      const uint32_t f0 = (*reinterpret_cast<volatile uint32_t*>(&p.lc->state) & kFrontAll) / U;
+      uint32_t f = f0;
+      for (;;) {
+        const uint32_t idx = f + lane;
+        const bool d = idx < p.n_tiles && *reinterpret_cast<volatile uint32_t*>(&p.tile_done[idx]) == epoch;
+        const unsigned m = __ballot_sync(0xffffffffu, d);
+        const int run = m == 0xffffffffu ? 32 : __ffs(~m) - 1;
+        f += run;
+        if (run < 32) break;
+      }
+      if (lane == 0 && f > f0) {
+        __threadfence();
+        atomicMax(&p.lc->state, curbit | (f * U));
+      }
+    }
+  }
+  tl_end(p.tl, 3, k);
+}
+
+// ---- TMA (bulk async copy) + mbarrier primitives, sm_100a
+__device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+// shared -> global, tracked by bulk async-groups
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// learn_pass_tma_kernel — the asynchronous pass, staged through shared memory by the TMA engine.
+// The pass has to stream 16 B per plastic synapse at HBM speed for a whole learn period WHILE the
+// step kernels run on the same SMs.  An LSU version needs ~10 MB of loads in flight = hundreds of
+// threads x 8 x 16-B registers per SM (it took half of every SM's register file and halved the
+// step kernels' occupancy).  Here one elected thread keeps kPassStages-1 16-KB bulk loads in
+// flight per block (cp.async.bulk + mbarrier complete_tx), 128 threads apply learn! in place in
+// shared memory, and the result leaves through a bulk store: ~4 K registers and 1/16 of the thread
+// slots per SM.  Loads and stores carry an L2 evict-first policy so that the pass does not flush
+// the neuron state (36 MB per step, L2-resident) out of the 126 MB L2.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPassThreads = 256, kPassStages = 4, kPassMaxStages = 12;
+constexpr uint32_t kPassChunkBytes = 16384;
+
+template <typename T>
+__global__ void __launch_bounds__(kPassThreads)
+learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
+  typedef typename DevNet<T>::T2 T2;
+  tl_begin(p.tl, 3, k);
+  extern __shared__ __align__(128) unsigned char pass_smem[];
+  __shared__ __align__(8) uint64_t mbar[kPassMaxStages];
+  const uint32_t S = (uint32_t)n_stages;
+  __shared__ uint32_t s_tile;
+  constexpr uint32_t CH = kPassChunkBytes / sizeof(T2);  // synapses per chunk
+  T2* const buf = reinterpret_cast<T2*>(pass_smem);      // [kPassStages][CH]
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) {
+    for (uint32_t s_ = 0; s_ < S; ++s_) mbar_init(&mbar[s_], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint64_t pol = l2_evict_first_policy();
+  const uint32_t st0 = *reinterpret_cast<const volatile uint32_t*>(&p.lc->state);
+  const uint32_t cur = st0 >> 31, curbit = st0 & 0x80000000u;
+  const uint32_t epoch = p.lc->epoch;
+  const T2* __restrict__ src = p.wsdX[cur ^ 1u];
+  T2* __restrict__ dst = p.wsdX[cur];
+  const uint32_t TS = p.tile_syn, U = TS >> 5;
+  uint32_t q = 0;  // chunks consumed so far by this block: stage = q % S, parity = (q / S) & 1
+  for (;;) {
+    if (tid == 0) s_tile = (p.exp_flags & 32) ? p.n_tiles : atomicAdd(&p.lc->next_tile, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    __syncthreads();
+    if (tile >= p.n_tiles) break;
+    const int64_t a = (int64_t)tile * TS, z = a + TS;
+    int b = 0;
+    if (p.B > 1) {  // first instance whose plastic range ends after a
+      int lo = 0, hi = p.B;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)p.inst_hi[mid] > a) hi = mid; else lo = mid + 1; }
+      b = lo;
+    }
+    for (; b < p.B && (int64_t)p.inst_lo[b] < z; ++b) {
+      int64_t lo = max((int64_t)p.inst_lo[b], a), hi = min((int64_t)p.inst_hi[b], z);
+      if (hi <= lo) continue;
+      const T g = p.lg[b];
+      const int64_t r0 = (int64_t)b * p.Nper;
+      auto one = [&](T2& ws, int64_t e) {
+        if (!p.plastic_ei && ((int64_t)p.post[e] - r0) >= p.Ne) return;  // exc->inh: not plastic (net_res.jl:213-216)
+        learn_one<T>(ws, g, p.wmin, p.wmax, p.sd_decay, 1, do_decay);
+      };
+      // bulk copies need 16-byte alignment: odd fp32 ends are done by hand
+      if (sizeof(T2) == 8) {
+        if ((lo & 1) && tid == 0) { T2 ws = src[lo]; one(ws, lo); dst[lo] = ws; }
+        lo = (lo + 1) & ~(int64_t)1;
+        if ((hi & 1) && hi > lo && tid == 1) { T2 ws = src[hi - 1]; one(ws, hi - 1); dst[hi - 1] = ws; }
+        hi &= ~(int64_t)1;
+      }
+      if (hi <= lo) continue;
+      const uint32_t n = (uint32_t)(hi - lo), nch = (n + CH - 1) / CH;
+      auto chunk_bytes = [&](uint32_t i) { return (uint32_t)((i + 1 < nch ? CH : n - i * CH) * sizeof(T2)); };
+      if (tid == 0) {
+        for (uint32_t i = 0; i < nch && i < S; ++i) {
+          const uint32_t sg = (q + i) % S;
+          mbar_expect_tx(&mbar[sg], chunk_bytes(i));
+          tma_load_1d(buf + (size_t)sg * CH, src + lo + (size_t)i * CH, chunk_bytes(i), &mbar[sg], pol);
+        }
+      }
+      for (uint32_t i = 0; i < nch; ++i) {
+        const uint32_t sg = (q + i) % S, par = ((q + i) / S) & 1u;
+        mbar_wait(&mbar[sg], par);
+        T2* const bs = buf + (size_t)sg * CH;
+        const uint32_t cnt = chunk_bytes(i) / (uint32_t)sizeof(T2);
+        const int64_t e0 = lo + (int64_t)i * CH;
+        if constexpr (sizeof(T2) == 8) {
+          // 16-byte shared-memory accesses: two synapses per thread and iteration (cnt is even)
+          float4* const b4 = reinterpret_cast<float4*>(bs);
+#pragma unroll 4
+          for (uint32_t x = tid; x < (cnt >> 1); x += kPassThreads) {
+            float4 r = b4[x];
+            float2 s0 = make_float2(r.x, r.y), s1 = make_float2(r.z, r.w);
+            one(s0, e0 + 2 * x);
+            one(s1, e0 + 2 * x + 1);
+            b4[x] = make_float4(s0.x, s0.y, s1.x, s1.y);
+          }
+        } else {
+          for (uint32_t x = tid; x < cnt; x += kPassThreads) {
+            T2 ws = bs[x];
+            one(ws, e0 + x);
+            bs[x] = ws;
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes to smem -> visible to the bulk store
+        __syncthreads();
+        if (tid == 0) {
+          tma_store_1d(dst + e0, bs, chunk_bytes(i), pol);
+          tma_commit();
+          if (i >= 1 && i - 1 + S < nch) {
+            tma_wait_read<1>();  // store(i-1) has read its stage: refill it with chunk i-1+S
+            const uint32_t c = i - 1 + S, sc = (q + c) % S;
+            mbar_expect_tx(&mbar[sc], chunk_bytes(c));
+            tma_load_1d(buf + (size_t)sc * CH, src + lo + (size_t)c * CH, chunk_bytes(c), &mbar[sc], pol);
+          }
+        }
+      }
+      if (tid == 0) tma_wait_read<0>();  // every stage is free again before the next range
+      __syncthreads();
+      q += nch;
+    }
+    // the tile's bulk stores are complete (written, not merely read) before its flag goes up
+    if (tid == 0) tma_wait_all();
+    __syncthreads();
+    if (tid < 32) {
+      const uint32_t lane = tid;
+      if (lane == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(&p.tile_done[tile]) = epoch;
+        __threadfence();
+      }
+      __syncwarp();
+      const uint32_t f0 = (*reinterpret_cast<volatile uint32_t*>(&p.lc->state) & kFrontAll) / U;
+      uint32_t f = f0;
+      for (;;) {
+        const uint32_t idx = f + lane;
+        const bool d = idx < p.n_tiles && *reinterpret_cast<volatile uint32_t*>(&p.tile_done[idx]) == epoch;
+        const unsigned m = __ballot_sync(0xffffffffu, d);
+        const int run = m == 0xffffffffu ? 32 : __ffs(~m) - 1;
+        f += run;
+        if (run < 32) break;
+      }
+      if (lane == 0 && f > f0) {
+        __threadfence();
+        atomicMax(&p.lc->state, curbit | (f * U));
+      }
+    }
+  }
+  tl_end(p.tl, 3, k);
+}
+
+enum { kCtlBegin = 0, kCtlAll = 1 };
+template <typename T>
+__global__ void learn_ctl_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int mode) {
+  const uint32_t st = p.lc->state;
+  if (mode == kCtlBegin) {
+    const int64_t t = cx->t0 + k;
+    for (int b = threadIdx.x; b < p.B; b += blockDim.x) p.lg[b] = learn_rate<T>(p, p.da[(size_t)((t + 1) & 1) * p.B + b]);
+    if (threadIdx.x == 0) {
+      p.lc->state = ((st >> 31) ^ 1u) << 31;
+      p.lc->epoch += 1u;
+      p.lc->next_tile = 0u;
+      p.lc->spilled = 0u;  // the replay before this kernel has merged the spill
+    }
+  } else if (threadIdx.x == 0) {
+    p.lc->state = (st & 0x80000000u) | kFrontAll;
+  }
+}
+
+// one block per log region (block-stride); empties the regions it replays
+template <typename T>
+__global__ void __launch_bounds__(256) learn_replay_kernel(DevNet<T> p) {
+  typename DevNet<T>::T2* w = p.wsdX[p.lc->state >> 31];
+  for (uint32_t r = blockIdx.x; r < p.log_regions; r += gridDim.x) {
+    const uint32_t cnt = p.log_cnt[(size_t)r * kLogStride];
+    const uint32_t n = cnt < p.log_region_cap ? cnt : p.log_region_cap;
+    const LogEntry<T>* __restrict__ lg = p.dlog + (size_t)r * p.log_region_cap;
+    for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) {
+      const LogEntry<T> le = lg[q];
+      atomicAdd(&w[le.e].y, le.d);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && cnt) p.log_cnt[(size_t)r * kLogStride] = 0u;
+  }
+  if (p.lc->spilled) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = tid; e < p.E; e += nth) {
+      const T d = p.dsd[e];
+      if (d != (T)0) { atomicAdd(&w[e].y, d); p.dsd[e] = (T)0; }
     }
   }
 }
+template <typename T>
+__global__ void learn_spill_reset_kernel(DevNet<T> p) { p.lc->spilled = 0u; }
 
 // ----------------------------------------------------------------------------- small helpers
 template <typename T>
@@ -786,13 +1287,19 @@ class Engine : public IEngine {
 
   int init(std::string& err) override {
     SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    int prio_lo = 0, prio_hi = 0;  // numerically: lowest priority = prio_lo, highest = prio_hi
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_lo;
+    if (cfg_.reserved[1] & 64) prio_lo = prio_mid = prio_hi = 0;  // experiment 64: no stream priorities
     SNN_CUDA_OK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
-    SNN_CUDA_OK(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+    SNN_CUDA_OK(cudaStreamCreateWithPriority(&side_stream_, cudaStreamNonBlocking, prio_mid));
+    SNN_CUDA_OK(cudaStreamCreateWithPriority(&chain_stream_, cudaStreamNonBlocking, prio_hi));   // neuron chain
+    SNN_CUDA_OK(cudaStreamCreateWithPriority(&learn_stream_, cudaStreamNonBlocking, prio_lo));   // async learn pass
     stream_ = own_stream_;
     SNN_CUDA_OK(cudaEventCreate(&ev_begin_));
     SNN_CUDA_OK(cudaEventCreate(&ev_end_));
     for (auto& e : dep_ev_) SNN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    SNN_CUDA_OK(cudaStreamCreateWithFlags(&side2_stream_, cudaStreamNonBlocking));
+    SNN_CUDA_OK(cudaStreamCreateWithPriority(&side2_stream_, cudaStreamNonBlocking, prio_mid));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device);
     n_sm_ = sms;
@@ -814,6 +1321,14 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMalloc(&p.counters, 4 * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMalloc(&p.blk_ev, kMaxSynBlocks * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMalloc(&p.blk_ltp, kMaxSynBlocks * sizeof(unsigned long long)));
+    SNN_CUDA_OK(cudaMalloc(&p.lc, sizeof(LearnCtl)));
+    SNN_CUDA_OK(cudaMalloc(&p.lg, (size_t)p.B * sizeof(T)));
+    SNN_CUDA_OK(cudaMemsetAsync(p.lg, 0, (size_t)p.B * sizeof(T), stream_));
+    {
+      LearnCtl lc0; lc0.state = kFrontAll; lc0.epoch = 0; lc0.next_tile = 0; lc0.spilled = 0;
+      SNN_CUDA_OK(cudaMemcpyAsync(p.lc, &lc0, sizeof(lc0), cudaMemcpyHostToDevice, stream_));
+      SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    }
     SNN_CUDA_OK(cudaMalloc(&d_ctx_, sizeof(WindowCtx<T>)));
     SNN_CUDA_OK(cudaMallocHost(&h_ctx_, sizeof(WindowCtx<T>)));
     SNN_CUDA_OK(cudaMallocHost(&h_blk_, 2 * kMaxSynBlocks * sizeof(unsigned long long)));
@@ -835,6 +1350,7 @@ class Engine : public IEngine {
     p.exact = cfg_.mode == SNN_MODE_EXACT;
     p.exp_flags = cfg_.reserved[1];
     p.part_lo = 0; p.part_hi = p.N;
+    if (cfg_.reserved[1] & 2) SNN_CUDA_OK(cudaMalloc(&p.tl, 2 * kTlClasses * kTlSteps * sizeof(unsigned long long)));
     p.homeostasis = !(cfg_.theta == 0.0 && cfg_.ttheta == 1.0);
     init_state_kernel<T><<<grid_for(p.Nld), 256, 0, stream_>>>(p);
     SNN_CUDA_OK(cudaGetLastError());
@@ -851,9 +1367,51 @@ class Engine : public IEngine {
     p.E = topo_.E;
     p.seg = topo_.seg; p.post = topo_.post; p.colptr = topo_.colptr; p.col_npl = topo_.col_npl;
     p.in_syn = topo_.in_syn; p.in_pre = topo_.in_pre;
-    cudaFree(p.wsd); p.wsd = nullptr;
+    free_synapse_state();
     const int64_t Ea = p.E > 0 ? p.E : 1;
-    SNN_CUDA_OK(cudaMalloc(&p.wsd, Ea * sizeof(typename DevNet<T>::T2)));
+    typedef typename DevNet<T>::T2 T2;
+    SNN_CUDA_OK(cudaMalloc(&p.wsdX[0], Ea * sizeof(T2)));
+    p.wsd = p.wsdX[0]; p.wsdX[1] = p.wsdX[0];
+    cur_ = 0;
+    {
+      LearnCtl lc0; lc0.state = kFrontAll; lc0.epoch = 0; lc0.next_tile = 0; lc0.spilled = 0;
+      SNN_CUDA_OK(cudaMemcpyAsync(p.lc, &lc0, sizeof(lc0), cudaMemcpyHostToDevice, stream_));
+    }
+    // plastic synapse range of every instance (exc rows are contiguous in the internal order)
+    inst_lo_.assign(p.B, 0); inst_hi_.assign(p.B, 0);
+    if (p.E > 0 && p.Ne > 0) {
+      const size_t pitch = (size_t)p.Nper * (p.Dmax + 1) * sizeof(uint32_t);
+      SNN_CUDA_OK(cudaMemcpy2D(inst_lo_.data(), sizeof(uint32_t), p.seg, pitch, sizeof(uint32_t), p.B, cudaMemcpyDeviceToHost));
+      SNN_CUDA_OK(cudaMemcpy2D(inst_hi_.data(), sizeof(uint32_t), p.seg + (size_t)(p.Ne - 1) * (p.Dmax + 1) + p.Dmax, pitch,
+                               sizeof(uint32_t), p.B, cudaMemcpyDeviceToHost));
+    }
+    n_plastic_ = 0;
+    for (int b = 0; b < p.B; ++b) n_plastic_ += (int64_t)inst_hi_[b] - (int64_t)inst_lo_[b];
+    // production mode: second (w, sd) buffer + update log for the asynchronous learn pass
+    have_async_ = !p.exact && use_graph_ && cfg_.reserved[4] != 1 && n_plastic_ > 0 &&
+                  cfg_.sd_decay_mode != SNN_SD_DECAY_EVERY_STEP;
+    if (have_async_) {
+      SNN_CUDA_OK(cudaMalloc(&p.wsdX[1], Ea * sizeof(T2)));
+      const Launch g = grids();
+      p.log_regions = (uint32_t)(g.gA + g.gP); p.log_ltp_base = (uint32_t)g.gA;
+      const int64_t log_cap = cfg_.reserved[5] > 0 ? cfg_.reserved[5]
+                                                  : std::min<int64_t>(std::max<int64_t>(1 << 20, n_plastic_ / 8), 1ll << 28);
+      p.log_region_cap = (uint32_t)std::max<int64_t>(1, log_cap / p.log_regions);
+      SNN_CUDA_OK(cudaMalloc(&p.dlog, (size_t)p.log_regions * p.log_region_cap * sizeof(LogEntry<T>)));
+      SNN_CUDA_OK(cudaMalloc(&p.log_cnt, (size_t)p.log_regions * kLogStride * sizeof(uint32_t)));
+      SNN_CUDA_OK(cudaMemsetAsync(p.log_cnt, 0, (size_t)p.log_regions * kLogStride * sizeof(uint32_t), stream_));
+      SNN_CUDA_OK(cudaMalloc(&p.dsd, Ea * sizeof(T)));
+      SNN_CUDA_OK(cudaMemsetAsync(p.dsd, 0, Ea * sizeof(T), stream_));
+      p.tile_syn = cfg_.reserved[3] > 0 ? (uint32_t)cfg_.reserved[3] * 1024u : kTileSyn;
+      p.n_tiles = (uint32_t)(((int64_t)inst_hi_[p.B - 1] + p.tile_syn - 1) / p.tile_syn);
+      SNN_CUDA_OK(cudaMalloc(&p.tile_done, (size_t)std::max<uint32_t>(1, p.n_tiles) * sizeof(uint32_t)));
+      SNN_CUDA_OK(cudaMemsetAsync(p.tile_done, 0, (size_t)std::max<uint32_t>(1, p.n_tiles) * sizeof(uint32_t), stream_));
+      uint32_t* d_lohi = nullptr;
+      SNN_CUDA_OK(cudaMalloc(&d_lohi, 2 * (size_t)p.B * sizeof(uint32_t)));
+      SNN_CUDA_OK(cudaMemcpyAsync(d_lohi, inst_lo_.data(), (size_t)p.B * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+      SNN_CUDA_OK(cudaMemcpyAsync(d_lohi + p.B, inst_hi_.data(), (size_t)p.B * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+      p.inst_lo = d_lohi; p.inst_hi = d_lohi + p.B;
+    }
     int rc = upload_wsd(h_w, 0, 1, err);
     if (rc) return rc;
     // lanes per work item from the mean item length
@@ -887,7 +1445,7 @@ class Engine : public IEngine {
         if (p.E == 0) return SNN_OK;
         double* d = nullptr;
         SNN_CUDA_OK(cudaMalloc(&d, p.E * sizeof(double)));
-        wsd_to_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(p.wsd, topo_.perm, d, p.E, field == SNN_FIELD_W ? 0 : 1);
+        wsd_to_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(p.wsdX[cur_], topo_.perm, d, p.E, field == SNN_FIELD_W ? 0 : 1);
         cudaError_t e = cudaMemcpyAsync(host, d, p.E * sizeof(double), cudaMemcpyDeviceToHost, stream_);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
         cudaFree(d);
@@ -966,6 +1524,13 @@ class Engine : public IEngine {
     return SNN_OK;
   }
 
+  int get_timeline(unsigned long long* host, int64_t count, std::string& err) override {
+    if (!p_.tl) { err = "timeline recording is off (snn_config.reserved[1] & 2)"; return SNN_ERR_STATE; }
+    if (count != 2 * kTlClasses * kTlSteps) { err = "timeline count mismatch"; return SNN_ERR_INVALID; }
+    SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    SNN_CUDA_OK(cudaMemcpy(host, p_.tl, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return SNN_OK;
+  }
   int64_t n_synapses() const override { return p_.E; }
   int64_t step_index() const override { return t_; }
   void set_profiling(int mode) override { profiling_ = mode; }
@@ -994,7 +1559,10 @@ class Engine : public IEngine {
     double* d = nullptr;
     SNN_CUDA_OK(cudaMalloc(&d, p.E * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(d, h, p.E * sizeof(double), cudaMemcpyHostToDevice, stream_);
-    wsd_from_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(d, topo_.perm, p.wsd, p.E, comp, zero_other);
+    // weights go to both buffers (non-plastic ones are read from either); sd lives in the current one
+    wsd_from_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(d, topo_.perm, p.wsdX[cur_], p.E, comp, zero_other);
+    if (p.wsdX[1] != p.wsdX[0] && comp == 0)
+      wsd_from_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(d, topo_.perm, p.wsdX[cur_ ^ 1], p.E, comp, zero_other);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
     cudaFree(d);
@@ -1003,6 +1571,7 @@ class Engine : public IEngine {
   }
   struct CachedGraph {
     std::string key; cudaGraphExec_t exec = nullptr; size_t prof_used = 0; std::vector<int> prof_cls;
+    int pass_launches = 0;
     std::vector<cudaEvent_t> prof_events;  // event record nodes are baked into the graph
   };
   void drop_graph() {
@@ -1012,12 +1581,20 @@ class Engine : public IEngine {
     }
     graphs_.clear();
   }
+  void free_synapse_state() {
+    DevNet<T>& p = p_;
+    if (p.wsdX[1] != p.wsdX[0]) cudaFree(p.wsdX[1]);
+    cudaFree(p.wsdX[0]); cudaFree(p.dlog); cudaFree(p.dsd); cudaFree(p.log_cnt); cudaFree(p.tile_done);
+    cudaFree(const_cast<uint32_t*>(p.inst_lo));
+    p.wsd = p.wsdX[0] = p.wsdX[1] = nullptr; p.dlog = nullptr; p.dsd = nullptr; p.log_cnt = nullptr;
+    p.tile_done = nullptr; p.inst_lo = p.inst_hi = nullptr; p.log_regions = p.log_region_cap = p.n_tiles = 0;
+  }
   void release() {
     DevNet<T>& p = p_;
     drop_graph();
     cudaFree(p.v); cudaFree(p.u); cudaFree(p.ho); cudaFree(p.Iacc); cudaFree(p.trace); cudaFree(p.bits);
     cudaFree(p.spk_list); cudaFree(p.spk_cnt); cudaFree(p.da); cudaFree(p.counters); cudaFree(p.blk_ev);
-    cudaFree(p.blk_ltp); cudaFree(p.wsd); cudaFree(d_ctx_);
+    cudaFree(p.blk_ltp); free_synapse_state(); cudaFree(d_ctx_); cudaFree(p.tl); cudaFree(p.lc); cudaFree(p.lg);
     if (h_ctx_) cudaFreeHost(h_ctx_);
     if (h_blk_) cudaFreeHost(h_blk_);
     b_noise_.release(); b_noise64_.release(); b_ev_off_.release(); b_ev_inst_.release(); b_ev_amt_.release();
@@ -1031,7 +1608,9 @@ class Engine : public IEngine {
     if (own_stream_) cudaStreamDestroy(own_stream_);
     if (side_stream_) cudaStreamDestroy(side_stream_);
     if (side2_stream_) cudaStreamDestroy(side2_stream_);
-    side2_stream_ = nullptr;
+    if (chain_stream_) cudaStreamDestroy(chain_stream_);
+    if (learn_stream_) cudaStreamDestroy(learn_stream_);
+    side2_stream_ = chain_stream_ = learn_stream_ = nullptr;
     memset(&p, 0, sizeof(p));
     own_stream_ = side_stream_ = nullptr; ev_begin_ = ev_end_ = nullptr; d_ctx_ = nullptr; h_ctx_ = nullptr; h_blk_ = nullptr;
   }
@@ -1090,6 +1669,8 @@ class Engine : public IEngine {
   void launch_serial(const StepArgs& a, const std::vector<int32_t>& force_off, const int32_t* d_force,
                      const std::vector<int32_t>& cur_off, const int32_t* d_cur_idx, const double* d_cur_val, bool prof);
   int launch_graph(const StepArgs& a, bool prof, std::string& err);
+  bool async_ok(const StepArgs& a) const;
+  void launch_pass(cudaStream_t s4, int k, int do_decay, bool prof);
 
   snn_config cfg_;
   DevNet<T> p_;
@@ -1100,8 +1681,14 @@ class Engine : public IEngine {
   int n_sm_ = 148, g_arr_log2_ = 5, g_ltp_log2_ = 5, gA_ = 0;
   cudaStream_t own_stream_ = nullptr, side_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev_begin_ = nullptr, ev_end_ = nullptr;
-  cudaEvent_t dep_ev_[12] = {};
-  cudaStream_t side2_stream_ = nullptr;
+  cudaEvent_t dep_ev_[16] = {};
+  cudaStream_t side2_stream_ = nullptr, chain_stream_ = nullptr, learn_stream_ = nullptr;
+  // asynchronous learn pass
+  bool have_async_ = false;
+  int cur_ = 0;                  // host mirror of LearnCtl.state >> 31 (read back after every window)
+  int64_t n_plastic_ = 0;
+  std::vector<uint32_t> inst_lo_, inst_hi_;
+  int last_pass_launches_ = 0;   // kernels of the async passes of the last window (chunks + control)
   std::vector<cudaEvent_t> prof_events_;
   std::vector<int> prof_cls_;
   size_t prof_used_ = 0;
@@ -1180,19 +1767,64 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
   }
 }
 
-// Whole window as one CUDA graph (captured once per (length, train pattern)), three streams.
+// Whole window as one CUDA graph (captured once per (length, train pattern)).
 //   needs(neuron(k))  : neuron(k-1) [stream], pushes for step k-1 = synapse(k-2) | push(k-2),
-//                       learn(k-1) (its delay-1 pushes read w)
-//   needs(synapse(k)) : neuron(k), learn(k-1), synapse(k-1) [stream]   (sd updates are reductions:
-//   needs(ltp(k))     : neuron(k), learn(k-1) [stream], ltp(k-1) [stream]  no LTD/LTP ordering)
-//   needs(learn(k))   : synapse(k) LTD, ltp(k) [stream]
-//   needs(push(k))    : learn(k)            (learn steps only; otherwise fused into synapse(k))
+//                       learn(k-1) begun (async) / done (in place): its delay-1 pushes read w
+//   needs(synapse(k)) : neuron(k), synapse(k-1) [stream]        (sd updates are reductions:
+//   needs(ltp(k))     : neuron(k), ltp(k-1) [stream]             no LTD/LTP ordering)
+//   needs(learn(k))   : synapse(k) LTD, ltp(k); async: the previous pass [stream] + its log replay
+//   needs(push(k))    : learn(k) begun / done   (learn steps only; otherwise fused into synapse(k))
+// Streams: sN neuron chain (highest priority), s2 synapse, s3 ltp (+ in-place learn), s4 the
+// asynchronous learn pass (lowest priority): learn_replay, learn_ctl(begin), chunks, learn_ctl(all).
+template <typename T>
+bool Engine<T>::async_ok(const StepArgs& a) const {
+  if (!have_async_) return false;
+  int last = -1000, n_learn = 0, dl, dd;
+  for (int k = 0; k < a.n_steps; ++k) {
+    if (!wants_learn(a, k, &dl, &dd)) continue;
+    if (k - last < 3) return false;  // passes back to back: nothing to overlap with
+    last = k; ++n_learn;
+  }
+  if (n_learn == 0) return false;
+  if (cfg_.reserved[4] == 2) return true;               // forced (tests on small nets)
+  return n_plastic_ * 2 * (int64_t)sizeof(typename DevNet<T>::T2) >= (32ll << 20);
+}
+
+template <typename T>
+void Engine<T>::launch_pass(cudaStream_t s4, int k, int do_decay, bool prof) {
+  DevNet<T>& p = p_;
+  // persistent pass: LB blocks per SM stay resident for the whole pass and leave the other
+  // thread slots to the step kernels (LB x 256 threads x 8 x 16 B in flight per SM)
+  const bool lsu = (cfg_.reserved[1] & 512) != 0;  // experiment 512: register-staged (LSU) pass instead of TMA
+  const int LB = cfg_.reserved[2] > 0 ? cfg_.reserved[2] : (lsu ? 2 : 3);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm_ * LB, p.n_tiles));
+  if (prof) prof_begin(2, s4, true);
+  if (lsu) {
+    learn_pass_kernel<T><<<grid, 256, 0, s4>>>(p, k, do_decay);
+  } else {
+    const int S = cfg_.reserved[6] >= 2 && cfg_.reserved[6] <= kPassMaxStages ? cfg_.reserved[6] : kPassStages;
+    const size_t smem = (size_t)S * kPassChunkBytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(learn_pass_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           kPassMaxStages * (int)kPassChunkBytes);
+      attr_set = true;
+    }
+    learn_pass_tma_kernel<T><<<grid, kPassThreads, smem, s4>>>(p, k, do_decay, S);
+  }
+  learn_ctl_kernel<T><<<1, 32, 0, s4>>>(p, d_ctx_, k, kCtlAll);
+  last_pass_launches_ += 2;
+  if (prof) prof_end(s4, true);
+}
+
 template <typename T>
 int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
   DevNet<T>& p = p_;
   const int n = a.n_steps;
+  const bool async = async_ok(a);
   std::string key(reinterpret_cast<const char*>(&n), sizeof(n));
   key.push_back(prof ? 'p' : '-');
+  key.push_back(async ? 'a' : 's');
   if (a.train_flags) key.append(reinterpret_cast<const char*>(a.train_flags), n);
   CachedGraph* hit = nullptr;
   for (auto& cg : graphs_) if (cg.key == key) hit = &cg;
@@ -1206,34 +1838,52 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
     std::vector<cudaEvent_t> saved_events;
     saved_events.swap(prof_events_);
     const Launch g = grids();
-    cudaStream_t s1 = stream_, s2 = side_stream_, s3 = side2_stream_;
+    cudaStream_t s0 = stream_, sN = chain_stream_, s2 = side_stream_, s3 = side2_stream_, s4 = learn_stream_;
     cudaGraph_t graph = nullptr;
     prof_used_ = 0; prof_cls_.clear();
+    last_pass_launches_ = 0;
     if (prof) prof_reserve(2 * (size_t)n + 2);  // no allocation while capturing
     // events: [0] neuron done, [1..3] pushes-for-step ready (ring of 3), [4..5] synapse LTD done
-    // (ring of 2), [6..7] ltp done (ring of 2), [8] learn done
-    cudaEvent_t evN = dep_ev_[0], evL = dep_ev_[8];
+    // (ring of 2), [6..7] ltp done (ring of 2), [8] learn done / begun, [9] fork, [10] pass+replay done
+    cudaEvent_t evL = dep_ev_[8], evFork = dep_ev_[9], evFin = dep_ev_[10];
     auto evPush = [&](int step) { return dep_ev_[1 + ((step % 3) + 3) % 3]; };  // pushes consumed by Euler(step)
     auto evS = [&](int step) { return dep_ev_[4 + (step & 1)]; };
     auto evP = [&](int step) { return dep_ev_[6 + (step & 1)]; };
-    SNN_CUDA_OK(cudaStreamBeginCapture(s1, cudaStreamCaptureModeThreadLocal));
-    cudaEventRecord(evN, s1);                      // fork point
-    cudaStreamWaitEvent(s2, evN, 0);
+    SNN_CUDA_OK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+    cudaEventRecord(evFork, s0);                    // fork point
+    cudaStreamWaitEvent(sN, evFork, 0);
+    cudaStreamWaitEvent(s2, evFork, 0);
     synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, -1, g_arr_log2_);  // pushes for step 0
     cudaEventRecord(evPush(0), s2);
-    bool learn_prev = false, s3_used = false;
-    for (int k = 0; k < n; ++k) {
+    bool s3_used = false, pass_open = false;
+    cudaEvent_t evNk[2] = {dep_ev_[0], dep_ev_[11]};
+    auto cap_neuron = [&](int k) {
+      int dl, dd;
+      const bool learn_prev = k >= 1 && wants_learn(a, k - 1, &dl, &dd);
+      if (k >= 1 && !(cfg_.reserved[1] & 4096)) cudaStreamWaitEvent(sN, evPush(k - 1), 0);  // Euler(k-1) consumes them
+      if (learn_prev) cudaStreamWaitEvent(sN, evL, 0);
+      if (k == 0) neuron_kernel<T, false, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
+      else if (cfg_.reserved[1] & 8192) {
+        cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3(g.gN); lc.blockDim = dim3(256); lc.dynamicSmemBytes = 0; lc.stream = sN;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        cudaLaunchKernelEx(&lc, neuron_kernel<T, true, true>, p, (const WindowCtx<T>*)d_ctx_, (int32_t)k, (int32_t)1);
+      }
+      else neuron_kernel<T, true, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
+      cudaEventRecord(evNk[k & 1], sN);
+    };
+    auto cap_side = [&](int k) {
       int dl, dd;
       const bool learn = wants_learn(a, k, &dl, &dd);
+      const bool learn_prev = k >= 1 && wants_learn(a, k - 1, &dl, &dd);
+      wants_learn(a, k, &dl, &dd);
       const bool push_next = k + 1 < n;
-      if (k >= 1) cudaStreamWaitEvent(s1, evPush(k - 1), 0);  // Euler(k-1) consumes them
-      if (learn_prev) cudaStreamWaitEvent(s1, evL, 0);
-      if (k == 0) neuron_kernel<T, false, true><<<g.gN, 256, 0, s1>>>(p, d_ctx_, k, 1);
-      else neuron_kernel<T, true, true><<<g.gN, 256, 0, s1>>>(p, d_ctx_, k, 1);
-      cudaEventRecord(evN, s1);
       // s2: synapse(k)
-      cudaStreamWaitEvent(s2, evN, 0);
-      if (learn_prev) cudaStreamWaitEvent(s2, evL, 0);  // sd reductions must not race the learn pass
+      cudaStreamWaitEvent(s2, evNk[k & 1], 0);
+      if (learn_prev && !async) cudaStreamWaitEvent(s2, evL, 0);  // sd reductions must not race the in-place pass
       if (push_next && !learn) {
         synapse_kernel<T, true, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
         cudaEventRecord(evPush(k + 1), s2);
@@ -1241,11 +1891,28 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
         synapse_kernel<T, true, false, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
       }
       cudaEventRecord(evS(k), s2);
-      // s3: ltp(k) [-> learn(k)]
-      cudaStreamWaitEvent(s3, evN, 0);
+      // s3: ltp(k) [-> in-place learn(k)]
+      cudaStreamWaitEvent(s3, evNk[k & 1], 0);
       ltp_kernel<T, true><<<g.gP, 256, 0, s3>>>(p, d_ctx_, k, g_ltp_log2_);
       s3_used = true;
-      if (learn) {
+      cudaEventRecord(evP(k), s3);
+      if (learn && async) {
+        // s4: [previous pass, stream order] -> replay its log -> begin -> pass -> frontier = all
+        cudaStreamWaitEvent(s4, evS(k), 0);
+        cudaStreamWaitEvent(s4, evP(k), 0);
+        if (pass_open) { learn_replay_kernel<T><<<n_sm_ * 2, 256, 0, s4>>>(p); ++last_pass_launches_; }
+        learn_ctl_kernel<T><<<1, 256, 0, s4>>>(p, d_ctx_, k, kCtlBegin);
+        ++last_pass_launches_;
+        cudaEventRecord(evL, s4);
+        launch_pass(s4, k, dd, prof);
+        if (cfg_.reserved[1] & 4) cudaEventRecord(evL, s4);  // experiment: nothing overlaps the pass
+        pass_open = true;
+        if (push_next) {
+          cudaStreamWaitEvent(s2, evL, 0);
+          synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
+          cudaEventRecord(evPush(k + 1), s2);
+        }
+      } else if (learn) {
         cudaStreamWaitEvent(s3, evS(k), 0);
         if (prof) prof_begin(2, s3, true);
         learn_kernel<T><<<g.gL, 256, 0, s3>>>(p, d_ctx_, k, dl, dd);
@@ -1256,24 +1923,68 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
           synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
           cudaEventRecord(evPush(k + 1), s2);
         }
+        cudaEventRecord(evP(k), s3);
       }
-      cudaEventRecord(evP(k), s3);
-      learn_prev = learn;
+    };
+    // Capture order = launch order of sibling nodes: the next neuron kernel (the only serial chain)
+    // goes in before the side kernels of the step it does not depend on.
+    const bool chain_first = !(cfg_.reserved[1] & 1024);
+    cap_neuron(0);
+    for (int k = 0; k < n; ++k) {
+      int dl, dd;
+      const bool learn = wants_learn(a, k, &dl, &dd);
+      if (k + 1 < n && !learn && chain_first) { cap_neuron(k + 1); cap_side(k); }
+      else { cap_side(k); if (k + 1 < n) cap_neuron(k + 1); }
     }
+    cudaEvent_t evN = evNk[0];
     // join everything, then the window-end Euler
     cudaEventRecord(evS(n), s2);
-    cudaStreamWaitEvent(s1, evS(n), 0);
-    if (s3_used) { cudaEventRecord(evP(n), s3); cudaStreamWaitEvent(s1, evP(n), 0); }
-    neuron_kernel<T, true, false><<<g.gN, 256, 0, s1>>>(p, d_ctx_, n, 1);
-    cudaError_t e = cudaStreamEndCapture(s1, &graph);
+    cudaStreamWaitEvent(sN, evS(n), 0);
+    if (s3_used) { cudaEventRecord(evP(n), s3); cudaStreamWaitEvent(sN, evP(n), 0); }
+    if (pass_open) {
+      // the pass still in flight ends with the window: replay its log onto the post-learn sd
+      cudaStreamWaitEvent(s4, evS(n), 0);
+      if (s3_used) cudaStreamWaitEvent(s4, evP(n), 0);
+      learn_replay_kernel<T><<<n_sm_ * 2, 256, 0, s4>>>(p);
+      learn_spill_reset_kernel<T><<<1, 1, 0, s4>>>(p);
+      last_pass_launches_ += 2;
+      cudaEventRecord(evFin, s4);
+      cudaStreamWaitEvent(sN, evFin, 0);
+    }
+    neuron_kernel<T, true, false><<<g.gN, 256, 0, sN>>>(p, d_ctx_, n, 1);
+    cudaEventRecord(evN, sN);
+    cudaStreamWaitEvent(s0, evN, 0);
+    cudaError_t e = cudaStreamEndCapture(s0, &graph);
     if (e != cudaSuccess || !graph) {
       for (auto& ev : prof_events_) cudaEventDestroy(ev);
       prof_events_.clear();
       prof_events_.swap(saved_events);
       err = std::string("graph capture: ") + cudaGetErrorString(e); return SNN_ERR_CUDA;
     }
+    if (cfg_.reserved[1] & 2048) {  // experiment 2048: explicit launch priorities on the kernel nodes
+      size_t nn = 0;
+      cudaGraphGetNodes(graph, nullptr, &nn);
+      std::vector<cudaGraphNode_t> nodes(nn);
+      cudaGraphGetNodes(graph, nodes.data(), &nn);
+      int plo = 0, phi = 0;
+      cudaDeviceGetStreamPriorityRange(&plo, &phi);
+      for (auto nd : nodes) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
+        int pr = phi + 1 < plo ? phi + 1 : plo;
+        if (kp.func == (void*)neuron_kernel<T, true, true> || kp.func == (void*)neuron_kernel<T, false, true> ||
+            kp.func == (void*)neuron_kernel<T, true, false>) pr = phi;
+        else if (kp.func == (void*)learn_pass_tma_kernel<T> || kp.func == (void*)learn_pass_kernel<T>) pr = plo;
+        cudaKernelNodeAttrValue v; memset(&v, 0, sizeof(v));
+        v.priority = pr;
+        cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributePriority, &v);
+      }
+      cudaGetLastError();
+    }
     CachedGraph cg;
-    cg.key = key; cg.prof_used = prof_used_; cg.prof_cls = prof_cls_;
+    cg.key = key; cg.prof_used = prof_used_; cg.prof_cls = prof_cls_; cg.pass_launches = last_pass_launches_;
     cg.prof_events.swap(prof_events_);
     prof_events_.swap(saved_events);
     e = cudaGraphInstantiate(&cg.exec, graph, 0);
@@ -1287,6 +1998,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
   }
   prof_used_ = hit->prof_used;
   prof_cls_ = hit->prof_cls;
+  last_pass_launches_ = hit->pass_launches;
   graph_prof_events_ = &hit->prof_events;
   SNN_CUDA_OK(cudaGraphLaunch(hit->exec, stream_));
   return SNN_OK;
@@ -1392,9 +2104,14 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   SNN_CUDA_OK(cudaMemcpyAsync(c_before, p.counters, sizeof(c_before), cudaMemcpyDeviceToHost, stream_));
   SNN_CUDA_OK(cudaMemsetAsync(p.blk_ev, 0, kMaxSynBlocks * sizeof(unsigned long long), stream_));
   SNN_CUDA_OK(cudaMemsetAsync(p.blk_ltp, 0, kMaxSynBlocks * sizeof(unsigned long long), stream_));
+  if (p.tl) {
+    SNN_CUDA_OK(cudaMemsetAsync(p.tl, 0xFF, kTlClasses * kTlSteps * sizeof(unsigned long long), stream_));
+    SNN_CUDA_OK(cudaMemsetAsync(p.tl + kTlClasses * kTlSteps, 0, kTlClasses * kTlSteps * sizeof(unsigned long long), stream_));
+  }
 
   // ---- the window
   const bool graphable = use_graph_ && !p.exact && a.n_force == 0 && a.n_cur == 0 && profiling_ != 1 && !exchange_;
+  last_pass_launches_ = 0;
   if (graphable) {
     int rc = launch_graph(a, profiling_ == 2, err);
     if (rc) return rc;
@@ -1425,11 +2142,17 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     if (total > 0) SNN_CUDA_OK(cudaMemcpyAsync(a.spikes_out, b_rec_.ptr, total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     for (int k = 0; k <= n; ++k) a.spike_offsets[k] = h_off[k];
   }
+  LearnCtl lc_h;
+  SNN_CUDA_OK(cudaMemcpyAsync(&lc_h, p.lc, sizeof(lc_h), cudaMemcpyDeviceToHost, stream_));
   SNN_CUDA_OK(cudaMemcpyAsync(c_after, p.counters, sizeof(c_after), cudaMemcpyDeviceToHost, stream_));
   SNN_CUDA_OK(cudaMemcpyAsync(h_blk_, p.blk_ev, kMaxSynBlocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
   SNN_CUDA_OK(cudaMemcpyAsync(h_blk_ + kMaxSynBlocks, p.blk_ltp, kMaxSynBlocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
   SNN_CUDA_OK(cudaEventRecord(ev_end_, stream_));
   SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+  cur_ = (int)(lc_h.state >> 31);
+  if ((lc_h.state & kFrontAll) != kFrontAll) {
+    err = "internal: learn pass still open at the end of the window"; return SNN_ERR_STATE;
+  }
   if (a.spikes_out && (int64_t)(c_after[0] - c_before[0]) > a.spikes_cap) {
     err = "spikes_cap too small: record truncated"; rc = SNN_ERR_CAPACITY;
   }
@@ -1458,6 +2181,7 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
         for (int k = 0; k < n; ++k) nl += wants_learn(a, k, &dl, &dd) ? 1 : 0;
         s.learn_launches = nl;
       }
+      s.reserved = last_pass_launches_;  // async pass: chunk + control kernels (learn_launches counts passes)
     } else if (profiling_ != 1) {
       s.neuron_launches = n + 1; s.synapse_launches = (p.exact ? 3 : 2) * n;
       int nl = 0, dl, dd;

@@ -56,6 +56,11 @@ class SparseNetwork:
         max_delay = int(params.pop("max_delay", int(delay.max()) if delay is not None and len(delay) else 1))
         use_graph = bool(params.pop("graph", True))
         exp_flags = int(params.pop("exp_flags", 0))
+        learn_async = {"auto": 0, "off": 1, "force": 2}[params.pop("learn_async", "auto")]
+        learn_log_cap = int(params.pop("learn_log_cap", 0))
+        learn_tile_k = int(params.pop("learn_tile_k", 0))
+        learn_stages = int(params.pop("learn_stages", 0))
+        learn_blocks = int(params.pop("learn_blocks", 0))
         cfg = default_config(
             dtype=L.SNN_F64 if dtype == "f64" else L.SNN_F32,
             mode=L.SNN_MODE_EXACT if mode == "exact" else L.SNN_MODE_FAST,
@@ -66,6 +71,11 @@ class SparseNetwork:
         if not use_graph:
             cfg.reserved[0] = 1  # plain stream-ordered launches instead of the captured window graph
         cfg.reserved[1] = exp_flags
+        cfg.reserved[2] = learn_blocks   # asynchronous learn pass: blocks per SM (0 = default)
+        cfg.reserved[3] = learn_tile_k   # tile of the asynchronous pass in units of 1024 synapses (0 = 32)
+        cfg.reserved[6] = learn_stages   # TMA pipeline depth of the asynchronous pass (0 = 6)
+        cfg.reserved[5] = learn_log_cap  # total entries of the sd-update log (0 = by size)
+        cfg.reserved[4] = learn_async    # 0 auto (large nets), 1 in-place pass only, 2 always asynchronous
         self.cfg = cfg
         self.n_neurons = int(cfg.n_neurons)
         self.n_instances = int(n_instances)

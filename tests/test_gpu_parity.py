@@ -282,7 +282,7 @@ def test_errors_and_field_roundtrip():
     assert st.n_syn_events == 0 and st.n_spikes == sum(len(s) for s in sp) > 0
 
 
-@pytest.mark.parametrize("graph", [True, False])
+@pytest.mark.parametrize("graph", [True, False, "async"])
 def test_fast_scheduler_bitexact_with_frozen_weights(graph):
     """With learn_base = 0 and no dopamine the weights stay +-1, so the atomic scatter sums are
     exact in any order and the production scheduler (CUDA graph, ltp/learn overlapped on a second
@@ -299,8 +299,9 @@ def test_fast_scheduler_bitexact_with_frozen_weights(graph):
     train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
     ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax, learn_base=0.0)
     ref = run_oracle_sparse(ora, noise, train)
+    kw = dict(graph=True, learn_async="force") if graph == "async" else dict(graph=graph, learn_async="off")
     net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="fast", max_delay=dmax,
-                        learn_base=0.0, graph=graph)
+                        learn_base=0.0, **kw)
     got = []
     for lo in range(0, t, 200):  # three windows: the second and third reuse the cached graph
         sp, _ = net.run(200, noise[lo:lo + 200], train[lo:lo + 200])
@@ -316,6 +317,57 @@ def test_fast_scheduler_bitexact_with_frozen_weights(graph):
     assert np.count_nonzero(sd_o) > 1000
     assert np.array_equal(net.get(L.FIELD_V), ora.get(0))
     assert np.array_equal(net.get(L.FIELD_TRACE), ora.get(2))
+
+
+@pytest.mark.parametrize("log_cap,batched", [(0, False), (4000, False), (0, True)])
+def test_fast_async_learn_matches_oracle(log_cap, batched):
+    """The asynchronous learn pass (production mode): learn!(k) streams beside steps k+1.. — pushes
+    of not-yet-processed synapses form clamp(w + g*sd) on the fly from the frozen buffer, their sd
+    updates are logged and replayed.  With real learning (base rate + dopamine) the fp64 production
+    build must still reproduce the oracle: identical spikes while rounding noise has not flipped a
+    threshold test, weights and sd to 1e-9 afterwards (atomic sums differ in the last bit only).
+    log_cap = 4000 leaves one or two entries per log region, so most logged updates take the dense
+    spill path."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    nper, ne, fan, dmax, t = 2500, 2000, 60, 8, 300
+    B = 4 if batched else 1
+    n = nper * B
+    rowptr, post, w, delay = synth.fixed_fanout(nper, ne, fan, dmax, seed=81, n_instances=B)
+    noise = synth.thalamic_noise(t, n, seed=13)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    da_events = [(55, b, 0.5 + 0.1 * b) for b in range(B)] + [(171, 0, 0.3)]
+    da_events.sort(key=lambda x: x[0])
+    oras, refs = [], []
+    for b in range(B):
+        sl = slice(rowptr[b * nper], rowptr[(b + 1) * nper])
+        rp = rowptr[b * nper:(b + 1) * nper + 1] - rowptr[b * nper]
+        o = po.Sparse(nper, ne, rp, post[sl] - b * nper, w[sl], delay[sl], max_delay=dmax)
+        refs.append(run_oracle_sparse(o, noise[:, b * nper:(b + 1) * nper], train,
+                                      [(s, 0, a) for s, i, a in da_events if i == b]))
+        oras.append(o)
+    net = SparseNetwork(nper, ne, rowptr, post, w, delay, n_instances=B, dtype="f64", mode="fast", max_delay=dmax,
+                        learn_async="force", learn_log_cap=log_cap)
+    got = []
+    for lo in range(0, t, 100):
+        sp, st = net.run(100, noise[lo:lo + 100], train[lo:lo + 100],
+                         da_events=[(s - lo, i, a) for s, i, a in da_events if lo <= s < lo + 100])
+        assert st.learn_launches == 10
+        got += sp
+    for k in range(t):
+        want = np.concatenate([refs[b][k] + b * nper for b in range(B)])
+        assert np.array_equal(got[k], want), k
+    assert sum(len(r) for r in refs[0]) > 500
+    wg, sg = net.get(L.FIELD_W), net.get(L.FIELD_SD)
+    for b in range(B):
+        sl = slice(rowptr[b * nper], rowptr[(b + 1) * nper])
+        plastic = np.repeat(np.arange(nper), np.diff(rowptr[b * nper:(b + 1) * nper + 1])) < ne
+        wo, so = oras[b].get(4), oras[b].get(5)
+        assert np.abs(wg[sl] - wo).max() <= 1e-9
+        assert np.abs(sg[sl][plastic] - so[plastic]).max() <= 1e-9 * max(1.0, np.abs(so).max())
+        assert np.abs(wo[plastic] - 1.0).max() > 1e-3  # learning did move the weights
 
 
 def test_variant_e_layered_izhikevich_exact():
