@@ -150,11 +150,15 @@ def run_b200(args):
     t_build = time.perf_counter()
     if args.partition and world > 1:
         # ONE network, neuron-partitioned over the ranks, spike bitmap all-gathered per ms (NCCL)
-        from rl_stdp_b200.partition import PartitionedRank, TorchDistExchange, plan
+        from rl_stdp_b200.partition import PartitionedRank, TorchDistExchange, connect_dist, plan
         rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9)
         lo, hi = plan(n, world)[rank]
-        net = PartitionedRank(n, ne, rowptr, post, w, delay, lo, hi, TorchDistExchange().callback(), dtype="f32",
-                              mode="fast", noise="philox", device=local, max_delay=dmax, noise_seed=10)
+        cb = TorchDistExchange().callback() if args.partition == "nccl" else None
+        net = PartitionedRank(n, ne, rowptr, post, w, delay, lo, hi, cb, dtype="f32",
+                              mode="fast", noise="philox", device=local, max_delay=dmax, noise_seed=10,
+                              learn_async=args.learn_async)
+        if cb is None:
+            connect_dist(net)  # in-library exchange: peer stores over NVLink, device-side wait
         n_plastic = int(np.count_nonzero(np.repeat(np.arange(n), np.diff(rowptr))[net.local_index] < ne))
     else:
         rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9 + rank, n_instances=n_inst)
@@ -256,8 +260,10 @@ def run_b200(args):
                        "instances_per_gpu": n_inst,
                        "window_ms_per_step": W, "learn_period_ms": LEARN_PERIOD, "noise": "on-device Philox4x32-10",
                        "instances": 1 if (args.partition and world > 1) else world,
-                       "sharding": ("one network, neurons partitioned over the ranks, NCCL all-gather of the spike "
-                                    "bitmap per ms") if (args.partition and world > 1) else
+                       "sharding": ("one network, neurons partitioned over the ranks; per ms the spike bitmap is exchanged "
+                                    + ("by NCCL all-gather from a host callback" if args.partition == "nccl" else
+                                       "by peer stores over NVLink + device-side wait (in-graph)"))
+                                   if (args.partition and world > 1) else
                                    "one independent instance per GPU, no collective",
                        "l2": "working set 2.2 GB per instance >> 126 MB L2 (no flush needed)"},
             "sim_ms_per_wall_s": sim_ms * n_inst * (1 if (args.partition and world > 1) else world) / (dev_ms * 1e-3),
@@ -451,7 +457,9 @@ def main():
     ap.add_argument("--learn-tile-k", type=int, default=0, help="async learn pass: tile size in units of 1024 synapses (0 = 32)")
     ap.add_argument("--learn-stages", type=int, default=0, help="async learn pass: TMA pipeline depth (0 = 6)")
     ap.add_argument("--learn-blocks", type=int, default=0, help="async learn pass: blocks per SM (0 = default)")
-    ap.add_argument("--partition", action="store_true", help="N>1: one network neuron-partitioned over the ranks (strong scaling) instead of one instance per rank")
+    ap.add_argument("--partition", nargs="?", const="p2p", default=None, choices=["p2p", "nccl"],
+                    help="N>1: ONE network neuron-partitioned over the ranks (strong scaling) instead of one instance "
+                         "per rank; p2p = in-library exchange over peer memory, nccl = host callback + all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -20,6 +20,7 @@ SNN_RATE_BASE_PLUS_DA, SNN_RATE_DA, SNN_RATE_ETA_DA = 0, 1, 2
 (FIELD_V, FIELD_U, FIELD_TRACE, FIELD_HO, FIELD_W, FIELD_SD, FIELD_DA, FIELD_I) = range(8)
 SNN_ERR_CAPACITY = -5
 SNN_TL_CLASSES, SNN_TL_STEPS = 6, 258
+SNN_PEER_BLOB_BYTES = 192
 
 
 class SnnConfig(C.Structure):
@@ -106,6 +107,8 @@ SYMBOLS = {
     "snn_set_stream": (C.c_int32, [_VP, _VP]),
     "snn_debug_timeline": (C.c_int32, [_VP, _VP, C.c_int64]),
     "snn_set_partition": (C.c_int32, [_VP, C.c_int64, C.c_int64, _VP, _VP]),
+    "snn_partition_export": (C.c_int32, [_VP, _VP]),
+    "snn_partition_connect": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP]),
     # batched LIF actors
     "snn_actor_config_default": (C.c_int32, [C.POINTER(SnnActorConfig)]),
     "snn_actor_create": (C.c_int32, [C.POINTER(SnnActorConfig), C.POINTER(_VP)]),

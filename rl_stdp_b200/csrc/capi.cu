@@ -165,6 +165,20 @@ int32_t snn_set_partition(snn_net* net, int64_t neuron_lo, int64_t neuron_hi, sn
   return rc ? fail(rc, err) : SNN_OK;
 }
 
+int32_t snn_partition_export(snn_net* net, void* blob) {
+  if (!net || !blob) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->export_peer(reinterpret_cast<snn::PeerBlob*>(blob), err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_partition_connect(snn_net* net, int32_t rank, int32_t world, const void* blobs) {
+  if (!net || !blobs) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->connect_peers(rank, world, reinterpret_cast<const snn::PeerBlob*>(blobs), err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
 int32_t snn_reset_v(snn_net* net) {
   if (!net) return fail(SNN_ERR_INVALID, "null net");
   std::string err;

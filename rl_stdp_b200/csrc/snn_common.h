@@ -45,6 +45,19 @@ int build_topology(const snn_config& cfg, const int64_t* h_rowptr, const int32_t
 int sort_segments(int32_t* d_keys, int64_t n_items, const int32_t* d_offsets, int32_t n_segments,
                   cudaStream_t stream, std::string& err);
 
+// What a rank publishes so that its peers can store spike bitmaps into its ring (snn_partition_export)
+constexpr uint64_t kPeerMagic = 0x534e4e5032503031ull;  // "SNNP2P01"
+struct PeerBlob {
+  uint64_t magic;
+  int32_t pid, device;
+  uint64_t raw_bits, raw_flag;     // device pointers, valid inside the exporting process
+  unsigned char ipc_bits[64];      // cudaIpcMemHandle_t of the bitmap ring
+  unsigned char ipc_flag[64];      // cudaIpcMemHandle_t of the step counters
+  int32_t words_per_slot, ring;
+  unsigned char pad[24];
+};
+static_assert(sizeof(PeerBlob) == SNN_PEER_BLOB_BYTES, "PeerBlob must match SNN_PEER_BLOB_BYTES");
+
 struct StepArgs {
   int32_t n_steps;
   const double* noise;
@@ -72,6 +85,8 @@ class IEngine {
   virtual int add_dopamine(int instance, double amount, std::string& err) = 0;
   virtual int reset_v(std::string& err) = 0;
   virtual int set_partition(int64_t lo, int64_t hi, snn_exchange_fn fn, void* user, std::string& err) = 0;
+  virtual int export_peer(PeerBlob* b, std::string& err) = 0;
+  virtual int connect_peers(int rank, int world, const PeerBlob* blobs, std::string& err) = 0;
   virtual int get_timeline(unsigned long long* host, int64_t count, std::string& err) = 0;
   virtual int64_t n_synapses() const = 0;
   virtual int64_t step_index() const = 0;

@@ -40,6 +40,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -93,6 +94,7 @@ __device__ __forceinline__ double philox_noise(uint64_t seed, int64_t t, int64_t
 }
 
 constexpr int kMaxSynBlocks = 148 * 16 * 2;
+constexpr int kMaxRanks = 8;
 
 // State of the asynchronous learn pass.  `state` packs (cur << 31) | frontier, frontier in units
 // of 32 synapses: synapses with (e >> 5) < frontier have been processed by the pass in flight
@@ -155,6 +157,14 @@ struct DevNet {
   // neuron partition (multi-GPU): this rank integrates neurons [part_lo, part_hi)
   // and holds every synapse whose POST is in that range; spike bitmaps are exchanged per step
   int64_t part_lo, part_hi;
+  // peer-to-peer spike exchange (snn_partition_connect): after detection every rank stores its
+  // bitmap words straight into the peers' rings over NVLink / NVSwitch and then raises, in each
+  // peer's memory, the count of steps it has completed; the receiver waits on those counters
+  uint32_t* peer_bits[kMaxRanks];            // peers' `bits` rings (IPC-mapped / same-process pointers)
+  unsigned long long* peer_flag[kMaxRanks];  // peers' xflag arrays
+  unsigned long long* xflag;                 // [kMaxRanks] own: xflag[src] = steps completed by rank src
+  uint32_t* xdone;                           // [0] block counter of neuron_kernel, [1] timeout flag
+  int32_t n_ranks, rank;
   // diagnostics (exp_flags & 2): per-node first-block-start / last-block-end %globaltimer stamps
   unsigned long long* tl;
 };
@@ -281,7 +291,7 @@ __device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, u
 // values.  A warp covers 128 neurons = 4 bitmap words.  Arrays are padded to Nld.
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool EULER, bool DETECT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : 2)
 neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev) {
   typedef Ops<T> O;
   // programmatic dependent launch (no-ops unless the launch carries the attribute): let the next
@@ -337,15 +347,27 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
 
   // whole warps only: the last rank's range is padded up to Nld (padding neurons are inactive)
   const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2);
-  for (uint32_t q = q_lo + blockIdx.x * blockDim.x + threadIdx.x; q < q_hi; q += gridDim.x * blockDim.x) {
-    const uint32_t j0 = q << 2;
-    // ---- all loads first
-    Vec4<T> v = ld4(p.v + j0), u = ld4(p.u + j0), I, tp, ho;
-    if (EULER) I = ld4(I_prev + j0);
+  // The grid covers the local neurons in ~two strides: the loads of a thread's next quad are
+  // issued before its current quad is processed, so the two round trips overlap (one resident
+  // wave instead of 1.65 waves of one-quad threads).
+  const uint32_t qstride = gridDim.x * blockDim.x;
+  uint32_t q = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  Vec4<T> nv, nu, nI, ntp, nho;
+  auto load_quad = [&](uint32_t qq) {
+    const uint32_t jj = qq << 2;
+    nv = ld4(p.v + jj); nu = ld4(p.u + jj);
+    if (EULER) nI = ld4(I_prev + jj);
     if (DETECT) {
-      tp = ld4(trp + j0);
-      if (p.homeostasis) ho = ld4(p.ho + j0);
+      ntp = ld4(trp + jj);
+      if (p.homeostasis) nho = ld4(p.ho + jj);
     }
+  };
+  if (q < q_hi) load_quad(q);
+  for (; q < q_hi; q += qstride) {
+    const uint32_t j0 = q << 2;
+    // ---- all loads first (issued one iteration ahead)
+    Vec4<T> v = nv, u = nu, I = nI, tp = ntp, ho = nho;
+    if (q + qstride < q_hi) load_quad(q + qstride);
     const uint32_t l0 = p.B == 1 ? j0 : j0 % Nper;
     bool exc[4], act[4];
 #pragma unroll
@@ -469,7 +491,58 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
     st4(p.v + j0, v);
     st4(p.u + j0, u);
   }
+  if (DETECT && p.n_ranks > 1) {
+    // Fused exchange: the last block to finish copies this rank's bitmap words of the step into
+    // every peer's ring (coalesced 16-byte stores over NVLink) and then publishes the step there.
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(&p.xdone[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const uint32_t w_lo = q_lo >> 3, w_hi = q_hi >> 3;  // 8 quads per bitmap word; multiples of 4
+      const uint4* __restrict__ srcw = reinterpret_cast<const uint4*>(bits + w_lo);
+      const uint32_t n4 = (w_hi - w_lo) >> 2;
+      for (int r = 0; r < p.n_ranks; ++r) {
+        if (r == p.rank) continue;
+        uint4* __restrict__ dstw = reinterpret_cast<uint4*>(p.peer_bits[r] + (size_t)slot * p.W + w_lo);
+        for (uint32_t x = threadIdx.x; x < n4; x += blockDim.x) dstw[x] = __ldcg(srcw + x);
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < (unsigned)p.n_ranks && (int)threadIdx.x != p.rank) {
+        unsigned long long* f = p.peer_flag[threadIdx.x] + p.rank;
+        const unsigned long long val = (unsigned long long)(t + 1);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(val) : "memory");
+      }
+      if (threadIdx.x == 0) p.xdone[0] = 0u;
+    }
+  }
   tl_end(p.tl, 0, k);
+}
+
+// xwait_kernel(k): one warp; lane r waits until rank r has published step k (its bitmap words are
+// then in this rank's ring).  A separate one-warp kernel so that nothing else ever spins; gives up
+// after ~4 s (flag in xdone[1]) instead of hanging the device.
+template <typename T>
+__global__ void xwait_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
+  const unsigned long long want = (unsigned long long)(cx->t0 + k + 1);
+  const int r = threadIdx.x;
+  if (r < p.n_ranks && r != p.rank && *reinterpret_cast<volatile uint32_t*>(&p.xdone[1]) == 0u) {
+    const unsigned long long t_start = gtime_ns();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.xflag + r) : "memory");
+      if (v >= want) break;
+      if (gtime_ns() - t_start > 4000000000ull) { p.xdone[1] = 1u; break; }
+      __nanosleep(200);
+    }
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1321,6 +1394,10 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMalloc(&p.counters, 4 * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMalloc(&p.blk_ev, kMaxSynBlocks * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMalloc(&p.blk_ltp, kMaxSynBlocks * sizeof(unsigned long long)));
+    SNN_CUDA_OK(cudaMalloc(&p.xflag, kMaxRanks * sizeof(unsigned long long)));
+    SNN_CUDA_OK(cudaMemsetAsync(p.xflag, 0, kMaxRanks * sizeof(unsigned long long), stream_));
+    SNN_CUDA_OK(cudaMalloc(&p.xdone, 2 * sizeof(uint32_t)));
+    SNN_CUDA_OK(cudaMemsetAsync(p.xdone, 0, 2 * sizeof(uint32_t), stream_));
     SNN_CUDA_OK(cudaMalloc(&p.lc, sizeof(LearnCtl)));
     SNN_CUDA_OK(cudaMalloc(&p.lg, (size_t)p.B * sizeof(T)));
     SNN_CUDA_OK(cudaMemsetAsync(p.lg, 0, (size_t)p.B * sizeof(T), stream_));
@@ -1516,7 +1593,6 @@ class Engine : public IEngine {
     }
     if (p_.B != 1) { err = "neuron partitioning applies to a single network instance"; return SNN_ERR_INVALID; }
     const bool whole = lo == 0 && hi == p_.N;
-    if (!whole && !fn) { err = "a partial partition needs an exchange function"; return SNN_ERR_INVALID; }
     if (t_ != 0) { err = "set the partition before the first step"; return SNN_ERR_STATE; }
     drop_graph();
     p_.part_lo = lo; p_.part_hi = hi;
@@ -1531,6 +1607,57 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMemcpy(host, p_.tl, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return SNN_OK;
   }
+  // ---- peer-to-peer exchange set-up (snn_partition_export / snn_partition_connect)
+  int export_peer(PeerBlob* b, std::string& err) override {
+    SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    memset(b, 0, sizeof(*b));
+    b->magic = kPeerMagic; b->pid = (int32_t)getpid(); b->device = cfg_.device;
+    b->raw_bits = (uint64_t)(uintptr_t)p_.bits; b->raw_flag = (uint64_t)(uintptr_t)p_.xflag;
+    b->words_per_slot = p_.W; b->ring = p_.R;
+    SNN_CUDA_OK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(b->ipc_bits), p_.bits));
+    SNN_CUDA_OK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(b->ipc_flag), p_.xflag));
+    return SNN_OK;
+  }
+  int connect_peers(int rank, int world, const PeerBlob* blobs, std::string& err) override {
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) { err = "rank / world out of range (world <= 8)"; return SNN_ERR_INVALID; }
+    if (t_ != 0) { err = "connect the peers before the first step"; return SNN_ERR_STATE; }
+    SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    drop_graph();
+    close_peers();
+    DevNet<T>& p = p_;
+    for (int r = 0; r < world; ++r) {
+      const PeerBlob& b = blobs[r];
+      if (b.magic != kPeerMagic || b.words_per_slot != p.W || b.ring != p.R) {
+        err = "peer blob of rank " + std::to_string(r) + " does not match this network (size / max_delay)"; return SNN_ERR_INVALID;
+      }
+      if (r == rank) { p.peer_bits[r] = p.bits; p.peer_flag[r] = p.xflag; continue; }
+      if (b.pid == (int32_t)getpid()) {  // several handles in one process: plain pointers
+        if (b.device != cfg_.device) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
+          cudaGetLastError();
+        }
+        p.peer_bits[r] = reinterpret_cast<uint32_t*>((uintptr_t)b.raw_bits);
+        p.peer_flag[r] = reinterpret_cast<unsigned long long*>((uintptr_t)b.raw_flag);
+      } else {
+        void *pb = nullptr, *pf = nullptr;
+        SNN_CUDA_OK(cudaIpcOpenMemHandle(&pb, *reinterpret_cast<const cudaIpcMemHandle_t*>(b.ipc_bits), cudaIpcMemLazyEnablePeerAccess));
+        SNN_CUDA_OK(cudaIpcOpenMemHandle(&pf, *reinterpret_cast<const cudaIpcMemHandle_t*>(b.ipc_flag), cudaIpcMemLazyEnablePeerAccess));
+        ipc_opened_.push_back(pb); ipc_opened_.push_back(pf);
+        p.peer_bits[r] = reinterpret_cast<uint32_t*>(pb);
+        p.peer_flag[r] = reinterpret_cast<unsigned long long*>(pf);
+      }
+    }
+    p.n_ranks = world; p.rank = rank;
+    return SNN_OK;
+  }
+  void close_peers() {
+    for (void* q : ipc_opened_) cudaIpcCloseMemHandle(q);
+    ipc_opened_.clear();
+    p_.n_ranks = 0; p_.rank = 0;
+    for (int r = 0; r < kMaxRanks; ++r) { p_.peer_bits[r] = nullptr; p_.peer_flag[r] = nullptr; }
+  }
+
   int64_t n_synapses() const override { return p_.E; }
   int64_t step_index() const override { return t_; }
   void set_profiling(int mode) override { profiling_ = mode; }
@@ -1595,6 +1722,8 @@ class Engine : public IEngine {
     cudaFree(p.v); cudaFree(p.u); cudaFree(p.ho); cudaFree(p.Iacc); cudaFree(p.trace); cudaFree(p.bits);
     cudaFree(p.spk_list); cudaFree(p.spk_cnt); cudaFree(p.da); cudaFree(p.counters); cudaFree(p.blk_ev);
     cudaFree(p.blk_ltp); free_synapse_state(); cudaFree(d_ctx_); cudaFree(p.tl); cudaFree(p.lc); cudaFree(p.lg);
+    close_peers();
+    cudaFree(p.xflag); cudaFree(p.xdone);
     if (h_ctx_) cudaFreeHost(h_ctx_);
     if (h_blk_) cudaFreeHost(h_blk_);
     b_noise_.release(); b_noise64_.release(); b_ev_off_.release(); b_ev_inst_.release(); b_ev_amt_.release();
@@ -1644,7 +1773,9 @@ class Engine : public IEngine {
     DevNet<T>& p = p_;
     Launch l;
     const int64_t local_quads = ((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2) - (p.part_lo >> 2);
-    l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((local_quads + 255) / 256, (int64_t)n_sm_ * 8));
+    // two quads per thread when that still fills the GPU (see neuron_kernel); exp 16384: one quad
+    const int64_t qpt = (local_quads >= (int64_t)n_sm_ * 256 * 4 && !(cfg_.reserved[1] & 16384)) ? 2 : 1;
+    l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((local_quads + 256 * qpt - 1) / (256 * qpt), (int64_t)n_sm_ * 8));
     l.gR = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 - local_quads + 255) / 256, (int64_t)n_sm_ * 8));
     if (gA_ == 0) {
       int per_sm = 0;
@@ -1695,6 +1826,7 @@ class Engine : public IEngine {
   WindowCtx<T>* d_ctx_ = nullptr; WindowCtx<T>* h_ctx_ = nullptr;
   unsigned long long* h_blk_ = nullptr;
   DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_, b_cur_idx_, b_cur_val_;
+  std::vector<void*> ipc_opened_;
   snn_exchange_fn exchange_ = nullptr; void* exchange_user_ = nullptr; int exchange_failed_ = 0;
   const std::vector<cudaEvent_t>* graph_prof_events_ = nullptr;
   std::vector<CachedGraph> graphs_;  // a few (length, train pattern, profiling) variants
@@ -1739,6 +1871,10 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
       uint32_t* slot_bits = p.bits + (size_t)slot_host(t_ + k) * p.W;
       const int rc = exchange_(exchange_user_, slot_bits, p.part_lo / 32, (p.part_hi - p.part_lo + 31) / 32, p.W, (void*)s);
       if (rc != 0) { exchange_failed_ = rc; return; }
+      remote_kernel<T><<<g.gR, 256, 0, s>>>(p, d_ctx_, k);
+    } else if (k < n && p.n_ranks > 1) {
+      // peer-to-peer exchange: neuron_kernel has stored this rank's words into the peers' rings
+      xwait_kernel<T><<<1, 32, 0, s>>>(p, d_ctx_, k);
       remote_kernel<T><<<g.gR, 256, 0, s>>>(p, d_ctx_, k);
     }
     if (prof) prof_end(s);
@@ -1848,7 +1984,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
     cudaEvent_t evL = dep_ev_[8], evFork = dep_ev_[9], evFin = dep_ev_[10];
     auto evPush = [&](int step) { return dep_ev_[1 + ((step % 3) + 3) % 3]; };  // pushes consumed by Euler(step)
     auto evS = [&](int step) { return dep_ev_[4 + (step & 1)]; };
-    auto evP = [&](int step) { return dep_ev_[6 + (step & 1)]; };
+    auto evP = [&](int step) { return dep_ev_[12 + (step & 3)]; };  // ltp done (ring of 4)
     SNN_CUDA_OK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
     cudaEventRecord(evFork, s0);                    // fork point
     cudaStreamWaitEvent(sN, evFork, 0);
@@ -1873,6 +2009,10 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
         cudaLaunchKernelEx(&lc, neuron_kernel<T, true, true>, p, (const WindowCtx<T>*)d_ctx_, (int32_t)k, (int32_t)1);
       }
       else neuron_kernel<T, true, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
+      if (p.n_ranks > 1) {  // neuron-partitioned: wait for the peers' words of this step, replay their detection
+        xwait_kernel<T><<<1, 32, 0, sN>>>(p, d_ctx_, k);
+        remote_kernel<T><<<g.gR, 256, 0, sN>>>(p, d_ctx_, k);
+      }
       cudaEventRecord(evNk[k & 1], sN);
     };
     auto cap_side = [&](int k) {
@@ -1881,7 +2021,12 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
       const bool learn_prev = k >= 1 && wants_learn(a, k - 1, &dl, &dd);
       wants_learn(a, k, &dl, &dd);
       const bool push_next = k + 1 < n;
-      // s2: synapse(k)
+      // s2: synapse(k).  It also keeps ltp from falling behind: neuron(m) overwrites the trace-ring
+      // slot of step m-R (R = Dmax+2), which ltp(j) still reads for j <= m-3.  neuron(m) waits for the
+      // pushes of synapse(m-2), so making synapse(k) wait for ltp(k-1) closes the chain.  (Without this
+      // edge a delayed ltp stream read pre traces that had already been overwritten — seen once in ~10
+      // runs as one synapse with a spurious LTP term.)
+      if (k >= 1) cudaStreamWaitEvent(s2, evP(k - 1), 0);
       cudaStreamWaitEvent(s2, evNk[k & 1], 0);
       if (learn_prev && !async) cudaStreamWaitEvent(s2, evL, 0);  // sd reductions must not race the in-place pass
       if (push_next && !learn) {
@@ -2016,6 +2161,9 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   DevNet<T>& p = p_;
   const int n = a.n_steps;
   const int64_t N = p.N;
+  if (!(p.part_lo == 0 && p.part_hi == p.N) && !exchange_ && p.n_ranks < 2) {
+    err = "a partial neuron partition needs an exchange: snn_partition_connect or an exchange callback"; return SNN_ERR_STATE;
+  }
 
   // ---- validate + stage the window's inputs (persistent grow-only buffers)
   std::vector<int32_t> ev_off, ev_inst, force_off(n + 1, 0), force_ids;
@@ -2143,13 +2291,19 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     for (int k = 0; k <= n; ++k) a.spike_offsets[k] = h_off[k];
   }
   LearnCtl lc_h;
+  uint32_t xdone_h[2] = {0, 0};
   SNN_CUDA_OK(cudaMemcpyAsync(&lc_h, p.lc, sizeof(lc_h), cudaMemcpyDeviceToHost, stream_));
+  SNN_CUDA_OK(cudaMemcpyAsync(xdone_h, p.xdone, sizeof(xdone_h), cudaMemcpyDeviceToHost, stream_));
   SNN_CUDA_OK(cudaMemcpyAsync(c_after, p.counters, sizeof(c_after), cudaMemcpyDeviceToHost, stream_));
   SNN_CUDA_OK(cudaMemcpyAsync(h_blk_, p.blk_ev, kMaxSynBlocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
   SNN_CUDA_OK(cudaMemcpyAsync(h_blk_ + kMaxSynBlocks, p.blk_ltp, kMaxSynBlocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
   SNN_CUDA_OK(cudaEventRecord(ev_end_, stream_));
   SNN_CUDA_OK(cudaStreamSynchronize(stream_));
   cur_ = (int)(lc_h.state >> 31);
+  if (xdone_h[1]) {
+    cudaMemsetAsync(p.xdone, 0, 2 * sizeof(uint32_t), stream_);
+    err = "peer exchange timed out: a rank of the partition did not publish its spikes"; return SNN_ERR_STATE;
+  }
   if ((lc_h.state & kFrontAll) != kFrontAll) {
     err = "internal: learn pass still open at the end of the window"; return SNN_ERR_STATE;
   }

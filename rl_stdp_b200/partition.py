@@ -7,7 +7,12 @@ neurons it does not own (replicated pre-trace ring + spike list).  `da` and the 
 (Philox keyed by the global neuron id) are replicated, so the union of the ranks reproduces the
 single-GPU run — bit for bit in exact mode.
 
-Exchange back-ends for `snn_set_partition`'s callback:
+In-library exchange (the production path, `connect_local` / `connect_dist`): the ranks swap IPC
+handles of their bitmap rings once; from then on `neuron_kernel` stores its spike words into the
+peers' rings over NVLink and raises a step counter there, the receiver waits on the device — no
+host code per step, the window runs as one CUDA graph.
+
+Exchange back-ends for `snn_set_partition`'s callback (host-driven, kept for comparison):
   TorchDistExchange  one process per GPU, `torch.distributed.all_gather_into_tensor` (NCCL over
                      NVLink) on the library's stream; also usable with CPU tensors over gloo.
   LocalExchange      several handles inside one process (threads), device-to-device copies — used
@@ -152,10 +157,39 @@ class LocalExchange:
         return f
 
 
+def export_blob(net) -> bytes:
+    buf = C.create_string_buffer(L.SNN_PEER_BLOB_BYTES)
+    L.check(L.load().snn_partition_export(net._h, buf))
+    return buf.raw
+
+
+def connect(net, rank: int, blobs):
+    """blobs: one export_blob() per rank, in rank order."""
+    allb = b"".join(blobs)
+    L.check(L.load().snn_partition_connect(net._h, int(rank), len(blobs), allb))
+
+
+def connect_local(nets):
+    """Handles of ONE process (same or different GPUs): plain device pointers, no IPC."""
+    blobs = [export_blob(n) for n in nets]
+    for r, n in enumerate(nets):
+        connect(n, r, blobs)
+
+
+def connect_dist(net, group=None):
+    """One process per GPU: all-gather the CUDA IPC blobs with torch.distributed, connect, barrier."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, export_blob(net), group=group)
+    connect(net, rank, blobs)
+    dist.barrier(group)  # nobody steps before every rank has mapped its peers
+
+
 class PartitionedRank(SparseNetwork):
     """The rank-local handle: same API as SparseNetwork, synapses restricted to local posts."""
 
-    def __init__(self, n_neurons, n_exc, rowptr, post, w, delay, lo, hi, exchange_cb, **kw):
+    def __init__(self, n_neurons, n_exc, rowptr, post, w, delay, lo, hi, exchange_cb=None, **kw):
         rp, po, ww, dd, idx = split_by_post(rowptr, post, w, delay, lo, hi)
         self.lo, self.hi, self.local_index = int(lo), int(hi), idx
         if dd is not None and "max_delay" not in kw:

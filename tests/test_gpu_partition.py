@@ -71,6 +71,82 @@ def test_partition_fast_mode_frozen_weights():
         assert np.array_equal(net.get(L.FIELD_V)[net.lo:net.hi], ora.get(0)[net.lo:net.hi])
 
 
+def _p2p_worker(rank, world, port, q, mode="exact", same_device=False):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = 0 if same_device else rank
+    torch.cuda.set_device(dev)
+    if same_device:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import _lib as L
+    from rl_stdp_b200.partition import PartitionedRank, connect_dist, plan
+    n, ne, dmax, t, rowptr, post, w, delay, noise, train = _case(seed=91 if mode == "fast" else 81)
+    kw = dict(learn_base=0.0) if mode == "fast" else {}
+    ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax, **kw)
+    ref = run_oracle_sparse(ora, noise, train)
+    lo, hi = plan(n, world)[rank]
+    net = PartitionedRank(n, ne, rowptr, post, w, delay, lo, hi, None, dtype="f64", mode=mode,
+                          max_delay=dmax, device=dev, **kw)
+    connect_dist(net)
+    spikes = []
+    for lo_t in range(0, t, 100):  # three windows: the captured graph of the production path is reused
+        sp, _ = net.run(100, noise[lo_t:lo_t + 100], train[lo_t:lo_t + 100])
+        spikes += sp
+    ok = all(np.array_equal(spikes[k], ref[k]) for k in range(t))
+    if mode == "exact":
+        ok = ok and rel_err(net.get(L.FIELD_W), ora.get(4)[net.local_index]) <= 1e-9
+    sd_o = ora.get(5)[net.local_index]
+    ok = ok and np.abs(net.get(L.FIELD_SD) - sd_o).max() <= 1e-9 * max(1.0, np.abs(sd_o).max())
+    ok = ok and np.array_equal(net.get(L.FIELD_V)[net.lo:net.hi], ora.get(0)[net.lo:net.hi])
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_workers(fn, world, port, *extra):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=fn, args=(r, world, port, q) + extra) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        res = [q.get(timeout=420) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    return res
+
+
+@pytest.mark.parametrize("mode,port", [("exact", 29575), ("fast", 29577)])
+def test_partition_p2p_ipc_two_processes_one_gpu(mode, port):
+    """The in-library exchange end to end on ONE GPU: two processes (one rank each) map each other's
+    bitmap ring and step counters through CUDA IPC; neuron_kernel stores its spike words into the
+    peer's ring and raises the peer's counter, xwait_kernel waits on the device.  The two contexts
+    time-slice the GPU, so a waiting rank is preempted until its peer has published."""
+    res = _run_workers(_p2p_worker, 2, port, mode, True)
+    assert all(ok for _, ok in res), res
+
+
+def test_partition_p2p_two_gpus():
+    """CUDA-IPC mapped peer rings over NVLink, one process per GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    res = _run_workers(_p2p_worker, 2, 29573, "fast", False)
+    assert all(ok for _, ok in res), res
+    res = _run_workers(_p2p_worker, 2, 29579, "exact", False)
+    assert all(ok for _, ok in res), res
+
+
 def _nccl_worker(rank, world, port, q):
     import os
     import torch
