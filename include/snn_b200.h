@@ -246,13 +246,15 @@ typedef int32_t (*snn_exchange_fn)(void* user, void* words, int64_t word_lo, int
 int32_t snn_set_partition(snn_net* net, int64_t neuron_lo, int64_t neuron_hi, snn_exchange_fn fn, void* user);
 
 /* In-library exchange for the neuron partition (no callback, the window runs as one CUDA graph):
- * every rank exports a blob describing its bitmap ring (CUDA IPC handles; plain pointers when the
- * ranks are handles of one process), the blobs of all ranks are gathered by the host program (e.g.
- * torch.distributed.all_gather / MPI) and passed, in rank order, to snn_partition_connect.  From
- * then on neuron_kernel stores this rank's spike words of every step straight into the peers'
- * rings over NVLink / NVSwitch and publishes the step in their memory; the receiving side waits
- * for the peers' counters on the device.  Call after snn_set_partition(lo, hi, NULL, NULL), before
- * the first step; all ranks must have connected before any of them steps (host barrier). */
+ * every rank exports a blob describing its exchange ring (a CUDA IPC handle; a plain pointer when
+ * the ranks are handles of one process), the blobs of all ranks are gathered by the host program
+ * (e.g. torch.distributed.all_gather_object / MPI) and passed, in rank order, to
+ * snn_partition_connect.  From then on neuron_kernel stores this rank's spike-bitmap words of every
+ * step straight into the peers' rings over NVLink / NVSwitch, each word in one 8-byte store together
+ * with its step number (flag-in-data: no fence, no separate flag); remote_kernel on the receiving
+ * side spins on the step tag of exactly the words it needs.  Call after
+ * snn_set_partition(lo, hi, NULL, NULL), before the first step; all ranks must have connected before
+ * any of them steps (host barrier). */
 #define SNN_PEER_BLOB_BYTES 192
 int32_t snn_partition_export(snn_net* net, void* blob /* SNN_PEER_BLOB_BYTES */);
 int32_t snn_partition_connect(snn_net* net, int32_t rank, int32_t world, const void* blobs /* world blobs */);

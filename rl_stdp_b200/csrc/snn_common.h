@@ -50,11 +50,10 @@ constexpr uint64_t kPeerMagic = 0x534e4e5032503031ull;  // "SNNP2P01"
 struct PeerBlob {
   uint64_t magic;
   int32_t pid, device;
-  uint64_t raw_bits, raw_flag;     // device pointers, valid inside the exporting process
-  unsigned char ipc_bits[64];      // cudaIpcMemHandle_t of the bitmap ring
-  unsigned char ipc_flag[64];      // cudaIpcMemHandle_t of the step counters
+  uint64_t raw_ring;               // device pointer of the exchange ring, valid inside the exporting process
+  unsigned char ipc_ring[64];      // cudaIpcMemHandle_t of the exchange ring ((word, step) pairs)
   int32_t words_per_slot, ring;
-  unsigned char pad[24];
+  unsigned char pad[96];
 };
 static_assert(sizeof(PeerBlob) == SNN_PEER_BLOB_BYTES, "PeerBlob must match SNN_PEER_BLOB_BYTES");
 

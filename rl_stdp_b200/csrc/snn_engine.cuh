@@ -157,13 +157,15 @@ struct DevNet {
   // neuron partition (multi-GPU): this rank integrates neurons [part_lo, part_hi)
   // and holds every synapse whose POST is in that range; spike bitmaps are exchanged per step
   int64_t part_lo, part_hi;
-  // peer-to-peer spike exchange (snn_partition_connect): after detection every rank stores its
-  // bitmap words straight into the peers' rings over NVLink / NVSwitch and then raises, in each
-  // peer's memory, the count of steps it has completed; the receiver waits on those counters
-  uint32_t* peer_bits[kMaxRanks];            // peers' `bits` rings (IPC-mapped / same-process pointers)
-  unsigned long long* peer_flag[kMaxRanks];  // peers' xflag arrays
-  unsigned long long* xflag;                 // [kMaxRanks] own: xflag[src] = steps completed by rank src
-  uint32_t* xdone;                           // [0] block counter of neuron_kernel, [1] timeout flag
+  // peer-to-peer spike exchange (snn_partition_connect): right after detection every warp stores
+  // its 4 bitmap words straight into every peer's exchange ring over NVLink / NVSwitch.  Each word
+  // travels in one 8-byte store together with the step it belongs to (word, step+1) — the
+  // low-latency flag-in-data protocol: no fence, no separate flag, no end-of-kernel rendezvous on
+  // the sending side (a __threadfence_system after peer stores cost ~12 us per step); the receiver
+  // (remote_kernel) spins on the tag of exactly the words it needs.
+  uint2* ll;                  // [R][W] own exchange ring, written by the peers
+  uint2* peer_ll[kMaxRanks];  // the peers' rings (CUDA-IPC mapped / same-process pointers)
+  uint32_t* xdone;            // [1] = a wait timed out
   int32_t n_ranks, rank;
   // diagnostics (exp_flags & 2): per-node first-block-start / last-block-end %globaltimer stamps
   unsigned long long* tl;
@@ -441,6 +443,18 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
       word |= __shfl_xor_sync(0xffffffffu, word, 2);
       word |= __shfl_xor_sync(0xffffffffu, word, 4);
       if ((lane & 7) == 0) bits[j0 >> 5] = word;
+      if (p.n_ranks > 1 && !(p.exp_flags & 65536)) {
+        // fused exchange: a warp owns 4 consecutive bitmap words = two 16-byte stores of
+        // (word, step tag) pairs into every peer's ring over NVLink
+        const unsigned w1 = __shfl_sync(0xffffffffu, word, 8), w2 = __shfl_sync(0xffffffffu, word, 16),
+                       w3 = __shfl_sync(0xffffffffu, word, 24);
+        if (lane < p.n_ranks && lane != p.rank) {
+          const uint32_t tag = (uint32_t)(t + 1);
+          uint4* dst = reinterpret_cast<uint4*>(p.peer_ll[lane] + (size_t)slot * p.W + (j0 >> 5));
+          dst[0] = make_uint4(word, tag, w1, tag);
+          dst[1] = make_uint4(w2, tag, w3, tag);
+        }
+      }
       if (__any_sync(0xffffffffu, nib != 0)) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -491,58 +505,26 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
     st4(p.v + j0, v);
     st4(p.u + j0, u);
   }
-  if (DETECT && p.n_ranks > 1) {
-    // Fused exchange: the last block to finish copies this rank's bitmap words of the step into
-    // every peer's ring (coalesced 16-byte stores over NVLink) and then publishes the step there.
-    __shared__ int s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      s_last = atomicAdd(&p.xdone[0], 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      const uint32_t w_lo = q_lo >> 3, w_hi = q_hi >> 3;  // 8 quads per bitmap word; multiples of 4
-      const uint4* __restrict__ srcw = reinterpret_cast<const uint4*>(bits + w_lo);
-      const uint32_t n4 = (w_hi - w_lo) >> 2;
-      for (int r = 0; r < p.n_ranks; ++r) {
-        if (r == p.rank) continue;
-        uint4* __restrict__ dstw = reinterpret_cast<uint4*>(p.peer_bits[r] + (size_t)slot * p.W + w_lo);
-        for (uint32_t x = threadIdx.x; x < n4; x += blockDim.x) dstw[x] = __ldcg(srcw + x);
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x < (unsigned)p.n_ranks && (int)threadIdx.x != p.rank) {
-        unsigned long long* f = p.peer_flag[threadIdx.x] + p.rank;
-        const unsigned long long val = (unsigned long long)(t + 1);
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(val) : "memory");
-      }
-      if (threadIdx.x == 0) p.xdone[0] = 0u;
-    }
-  }
   tl_end(p.tl, 0, k);
 }
 
-// xwait_kernel(k): one warp; lane r waits until rank r has published step k (its bitmap words are
-// then in this rank's ring).  A separate one-warp kernel so that nothing else ever spins; gives up
-// after ~4 s (flag in xdone[1]) instead of hanging the device.
+// The bitmap word `wi` of ring slot `slot` as sent by its owner for the step tagged `tag`: spins on
+// the (word, tag) pair until the tag matches.  Gives up after ~4 s (flag in xdone[1]) instead of
+// hanging the device.
 template <typename T>
-__global__ void xwait_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
-  const unsigned long long want = (unsigned long long)(cx->t0 + k + 1);
-  const int r = threadIdx.x;
-  if (r < p.n_ranks && r != p.rank && *reinterpret_cast<volatile uint32_t*>(&p.xdone[1]) == 0u) {
-    const unsigned long long t_start = gtime_ns();
-    for (;;) {
-      unsigned long long v;
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.xflag + r) : "memory");
-      if (v >= want) break;
-      if (gtime_ns() - t_start > 4000000000ull) { p.xdone[1] = 1u; break; }
-      __nanosleep(200);
-    }
+__device__ __forceinline__ uint32_t ll_word(const DevNet<T>& p, int slot, uint32_t wi, uint32_t tag) {
+  const uint2* q = p.ll + (size_t)slot * p.W + wi;
+  uint32_t w, g;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(w), "=r"(g) : "l"(q) : "memory");
+  if (g == tag) return w;
+  if (*reinterpret_cast<volatile uint32_t*>(&p.xdone[1]) != 0u) return 0u;
+  const unsigned long long t_start = gtime_ns();
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(w), "=r"(g) : "l"(q) : "memory");
+    if (g == tag) return w;
+    if (gtime_ns() - t_start > 4000000000ull) { p.xdone[1] = 1u; return 0u; }
+    __nanosleep(64);
   }
-  __syncwarp();
-  if (threadIdx.x == 0) __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -554,15 +536,16 @@ __global__ void xwait_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, i
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
+remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t wait_peers) {
   typedef Ops<T> O;
   tl_begin(p.tl, 4, k);
+  const bool from_ll = wait_peers && !(p.exp_flags & 65536);
   const int lane = threadIdx.x & 31;
   const int64_t t = cx->t0 + k;
   const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
   T* __restrict__ tr = p.trace + (size_t)slot * p.Nld;
   const T* __restrict__ trp = p.trace + (size_t)prev * p.Nld;
-  const uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
+  uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
   int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.Nld;
   int32_t* __restrict__ rec_ids = cx->rec_ids;
   const int64_t rec_cap = cx->rec_cap;
@@ -580,7 +563,14 @@ remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
     const uint32_t q = r < q_lo ? r : r + (q_hi - q_lo);  // part bounds are multiples of 128: warps stay whole
     const uint32_t j0 = q << 2;
     Vec4<T> tp = ld4(trp + j0);
-    const unsigned nib = (bits[j0 >> 5] >> (j0 & 31)) & 0xFu;
+    uint32_t word;
+    if (from_ll) {  // peer-to-peer exchange: wait for the owner's (word, step) pair, keep `bits` complete
+      word = ll_word<T>(p, slot, j0 >> 5, (uint32_t)(t + 1));
+      if ((lane & 7) == 0) bits[j0 >> 5] = word;
+    } else {
+      word = bits[j0 >> 5];
+    }
+    const unsigned nib = (word >> (j0 & 31)) & 0xFu;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const bool s = (nib >> c) & 1u;
@@ -1394,8 +1384,6 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMalloc(&p.counters, 4 * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMalloc(&p.blk_ev, kMaxSynBlocks * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMalloc(&p.blk_ltp, kMaxSynBlocks * sizeof(unsigned long long)));
-    SNN_CUDA_OK(cudaMalloc(&p.xflag, kMaxRanks * sizeof(unsigned long long)));
-    SNN_CUDA_OK(cudaMemsetAsync(p.xflag, 0, kMaxRanks * sizeof(unsigned long long), stream_));
     SNN_CUDA_OK(cudaMalloc(&p.xdone, 2 * sizeof(uint32_t)));
     SNN_CUDA_OK(cudaMemsetAsync(p.xdone, 0, 2 * sizeof(uint32_t), stream_));
     SNN_CUDA_OK(cudaMalloc(&p.lc, sizeof(LearnCtl)));
@@ -1413,6 +1401,8 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMemsetAsync(p.Iacc, 0, 2 * N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.trace, 0, (size_t)p.R * N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.bits, 0, (size_t)p.R * p.W * sizeof(uint32_t), stream_));
+    SNN_CUDA_OK(cudaMalloc(&p.ll, (size_t)p.R * p.W * sizeof(uint2)));
+    SNN_CUDA_OK(cudaMemsetAsync(p.ll, 0xFF, (size_t)p.R * p.W * sizeof(uint2), stream_));  // tag 0xffffffff: never a step
     SNN_CUDA_OK(cudaMemsetAsync(p.spk_cnt, 0, (size_t)p.R * sizeof(int32_t), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.da, 0, 2 * (size_t)p.B * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.counters, 0, 4 * sizeof(unsigned long long), stream_));
@@ -1612,10 +1602,9 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaSetDevice(cfg_.device));
     memset(b, 0, sizeof(*b));
     b->magic = kPeerMagic; b->pid = (int32_t)getpid(); b->device = cfg_.device;
-    b->raw_bits = (uint64_t)(uintptr_t)p_.bits; b->raw_flag = (uint64_t)(uintptr_t)p_.xflag;
+    b->raw_ring = (uint64_t)(uintptr_t)p_.ll;
     b->words_per_slot = p_.W; b->ring = p_.R;
-    SNN_CUDA_OK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(b->ipc_bits), p_.bits));
-    SNN_CUDA_OK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(b->ipc_flag), p_.xflag));
+    SNN_CUDA_OK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(b->ipc_ring), p_.ll));
     return SNN_OK;
   }
   int connect_peers(int rank, int world, const PeerBlob* blobs, std::string& err) override {
@@ -1630,22 +1619,19 @@ class Engine : public IEngine {
       if (b.magic != kPeerMagic || b.words_per_slot != p.W || b.ring != p.R) {
         err = "peer blob of rank " + std::to_string(r) + " does not match this network (size / max_delay)"; return SNN_ERR_INVALID;
       }
-      if (r == rank) { p.peer_bits[r] = p.bits; p.peer_flag[r] = p.xflag; continue; }
+      if (r == rank) { p.peer_ll[r] = p.ll; continue; }
       if (b.pid == (int32_t)getpid()) {  // several handles in one process: plain pointers
         if (b.device != cfg_.device) {
           cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
           if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
           cudaGetLastError();
         }
-        p.peer_bits[r] = reinterpret_cast<uint32_t*>((uintptr_t)b.raw_bits);
-        p.peer_flag[r] = reinterpret_cast<unsigned long long*>((uintptr_t)b.raw_flag);
+        p.peer_ll[r] = reinterpret_cast<uint2*>((uintptr_t)b.raw_ring);
       } else {
-        void *pb = nullptr, *pf = nullptr;
-        SNN_CUDA_OK(cudaIpcOpenMemHandle(&pb, *reinterpret_cast<const cudaIpcMemHandle_t*>(b.ipc_bits), cudaIpcMemLazyEnablePeerAccess));
-        SNN_CUDA_OK(cudaIpcOpenMemHandle(&pf, *reinterpret_cast<const cudaIpcMemHandle_t*>(b.ipc_flag), cudaIpcMemLazyEnablePeerAccess));
-        ipc_opened_.push_back(pb); ipc_opened_.push_back(pf);
-        p.peer_bits[r] = reinterpret_cast<uint32_t*>(pb);
-        p.peer_flag[r] = reinterpret_cast<unsigned long long*>(pf);
+        void* pb = nullptr;
+        SNN_CUDA_OK(cudaIpcOpenMemHandle(&pb, *reinterpret_cast<const cudaIpcMemHandle_t*>(b.ipc_ring), cudaIpcMemLazyEnablePeerAccess));
+        ipc_opened_.push_back(pb);
+        p.peer_ll[r] = reinterpret_cast<uint2*>(pb);
       }
     }
     p.n_ranks = world; p.rank = rank;
@@ -1655,7 +1641,7 @@ class Engine : public IEngine {
     for (void* q : ipc_opened_) cudaIpcCloseMemHandle(q);
     ipc_opened_.clear();
     p_.n_ranks = 0; p_.rank = 0;
-    for (int r = 0; r < kMaxRanks; ++r) { p_.peer_bits[r] = nullptr; p_.peer_flag[r] = nullptr; }
+    for (int r = 0; r < kMaxRanks; ++r) p_.peer_ll[r] = nullptr;
   }
 
   int64_t n_synapses() const override { return p_.E; }
@@ -1723,7 +1709,7 @@ class Engine : public IEngine {
     cudaFree(p.spk_list); cudaFree(p.spk_cnt); cudaFree(p.da); cudaFree(p.counters); cudaFree(p.blk_ev);
     cudaFree(p.blk_ltp); free_synapse_state(); cudaFree(d_ctx_); cudaFree(p.tl); cudaFree(p.lc); cudaFree(p.lg);
     close_peers();
-    cudaFree(p.xflag); cudaFree(p.xdone);
+    cudaFree(p.ll); cudaFree(p.xdone);
     if (h_ctx_) cudaFreeHost(h_ctx_);
     if (h_blk_) cudaFreeHost(h_blk_);
     b_noise_.release(); b_noise64_.release(); b_ev_off_.release(); b_ev_inst_.release(); b_ev_amt_.release();
@@ -1871,11 +1857,10 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
       uint32_t* slot_bits = p.bits + (size_t)slot_host(t_ + k) * p.W;
       const int rc = exchange_(exchange_user_, slot_bits, p.part_lo / 32, (p.part_hi - p.part_lo + 31) / 32, p.W, (void*)s);
       if (rc != 0) { exchange_failed_ = rc; return; }
-      remote_kernel<T><<<g.gR, 256, 0, s>>>(p, d_ctx_, k);
+      remote_kernel<T><<<g.gR, 256, 0, s>>>(p, d_ctx_, k, 0);
     } else if (k < n && p.n_ranks > 1) {
       // peer-to-peer exchange: neuron_kernel has stored this rank's words into the peers' rings
-      xwait_kernel<T><<<1, 32, 0, s>>>(p, d_ctx_, k);
-      remote_kernel<T><<<g.gR, 256, 0, s>>>(p, d_ctx_, k);
+      remote_kernel<T><<<g.gR, 256, 0, s>>>(p, d_ctx_, k, 1);
     }
     if (prof) prof_end(s);
     if (k == n) break;
@@ -2010,8 +1995,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
       }
       else neuron_kernel<T, true, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
       if (p.n_ranks > 1) {  // neuron-partitioned: wait for the peers' words of this step, replay their detection
-        xwait_kernel<T><<<1, 32, 0, sN>>>(p, d_ctx_, k);
-        remote_kernel<T><<<g.gR, 256, 0, sN>>>(p, d_ctx_, k);
+        remote_kernel<T><<<g.gR, 256, 0, sN>>>(p, d_ctx_, k, 1);
       }
       cudaEventRecord(evNk[k & 1], sN);
     };

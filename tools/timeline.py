@@ -28,14 +28,33 @@ def main():
     wl = bench.WORKLOADS[a.workload]
     n, ne, fan, dmax = wl[:4]
     n_inst = wl[4] if len(wl) > 4 else 1
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9, n_instances=n_inst)
-    net = SparseNetwork(n, ne, rowptr, post, w, delay, n_instances=n_inst, dtype="f32", mode="fast", noise="philox",
+    if world > 1:  # torchrun: ONE network neuron-partitioned over the ranks, in-library exchange
+        import torch, torch.distributed as dist
+        from rl_stdp_b200.partition import PartitionedRank, connect_dist, plan
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        lo, hi = plan(n, world)[rank]
+        net = PartitionedRank(n, ne, rowptr, post, w, delay, lo, hi, None, dtype="f32", mode="fast", noise="philox",
+                              device=local, max_delay=dmax, noise_seed=10, exp_flags=2 | a.exp_flags,
+                              learn_async=a.learn_async)
+        connect_dist(net)
+    else:
+        net = SparseNetwork(n, ne, rowptr, post, w, delay, n_instances=n_inst, dtype="f32", mode="fast", noise="philox",
                         max_delay=dmax, noise_seed=10, exp_flags=2 | a.exp_flags, learn_blocks=a.learn_blocks,
-                        learn_async=a.learn_async)
+                            learn_async=a.learn_async)
     W = a.window_ms
     for kw in range(a.warm):
         tr, da = bench.window_inputs(kw, W)
         _, st = net.run(W, None, tr, da_events=da, record=False)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     S, K = L.SNN_TL_STEPS, L.SNN_TL_CLASSES
     buf = np.zeros(2 * K * S, np.uint64)
     L.check(L.load().snn_debug_timeline(net._h, buf.ctypes.data_as(C.c_void_p), buf.size))
