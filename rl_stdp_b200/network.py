@@ -34,6 +34,7 @@ class StepStats:
     learn_launches: int
     neuron_launches: int
     synapse_launches: int
+    pass_launches: int = 0  # kernels of the asynchronous learn passes (pass + control + replay)
 
 
 def default_config(**over) -> L.SnnConfig:
@@ -156,7 +157,7 @@ class SparseNetwork:
                               cap, C.byref(st))
         L.check(rc)
         stats = StepStats(st.n_spikes, st.n_syn_events, st.n_ltp_events, st.device_ms, st.learn_ms, st.neuron_ms,
-                          st.synapse_ms, st.learn_launches, st.neuron_launches, st.synapse_launches)
+                          st.synapse_ms, st.learn_launches, st.neuron_launches, st.synapse_launches, st.reserved)
         spikes = None
         if record:
             spikes = [out[offs[k]:offs[k + 1]].copy() for k in range(n_steps)]
