@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 1
+#define SNN_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -100,6 +100,12 @@ typedef struct snn_config {
   double theta;            /* homeostasis increment (0 = off)  net_res.jl:171 */
   double ttheta;           /* homeostasis decay                net_res.jl:204 */
   int64_t ho_from;         /* local ids >= ho_from (and < n_exc) get homeostasis (arch[1]) */
+  int32_t ho_inh;          /* 1: inhibitory spikers raise their ho too (Old_net/new_net_col_sep.jl:149-150
+                              filters on `x > arch[1]` only); 0: excitatory only (net_res.jl:169) */
+  int32_t variant_g;       /* 1: the ordering of Old_net/DASTDP.jl + Julia_DA_STDPv2.jl:71-96 — LTP reads the
+                              pre trace of the PREVIOUS ms (STDP[pre,msec], :62-68: a presynaptic spike of
+                              the same ms is not seen), all LTP before all LTD, the input current
+                              accumulates in descending presynaptic id (:70-80 walks `firings` backwards) */
   int32_t reserved[8];     /* tuning / A-B switches, 0 = default:
                               [0] = 1 disables the CUDA-graph scheduler (plain launches)
                               [1] experiment flags (bit 1: kernel timeline for snn_debug_timeline)

@@ -27,6 +27,7 @@ mutable struct SnnConfig
     sd_decay_mode::Int32; rate_mode::Int32; noise_mode::Int32; plastic_ei::Int32
     noise_amp::Float64; noise_seed::UInt64
     theta::Float64; ttheta::Float64; ho_from::Int64
+    ho_inh::Int32; variant_g::Int32
     reserved::NTuple{8,Int32}
     SnnConfig() = new()
 end

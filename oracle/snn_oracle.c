@@ -183,6 +183,10 @@ typedef struct {
   int32_t Dmax, R;
   /* parameters (mirror of snn_config) */
   int32_t threshold_ge, sd_decay_mode, rate_mode, plastic_ei;
+  int32_t ho_inh;    /* new_net_col_sep.jl:149-150: inhibitory spikers raise their ho too */
+  int32_t variant_g; /* Old_net/DASTDP.jl ordering: LTP reads the pre trace of the previous ms
+                        (:62-68 STDP[pre,msec]), every LTP precedes every LTD (Julia_DA_STDPv2.jl:78-80),
+                        I accumulates in descending presynaptic id (:70-80 walks firings backwards) */
   double vthresh, v_reset, a_exc, a_inh, d_exc, d_inh, trace_set, trace_decay, apost, apre,
       da_decay, learn_base, eta, wmin, wmax, sd_decay, theta, ttheta;
   int64_t ho_from;
@@ -221,6 +225,7 @@ ora_sparse* ora_sparse_create(int64_t N, int64_t Nper, int64_t Ne, int32_t Dmax,
   o->da_decay = p[11]; o->learn_base = p[12]; o->eta = p[13]; o->wmin = p[14]; o->wmax = p[15];
   o->sd_decay = p[16]; o->sd_decay_mode = (int32_t)p[17]; o->rate_mode = (int32_t)p[18];
   o->plastic_ei = (int32_t)p[19]; o->theta = p[20]; o->ttheta = p[21]; o->ho_from = (int64_t)p[22];
+  o->ho_inh = (int32_t)p[23]; o->variant_g = (int32_t)p[24];
   o->rowptr = (int64_t*)malloc((N + 1) * sizeof(int64_t));
   memcpy(o->rowptr, rowptr, (N + 1) * sizeof(int64_t));
   o->post = (int32_t*)malloc((E + 1) * sizeof(int32_t));
@@ -334,7 +339,7 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
   for (int64_t q = 0; q < k; ++q) {
     int64_t n = spiked[q];
     int64_t l = n % Nper;
-    if (l < Ne && l >= o->ho_from) o->ho[n] += o->theta; /* net_res.jl:170-171 */
+    if ((l < Ne || o->ho_inh) && l >= o->ho_from) o->ho[n] += o->theta; /* net_res.jl:170-171 */
     o->v[n] = o->v_reset;
     o->u[n] += (l < Ne) ? o->d_exc : o->d_inh;
   }
@@ -343,7 +348,9 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
   /* arrivals, pull order */
   for (int64_t j = 0; j < N; ++j) {
     double acc = o->I[j];
-    for (int64_t q = o->colptr[j]; q < o->colptr[j + 1]; ++q) {
+    const int64_t c0 = o->colptr[j], c1 = o->colptr[j + 1];
+    for (int64_t qq = c0; qq < c1; ++qq) {
+      int64_t q = o->variant_g ? (c1 - 1 - (qq - c0)) : qq; /* DASTDP.jl:72 last_ walks backwards */
       int64_t e = o->in_syn[q];
       int64_t ts = t - (o->delay[e] - 1);
       if (ts < 0) continue;
@@ -368,11 +375,12 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
     int ltp = sp[j];
     if (ltp) o->n_ltp_events++;
     if (!ltd && !ltp) continue;
-    double pre_tr = ts >= 0 ? o->trace[(size_t)(ts % R) * N + i] : 0.0;
+    int64_t tsp = o->variant_g ? ts - 1 : ts; /* DASTDP.jl:65 STDP[pre_neurons,msec]: before this ms's spikes */
+    double pre_tr = tsp >= 0 ? o->trace[(size_t)(tsp % R) * N + i] : 0.0;
     double up = o->apost * pre_tr;
     double dn = o->apre * tr[j];
     double x = o->sd[e];
-    if (ltd && ltp) x = (j <= i) ? (x + up) - dn : (x - dn) + up;
+    if (ltd && ltp) x = (o->variant_g || j <= i) ? (x + up) - dn : (x - dn) + up;
     else if (ltp) x = x + up;
     else x = x - dn;
     o->sd[e] = x;

@@ -36,6 +36,7 @@ class SnnConfig(C.Structure):
         ("sd_decay_mode", C.c_int32), ("rate_mode", C.c_int32), ("noise_mode", C.c_int32),
         ("plastic_ei", C.c_int32), ("noise_amp", C.c_double), ("noise_seed", C.c_uint64),
         ("theta", C.c_double), ("ttheta", C.c_double), ("ho_from", C.c_int64),
+        ("ho_inh", C.c_int32), ("variant_g", C.c_int32),
         ("reserved", C.c_int32 * 8),
     ]
 

@@ -56,7 +56,7 @@ int32_t snn_config_default(snn_config* c) {
   c->da_decay = 0.995; c->learn_base = 0.002; c->eta = 0.0; c->wmin = 0.0; c->wmax = 4.0;
   c->sd_decay = 0.99; c->sd_decay_mode = SNN_SD_DECAY_ON_LEARN; c->rate_mode = SNN_RATE_BASE_PLUS_DA;
   c->noise_mode = SNN_NOISE_REPLAY; c->plastic_ei = 1; c->noise_amp = 13.0; c->noise_seed = 0;
-  c->theta = 0.0; c->ttheta = 1.0; c->ho_from = 0;
+  c->theta = 0.0; c->ttheta = 1.0; c->ho_from = 0; c->ho_inh = 0; c->variant_g = 0;
   return SNN_OK;
 }
 

@@ -153,6 +153,7 @@ struct DevNet {
   double noise_amp; uint64_t noise_seed;
   int64_t ho_from;
   int32_t threshold_ge, sd_decay_mode, rate_mode, plastic_ei, noise_mode, exact, homeostasis;
+  int32_t ho_inh, variant_g;  // see snn_config
   int32_t exp_flags;  // experiments only (snn_config.reserved[1]); 0 in production
   // neuron partition (multi-GPU): this rank integrates neurons [part_lo, part_hi)
   // and holds every synapse whose POST is in that range; spike bitmaps are exchanged per step
@@ -429,7 +430,7 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
           uint32_t l = l0 + c;
           if (l >= Nper) l -= Nper;
           T h = ho.x[c];
-          if (s && exc[c] && (int64_t)l >= p.ho_from) h = O::add(h, p.theta);
+          if (s && (exc[c] || p.ho_inh) && (int64_t)l >= p.ho_from) h = O::add(h, p.theta);
           ho.x[c] = O::mul(h, p.ttheta);
         }
         tp.x[c] = s ? p.trace_set : (t > 0 ? O::mul(tp.x[c], p.trace_decay) : (T)0);
@@ -659,7 +660,8 @@ gather_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
     if (p.noise_mode == SNN_NOISE_REPLAY) acc = noise[j];
     else if (p.noise_mode == SNN_NOISE_PHILOX) acc = (T)philox_noise(p.noise_seed, t, j, p.noise_amp);
     const uint32_t c0 = p.colptr[j], c1 = p.colptr[j + 1];
-    for (uint32_t q = c0; q < c1; ++q) {
+    for (uint32_t qq = c0; qq < c1; ++qq) {
+      const uint32_t q = p.variant_g ? c1 - 1u - (qq - c0) : qq;  // DASTDP.jl:72 walks the spikers backwards
       const uint32_t pk = p.in_pre[q];
       const uint32_t i = pk & kPreMask;
       const int sl = wrap_slot(slot - (int)(pk >> kPreBits), p.R);
@@ -733,7 +735,9 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
     const uint32_t inst = p.B == 1 ? 0u : i / Nper, ibase = inst * Nper;
     const bool row_exc = (i - ibase) < Ne;
     const bool row_plastic = LTD && row_exc;
-    const T pre_up = (row_plastic && !ATOMIC) ? O::mul(p.apost, p.trace[(size_t)sl * Nld + i]) : (T)0;
+    // variant_g: the LTP term of a simultaneous post spike reads the pre trace of the step before
+    const T pre_up = (row_plastic && !ATOMIC)
+                         ? O::mul(p.apost, p.trace[(size_t)(p.variant_g ? wrap_slot(sl - 1, p.R) : sl) * Nld + i]) : (T)0;
     if (LTD && gl == 0) n_ev += (s1 - s0);
     for (uint32_t e = (LTD ? s0 : s1) + gl; e < s2; e += G) {
       const uint32_t j = (uint32_t)p.post[e];
@@ -749,7 +753,7 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
         }
         const bool jsp = (bits_now[j >> 5] >> (j & 31)) & 1u;
         T sd = vw.cur[e].y;
-        if (jsp) sd = (j <= i) ? O::sub(O::add(sd, pre_up), dn) : O::add(O::sub(sd, dn), pre_up);
+        if (jsp) sd = (p.variant_g || j <= i) ? O::sub(O::add(sd, pre_up), dn) : O::add(O::sub(sd, dn), pre_up);
         else sd = O::sub(sd, dn);
         vw.cur[e].y = sd;
       }
@@ -809,7 +813,7 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
       for (int q = 0; q < 3; ++q) {
         const uint32_t i = pk[q] & kPreMask;
         const int sl = wrap_slot(slot - (int)(pk[q] >> kPreBits), p.R);
-        toff[q] = (size_t)sl * Nld + i;
+        toff[q] = (size_t)(p.variant_g ? wrap_slot(sl - 1, p.R) : sl) * Nld + i;  // DASTDP.jl:65 STDP[pre,msec]
         if (!ATOMIC && ok[q]) {
           const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
           ok[q] = !((word >> (i & 31)) & 1u);
@@ -1370,7 +1374,8 @@ class Engine : public IEngine {
     DevNet<T>& p = p_;
     memset(&p, 0, sizeof(p));
     p.N = cfg_.n_neurons; p.Nld = (p.N + 127) / 128 * 128; p.Nper = cfg_.n_per_instance; p.Ne = cfg_.n_exc;
-    p.Dmax = cfg_.max_delay; p.R = p.Dmax + 2; p.B = (int32_t)(p.N / p.Nper); p.W = (int32_t)(p.Nld / 32);
+    // ring: R-1 steps of history + the slot being prepared; variant_g reads one step further back
+    p.Dmax = cfg_.max_delay; p.R = p.Dmax + 2 + (cfg_.variant_g ? 1 : 0); p.B = (int32_t)(p.N / p.Nper); p.W = (int32_t)(p.Nld / 32);
     const size_t N = (size_t)p.Nld;  // padded: vector accesses never leave the allocation
     SNN_CUDA_OK(cudaMalloc(&p.v, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.u, N * sizeof(T)));
@@ -1415,6 +1420,7 @@ class Engine : public IEngine {
     p.ho_from = cfg_.ho_from; p.threshold_ge = cfg_.threshold_ge; p.sd_decay_mode = cfg_.sd_decay_mode;
     p.rate_mode = cfg_.rate_mode; p.plastic_ei = cfg_.plastic_ei; p.noise_mode = cfg_.noise_mode;
     p.exact = cfg_.mode == SNN_MODE_EXACT;
+    p.ho_inh = cfg_.ho_inh; p.variant_g = cfg_.variant_g;
     p.exp_flags = cfg_.reserved[1];
     p.part_lo = 0; p.part_hi = p.N;
     if (cfg_.reserved[1] & 2) SNN_CUDA_OK(cudaMalloc(&p.tl, 2 * kTlClasses * kTlSteps * sizeof(unsigned long long)));

@@ -188,3 +188,141 @@ def test_cartpole_restated_physics():
     s2, d2 = po.cartpole_step(np.array([0.0, 0.0, 0.0, 0.0]), 1)
     # one Euler step from rest with +10 N: xacc = temp - pml*thetaacc/total ; theta_dot < 0
     assert s2[1] > 0 and s2[3] < 0 and not d2
+
+
+def _dense_sd_of(ora, rowptr, post, n):
+    pre = np.repeat(np.arange(n), np.diff(rowptr))
+    w, sd = np.zeros((n, n)), np.zeros((n, n))
+    w[pre, post] = ora.get(4)
+    sd[pre, post] = ora.get(5)
+    return w, sd
+
+
+def test_variant_c_restatement_equals_sparse_oracle():
+    """new_net_col_sep.jl restated literally (numpy) == the sparse C oracle configured as variant C
+    (plastic exc->exc only, fixed -0.5 inhibition, homeostasis for every spiker incl. inhibitory)."""
+    from oracle import np_restate as nr, py_oracle as po
+    from rl_stdp_b200 import synth
+    n, ne, t = 120, 96, 400
+    conn = synth.dense_connection(n, 0.15, seed=31)
+    noise = synth.thalamic_noise(t, n, seed=32, amp=40.0)
+    ref = nr.NetColSep(n, ne, conn)
+    pre, post = np.nonzero(conn)
+    rowptr = np.zeros(n + 1, np.int64); np.add.at(rowptr, pre + 1, 1); rowptr = np.cumsum(rowptr)
+    w = np.where(pre < ne, 1.0, -0.5)
+    ora = po.Sparse(n, ne, rowptr, post.astype(np.int32), w, plastic_ei=0, theta=2.0, ttheta=0.9999, ho_inh=1)
+    total = 0
+    for k in range(t):
+        train = (k + 1) % 10 == 0
+        a = ref.step(noise[k], train)
+        b = ora.step(noise[k], train)
+        assert np.array_equal(a, b), k
+        total += len(a)
+        if k == 150:
+            ref.da += 0.5; ora.add_da(0, 0.5)
+    assert total > 300 and np.any(ref.ho[ne:] > 0)  # inhibitory neurons did get homeostasis
+    wd, sdd = _dense_sd_of(ora, rowptr, post, n)
+    s_ref = np.concatenate([ref.s_exc, ref.s_inh], axis=1).T  # [pre, post]
+    assert np.array_equal(wd, s_ref)
+    ee = (conn != 0) & (np.arange(n)[:, None] < ne) & (np.arange(n)[None, :] < ne)
+    assert np.array_equal(sdd[ee], ref.sd.T[:ne][ee[:ne]])
+    assert np.array_equal(ora.get(0), ref.v) and np.array_equal(ora.get(3), ref.ho)
+
+
+@pytest.mark.parametrize("random_graph", [True, False])
+def test_variant_d_restatement_equals_sparse_oracle(random_graph):
+    """net_res.jl restated literally == the sparse oracle configured from the YAML parameter dict."""
+    from oracle import np_restate as nr, py_oracle as po
+    rng = np.random.Generator(np.random.Philox(key=41))
+    P = dict(c=-65.0, de=8.0, di=2.0, ae=0.02, ai=0.1, theta=1.5, ttheta=0.998, apost=1.2, apre=1.7, tda=0.99,
+             wmax=3.0, imin=10.0, imax=40.0, wee=1.0, wei=2.0, wie=-1.5, i_per=0.3)
+    if random_graph:
+        n, ne, arch = 100, 80, [0]
+        conn = (rng.random((n, n)) < 0.12).astype(np.int64)
+        conn[ne:, ne:] = 0                                   # net_res.jl:42
+    else:
+        P.update(wee=9.0, wmax=12.0, wei=25.0, wie=-4.0)     # no thalamic noise in this variant: strong feed-forward drive
+        arch = [12, 10, 8]
+        ne, n = sum(arch), sum(arch) + arch[1]
+        conn = np.zeros((n, n), np.int64)
+        conn[0:12, 12:22] = 1; conn[12:22, 22:30] = 1        # :47-55 layer blocks
+        mat_ie = (rng.random((10, 10)) < 0.3).astype(np.int64); np.fill_diagonal(mat_ie, 0)
+        conn[ne:ne + 10, 12:22] = mat_ie                     # :68 recorded lateral inhibition
+        conn[12:22, ne:ne + 10] = np.eye(10, dtype=np.int64)  # :69
+    ref = nr.NetRes(n, ne, conn, arch, P)
+    pre, post = np.nonzero(conn)
+    rowptr = np.zeros(n + 1, np.int64); np.add.at(rowptr, pre + 1, 1); rowptr = np.cumsum(rowptr)
+    w = np.where(pre < ne, np.where(post < ne, P["wee"], P["wei"]), P["wie"])
+    ora = po.Sparse(n, ne, rowptr, post.astype(np.int32), w, v_reset=P["c"], a_exc=P["ae"], a_inh=P["ai"],
+                    d_exc=P["de"], d_inh=P["di"], theta=P["theta"], ttheta=P["ttheta"], ho_from=arch[0],
+                    apost=P["apost"], apre=P["apre"], da_decay=P["tda"], wmax=P["wmax"],
+                    plastic_ei=1 if random_graph else 0)
+    total = 0
+    n_in = 12 if not random_graph else n
+    for k in range(300):
+        train = (k + 1) % 5 == 0
+        idx = rng.choice(n_in, size=4, replace=False)
+        if k % 3 == 0:   # forced spikes
+            a = ref.step(train, input_spikes=idx)
+            b = ora.step(None, train, idx.astype(np.int32))
+        else:            # injected currents: two half-steps on v[idx] before spike! (:150-160)
+            inten = rng.random(4)
+            a = ref.step(train, input_current=(idx, inten))
+            cur = (P["imax"] - P["imin"]) * inten + P["imin"]
+            v = ora.get(0); u = ora.get(1)
+            for _ in range(2):
+                v[idx] = v[idx] + 0.5 * ((0.04 * v[idx] + 5) * v[idx] + 140 - u[idx] + cur)
+            ora.set(0, v)
+            b = ora.step(None, train)
+        assert np.array_equal(a, b), k
+        total += len(a)
+        if k % 40 == 7:
+            ref.da += 0.3; ora.add_da(0, 0.3)
+    assert total > 200
+    wd, sdd = _dense_sd_of(ora, rowptr, post, n)
+    s_ref = np.zeros((n, n)); s_ref[:ne, :ne] = ref.s_ee; s_ref[:ne, ne:] = ref.s_ei; s_ref[ne:, :ne] = ref.s_ie
+    assert np.array_equal(wd, s_ref)
+    c = conn != 0
+    assert np.array_equal(sdd[:ne, :ne][c[:ne, :ne]], ref.sd_ee[c[:ne, :ne]])
+    if random_graph:
+        assert np.array_equal(sdd[:ne, ne:][c[:ne, ne:]], ref.sd_ei[c[:ne, ne:]])
+        assert np.abs(ref.sd_ei).max() > 0
+    assert np.array_equal(ora.get(0), ref.v) and np.array_equal(ora.get(3), ref.ho)
+    assert np.abs(s_ref[:ne, :ne][c[:ne, :ne]] - P["wee"]).max() > 1e-3  # learning moved the weights
+
+
+def _g_post_table(n, ne, m, seed):
+    """vcat(rand(1:N,Ne,M), rand(1:Ne,Ni,M)) (DASTDP.jl:32) without repeated targets inside a row."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    post = np.zeros((n, m), np.int64)
+    for i in range(n):
+        post[i] = rng.choice(n if i < ne else ne, size=m, replace=False)
+    return post
+
+
+def test_variant_g_restatement_equals_sparse_oracle():
+    """DASTDP.jl + Julia_DA_STDPv2.jl restated literally == the sparse oracle with variant_g = 1
+    (LTP from the previous ms's pre trace, LTP before LTD, descending accumulation) and `>=`."""
+    from oracle import np_restate as nr, py_oracle as po
+    from rl_stdp_b200 import synth
+    n, ne, m, t = 200, 160, 25, 600
+    post = _g_post_table(n, ne, m, 51)
+    noise = synth.thalamic_noise(t, n, seed=52, amp=30.0)
+    ref = nr.NetG(post, ne)
+    rowptr = np.arange(n + 1, dtype=np.int64) * m
+    w = np.repeat(np.where(np.arange(n) < ne, 1.0, -1.0), m)
+    ora = po.Sparse(n, ne, rowptr, post.reshape(-1).astype(np.int32), w, threshold_ge=1, variant_g=1)
+    total = both = 0
+    for k in range(t):
+        msec = k + 1
+        a = ref.step(noise[k], msec)
+        b = ora.step(noise[k], msec % 10 == 0)
+        assert np.array_equal(a, b), k
+        total += len(a)
+        if k == 200:
+            ref.DA += 0.5; ora.add_da(0, 0.5)                # DA_inc after the step (:90)
+    assert total > 500
+    assert np.array_equal(ora.get(4).reshape(n, m), ref.s)
+    assert np.array_equal(ora.get(5).reshape(n, m)[:ne], ref.sd[:ne])  # sd of inhibitory rows is dead state
+    assert np.array_equal(ora.get(0), ref.v)
+    assert np.abs(ref.s[:ne] - 1.0).max() > 1e-3
