@@ -78,3 +78,29 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/_" not in txt, f
+
+
+def test_yaml_param_files_map_to_configs(tmp_path):
+    """cfg*.yml -> the Dict the Julia code indexes -> snn_config / snn_actor_config fields."""
+    from rl_stdp_b200 import _lib as L, params
+    p = params.load_params(os.path.join(ROOT, "tests", "golden", "cfg_example.yml"))
+    assert p["apost"] == 1.2 and p["wie"] == -1.5 and "b" in p
+    d = params.izhikevich_config(p, layered=False)     # net_res.jl
+    assert d == dict(v_reset=-65.0, a_exc=0.02, a_inh=0.1, d_exc=8.0, d_inh=2.0, theta=1.5, ttheta=0.998, apost=1.2,
+                     apre=1.7, da_decay=0.99, wmax=3.0, vthresh=30.0)
+    e = params.izhikevich_config(p, layered=True)      # net_arch.jl (Izhikevich)
+    assert e["rate_mode"] == L.SNN_RATE_DA and e["sd_decay_mode"] == L.SNN_SD_DECAY_NEVER and e["trace_decay"] == 0.9
+    cfg = L.SnnConfig()
+    L.check(L.load().snn_config_default(C.byref(cfg)))
+    for k, v in e.items():
+        assert hasattr(cfg, k), k
+        setattr(cfg, k, v)
+    a = params.actor_config(p)
+    acfg = L.SnnActorConfig()
+    for k, v in a.items():
+        assert hasattr(acfg, k), k
+    assert a["taulif"] == 5.0 and a["imin"] == 10.0
+    bad = tmp_path / "bad.yml"
+    bad.write_text("apost: 1.0\n")
+    with pytest.raises(KeyError):
+        params.izhikevich_config(params.load_params(str(bad)), layered=False)

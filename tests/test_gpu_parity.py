@@ -230,6 +230,22 @@ def test_fast_mode_statistics(dtype):
     qs = np.linspace(0.001, 0.999, 999)
     assert np.abs(np.quantile(wr, qs) - np.quantile(wg, qs)).max() < 5e-3
     assert abs(wg.std() - wr.std()) / wr.std() < 0.05
+    # SURVEY §8d gates: two-sample KS of the weight histograms (weights binned to 1e-4 so that the atom
+    # at the initial weight stays one atom in fp32) < 0.02; CV of the pooled inter-spike intervals +-5 %
+    from scipy.stats import ks_2samp
+    assert ks_2samp(np.round(wr, 4), np.round(wg, 4)).statistic < 0.02
+
+    def isi_cv(trains):
+        last = -np.ones(n, np.int64)
+        isis = []
+        for k, ids in enumerate(trains):
+            seen = ids[last[ids] >= 0]
+            isis.append(k - last[seen])
+            last[ids] = k
+        x = np.concatenate(isis).astype(float)
+        return x.std() / x.mean()
+    cr, cg = isi_cv(ref), isi_cv(spikes)
+    assert abs(cg - cr) / cr < 0.05, (cr, cg)
     if dtype == "f64":
         for k in range(50):  # weights are still +-1 (exactly summable) before the first learn!
             assert np.array_equal(spikes[k], ref[k]), k
