@@ -142,6 +142,8 @@ struct DevNet {
   uint32_t* tile_done;   // [n_tiles]
   const uint32_t *inst_lo, *inst_hi;  // [B] plastic synapse range of every instance
   uint32_t n_tiles, tile_syn;
+  int32_t static_cur;    // >= 0: no pass can be in flight while this launch runs and wsdX[static_cur] is
+                         // current — kernels skip the LearnCtl load (in-place windows, exact mode)
   const uint32_t *colptr, *col_npl, *in_syn, *in_pre;
   // counters[0] = spikes, [1] = synaptic events (exact mode); per-block partial sums otherwise
   unsigned long long* counters;
@@ -230,8 +232,12 @@ struct WView {
 };
 template <typename T>
 __device__ __forceinline__ WView<T> wview(const DevNet<T>& p) {
-  const uint32_t s = *reinterpret_cast<const volatile uint32_t*>(&p.lc->state);
   WView<T> v;
+  if (p.static_cur >= 0) {
+    v.cur = p.wsdX[p.static_cur]; v.old = p.wsdX[p.static_cur ^ 1]; v.front = kFrontAll;
+    return v;
+  }
+  const uint32_t s = *reinterpret_cast<const volatile uint32_t*>(&p.lc->state);
   v.cur = p.wsdX[s >> 31];
   v.old = p.wsdX[(s >> 31) ^ 1u];
   v.front = (p.exp_flags & 16) ? kFrontAll : (s & kFrontAll);  // experiment 16: ignore the frontier (wrong numerics)
@@ -294,7 +300,7 @@ __device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, u
 // values.  A warp covers 128 neurons = 4 bitmap words.  Arrays are padded to Nld.
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool EULER, bool DETECT>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : 2)
+__global__ void __launch_bounds__(256)
 neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev) {
   typedef Ops<T> O;
   // programmatic dependent launch (no-ops unless the launch carries the attribute): let the next
@@ -350,27 +356,15 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
 
   // whole warps only: the last rank's range is padded up to Nld (padding neurons are inactive)
   const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2);
-  // The grid covers the local neurons in ~two strides: the loads of a thread's next quad are
-  // issued before its current quad is processed, so the two round trips overlap (one resident
-  // wave instead of 1.65 waves of one-quad threads).
-  const uint32_t qstride = gridDim.x * blockDim.x;
-  uint32_t q = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  Vec4<T> nv, nu, nI, ntp, nho;
-  auto load_quad = [&](uint32_t qq) {
-    const uint32_t jj = qq << 2;
-    nv = ld4(p.v + jj); nu = ld4(p.u + jj);
-    if (EULER) nI = ld4(I_prev + jj);
-    if (DETECT) {
-      ntp = ld4(trp + jj);
-      if (p.homeostasis) nho = ld4(p.ho + jj);
-    }
-  };
-  if (q < q_hi) load_quad(q);
-  for (; q < q_hi; q += qstride) {
+  for (uint32_t q = q_lo + blockIdx.x * blockDim.x + threadIdx.x; q < q_hi; q += gridDim.x * blockDim.x) {
     const uint32_t j0 = q << 2;
-    // ---- all loads first (issued one iteration ahead)
-    Vec4<T> v = nv, u = nu, I = nI, tp = ntp, ho = nho;
-    if (q + qstride < q_hi) load_quad(q + qstride);
+    // ---- all loads first
+    Vec4<T> v = ld4(p.v + j0), u = ld4(p.u + j0), I, tp, ho;
+    if (EULER) I = ld4(I_prev + j0);
+    if (DETECT) {
+      tp = ld4(trp + j0);
+      if (p.homeostasis) ho = ld4(p.ho + j0);
+    }
     const uint32_t l0 = p.B == 1 ? j0 : j0 % Nper;
     bool exc[4], act[4];
 #pragma unroll
@@ -859,7 +853,7 @@ __device__ __forceinline__ void learn_one(typename Real2<T>::type& ws, T g, T wm
 }
 
 // synapses [lo, hi) of one instance (first neuron r0): dst = learn(src); src == dst for the in-place pass
-template <typename T, int UNR>
+template <typename T, int UNR, bool STREAM>
 __device__ __forceinline__ void learn_range(const DevNet<T>& p, const typename Real2<T>::type* src,
                                             typename Real2<T>::type* dst, int64_t lo, int64_t hi, int64_t r0, T g,
                                             int do_learn, int do_decay, int64_t tid, int64_t nth) {
@@ -883,21 +877,23 @@ __device__ __forceinline__ void learn_range(const DevNet<T>& p, const typename R
         for (; x + (UNR - 1) * nth < n4; x += UNR * nth) {
           float4 r[UNR];
 #pragma unroll
-          for (int c = 0; c < UNR; ++c) r[c] = __ldcs(qs + x + c * nth);
+          for (int c = 0; c < UNR; ++c) r[c] = STREAM ? __ldcs(qs + x + c * nth) : qs[x + c * nth];
 #pragma unroll
           for (int c = 0; c < UNR; ++c) {
             float2 s0 = make_float2(r[c].x, r[c].y), s1 = make_float2(r[c].z, r[c].w);
             learn_one<float>(s0, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
             learn_one<float>(s1, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
-            __stcs(qd + x + c * nth, make_float4(s0.x, s0.y, s1.x, s1.y));
+            if (STREAM) __stcs(qd + x + c * nth, make_float4(s0.x, s0.y, s1.x, s1.y));
+            else qd[x + c * nth] = make_float4(s0.x, s0.y, s1.x, s1.y);
           }
         }
         for (; x < n4; x += nth) {
-          float4 r = __ldcs(qs + x);
+          float4 r = STREAM ? __ldcs(qs + x) : qs[x];
           float2 s0 = make_float2(r.x, r.y), s1 = make_float2(r.z, r.w);
           learn_one<float>(s0, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
           learn_one<float>(s1, (float)g, (float)p.wmin, (float)p.wmax, (float)p.sd_decay, do_learn, do_decay);
-          __stcs(qd + x, make_float4(s0.x, s0.y, s1.x, s1.y));
+          if (STREAM) __stcs(qd + x, make_float4(s0.x, s0.y, s1.x, s1.y));
+          else qd[x] = make_float4(s0.x, s0.y, s1.x, s1.y);
         }
       }
     } else {
@@ -948,7 +944,7 @@ learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int do
   const uint32_t hi = p.seg[(size_t)(r0 + p.Ne - 1) * (p.Dmax + 1) + p.Dmax];
   const T g = learn_rate<T>(p, p.da[(size_t)((t + 1) & 1) * p.B + b]);
   typename DevNet<T>::T2* w = wview(p).cur;
-  learn_range<T, 4>(p, w, w, lo, hi, r0, g, do_learn, do_decay, blockIdx.x * (int64_t)blockDim.x + threadIdx.x,
+  learn_range<T, 4, false>(p, w, w, lo, hi, r0, g, do_learn, do_decay, blockIdx.x * (int64_t)blockDim.x + threadIdx.x,
                     (int64_t)gridDim.x * blockDim.x);
   tl_end(p.tl, 3, k);
 }
@@ -1027,7 +1023,7 @@ learn_pass_kernel(DevNet<T> p, int32_t k, int do_decay) {
     if (!done) {
       for (; b < p.B && (int64_t)p.inst_lo[b] < z; ++b) {
         const int64_t lo = max((int64_t)p.inst_lo[b], a), hi = min((int64_t)p.inst_hi[b], z);
-        learn_range<T, 8>(p, src, dst, lo, hi, (int64_t)b * p.Nper, p.lg[b], 1, do_decay, threadIdx.x, blockDim.x);
+        learn_range<T, 8, true>(p, src, dst, lo, hi, (int64_t)b * p.Nper, p.lg[b], 1, do_decay, threadIdx.x, blockDim.x);
       }
     }
     __syncthreads();
@@ -1423,6 +1419,7 @@ class Engine : public IEngine {
     p.ho_inh = cfg_.ho_inh; p.variant_g = cfg_.variant_g;
     p.exp_flags = cfg_.reserved[1];
     p.part_lo = 0; p.part_hi = p.N;
+    p.static_cur = -1;
     if (cfg_.reserved[1] & 2) SNN_CUDA_OK(cudaMalloc(&p.tl, 2 * kTlClasses * kTlSteps * sizeof(unsigned long long)));
     p.homeostasis = !(cfg_.theta == 0.0 && cfg_.ttheta == 1.0);
     init_state_kernel<T><<<grid_for(p.Nld), 256, 0, stream_>>>(p);
@@ -1765,9 +1762,7 @@ class Engine : public IEngine {
     DevNet<T>& p = p_;
     Launch l;
     const int64_t local_quads = ((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2) - (p.part_lo >> 2);
-    // two quads per thread when that still fills the GPU (see neuron_kernel); exp 16384: one quad
-    const int64_t qpt = (local_quads >= (int64_t)n_sm_ * 256 * 4 && !(cfg_.reserved[1] & 16384)) ? 2 : 1;
-    l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((local_quads + 256 * qpt - 1) / (256 * qpt), (int64_t)n_sm_ * 8));
+    l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((local_quads + 255) / 256, (int64_t)n_sm_ * 8));
     l.gR = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 - local_quads + 255) / 256, (int64_t)n_sm_ * 8));
     if (gA_ == 0) {
       int per_sm = 0;
@@ -1829,7 +1824,8 @@ template <typename T>
 void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& force_off, const int32_t* d_force,
                               const std::vector<int32_t>& cur_off, const int32_t* d_cur_idx, const double* d_cur_val,
                               bool prof) {
-  DevNet<T>& p = p_;
+  DevNet<T> p = p_;          // by-value copy handed to the kernels
+  p.static_cur = cur_;       // plain launches: learn! runs in place, no pass is ever in flight
   const int n = a.n_steps;
   const Launch g = grids();
   cudaStream_t s = stream_;
@@ -1946,12 +1942,13 @@ void Engine<T>::launch_pass(cudaStream_t s4, int k, int do_decay, bool prof) {
 
 template <typename T>
 int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
-  DevNet<T>& p = p_;
   const int n = a.n_steps;
   const bool async = async_ok(a);
+  DevNet<T> p = p_;                  // by-value copy baked into the captured kernel nodes
+  p.static_cur = async ? -1 : cur_;  // in-place windows: the (w, sd) view is fixed, skip the LearnCtl load
   std::string key(reinterpret_cast<const char*>(&n), sizeof(n));
   key.push_back(prof ? 'p' : '-');
-  key.push_back(async ? 'a' : 's');
+  key.push_back(async ? 'a' : (cur_ ? 't' : 's'));
   if (a.train_flags) key.append(reinterpret_cast<const char*>(a.train_flags), n);
   CachedGraph* hit = nullptr;
   for (auto& cg : graphs_) if (cg.key == key) hit = &cg;
