@@ -1358,6 +1358,7 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaStreamCreateWithPriority(&side_stream_, cudaStreamNonBlocking, prio_mid));
     SNN_CUDA_OK(cudaStreamCreateWithPriority(&chain_stream_, cudaStreamNonBlocking, prio_hi));   // neuron chain
     SNN_CUDA_OK(cudaStreamCreateWithPriority(&learn_stream_, cudaStreamNonBlocking, prio_lo));   // async learn pass
+    SNN_CUDA_OK(cudaStreamCreateWithPriority(&remote_stream_, cudaStreamNonBlocking, prio_hi));  // remote_kernel beside neuron_kernel
     stream_ = own_stream_;
     SNN_CUDA_OK(cudaEventCreate(&ev_begin_));
     SNN_CUDA_OK(cudaEventCreate(&ev_end_));
@@ -1728,7 +1729,8 @@ class Engine : public IEngine {
     if (side2_stream_) cudaStreamDestroy(side2_stream_);
     if (chain_stream_) cudaStreamDestroy(chain_stream_);
     if (learn_stream_) cudaStreamDestroy(learn_stream_);
-    side2_stream_ = chain_stream_ = learn_stream_ = nullptr;
+    if (remote_stream_) cudaStreamDestroy(remote_stream_);
+    side2_stream_ = chain_stream_ = learn_stream_ = remote_stream_ = nullptr;
     memset(&p, 0, sizeof(p));
     own_stream_ = side_stream_ = nullptr; ev_begin_ = ev_end_ = nullptr; d_ctx_ = nullptr; h_ctx_ = nullptr; h_blk_ = nullptr;
   }
@@ -1800,7 +1802,7 @@ class Engine : public IEngine {
   cudaStream_t own_stream_ = nullptr, side_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev_begin_ = nullptr, ev_end_ = nullptr;
   cudaEvent_t dep_ev_[16] = {};
-  cudaStream_t side2_stream_ = nullptr, chain_stream_ = nullptr, learn_stream_ = nullptr;
+  cudaStream_t side2_stream_ = nullptr, chain_stream_ = nullptr, learn_stream_ = nullptr, remote_stream_ = nullptr;
   // asynchronous learn pass
   bool have_async_ = false;
   int cur_ = 0;                  // host mirror of LearnCtl.state >> 31 (read back after every window)
@@ -1969,7 +1971,8 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
     if (prof) prof_reserve(2 * (size_t)n + 2);  // no allocation while capturing
     // events: [0] neuron done, [1..3] pushes-for-step ready (ring of 3), [4..5] synapse LTD done
     // (ring of 2), [6..7] ltp done (ring of 2), [8] learn done / begun, [9] fork, [10] pass+replay done
-    cudaEvent_t evL = dep_ev_[8], evFork = dep_ev_[9], evFin = dep_ev_[10];
+    cudaEvent_t evL = dep_ev_[8], evFork = dep_ev_[9], evFin = dep_ev_[10], evPre = dep_ev_[6], evR = dep_ev_[7];
+    cudaStream_t sR = remote_stream_;
     auto evPush = [&](int step) { return dep_ev_[1 + ((step % 3) + 3) % 3]; };  // pushes consumed by Euler(step)
     auto evS = [&](int step) { return dep_ev_[4 + (step & 1)]; };
     auto evP = [&](int step) { return dep_ev_[12 + (step & 3)]; };  // ltp done (ring of 4)
@@ -1986,6 +1989,16 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
       const bool learn_prev = k >= 1 && wants_learn(a, k - 1, &dl, &dd);
       if (k >= 1 && !(cfg_.reserved[1] & 4096)) cudaStreamWaitEvent(sN, evPush(k - 1), 0);  // Euler(k-1) consumes them
       if (learn_prev) cudaStreamWaitEvent(sN, evL, 0);
+      const bool peers = p.n_ranks > 1;
+      if (peers) {
+        // neuron-partitioned: remote_kernel(k) runs BESIDE neuron_kernel(k) on its own stream — the
+        // peers detect at the same time, so their (word, step) pairs arrive while we integrate, and
+        // the replay of their detection is finished shortly after our own kernel instead of after it
+        cudaEventRecord(evPre, sN);
+        cudaStreamWaitEvent(sR, evPre, 0);
+        remote_kernel<T><<<g.gR, 256, 0, sR>>>(p, d_ctx_, k, 1);
+        cudaEventRecord(evR, sR);
+      }
       if (k == 0) neuron_kernel<T, false, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
       else if (cfg_.reserved[1] & 8192) {
         cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
@@ -1997,9 +2010,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
         cudaLaunchKernelEx(&lc, neuron_kernel<T, true, true>, p, (const WindowCtx<T>*)d_ctx_, (int32_t)k, (int32_t)1);
       }
       else neuron_kernel<T, true, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
-      if (p.n_ranks > 1) {  // neuron-partitioned: wait for the peers' words of this step, replay their detection
-        remote_kernel<T><<<g.gR, 256, 0, sN>>>(p, d_ctx_, k, 1);
-      }
+      if (peers) cudaStreamWaitEvent(sN, evR, 0);
       cudaEventRecord(evNk[k & 1], sN);
     };
     auto cap_side = [&](int k) {
