@@ -239,22 +239,40 @@ int build_topology(const snn_config& cfg, const int64_t* h_rowptr, const int32_t
   return SNN_OK;
 }
 
+void SortScratch::release() {
+  if (tmp) cudaFree(tmp);
+  if (out) cudaFree(out);
+  tmp = nullptr; out = nullptr; tmp_cap = out_cap = 0;
+}
+
+// Spike-record formatting: ascending ids inside every step.  The scratch buffers are grow-only and
+// owned by the engine: a cudaMalloc/cudaFree pair per window costs more than the sort itself.
 int sort_segments(int32_t* d_keys, int64_t n_items, const int32_t* d_offsets, int32_t n_segments,
-                  cudaStream_t stream, std::string& err) {
+                  cudaStream_t stream, SortScratch* sc, std::string& err) {
   if (n_items <= 0 || n_segments <= 0) return SNN_OK;
-  int32_t* d_out = nullptr; void* d_tmp = nullptr;
+  const size_t out_bytes = (size_t)n_items * sizeof(int32_t);
+  if (out_bytes > sc->out_cap) {
+    if (sc->out) cudaFree(sc->out);
+    sc->out = nullptr; sc->out_cap = 0;
+    SNN_CUDA_OK(cudaMalloc(&sc->out, out_bytes + out_bytes / 2 + 256));
+    sc->out_cap = out_bytes + out_bytes / 2 + 256;
+  }
   size_t tmp_bytes = 0;
-  SNN_CUDA_OK(cudaMalloc(&d_out, n_items * sizeof(int32_t)));
-  cudaError_t e = cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_keys, d_out, (int)n_items,
+  cudaError_t e = cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_keys, sc->out, (int)n_items,
                                                      n_segments, d_offsets, d_offsets + 1, stream);
-  if (e == cudaSuccess) e = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
-  if (e == cudaSuccess)
-    e = cub::DeviceSegmentedSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_out, (int)n_items, n_segments,
+  if (e == cudaSuccess && tmp_bytes > sc->tmp_cap) {
+    if (sc->tmp) cudaFree(sc->tmp);
+    sc->tmp = nullptr; sc->tmp_cap = 0;
+    e = cudaMalloc(&sc->tmp, tmp_bytes + tmp_bytes / 2 + 256);
+    if (e == cudaSuccess) sc->tmp_cap = tmp_bytes + tmp_bytes / 2 + 256;
+  }
+  if (e == cudaSuccess) {
+    tmp_bytes = sc->tmp_cap;
+    e = cub::DeviceSegmentedSort::SortKeys(sc->tmp, tmp_bytes, d_keys, sc->out, (int)n_items, n_segments,
                                            d_offsets, d_offsets + 1, stream);
+  }
   if (e == cudaSuccess)
-    e = cudaMemcpyAsync(d_keys, d_out, n_items * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  cudaFree(d_out); cudaFree(d_tmp);
+    e = cudaMemcpyAsync(d_keys, sc->out, out_bytes, cudaMemcpyDeviceToDevice, stream);
   if (e != cudaSuccess) { err = std::string("sort_segments: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
   return SNN_OK;
 }

@@ -42,8 +42,13 @@ int build_topology(const snn_config& cfg, const int64_t* h_rowptr, const int32_t
                    const uint8_t* h_delay, Topo* out, cudaStream_t stream, std::string& err);
 
 // Sort every [off[k], off[k+1]) segment of keys ascending (spike record formatting).
+struct SortScratch {
+  void* tmp = nullptr; size_t tmp_cap = 0;
+  int32_t* out = nullptr; size_t out_cap = 0;
+  void release();
+};
 int sort_segments(int32_t* d_keys, int64_t n_items, const int32_t* d_offsets, int32_t n_segments,
-                  cudaStream_t stream, std::string& err);
+                  cudaStream_t stream, SortScratch* scratch, std::string& err);
 
 // What a rank publishes so that its peers can store spike bitmaps into its ring (snn_partition_export)
 constexpr uint64_t kPeerMagic = 0x534e4e5032503031ull;  // "SNNP2P01"

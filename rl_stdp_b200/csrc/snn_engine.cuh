@@ -1717,6 +1717,7 @@ class Engine : public IEngine {
     if (h_ctx_) cudaFreeHost(h_ctx_);
     if (h_blk_) cudaFreeHost(h_blk_);
     b_noise_.release(); b_noise64_.release(); b_ev_off_.release(); b_ev_inst_.release(); b_ev_amt_.release();
+    sort_scratch_.release();
     b_force_.release(); b_rec_.release(); b_rec_off_.release(); b_cur_idx_.release(); b_cur_val_.release();
     topo_.release();
     if (ev_begin_) cudaEventDestroy(ev_begin_);
@@ -1815,6 +1816,7 @@ class Engine : public IEngine {
   WindowCtx<T>* d_ctx_ = nullptr; WindowCtx<T>* h_ctx_ = nullptr;
   unsigned long long* h_blk_ = nullptr;
   DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_, b_cur_idx_, b_cur_val_;
+  SortScratch sort_scratch_;
   std::vector<void*> ipc_opened_;
   snn_exchange_fn exchange_ = nullptr; void* exchange_user_ = nullptr; int exchange_failed_ = 0;
   const std::vector<cudaEvent_t>* graph_prof_events_ = nullptr;
@@ -2283,7 +2285,7 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     SNN_CUDA_OK(cudaMemcpyAsync(h_off.data(), b_rec_off_.ptr, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     SNN_CUDA_OK(cudaStreamSynchronize(stream_));
     const int64_t total = h_off[n];
-    int src = sort_segments(b_rec_.as<int32_t>(), total, b_rec_off_.as<int32_t>(), n, stream_, err);
+    int src = sort_segments(b_rec_.as<int32_t>(), total, b_rec_off_.as<int32_t>(), n, stream_, &sort_scratch_, err);
     if (src) return src;
     if (total > 0) SNN_CUDA_OK(cudaMemcpyAsync(a.spikes_out, b_rec_.ptr, total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     for (int k = 0; k <= n; ++k) a.spike_offsets[k] = h_off[k];
