@@ -183,4 +183,24 @@ add_dopamine!(net::Network, x::Real; instance::Integer = 0) =
     check(ccall((:snn_add_dopamine, LIB), Int32, (Ptr{Cvoid}, Int32, Float64), net.handle, instance, x))
 reset_v!(net::Network) = check(ccall((:snn_reset_v, LIB), Int32, (Ptr{Cvoid},), net.handle))
 
+# ---- one network over several GPUs (one Julia process per GPU; include/snn_b200.h snn_partition_*)
+const PEER_BLOB_BYTES = 192
+
+"Integrate only neurons lo:hi (1-based, inclusive; multiples of 128 except the last bound) on this handle."
+set_partition!(net::Network, lo::Integer, hi::Integer) =
+    check(ccall((:snn_set_partition, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+                net.handle, lo - 1, hi, C_NULL, C_NULL))
+
+"This rank's exchange-ring descriptor (a CUDA IPC handle); gather one per rank, e.g. with MPI.Allgather."
+function partition_export(net::Network)
+    blob = zeros(UInt8, PEER_BLOB_BYTES)
+    check(ccall((:snn_partition_export, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), net.handle, blob))
+    return blob
+end
+
+"`blobs` = the descriptors of all ranks concatenated in rank order; call a barrier afterwards, then step."
+partition_connect!(net::Network, rank::Integer, world::Integer, blobs::Vector{UInt8}) =
+    check(ccall((:snn_partition_connect, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}),
+                net.handle, rank, world, blobs))
+
 end # module
