@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsnn_b200.so")
+LIB_PATH = os.environ.get("SNN_B200_LIB") or os.path.join(HERE, "libsnn_b200.so")  # override: A/B builds only
 
 SNN_F32, SNN_F64 = 0, 1
 SNN_MODE_FAST, SNN_MODE_EXACT = 0, 1

@@ -50,6 +50,10 @@
 
 #include "snn_common.h"
 
+#ifndef NEURON_MIN_BLOCKS
+#define NEURON_MIN_BLOCKS 4
+#endif
+
 namespace snn {
 
 template <typename T> struct LogEntry { uint32_t e; T d; };
@@ -300,7 +304,7 @@ __device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, u
 // values.  A warp covers 128 neurons = 4 bitmap words.  Arrays are padded to Nld.
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool EULER, bool DETECT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? NEURON_MIN_BLOCKS : 2)
 neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev) {
   typedef Ops<T> O;
   // programmatic dependent launch (no-ops unless the launch carries the attribute): let the next
