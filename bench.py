@@ -459,7 +459,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-ms-per-step", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--exp-flags", type=int, default=0, help="kernel experiments (wrong numerics), never for reported numbers")
+    ap.add_argument("--exp-flags", type=int, default=0, help="snn_config.reserved[1] diagnostics (2 timeline, 4 serialise the learn pass, 512 LSU pass); 0 for reported numbers")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--learn-async", default="auto", choices=["auto", "off", "force"], help="learn pass beside the following steps (auto: large nets) or in place")
     ap.add_argument("--learn-tile-k", type=int, default=0, help="async learn pass: tile size in units of 1024 synapses (0 = 32)")

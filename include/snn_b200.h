@@ -108,7 +108,8 @@ typedef struct snn_config {
                               accumulates in descending presynaptic id (:70-80 walks `firings` backwards) */
   int32_t reserved[8];     /* tuning / A-B switches, 0 = default:
                               [0] = 1 disables the CUDA-graph scheduler (plain launches)
-                              [1] experiment flags (bit 1: kernel timeline for snn_debug_timeline)
+                              [1] diagnostics: 2 = kernel timeline for snn_debug_timeline, 4 = nothing overlaps
+                                  the asynchronous learn pass, 512 = register-staged pass instead of TMA
                               [2] asynchronous learn pass: resident blocks per SM
                               [4] learn pass: 0 auto (asynchronous on large nets), 1 always in place,
                                   2 always asynchronous

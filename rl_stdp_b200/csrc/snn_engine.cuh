@@ -160,7 +160,7 @@ struct DevNet {
   int64_t ho_from;
   int32_t threshold_ge, sd_decay_mode, rate_mode, plastic_ei, noise_mode, exact, homeostasis;
   int32_t ho_inh, variant_g;  // see snn_config
-  int32_t exp_flags;  // experiments only (snn_config.reserved[1]); 0 in production
+  int32_t exp_flags;  // snn_config.reserved[1]: 2 = kernel timeline, 4 = nothing overlaps the learn pass, 512 = LSU pass
   // neuron partition (multi-GPU): this rank integrates neurons [part_lo, part_hi)
   // and holds every synapse whose POST is in that range; spike bitmaps are exchanged per step
   int64_t part_lo, part_hi;
@@ -244,7 +244,7 @@ __device__ __forceinline__ WView<T> wview(const DevNet<T>& p) {
   const uint32_t s = *reinterpret_cast<const volatile uint32_t*>(&p.lc->state);
   v.cur = p.wsdX[s >> 31];
   v.old = p.wsdX[(s >> 31) ^ 1u];
-  v.front = (p.exp_flags & 16) ? kFrontAll : (s & kFrontAll);  // experiment 16: ignore the frontier (wrong numerics)
+  v.front = s & kFrontAll;
   return v;
 }
 __device__ __forceinline__ float ldcg_x(const float2* q) { return __ldcg(reinterpret_cast<const float*>(q)); }
@@ -307,10 +307,6 @@ template <typename T, bool EULER, bool DETECT>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? NEURON_MIN_BLOCKS : 2)
 neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev) {
   typedef Ops<T> O;
-  // programmatic dependent launch (no-ops unless the launch carries the attribute): let the next
-  // kernel of the chain be launched now, and wait here for the previous one to complete and flush
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   tl_begin(p.tl, 0, k);
   const int lane = threadIdx.x & 31;
   const int64_t t = cx->t0 + k;
@@ -442,7 +438,7 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
       word |= __shfl_xor_sync(0xffffffffu, word, 2);
       word |= __shfl_xor_sync(0xffffffffu, word, 4);
       if ((lane & 7) == 0) bits[j0 >> 5] = word;
-      if (p.n_ranks > 1 && !(p.exp_flags & 65536)) {
+      if (p.n_ranks > 1) {
         // fused exchange: a warp owns 4 consecutive bitmap words = two 16-byte stores of
         // (word, step tag) pairs into every peer's ring over NVLink
         const unsigned w1 = __shfl_sync(0xffffffffu, word, 8), w2 = __shfl_sync(0xffffffffu, word, 16),
@@ -468,7 +464,7 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
               list[pos] = (int32_t)(j0 + c);
               if (rec_ids && (int64_t)rec_base + pos < rec_cap) rec_ids[rec_base + pos] = (int32_t)(j0 + c);
             }
-            if (!p.exact && !(p.exp_flags & 1)) {
+            if (!p.exact) {
               // delay-1 synapses of this step's spikers feed the Euler update of this very step
               // (new_net.jl:116-121): push them now, warp-cooperatively, into Iacc[t&1]
               unsigned mm = m;
@@ -538,7 +534,7 @@ __global__ void __launch_bounds__(256)
 remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t wait_peers) {
   typedef Ops<T> O;
   tl_begin(p.tl, 4, k);
-  const bool from_ll = wait_peers && !(p.exp_flags & 65536);
+  const bool from_ll = wait_peers != 0;
   const int lane = threadIdx.x & 31;
   const int64_t t = cx->t0 + k;
   const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
@@ -979,7 +975,7 @@ learn_pass_kernel(DevNet<T> p, int32_t k, int do_decay) {
   typename DevNet<T>::T2* __restrict__ dst = p.wsdX[cur];
   const uint32_t TS = p.tile_syn, U = TS >> 5;  // frontier units per tile
   for (;;) {
-    if (threadIdx.x == 0) s_tile = (p.exp_flags & 32) ? p.n_tiles : atomicAdd(&p.lc->next_tile, 1u);
+    if (threadIdx.x == 0) s_tile = atomicAdd(&p.lc->next_tile, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
     __syncthreads();
@@ -1001,7 +997,7 @@ learn_pass_kernel(DevNet<T> p, int32_t k, int do_decay) {
         const float4* __restrict__ qs = reinterpret_cast<const float4*>(src + a);
         float4* __restrict__ qd = reinterpret_cast<float4*>(dst + a);
         const uint32_t n4 = TS >> 1;  // multiple of 512
-        const uint32_t rot = (p.exp_flags & 256) ? 0u : ((tile * 2654435761u) >> 8) % (n4 >> 5) << 5;
+        const uint32_t rot = ((tile * 2654435761u) >> 8) % (n4 >> 5) << 5;
         const float g = p.lg[b];
         for (uint32_t x0 = threadIdx.x; x0 < n4; x0 += 8 * 256) {
           float4 r[8]; uint32_t ix[8];
@@ -1139,7 +1135,7 @@ learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
   const uint32_t TS = p.tile_syn, U = TS >> 5;
   uint32_t q = 0;  // chunks consumed so far by this block: stage = q % S, parity = (q / S) & 1
   for (;;) {
-    if (tid == 0) s_tile = (p.exp_flags & 32) ? p.n_tiles : atomicAdd(&p.lc->next_tile, 1u);
+    if (tid == 0) s_tile = atomicAdd(&p.lc->next_tile, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
     __syncthreads();
@@ -1357,7 +1353,6 @@ class Engine : public IEngine {
     int prio_lo = 0, prio_hi = 0;  // numerically: lowest priority = prio_lo, highest = prio_hi
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_lo;
-    if (cfg_.reserved[1] & 64) prio_lo = prio_mid = prio_hi = 0;  // experiment 64: no stream priorities
     SNN_CUDA_OK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
     SNN_CUDA_OK(cudaStreamCreateWithPriority(&side_stream_, cudaStreamNonBlocking, prio_mid));
     SNN_CUDA_OK(cudaStreamCreateWithPriority(&chain_stream_, cudaStreamNonBlocking, prio_hi));   // neuron chain
@@ -1993,7 +1988,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
     auto cap_neuron = [&](int k) {
       int dl, dd;
       const bool learn_prev = k >= 1 && wants_learn(a, k - 1, &dl, &dd);
-      if (k >= 1 && !(cfg_.reserved[1] & 4096)) cudaStreamWaitEvent(sN, evPush(k - 1), 0);  // Euler(k-1) consumes them
+      if (k >= 1) cudaStreamWaitEvent(sN, evPush(k - 1), 0);  // Euler(k-1) consumes them
       if (learn_prev) cudaStreamWaitEvent(sN, evL, 0);
       const bool peers = p.n_ranks > 1;
       if (peers) {
@@ -2006,15 +2001,6 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
         cudaEventRecord(evR, sR);
       }
       if (k == 0) neuron_kernel<T, false, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
-      else if (cfg_.reserved[1] & 8192) {
-        cudaLaunchConfig_t lc; memset(&lc, 0, sizeof(lc));
-        lc.gridDim = dim3(g.gN); lc.blockDim = dim3(256); lc.dynamicSmemBytes = 0; lc.stream = sN;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at; lc.numAttrs = 1;
-        cudaLaunchKernelEx(&lc, neuron_kernel<T, true, true>, p, (const WindowCtx<T>*)d_ctx_, (int32_t)k, (int32_t)1);
-      }
       else neuron_kernel<T, true, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
       if (peers) cudaStreamWaitEvent(sN, evR, 0);
       cudaEventRecord(evNk[k & 1], sN);
@@ -2077,12 +2063,11 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
     };
     // Capture order = launch order of sibling nodes: the next neuron kernel (the only serial chain)
     // goes in before the side kernels of the step it does not depend on.
-    const bool chain_first = !(cfg_.reserved[1] & 1024);
     cap_neuron(0);
     for (int k = 0; k < n; ++k) {
       int dl, dd;
       const bool learn = wants_learn(a, k, &dl, &dd);
-      if (k + 1 < n && !learn && chain_first) { cap_neuron(k + 1); cap_side(k); }
+      if (k + 1 < n && !learn) { cap_neuron(k + 1); cap_side(k); }
       else { cap_side(k); if (k + 1 < n) cap_neuron(k + 1); }
     }
     cudaEvent_t evN = evNk[0];
@@ -2109,28 +2094,6 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
       prof_events_.clear();
       prof_events_.swap(saved_events);
       err = std::string("graph capture: ") + cudaGetErrorString(e); return SNN_ERR_CUDA;
-    }
-    if (cfg_.reserved[1] & 2048) {  // experiment 2048: explicit launch priorities on the kernel nodes
-      size_t nn = 0;
-      cudaGraphGetNodes(graph, nullptr, &nn);
-      std::vector<cudaGraphNode_t> nodes(nn);
-      cudaGraphGetNodes(graph, nodes.data(), &nn);
-      int plo = 0, phi = 0;
-      cudaDeviceGetStreamPriorityRange(&plo, &phi);
-      for (auto nd : nodes) {
-        cudaGraphNodeType ty;
-        if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
-        cudaKernelNodeParams kp;
-        if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
-        int pr = phi + 1 < plo ? phi + 1 : plo;
-        if (kp.func == (void*)neuron_kernel<T, true, true> || kp.func == (void*)neuron_kernel<T, false, true> ||
-            kp.func == (void*)neuron_kernel<T, true, false>) pr = phi;
-        else if (kp.func == (void*)learn_pass_tma_kernel<T> || kp.func == (void*)learn_pass_kernel<T>) pr = plo;
-        cudaKernelNodeAttrValue v; memset(&v, 0, sizeof(v));
-        v.priority = pr;
-        cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributePriority, &v);
-      }
-      cudaGetLastError();
     }
     CachedGraph cg;
     cg.key = key; cg.prof_used = prof_used_; cg.prof_cls = prof_cls_; cg.pass_launches = last_pass_launches_;

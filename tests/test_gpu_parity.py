@@ -431,3 +431,51 @@ def test_variant_e_layered_izhikevich_exact():
         assert np.array_equal(net.de(l), ora.de(l)), l
         changed += int(np.any(ora.e(l) != e0[l]))
     assert changed == 2
+
+
+def test_full_size_c5_properties():
+    """BASELINE config 5 at full size (1M neurons / 100M synapses, delays 1-20, on-device noise,
+    production fp32 mode) through size-independent properties:
+      * the asynchronous learn pass and the in-place pass are two schedulers of ONE computation: with
+        the weights frozen (learn_base = 0, no dopamine: +-1 weights sum exactly in any order) the two
+        handles must return bit-identical spike records, v and traces, and sd to rounding;
+      * spike ids ascending and in range; delivered events == sum over spikes of the synapses whose
+        delay lets them arrive inside the run; inhibitory weights untouched, excitatory ones in [0, 4]
+        when learning is on."""
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    n, ne, fan, dmax, t = 1_000_000, 800_000, 100, 20, 200
+    rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    kw = dict(dtype="f32", mode="fast", noise="philox", max_delay=dmax, noise_seed=10)
+    recs = []
+    for sched in ("force", "off"):
+        net = SparseNetwork(n, ne, rowptr, post, w, delay, learn_base=0.0, learn_async=sched, **kw)
+        sp = []
+        for lo in range(0, t, 100):
+            s, st = net.run(100, None, train[lo:lo + 100], spikes_cap=1 << 22)
+            sp += s
+        recs.append((sp, net.get(L.FIELD_V), net.get(L.FIELD_TRACE), net.get(L.FIELD_SD), net.get(L.FIELD_W)))
+        net.close()
+    (sa, va, ta, sda, wa), (sb, vb, tb, sdb, wb) = recs
+    total = sum(len(x) for x in sa)
+    assert total > 100_000
+    for k in range(t):
+        assert np.array_equal(sa[k], sb[k]), k
+        assert np.all(np.diff(sa[k]) > 0) and (len(sa[k]) == 0 or (sa[k][0] >= 0 and sa[k][-1] < n))
+    assert np.array_equal(va, vb) and np.array_equal(ta, tb) and np.array_equal(wa, w) and np.array_equal(wb, w)
+    assert np.abs(sda - sdb).max() <= 1e-5 * max(1.0, np.abs(sdb).max())
+    assert np.count_nonzero(sdb) > 1_000_000
+    del recs, sda, sdb, va, vb, ta, tb
+    # learning on: event accounting and weight bounds
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, **kw)
+    sp, st = net.run(100, None, train[:100], da_events=[(50, 0, 0.5)], spikes_cap=1 << 22)
+    cnt = np.zeros((n, dmax + 1), np.int64)
+    np.add.at(cnt, (np.repeat(np.arange(n), fan), delay), 1)
+    cum = np.cumsum(cnt, axis=1)
+    expect = sum(int(cum[s, min(dmax, 100 - k)].sum()) for k, s in enumerate(sp))
+    assert st.n_syn_events == expect
+    wg = net.get(L.FIELD_W)
+    assert np.array_equal(wg[ne * fan:], w[ne * fan:])
+    assert wg[:ne * fan].min() >= 0.0 and wg[:ne * fan].max() <= 4.0 and np.abs(wg[:ne * fan] - 1.0).max() > 1e-4
