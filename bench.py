@@ -270,7 +270,7 @@ def run_b200(args):
                                        "by peer stores over NVLink + device-side wait (in-graph)"))
                                    if (args.partition and world > 1) else
                                    "one independent instance per GPU, no collective",
-                       "l2": "working set 2.2 GB per instance >> 126 MB L2 (no flush needed)"},
+                       "l2": "working set ~4 GB per instance >> 126 MB L2 (no flush needed)"},
             "sim_ms_per_wall_s": sim_ms * n_inst * (1 if (args.partition and world > 1) else world) / (dev_ms * 1e-3),
             "x_realtime_per_instance": sim_ms / dev_ms,
             "firing_rate_hz": spikes_all / world / (n * n_inst) / (sim_ms * 1e-3),
