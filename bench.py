@@ -164,7 +164,7 @@ def run_b200(args):
         rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9 + rank, n_instances=n_inst)
         net = SparseNetwork(n, ne, rowptr, post, w, delay, n_instances=n_inst, dtype="f32", mode="fast", noise="philox",
                             device=local, max_delay=dmax, noise_seed=10 + rank, exp_flags=args.exp_flags,
-                            graph=not args.no_graph, learn_async=args.learn_async, learn_blocks=args.learn_blocks, learn_tile_k=args.learn_tile_k, learn_stages=args.learn_stages)
+                            graph=not args.no_graph, learn_async=args.learn_async, learn_blocks=args.learn_blocks, learn_tile_k=args.learn_tile_k, learn_stages=args.learn_stages, side_blocks=args.side_blocks)
         n_plastic = int(rowptr[ne]) * n_inst
     del post, w, delay
     t_build = time.perf_counter() - t_build
@@ -464,6 +464,7 @@ def main():
     ap.add_argument("--learn-async", default="auto", choices=["auto", "off", "force"], help="learn pass beside the following steps (auto: large nets) or in place")
     ap.add_argument("--learn-tile-k", type=int, default=0, help="async learn pass: tile size in units of 1024 synapses (0 = 32)")
     ap.add_argument("--learn-stages", type=int, default=0, help="async learn pass: TMA pipeline depth (0 = 6)")
+    ap.add_argument("--side-blocks", type=int, default=0, help="10*synapse + ltp kernel blocks per SM (0 = default)")
     ap.add_argument("--learn-blocks", type=int, default=0, help="async learn pass: blocks per SM (0 = default)")
     ap.add_argument("--partition", nargs="?", const="p2p", default=None, choices=["p2p", "nccl"],
                     help="N>1: ONE network neuron-partitioned over the ranks (strong scaling) instead of one instance "

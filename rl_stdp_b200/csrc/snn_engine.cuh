@@ -303,9 +303,11 @@ __device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, u
 // flight per warp and ran at 0.5 TB/s — profiles/r1a), one Philox4x32 call yields the four noise
 // values.  A warp covers 128 neurons = 4 bitmap words.  Arrays are padded to Nld.
 // ---------------------------------------------------------------------------------------------
+// `bid` / `nblk`: this block's index and the block count of the neuron part (the partitioned runs
+// launch it fused with remote_body in one grid)
 template <typename T, bool EULER, bool DETECT>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? NEURON_MIN_BLOCKS : 2)
-neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev) {
+__device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev,
+                                            const uint32_t bid, const uint32_t nblk) {
   typedef Ops<T> O;
   tl_begin(p.tl, 0, k);
   const int lane = threadIdx.x & 31;
@@ -319,7 +321,7 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
   const int64_t rec_cap = cx->rec_cap;
   // spike-record offset of this step = offset of the previous step + its (final) spike count
   int32_t rec_base = 0;
-  const int n_prev = (k > 0 && (rec_ids || blockIdx.x == 0)) ? p.spk_cnt[prev] : 0;
+  const int n_prev = (k > 0 && (rec_ids || bid == 0)) ? p.spk_cnt[prev] : 0;
   if (rec_ids && k > 0) {
     int64_t nxt = (int64_t)cx->rec_off[k - 1] + n_prev;
     rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
@@ -332,7 +334,7 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
   if (DETECT) vw = wview(p);
 
   // dopamine (new_net.jl:131 da *= 0.995 ; newnet_DASTDP.jl:54-56 da += 0.5 after step!)
-  if (blockIdx.x == 0) {
+  if (bid == 0) {
     if (threadIdx.x == 0) {
       if (EULER && k > 0) {  // exactly one EULER launch per step k >= 1 (and the window-end launch)
         p.counters[0] += (unsigned long long)n_prev;
@@ -356,7 +358,7 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
 
   // whole warps only: the last rank's range is padded up to Nld (padding neurons are inactive)
   const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2);
-  for (uint32_t q = q_lo + blockIdx.x * blockDim.x + threadIdx.x; q < q_hi; q += gridDim.x * blockDim.x) {
+  for (uint32_t q = q_lo + bid * blockDim.x + threadIdx.x; q < q_hi; q += nblk * blockDim.x) {
     const uint32_t j0 = q << 2;
     // ---- all loads first
     Vec4<T> v = ld4(p.v + j0), u = ld4(p.u + j0), I, tp, ho;
@@ -500,7 +502,14 @@ neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
     st4(p.v + j0, v);
     st4(p.u + j0, u);
   }
+  if (p.tl) __syncthreads();  // timeline: stamp when the block's last warp (spike pushes) is done
   tl_end(p.tl, 0, k);
+}
+
+template <typename T, bool EULER, bool DETECT>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? NEURON_MIN_BLOCKS : 2)
+neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev) {
+  neuron_body<T, EULER, DETECT>(p, cx, k, apply_ev, blockIdx.x, gridDim.x);
 }
 
 // The bitmap word `wi` of ring slot `slot` as sent by its owner for the step tagged `tag`: spins on
@@ -530,8 +539,8 @@ __device__ __forceinline__ uint32_t ll_word(const DevNet<T>& p, int slot, uint32
 // neuron_kernel; no v/u traffic (16 B/neuron).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256)
-remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t wait_peers) {
+__device__ __forceinline__ void remote_body(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t wait_peers,
+                                            const uint32_t bid, const uint32_t nblk) {
   typedef Ops<T> O;
   tl_begin(p.tl, 4, k);
   const bool from_ll = wait_peers != 0;
@@ -554,7 +563,7 @@ remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
   // whole warps only: the last rank's range is padded up to Nld (padding neurons are inactive)
   const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2);
   const uint32_t nquad = (uint32_t)(p.Nld >> 2), n_remote = nquad - (q_hi - q_lo);
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_remote; r += gridDim.x * blockDim.x) {
+  for (uint32_t r = bid * blockDim.x + threadIdx.x; r < n_remote; r += nblk * blockDim.x) {
     const uint32_t q = r < q_lo ? r : r + (q_hi - q_lo);  // part bounds are multiples of 128: warps stay whole
     const uint32_t j0 = q << 2;
     Vec4<T> tp = ld4(trp + j0);
@@ -606,6 +615,23 @@ remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32
     }
   }
   tl_end(p.tl, 4, k);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t wait_peers) {
+  remote_body<T>(p, cx, k, wait_peers, blockIdx.x, gridDim.x);
+}
+
+// Partitioned runs: detection of the local neurons and the replay of the peers' detection in ONE
+// grid (blocks [0, n_local) / [n_local, gridDim)).  Both halves of a step start together — the
+// peers detect at the same time, so their (word, step) pairs arrive while the local half
+// integrates — and the step is one graph node instead of two kernels and a join.
+template <typename T, bool EULER>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? NEURON_MIN_BLOCKS : 2)
+neuron_remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t apply_ev, uint32_t n_local) {
+  if (blockIdx.x < n_local) neuron_body<T, EULER, true>(p, cx, k, apply_ev, blockIdx.x, n_local);
+  else remote_body<T>(p, cx, k, 1, blockIdx.x - n_local, gridDim.x - n_local);
 }
 
 // v[idx] = 40 (input! new_net.jl:104-106)
@@ -1769,10 +1795,14 @@ class Engine : public IEngine {
     if (gA_ == 0) {
       int per_sm = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synapse_kernel<T, true, true, true>, 256, 0);
-      gA_ = std::min(kMaxSynBlocks, n_sm_ * std::max(1, per_sm));
+      // reserved[7]: side-kernel footprint, tens = synapse blocks per SM, units = ltp blocks per SM
+      // default 6 + 2: the side kernels are persistent (their blocks live as long as the kernel), so
+      // whatever they hold is not available to the next neuron kernel when it becomes ready
+      const int syn_per_sm = cfg_.reserved[7] >= 10 ? cfg_.reserved[7] / 10 : 6;
+      gA_ = std::min(kMaxSynBlocks, n_sm_ * std::max(1, std::min(per_sm, syn_per_sm)));
     }
     l.gA = gA_;
-    l.gP = std::min(kMaxSynBlocks, n_sm_ * 4);
+    l.gP = std::min(kMaxSynBlocks, n_sm_ * ((cfg_.reserved[7] % 10) > 0 ? cfg_.reserved[7] % 10 : 2));
     int64_t plastic_per_inst = p.B ? (p.E / p.B) : 0;
     int gLx = (int)std::max<int64_t>(1, std::min<int64_t>((plastic_per_inst / 2 + 256 * 4 - 1) / (256 * 4),
                                                            std::max<int64_t>(1, (int64_t)n_sm_ * 8 / p.B)));
@@ -1972,8 +2002,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
     if (prof) prof_reserve(2 * (size_t)n + 2);  // no allocation while capturing
     // events: [0] neuron done, [1..3] pushes-for-step ready (ring of 3), [4..5] synapse LTD done
     // (ring of 2), [6..7] ltp done (ring of 2), [8] learn done / begun, [9] fork, [10] pass+replay done
-    cudaEvent_t evL = dep_ev_[8], evFork = dep_ev_[9], evFin = dep_ev_[10], evPre = dep_ev_[6], evR = dep_ev_[7];
-    cudaStream_t sR = remote_stream_;
+    cudaEvent_t evL = dep_ev_[8], evFork = dep_ev_[9], evFin = dep_ev_[10];
     auto evPush = [&](int step) { return dep_ev_[1 + ((step % 3) + 3) % 3]; };  // pushes consumed by Euler(step)
     auto evS = [&](int step) { return dep_ev_[4 + (step & 1)]; };
     auto evP = [&](int step) { return dep_ev_[12 + (step & 3)]; };  // ltp done (ring of 4)
@@ -1990,19 +2019,14 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
       const bool learn_prev = k >= 1 && wants_learn(a, k - 1, &dl, &dd);
       if (k >= 1) cudaStreamWaitEvent(sN, evPush(k - 1), 0);  // Euler(k-1) consumes them
       if (learn_prev) cudaStreamWaitEvent(sN, evL, 0);
-      const bool peers = p.n_ranks > 1;
-      if (peers) {
-        // neuron-partitioned: remote_kernel(k) runs BESIDE neuron_kernel(k) on its own stream — the
-        // peers detect at the same time, so their (word, step) pairs arrive while we integrate, and
-        // the replay of their detection is finished shortly after our own kernel instead of after it
-        cudaEventRecord(evPre, sN);
-        cudaStreamWaitEvent(sR, evPre, 0);
-        remote_kernel<T><<<g.gR, 256, 0, sR>>>(p, d_ctx_, k, 1);
-        cudaEventRecord(evR, sR);
+      if (p.n_ranks > 1) {  // neuron-partitioned: local detection + replay of the peers' detection, one node
+        if (k == 0) neuron_remote_kernel<T, false><<<g.gN + g.gR, 256, 0, sN>>>(p, d_ctx_, k, 1, (uint32_t)g.gN);
+        else neuron_remote_kernel<T, true><<<g.gN + g.gR, 256, 0, sN>>>(p, d_ctx_, k, 1, (uint32_t)g.gN);
+      } else if (k == 0) {
+        neuron_kernel<T, false, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
+      } else {
+        neuron_kernel<T, true, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
       }
-      if (k == 0) neuron_kernel<T, false, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
-      else neuron_kernel<T, true, true><<<g.gN, 256, 0, sN>>>(p, d_ctx_, k, 1);
-      if (peers) cudaStreamWaitEvent(sN, evR, 0);
       cudaEventRecord(evNk[k & 1], sN);
     };
     auto cap_side = [&](int k) {
