@@ -7,7 +7,7 @@ Workload (BASELINE.json target): N = 1 000 000 Izhikevich neuron
 inh), fan-out 100 -> 100 000 000 synapses, exc delays U{1..20} ms, inh delay 1 ms, DA-STDP on
 (learn! every 10th ms, dopamine +0.5 once per simulated second), fp32 production mode, thalamic
 noise 13*(U-0.5) from on-device Philox.  One bench "step" = one snn_step() window of
---window-ms simulated milliseconds (default 100).
+--window-ms simulated milliseconds (default 250).
 
 Metric: synaptic events/s (one spike delivered across one synapse), whole job.  Also reported:
 simulated-ms per wall-s (x real time), per-kernel roofline fractions, and the CPU oracle port
@@ -455,7 +455,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5_1M_100M", choices=sorted(WORKLOADS))
-    ap.add_argument("--window-ms", type=int, default=100)
+    ap.add_argument("--window-ms", type=int, default=250, help="simulated ms per snn_step() call (one bench step)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-ms-per-step", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")

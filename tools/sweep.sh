@@ -6,7 +6,7 @@ for a in "$@"; do
 import json, sys
 try:
     d = json.loads(sys.argv[2])
-    print(f"{sys.argv[1]:50s} us/ms={10*d['ms_per_step']:7.2f} xrt={d['x_realtime_per_instance']:6.2f} ev/s={d['value']:.3e} path={d['roofline_path']['frac']:.3f} learn={d['roofline']['frac']:.3f} ({1e3*d['roofline']['avg_launch_ms']:.0f} us) e2e={d['e2e']['value']:.3e}")
+    print(f"{sys.argv[1]:50s} xrt={d['x_realtime_per_instance']:6.2f} ev/s={d['value']:.3e} path={d['roofline_path']['frac']:.3f} learn={d['roofline']['frac']:.3f} ({1e3*d['roofline']['avg_launch_ms']:.0f} us) e2e={d['e2e']['value']:.3e}")
 except Exception as e:
     print(sys.argv[1], "FAILED", e, sys.argv[2][:300])
 PY
