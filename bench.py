@@ -40,6 +40,7 @@ WORKLOADS = {
     # name: (neurons, n_exc, fanout, max_delay)
     "c5_1M_100M": (1_000_000, 800_000, 100, 20),
     "c3_10k_1M": (10_000, 8_000, 100, 1),
+    "c1_single": (1_000, 800, 100, 1),   # BASELINE config 1 as the reference runs it: ONE 1000-neuron net
     # batched small nets: (neurons per instance, n_exc, fanout, max_delay, instances)
     "c1_x1024": (1_000, 800, 100, 1, 1024),
     "c3_x64": (10_000, 8_000, 100, 1, 64),
@@ -300,7 +301,8 @@ def run_b200(args):
             "clocks": clocks, "build_s": t_build,
         }
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            line["cpu_baseline"] = (cpu_baseline_dense_c1(args.cpu_seconds) if args.workload == "c1_single"
+                                    else cpu_baseline(args.cpu_seconds))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -375,6 +377,28 @@ def run_actors(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline_dense_c1(budget_s: float = 12.0):
+    """Config 1 exactly as the reference computes it: the DENSE N x N algorithm of new_net.jl
+    (oracle/snn_oracle.c ora_dense_*, fp64, 1 thread) on the full 1000-neuron net."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    n, ne = 1000, 800
+    conn = synth.dense_connection(n, 0.1, 1)
+    ora = po.DenseA(n, ne, conn)
+    fan = conn.sum(axis=1)
+    rng = np.random.Generator(np.random.Philox(key=2))
+    ev = steps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        sp = ora.step(13.0 * (rng.random(n) - 0.5), (steps + 1) % LEARN_PERIOD == 0)
+        ev += int(fan[sp].sum())
+        steps += 1
+    dt = time.perf_counter() - t0
+    return {"value": ev / dt, "unit": "events/s", "cores": 1, "kind": "port",
+            "sample": f"the full config-1 net (N=1000, dense N x N matrices as in new_net.jl), {steps} ms simulated in {dt:.1f} s",
+            "sim_ms_per_wall_s": steps / dt, "host_cpus": os.cpu_count()}
 
 
 def cpu_baseline(budget_s: float = 12.0, n=50_000, ne=40_000, fan=100, dmax=20):

@@ -1383,7 +1383,6 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaStreamCreateWithPriority(&side_stream_, cudaStreamNonBlocking, prio_mid));
     SNN_CUDA_OK(cudaStreamCreateWithPriority(&chain_stream_, cudaStreamNonBlocking, prio_hi));   // neuron chain
     SNN_CUDA_OK(cudaStreamCreateWithPriority(&learn_stream_, cudaStreamNonBlocking, prio_lo));   // async learn pass
-    SNN_CUDA_OK(cudaStreamCreateWithPriority(&remote_stream_, cudaStreamNonBlocking, prio_hi));  // remote_kernel beside neuron_kernel
     stream_ = own_stream_;
     SNN_CUDA_OK(cudaEventCreate(&ev_begin_));
     SNN_CUDA_OK(cudaEventCreate(&ev_end_));
@@ -1755,8 +1754,7 @@ class Engine : public IEngine {
     if (side2_stream_) cudaStreamDestroy(side2_stream_);
     if (chain_stream_) cudaStreamDestroy(chain_stream_);
     if (learn_stream_) cudaStreamDestroy(learn_stream_);
-    if (remote_stream_) cudaStreamDestroy(remote_stream_);
-    side2_stream_ = chain_stream_ = learn_stream_ = remote_stream_ = nullptr;
+    side2_stream_ = chain_stream_ = learn_stream_ = nullptr;
     memset(&p, 0, sizeof(p));
     own_stream_ = side_stream_ = nullptr; ev_begin_ = ev_end_ = nullptr; d_ctx_ = nullptr; h_ctx_ = nullptr; h_blk_ = nullptr;
   }
@@ -1832,7 +1830,7 @@ class Engine : public IEngine {
   cudaStream_t own_stream_ = nullptr, side_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev_begin_ = nullptr, ev_end_ = nullptr;
   cudaEvent_t dep_ev_[16] = {};
-  cudaStream_t side2_stream_ = nullptr, chain_stream_ = nullptr, learn_stream_ = nullptr, remote_stream_ = nullptr;
+  cudaStream_t side2_stream_ = nullptr, chain_stream_ = nullptr, learn_stream_ = nullptr;
   // asynchronous learn pass
   bool have_async_ = false;
   int cur_ = 0;                  // host mirror of LearnCtl.state >> 31 (read back after every window)
