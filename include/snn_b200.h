@@ -292,7 +292,7 @@ typedef struct snn_actor_config {
   int32_t device;
   int32_t n_agents;
   int32_t n_layers;      /* length(arch) */
-  int32_t arch[8];       /* e.g. {8,8,8}: sum(arch) + sum(arch[2:end-1]) must be <= 32 */
+  int32_t arch[8];       /* e.g. {8,8,8}: sum(arch) + sum(arch[2:end-1]) must be <= 64, every layer <= 32 */
   double vthresh, c;     /* cartpole_cfglif.yml:7-41 keys */
   double wei, wie, wmax;
   double theta, ttheta;

@@ -7,7 +7,8 @@
 // 40-ms spike-count window, left_right, tie -> replayed random action with -0.9 reward) with a
 // RESTATED CartPole-v1 (the reference calls OpenAI gym through PyCall; not in the reference).
 //
-// Mapping: lane j of a warp IS neuron j (n_neurons <= 32: the [8,8,8] actor has 24 exc + 8 inh).
+// Mapping: neuron j lives in lane j & 31, slot j >> 5 of its agent's warp (one neuron per lane for the
+// [8,8,8] actor: 24 exc + 8 inh; two for nets of up to 64 neurons such as [8,8,8,8,8]).
 // Weights e[l] and eligibility de[l] of the agent live in shared memory for the whole window /
 // episode; state is read from and written back to HBM once per launch.  fp64 with explicit
 // round-to-nearest mul/add (never contracted) so results are bit-identical to the oracle
@@ -36,9 +37,9 @@ struct ActorDev {
   double *v, *ho, *trace, *e, *de, *da;  // [A][n], [A][n], [A][n_exc], [A][w_tot], [A][w_tot], [A]
 };
 
-struct Lane {          // per-lane view of "its" neuron
+struct Lane {          // per-slot view of one neuron (neuron j lives in lane j & 31, slot j >> 5)
   int layer;           // exc layer index, or -1
-  int ilayer;          // hidden layer whose inh partner this lane is, or -1
+  int ilayer;          // hidden layer whose inh partner this neuron is, or -1
   int local;           // index inside the layer
 };
 
@@ -50,67 +51,86 @@ __device__ __forceinline__ Lane lane_info(const ActorDev& p, int j) {
   }
   return li;
 }
+// the `cnt` (<= 32) spike bits of the neurons off .. off+cnt-1
+__device__ __forceinline__ unsigned ext(unsigned long long mask, int off, int cnt) {
+  return (unsigned)(mask >> off) & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+}
 
 // One call of step_LIF!(net, spikes, train) / step_LIF_critic! for the agent owned by this warp.
-// se/sde: the agent's weights in shared memory, str: trace_e in shared memory.
-// Returns the spike mask (bit j = neuron j spiked).
-__device__ __forceinline__ unsigned lif_step(const ActorDev& p, const Lane& li, int lane, double intensity,
-                                             double& v, double& ho, double& da, double* se, double* sde,
-                                             double* str, int train, int critic) {
+// NS = neurons per lane (1: nets of <= 32 neurons, 2: <= 64).  se/sde: the agent's weights in shared
+// memory, str: trace_e in shared memory.  Returns the spike mask (bit j = neuron j spiked).
+template <int NS>
+__device__ __forceinline__ unsigned long long lif_step(const ActorDev& p, const Lane (&li)[NS], int lane,
+                                                       const double (&intensity)[NS], double (&v)[NS], double (&ho)[NS],
+                                                       double& da, double* se, double* sde, double* str, int train,
+                                                       int critic) {
   const unsigned FULL = 0xffffffffu;
-  const bool alive = lane < p.n;
   const double kk = 1.0 / p.taulif;  // (1/taulif) :151,:181
-  // input_LIF! :142-152 — I = (max-min)*intensity + min with max = imin + 1.0 computed literally
-  if (alive && li.layer == 0) {
-    const double gain = DSUB(DADD(p.imin, 1.0), p.imin);
-    const double I = DADD(0.0, DADD(DMUL(gain, intensity), p.imin));
-    v = DADD(v, DMUL(kk, DADD(DADD(-v, I), p.c)));
+  bool alive[NS], is_exc[NS], s[NS];
+  unsigned long long mask = 0ull;
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) {
+    const int j = lane + 32 * sl;
+    alive[sl] = j < p.n;
+    is_exc[sl] = j < p.n_exc;
+    // input_LIF! :142-152 — I = (max-min)*intensity + min with max = imin + 1.0 computed literally
+    if (alive[sl] && li[sl].layer == 0) {
+      const double gain = DSUB(DADD(p.imin, 1.0), p.imin);
+      const double I = DADD(0.0, DADD(DMUL(gain, intensity[sl]), p.imin));
+      v[sl] = DADD(v[sl], DMUL(kk, DADD(DADD(-v[sl], I), p.c)));
+    }
+    // spike_LIF! :154-211
+    s[sl] = alive[sl] && (DSUB(v[sl], ho[sl]) > p.vthresh);
+    mask |= (unsigned long long)__ballot_sync(FULL, s[sl]) << (32 * sl);
   }
-  // spike_LIF! :154-211
-  const bool s = alive && (DSUB(v, ho) > p.vthresh);
-  const unsigned mask = __ballot_sync(FULL, s);
-  const bool is_exc = alive && lane < p.n_exc;
-  if (s && is_exc) ho = DADD(ho, p.theta);  // :160 (every layer)
-  if (s) v = p.c;
-  // propagate :164-176 — ascending spiker id: exc sources first, then inh partners
-  double I = 0.0;
-  if (alive) {
-    if (li.layer >= 1) {
-      const int l = li.layer - 1;  // source layer
-      unsigned m = (mask >> p.off[l]) & ((1u << p.arch[l]) - 1u);
-      while (m) {
-        const int np = __ffs(m) - 1; m &= m - 1;
-        I = DADD(I, se[p.woff[l] + np + p.arch[l] * li.local]);
-      }
-      if (p.ioff[li.layer] >= 0) {  // ie[l] = wie .* (ones - I) :29
-        unsigned mi = (mask >> p.ioff[li.layer]) & ((1u << p.arch[li.layer]) - 1u);
-        while (mi) {
-          const int np = __ffs(mi) - 1; mi &= mi - 1;
-          I = DADD(I, DMUL(p.wie, DSUB(1.0, np == li.local ? 1.0 : 0.0)));
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) {
+    if (s[sl] && is_exc[sl]) ho[sl] = DADD(ho[sl], p.theta);  // :160 (every layer)
+    if (s[sl]) v[sl] = p.c;
+  }
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) {
+    // propagate :164-176 — ascending spiker id: exc sources first, then inh partners
+    double I = 0.0;
+    if (alive[sl]) {
+      if (li[sl].layer >= 1) {
+        const int l = li[sl].layer - 1;  // source layer
+        unsigned m = ext(mask, p.off[l], p.arch[l]);
+        while (m) {
+          const int np = __ffs(m) - 1; m &= m - 1;
+          I = DADD(I, se[p.woff[l] + np + p.arch[l] * li[sl].local]);
+        }
+        if (p.ioff[li[sl].layer] >= 0) {  // ie[l] = wie .* (ones - I) :29
+          unsigned mi = ext(mask, p.ioff[li[sl].layer], p.arch[li[sl].layer]);
+          while (mi) {
+            const int np = __ffs(mi) - 1; mi &= mi - 1;
+            I = DADD(I, DMUL(p.wie, DSUB(1.0, np == li[sl].local ? 1.0 : 0.0)));
+          }
+        }
+      } else if (li[sl].ilayer >= 0) {    // ei[l] = wei .* I(arch[l]) :30
+        unsigned m = ext(mask, p.off[li[sl].ilayer], p.arch[li[sl].ilayer]);
+        while (m) {
+          const int np = __ffs(m) - 1; m &= m - 1;
+          I = DADD(I, DMUL(p.wei, np == li[sl].local ? 1.0 : 0.0));
         }
       }
-    } else if (li.ilayer >= 0) {    // ei[l] = wei .* I(arch[l]) :30
-      unsigned m = (mask >> p.off[li.ilayer]) & ((1u << p.arch[li.ilayer]) - 1u);
-      while (m) {
-        const int np = __ffs(m) - 1; m &= m - 1;
-        I = DADD(I, DMUL(p.wei, np == li.local ? 1.0 : 0.0));
-      }
     }
+    // lr = arch[1]+1 : n_exc  :179-182 (inhibitory neurons are never integrated in LIF mode)
+    if (alive[sl] && li[sl].layer >= 1) {
+      double x = DADD(v[sl], I);
+      x = DADD(x, DMUL(kk, DADD(-x, p.c)));
+      v[sl] = fmax(x, 0.);
+    }
+    // trace_e[spiked_e] = 1.0 :185
+    if (is_exc[sl] && s[sl]) str[lane + 32 * sl] = 1.0;
   }
-  // lr = arch[1]+1 : n_exc  :179-182 (inhibitory neurons are never integrated in LIF mode)
-  if (alive && li.layer >= 1) {
-    double x = DADD(v, I);
-    x = DADD(x, DMUL(kk, DADD(-x, p.c)));
-    v = fmax(x, 0.);
-  }
-  // trace_e[spiked_e] = 1.0 :185, then STDP :188-200 with the new traces
-  if (is_exc) { if (s) str[lane] = 1.0; }
   __syncwarp();
-  if (mask & ((p.n_exc >= 32) ? FULL : ((1u << p.n_exc) - 1u))) {
+  // STDP :188-200 with the new traces
+  if (mask & (p.n_exc >= 64 ? ~0ull : ((1ull << p.n_exc) - 1ull))) {
     for (int l = 0; l < p.L - 1; ++l) {
       const int nr = p.arch[l], nc = p.arch[l + 1];
-      const unsigned mr = (mask >> p.off[l]) & ((1u << nr) - 1u);
-      const unsigned mc = (mask >> p.off[l + 1]) & ((1u << nc) - 1u);
+      const unsigned mr = ext(mask, p.off[l], nr);
+      const unsigned mc = ext(mask, p.off[l + 1], nc);
       if (!(mr | mc)) continue;
       for (int q = lane; q < nr * nc; q += 32) {
         const int i = q % nr, jj = q / nr;  // column-major [i + nr*jj]
@@ -124,8 +144,11 @@ __device__ __forceinline__ unsigned lif_step(const ActorDev& p, const Lane& li, 
   }
   __syncwarp();
   // time decay :204-209
-  if (alive) ho = DMUL(ho, p.ttheta);
-  if (is_exc) str[lane] = DMUL(str[lane], p.ttrace);
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) {
+    if (alive[sl]) ho[sl] = DMUL(ho[sl], p.ttheta);
+    if (is_exc[sl]) str[lane + 32 * sl] = DMUL(str[lane + 32 * sl], p.ttrace);
+  }
   da = DMUL(da, p.tde);  // (tde, not tda)
   for (int q = lane; q < p.w_tot; q += 32) sde[q] = DMUL(sde[q], p.tde);
   __syncwarp();
@@ -150,24 +173,36 @@ __device__ __forceinline__ unsigned lif_step(const ActorDev& p, const Lane& li, 
   return mask;
 }
 
-__device__ __forceinline__ void load_agent(const ActorDev& p, int a, int lane, double& v, double& ho, double& da,
+constexpr int kActorTraceSlots = 64;  // shared-memory slots of trace_e per agent
+
+template <int NS>
+__device__ __forceinline__ void load_agent(const ActorDev& p, int a, int lane, double (&v)[NS], double (&ho)[NS], double& da,
                                            double* se, double* sde, double* str) {
-  v = lane < p.n ? p.v[(size_t)a * p.n + lane] : 0.0;
-  ho = lane < p.n ? p.ho[(size_t)a * p.n + lane] : 0.0;
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) {
+    const int j = lane + 32 * sl;
+    v[sl] = j < p.n ? p.v[(size_t)a * p.n + j] : 0.0;
+    ho[sl] = j < p.n ? p.ho[(size_t)a * p.n + j] : 0.0;
+    if (j < p.n_exc) str[j] = p.trace[(size_t)a * p.n_exc + j];
+  }
   da = p.da[a];
-  if (lane < p.n_exc) str[lane] = p.trace[(size_t)a * p.n_exc + lane];
   for (int q = lane; q < p.w_tot; q += 32) {
     se[q] = p.e[(size_t)a * p.w_tot + q];
     sde[q] = p.de[(size_t)a * p.w_tot + q];
   }
   __syncwarp();
 }
-__device__ __forceinline__ void store_agent(const ActorDev& p, int a, int lane, double v, double ho, double da,
-                                            const double* se, const double* sde, const double* str) {
+template <int NS>
+__device__ __forceinline__ void store_agent(const ActorDev& p, int a, int lane, const double (&v)[NS], const double (&ho)[NS],
+                                            double da, const double* se, const double* sde, const double* str) {
   __syncwarp();
-  if (lane < p.n) { p.v[(size_t)a * p.n + lane] = v; p.ho[(size_t)a * p.n + lane] = ho; }
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) {
+    const int j = lane + 32 * sl;
+    if (j < p.n) { p.v[(size_t)a * p.n + j] = v[sl]; p.ho[(size_t)a * p.n + j] = ho[sl]; }
+    if (j < p.n_exc) p.trace[(size_t)a * p.n_exc + j] = str[j];
+  }
   if (lane == 0) p.da[a] = da;
-  if (lane < p.n_exc) p.trace[(size_t)a * p.n_exc + lane] = str[lane];
   for (int q = lane; q < p.w_tot; q += 32) {
     p.e[(size_t)a * p.w_tot + q] = se[q];
     p.de[(size_t)a * p.w_tot + q] = sde[q];
@@ -176,6 +211,7 @@ __device__ __forceinline__ void store_agent(const ActorDev& p, int a, int lane, 
 
 // n_steps calls of step_LIF! with a constant input (cartpole_fitness.jl:70-79): optional v .= c
 // first, last-layer spike counts accumulated from step index >= L-1 (1-based msec >= L-1).
+template <int NS>
 __global__ void __launch_bounds__(128)
 actor_window_kernel(ActorDev p, const double* __restrict__ intensity, int n_steps, int train, int critic,
                     int reset_v, int32_t* __restrict__ counts, int32_t* __restrict__ spikes, int64_t spikes_stride) {
@@ -183,22 +219,33 @@ actor_window_kernel(ActorDev p, const double* __restrict__ intensity, int n_step
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int a = blockIdx.x * (blockDim.x >> 5) + wib;
   if (a >= p.n_agents) return;
-  double* se = smem + (size_t)wib * (2 * p.w_tot + 32);
+  double* se = smem + (size_t)wib * (2 * p.w_tot + kActorTraceSlots);
   double* sde = se + p.w_tot;
   double* str = sde + p.w_tot;
-  double v, ho, da;
-  load_agent(p, a, lane, v, ho, da, se, sde, str);
-  const Lane li = lane_info(p, lane);
-  const double inten = (li.layer == 0 && lane < p.n) ? intensity[(size_t)a * p.arch[0] + li.local] : 0.0;
-  if (reset_v && lane < p.n) v = p.c;  // net.v .= c  cartpole_fitness.jl:71
-  int cnt = 0;
-  for (int msec = 1; msec <= n_steps; ++msec) {
-    const unsigned m = lif_step(p, li, lane, inten, v, ho, da, se, sde, str, train, critic);
-    if (msec >= p.L - 1 && li.layer == p.L - 1 && ((m >> lane) & 1u)) ++cnt;
-    if (spikes && lane == 0) spikes[(size_t)a * spikes_stride + (msec - 1)] = (int32_t)m;
+  double v[NS], ho[NS], da, inten[NS];
+  Lane li[NS];
+  int cnt[NS];
+  load_agent<NS>(p, a, lane, v, ho, da, se, sde, str);
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) {
+    const int j = lane + 32 * sl;
+    li[sl] = lane_info(p, j);
+    inten[sl] = (li[sl].layer == 0 && j < p.n) ? intensity[(size_t)a * p.arch[0] + li[sl].local] : 0.0;
+    if (reset_v && j < p.n) v[sl] = p.c;  // net.v .= c  cartpole_fitness.jl:71
+    cnt[sl] = 0;
   }
-  if (counts && li.layer == p.L - 1 && lane < p.n) counts[(size_t)a * p.arch[p.L - 1] + li.local] = cnt;
-  store_agent(p, a, lane, v, ho, da, se, sde, str);
+  for (int msec = 1; msec <= n_steps; ++msec) {
+    const unsigned long long m = lif_step<NS>(p, li, lane, inten, v, ho, da, se, sde, str, train, critic);
+#pragma unroll
+    for (int sl = 0; sl < NS; ++sl)
+      if (msec >= p.L - 1 && li[sl].layer == p.L - 1 && ((m >> (lane + 32 * sl)) & 1ull)) ++cnt[sl];
+    if (spikes && lane == 0) spikes[(size_t)a * spikes_stride + (msec - 1)] = (int32_t)(unsigned)m;
+  }
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl)
+    if (counts && li[sl].layer == p.L - 1 && lane + 32 * sl < p.n)
+      counts[(size_t)a * p.arch[p.L - 1] + li[sl].local] = cnt[sl];
+  store_agent<NS>(p, a, lane, v, ho, da, se, sde, str);
 }
 
 // sin/cos restated with the fdlibm kernel polynomials (|x| <= pi/4 — the pole angle never leaves
@@ -240,6 +287,7 @@ __device__ __forceinline__ int cartpole_step(double s[4], int action) {
 
 // play_episode (cartpole_fitness.jl:51-114) for every agent; optional teacher-style dopamine
 // (CartPole/Teacher/teacher_sim.jl:61-80,132-133: da += (action==draw ? 1 : -200) * da_inc).
+template <int NS>
 __global__ void __launch_bounds__(128)
 actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const double* __restrict__ state0,
                      const int32_t* __restrict__ tie_actions, const int32_t* __restrict__ teach_actions,
@@ -250,19 +298,23 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int a = blockIdx.x * (blockDim.x >> 5) + wib;
   if (a >= p.n_agents) return;
-  double* se = smem + (size_t)wib * (2 * p.w_tot + 32);
+  double* se = smem + (size_t)wib * (2 * p.w_tot + kActorTraceSlots);
   double* sde = se + p.w_tot;
   double* str = sde + p.w_tot;
-  double v, ho, da;
-  load_agent(p, a, lane, v, ho, da, se, sde, str);
-  const Lane li = lane_info(p, lane);
+  double v[NS], ho[NS], da;
+  Lane li[NS];
+  load_agent<NS>(p, a, lane, v, ho, da, se, sde, str);
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl) li[sl] = lane_info(p, lane + 32 * sl);
   const int A0 = p.arch[0], Lout = p.arch[p.L - 1], n_left = Lout / 2;
   double st[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) st[c] = state0[(size_t)a * 4 + c];
-  double ma[4] = {0, 0, 0, 0};  // row `local` of matalpha (arch[0] x 4, column-major)
-  if (li.layer == 0 && lane < p.n)
-    for (int c = 0; c < 4; ++c) ma[c] = matalpha[(size_t)a * A0 * 4 + li.local + A0 * c];
+  double ma[NS][4];  // row `local` of matalpha (arch[0] x 4, column-major)
+#pragma unroll
+  for (int sl = 0; sl < NS; ++sl)
+    for (int c = 0; c < 4; ++c)
+      ma[sl][c] = (li[sl].layer == 0 && lane + 32 * sl < p.n) ? matalpha[(size_t)a * A0 * 4 + li[sl].local + A0 * c] : 0.0;
   double tot_reward = 0.0;
   int n_rand = 0, n_tot = 0;
   const double pi = 3.14159265358979323846;
@@ -277,18 +329,30 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
     on[1] = __ddiv_rn(DADD(st[1], 7.5), 15.0);
     on[2] = __ddiv_rn(DADD(theta, cone), DMUL(2.0, cone));
     on[3] = __ddiv_rn(DADD(st[3], 7.5), 15.0);
-    double inten = 0.0;  // matalpha*norm_cartpole(obs) :67
+    double inten[NS];  // matalpha*norm_cartpole(obs) :67
+    int cnt[NS];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) inten = DADD(inten, DMUL(ma[c], on[c]));
-    if (lane < p.n) v = p.c;  // :71
-    int cnt = 0;
+    for (int q = 0; q < NS; ++q) {
+      inten[q] = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) inten[q] = DADD(inten[q], DMUL(ma[q][c], on[c]));
+      if (lane + 32 * q < p.n) v[q] = p.c;  // :71
+      cnt[q] = 0;
+    }
     for (int msec = 1; msec <= win_size; ++msec) {
-      const unsigned m = lif_step(p, li, lane, inten, v, ho, da, se, sde, str, train, 0);
-      if (msec >= p.L - 1 && li.layer == p.L - 1 && ((m >> lane) & 1u)) ++cnt;
+      const unsigned long long m = lif_step<NS>(p, li, lane, inten, v, ho, da, se, sde, str, train, 0);
+#pragma unroll
+      for (int q = 0; q < NS; ++q)
+        if (msec >= p.L - 1 && li[q].layer == p.L - 1 && ((m >> (lane + 32 * q)) & 1ull)) ++cnt[q];
     }
     // left_right :36-41 — counts are small integers: any summation order is exact
-    const bool outl = li.layer == p.L - 1 && lane < p.n;
-    int sl = (outl && li.local < n_left) ? cnt : 0, sr = (outl && li.local >= n_left) ? cnt : 0;
+    int sl = 0, sr = 0;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const bool outl = li[q].layer == p.L - 1 && lane + 32 * q < p.n;
+      sl += (outl && li[q].local < n_left) ? cnt[q] : 0;
+      sr += (outl && li[q].local >= n_left) ? cnt[q] : 0;
+    }
     for (int o = 16; o > 0; o >>= 1) { sl += __shfl_xor_sync(FULL, sl, o); sr += __shfl_xor_sync(FULL, sr, o); }
     int action = (sl >= sr) ? 0 : 1;
     if (sl == sr) {  // :87-95
@@ -311,7 +375,7 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
     if (n_rand_out) n_rand_out[a] = n_rand;
     if (state_out) for (int c = 0; c < 4; ++c) state_out[(size_t)a * 4 + c] = st[c];
   }
-  store_agent(p, a, lane, v, ho, da, se, sde, str);
+  store_agent<NS>(p, a, lane, v, ho, da, se, sde, str);
 }
 
 __global__ void fill_d(double* a, int64_t n, double x) {
@@ -361,8 +425,9 @@ int Actor::init(const snn_actor_config& c, std::string& err) {
     if (l < d.L - 1) { d.woff[l] = wacc; wacc += c.arch[l] * c.arch[l + 1]; }
   }
   d.n = iacc; d.n_inh = iacc - acc; d.w_tot = wacc;
-  if (d.n > 32) { err = "actor kernel maps one neuron per lane: n_exc + n_inh must be <= 32 (use the sparse engine for larger nets)"; return SNN_ERR_INVALID; }
-  for (int l = 0; l < d.L; ++l) if (c.arch[l] < 1 || c.arch[l] > 31) { err = "layer sizes must be in 1..31"; return SNN_ERR_INVALID; }
+  if (d.n > 64) { err = "actor kernel maps at most two neurons per lane: n_exc + n_inh must be <= 64 (use the sparse engine for larger nets)"; return SNN_ERR_INVALID; }
+  for (int l = 0; l < d.L; ++l) if (c.arch[l] < 1 || c.arch[l] > 32) { err = "layer sizes must be in 1..32"; return SNN_ERR_INVALID; }
+  if ((size_t)(2 * wacc + kActorTraceSlots) * sizeof(double) > 48 * 1024) { err = "actor weights exceed 48 KB of shared memory per agent"; return SNN_ERR_INVALID; }
   d.vthresh = c.vthresh; d.c = c.c; d.wei = c.wei; d.wie = c.wie; d.wmax = c.wmax; d.theta = c.theta; d.ttheta = c.ttheta;
   d.imin = c.imin; d.apost = c.apost; d.apre = c.apre; d.tde = c.tde; d.ttrace = c.ttrace; d.taulif = c.taulif;
   d.eta = c.eta; d.winh = c.winh; d.da_inc = c.da_inc;
@@ -425,12 +490,19 @@ int Actor::set_array(int field, int layer, const double* host, int64_t count, st
   return SNN_OK;
 }
 
-static inline size_t actor_smem(const ActorDev& d, int warps) { return (size_t)warps * (2 * d.w_tot + 32) * sizeof(double); }
+// agents (warps) per block: four while their weights fit the default 48 KB of dynamic shared memory
+static inline int actor_warps(const ActorDev& d) {
+  for (int w = 4; w > 1; w >>= 1)
+    if ((size_t)w * (2 * d.w_tot + kActorTraceSlots) * sizeof(double) <= 48 * 1024) return w;
+  return 1;
+}
+static inline size_t actor_smem(const ActorDev& d, int warps) { return (size_t)warps * (2 * d.w_tot + kActorTraceSlots) * sizeof(double); }
 
 int Actor::window(int n_steps, const double* intensity, int train, int critic, int reset_v, int32_t* counts,
                   int32_t* spike_masks, double* device_ms, std::string& err) {
   ActorDev& d = impl_->d;
   if (n_steps <= 0 || !intensity) { err = "n_steps must be > 0 and intensity non-null"; return SNN_ERR_INVALID; }
+  if (spike_masks && d.n > 32) { err = "spike_masks hold 32 neurons: not available for nets with more than 32 neurons"; return SNN_ERR_INVALID; }
   ACT_OK(cudaSetDevice(impl_->device));
   const size_t A = (size_t)d.n_agents;
   double* d_int = nullptr; int32_t *d_cnt = nullptr, *d_spk = nullptr;
@@ -440,10 +512,14 @@ int Actor::window(int n_steps, const double* intensity, int train, int critic, i
   if (e == cudaSuccess && spike_masks) e = cudaMalloc(&d_spk, A * n_steps * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_int, intensity, A * d.arch[0] * sizeof(double), cudaMemcpyHostToDevice, impl_->stream);
   if (e == cudaSuccess) {
-    const int warps = 4, blocks = (int)((A + warps - 1) / warps);
+    const int warps = actor_warps(d), blocks = (int)((A + warps - 1) / warps);
     cudaEventRecord(impl_->e0, impl_->stream);
-    actor_window_kernel<<<blocks, warps * 32, actor_smem(d, warps), impl_->stream>>>(d, d_int, n_steps, train, critic, reset_v,
-                                                                                      d_cnt, d_spk, n_steps);
+    if (d.n <= 32)
+      actor_window_kernel<1><<<blocks, warps * 32, actor_smem(d, warps), impl_->stream>>>(d, d_int, n_steps, train, critic,
+                                                                                           reset_v, d_cnt, d_spk, n_steps);
+    else
+      actor_window_kernel<2><<<blocks, warps * 32, actor_smem(d, warps), impl_->stream>>>(d, d_int, n_steps, train, critic,
+                                                                                           reset_v, d_cnt, d_spk, n_steps);
     cudaEventRecord(impl_->e1, impl_->stream);
     e = cudaGetLastError();
   }
@@ -482,10 +558,14 @@ int Actor::episodes(const double* matalpha, const double* state0, const int32_t*
   if (e == cudaSuccess && teach_actions)
     e = cudaMemcpyAsync(d_teach, teach_actions, A * n_decisions_max * sizeof(int32_t), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) {
-    const int warps = 4, blocks = (int)((A + warps - 1) / warps);
+    const int warps = actor_warps(d), blocks = (int)((A + warps - 1) / warps);
     cudaEventRecord(impl_->e0, s);
-    actor_episode_kernel<<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, d_teach, n_decisions_max,
-                                                                           win_size, train, d_rw, d_nd, d_nr, d_so);
+    if (d.n <= 32)
+      actor_episode_kernel<1><<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, d_teach, n_decisions_max,
+                                                                                win_size, train, d_rw, d_nd, d_nr, d_so);
+    else
+      actor_episode_kernel<2><<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, d_teach, n_decisions_max,
+                                                                                win_size, train, d_rw, d_nd, d_nr, d_so);
     cudaEventRecord(impl_->e1, s);
     e = cudaGetLastError();
   }

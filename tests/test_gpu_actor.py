@@ -63,6 +63,55 @@ def test_decision_window_bitexact(train, critic):
     assert tot > 0
 
 
+@pytest.mark.parametrize("arch", [[8, 8, 8, 8, 8], [12, 10, 6], [16, 16, 16]])
+def test_larger_actors_two_neurons_per_lane(arch):
+    """Nets of 33..64 neurons (e.g. the [8,8,8,8,8] actors of CartPole/LIF_base): two neurons per lane.
+    Decision windows with learning and whole episodes, bit-exact against the oracle."""
+    from rl_stdp_b200 import _lib as L
+    from rl_stdp_b200.lif import borne
+    A, T = 19, 40
+    param = dict(theta=0.05, wei=0.3, wie=-0.2, apost=0.014, apre=0.019, ttrace=0.95, imin=0.9)
+    pop, oras, rng = _mk(A, arch, 21, **param)
+    idx = np.arange(arch[0], dtype=np.int32)
+    n_out0 = sum(arch[:-1])
+    for rep in range(2):
+        inten = rng.random((A, arch[0])) * 1.5
+        da0 = rng.random(A) * 0.02 - 0.005
+        pop.set(L.FIELD_DA, pop.get(L.FIELD_DA)[:, 0] + da0)
+        counts, _, _ = pop.decision_window(inten, T, train=True, reset_v=True)
+        for a, o in enumerate(oras):
+            o.da = o.da + da0[a]
+            o.v[:] = o.params["c"]
+            cnt = np.zeros(arch[-1], np.int32)
+            for msec in range(1, T + 1):
+                sp = o.step_lif(idx, inten[a], True, False)
+                if msec >= len(arch) - 1:
+                    for j in sp:
+                        if n_out0 <= j < sum(arch):
+                            cnt[j - n_out0] += 1
+            assert np.array_equal(counts[a], cnt), (rep, a)
+    v, ho, tr, da = pop.get(L.FIELD_V), pop.get(L.FIELD_HO), pop.get(L.FIELD_TRACE), pop.get(L.FIELD_DA)
+    moved = 0
+    for a, o in enumerate(oras):
+        assert np.array_equal(v[a], o.v) and np.array_equal(ho[a], o.ho) and np.array_equal(tr[a], o.trace_e)
+        assert da[a, 0] == o.da
+        for l in range(len(arch) - 1):
+            assert np.array_equal(pop.weights(l)[a], o.e(l)), (a, l)
+            assert np.array_equal(pop.weights(l, L.FIELD_SD)[a], o.de(l)), (a, l)
+            moved += np.abs(o.de(l)).sum()
+    assert moved > 0 and counts.sum() > 0
+    # whole episodes
+    n_steps = 120
+    matalpha = borne(rng.random((A, arch[0], 4)) * 20 - 10, -1.0, 1.0)
+    state0 = rng.random((A, 4)) * 0.1 - 0.05
+    ties = rng.integers(0, 2, size=(A, n_steps), dtype=np.int32)
+    out = pop.play_episodes(matalpha, state0, ties, n_steps=n_steps)
+    for a, o in enumerate(oras):
+        r, nd, nr, so = o.play_episode(matalpha[a], state0[a], ties[a], n_steps, train=False)
+        assert out["rewards"][a] == r and out["n_decisions"][a] == nd and out["n_rand"][a] == nr
+        assert np.array_equal(out["state"][a], so)
+
+
 def test_episodes_bitexact_and_ragged():
     """play_episode for 64 agents (different weights, M_alpha, reset states, tie streams): returns,
     decision counts, tie counts and final env states identical to the oracle; episodes end at
@@ -113,6 +162,8 @@ def test_actor_config_errors():
     from rl_stdp_b200 import _lib as L
     from rl_stdp_b200.lif import ActorPopulation
     with pytest.raises(L.SnnError):
-        ActorPopulation([16, 16, 16], 4)  # 48 exc + 16 inh > 32 lanes
+        ActorPopulation([24, 24, 24], 4)  # 72 exc + 24 inh > 64 neurons (two per lane)
+    with pytest.raises(L.SnnError):
+        ActorPopulation([8, 40, 8], 4)    # a layer wider than 32
     with pytest.raises(L.SnnError):
         ActorPopulation([8, 8, 8], 0)
