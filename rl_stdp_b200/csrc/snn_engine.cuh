@@ -1832,7 +1832,7 @@ class Engine : public IEngine {
   cudaEvent_t dep_ev_[16] = {};
   cudaStream_t side2_stream_ = nullptr, chain_stream_ = nullptr, learn_stream_ = nullptr;
   // asynchronous learn pass
-  bool have_async_ = false;
+  bool have_async_ = false, pass_attr_set_ = false;
   int cur_ = 0;                  // host mirror of LearnCtl.state >> 31 (read back after every window)
   int64_t n_plastic_ = 0;
   std::vector<uint32_t> inst_lo_, inst_hi_;
@@ -1958,11 +1958,10 @@ void Engine<T>::launch_pass(cudaStream_t s4, int k, int do_decay, bool prof) {
   } else {
     const int S = cfg_.reserved[6] >= 2 && cfg_.reserved[6] <= kPassMaxStages ? cfg_.reserved[6] : kPassStages;
     const size_t smem = (size_t)S * kPassChunkBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!pass_attr_set_) {  // per engine: the attribute belongs to the (function, device) pair
       cudaFuncSetAttribute(learn_pass_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            kPassMaxStages * (int)kPassChunkBytes);
-      attr_set = true;
+      pass_attr_set_ = true;
     }
     learn_pass_tma_kernel<T><<<grid, kPassThreads, smem, s4>>>(p, k, do_decay, S);
   }
