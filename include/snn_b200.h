@@ -223,6 +223,13 @@ typedef struct snn_step_io {
   int64_t* spike_offsets;
   int64_t spikes_cap;
   snn_step_stats* stats;
+  /* synapse probes: (w, sd) of `n_probes` synapses (indices in the caller's CSR order) after every
+   * step of the window, probe_out[n_steps][n_probes][2] — `shist[time,:] = [net.s[n1,syn],
+   * net.sd[n1,syn]]` of Old_net/Julia_DA_STDPv2.jl:91 / newnet_DASTDP.jl:57-60.  A window with probes
+   * runs as plain launches with learn! in place (a diagnostics path). */
+  const int64_t* probe_syn;
+  double* probe_out;
+  int32_t n_probes, reserved2;
 } snn_step_io;
 int32_t snn_step_ex(snn_net* net, const snn_step_io* io);
 

@@ -82,6 +82,7 @@ class SnnStepIO(C.Structure):
         ("n_force", C.c_int32), ("n_da", C.c_int32), ("n_currents", C.c_int32), ("reserved", C.c_int32),
         ("spikes_out", C.c_void_p), ("spike_offsets", C.c_void_p), ("spikes_cap", C.c_int64),
         ("stats", C.POINTER(SnnStepStats)),
+        ("probe_syn", C.c_void_p), ("probe_out", C.c_void_p), ("n_probes", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

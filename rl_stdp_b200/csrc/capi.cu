@@ -146,6 +146,8 @@ int32_t snn_step_ex(snn_net* net, const snn_step_io* io) {
   a.n_steps = io->n_steps; a.noise = io->noise; a.train_flags = io->train_flags; a.force = io->force;
   a.n_force = io->n_force; a.da = io->da; a.n_da = io->n_da; a.cur = io->currents; a.n_cur = io->n_currents;
   a.spikes_out = io->spikes_out; a.spike_offsets = io->spike_offsets; a.spikes_cap = io->spikes_cap; a.stats = io->stats;
+  a.probe_syn = io->probe_syn; a.n_probes = io->n_probes; a.probe_out = io->probe_out;
+  if (io->n_probes < 0) return fail(SNN_ERR_INVALID, "n_probes < 0");
   std::string err;
   int rc = net->eng->step(a, err);
   return rc ? fail(rc, err) : SNN_OK;

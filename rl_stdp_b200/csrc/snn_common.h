@@ -76,6 +76,9 @@ struct StepArgs {
   int64_t* spike_offsets;
   int64_t spikes_cap;
   snn_step_stats* stats;
+  const int64_t* probe_syn = nullptr;  // caller-order synapse indices
+  int32_t n_probes = 0;
+  double* probe_out = nullptr;         // [n_steps][n_probes][2] = (w, sd) after each step
 };
 
 class IEngine {

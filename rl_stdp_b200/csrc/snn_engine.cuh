@@ -1351,6 +1351,24 @@ __global__ void wsd_to_caller(const typename Real2<T>::type* __restrict__ wsd, c
     out[perm[e]] = (double)(comp == 0 ? wsd[e].x : wsd[e].y);
 }
 
+// ---- synapse probes: (w, sd) of a few chosen synapses after every step — the reference's
+// `shist[time,:] = [net.s[n1,syn], net.sd[n1,syn]]` (Old_net/Julia_DA_STDPv2.jl:91, newnet_DASTDP.jl:57-60)
+static __global__ void probe_locate_kernel(const uint32_t* __restrict__ perm, int64_t E, const int64_t* __restrict__ want,
+                                    int n, uint32_t* __restrict__ pos) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = perm[e];
+    for (int q = 0; q < n; ++q) if (want[q] == c) pos[q] = (uint32_t)e;
+  }
+}
+template <typename T>
+__global__ void probe_kernel(DevNet<T> p, const uint32_t* __restrict__ pos, int n, double* __restrict__ out, int32_t k) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const typename DevNet<T>::T2 ws = wview(p).cur[pos[q]];
+  out[((size_t)k * n + q) * 2] = (double)ws.x;
+  out[((size_t)k * n + q) * 2 + 1] = (double)ws.y;
+}
+
 // grow-only device buffer
 struct DevBuf {
   void* ptr = nullptr; size_t cap = 0;
@@ -1741,7 +1759,7 @@ class Engine : public IEngine {
     if (h_ctx_) cudaFreeHost(h_ctx_);
     if (h_blk_) cudaFreeHost(h_blk_);
     b_noise_.release(); b_noise64_.release(); b_ev_off_.release(); b_ev_inst_.release(); b_ev_amt_.release();
-    sort_scratch_.release();
+    sort_scratch_.release(); b_probe_want_.release(); b_probe_pos_.release(); b_probe_out_.release();
     b_force_.release(); b_rec_.release(); b_rec_off_.release(); b_cur_idx_.release(); b_cur_val_.release();
     topo_.release();
     if (ev_begin_) cudaEventDestroy(ev_begin_);
@@ -1844,6 +1862,7 @@ class Engine : public IEngine {
   unsigned long long* h_blk_ = nullptr;
   DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_, b_cur_idx_, b_cur_val_;
   SortScratch sort_scratch_;
+  DevBuf b_probe_want_, b_probe_pos_, b_probe_out_;
   std::vector<void*> ipc_opened_;
   snn_exchange_fn exchange_ = nullptr; void* exchange_user_ = nullptr; int exchange_failed_ = 0;
   const std::vector<cudaEvent_t>* graph_prof_events_ = nullptr;
@@ -1918,6 +1937,8 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
       // the pushes of step k+1 must see the weights after learn!(k)
       if (push_next) synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
     }
+    if (a.n_probes > 0)
+      probe_kernel<T><<<(a.n_probes + 63) / 64, 64, 0, s>>>(p, b_probe_pos_.as<uint32_t>(), a.n_probes, b_probe_out_.as<double>(), k);
   }
 }
 
@@ -2249,7 +2270,19 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   }
 
   // ---- the window
-  const bool graphable = use_graph_ && !p.exact && a.n_force == 0 && a.n_cur == 0 && profiling_ != 1 && !exchange_;
+  if (a.n_probes > 0) {  // per-step probes: plain launches, learn! in place (diagnostics path)
+    if (a.n_probes > 4096 || !a.probe_syn || !a.probe_out) { err = "probes: 1..4096 synapse indices and an output buffer"; return SNN_ERR_INVALID; }
+    for (int q = 0; q < a.n_probes; ++q)
+      if (a.probe_syn[q] < 0 || a.probe_syn[q] >= p.E) { err = "probe synapse index out of range"; return SNN_ERR_INVALID; }
+    SNN_CUDA_OK(b_probe_want_.reserve(a.n_probes * sizeof(int64_t)));
+    SNN_CUDA_OK(b_probe_pos_.reserve(a.n_probes * sizeof(uint32_t)));
+    SNN_CUDA_OK(b_probe_out_.reserve((size_t)n * a.n_probes * 2 * sizeof(double)));
+    SNN_CUDA_OK(cudaMemcpyAsync(b_probe_want_.ptr, a.probe_syn, a.n_probes * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+    probe_locate_kernel<<<grid_for(p.E), 256, 0, stream_>>>(topo_.perm, p.E, b_probe_want_.as<int64_t>(), a.n_probes,
+                                                            b_probe_pos_.as<uint32_t>());
+  }
+  const bool graphable = use_graph_ && !p.exact && a.n_force == 0 && a.n_cur == 0 && profiling_ != 1 && !exchange_ &&
+                         a.n_probes == 0;
   last_pass_launches_ = 0;
   if (graphable) {
     int rc = launch_graph(a, profiling_ == 2, err);
@@ -2281,6 +2314,9 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     if (total > 0) SNN_CUDA_OK(cudaMemcpyAsync(a.spikes_out, b_rec_.ptr, total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     for (int k = 0; k <= n; ++k) a.spike_offsets[k] = h_off[k];
   }
+  if (a.n_probes > 0)
+    SNN_CUDA_OK(cudaMemcpyAsync(a.probe_out, b_probe_out_.ptr, (size_t)n * a.n_probes * 2 * sizeof(double),
+                                cudaMemcpyDeviceToHost, stream_));
   LearnCtl lc_h;
   uint32_t xdone_h[2] = {0, 0};
   SNN_CUDA_OK(cudaMemcpyAsync(&lc_h, p.lc, sizeof(lc_h), cudaMemcpyDeviceToHost, stream_));

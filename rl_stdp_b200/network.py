@@ -106,11 +106,12 @@ class SparseNetwork:
 
     # -- step!(net[, input_spikes], train) for a whole window
     def run(self, n_steps, noise=None, train=None, da_events=None, force=None, record=True,
-            spikes_cap=None, profile=False, currents=None):
+            spikes_cap=None, profile=False, currents=None, probes=None):
         """Runs n_steps milliseconds on the device.  noise: [n_steps, n_neurons] float64 or None;
         train: bool array [n_steps] (learn! after that step); da_events: [(step, instance,
         amount)]; force: [(step, neuron)]; currents: [(step, neuron, current)] (injected-current
-        input!).  Returns (list of ascending spike-id arrays, stats)."""
+        input!); probes: synapse indices (caller's CSR order) whose (w, sd) is recorded after every step
+        into self.last_probes [n_steps, n_probes, 2].  Returns (list of ascending spike-id arrays, stats)."""
         lib = L.load()
         n_steps = int(n_steps)
         if noise is not None:
@@ -137,9 +138,14 @@ class SparseNetwork:
         st = L.SnnStepStats()
         # profile: False | 'kernels' (events around every kernel class, serial launches) | 'learn'
         lib.snn_set_profiling(self._h, {False: 0, None: 0, True: 1, 'kernels': 1, 'learn': 2}[profile])
-        if currents:
+        probe_idx = probe_out = None
+        if probes is not None and len(probes):
+            probe_idx = np.ascontiguousarray(probes, np.int64)
+            probe_out = np.zeros((n_steps, len(probe_idx), 2), np.float64)
+        if currents or probe_idx is not None:
+            currents = currents or []
             n_cur = len(currents)
-            ce = (L.SnnCurrentEvent * n_cur)(*[L.SnnCurrentEvent(int(s_), int(j), float(c)) for s_, j, c in currents])
+            ce = (L.SnnCurrentEvent * max(1, n_cur))(*[L.SnnCurrentEvent(int(s_), int(j), float(c)) for s_, j, c in currents])
             io = L.SnnStepIO()
             io.struct_size = C.sizeof(L.SnnStepIO)
             io.n_steps = n_steps
@@ -147,12 +153,14 @@ class SparseNetwork:
             io.train_flags = None if tf is None else tf.ctypes.data
             io.force = C.cast(fe, C.c_void_p) if fe is not None else None
             io.da = C.cast(ev, C.c_void_p) if ev is not None else None
-            io.currents = C.cast(ce, C.c_void_p)
+            io.currents = C.cast(ce, C.c_void_p) if n_cur else None
             io.n_force, io.n_da, io.n_currents = n_force, n_da, n_cur
             io.spikes_out = None if out is None else out.ctypes.data
             io.spike_offsets = None if offs is None else offs.ctypes.data
             io.spikes_cap = cap
             io.stats = C.pointer(st)
+            if probe_idx is not None:
+                io.probe_syn, io.probe_out, io.n_probes = probe_idx.ctypes.data, probe_out.ctypes.data, len(probe_idx)
             rc = lib.snn_step_ex(self._h, C.byref(io))
         else:
             rc = lib.snn_step(self._h, n_steps, _ptr(noise), _ptr(tf), fe, n_force, ev, n_da, _ptr(out), _ptr(offs),
@@ -163,6 +171,8 @@ class SparseNetwork:
         spikes = None
         if record:
             spikes = [out[offs[k]:offs[k + 1]].copy() for k in range(n_steps)]
+        if probe_out is not None:
+            self.last_probes = probe_out  # [n_steps, n_probes, (w, sd)] after every step
         return spikes, stats
 
     def get(self, field) -> np.ndarray:

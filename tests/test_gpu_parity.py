@@ -62,7 +62,7 @@ def test_c1_variant_a_fp64_exact_1000ms():
     assert stats.n_syn_events == int(sum(fan[r].sum() for r in ref))
 
 
-@pytest.mark.parametrize("dmax", [1, 5, 20])
+@pytest.mark.parametrize("dmax", [1, 5, 20, 63])  # 63 = the largest delay the packed incoming index holds
 def test_sparse_delays_fp64_exact(dmax):
     """CSR + axonal delays (the generalisation) against the sparse oracle, with learning,
     dopamine events and forced spikes."""
@@ -479,3 +479,40 @@ def test_full_size_c5_properties():
     wg = net.get(L.FIELD_W)
     assert np.array_equal(wg[ne * fan:], w[ne * fan:])
     assert wg[:ne * fan].min() >= 0.0 and wg[:ne * fan].max() <= 4.0 and np.abs(wg[:ne * fan] - 1.0).max() > 1e-4
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_synapse_probes_per_ms(mode):
+    """`shist[time,:] = [s[n1,syn], sd[n1,syn]]` (Julia_DA_STDPv2.jl:91): (w, sd) of chosen synapses after
+    EVERY step of a window, against the oracle stepped ms by ms."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    n, ne, fan, dmax, t = 600, 480, 40, 6, 240
+    rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=91)
+    noise = synth.thalamic_noise(t, n, seed=92, amp=20.0)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    probes = np.array([0, 7, 1234, ne * fan - 1, ne * fan + 5, n * fan - 1], np.int64)  # the last two: inhibitory rows
+    kw = dict(learn_base=0.0) if mode == "fast" else {}
+    ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax, **kw)
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode=mode, max_delay=dmax, **kw)
+    want = np.zeros((t, len(probes), 2))
+    for k in range(t):
+        ora.step(noise[k], bool(train[k]))
+        if k == 100:
+            ora.add_da(0, 0.5)
+        want[k, :, 0] = ora.get(4)[probes]
+        want[k, :, 1] = ora.get(5)[probes]
+    got = []
+    for lo in range(0, t, 120):
+        da = [(100 - lo, 0, 0.5)] if lo <= 100 < lo + 120 else None
+        net.run(120, noise[lo:lo + 120], train[lo:lo + 120], da_events=da, probes=probes)
+        got.append(net.last_probes.copy())
+    got = np.concatenate(got)
+    plastic = probes < ne * fan
+    assert np.abs(got[:, :, 0] - want[:, :, 0]).max() <= 1e-12
+    assert np.abs(got[:, plastic, 1] - want[:, plastic, 1]).max() <= 1e-12
+    assert np.abs(want[:, plastic, 1]).max() > 0
+    if mode == "exact":
+        assert np.array_equal(got[:, :, 0], want[:, :, 0]) and np.array_equal(got[:, plastic, 1], want[:, plastic, 1])
+        assert np.abs(want[:, plastic, 0] - 1.0).max() > 1e-4  # the probed weights did learn
