@@ -981,14 +981,16 @@ learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int do
 //   learn_ctl(begin)  : g[b] from da as decayed by step k, flip cur, frontier = 0, new epoch
 //   learn_pass        : blocks take 32K-synapse tiles in ascending order: wsdX[cur] =
 //                       learn(wsdX[cur^1]); a finished tile is flagged and the frontier (the
-//                       contiguous prefix of finished tiles) advanced with a CAS on `state`
+//                       contiguous prefix of finished tiles) advanced with one atomicMax on `state`
 //   learn_ctl(all)    : frontier = all
 //   learn_replay      : (before the next begin / at the window end) sd[e] += logged deltas
 // Readers (w_fetch/w_resolve, sd_add) never wait: an unprocessed synapse's post-learn weight is
 // formed on the fly from the frozen buffer, its sd updates are logged.
 // ---------------------------------------------------------------------------------------------
-// <= 64 registers: two resident blocks must leave half of the SM's register file to the step kernels
-// (at 128 registers two blocks owned the whole file and nothing ran beside the pass)
+// learn_pass_kernel: the register-staged (LSU) version of the pass, kept as the A/B alternative of
+// learn_pass_tma_kernel (snn_config.reserved[1] & 512).  <= 64 registers: two resident blocks must
+// leave half of the SM's register file to the step kernels (at 128 registers two blocks owned the
+// whole file and nothing ran beside the pass).
 template <typename T>
 __global__ void __launch_bounds__(256, 4)
 learn_pass_kernel(DevNet<T> p, int32_t k, int do_decay) {
@@ -1017,8 +1019,9 @@ learn_pass_kernel(DevNet<T> p, int32_t k, int do_decay) {
     bool done = false;
     if constexpr (sizeof(T) == 4) {
       // whole tile inside one instance's plastic range: 16-byte accesses, 8 in flight per thread.
-      // The blocks run in lockstep through tiles that are TS*8 bytes apart; starting every tile at
-      // its own offset keeps them from all hitting the same HBM channels at the same time.
+      // Every tile starts at its own offset (the blocks walk tiles that are TS*8 bytes apart in
+      // lockstep).  Measured neutral — the slowness this was written against was the per-tile CAS
+      // chain of the frontier, see learn_pass_tma_kernel — kept because it costs nothing.
       if (p.plastic_ei && b < p.B && (int64_t)p.inst_lo[b] <= a && (int64_t)p.inst_hi[b] >= z) {
         const float4* __restrict__ qs = reinterpret_cast<const float4*>(src + a);
         float4* __restrict__ qd = reinterpret_cast<float4*>(dst + a);
