@@ -14,7 +14,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_build", "libsnn_oracle.so")
+# ORACLE_OMP=1 (set before the first use) loads the OpenMP build: same sources, same results, the
+# independent loops of the sparse step split over the host cores (bench.py --impl reference)
+_OMP = os.environ.get("ORACLE_OMP", "") == "1"
+_SO = os.path.join(_HERE, "_build", "libsnn_oracle_omp.so" if _OMP else "libsnn_oracle.so")
 
 # order of the double[] parameter block of ora_sparse_create
 PARAM_ORDER = [
@@ -41,10 +44,20 @@ CARTPOLE_CFGLIF = dict(
 
 
 def build(force: bool = False) -> str:
+    global _SO, _OMP
     srcs = [os.path.join(_HERE, f) for f in ("snn_oracle.c", "lif_oracle.c")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
+    if _OMP and not os.path.exists(_SO):  # no OpenMP toolchain on this host: the serial build
+        _OMP = False
+        _SO = os.path.join(_HERE, "_build", "libsnn_oracle.so")
     return _SO
+
+
+def omp_threads() -> int:
+    """Threads the loaded oracle library uses for ora_sparse_step (1 for the serial build)."""
+    lib()
+    return (os.cpu_count() or 1) if _OMP else 1
 
 
 _lib = None

@@ -329,13 +329,17 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
   uint8_t* sp = o->spk + (size_t)slot * N;
   int64_t k = 0;
   for (int64_t q = 0; q < n_force; ++q) o->v[force[q]] = 40.0; /* input! new_net.jl:104-106 */
+  /* the OpenMP build (libsnn_oracle_omp.so, bench.py --impl reference) splits the loops whose
+   * iterations are independent; every per-neuron / per-synapse expression is evaluated by one
+   * thread in the same order, so its results are bit-identical to the serial build */
+  #pragma omp parallel for schedule(static)
   for (int64_t j = 0; j < N; ++j) {
     o->I[j] = noise ? noise[j] : 0.0;
     double x = o->v[j] - o->ho[j];
     int s = o->threshold_ge ? (x >= o->vthresh) : (x > o->vthresh);
     sp[j] = (uint8_t)s;
-    if (s) spiked[k++] = (int32_t)j;
   }
+  for (int64_t j = 0; j < N; ++j) if (sp[j]) spiked[k++] = (int32_t)j;
   for (int64_t q = 0; q < k; ++q) {
     int64_t n = spiked[q];
     int64_t l = n % Nper;
@@ -344,8 +348,11 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
     o->u[n] += (l < Ne) ? o->d_exc : o->d_inh;
   }
   /* traces: set for this call's spikers, decayed copy of the previous call otherwise */
+  #pragma omp parallel for schedule(static)
   for (int64_t j = 0; j < N; ++j) tr[j] = sp[j] ? o->trace_set : (t == 0 ? 0.0 : trp[j] * o->trace_decay);
   /* arrivals, pull order */
+  int64_t n_ev = 0, n_ltp = 0;
+  #pragma omp parallel for schedule(dynamic, 256) reduction(+ : n_ev)
   for (int64_t j = 0; j < N; ++j) {
     double acc = o->I[j];
     const int64_t c0 = o->colptr[j], c1 = o->colptr[j + 1];
@@ -354,10 +361,12 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
       int64_t e = o->in_syn[q];
       int64_t ts = t - (o->delay[e] - 1);
       if (ts < 0) continue;
-      if (o->spk[(size_t)(ts % R) * N + o->pre[e]]) { acc += o->w[e]; o->n_syn_events++; }
+      if (o->spk[(size_t)(ts % R) * N + o->pre[e]]) { acc += o->w[e]; n_ev++; }
     }
     o->I[j] = acc;
   }
+  o->n_syn_events += n_ev;
+  #pragma omp parallel for schedule(static)
   for (int64_t j = 0; j < N; ++j) {
     double v = o->v[j], u = o->u[j], I = o->I[j];
     v = v + 0.5 * ((0.04 * v + 5) * v + 140 - u + I);
@@ -367,13 +376,14 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
     o->v[j] = v; o->u[j] = u;
   }
   /* STDP on plastic synapses */
+  #pragma omp parallel for schedule(static) reduction(+ : n_ltp)
   for (int64_t e = 0; e < o->E; ++e) {
     if (!o->plastic[e]) continue;
     int64_t i = o->pre[e], j = o->post[e];
     int64_t ts = t - (o->delay[e] - 1);
     int ltd = ts >= 0 && o->spk[(size_t)(ts % R) * N + i];
     int ltp = sp[j];
-    if (ltp) o->n_ltp_events++;
+    if (ltp) n_ltp++;
     if (!ltd && !ltp) continue;
     int64_t tsp = o->variant_g ? ts - 1 : ts; /* DASTDP.jl:65 STDP[pre_neurons,msec]: before this ms's spikes */
     double pre_tr = tsp >= 0 ? o->trace[(size_t)(tsp % R) * N + i] : 0.0;
@@ -385,11 +395,15 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
     else x = x - dn;
     o->sd[e] = x;
   }
+  o->n_ltp_events += n_ltp;
   for (int64_t b = 0; b < N / Nper; ++b) o->da[b] *= o->da_decay;
   for (int64_t j = 0; j < N; ++j) o->ho[j] *= o->ttheta; /* net_res.jl:204 */
-  if (o->sd_decay_mode == 1)
+  if (o->sd_decay_mode == 1) {
+    #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < o->E; ++e) if (o->plastic[e]) o->sd[e] *= o->sd_decay;
+  }
   if (train) {
+    #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < o->E; ++e) {
       if (!o->plastic[e]) continue;
       double da = o->da[o->pre[e] / Nper];
