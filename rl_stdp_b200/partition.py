@@ -176,13 +176,14 @@ def connect_local(nets):
         connect(n, r, blobs)
 
 
-def connect_dist(net, group=None):
-    """One process per GPU: all-gather the CUDA IPC blobs with torch.distributed, connect, barrier."""
+def connect_dist(net, group=None, _export=None, _connect=None):
+    """One process per GPU: all-gather the CUDA IPC blobs with torch.distributed, connect, barrier.
+    (`_export` / `_connect` replace the library calls in the CPU test of this host logic.)"""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     blobs = [None] * world
-    dist.all_gather_object(blobs, export_blob(net), group=group)
-    connect(net, rank, blobs)
+    dist.all_gather_object(blobs, (_export or export_blob)(net), group=group)
+    (_connect or connect)(net, rank, blobs)
     dist.barrier(group)  # nobody steps before every rank has mapped its peers
 
 

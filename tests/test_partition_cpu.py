@@ -60,6 +60,12 @@ def _gloo_worker(rank, world, port, q):
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     ok = ok and mx[0].item() == 10.0 + world - 1 and sm[1].item() == 100.0 * world * (world + 1) / 2
+    # the peer-exchange set-up (connect_dist): every rank must receive all blobs in rank order
+    from rl_stdp_b200.partition import connect_dist
+    got = {}
+    connect_dist(object(), _export=lambda net: bytes([rank]) * 192,
+                 _connect=lambda net, r, blobs: got.update(rank=r, blobs=blobs))
+    ok = ok and got["rank"] == rank and got["blobs"] == [bytes([r]) * 192 for r in range(world)]
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
