@@ -109,6 +109,7 @@ struct LearnCtl {
   uint32_t epoch;      // pass counter: tile_done[t] == epoch <=> tile t of the pass in flight is written
   uint32_t next_tile;  // tile dispenser of the persistent pass kernel
   uint32_t spilled;    // some sd update went to the dense spill (a log region was full)
+  uint32_t ticket;     // block counter of learn_replay_kernel (its last block begins the next pass)
 };
 constexpr uint32_t kFrontAll = 0x7fffffffu;
 constexpr uint32_t kTileSyn = 32768;   // default synapses per tile of the learn pass (multiple of 1024)
@@ -1274,26 +1275,29 @@ learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
 }
 
 enum { kCtlBegin = 0, kCtlAll = 1 };
+// begin of a pass, by one block: g[b] from da as decayed by step k, flip cur, frontier = 0, new epoch
+template <typename T>
+__device__ __forceinline__ void learn_begin(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
+  const uint32_t st = p.lc->state;
+  const int64_t t = cx->t0 + k;
+  for (int b = threadIdx.x; b < p.B; b += blockDim.x) p.lg[b] = learn_rate<T>(p, p.da[(size_t)((t + 1) & 1) * p.B + b]);
+  if (threadIdx.x == 0) {
+    p.lc->state = ((st >> 31) ^ 1u) << 31;
+    p.lc->epoch += 1u;
+    p.lc->next_tile = 0u;
+    p.lc->spilled = 0u;  // the replay before this has merged the spill
+  }
+}
 template <typename T>
 __global__ void learn_ctl_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int mode) {
-  const uint32_t st = p.lc->state;
-  if (mode == kCtlBegin) {
-    const int64_t t = cx->t0 + k;
-    for (int b = threadIdx.x; b < p.B; b += blockDim.x) p.lg[b] = learn_rate<T>(p, p.da[(size_t)((t + 1) & 1) * p.B + b]);
-    if (threadIdx.x == 0) {
-      p.lc->state = ((st >> 31) ^ 1u) << 31;
-      p.lc->epoch += 1u;
-      p.lc->next_tile = 0u;
-      p.lc->spilled = 0u;  // the replay before this kernel has merged the spill
-    }
-  } else if (threadIdx.x == 0) {
-    p.lc->state = (st & 0x80000000u) | kFrontAll;
-  }
+  if (mode == kCtlBegin) learn_begin<T>(p, cx, k);
+  else if (threadIdx.x == 0) p.lc->state = (p.lc->state & 0x80000000u) | kFrontAll;
 }
 
 // one block per log region (block-stride); empties the regions it replays
 template <typename T>
-__global__ void __launch_bounds__(256) learn_replay_kernel(DevNet<T> p) {
+__global__ void __launch_bounds__(256)
+learn_replay_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int begin_next) {
   typename DevNet<T>::T2* w = p.wsdX[p.lc->state >> 31];
   for (uint32_t r = blockIdx.x; r < p.log_regions; r += gridDim.x) {
     const uint32_t cnt = p.log_cnt[(size_t)r * kLogStride];
@@ -1311,6 +1315,19 @@ __global__ void __launch_bounds__(256) learn_replay_kernel(DevNet<T> p) {
     for (int64_t e = tid; e < p.E; e += nth) {
       const T d = p.dsd[e];
       if (d != (T)0) { atomicAdd(&w[e].y, d); p.dsd[e] = (T)0; }
+    }
+  }
+  if (begin_next) {
+    // the last block to finish begins the next pass: one node less on the learn step's critical path
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&p.lc->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      learn_begin<T>(p, cx, k);
+      if (threadIdx.x == 0) p.lc->ticket = 0u;
     }
   }
 }
@@ -1437,7 +1454,7 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMalloc(&p.lg, (size_t)p.B * sizeof(T)));
     SNN_CUDA_OK(cudaMemsetAsync(p.lg, 0, (size_t)p.B * sizeof(T), stream_));
     {
-      LearnCtl lc0; lc0.state = kFrontAll; lc0.epoch = 0; lc0.next_tile = 0; lc0.spilled = 0;
+      LearnCtl lc0; lc0.state = kFrontAll; lc0.epoch = 0; lc0.next_tile = 0; lc0.spilled = 0; lc0.ticket = 0;
       SNN_CUDA_OK(cudaMemcpyAsync(p.lc, &lc0, sizeof(lc0), cudaMemcpyHostToDevice, stream_));
       SNN_CUDA_OK(cudaStreamSynchronize(stream_));
     }
@@ -1490,7 +1507,7 @@ class Engine : public IEngine {
     p.wsd = p.wsdX[0]; p.wsdX[1] = p.wsdX[0];
     cur_ = 0;
     {
-      LearnCtl lc0; lc0.state = kFrontAll; lc0.epoch = 0; lc0.next_tile = 0; lc0.spilled = 0;
+      LearnCtl lc0; lc0.state = kFrontAll; lc0.epoch = 0; lc0.next_tile = 0; lc0.spilled = 0; lc0.ticket = 0;
       SNN_CUDA_OK(cudaMemcpyAsync(p.lc, &lc0, sizeof(lc0), cudaMemcpyHostToDevice, stream_));
     }
     // plastic synapse range of every instance (exc rows are contiguous in the internal order)
@@ -2083,8 +2100,8 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
         // s4: [previous pass, stream order] -> replay its log -> begin -> pass -> frontier = all
         cudaStreamWaitEvent(s4, evS(k), 0);
         cudaStreamWaitEvent(s4, evP(k), 0);
-        if (pass_open) { learn_replay_kernel<T><<<n_sm_ * 2, 256, 0, s4>>>(p); ++last_pass_launches_; }
-        learn_ctl_kernel<T><<<1, 256, 0, s4>>>(p, d_ctx_, k, kCtlBegin);
+        if (pass_open) learn_replay_kernel<T><<<n_sm_ * 2, 256, 0, s4>>>(p, d_ctx_, k, 1);  // replay + begin
+        else learn_ctl_kernel<T><<<1, 256, 0, s4>>>(p, d_ctx_, k, kCtlBegin);
         ++last_pass_launches_;
         cudaEventRecord(evL, s4);
         launch_pass(s4, k, dd, prof);
@@ -2127,7 +2144,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
       // the pass still in flight ends with the window: replay its log onto the post-learn sd
       cudaStreamWaitEvent(s4, evS(n), 0);
       if (s3_used) cudaStreamWaitEvent(s4, evP(n), 0);
-      learn_replay_kernel<T><<<n_sm_ * 2, 256, 0, s4>>>(p);
+      learn_replay_kernel<T><<<n_sm_ * 2, 256, 0, s4>>>(p, d_ctx_, n, 0);
       learn_spill_reset_kernel<T><<<1, 1, 0, s4>>>(p);
       last_pass_launches_ += 2;
       cudaEventRecord(evFin, s4);
