@@ -5,11 +5,17 @@
  * (Izhikevich layered: input! :135-137,:316-326, spike! :328-379), plus the CartPole decision
  * loop of Julia/Actors/cartpole_fitness.jl:14-114 and a restated CartPole-v1.
  *
- * TEST INFRASTRUCTURE ONLY (see snn_oracle.c header).  PARITY UNPINNED BY THE REFERENCE: no
- * golden vectors exist upstream; pinned against the independent numpy restatement
- * oracle/np_restate.py.  CartPole-v1 physics is NOT in the reference (PyCall -> OpenAI gym,
- * version unpinned, cartpole_fitness.jl:3-4,52,99): restated from the public classic-control
- * definition and labelled as such.
+ * TEST INFRASTRUCTURE ONLY (see snn_oracle.c header).  The reference has no tests or golden
+ * vectors; what it does ship is results.  Variant F with train = false (LIF step, encoder,
+ * read-out, decision loop, CartPole) is PINNED by ten known answers: the sNES elites saved in
+ * Actors/cartpoleElites/sNESelites_cartpole_1.jld each carry fitness 200.0 from gym's seed-0
+ * reset state, and ora_play_episode reproduces all ten (200 decisions, no tie;
+ * tests/test_oracle_cpu.py::test_reference_elites_known_answers).  The answers are saturated
+ * (the episode cap), so the pin is coarse; the learning rules (learn!, learn_critic!) and
+ * variant E stay PARITY UNPINNED BY THE REFERENCE and are checked against the independent
+ * numpy restatement oracle/np_restate.py.  CartPole-v1 physics is NOT in the reference
+ * (PyCall -> OpenAI gym, version unpinned, cartpole_fitness.jl:3-4,52,99): restated from the
+ * public classic-control definition and labelled as such.
  */
 #include <math.h>
 #include <stdint.h>

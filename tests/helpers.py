@@ -39,3 +39,33 @@ def run_oracle_sparse(ora, noise, train, da_events=(), force=()):
         for i, a in da_by.get(k, ()):
             ora.add_da(i, a)
     return out
+
+
+def gym_seed0_reset_state():
+    """The observation gym's classic CartPole returns from `env.seed(0); env.reset()`
+    (cartpole_fitness.jl:53-62): gym.utils.seeding hashes the seed with SHA-512, keeps 8 bytes, seeds a
+    numpy RandomState with the two little-endian 32-bit words, and CartPoleEnv.reset draws
+    uniform(-0.05, 0.05, 4) from it.  Published value: [-0.04456399, 0.04653909, 0.01326909, -0.02099827]."""
+    import hashlib
+    h = int.from_bytes(hashlib.sha512(b"0").digest()[:8], "little")
+    rs = np.random.RandomState()
+    rs.seed([h % 2**32, h >> 32])
+    s = rs.uniform(-0.05, 0.05, size=(4,))
+    assert np.allclose(s, [-0.04456399, 0.04653909, 0.01326909, -0.02099827], atol=5e-9), s
+    return s
+
+
+def reference_elites():
+    """The ten genomes of Actors/cartpoleElites/sNESelites_cartpole_1.jld decoded as fitness() does
+    (cartpole_fitness.jl:158-176, cartpole_tryout.jl:20-38): [(matalpha 8x4, [e0, e1], saved fitness)]."""
+    import os
+    from rl_stdp_b200 import jld
+    from rl_stdp_b200.lif import borne, set_weight
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sNESelites_cartpole_1.jld")
+    arch = [8, 8, 8]
+    out = []
+    for el in jld.load(path, "elites"):
+        g = np.asarray(el["genes"], np.float64)
+        m = borne(g[:arch[0] * 4], -1.0, 1.0).reshape((4, arch[0])).T   # reshape(genes_alpha, (arch[1], 4))
+        out.append((m, set_weight(arch, g[arch[0] * 4:]), float(np.asarray(el["fitness"]).ravel()[0])))
+    return out

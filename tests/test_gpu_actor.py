@@ -212,3 +212,26 @@ def test_reference_elites_balance_the_pole():
     ma_r = np.array([borne(x[:32], -1.0, 1.0).reshape((4, 8)).T for x in g])
     out_r = rnd.play_episodes(ma_r, state0, ties, n_steps=200)
     assert out_r["rewards"].mean() < 0.5 * rew.mean(), out_r["rewards"].mean()
+
+
+def test_reference_elites_known_answers_on_device():
+    """The reference's saved fitness values (200.0 for each of the ten elites, gym seed-0 start) reproduced
+    by the CUDA actor through snn_actor_episodes, and the final CartPole states bit-equal to the oracle's."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200.lif import ActorPopulation
+    from tests.helpers import gym_seed0_reset_state, reference_elites
+    s0 = gym_seed0_reset_state()
+    el = reference_elites()
+    pop = ActorPopulation([8, 8, 8], len(el))
+    for l in range(2):
+        pop.set_weights(l, np.array([w[l] for _, w, _ in el]))
+    out = pop.play_episodes(np.array([m for m, _, _ in el]), np.tile(s0, (len(el), 1)),
+                            np.zeros((len(el), 200), np.int32), n_steps=200)
+    assert np.array_equal(out["rewards"], [fit for _, _, fit in el])
+    assert np.all(out["n_decisions"] == 200) and np.all(out["n_rand"] == 0)
+    for a, (m, w, _) in enumerate(el):
+        o = po.Layered([8, 8, 8])
+        for l in range(2):
+            o.e(l)[:, :] = w[l]
+        _, _, _, so = o.play_episode(m, s0, np.zeros(200, np.int32))
+        assert np.array_equal(out["state"][a], so), a

@@ -326,3 +326,28 @@ def test_variant_g_restatement_equals_sparse_oracle():
     assert np.array_equal(ora.get(5).reshape(n, m)[:ne], ref.sd[:ne])  # sd of inhibitory rows is dead state
     assert np.array_equal(ora.get(0), ref.v)
     assert np.abs(ref.s[:ne] - 1.0).max() > 1e-3
+
+
+def test_reference_elites_known_answers():
+    """The one place the reference pins this path with its OWN outputs: the ten sNES elites saved in
+    Actors/cartpoleElites/sNESelites_cartpole_1.jld carry `fitness = 200.0`, computed by play_episode
+    (cartpole_fitness.jl:51-114) from gym's seed-0 reset state with the stock cartpole_cfglif.yml — 200
+    decisions survived and not one tie (a tie costs 0.9).  The oracle (LIF step, encoder, read-out,
+    restated CartPole-v1) must reproduce every one of them from that start; from other starts only six or
+    seven of the ten do, and vthresh off by 0.2 mV gives 0.9 for all ten."""
+    from tests.helpers import gym_seed0_reset_state, reference_elites
+    s0 = gym_seed0_reset_state()
+    no_ties = np.zeros(200, np.int32)
+    for m, w, fit in reference_elites():
+        assert fit == 200.0
+        n = po.Layered([8, 8, 8])                      # defaults = Julia/Actors/cartpole_cfglif.yml
+        for l in range(2):
+            n.e(l)[:, :] = w[l]
+        r, nd, nr, _ = n.play_episode(m, s0, no_ties)
+        assert (r, nd, nr) == (fit, 200, 0)
+    # sensitivity: the same elites with the threshold 0.2 mV higher never reach a decision
+    m, w, _ = reference_elites()[0]
+    n = po.Layered([8, 8, 8], vthresh=-68.5)
+    for l in range(2):
+        n.e(l)[:, :] = w[l]
+    assert n.play_episode(m, s0, no_ties)[0] < 10.0
