@@ -7,10 +7,10 @@
  *
  * TEST INFRASTRUCTURE ONLY (see snn_oracle.c header).  The reference has no tests or golden
  * vectors; what it does ship is results.  Variant F with train = false (LIF step, encoder,
- * read-out, decision loop, CartPole) is PINNED by ten known answers: the sNES elites saved in
- * Actors/cartpoleElites/sNESelites_cartpole_1.jld each carry fitness 200.0 from gym's seed-0
- * reset state, and ora_play_episode reproduces all ten (200 decisions, no tie;
- * tests/test_oracle_cpu.py::test_reference_elites_known_answers).  The answers are saturated
+ * read-out, decision loop, CartPole) is PINNED by 60 known answers: the distinct sNES elites
+ * saved in Actors/cartpoleElites/sNESelites_cartpole_{1..17}.jld carry the fitness computed from
+ * gym's seed-0 reset state (59 x 200.0, one 199.1 = one tie), and ora_play_episode reproduces
+ * all 60 (tests/test_oracle_cpu.py::test_reference_elites_known_answers).  59 answers are saturated
  * (the episode cap), so the pin is coarse; the learning rules (learn!, learn_critic!) and
  * variant E stay PARITY UNPINNED BY THE REFERENCE and are checked against the independent
  * numpy restatement oracle/np_restate.py.  CartPole-v1 physics is NOT in the reference

@@ -55,17 +55,22 @@ def gym_seed0_reset_state():
     return s
 
 
-def reference_elites():
-    """The ten genomes of Actors/cartpoleElites/sNESelites_cartpole_1.jld decoded as fitness() does
-    (cartpole_fitness.jl:158-176, cartpole_tryout.jl:20-38): [(matalpha 8x4, [e0, e1], saved fitness)]."""
+def reference_elites(unique=True):
+    """The genomes of Actors/cartpoleElites/sNESelites_cartpole_{1..17}.jld (fixture
+    tests/golden/cartpole_elites.npz, made by tests/golden/make_elites.py: 170 saved individuals, 60
+    distinct) decoded as fitness() does (cartpole_fitness.jl:158-176, cartpole_tryout.jl:20-38):
+    [(matalpha 8x4, [e0, e1], saved fitness)]."""
     import os
-    from rl_stdp_b200 import jld
     from rl_stdp_b200.lif import borne, set_weight
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sNESelites_cartpole_1.jld")
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cartpole_elites.npz"))
+    genes, fit = d["genes"], d["fitness"]
+    if unique:
+        _, first = np.unique(genes, axis=0, return_index=True)
+        first.sort()
+        genes, fit = genes[first], fit[first]
     arch = [8, 8, 8]
     out = []
-    for el in jld.load(path, "elites"):
-        g = np.asarray(el["genes"], np.float64)
+    for g, f in zip(genes, fit):
         m = borne(g[:arch[0] * 4], -1.0, 1.0).reshape((4, arch[0])).T   # reshape(genes_alpha, (arch[1], 4))
-        out.append((m, set_weight(arch, g[arch[0] * 4:]), float(np.asarray(el["fitness"]).ravel()[0])))
+        out.append((m, set_weight(arch, g[arch[0] * 4:]), float(f)))
     return out

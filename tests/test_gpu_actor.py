@@ -215,8 +215,9 @@ def test_reference_elites_balance_the_pole():
 
 
 def test_reference_elites_known_answers_on_device():
-    """The reference's saved fitness values (200.0 for each of the ten elites, gym seed-0 start) reproduced
-    by the CUDA actor through snn_actor_episodes, and the final CartPole states bit-equal to the oracle's."""
+    """The reference's saved fitness values (59 x 200.0 and one 199.1 over the 60 distinct sNES elites, gym
+    seed-0 start; tests/test_oracle_cpu.py::test_reference_elites_known_answers) reproduced by the CUDA actor
+    through snn_actor_episodes, with tie counts and final CartPole states bit-equal to the oracle's."""
     from oracle import py_oracle as po
     from rl_stdp_b200.lif import ActorPopulation
     from tests.helpers import gym_seed0_reset_state, reference_elites
@@ -225,13 +226,15 @@ def test_reference_elites_known_answers_on_device():
     pop = ActorPopulation([8, 8, 8], len(el))
     for l in range(2):
         pop.set_weights(l, np.array([w[l] for _, w, _ in el]))
-    out = pop.play_episodes(np.array([m for m, _, _ in el]), np.tile(s0, (len(el), 1)),
-                            np.zeros((len(el), 200), np.int32), n_steps=200)
-    assert np.array_equal(out["rewards"], [fit for _, _, fit in el])
-    assert np.all(out["n_decisions"] == 200) and np.all(out["n_rand"] == 0)
-    for a, (m, w, _) in enumerate(el):
-        o = po.Layered([8, 8, 8])
-        for l in range(2):
-            o.e(l)[:, :] = w[l]
-        _, _, _, so = o.play_episode(m, s0, np.zeros(200, np.int32))
-        assert np.array_equal(out["state"][a], so), a
+    for tie in (0, 1):
+        out = pop.play_episodes(np.array([m for m, _, _ in el]), np.tile(s0, (len(el), 1)),
+                                np.full((len(el), 200), tie, np.int32), n_steps=200)
+        fit = np.array([f for _, _, f in el])
+        assert np.array_equal(out["rewards"], fit)
+        assert np.all(out["n_decisions"] == 200) and np.array_equal(out["n_rand"], (fit != 200.0).astype(np.int32))
+        for a, (m, w, _) in enumerate(el):
+            o = po.Layered([8, 8, 8])
+            for l in range(2):
+                o.e(l)[:, :] = w[l]
+            _, _, _, so = o.play_episode(m, s0, np.full(200, tie, np.int32))
+            assert np.array_equal(out["state"][a], so), a
