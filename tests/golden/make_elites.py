@@ -5,7 +5,11 @@ Source: Julia/Actors/cartpoleElites/sNESelites_cartpole_{1..17}.jld — `elites`
 each (`genes` 160 x Float64, `fitness` 1 x Float64), written by the sNES runs of Actors/optim.jl and read
 back by Actors/cartpole_tryout.jl:15.  Read with rl_stdp_b200/jld.py (no HDF5 library in the image).
 
-Output: tests/golden/cartpole_elites.npz  genes [170,160] f64, fitness [170] f64, run [170] i32.
+        Julia/Actors/sNESelites_mountcar.jld — ten elites of the MountainCar-v0 runs (mountcar_fitness.jl),
+        fitness -129 ... -117 (minus the decisions needed to reach the flag, ties counted twice).
+
+Output: tests/golden/cartpole_elites.npz  genes [170,160] f64, fitness [170] f64, run [170] i32;
+        tests/golden/mountcar_elites.npz  genes [10,160] f64, fitness [10] f64.
 """
 import glob
 import os
@@ -32,6 +36,11 @@ def main():
     np.savez_compressed(os.path.join(HERE, "cartpole_elites.npz"), genes=np.array(genes), fitness=np.array(fit),
                         run=np.array(run, np.int32))
     print(len(genes), "elites from", len(files), "files; fitness values:", sorted(set(fit)))
+    el = jld.load("/root/reference/Julia/Actors/sNESelites_mountcar.jld", "elites")
+    np.savez_compressed(os.path.join(HERE, "mountcar_elites.npz"),
+                        genes=np.array([np.asarray(e["genes"], np.float64) for e in el]),
+                        fitness=np.array([float(np.ravel(e["fitness"])[0]) for e in el]))
+    print(len(el), "mountain-car elites; fitness:", [float(np.ravel(e["fitness"])[0]) for e in el])
 
 
 if __name__ == "__main__":

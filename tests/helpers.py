@@ -41,16 +41,22 @@ def run_oracle_sparse(ora, noise, train, da_events=(), force=()):
     return out
 
 
+def _gym_np_random(seed):
+    """gym.utils.seeding.np_random of the gym releases that still had env.seed(): hash_seed = first 8 bytes
+    of SHA-512(str(seed)) as a little-endian integer, split into 32-bit words for RandomState.seed."""
+    import hashlib
+    h = int.from_bytes(hashlib.sha512(str(seed).encode()).digest()[:8], "little")
+    rs = np.random.RandomState()
+    rs.seed([h % 2**32, h >> 32])
+    return rs
+
+
 def gym_seed0_reset_state():
     """The observation gym's classic CartPole returns from `env.seed(0); env.reset()`
     (cartpole_fitness.jl:53-62): gym.utils.seeding hashes the seed with SHA-512, keeps 8 bytes, seeds a
     numpy RandomState with the two little-endian 32-bit words, and CartPoleEnv.reset draws
     uniform(-0.05, 0.05, 4) from it.  Published value: [-0.04456399, 0.04653909, 0.01326909, -0.02099827]."""
-    import hashlib
-    h = int.from_bytes(hashlib.sha512(b"0").digest()[:8], "little")
-    rs = np.random.RandomState()
-    rs.seed([h % 2**32, h >> 32])
-    s = rs.uniform(-0.05, 0.05, size=(4,))
+    s = _gym_np_random(0).uniform(-0.05, 0.05, size=(4,))
     assert np.allclose(s, [-0.04456399, 0.04653909, 0.01326909, -0.02099827], atol=5e-9), s
     return s
 
@@ -74,3 +80,52 @@ def reference_elites(unique=True):
         m = borne(g[:arch[0] * 4], -1.0, 1.0).reshape((4, arch[0])).T   # reshape(genes_alpha, (arch[1], 4))
         out.append((m, set_weight(arch, g[arch[0] * 4:]), float(f)))
     return out
+
+
+def mountcar_elites():
+    """Actors/sNESelites_mountcar.jld decoded as mountcar_fitness.jl:158-178 does: matalpha = borne(genes[1:16])
+    reshaped (8, 2); the weights start at gene 33 (`genes[arch[1]*4+1:end]`, genes 17..32 are unused)."""
+    import os
+    from rl_stdp_b200.lif import borne, set_weight
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mountcar_elites.npz"))
+    arch = [8, 8, 8]
+    return [(borne(g[:16], -1.0, 1.0).reshape((2, 8)).T, set_weight(arch, g[32:]), float(f))
+            for g, f in zip(d["genes"], d["fitness"])]
+
+
+def play_mountcar(window_fn, matalpha, tie_bits, n_steps=200):
+    """play_episode of Actors/mountcar_fitness.jl:48-107 for A agents in lock-step, with MountainCar-v0 restated
+    from gym's classic-control definition (NOT in the reference: PyCall -> gym) and gym's seed-0 reset
+    position.  window_fn(intensity [A, 8]) -> last-layer spike counts [A, 8] of one 40-ms decision window
+    (v reset to c first, counted from msec >= length(arch) - 1).  tie_bits = the stream of
+    rand(MersenneTwister(0), pool) picks (tests/julia_rng.py); every episode restarts it.
+    Returns (reward [A], decisions [A], ties [A])."""
+    import math
+    A = len(matalpha)
+    p0 = _gym_np_random(0).uniform(low=-0.6, high=-0.4)
+    pos, vel = np.full(A, p0), np.zeros(A)
+    tot, used, nd = np.zeros(A), np.zeros(A, np.int64), np.zeros(A, np.int64)
+    live = np.ones(A, bool)
+    for _ in range(n_steps):
+        if not live.any():
+            break
+        obs = np.stack([(pos + 1.2) / 1.8, (vel + 0.07) / 0.14], axis=1)          # norm_mountcar :13-20
+        cnt = np.asarray(window_fn(np.einsum("aij,aj->ai", np.asarray(matalpha), obs)), np.float64)
+        for a in np.flatnonzero(live):
+            sl, sm, sr = cnt[a, :2].sum(), cnt[a, 2:4].sum(), cnt[a, 4:].sum()    # div(8,3) = 2, 2, 4
+            act, fac = int(np.argmax([sl, sm, sr])), 1                            # push_or_not :33-39
+            for d, pool in zip((sl - sr, sl - sm, sm - sr), ((1, 3), (1, 2), (2, 3))):   # :84-93
+                if d == 0.0:
+                    act, fac = pool[tie_bits[used[a]]] - 1, 2
+                    used[a] += 1
+            v = vel[a] + (act - 1) * 0.001 + math.cos(3 * pos[a]) * (-0.0025)
+            v = min(max(v, -0.07), 0.07)
+            x = min(max(pos[a] + v, -1.2), 0.6)
+            if x == -1.2 and v < 0:
+                v = 0.0
+            pos[a], vel[a] = x, v
+            tot[a] -= fac
+            nd[a] += 1
+            if x >= 0.5 and v >= 0:
+                live[a] = False
+    return tot, nd, used

@@ -238,3 +238,21 @@ def test_reference_elites_known_answers_on_device():
                 o.e(l)[:, :] = w[l]
             _, _, _, so = o.play_episode(m, s0, np.full(200, tie, np.int32))
             assert np.array_equal(out["state"][a], so), a
+
+
+def test_reference_mountcar_elites_known_answers_on_device():
+    """The ten non-saturated MountainCar answers (tests/test_oracle_cpu.py::
+    test_reference_mountcar_elites_known_answers) with every 40-ms decision window run by the CUDA actor
+    (snn_actor_window); environment, read-out and Julia's tie stream on the host."""
+    from rl_stdp_b200.lif import ActorPopulation
+    from tests.helpers import mountcar_elites, play_mountcar
+    from tests.julia_rng import julia_mt_pick_bits
+    el = mountcar_elites()
+    pop = ActorPopulation([8, 8, 8], len(el))
+    for l in range(2):
+        pop.set_weights(l, np.array([w[l] for _, w, _ in el]))
+    tot, nd, ties = play_mountcar(lambda it: pop.decision_window(it, 40, reset_v=True)[0],
+                                  [m for m, _, _ in el], julia_mt_pick_bits(0, 64))
+    assert tot.tolist() == [f for _, _, f in el]
+    assert nd.tolist() == [121, 122, 118, 126, 111, 113, 121, 118, 117, 116]
+    assert ties.tolist() == [8, 7, 9, 1, 18, 12, 4, 5, 4, 1]

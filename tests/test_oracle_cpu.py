@@ -356,3 +356,50 @@ def test_reference_elites_known_answers():
             assert play(m, w, tie) == (fit, 200, n_ties)
     # sensitivity: with the threshold 5 % higher almost none of the answers survives
     assert sum(play(m, w, 0, vthresh=1.05)[0] == fit for m, w, fit in el) < 10
+
+
+def test_julia_mersenne_twister_restatement():
+    """tests/julia_rng.py against the published head of `rand(MersenneTwister(0), 10)`."""
+    from tests.julia_rng import DSFMT, julia_mt_pick_bits
+    g = DSFMT([0])
+    assert [g.rand() for _ in range(10)] == [
+        0.8236475079774124, 0.9103565379264364, 0.16456579813368521, 0.17732884646626457, 0.278880109331201,
+        0.20347655804192266, 0.042301665932029664, 0.06826925550564478, 0.3618283907762174, 0.9732164043865108]
+    assert julia_mt_pick_bits(0, 10) == [0, 0, 1, 1, 0, 0, 0, 1, 1, 0]
+    g = DSFMT([0])
+    for _ in range(1000):   # crosses two state regenerations
+        assert 0.0 <= g.rand() < 1.0
+
+
+def test_reference_mountcar_elites_known_answers():
+    """Ten NON-saturated known answers: Actors/sNESelites_mountcar.jld stores, for ten genomes, the fitness
+    play_episode (mountcar_fitness.jl:48-107) returned — minus one per decision until the flag is reached,
+    minus two for a decision with a tie, the tie resolved by `rand(MersenneTwister(0), pool)`.  With gym's
+    seed-0 reset position, Julia's tie stream (tests/julia_rng.py) and a restated MountainCar-v0, the oracle's
+    LIF step reproduces all ten, e.g. -129 = 121 decisions with 8 ties."""
+    from tests.helpers import mountcar_elites, play_mountcar
+    from tests.julia_rng import julia_mt_pick_bits
+    el = mountcar_elites()
+    nets = []
+    for _, w, _ in el:
+        n = po.Layered([8, 8, 8])          # mountcar_cfglif.yml == the cartpole defaults
+        for l in range(2):
+            n.e(l)[:, :] = w[l]
+        nets.append(n)
+    idx = np.arange(8, dtype=np.int32)
+
+    def window(intensity):
+        out = np.zeros((len(nets), 8))
+        for a, n in enumerate(nets):
+            n.v[:] = n.params["c"]
+            for ms in range(1, 41):
+                for x in n.step_lif(idx, intensity[a], False):
+                    if ms >= 2 and 16 <= x < 24:
+                        out[a, x - 16] += 1
+        return out
+
+    tot, nd, ties = play_mountcar(window, [m for m, _, _ in el], julia_mt_pick_bits(0, 64))
+    assert tot.tolist() == [f for _, _, f in el] == [-129.0, -129.0, -127.0, -127.0, -127.0, -125.0, -125.0,
+                                                     -123.0, -121.0, -117.0]
+    assert nd.tolist() == [121, 122, 118, 126, 111, 113, 121, 118, 117, 116]
+    assert ties.tolist() == [8, 7, 9, 1, 18, 12, 4, 5, 4, 1]
