@@ -11,7 +11,10 @@
  * saved in Actors/cartpoleElites/sNESelites_cartpole_{1..17}.jld carry the fitness computed from
  * gym's seed-0 reset state (59 x 200.0, one 199.1 = one tie), and ora_play_episode reproduces
  * all 60 (tests/test_oracle_cpu.py::test_reference_elites_known_answers; a 2 % change of vthresh
- * or 4 % of taulif leaves fewer than 10 of the 60).  The learning rules
+ * or 4 % of taulif leaves fewer than 10 of the 60), plus ten NON-saturated
+ * answers: the MountainCar elites of Actors/sNESelites_mountcar.jld (-129 ... -117), reproduced by
+ * ora_lay_step_lif with Julia's MersenneTwister(0) tie stream restated in tests/julia_rng.py.  The
+ * learning rules
  * (learn!, learn_critic!) and variant E stay PARITY UNPINNED BY THE REFERENCE and are checked against the independent
  * numpy restatement oracle/np_restate.py.  CartPole-v1 physics is NOT in the reference
  * (PyCall -> OpenAI gym, version unpinned, cartpole_fitness.jl:3-4,52,99): restated from the

@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and ben
 cpu_baseline / --impl reference legs, never by the product package rl_stdp_b200/.
 The oracle is a restatement of the Julia reference (file:line cited in the C sources), not the
 Julia binary: "parity unpinned" by the reference's own tests (it has none) — except the LIF actor
-episode path, which reproduces the fitness values the reference saved with its 60 distinct sNES elites
+episode path, which reproduces the fitness values the reference saved with its sNES elites (60 CartPole genomes, 10 MountainCar genomes)
 (tests/test_oracle_cpu.py::test_reference_elites_known_answers).
 """
 from __future__ import annotations

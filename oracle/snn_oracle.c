@@ -9,7 +9,7 @@
  * fixtures for this path, and Julia is not installed here, so this restatement cannot be pinned
  * against reference outputs.  It is pinned against an INDEPENDENT numpy restatement written
  * from the same cited lines (oracle/np_restate.py, fixtures under tests/golden/).  (The LIF actor
- * of lif_oracle.c is the exception: 60 saved results of the reference pin it, see there.)
+ * of lif_oracle.c is the exception: 70 saved results of the reference pin it, see there.)
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math (Julia/LLVM never contracts a*b+c without
  * @fastmath/muladd, neither is used by the reference), see oracle/Makefile.
