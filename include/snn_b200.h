@@ -342,6 +342,23 @@ int32_t snn_actor_episodes(snn_actor* a, const double* matalpha, const double* s
                            double* rewards, int32_t* n_decisions, int32_t* n_rand, double* state_out,
                            double* device_ms);
 
+/* The same decision loop with a selectable restated environment (no teacher signal).
+ *   SNN_ENV_CARTPOLE     exactly snn_actor_episodes (matalpha arch[1] x 4).
+ *   SNN_ENV_MOUNTAINCAR  play_episode of Actors/mountcar_fitness.jl:48-107: matalpha
+ *                        [n_agents][arch[1]*2] column-major over norm_mountcar(obs) (:13-20); state0
+ *                        [n_agents][4] = (position, velocity, -, -); three output pools of div(n,3),
+ *                        div(n,3) and the remaining neurons, action = argmax - 1 (:33-39, :77-80);
+ *                        every tied pair of pools draws `rand(rng_action, pool)` (:83-93) and the
+ *                        decision then costs 2 instead of 1.
+ * tie_picks [n_agents][tie_stride]: the replayed draw stream as 0-based indices into the
+ * two-element pool (CartPole: the action itself); a MountainCar decision can consume three. */
+#define SNN_ENV_CARTPOLE 0
+#define SNN_ENV_MOUNTAINCAR 1
+int32_t snn_actor_episodes_env(snn_actor* a, int32_t env, const double* matalpha, const double* state0,
+                               const int32_t* tie_picks, int32_t tie_stride, int32_t n_decisions_max, int32_t win_size,
+                               int32_t train, double* rewards, int32_t* n_decisions, int32_t* n_rand,
+                               double* state_out, double* device_ms);
+
 #ifdef __cplusplus
 }
 #endif

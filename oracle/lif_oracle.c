@@ -13,10 +13,10 @@
  * all 60 (tests/test_oracle_cpu.py::test_reference_elites_known_answers; a 2 % change of vthresh
  * or 4 % of taulif leaves fewer than 10 of the 60), plus ten NON-saturated
  * answers: the MountainCar elites of Actors/sNESelites_mountcar.jld (-129 ... -117), reproduced by
- * ora_lay_step_lif with Julia's MersenneTwister(0) tie stream restated in tests/julia_rng.py.  The
- * learning rules
- * (learn!, learn_critic!) and variant E stay PARITY UNPINNED BY THE REFERENCE and are checked against the independent
- * numpy restatement oracle/np_restate.py.  CartPole-v1 physics is NOT in the reference
+ * ora_lay_step_lif with Julia's MersenneTwister(0) tie stream restated in rl_stdp_b200/julia_rng.py.  The
+ * learning rules (learn!, learn_critic!) and variant E stay PARITY UNPINNED BY THE REFERENCE and
+ * are checked against the independent numpy restatement oracle/np_restate.py.  CartPole-v1 and
+ * MountainCar-v0 physics are NOT in the reference
  * (PyCall -> OpenAI gym, version unpinned, cartpole_fitness.jl:3-4,52,99): restated from the
  * public classic-control definition and labelled as such.
  */
@@ -336,5 +336,91 @@ double ora_play_episode(ora_lay* o, const double* matalpha, const double state0[
   if (n_dec_out) *n_dec_out = n_tot;
   if (n_rand_out) *n_rand_out = n_rand;
   if (state_out) for (int q = 0; q < 4; ++q) state_out[q] = st[q];
+  return tot_reward;
+}
+
+/* ---- MountainCar-v0, restated (NOT in the reference: PyCall -> gym classic_control/mountain_car.py).
+ * cos(3*position) needs an argument reduction (|3*position| <= 3.6): Cody-Waite with the two leading
+ * parts of pi/2 (fdlibm's pio2_1, pio2_1t) and the kernel polynomials above, in plain IEEE operations so
+ * the device reproduces it bit for bit (within ~1 ulp of libm; the reference's ten saved MountainCar
+ * results are reproduced with it, tests/test_oracle_cpu.py). */
+double ora_cos_reduced(double x) {
+  const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00,
+               pio2_1t = 6.07710050650619224932e-11;
+  double fn = rint(x * invpio2);
+  double y = (x - fn * pio2_1) - fn * pio2_1t;
+  switch (((int)fn) & 3) {
+    case 0: return k_cos(y);
+    case 1: return -k_sin(y);
+    case 2: return -k_cos(y);
+    default: return k_sin(y);
+  }
+}
+/* st = (position, velocity); action 0 push left, 1 none, 2 push right; returns done */
+int ora_mountcar_step(double st[2], int action) {
+  const double min_position = -1.2, max_position = 0.6, max_speed = 0.07, goal_position = 0.5, force = 0.001,
+               gravity = 0.0025;
+  double position = st[0], velocity = st[1];
+  velocity = velocity + ((double)(action - 1) * force + ora_cos_reduced(3 * position) * (-gravity));
+  velocity = velocity < -max_speed ? -max_speed : (velocity > max_speed ? max_speed : velocity);
+  position = position + velocity;
+  position = position < min_position ? min_position : (position > max_position ? max_position : position);
+  if (position == min_position && velocity < 0) velocity = 0;
+  st[0] = position; st[1] = velocity;
+  return position >= goal_position && velocity >= 0;
+}
+
+/* play_episode of Actors/mountcar_fitness.jl:48-107.  matalpha: arch[0] x 2 column-major; state0 =
+ * (position, velocity) of env.reset(); tie_picks: replayed stream of the `rand(rng_action, pool)` draws
+ * (:88) as 0-based indices into the two-element pool, n_picks entries (0 is used beyond). */
+double ora_play_episode_mountcar(ora_lay* o, const double* matalpha, const double state0[2],
+                                 const int32_t* tie_picks, int n_picks, int n_steps, int train,
+                                 int32_t* n_dec_out, int32_t* n_rand_out, double* state_out) {
+  const int win_size = 40;
+  double tot_reward = 0;
+  double st[2] = {state0[0], state0[1]};
+  int32_t idx[64]; double inten[64]; int32_t spiked[1024];
+  int n_rand = 0, n_tot = 0;
+  const int A0 = o->arch[0], Lout = o->arch[o->L - 1];
+  for (int j = 0; j < n_steps; ++j) {
+    double on[2] = {(st[0] + 1.2) / 1.8, (st[1] + 0.07) / 0.14}; /* norm_mountcar :13-20 */
+    for (int r = 0; r < A0; ++r) {
+      double a = 0.0;
+      for (int c = 0; c < 2; ++c) a += matalpha[r + A0 * c] * on[c];
+      idx[r] = r; inten[r] = a;
+    }
+    double count_tot[64] = {0};
+    for (int q = 0; q < o->n; ++q) o->v[q] = o->c; /* :66 */
+    for (int msec = 1; msec <= win_size; ++msec) {
+      int k = ora_lay_step_lif(o, idx, inten, A0, train, 0, spiked);
+      if (msec >= o->L - 1) /* :71 */
+        for (int q = 0; q < k; ++q) {
+          int n = spiked[q];
+          if (n >= o->off[o->L - 1] && n < o->off[o->L]) count_tot[n - o->off[o->L - 1]] += 1;
+        }
+    }
+    const int n_left = Lout / 3; /* :77-79: left, middle = div(n,3), right = the rest */
+    double s3[3] = {0, 0, 0};
+    for (int q = 0; q < Lout; ++q) s3[q < n_left ? 0 : (q < 2 * n_left ? 1 : 2)] += count_tot[q];
+    int action = 0; /* argmax([sl,sm,sr]) - 1: the first maximum :37 */
+    if (s3[1] > s3[action]) action = 1;
+    if (s3[2] > s3[action]) action = 2;
+    double fac_reward = 1; /* :83-93: every tied pair draws, the last draw wins */
+    const double difs[3] = {s3[0] - s3[2], s3[0] - s3[1], s3[1] - s3[2]};
+    const int pools[3][2] = {{0, 2}, {0, 1}, {1, 2}};
+    for (int i = 0; i < 3; ++i)
+      if (difs[i] == 0.0) {
+        action = pools[i][n_rand < n_picks ? tie_picks[n_rand] : 0];
+        fac_reward = 2;
+        n_rand++;
+      }
+    n_tot++;
+    int done = ora_mountcar_step(st, action);
+    tot_reward += -1.0 * fac_reward; /* :98 */
+    if (done) break;
+  }
+  if (n_dec_out) *n_dec_out = n_tot;
+  if (n_rand_out) *n_rand_out = n_rand;
+  if (state_out) { state_out[0] = st[0]; state_out[1] = st[1]; }
   return tot_reward;
 }

@@ -111,6 +111,12 @@ def lib() -> C.CDLL:
         L.ora_play_episode.argtypes = [vp, vp, vp, vp, vp, dbl, C.c_int, C.c_int, vp, vp, vp]
         L.ora_ksin.restype = dbl
         L.ora_ksin.argtypes = [dbl]
+        L.ora_cos_reduced.restype = dbl
+        L.ora_cos_reduced.argtypes = [dbl]
+        L.ora_mountcar_step.restype = C.c_int
+        L.ora_mountcar_step.argtypes = [vp, C.c_int]
+        L.ora_play_episode_mountcar.restype = dbl
+        L.ora_play_episode_mountcar.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         L.ora_kcos.restype = dbl
         L.ora_kcos.argtypes = [dbl]
         _lib = L
@@ -292,6 +298,26 @@ class Layered:
         r = lib().ora_play_episode(self._h, _p(ma), _p(s0), _p(ta), _p(te), float(da_inc), int(n_steps), int(train),
                                    C.byref(nd), C.byref(nr), _p(so))
         return float(r), nd.value, nr.value, so
+
+    def play_episode_mountcar(self, matalpha, state0, tie_picks, n_steps=200, train=False):
+        ma = np.asfortranarray(matalpha, np.float64)
+        s0 = np.ascontiguousarray(state0, np.float64)
+        tp = np.ascontiguousarray(tie_picks, np.int32)
+        nd, nr = C.c_int32(0), C.c_int32(0)
+        so = np.zeros(2, np.float64)
+        r = lib().ora_play_episode_mountcar(self._h, _p(ma), _p(s0), _p(tp), len(tp), int(n_steps), int(train),
+                                            C.byref(nd), C.byref(nr), _p(so))
+        return float(r), nd.value, nr.value, so
+
+
+def cos_reduced(x):
+    return float(lib().ora_cos_reduced(float(x)))
+
+
+def mountcar_step(state, action):
+    s = np.ascontiguousarray(state, np.float64).copy()
+    done = lib().ora_mountcar_step(_p(s), int(action))
+    return s, bool(done)
 
 
 def cartpole_step(state, action):

@@ -120,7 +120,11 @@ SYMBOLS = {
     "snn_actor_window": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP]),
     "snn_actor_episodes": (C.c_int32, [_VP, _VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP,
                                        _VP]),
+    "snn_actor_episodes_env": (C.c_int32, [_VP, C.c_int32, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           _VP, _VP, _VP, _VP, _VP]),
 }
+
+SNN_ENV_CARTPOLE, SNN_ENV_MOUNTAINCAR = 0, 1
 
 _lib = None
 

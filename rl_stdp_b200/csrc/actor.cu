@@ -285,12 +285,39 @@ __device__ __forceinline__ int cartpole_step(double s[4], int action) {
   return x < -2.4 || x > 2.4 || theta < -th || theta > th;
 }
 
-// play_episode (cartpole_fitness.jl:51-114) for every agent; optional teacher-style dopamine
+// MountainCar-v0 step, restated (gym classic_control/mountain_car.py); cos(3*position) by Cody-Waite
+// reduction + the kernel polynomials, the same IEEE operations as oracle/lif_oracle.c::ora_cos_reduced
+__device__ __forceinline__ double cos_reduced(double x) {
+  const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00,
+               pio2_1t = 6.07710050650619224932e-11;
+  const double fn = rint(DMUL(x, invpio2));
+  const double y = DSUB(DSUB(x, DMUL(fn, pio2_1)), DMUL(fn, pio2_1t));
+  switch (((int)fn) & 3) {
+    case 0: return k_cos(y);
+    case 1: return -k_sin(y);
+    case 2: return -k_cos(y);
+    default: return k_sin(y);
+  }
+}
+__device__ __forceinline__ int mountcar_step(double s[4], int action) {
+  const double min_position = -1.2, max_position = 0.6, max_speed = 0.07, goal_position = 0.5, force = 0.001,
+               gravity = 0.0025;
+  double position = s[0], velocity = s[1];
+  velocity = DADD(velocity, DADD(DMUL((double)(action - 1), force), DMUL(cos_reduced(DMUL(3.0, position)), -gravity)));
+  velocity = velocity < -max_speed ? -max_speed : (velocity > max_speed ? max_speed : velocity);
+  position = DADD(position, velocity);
+  position = position < min_position ? min_position : (position > max_position ? max_position : position);
+  if (position == min_position && velocity < 0) velocity = 0;
+  s[0] = position; s[1] = velocity;
+  return position >= goal_position && velocity >= 0;
+}
+
+// play_episode (cartpole_fitness.jl:51-114; ENV 1: mountcar_fitness.jl:48-107) for every agent; optional teacher-style dopamine
 // (CartPole/Teacher/teacher_sim.jl:61-80,132-133: da += (action==draw ? 1 : -200) * da_inc).
-template <int NS>
+template <int NS, int ENV>
 __global__ void __launch_bounds__(128)
 actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const double* __restrict__ state0,
-                     const int32_t* __restrict__ tie_actions, const int32_t* __restrict__ teach_actions,
+                     const int32_t* __restrict__ tie_actions, int tie_stride, const int32_t* __restrict__ teach_actions,
                      int n_decisions_max, int win_size, int train, double* __restrict__ rewards,
                      int32_t* __restrict__ n_dec, int32_t* __restrict__ n_rand_out, double* __restrict__ state_out) {
   extern __shared__ double smem[];
@@ -310,32 +337,37 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
   double st[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) st[c] = state0[(size_t)a * 4 + c];
-  double ma[NS][4];  // row `local` of matalpha (arch[0] x 4, column-major)
+  constexpr int NOBS = ENV == 0 ? 4 : 2;
+  double ma[NS][NOBS];  // row `local` of matalpha (arch[0] x NOBS, column-major)
 #pragma unroll
   for (int sl = 0; sl < NS; ++sl)
-    for (int c = 0; c < 4; ++c)
-      ma[sl][c] = (li[sl].layer == 0 && lane + 32 * sl < p.n) ? matalpha[(size_t)a * A0 * 4 + li[sl].local + A0 * c] : 0.0;
+    for (int c = 0; c < NOBS; ++c)
+      ma[sl][c] = (li[sl].layer == 0 && lane + 32 * sl < p.n) ? matalpha[(size_t)a * A0 * NOBS + li[sl].local + A0 * c] : 0.0;
   double tot_reward = 0.0;
   int n_rand = 0, n_tot = 0;
   const double pi = 3.14159265358979323846;
   for (int jdec = 0; jdec < n_decisions_max; ++jdec) {
-    // norm_cartpole :14-24
-    double r = fmod(DADD(st[2], pi), DMUL(2.0, pi));
-    if (r == 0) r = copysign(r, DMUL(2.0, pi)); else if (r < 0) r = DADD(r, DMUL(2.0, pi));
-    const double theta = DSUB(r, pi);
-    const double cone = __ddiv_rn(DMUL(12.0, pi), 180.0);
-    double on[4];
-    on[0] = __ddiv_rn(DADD(st[0], 2.4), 4.8);
-    on[1] = __ddiv_rn(DADD(st[1], 7.5), 15.0);
-    on[2] = __ddiv_rn(DADD(theta, cone), DMUL(2.0, cone));
-    on[3] = __ddiv_rn(DADD(st[3], 7.5), 15.0);
+    double on[NOBS];
+    if (ENV == 0) {  // norm_cartpole :14-24
+      double r = fmod(DADD(st[2], pi), DMUL(2.0, pi));
+      if (r == 0) r = copysign(r, DMUL(2.0, pi)); else if (r < 0) r = DADD(r, DMUL(2.0, pi));
+      const double theta = DSUB(r, pi);
+      const double cone = __ddiv_rn(DMUL(12.0, pi), 180.0);
+      on[0] = __ddiv_rn(DADD(st[0], 2.4), 4.8);
+      on[1] = __ddiv_rn(DADD(st[1], 7.5), 15.0);
+      on[NOBS - 2] = __ddiv_rn(DADD(theta, cone), DMUL(2.0, cone));
+      on[NOBS - 1] = __ddiv_rn(DADD(st[3], 7.5), 15.0);
+    } else {  // norm_mountcar mountcar_fitness.jl:13-20
+      on[0] = __ddiv_rn(DADD(st[0], 1.2), 1.8);
+      on[1] = __ddiv_rn(DADD(st[1], 0.07), 0.14);
+    }
     double inten[NS];  // matalpha*norm_cartpole(obs) :67
     int cnt[NS];
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
       inten[q] = 0.0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) inten[q] = DADD(inten[q], DMUL(ma[q][c], on[c]));
+      for (int c = 0; c < NOBS; ++c) inten[q] = DADD(inten[q], DMUL(ma[q][c], on[c]));
       if (lane + 32 * q < p.n) v[q] = p.c;  // :71
       cnt[q] = 0;
     }
@@ -345,28 +377,56 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
       for (int q = 0; q < NS; ++q)
         if (msec >= p.L - 1 && li[q].layer == p.L - 1 && ((m >> (lane + 32 * q)) & 1ull)) ++cnt[q];
     }
-    // left_right :36-41 — counts are small integers: any summation order is exact
-    int sl = 0, sr = 0;
+    // left_right :36-41 / push_or_not mountcar_fitness.jl:33-39 — counts are small integers: any
+    // summation order is exact.  ENV 1: pools of div(n,3), div(n,3) and the rest (:77-79)
+    const int n_mid_end = ENV == 0 ? n_left : 2 * (Lout / 3), n_left_e = ENV == 0 ? n_left : Lout / 3;
+    int sl = 0, sm = 0, sr = 0;
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
       const bool outl = li[q].layer == p.L - 1 && lane + 32 * q < p.n;
-      sl += (outl && li[q].local < n_left) ? cnt[q] : 0;
-      sr += (outl && li[q].local >= n_left) ? cnt[q] : 0;
+      sl += (outl && li[q].local < n_left_e) ? cnt[q] : 0;
+      sm += (outl && li[q].local >= n_left_e && li[q].local < n_mid_end) ? cnt[q] : 0;
+      sr += (outl && li[q].local >= n_mid_end) ? cnt[q] : 0;
     }
-    for (int o = 16; o > 0; o >>= 1) { sl += __shfl_xor_sync(FULL, sl, o); sr += __shfl_xor_sync(FULL, sr, o); }
-    int action = (sl >= sr) ? 0 : 1;
-    if (sl == sr) {  // :87-95
-      action = tie_actions[(size_t)a * n_decisions_max + n_rand];
-      tot_reward = DSUB(tot_reward, 0.9);
-      ++n_rand;
+    for (int o = 16; o > 0; o >>= 1) {
+      sl += __shfl_xor_sync(FULL, sl, o); sr += __shfl_xor_sync(FULL, sr, o);
+      if (ENV != 0) sm += __shfl_xor_sync(FULL, sm, o);
     }
-    ++n_tot;
-    if (train && teach_actions) {  // teacher_sim.jl:92-99,132-133
-      const double inc = (action == teach_actions[(size_t)a * n_decisions_max + jdec]) ? 1.0 : -200.0;
-      da = DADD(da, DMUL(inc, p.da_inc));
+    int action, done;
+    if (ENV == 0) {
+      action = (sl >= sr) ? 0 : 1;
+      if (sl == sr) {  // :87-95
+        action = n_rand < tie_stride ? tie_actions[(size_t)a * tie_stride + n_rand] : 0;
+        tot_reward = DSUB(tot_reward, 0.9);
+        ++n_rand;
+      }
+      ++n_tot;
+      if (train && teach_actions) {  // teacher_sim.jl:92-99,132-133
+        const double inc = (action == teach_actions[(size_t)a * n_decisions_max + jdec]) ? 1.0 : -200.0;
+        da = DADD(da, DMUL(inc, p.da_inc));
+      }
+      done = cartpole_step(st, action);
+      tot_reward = DADD(tot_reward, 1.0);
+    } else {
+      action = 0;  // argmax([sl, sm, sr]) - 1: the first maximum
+      int best = sl;
+      if (sm > best) { action = 1; best = sm; }
+      if (sr > best) action = 2;
+      double fac = 1.0;  // :83-93 every tied pair draws from its pool, the last draw wins
+      const int dif[3] = {sl - sr, sl - sm, sm - sr};
+      const int pool[3][2] = {{0, 2}, {0, 1}, {1, 2}};
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (dif[i] == 0) {
+          const int pick = n_rand < tie_stride ? tie_actions[(size_t)a * tie_stride + n_rand] : 0;
+          action = pool[i][pick & 1];
+          fac = 2.0;
+          ++n_rand;
+        }
+      ++n_tot;
+      done = mountcar_step(st, action);
+      tot_reward = DADD(tot_reward, DMUL(-1.0, fac));  // :98
     }
-    const int done = cartpole_step(st, action);
-    tot_reward = DADD(tot_reward, 1.0);
     if (done) break;
   }
   if (lane == 0) {
@@ -532,40 +592,46 @@ int Actor::window(int n_steps, const double* intensity, int train, int critic, i
   return SNN_OK;
 }
 
-int Actor::episodes(const double* matalpha, const double* state0, const int32_t* tie_actions,
+int Actor::episodes(int env, const double* matalpha, const double* state0, const int32_t* tie_actions, int tie_stride,
                     const int32_t* teach_actions, int n_decisions_max, int win_size, int train, double* rewards,
                     int32_t* n_dec, int32_t* n_rand, double* state_out, double* device_ms, std::string& err) {
   ActorDev& d = impl_->d;
-  if (!matalpha || !state0 || !tie_actions || !rewards || n_decisions_max <= 0 || win_size <= 0) {
+  if (!matalpha || !state0 || !tie_actions || !rewards || n_decisions_max <= 0 || win_size <= 0 || tie_stride <= 0) {
     err = "episodes: null argument / non-positive sizes"; return SNN_ERR_INVALID;
   }
+  if (env != SNN_ENV_CARTPOLE && env != SNN_ENV_MOUNTAINCAR) { err = "episodes: unknown environment"; return SNN_ERR_INVALID; }
+  if (env == SNN_ENV_MOUNTAINCAR && (teach_actions || d.arch[d.L - 1] < 3)) {
+    err = "episodes: MountainCar needs >= 3 output neurons and has no teacher signal"; return SNN_ERR_INVALID;
+  }
+  const size_t nobs = env == SNN_ENV_CARTPOLE ? 4 : 2;
   ACT_OK(cudaSetDevice(impl_->device));
   const size_t A = (size_t)d.n_agents;
   double *d_ma = nullptr, *d_s0 = nullptr, *d_rw = nullptr, *d_so = nullptr;
   int32_t *d_tie = nullptr, *d_teach = nullptr, *d_nd = nullptr, *d_nr = nullptr;
   cudaStream_t s = impl_->stream;
-  cudaError_t e = cudaMalloc(&d_ma, A * d.arch[0] * 4 * sizeof(double));
+  cudaError_t e = cudaMalloc(&d_ma, A * d.arch[0] * nobs * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&d_s0, A * 4 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&d_so, A * 4 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&d_rw, A * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&d_tie, A * n_decisions_max * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_tie, A * tie_stride * sizeof(int32_t));
   if (e == cudaSuccess && teach_actions) e = cudaMalloc(&d_teach, A * n_decisions_max * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMalloc(&d_nd, A * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMalloc(&d_nr, A * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ma, matalpha, A * d.arch[0] * 4 * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ma, matalpha, A * d.arch[0] * nobs * sizeof(double), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_s0, state0, A * 4 * sizeof(double), cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_tie, tie_actions, A * n_decisions_max * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_tie, tie_actions, A * tie_stride * sizeof(int32_t), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess && teach_actions)
     e = cudaMemcpyAsync(d_teach, teach_actions, A * n_decisions_max * sizeof(int32_t), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) {
     const int warps = actor_warps(d), blocks = (int)((A + warps - 1) / warps);
     cudaEventRecord(impl_->e0, s);
-    if (d.n <= 32)
-      actor_episode_kernel<1><<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, d_teach, n_decisions_max,
-                                                                                win_size, train, d_rw, d_nd, d_nr, d_so);
-    else
-      actor_episode_kernel<2><<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, d_teach, n_decisions_max,
-                                                                                win_size, train, d_rw, d_nd, d_nr, d_so);
+#define EPISODE_LAUNCH(NS, ENV)                                                                                      \
+  actor_episode_kernel<NS, ENV><<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, tie_stride, d_teach, \
+                                                                                 n_decisions_max, win_size, train, d_rw, \
+                                                                                 d_nd, d_nr, d_so)
+    if (env == SNN_ENV_CARTPOLE) { if (d.n <= 32) EPISODE_LAUNCH(1, 0); else EPISODE_LAUNCH(2, 0); }
+    else                         { if (d.n <= 32) EPISODE_LAUNCH(1, 1); else EPISODE_LAUNCH(2, 1); }
+#undef EPISODE_LAUNCH
     cudaEventRecord(impl_->e1, s);
     e = cudaGetLastError();
   }

@@ -19,8 +19,8 @@ class Actor {
   int set_array(int field, int layer, const double* host, int64_t count, std::string& err);
   int window(int n_steps, const double* intensity, int train, int critic, int reset_v, int32_t* counts,
              int32_t* spike_masks, double* device_ms, std::string& err);
-  int episodes(const double* matalpha, const double* state0, const int32_t* tie_actions, const int32_t* teach_actions,
-               int n_decisions_max, int win_size, int train, double* rewards, int32_t* n_dec, int32_t* n_rand,
+  int episodes(int env, const double* matalpha, const double* state0, const int32_t* tie_actions, int tie_stride,
+               const int32_t* teach_actions, int n_decisions_max, int win_size, int train, double* rewards, int32_t* n_dec, int32_t* n_rand,
                double* state_out, double* device_ms, std::string& err);
   const snn_actor_config& config() const { return cfg_; }
 

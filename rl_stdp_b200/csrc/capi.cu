@@ -287,8 +287,19 @@ int32_t snn_actor_episodes(snn_actor* a, const double* matalpha, const double* s
                            double* device_ms) {
   if (!a) return fail(SNN_ERR_INVALID, "null actor");
   std::string err;
-  int rc = a->impl.episodes(matalpha, state0, tie_actions, teach_actions, n_decisions_max, win_size, train, rewards,
-                            n_decisions, n_rand, state_out, device_ms, err);
+  int rc = a->impl.episodes(SNN_ENV_CARTPOLE, matalpha, state0, tie_actions, n_decisions_max, teach_actions,
+                            n_decisions_max, win_size, train, rewards, n_decisions, n_rand, state_out, device_ms, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_actor_episodes_env(snn_actor* a, int32_t env, const double* matalpha, const double* state0,
+                               const int32_t* tie_picks, int32_t tie_stride, int32_t n_decisions_max, int32_t win_size,
+                               int32_t train, double* rewards, int32_t* n_decisions, int32_t* n_rand,
+                               double* state_out, double* device_ms) {
+  if (!a) return fail(SNN_ERR_INVALID, "null actor");
+  std::string err;
+  int rc = a->impl.episodes(env, matalpha, state0, tie_picks, tie_stride, nullptr, n_decisions_max, win_size, train,
+                            rewards, n_decisions, n_rand, state_out, device_ms, err);
   return rc ? fail(rc, err) : SNN_OK;
 }
 

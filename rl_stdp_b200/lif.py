@@ -136,21 +136,48 @@ class ActorPopulation:
                                           _ptr(counts), _ptr(masks), C.byref(ms)))
         return counts, masks, ms.value
 
-    def play_episodes(self, matalpha, state0, tie_actions, n_steps=200, win_size=40, train=False, teach_actions=None):
-        """play_episode for every agent.  matalpha [n_agents, arch[0], 4]; state0 [n_agents, 4];
-        tie_actions [n_agents, n_steps].  Returns dict(rewards, n_decisions, n_rand, state, device_ms)."""
-        ma = np.asarray(matalpha, np.float64).reshape(self.n_agents, self.arch[0], 4)
+    def play_episodes(self, matalpha, state0, tie_actions=None, n_steps=200, win_size=40, train=False,
+                      teach_actions=None, env="cartpole"):
+        """play_episode for every agent, environment on the device.
+
+        env="cartpole" (cartpole_fitness.jl:51-114): matalpha [n_agents, arch[0], 4], state0 [n_agents, 4].
+        env="mountaincar" (mountcar_fitness.jl:48-107): matalpha [n_agents, arch[0], 2], state0 [n_agents, 2].
+        tie_actions [n_agents, k]: the replayed `rand(rng_action, ...)` stream (k >= n_steps; a MountainCar
+        decision can consume three draws); None = the reference's default `rng_seed = true`, i.e. every
+        episode draws from a fresh MersenneTwister(0) (julia_rng.py).
+        Returns dict(rewards, n_decisions, n_rand, state, device_ms)."""
+        envs = {"cartpole": (L.SNN_ENV_CARTPOLE, 4), "mountaincar": (L.SNN_ENV_MOUNTAINCAR, 2)}
+        if env not in envs:
+            raise ValueError(f"unknown environment {env!r}")
+        env_id, nobs = envs[env]
+        ma = np.asarray(matalpha, np.float64).reshape(self.n_agents, self.arch[0], nobs)
         ma = np.ascontiguousarray(np.transpose(ma, (0, 2, 1)).reshape(self.n_agents, -1))  # column-major
-        s0 = np.ascontiguousarray(np.asarray(state0, np.float64).reshape(self.n_agents, 4))
-        ta = np.ascontiguousarray(np.asarray(tie_actions, np.int32).reshape(self.n_agents, n_steps))
+        s0 = np.zeros((self.n_agents, 4), np.float64)
+        s0[:, :nobs] = np.asarray(state0, np.float64).reshape(self.n_agents, nobs)
+        if tie_actions is None:
+            from .julia_rng import julia_mt_pick_bits
+            k = n_steps * (1 if env_id == L.SNN_ENV_CARTPOLE else 3)
+            tie_actions = np.tile(np.asarray(julia_mt_pick_bits(0, k), np.int32), (self.n_agents, 1))
+        ta = np.ascontiguousarray(np.asarray(tie_actions, np.int32).reshape(self.n_agents, -1))
+        if ta.shape[1] < n_steps:
+            raise ValueError("tie_actions needs at least n_steps entries per agent")
         te = None if teach_actions is None else np.ascontiguousarray(
             np.asarray(teach_actions, np.int32).reshape(self.n_agents, n_steps))
+        if te is not None:
+            ta = np.ascontiguousarray(ta[:, :n_steps])   # snn_actor_episodes: stride n_steps
         rewards = np.zeros(self.n_agents, np.float64)
         nd = np.zeros(self.n_agents, np.int32)
         nr = np.zeros(self.n_agents, np.int32)
         so = np.zeros((self.n_agents, 4), np.float64)
         ms = C.c_double(0.0)
-        L.check(L.load().snn_actor_episodes(self._h, _ptr(ma), _ptr(s0), _ptr(ta), _ptr(te), int(n_steps),
-                                            int(win_size), int(train), _ptr(rewards), _ptr(nd), _ptr(nr), _ptr(so),
-                                            C.byref(ms)))
-        return dict(rewards=rewards, n_decisions=nd, n_rand=nr, state=so, device_ms=ms.value)
+        if env_id == L.SNN_ENV_CARTPOLE and (te is not None or ta.shape[1] == n_steps):
+            L.check(L.load().snn_actor_episodes(self._h, _ptr(ma), _ptr(s0), _ptr(ta), _ptr(te), int(n_steps),
+                                                int(win_size), int(train), _ptr(rewards), _ptr(nd), _ptr(nr),
+                                                _ptr(so), C.byref(ms)))
+        else:
+            if te is not None:
+                raise ValueError("teach_actions: CartPole only")
+            L.check(L.load().snn_actor_episodes_env(self._h, env_id, _ptr(ma), _ptr(s0), _ptr(ta), int(ta.shape[1]),
+                                                    int(n_steps), int(win_size), int(train), _ptr(rewards),
+                                                    _ptr(nd), _ptr(nr), _ptr(so), C.byref(ms)))
+        return dict(rewards=rewards, n_decisions=nd, n_rand=nr, state=so[:, :nobs], device_ms=ms.value)

@@ -98,7 +98,7 @@ def play_mountcar(window_fn, matalpha, tie_bits, n_steps=200):
     from gym's classic-control definition (NOT in the reference: PyCall -> gym) and gym's seed-0 reset
     position.  window_fn(intensity [A, 8]) -> last-layer spike counts [A, 8] of one 40-ms decision window
     (v reset to c first, counted from msec >= length(arch) - 1).  tie_bits = the stream of
-    rand(MersenneTwister(0), pool) picks (tests/julia_rng.py); every episode restarts it.
+    rand(MersenneTwister(0), pool) picks (rl_stdp_b200/julia_rng.py); every episode restarts it.
     Returns (reward [A], decisions [A], ties [A])."""
     import math
     A = len(matalpha)
@@ -118,7 +118,7 @@ def play_mountcar(window_fn, matalpha, tie_bits, n_steps=200):
                 if d == 0.0:
                     act, fac = pool[tie_bits[used[a]]] - 1, 2
                     used[a] += 1
-            v = vel[a] + (act - 1) * 0.001 + math.cos(3 * pos[a]) * (-0.0025)
+            v = vel[a] + ((act - 1) * 0.001 + math.cos(3 * pos[a]) * (-0.0025))   # gym: velocity += A + B
             v = min(max(v, -0.07), 0.07)
             x = min(max(pos[a] + v, -1.2), 0.6)
             if x == -1.2 and v < 0:

@@ -246,7 +246,7 @@ def test_reference_mountcar_elites_known_answers_on_device():
     (snn_actor_window); environment, read-out and Julia's tie stream on the host."""
     from rl_stdp_b200.lif import ActorPopulation
     from tests.helpers import mountcar_elites, play_mountcar
-    from tests.julia_rng import julia_mt_pick_bits
+    from rl_stdp_b200.julia_rng import julia_mt_pick_bits
     el = mountcar_elites()
     pop = ActorPopulation([8, 8, 8], len(el))
     for l in range(2):
@@ -256,3 +256,43 @@ def test_reference_mountcar_elites_known_answers_on_device():
     assert tot.tolist() == [f for _, _, f in el]
     assert nd.tolist() == [121, 122, 118, 126, 111, 113, 121, 118, 117, 116]
     assert ties.tolist() == [8, 7, 9, 1, 18, 12, 4, 5, 4, 1]
+
+
+def test_mountcar_episodes_on_device():
+    """snn_actor_episodes_env(SNN_ENV_MOUNTAINCAR): the whole mountcar_fitness.jl play_episode on the device.
+    (1) the reference's ten saved results with Julia's default tie stream; (2) random genomes, random starts
+    and random tie streams bit-equal to the oracle (reward, decisions, ties, final position and velocity)."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200.lif import ActorPopulation, borne, set_weight
+    from tests.helpers import _gym_np_random, mountcar_elites
+    el = mountcar_elites()
+    p0 = _gym_np_random(0).uniform(low=-0.6, high=-0.4)
+    pop = ActorPopulation([8, 8, 8], len(el))
+    for l in range(2):
+        pop.set_weights(l, np.array([w[l] for _, w, _ in el]))
+    out = pop.play_episodes(np.array([m for m, _, _ in el]), np.tile([p0, 0.0], (len(el), 1)), env="mountaincar")
+    assert out["rewards"].tolist() == [f for _, _, f in el]
+    assert out["n_decisions"].tolist() == [121, 122, 118, 126, 111, 113, 121, 118, 117, 116]
+    assert out["n_rand"].tolist() == [8, 7, 9, 1, 18, 12, 4, 5, 4, 1]
+
+    arch, A = [8, 8, 9], 64   # 9 outputs: pools of 3, 3, 3
+    rng = np.random.Generator(np.random.Philox(key=91))
+    genes = rng.standard_normal((A, 16 + 8 * 8 + 8 * 9 + 16)) * 4.0
+    ma = np.array([borne(g[:16], -1.0, 1.0).reshape((2, 8)).T for g in genes])
+    ws = [set_weight(arch, g[32:]) for g in genes]
+    s0 = np.stack([rng.uniform(-0.6, -0.4, A), rng.uniform(-0.01, 0.01, A)], axis=1)
+    ties = rng.integers(0, 2, size=(A, 600), dtype=np.int32)
+    pop = ActorPopulation(arch, A)
+    for l in range(2):
+        pop.set_weights(l, np.array([w[l] for w in ws]))
+    out = pop.play_episodes(ma, s0, ties, n_steps=200, env="mountaincar")
+    n_tied = 0
+    for a in range(A):
+        o = po.Layered(arch)
+        for l in range(2):
+            o.e(l)[:, :] = ws[a][l]
+        r, nd, nr, so = o.play_episode_mountcar(ma[a], s0[a], ties[a])
+        assert (out["rewards"][a], out["n_decisions"][a], out["n_rand"][a]) == (r, nd, nr), a
+        assert np.array_equal(out["state"][a], so), a
+        n_tied += nr
+    assert n_tied > 0 and out["n_decisions"].min() < 200   # ties and early finishes both exercised

@@ -359,8 +359,8 @@ def test_reference_elites_known_answers():
 
 
 def test_julia_mersenne_twister_restatement():
-    """tests/julia_rng.py against the published head of `rand(MersenneTwister(0), 10)`."""
-    from tests.julia_rng import DSFMT, julia_mt_pick_bits
+    """rl_stdp_b200/julia_rng.py against the published head of `rand(MersenneTwister(0), 10)`."""
+    from rl_stdp_b200.julia_rng import DSFMT, julia_mt_pick_bits
     g = DSFMT([0])
     assert [g.rand() for _ in range(10)] == [
         0.8236475079774124, 0.9103565379264364, 0.16456579813368521, 0.17732884646626457, 0.278880109331201,
@@ -375,10 +375,10 @@ def test_reference_mountcar_elites_known_answers():
     """Ten NON-saturated known answers: Actors/sNESelites_mountcar.jld stores, for ten genomes, the fitness
     play_episode (mountcar_fitness.jl:48-107) returned — minus one per decision until the flag is reached,
     minus two for a decision with a tie, the tie resolved by `rand(MersenneTwister(0), pool)`.  With gym's
-    seed-0 reset position, Julia's tie stream (tests/julia_rng.py) and a restated MountainCar-v0, the oracle's
+    seed-0 reset position, Julia's tie stream (rl_stdp_b200/julia_rng.py) and a restated MountainCar-v0, the oracle's
     LIF step reproduces all ten, e.g. -129 = 121 decisions with 8 ties."""
     from tests.helpers import mountcar_elites, play_mountcar
-    from tests.julia_rng import julia_mt_pick_bits
+    from rl_stdp_b200.julia_rng import julia_mt_pick_bits
     el = mountcar_elites()
     nets = []
     for _, w, _ in el:
@@ -403,3 +403,27 @@ def test_reference_mountcar_elites_known_answers():
                                                      -123.0, -121.0, -117.0]
     assert nd.tolist() == [121, 122, 118, 126, 111, 113, 121, 118, 117, 116]
     assert ties.tolist() == [8, 7, 9, 1, 18, 12, 4, 5, 4, 1]
+
+
+def test_mountcar_oracle_episode_function():
+    """ora_play_episode_mountcar (the C restatement the device is compared with) gives the same ten known
+    answers as the Python-level replay above, which uses libm's cos; its reduced-argument cosine stays
+    within one ulp of libm over the track."""
+    import math
+    from tests.helpers import _gym_np_random, mountcar_elites
+    from rl_stdp_b200.julia_rng import julia_mt_pick_bits
+    for x in np.linspace(-3.6, 1.8, 20001):
+        c = po.cos_reduced(float(x))
+        assert abs(c - math.cos(x)) <= np.spacing(abs(c)) * 1.0001, x
+    p0 = _gym_np_random(0).uniform(low=-0.6, high=-0.4)
+    assert abs(p0 - -0.5891279887498433) < 1e-15
+    bits = julia_mt_pick_bits(0, 600)
+    got = []
+    for m, w, fit in mountcar_elites():
+        n = po.Layered([8, 8, 8])
+        for l in range(2):
+            n.e(l)[:, :] = w[l]
+        r, nd, nr, _ = n.play_episode_mountcar(m, [p0, 0.0], bits)
+        assert r == fit
+        got.append((nd, nr))
+    assert got == list(zip([121, 122, 118, 126, 111, 113, 121, 118, 117, 116], [8, 7, 9, 1, 18, 12, 4, 5, 4, 1]))
