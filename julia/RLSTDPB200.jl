@@ -10,7 +10,10 @@
 #     spiked = step!(n, noise_row, train)                              # noise_row = 13 .* (rand(N) .- 0.5)
 module RLSTDPB200
 
-export Network, step!, run_window!, add_dopamine!, reset_v!, weights, eligibility
+import Random
+
+export Network, step!, run_window!, add_dopamine!, reset_v!, weights, eligibility,
+       ActorPopulation, set_weights!, play_episodes
 
 const LIB = get(ENV, "SNN_B200_LIB", joinpath(@__DIR__, "..", "rl_stdp_b200", "libsnn_b200.so"))
 
@@ -202,5 +205,89 @@ end
 partition_connect!(net::Network, rank::Integer, world::Integer, blobs::Vector{UInt8}) =
     check(ccall((:snn_partition_connect, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}),
                 net.handle, rank, world, blobs))
+
+# ---- LIF actor populations (Modules/Networks/net_arch.jl variant F; Actors/cartpole_fitness.jl,
+#      Actors/mountcar_fitness.jl): one handle = n_agents networks of the same `arch`
+
+# mirrors `struct snn_actor_config` of include/snn_b200.h
+mutable struct SnnActorConfig
+    struct_size::Int32; device::Int32; n_agents::Int32; n_layers::Int32
+    arch::NTuple{8,Int32}
+    vthresh::Float64; c::Float64
+    wei::Float64; wie::Float64; wmax::Float64
+    theta::Float64; ttheta::Float64
+    imin::Float64
+    apost::Float64; apre::Float64
+    tde::Float64; ttrace::Float64
+    taulif::Float64
+    eta::Float64; winh::Float64
+    da_inc::Float64
+    reserved::NTuple{8,Int32}
+    SnnActorConfig() = new()
+end
+
+const ENV_CARTPOLE, ENV_MOUNTAINCAR = Int32(0), Int32(1)
+
+mutable struct ActorPopulation
+    handle::Ptr{Cvoid}
+    arch::Vector{Int64}
+    n_agents::Int64
+end
+
+"`ActorPopulation(arch, params, n)` stands for `[Network(arch, params) for _ in 1:n]` (net_arch.jl:98-128)."
+function ActorPopulation(arch::Vector{Int64}, params::Dict, n_agents::Integer; device::Integer = 0)
+    cfg = SnnActorConfig()
+    check(ccall((:snn_actor_config_default, LIB), Int32, (Ref{SnnActorConfig},), cfg))
+    cfg.device = device; cfg.n_agents = n_agents; cfg.n_layers = length(arch)
+    cfg.arch = ntuple(i -> i <= length(arch) ? Int32(arch[i]) : Int32(0), 8)
+    for (k, f) in (("vthresh", :vthresh), ("c", :c), ("wei", :wei), ("wie", :wie), ("wmax", :wmax),
+                   ("theta", :theta), ("ttheta", :ttheta), ("imin", :imin), ("apost", :apost), ("apre", :apre),
+                   ("tde", :tde), ("ttrace", :ttrace), ("taulif", :taulif), ("eta", :eta), ("da_inc", :da_inc))
+        haskey(params, k) && setfield!(cfg, f, Float64(params[k]))
+    end
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:snn_actor_create, LIB), Int32, (Ref{SnnActorConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+    pop = ActorPopulation(h[], arch, n_agents)
+    finalizer(p -> (p.handle != C_NULL && ccall((:snn_actor_destroy, LIB), Int32, (Ptr{Cvoid},), p.handle); p.handle = C_NULL), pop)
+    return pop
+end
+
+"`e[:, :, a]` = the `net.s.e[layer]` of agent a (arch[layer] x arch[layer+1], as set_weight! fills it)."
+function set_weights!(pop::ActorPopulation, layer::Integer, e::Array{Float64,3})
+    @assert size(e) == (pop.arch[layer], pop.arch[layer+1], pop.n_agents)   # column-major per agent == the C layout
+    check(ccall((:snn_actor_set_array, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64),
+                pop.handle, FIELD_W, layer - 1, e, length(e)))
+end
+
+"""
+    play_episodes(pop, matalpha, state0; env, tie_picks, n_steps = 200) -> (rewards, n_decisions, n_rand)
+
+`play_episode` (cartpole_fitness.jl:51-114 / mountcar_fitness.jl:48-107) for every agent at once — the body of
+the `fitness(i::Individual)` callback for a whole Cambrian population.  `matalpha[:, :, a]` is arch[1] x 4
+(CartPole) or arch[1] x 2 (MountainCar); `state0[:, a]` the `env.reset()` observation; `tie_picks[:, a]` the
+`rand(rng_action, ...)` draws as 0-based picks (default: what `MersenneTwister(0)` gives).
+"""
+function play_episodes(pop::ActorPopulation, matalpha::Array{Float64,3}, state0::Matrix{Float64};
+                       env::Int32 = ENV_CARTPOLE, n_steps::Integer = 200, win_size::Integer = 40,
+                       tie_picks::Matrix{Int32} = default_tie_picks(env, n_steps, pop.n_agents))
+    A = pop.n_agents
+    s0 = zeros(4, A); s0[1:size(state0, 1), :] .= state0
+    rewards = zeros(A); nd = zeros(Int32, A); nr = zeros(Int32, A); so = zeros(4, A); ms = Ref{Float64}(0.0)
+    GC.@preserve matalpha s0 tie_picks begin
+        check(ccall((:snn_actor_episodes_env, LIB), Int32,
+                    (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32, Int32, Int32, Int32,
+                     Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ref{Float64}),
+                    pop.handle, env, matalpha, s0, tie_picks, size(tie_picks, 1), n_steps, win_size, 0,
+                    rewards, nd, nr, so, ms))
+    end
+    return rewards, nd, nr
+end
+
+function default_tie_picks(env::Int32, n_steps::Integer, n_agents::Integer)
+    k = env == ENV_CARTPOLE ? n_steps : 3 * n_steps
+    rng = Random.MersenneTwister(0)
+    picks = Int32[rand(rng, 0:1) for _ in 1:k]            # cartpole_fitness.jl:55,89; a fresh generator per episode
+    return repeat(picks, 1, n_agents)
+end
 
 end # module
