@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import py_oracle as O  # noqa: E402
 from rl_stdp_b200 import jld  # noqa: E402
 from rl_stdp_b200.lif import borne, set_weight  # noqa: E402

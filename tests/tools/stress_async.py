@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Repeats the frozen-weight production-mode case (async learn pass) to expose rare races.
-  python tools/stress_async.py [--reps 20] [--exp-flags 0]"""
+  python tests/tools/stress_async.py [--reps 20] [--exp-flags 0]"""
 import argparse, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import py_oracle as po
 from rl_stdp_b200 import _lib as L, synth
