@@ -47,7 +47,7 @@ WORKLOADS = {
     "tiny": (20_000, 16_000, 100, 20),
     "c4_actors": None,  # 4096 x LIF [8,8,8] CartPole actors, whole episodes on the device (per GPU: 4096/N)
 }
-LEARN_PERIOD = 10
+LEARN_PERIOD = int(os.environ.get("BENCH_LEARN_PERIOD", "10"))  # the reference learns every 10th ms (newnet_DASTDP.jl:48-51); the override is a diagnostic
 DA_PERIOD = 1000
 # algorithmic bytes (fp32), SURVEY §8(d)
 B_NEURON = 36      # per neuron per ms
