@@ -165,7 +165,8 @@ def run_b200(args):
         rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9 + rank, n_instances=n_inst)
         net = SparseNetwork(n, ne, rowptr, post, w, delay, n_instances=n_inst, dtype="f32", mode="fast", noise="philox",
                             device=local, max_delay=dmax, noise_seed=10 + rank, exp_flags=args.exp_flags,
-                            graph=not args.no_graph, learn_async=args.learn_async, learn_blocks=args.learn_blocks, learn_tile_k=args.learn_tile_k, learn_stages=args.learn_stages, side_blocks=args.side_blocks)
+                            graph=not args.no_graph, learn_async=args.learn_async, learn_blocks=args.learn_blocks, learn_tile_k=args.learn_tile_k, learn_stages=args.learn_stages, side_blocks=args.side_blocks,
+                            learn_lazy=args.learn_lazy, learn_lazy_da=args.learn_lazy_da)
         n_plastic = int(rowptr[ne]) * n_inst
     del post, w, delay
     t_build = time.perf_counter() - t_build
@@ -267,7 +268,8 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "neurons": n * n_inst, "synapses": int(rowptr[-1]), "max_delay_ms": dmax,
                        "instances_per_gpu": n_inst,
-                       "window_ms_per_step": W, "learn_period_ms": LEARN_PERIOD, "noise": "on-device Philox4x32-10",
+                       "window_ms_per_step": W, "learn_period_ms": LEARN_PERIOD,
+                       **({"learn_rule": f"EXPERIMENTAL event-driven, re-basing every {args.learn_lazy} learn steps (approximates the clamp)"} if args.learn_lazy else {}), "noise": "on-device Philox4x32-10",
                        "instances": 1 if (args.partition and world > 1) else world,
                        "sharding": ("one network, neurons partitioned over the ranks; per ms the spike bitmap is exchanged "
                                     + ("by NCCL all-gather from a host callback" if args.partition == "nccl" else
@@ -494,6 +496,8 @@ def main():
     ap.add_argument("--exp-flags", type=int, default=0, help="snn_config.reserved[1] diagnostics (2 timeline, 4 serialise the learn pass, 512 LSU pass); 0 for reported numbers")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--learn-async", default="auto", choices=["auto", "off", "force"], help="learn pass beside the following steps (auto: large nets) or in place")
+    ap.add_argument("--learn-lazy", type=int, default=0, help="EXPERIMENTAL event-driven learning: dense re-basing pass every M learn steps (0 = the reference's rule; not for reported numbers)")
+    ap.add_argument("--learn-lazy-da", type=float, default=0.0, help="with --learn-lazy: re-base at every learn step while da exceeds this (0 = never)")
     ap.add_argument("--learn-tile-k", type=int, default=0, help="async learn pass: tile size in units of 1024 synapses (0 = 32)")
     ap.add_argument("--learn-stages", type=int, default=0, help="async learn pass: TMA pipeline depth (0 = 6)")
     ap.add_argument("--side-blocks", type=int, default=0, help="10*synapse + ltp kernel blocks per SM (0 = default)")

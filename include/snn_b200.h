@@ -112,8 +112,13 @@ typedef struct snn_config {
                                   the asynchronous learn pass, 512 = register-staged pass instead of TMA
                               [2] asynchronous learn pass: resident blocks per SM
                               [4] learn pass: 0 auto (asynchronous on large nets), 1 always in place,
-                                  2 always asynchronous
-                              [5] asynchronous learn pass: total entries of the sd-update log */
+                                  2 always asynchronous; 16+M = EXPERIMENTAL event-driven learning
+                                  (SNN_MODE_FAST only; an approximation of the reference's rule: the
+                                  clamp wmin <= w <= wmax is applied when a weight is read and at a
+                                  dense re-basing pass every M learn steps instead of at every learn
+                                  step; M = 1 is the reference's rule.  DESIGN.md section 11.1)
+                              [5] asynchronous learn pass: total entries of the sd-update log; with
+                                  [4] >= 16: re-base at every learn step while da > [5]/1000 (0 = never) */
 } snn_config;
 
 typedef struct snn_net snn_net;

@@ -149,6 +149,16 @@ struct DevNet {
   uint32_t n_tiles, tile_syn;
   int32_t static_cur;    // >= 0: no pass can be in flight while this launch runs and wsdX[static_cur] is
                          // current — kernels skip the LearnCtl load (in-place windows, exact mode)
+  // event-driven ("lazy") learning, production mode, opt-in: between two
+  // re-basing passes wsd holds (s0, sd' = sd / r^k), cacc the accumulator C = sum_events d' * H[k_e]
+  // and the weight is s = clamp(s0 + H*sd' - C) with H = sum_j rate_j * r^(j-1) over the learn steps
+  // since the last re-basing; learn! touches no synapse except every `lazy`-th time (or while
+  // da > lazy_da), when a dense pass writes s0 = s, sd' = sd, C = 0.
+  int32_t lazy;          // 0 = off, else M = learn steps per re-basing pass
+  T lazy_da;
+  T* cacc;               // [E]
+  T *lzH, *lzR, *lzInv;  // [B] H, r^k, 1/r^k
+  int32_t* lzK;          // [B] learn steps since the last re-basing
   const uint32_t *colptr, *col_npl, *in_syn, *in_pre;
   // counters[0] = spikes, [1] = synaptic events (exact mode); per-block partial sums otherwise
   unsigned long long* counters;
@@ -234,10 +244,12 @@ struct WView {
   typename Real2<T>::type* cur;        // post-learn values of processed synapses; all non-plastic ones
   const typename Real2<T>::type* old;  // frozen pre-learn values (valid for every synapse)
   uint32_t front;                      // in units of 32 synapses
+  bool lazy;                           // event-driven learning: cur holds (s0, sd'), see DevNet::lazy
 };
 template <typename T>
 __device__ __forceinline__ WView<T> wview(const DevNet<T>& p) {
   WView<T> v;
+  v.lazy = p.lazy != 0;
   if (p.static_cur >= 0) {
     v.cur = p.wsdX[p.static_cur]; v.old = p.wsdX[p.static_cur ^ 1]; v.front = kFrontAll;
     return v;
@@ -256,24 +268,37 @@ __device__ __forceinline__ double ldcg_x(const double2* q) { return __ldcg(reint
 // `row_exc`: the presynaptic neuron is excitatory (only those rows can be plastic).
 template <typename T>
 __device__ __forceinline__ typename Real2<T>::type w_fetch(const WView<T>& vw, uint32_t e, bool row_exc, bool& fly) {
-  fly = row_exc && (e >> 5) >= vw.front;
+  fly = row_exc && (vw.lazy || (e >> 5) >= vw.front);
   typename Real2<T>::type ws;
-  if (fly) ws = __ldcg(vw.old + e);
+  if (fly) ws = __ldcg((vw.lazy ? (const typename Real2<T>::type*)vw.cur : vw.old) + e);
   else { ws.x = ldcg_x(vw.cur + e); ws.y = (T)0; }
   return ws;
 }
+// event-driven learning: the C accumulator of a possibly plastic synapse (issued with w_fetch)
+template <typename T>
+__device__ __forceinline__ T c_fetch(const DevNet<T>& p, const WView<T>& vw, uint32_t e, bool fly) {
+  return (vw.lazy && fly) ? __ldcg(p.cacc + e) : (T)0;
+}
 template <typename T>
 __device__ __forceinline__ T w_resolve(const DevNet<T>& p, const typename Real2<T>::type& ws, bool fly, bool plastic,
-                                       uint32_t inst) {
+                                       uint32_t inst, T c) {
   if (!(fly && plastic)) return ws.x;  // non-plastic weights never change: both buffers hold them
-  const T x = Ops<T>::add(ws.x, Ops<T>::mul(p.lg[inst], ws.y));
+  const T x = p.lazy ? Ops<T>::sub(Ops<T>::add(ws.x, Ops<T>::mul(p.lzH[inst], ws.y)), c)
+                     : Ops<T>::add(ws.x, Ops<T>::mul(p.lg[inst], ws.y));
   return x > p.wmax ? p.wmax : (x < p.wmin ? p.wmin : x);
 }
 // sd[e] += delta (production mode: unordered reductions).  A synapse the pass in flight has not
 // reached keeps its frozen sd: the update is logged (region = this block's private log) and
 // replayed onto the post-learn value.
 template <typename T>
-__device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, uint32_t e, T delta, uint32_t region) {
+__device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, uint32_t e, T delta, uint32_t region,
+                                       uint32_t inst) {
+  if (vw.lazy) {  // two fire-and-forget reductions: sd' += d', C += d' * H
+    const T d = Ops<T>::mul(delta, p.lzInv[inst]);
+    atomicAdd(&vw.cur[e].y, d);
+    atomicAdd(&p.cacc[e], Ops<T>::mul(d, p.lzH[inst]));
+    return;
+  }
   if ((e >> 5) < vw.front) {
     atomicAdd(&vw.cur[e].y, delta);
     return;
@@ -480,19 +505,19 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
                 // four loads in flight per lane before the first reduction (an inhibitory row has
                 // ~100 delay-1 synapses; one round trip instead of four)
                 for (uint32_t e0 = s0 + lane; e0 < s1; e0 += 128) {
-                  int32_t pj[4]; typename DevNet<T>::T2 pw[4]; bool fly[4];
+                  int32_t pj[4]; typename DevNet<T>::T2 pw[4]; bool fly[4]; T pc[4];
 #pragma unroll
                   for (int q4 = 0; q4 < 4; ++q4) {
                     const uint32_t e = e0 + 32 * q4;
                     pj[q4] = e < s1 ? p.post[e] : -1;
-                    fly[q4] = false;
-                    if (e < s1) pw[q4] = w_fetch<T>(vw, e, row_exc, fly[q4]);
+                    fly[q4] = false; pc[q4] = (T)0;
+                    if (e < s1) { pw[q4] = w_fetch<T>(vw, e, row_exc, fly[q4]); pc[q4] = c_fetch<T>(p, vw, e, fly[q4]); }
                   }
 #pragma unroll
                   for (int q4 = 0; q4 < 4; ++q4)
                     if (pj[q4] >= 0)
                       atomicAdd(&I_now[pj[q4]],
-                                w_resolve<T>(p, pw[q4], fly[q4], p.plastic_ei || ((uint32_t)pj[q4] - ibase) < Ne, inst));
+                                w_resolve<T>(p, pw[q4], fly[q4], p.plastic_ei || ((uint32_t)pj[q4] - ibase) < Ne, inst, pc[q4]));
                 }
               }
             }
@@ -607,7 +632,8 @@ __device__ __forceinline__ void remote_body(const DevNet<T>& p, const WindowCtx<
                 const uint32_t j = (uint32_t)p.post[e];
                 bool fly;
                 const typename DevNet<T>::T2 ws = w_fetch<T>(vw, e, row_exc, fly);
-                atomicAdd(&I_now[j], w_resolve<T>(p, ws, fly, p.plastic_ei || j < (uint32_t)p.Ne, 0u));
+                const T wc = c_fetch<T>(p, vw, e, fly);
+                atomicAdd(&I_now[j], w_resolve<T>(p, ws, fly, p.plastic_ei || j < (uint32_t)p.Ne, 0u, wc));
               }
             }
           }
@@ -765,11 +791,12 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
       if (e >= s1) {                       // arrives at k+1: push only
         bool fly;
         const typename DevNet<T>::T2 ws = w_fetch<T>(vw, e, row_exc, fly);
-        atomicAdd(&I_next[j], w_resolve<T>(p, ws, fly, p.plastic_ei || (j - ibase) < Ne, inst));
+        const T wc = c_fetch<T>(p, vw, e, fly);
+        atomicAdd(&I_next[j], w_resolve<T>(p, ws, fly, p.plastic_ei || (j - ibase) < Ne, inst, wc));
       } else if (row_plastic && (p.plastic_ei || (j - ibase) < Ne)) {
         const T dn = O::mul(p.apre, tr_now[j]);
         if (ATOMIC) {  // production: fire-and-forget reduction, LTP of this step comes from ltp_kernel
-          sd_add<T>(p, vw, e, -dn, blockIdx.x);
+          sd_add<T>(p, vw, e, -dn, blockIdx.x, inst);
           continue;
         }
         const bool jsp = (bits_now[j >> 5] >> (j & 31)) & 1u;
@@ -818,6 +845,7 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
   unsigned long long n_ltp = 0;
   for (uint32_t item = gtid >> g_log2; item < (uint32_t)n_now; item += ngroups) {
     const int32_t j = list[item];
+    const uint32_t inst = p.B == 1 ? 0u : (uint32_t)j / (uint32_t)p.Nper;
     const uint32_t c0 = p.colptr[j], c1 = c0 + p.col_npl[j];
     if (gl == 0) n_ltp += (c1 - c0);
     for (uint32_t kb = c0 + gl; kb < c1; kb += 3 * G) {
@@ -849,7 +877,7 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         if (!ok[q]) continue;
-        if (ATOMIC) sd_add<T>(p, vw, e[q], O::mul(p.apost, trv[q]), p.log_ltp_base + blockIdx.x);
+        if (ATOMIC) sd_add<T>(p, vw, e[q], O::mul(p.apost, trv[q]), p.log_ltp_base + blockIdx.x, inst);
         else vw.cur[e[q]].y = O::add(sdv[q], O::mul(p.apost, trv[q]));
       }
     }
@@ -974,6 +1002,60 @@ learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int do
   learn_range<T, 4, false>(p, w, w, lo, hi, r0, g, do_learn, do_decay, blockIdx.x * (int64_t)blockDim.x + threadIdx.x,
                     (int64_t)gridDim.x * blockDim.x);
   tl_end(p.tl, 3, k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Event-driven learning (DevNet::lazy): learn!(k) of instance b only advances (H, r^k, count) —
+// lazy_commit_kernel — unless this is a re-basing step, where lazy_learn_kernel first runs the dense
+// pass  s0 = clamp(s0 + H*sd' - C), sd' = sd' * r^k, C = 0  over the plastic synapses with the
+// advanced values (both kernels recompute them from the same, not yet committed, state).
+// force: materialise only (snn_get_array / snn_set_array), no learn step is counted.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ bool lazy_next(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k, int b,
+                                          int do_learn, int do_decay, int force, T& Hn, T& Rn, int& Kn) {
+  typedef Ops<T> O;
+  const int64_t t = cx->t0 + k;
+  const T da = p.da[(size_t)((t + 1) & 1) * p.B + b];
+  const T H = p.lzH[b], R = p.lzR[b];
+  Hn = do_learn ? O::add(H, O::mul(learn_rate<T>(p, da), R)) : H;
+  Rn = do_decay ? O::mul(R, p.sd_decay) : R;
+  Kn = p.lzK[b] + (do_learn ? 1 : 0);
+  return force || Kn >= p.lazy || (do_learn && da > p.lazy_da);
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+lazy_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int do_learn, int do_decay, int force) {
+  typedef Ops<T> O;
+  tl_begin(p.tl, 3, k);
+  const int b = blockIdx.y;
+  T Hn, Rn; int Kn;
+  if (lazy_next<T>(p, cx, k, b, do_learn, do_decay, force, Hn, Rn, Kn)) {
+    const int64_t r0 = (int64_t)b * p.Nper;
+    const int64_t lo = p.seg[(size_t)r0 * (p.Dmax + 1)];
+    const int64_t hi = p.seg[(size_t)(r0 + p.Ne - 1) * (p.Dmax + 1) + p.Dmax];
+    typename DevNet<T>::T2* w = wview(p).cur;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < hi; e += nth) {
+      if (!p.plastic_ei && ((int64_t)p.post[e] - r0) >= p.Ne) continue;
+      typename DevNet<T>::T2 ws = w[e];
+      const T x = O::sub(O::add(ws.x, O::mul(Hn, ws.y)), p.cacc[e]);
+      ws.x = x > p.wmax ? p.wmax : (x < p.wmin ? p.wmin : x);
+      ws.y = O::mul(ws.y, Rn);
+      w[e] = ws;
+      p.cacc[e] = (T)0;
+    }
+  }
+  tl_end(p.tl, 3, k);
+}
+template <typename T>
+__global__ void lazy_commit_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int do_learn, int do_decay,
+                                   int force) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  T Hn, Rn; int Kn;
+  if (lazy_next<T>(p, cx, k, b, do_learn, do_decay, force, Hn, Rn, Kn)) { Hn = (T)0; Rn = (T)1; Kn = 0; }
+  p.lzH[b] = Hn; p.lzR[b] = Rn; p.lzInv[b] = (T)1 / Rn; p.lzK[b] = Kn;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1521,7 +1603,30 @@ class Engine : public IEngine {
     n_plastic_ = 0;
     for (int b = 0; b < p.B; ++b) n_plastic_ += (int64_t)inst_hi_[b] - (int64_t)inst_lo_[b];
     // production mode: second (w, sd) buffer + update log for the asynchronous learn pass
-    have_async_ = !p.exact && use_graph_ && cfg_.reserved[4] != 1 && n_plastic_ > 0 &&
+    // reserved[4] >= 16: event-driven learning, re-basing every reserved[4]-16 learn steps (and at every
+    // learn step while da > reserved[5]/1000 when that is > 0); production mode only
+    p.lazy = 0;
+    if (cfg_.reserved[4] >= 16) {
+      if (p.exact) { err = "event-driven learning (reserved[4] >= 16) needs SNN_MODE_FAST"; return SNN_ERR_INVALID; }
+      if (cfg_.sd_decay_mode == SNN_SD_DECAY_EVERY_STEP) {
+        err = "event-driven learning does not support SNN_SD_DECAY_EVERY_STEP"; return SNN_ERR_INVALID;
+      }
+      if (n_plastic_ > 0) {
+        p.lazy = std::max(1, cfg_.reserved[4] - 16);
+        p.lazy_da = cfg_.reserved[5] > 0 ? (T)(cfg_.reserved[5] * 1e-3) : (T)1e30;
+        SNN_CUDA_OK(cudaMalloc(&p.cacc, Ea * sizeof(T)));
+        SNN_CUDA_OK(cudaMemsetAsync(p.cacc, 0, Ea * sizeof(T), stream_));
+        SNN_CUDA_OK(cudaMalloc(&p.lzH, 3 * (size_t)p.B * sizeof(T)));
+        p.lzR = p.lzH + p.B; p.lzInv = p.lzR + p.B;
+        SNN_CUDA_OK(cudaMalloc(&p.lzK, (size_t)p.B * sizeof(int32_t)));
+        SNN_CUDA_OK(cudaMemsetAsync(p.lzK, 0, (size_t)p.B * sizeof(int32_t), stream_));
+        std::vector<T> init(3 * (size_t)p.B, (T)1);
+        std::fill(init.begin(), init.begin() + p.B, (T)0);
+        SNN_CUDA_OK(cudaMemcpyAsync(p.lzH, init.data(), init.size() * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+      }
+    }
+    have_async_ = !p.lazy && !p.exact && use_graph_ && cfg_.reserved[4] != 1 && n_plastic_ > 0 &&
                   cfg_.sd_decay_mode != SNN_SD_DECAY_EVERY_STEP;
     if (have_async_) {
       SNN_CUDA_OK(cudaMalloc(&p.wsdX[1], Ea * sizeof(T2)));
@@ -1576,6 +1681,7 @@ class Engine : public IEngine {
         if (!have_topo_) { err = "synapses not set"; return SNN_ERR_STATE; }
         if (count != p.E) { err = "count mismatch"; return SNN_ERR_INVALID; }
         if (p.E == 0) return SNN_OK;
+        { const int rcf = lazy_flush(err); if (rcf) return rcf; }
         double* d = nullptr;
         SNN_CUDA_OK(cudaMalloc(&d, p.E * sizeof(double)));
         wsd_to_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(p.wsdX[cur_], topo_.perm, d, p.E, field == SNN_FIELD_W ? 0 : 1);
@@ -1610,6 +1716,7 @@ class Engine : public IEngine {
       case SNN_FIELD_W: case SNN_FIELD_SD:
         if (!have_topo_) { err = "synapses not set"; return SNN_ERR_STATE; }
         if (count != p.E) { err = "count mismatch"; return SNN_ERR_INVALID; }
+        { const int rcf = lazy_flush(err); if (rcf) return rcf; }
         return upload_wsd(host, field == SNN_FIELD_W ? 0 : 1, 0, err);
       default: err = "field is not settable"; return SNN_ERR_INVALID;
     }
@@ -1764,6 +1871,7 @@ class Engine : public IEngine {
     DevNet<T>& p = p_;
     if (p.wsdX[1] != p.wsdX[0]) cudaFree(p.wsdX[1]);
     cudaFree(p.wsdX[0]); cudaFree(p.dlog); cudaFree(p.dsd); cudaFree(p.log_cnt); cudaFree(p.tile_done);
+    cudaFree(p.cacc); cudaFree(p.lzH); cudaFree(p.lzK);
     cudaFree(const_cast<uint32_t*>(p.inst_lo));
     p.wsd = p.wsdX[0] = p.wsdX[1] = nullptr; p.dlog = nullptr; p.dsd = nullptr; p.log_cnt = nullptr;
     p.tile_done = nullptr; p.inst_lo = p.inst_hi = nullptr; p.log_regions = p.log_region_cap = p.n_tiles = 0;
@@ -1844,6 +1952,19 @@ class Engine : public IEngine {
                                                            std::max<int64_t>(1, (int64_t)n_sm_ * 8 / p.B)));
     l.gL = dim3(gLx, p.B);
     return l;
+  }
+  // event-driven learning: learn step k (or, force = 1, materialise (w, sd) for the host)
+  void launch_lazy(const DevNet<T>& p, const Launch& g, cudaStream_t s, int k, int dl, int dd, int force) {
+    lazy_learn_kernel<T><<<g.gL, 256, 0, s>>>(p, d_ctx_, k, dl, dd, force);
+    lazy_commit_kernel<T><<<(p.B + 127) / 128, 128, 0, s>>>(p, d_ctx_, k, dl, dd, force);
+  }
+  int lazy_flush(std::string& err) {
+    if (!p_.lazy || !have_topo_ || p_.E == 0 || p_.Ne == 0) return SNN_OK;
+    DevNet<T> p = p_;
+    p.static_cur = cur_;
+    launch_lazy(p, grids(), stream_, 0, 0, 0, 1);
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    return SNN_OK;
   }
   bool wants_learn(const StepArgs& a, int k, int* do_learn, int* do_decay) const {
     const bool train = a.train_flags && a.train_flags[k];
@@ -1952,7 +2073,8 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
     if (prof) prof_end(s);
     if (learn) {
       if (prof) prof_begin(2, s);
-      learn_kernel<T><<<g.gL, 256, 0, s>>>(p, d_ctx_, k, dl, dd);
+      if (p.lazy) launch_lazy(p, g, s, k, dl, dd, 0);
+      else learn_kernel<T><<<g.gL, 256, 0, s>>>(p, d_ctx_, k, dl, dd);
       if (prof) prof_end(s);
       // the pushes of step k+1 must see the weights after learn!(k)
       if (push_next) synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s>>>(p, d_ctx_, k, g_arr_log2_);
@@ -1973,6 +2095,7 @@ void Engine<T>::launch_serial(const StepArgs& a, const std::vector<int32_t>& for
 // asynchronous learn pass (lowest priority): learn_replay, learn_ctl(begin), chunks, learn_ctl(all).
 template <typename T>
 bool Engine<T>::async_ok(const StepArgs& a) const {
+  if (p_.lazy) return false;  // event-driven learning: the (rare) dense pass runs in place
   if (!have_async_) return false;
   int last = -1000, n_learn = 0, dl, dd;
   for (int k = 0; k < a.n_steps; ++k) {
@@ -2115,7 +2238,8 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
       } else if (learn) {
         cudaStreamWaitEvent(s3, evS(k), 0);
         if (prof) prof_begin(2, s3, true);
-        learn_kernel<T><<<g.gL, 256, 0, s3>>>(p, d_ctx_, k, dl, dd);
+        if (p.lazy) launch_lazy(p, g, s3, k, dl, dd, 0);
+        else learn_kernel<T><<<g.gL, 256, 0, s3>>>(p, d_ctx_, k, dl, dd);
         if (prof) prof_end(s3, true);
         cudaEventRecord(evL, s3);
         if (push_next) {
@@ -2290,6 +2414,7 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   }
 
   // ---- the window
+  if (a.n_probes > 0 && p_.lazy) { err = "synapse probes are not available with event-driven learning"; return SNN_ERR_INVALID; }
   if (a.n_probes > 0) {  // per-step probes: plain launches, learn! in place (diagnostics path)
     if (a.n_probes > 4096 || !a.probe_syn || !a.probe_out) { err = "probes: 1..4096 synapse indices and an output buffer"; return SNN_ERR_INVALID; }
     for (int q = 0; q < a.n_probes; ++q)

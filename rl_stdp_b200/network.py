@@ -59,6 +59,10 @@ class SparseNetwork:
         exp_flags = int(params.pop("exp_flags", 0))
         learn_async = {"auto": 0, "off": 1, "force": 2}[params.pop("learn_async", "auto")]
         learn_log_cap = int(params.pop("learn_log_cap", 0))
+        # opt-in, production mode only: event-driven learning, one dense re-basing pass
+        # every `learn_lazy` learn steps (and at every learn step while da > learn_lazy_da, if given)
+        learn_lazy = int(params.pop("learn_lazy", 0))
+        learn_lazy_da = float(params.pop("learn_lazy_da", 0.0))
         learn_tile_k = int(params.pop("learn_tile_k", 0))
         learn_stages = int(params.pop("learn_stages", 0))
         side_blocks = int(params.pop("side_blocks", 0))
@@ -79,6 +83,9 @@ class SparseNetwork:
         cfg.reserved[7] = side_blocks    # 10*synapse + ltp blocks per SM (0 = default: occupancy limit / 4)
         cfg.reserved[5] = learn_log_cap  # total entries of the sd-update log (0 = by size)
         cfg.reserved[4] = learn_async    # 0 auto (large nets), 1 in-place pass only, 2 always asynchronous
+        if learn_lazy > 0:
+            cfg.reserved[4] = 16 + learn_lazy
+            cfg.reserved[5] = int(round(learn_lazy_da * 1000))
         self.cfg = cfg
         self.n_neurons = int(cfg.n_neurons)
         self.n_instances = int(n_instances)

@@ -194,8 +194,8 @@ def test_homeostasis_and_ge_threshold():
     assert sum(len(r) for r in ref) > 200
 
 
-@pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_fast_mode_statistics(dtype):
+@pytest.mark.parametrize("dtype,lazy", [("f64", 0), ("f32", 0), ("f32", 8)])
+def test_fast_mode_statistics(dtype, lazy):
     """Production mode (atomic scatter; fp32): the dynamics are chaotic, so parity is statistical
     (SURVEY §8d gates): mean rate within 2 %, exc/inh rates within 5 %, mean plastic weight within
     1 %, weight quantiles within 5e-3, and the early spike trains (before divergence) identical for fp64."""
@@ -210,7 +210,9 @@ def test_fast_mode_statistics(dtype):
     da_events = [(500, 0, 0.5), (1000, 0, 0.5)]
     ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax)
     ref = run_oracle_sparse(ora, noise, train, da_events)
-    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype=dtype, mode="fast", max_delay=dmax)
+    # lazy = 8: the experimental event-driven learning (dense re-basing pass every 8th learn step) must pass
+    # the same gates as the reference's rule
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype=dtype, mode="fast", max_delay=dmax, learn_lazy=lazy)
     spikes, stats = net.run(t, noise, train, da_events=da_events)
     nr = np.array([len(r) for r in ref], float)
     ng = np.array([len(s) for s in spikes], float)
@@ -384,6 +386,60 @@ def test_fast_async_learn_matches_oracle(log_cap, batched):
         assert np.abs(wg[sl] - wo).max() <= 1e-9
         assert np.abs(sg[sl][plastic] - so[plastic]).max() <= 1e-9 * max(1.0, np.abs(so).max())
         assert np.abs(wo[plastic] - 1.0).max() > 1e-3  # learning did move the weights
+
+
+@pytest.mark.parametrize("m,clamp,batched", [(1, True, False), (3, False, True), (8, False, False)])
+def test_event_driven_learning_algebra(m, clamp, batched):
+    """Experimental event-driven learning (snn_config.reserved[4] = 16 + M): between
+    dense re-basing passes the weight is s0 + H*sd' - C, formed when it is read.  Without the clamp that is
+    the reference's rule re-associated, so the fp64 production build must reproduce the oracle (spikes for
+    300 ms, weights and sd to 1e-9) for any M — here with the bounds moved out of reach (M = 3 batched with a
+    different dopamine history per instance, M = 8); with M = 1 every learn step re-bases and the real
+    bounds [0, 4] are exact too."""
+    from oracle import py_oracle as po
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    nper, ne, fan, dmax, t = 2500, 2000, 60, 8, 300
+    B = 4 if batched else 1
+    n = nper * B
+    rowptr, post, w, delay = synth.fixed_fanout(nper, ne, fan, dmax, seed=81, n_instances=B)
+    noise = synth.thalamic_noise(t, n, seed=13)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    da_events = [(55, b, 0.5 + 0.1 * b) for b in range(B)] + [(171, 0, 0.3)]
+    da_events.sort(key=lambda x: x[0])
+    bounds = {} if clamp else dict(wmin=-100.0, wmax=100.0)
+    oras, refs = [], []
+    for b in range(B):
+        sl = slice(rowptr[b * nper], rowptr[(b + 1) * nper])
+        rp = rowptr[b * nper:(b + 1) * nper + 1] - rowptr[b * nper]
+        o = po.Sparse(nper, ne, rp, post[sl] - b * nper, w[sl], delay[sl], max_delay=dmax, **bounds)
+        refs.append(run_oracle_sparse(o, noise[:, b * nper:(b + 1) * nper], train,
+                                      [(s, 0, a) for s, i, a in da_events if i == b]))
+        oras.append(o)
+    net = SparseNetwork(nper, ne, rowptr, post, w, delay, n_instances=B, dtype="f64", mode="fast", max_delay=dmax,
+                        learn_lazy=m, **bounds)
+    got = []
+    for lo in range(0, t, 100):
+        sp, _ = net.run(100, noise[lo:lo + 100], train[lo:lo + 100],
+                        da_events=[(s - lo, i, a) for s, i, a in da_events if lo <= s < lo + 100])
+        got += sp
+    for k in range(t):
+        want = np.concatenate([refs[b][k] + b * nper for b in range(B)])
+        assert np.array_equal(got[k], want), k
+    wg, sg = net.get(L.FIELD_W), net.get(L.FIELD_SD)
+    for b in range(B):
+        sl = slice(rowptr[b * nper], rowptr[(b + 1) * nper])
+        plastic = np.repeat(np.arange(nper), np.diff(rowptr[b * nper:(b + 1) * nper + 1])) < ne
+        wo, so = oras[b].get(4), oras[b].get(5)
+        assert np.abs(wg[sl] - wo).max() <= 1e-9
+        assert np.abs(sg[sl][plastic] - so[plastic]).max() <= 1e-9 * max(1.0, np.abs(so).max())
+        assert np.abs(wo[plastic] - 1.0).max() > 1e-3  # learning did move the weights
+    # a second read (another forced re-basing with H = 0, C = 0) must not change anything
+    assert np.array_equal(net.get(L.FIELD_W), wg) and np.array_equal(net.get(L.FIELD_SD), sg)
+    # and the run continues from the materialised state
+    sp, _ = net.run(20, noise[:20], train[:20])
+    assert len(sp) == 20
 
 
 def test_variant_e_layered_izhikevich_exact():
