@@ -1035,16 +1035,50 @@ lazy_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, i
     const int64_t lo = p.seg[(size_t)r0 * (p.Dmax + 1)];
     const int64_t hi = p.seg[(size_t)(r0 + p.Ne - 1) * (p.Dmax + 1) + p.Dmax];
     typename DevNet<T>::T2* w = wview(p).cur;
-    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < hi; e += nth) {
-      if (!p.plastic_ei && ((int64_t)p.post[e] - r0) >= p.Ne) continue;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x, tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    auto one = [&](int64_t e) {
       typename DevNet<T>::T2 ws = w[e];
       const T x = O::sub(O::add(ws.x, O::mul(Hn, ws.y)), p.cacc[e]);
       ws.x = x > p.wmax ? p.wmax : (x < p.wmin ? p.wmin : x);
       ws.y = O::mul(ws.y, Rn);
       w[e] = ws;
       p.cacc[e] = (T)0;
+    };
+    bool done = false;
+    if constexpr (sizeof(T) == 4) {
+      if (p.plastic_ei) {  // two synapses per 16-byte access, four accesses in flight (24 B per synapse in all)
+        done = true;
+        const int64_t lo2 = (lo + 1) & ~(int64_t)1, hi2 = hi & ~(int64_t)1;
+        if (tid == 0 && lo < lo2 && lo < hi) one(lo);
+        if (tid == 1 % nth && hi2 < hi && hi2 >= lo2) one(hi2);
+        if (hi2 > lo2) {
+          float4* __restrict__ q = reinterpret_cast<float4*>(w + lo2);
+          float2* __restrict__ c2 = reinterpret_cast<float2*>(p.cacc + lo2);
+          const int64_t n2 = (hi2 - lo2) >> 1;
+          const float H = (float)Hn, R = (float)Rn, wmin = (float)p.wmin, wmax = (float)p.wmax;
+          auto two = [&](float4 r, float2 c) {
+            float x0 = r.x + H * r.y - c.x, x1 = r.z + H * r.w - c.y;
+            x0 = x0 > wmax ? wmax : (x0 < wmin ? wmin : x0);
+            x1 = x1 > wmax ? wmax : (x1 < wmin ? wmin : x1);
+            return make_float4(x0, r.y * R, x1, r.w * R);
+          };
+          int64_t x = tid;
+          for (; x + 3 * nth < n2; x += 4 * nth) {
+            float4 r[4]; float2 c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { r[u] = q[x + u * nth]; c[u] = c2[x + u * nth]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { q[x + u * nth] = two(r[u], c[u]); c2[x + u * nth] = make_float2(0.f, 0.f); }
+          }
+          for (; x < n2; x += nth) { const float4 r = q[x]; const float2 c = c2[x]; q[x] = two(r, c); c2[x] = make_float2(0.f, 0.f); }
+        }
+      }
     }
+    if (!done)
+      for (int64_t e = lo + tid; e < hi; e += nth) {
+        if (!p.plastic_ei && ((int64_t)p.post[e] - r0) >= p.Ne) continue;
+        one(e);
+      }
   }
   tl_end(p.tl, 3, k);
 }

@@ -442,6 +442,34 @@ def test_event_driven_learning_algebra(m, clamp, batched):
     assert len(sp) == 20
 
 
+@pytest.mark.parametrize("graph", [True, False])
+def test_event_driven_learning_fp32_equals_reference_rule_without_clamp(graph):
+    """fp32 production build, two instances with an odd synapse count each (the vectorised re-basing kernel
+    then starts and ends on odd positions), bounds out of reach: event-driven learning with M = 3 and the
+    reference's rule differ by fp32 rounding only.  graph = False drives the plain-launch scheduler."""
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _lib()
+    nper, ne, fan, dmax, t, B = 2501, 2001, 61, 6, 120, 2
+    rowptr, post, w, delay = synth.fixed_fanout(nper, ne, fan, dmax, seed=83, n_instances=B)
+    assert (rowptr[nper] % 2) == 1
+    noise = synth.thalamic_noise(t, nper * B, seed=14)
+    train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
+    da_events = [(35, 0, 0.5), (35, 1, 0.2)]
+    out = []
+    for lazy in (0, 3):
+        net = SparseNetwork(nper, ne, rowptr, post, w, delay, n_instances=B, dtype="f32", mode="fast", max_delay=dmax,
+                            learn_lazy=lazy, graph=graph, wmin=-100.0, wmax=100.0)
+        sp, _ = net.run(t, noise, train, da_events=da_events)
+        out.append((sp, net.get(L.FIELD_W), net.get(L.FIELD_SD)))
+    (sp0, w0, sd0), (sp1, w1, sd1) = out
+    n0, n1 = sum(len(x) for x in sp0), sum(len(x) for x in sp1)
+    assert n0 > 300 and abs(n1 - n0) <= 0.01 * n0
+    assert np.abs(w0 - 1.0).max() > 1e-3          # learning moved the weights
+    assert np.abs(w1 - w0).max() < 5e-3 and np.abs(w1 - w0).mean() < 1e-5
+    assert np.abs(sd1 - sd0).max() < 5e-2 and np.abs(sd1 - sd0).mean() < 1e-4
+
+
 def test_variant_e_layered_izhikevich_exact():
     """Variant E (net_arch.jl:316-379): layered Izhikevich net with forced-spike and injected-current
     inputs, homeostasis beyond layer 1, lateral inhibition partners, `e += da*de` learning with an
