@@ -183,3 +183,40 @@ def binary_spikes(obs, cells_pos, cells_vel):
     """StateSpikeGrid.jl:6-30: ids of the grids with a node within one node_size of the state."""
     ids, _ = input_spikes(obs, cells_pos, cells_vel, reach=1.0)
     return ids
+
+
+# ---- DVS-style change encoder (Julia/Modules/DVS/StateSpikeDVSv2.jl) -------------------------------------
+# Third-party piece: Discretizers.jl `LinearDiscretizer` (unpinned in the reference).  Restated from its
+# published behaviour: nbins equal-width bins over [lo, hi], a value below / above the range falls into the
+# first / last bin, bin i covers [edge_i, edge_{i+1}) and the last bin includes its right edge.
+
+def lindisc(obs_low, obs_high, neurons=(200, 150, 100, 150)):
+    """lindisc :5-18: per observation component (lo, hi, nbins); velocities are binned over [-50, 50]."""
+    return [(float(obs_low[0]), float(obs_high[0]), int(neurons[0])), (-50.0, 50.0, int(neurons[1])),
+            (float(obs_low[2]), float(obs_high[2]), int(neurons[2])), (-50.0, 50.0, int(neurons[3]))]
+
+
+def _encode(disc, x):
+    lo, hi, n = disc
+    if x < lo:
+        return 1
+    if x >= hi:
+        return n
+    return min(n, int(math.floor((x - lo) / ((hi - lo) / n))) + 1)
+
+
+def dvs_spikes(obs, obs_pre, discs, neurons=(200, 150, 100, 150)):
+    """input_spikes :30-47: one spike per bin crossed between two observations — an 'up' population and a
+    'down' population of neurons[i] cells per component.  0-based ids, in the reference's push order."""
+    spikes = []
+    off = 0
+    for i in range(4):
+        a, b = _encode(discs[i], obs[i]), _encode(discs[i], obs_pre[i])
+        delta = a - b
+        for j in range(1, abs(delta) + 1):
+            if delta > 0:
+                spikes.append(a - j + 2 * off - 1)
+            else:
+                spikes.append(a + j + 2 * off + neurons[i] - 1)
+        off += neurons[i]
+    return np.array(spikes, np.int32)

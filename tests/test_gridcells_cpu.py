@@ -102,3 +102,27 @@ def test_hex_modules_over_the_state_box():
     first = [i for i in ids.tolist() if i < 4]
     second = [i - 4 for i in ids.tolist() if 4 <= i < 8]
     assert first == second
+
+
+def test_dvs_change_encoder():
+    discs = gc.lindisc([-4.8, -1e38, -0.418, -1e38], [4.8, 1e38, 0.418, 1e38])
+    assert discs[1] == (-50.0, 50.0, 150) and discs[0][2] == 200
+    same = gc.dvs_spikes(OBS, OBS, discs)
+    assert same.size == 0
+    # the cart moves right by three position bins (bin width 9.6 / 200 = 0.048): three 'up' cells of component 1
+    pre = list(OBS)
+    cur = list(OBS)
+    cur[0] = pre[0] + 3 * 0.048
+    up = gc.dvs_spikes(cur, pre, discs)
+    b = gc._encode(discs[0], cur[0])
+    assert up.tolist() == [b - 1 - 1, b - 2 - 1, b - 3 - 1]
+    down = gc.dvs_spikes(pre, cur, discs)
+    b0 = gc._encode(discs[0], pre[0])
+    assert down.tolist() == [b0 + 1 + 200 - 1, b0 + 2 + 200 - 1, b0 + 3 + 200 - 1]
+    # component offsets: 2 * (200), 2 * (200 + 150), ...
+    cur2 = list(OBS)
+    cur2[3] = OBS[3] + 100.0 / 150 * 1.5
+    ids = gc.dvs_spikes(cur2, OBS, discs)
+    assert ids.size >= 1 and np.all(ids >= 2 * (200 + 150 + 100)) and np.all(ids < 2 * (200 + 150 + 100) + 150)
+    # out-of-range values fall into the edge bins
+    assert gc._encode(discs[0], -100.0) == 1 and gc._encode(discs[0], 100.0) == 200
