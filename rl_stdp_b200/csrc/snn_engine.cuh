@@ -150,13 +150,15 @@ struct DevNet {
   int32_t static_cur;    // >= 0: no pass can be in flight while this launch runs and wsdX[static_cur] is
                          // current — kernels skip the LearnCtl load (in-place windows, exact mode)
   // event-driven ("lazy") learning, production mode, opt-in: between two
-  // re-basing passes wsd holds (s0, sd' = sd / r^k), cacc the accumulator C = sum_events d' * H[k_e]
-  // and the weight is s = clamp(s0 + H*sd' - C) with H = sum_j rate_j * r^(j-1) over the learn steps
-  // since the last re-basing; learn! touches no synapse except every `lazy`-th time (or while
-  // da > lazy_da), when a dense pass writes s0 = s, sd' = sd, C = 0.
+  // re-basing passes wsd holds the two accumulators (sd' = sd / r^k, C = sum_events d' * H[k_e]) —
+  // adjacent, so that one 8-byte vector reduction serves an STDP event — and cacc the base weight s0
+  // of EVERY synapse; the weight is s = clamp(s0 + H*sd' - C) with H = sum_j rate_j * r^(j-1) over the
+  // learn steps since the last re-basing; learn! touches no synapse except every `lazy`-th time (or
+  // while da > lazy_da), when a dense pass writes s0 = s, sd' = sd, C = 0.  The API layout (w, sd) is
+  // restored around snn_get_array / snn_set_array.
   int32_t lazy;          // 0 = off, else M = learn steps per re-basing pass
   T lazy_da;
-  T* cacc;               // [E]
+  T* cacc;               // [E] s0
   T *lzH, *lzR, *lzInv;  // [B] H, r^k, 1/r^k
   int32_t* lzK;          // [B] learn steps since the last re-basing
   const uint32_t *colptr, *col_npl, *in_syn, *in_pre;
@@ -270,20 +272,23 @@ template <typename T>
 __device__ __forceinline__ typename Real2<T>::type w_fetch(const WView<T>& vw, uint32_t e, bool row_exc, bool& fly) {
   fly = row_exc && (vw.lazy || (e >> 5) >= vw.front);
   typename Real2<T>::type ws;
-  if (fly) ws = __ldcg((vw.lazy ? (const typename Real2<T>::type*)vw.cur : vw.old) + e);
+  if (vw.lazy) {  // (sd', C) of a possibly plastic synapse; the base weight comes from c_fetch
+    if (fly) ws = __ldcg(vw.cur + e);
+    else { ws.x = (T)0; ws.y = (T)0; }
+  } else if (fly) ws = __ldcg(vw.old + e);
   else { ws.x = ldcg_x(vw.cur + e); ws.y = (T)0; }
   return ws;
 }
-// event-driven learning: the C accumulator of a possibly plastic synapse (issued with w_fetch)
+// event-driven learning: the base weight s0 (issued together with w_fetch)
 template <typename T>
 __device__ __forceinline__ T c_fetch(const DevNet<T>& p, const WView<T>& vw, uint32_t e, bool fly) {
-  return (vw.lazy && fly) ? __ldcg(p.cacc + e) : (T)0;
+  return vw.lazy ? __ldcg(p.cacc + e) : (T)0;
 }
 template <typename T>
 __device__ __forceinline__ T w_resolve(const DevNet<T>& p, const typename Real2<T>::type& ws, bool fly, bool plastic,
                                        uint32_t inst, T c) {
-  if (!(fly && plastic)) return ws.x;  // non-plastic weights never change: both buffers hold them
-  const T x = p.lazy ? Ops<T>::sub(Ops<T>::add(ws.x, Ops<T>::mul(p.lzH[inst], ws.y)), c)
+  if (!(fly && plastic)) return p.lazy ? c : ws.x;  // non-plastic weights never change: both buffers hold them
+  const T x = p.lazy ? Ops<T>::sub(Ops<T>::add(c, Ops<T>::mul(p.lzH[inst], ws.x)), ws.y)
                      : Ops<T>::add(ws.x, Ops<T>::mul(p.lg[inst], ws.y));
   return x > p.wmax ? p.wmax : (x < p.wmin ? p.wmin : x);
 }
@@ -293,10 +298,15 @@ __device__ __forceinline__ T w_resolve(const DevNet<T>& p, const typename Real2<
 template <typename T>
 __device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, uint32_t e, T delta, uint32_t region,
                                        uint32_t inst) {
-  if (vw.lazy) {  // two fire-and-forget reductions: sd' += d', C += d' * H
+  if (vw.lazy) {  // sd' += d', C += d' * H: one fire-and-forget 8-byte vector reduction in fp32
     const T d = Ops<T>::mul(delta, p.lzInv[inst]);
-    atomicAdd(&vw.cur[e].y, d);
-    atomicAdd(&p.cacc[e], Ops<T>::mul(d, p.lzH[inst]));
+    const T dh = Ops<T>::mul(d, p.lzH[inst]);
+    if constexpr (sizeof(T) == 4) {
+      asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(vw.cur + e), "f"(d), "f"(dh) : "memory");
+    } else {
+      atomicAdd(&vw.cur[e].x, d);
+      atomicAdd(&vw.cur[e].y, dh);
+    }
     return;
   }
   if ((e >> 5) < vw.front) {
@@ -1037,12 +1047,12 @@ lazy_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, i
     typename DevNet<T>::T2* w = wview(p).cur;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x, tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     auto one = [&](int64_t e) {
-      typename DevNet<T>::T2 ws = w[e];
-      const T x = O::sub(O::add(ws.x, O::mul(Hn, ws.y)), p.cacc[e]);
-      ws.x = x > p.wmax ? p.wmax : (x < p.wmin ? p.wmin : x);
-      ws.y = O::mul(ws.y, Rn);
-      w[e] = ws;
-      p.cacc[e] = (T)0;
+      typename DevNet<T>::T2 ac = w[e];  // (sd', C)
+      const T x = O::sub(O::add(p.cacc[e], O::mul(Hn, ac.x)), ac.y);
+      p.cacc[e] = x > p.wmax ? p.wmax : (x < p.wmin ? p.wmin : x);
+      ac.x = O::mul(ac.x, Rn);
+      ac.y = (T)0;
+      w[e] = ac;
     };
     bool done = false;
     if constexpr (sizeof(T) == 4) {
@@ -1056,11 +1066,12 @@ lazy_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, i
           float2* __restrict__ c2 = reinterpret_cast<float2*>(p.cacc + lo2);
           const int64_t n2 = (hi2 - lo2) >> 1;
           const float H = (float)Hn, R = (float)Rn, wmin = (float)p.wmin, wmax = (float)p.wmax;
+          // r = (sd'0, C0, sd'1, C1), c = (s0_0, s0_1)
           auto two = [&](float4 r, float2 c) {
-            float x0 = r.x + H * r.y - c.x, x1 = r.z + H * r.w - c.y;
+            float x0 = c.x + H * r.x - r.y, x1 = c.y + H * r.z - r.w;
             x0 = x0 > wmax ? wmax : (x0 < wmin ? wmin : x0);
             x1 = x1 > wmax ? wmax : (x1 < wmin ? wmin : x1);
-            return make_float4(x0, r.y * R, x1, r.w * R);
+            return make_float2(x0, x1);
           };
           int64_t x = tid;
           for (; x + 3 * nth < n2; x += 4 * nth) {
@@ -1068,9 +1079,16 @@ lazy_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, i
 #pragma unroll
             for (int u = 0; u < 4; ++u) { r[u] = q[x + u * nth]; c[u] = c2[x + u * nth]; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { q[x + u * nth] = two(r[u], c[u]); c2[x + u * nth] = make_float2(0.f, 0.f); }
+            for (int u = 0; u < 4; ++u) {
+              c2[x + u * nth] = two(r[u], c[u]);
+              q[x + u * nth] = make_float4(r[u].x * R, 0.f, r[u].z * R, 0.f);
+            }
           }
-          for (; x < n2; x += nth) { const float4 r = q[x]; const float2 c = c2[x]; q[x] = two(r, c); c2[x] = make_float2(0.f, 0.f); }
+          for (; x < n2; x += nth) {
+            const float4 r = q[x]; const float2 c = c2[x];
+            c2[x] = two(r, c);
+            q[x] = make_float4(r.x * R, 0.f, r.z * R, 0.f);
+          }
         }
       }
     }
@@ -1081,6 +1099,16 @@ lazy_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, i
       }
   }
   tl_end(p.tl, 3, k);
+}
+// API layout (w, sd) <-> event-driven layout (wsd = (sd', C = 0), cacc = s0); only right after a re-basing
+template <typename T>
+__global__ void lazy_layout_kernel(typename Real2<T>::type* __restrict__ wsd, T* __restrict__ cacc, int64_t E, int to_lazy) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    typename Real2<T>::type a = wsd[e];
+    if (to_lazy) { cacc[e] = a.x; a.x = a.y; a.y = (T)0; }
+    else { a.y = a.x; a.x = cacc[e]; }
+    wsd[e] = a;
+  }
 }
 template <typename T>
 __global__ void lazy_commit_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int do_learn, int do_decay,
@@ -1684,7 +1712,10 @@ class Engine : public IEngine {
       SNN_CUDA_OK(cudaMemcpyAsync(d_lohi + p.B, inst_hi_.data(), (size_t)p.B * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
       p.inst_lo = d_lohi; p.inst_hi = d_lohi + p.B;
     }
+    lazy_layout_ = false;
     int rc = upload_wsd(h_w, 0, 1, err);
+    if (rc) return rc;
+    rc = lazy_from_api(err);  // event-driven learning keeps its own layout between API calls
     if (rc) return rc;
     // lanes per work item from the mean item length
     const double mean_row = p.N ? (double)p.E / (double)p.N : 0.0;
@@ -1715,13 +1746,14 @@ class Engine : public IEngine {
         if (!have_topo_) { err = "synapses not set"; return SNN_ERR_STATE; }
         if (count != p.E) { err = "count mismatch"; return SNN_ERR_INVALID; }
         if (p.E == 0) return SNN_OK;
-        { const int rcf = lazy_flush(err); if (rcf) return rcf; }
+        { const int rcf = lazy_to_api(err); if (rcf) return rcf; }
         double* d = nullptr;
         SNN_CUDA_OK(cudaMalloc(&d, p.E * sizeof(double)));
         wsd_to_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(p.wsdX[cur_], topo_.perm, d, p.E, field == SNN_FIELD_W ? 0 : 1);
         cudaError_t e = cudaMemcpyAsync(host, d, p.E * sizeof(double), cudaMemcpyDeviceToHost, stream_);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
         cudaFree(d);
+        { const int rcf = lazy_from_api(err); if (rcf) return rcf; }
         if (e != cudaSuccess) { err = cudaGetErrorString(e); return SNN_ERR_CUDA; }
         return SNN_OK;
       }
@@ -1750,8 +1782,13 @@ class Engine : public IEngine {
       case SNN_FIELD_W: case SNN_FIELD_SD:
         if (!have_topo_) { err = "synapses not set"; return SNN_ERR_STATE; }
         if (count != p.E) { err = "count mismatch"; return SNN_ERR_INVALID; }
-        { const int rcf = lazy_flush(err); if (rcf) return rcf; }
-        return upload_wsd(host, field == SNN_FIELD_W ? 0 : 1, 0, err);
+        {
+          int rcf = lazy_to_api(err);
+          if (rcf) return rcf;
+          rcf = upload_wsd(host, field == SNN_FIELD_W ? 0 : 1, 0, err);
+          if (rcf) return rcf;
+          return lazy_from_api(err);
+        }
       default: err = "field is not settable"; return SNN_ERR_INVALID;
     }
     if (count != n) { err = "count mismatch"; return SNN_ERR_INVALID; }
@@ -1992,12 +2029,22 @@ class Engine : public IEngine {
     lazy_learn_kernel<T><<<g.gL, 256, 0, s>>>(p, d_ctx_, k, dl, dd, force);
     lazy_commit_kernel<T><<<(p.B + 127) / 128, 128, 0, s>>>(p, d_ctx_, k, dl, dd, force);
   }
-  int lazy_flush(std::string& err) {
-    if (!p_.lazy || !have_topo_ || p_.E == 0 || p_.Ne == 0) return SNN_OK;
+  // materialise and switch wsdX[cur_] to the API layout (w, sd) / back to the event-driven layout
+  int lazy_to_api(std::string& err) {
+    if (!p_.lazy || !lazy_layout_) return SNN_OK;
     DevNet<T> p = p_;
     p.static_cur = cur_;
     launch_lazy(p, grids(), stream_, 0, 0, 0, 1);
+    lazy_layout_kernel<T><<<grid_for(p.E), 256, 0, stream_>>>(p.wsdX[cur_], p.cacc, p.E, 0);
     SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    lazy_layout_ = false;
+    return SNN_OK;
+  }
+  int lazy_from_api(std::string& err) {
+    if (!p_.lazy || lazy_layout_ || p_.E == 0) return SNN_OK;
+    lazy_layout_kernel<T><<<grid_for(p_.E), 256, 0, stream_>>>(p_.wsdX[cur_], p_.cacc, p_.E, 1);
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    lazy_layout_ = true;
     return SNN_OK;
   }
   bool wants_learn(const StepArgs& a, int k, int* do_learn, int* do_decay) const {
@@ -2017,6 +2064,7 @@ class Engine : public IEngine {
   DevNet<T> p_;
   Topo topo_;
   bool have_topo_ = false, use_graph_ = true;
+  bool lazy_layout_ = false;  // wsdX[cur_] / cacc hold the event-driven layout (DevNet::lazy)
   int profiling_ = 0;
   int64_t t_ = 0;
   int n_sm_ = 148, g_arr_log2_ = 5, g_ltp_log2_ = 5, gA_ = 0;
