@@ -116,7 +116,8 @@ typedef struct snn_config {
                                   (SNN_MODE_FAST only; an approximation of the reference's rule: the
                                   clamp wmin <= w <= wmax is applied when a weight is read and at a
                                   dense re-basing pass every M learn steps instead of at every learn
-                                  step; M = 1 is the reference's rule.  DESIGN.md section 11.1)
+                                  step; M = 1 is the reference's rule; not with snn_set_partition or synapse probes.
+                                  DESIGN.md section 11.1)
                               [5] asynchronous learn pass: total entries of the sd-update log; with
                                   [4] >= 16: re-base at every learn step while da > [5]/1000 (0 = never) */
 } snn_config;

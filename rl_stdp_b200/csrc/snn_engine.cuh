@@ -1828,6 +1828,9 @@ class Engine : public IEngine {
     if (p_.B != 1) { err = "neuron partitioning applies to a single network instance"; return SNN_ERR_INVALID; }
     const bool whole = lo == 0 && hi == p_.N;
     if (t_ != 0) { err = "set the partition before the first step"; return SNN_ERR_STATE; }
+    if (!whole && (p_.lazy || cfg_.reserved[4] >= 16)) {
+      err = "event-driven learning (reserved[4] >= 16) has not been validated on neuron-partitioned runs"; return SNN_ERR_INVALID;
+    }
     drop_graph();
     p_.part_lo = lo; p_.part_hi = hi;
     exchange_ = whole ? nullptr : fn; exchange_user_ = user;
