@@ -26,12 +26,13 @@ PARAM_ORDER = [
     "threshold_ge", "vthresh", "v_reset", "a_exc", "a_inh", "d_exc", "d_inh", "trace_set",
     "trace_decay", "apost", "apre", "da_decay", "learn_base", "eta", "wmin", "wmax", "sd_decay",
     "sd_decay_mode", "rate_mode", "plastic_ei", "theta", "ttheta", "ho_from", "ho_inh", "variant_g",
+    "lazy", "lazy_da",   # event-driven learning of the production build (0 = the reference's rule)
 ]
 VARIANT_A = dict(
     threshold_ge=0, vthresh=30.0, v_reset=-65.0, a_exc=0.02, a_inh=0.1, d_exc=8.0, d_inh=2.0,
     trace_set=0.1, trace_decay=0.95, apost=1.0, apre=1.5, da_decay=0.995, learn_base=0.002,
     eta=0.0, wmin=0.0, wmax=4.0, sd_decay=0.99, sd_decay_mode=0, rate_mode=0, plastic_ei=1,
-    theta=0.0, ttheta=1.0, ho_from=0, ho_inh=0, variant_g=0,
+    theta=0.0, ttheta=1.0, ho_from=0, ho_inh=0, variant_g=0, lazy=0, lazy_da=0.0,
 )
 LAY_PARAM_ORDER = [
     "vthresh", "c", "ae", "ai", "de", "di", "wei", "wie", "wmax", "theta", "ttheta", "imin", "imax",

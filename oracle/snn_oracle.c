@@ -203,6 +203,11 @@ typedef struct {
   double* da;      /* per instance */
   int64_t t;       /* absolute step counter */
   int64_t n_syn_events, n_ltp_events;
+  /* event-driven learning of the production build (snn_config.reserved[4] = 16 + M),
+   * restated so that that path has a checker WITH the clamp: w holds s0, sd holds sd' = sd / r^k,
+   * cacc the accumulator C; per instance H, r^k, 1/r^k and the learn steps since the last re-basing */
+  int32_t lazy; double lazy_da;
+  double *cacc, *lzH, *lzR, *lzInv; int32_t* lzK;
 } ora_sparse;
 
 typedef struct { int64_t key; int64_t e; } ora_sortrec;
@@ -227,6 +232,7 @@ ora_sparse* ora_sparse_create(int64_t N, int64_t Nper, int64_t Ne, int32_t Dmax,
   o->sd_decay = p[16]; o->sd_decay_mode = (int32_t)p[17]; o->rate_mode = (int32_t)p[18];
   o->plastic_ei = (int32_t)p[19]; o->theta = p[20]; o->ttheta = p[21]; o->ho_from = (int64_t)p[22];
   o->ho_inh = (int32_t)p[23]; o->variant_g = (int32_t)p[24];
+  o->lazy = (int32_t)p[25]; o->lazy_da = p[26] > 0 ? p[26] : 1e30;
   o->rowptr = (int64_t*)malloc((N + 1) * sizeof(int64_t));
   memcpy(o->rowptr, rowptr, (N + 1) * sizeof(int64_t));
   o->post = (int32_t*)malloc((E + 1) * sizeof(int32_t));
@@ -267,18 +273,49 @@ ora_sparse* ora_sparse_create(int64_t N, int64_t Nper, int64_t Ne, int32_t Dmax,
   o->da = (double*)calloc(N / Nper, sizeof(double));
   for (int64_t j = 0; j < N; ++j) { o->v[j] = o->v_reset; o->u[j] = 0.2 * o->v[j]; }
   o->t = 0;
+  if (o->lazy) {
+    const int64_t B = N / Nper;
+    o->cacc = (double*)calloc(E + 1, sizeof(double));
+    o->lzH = (double*)calloc(B, sizeof(double));
+    o->lzR = (double*)malloc(B * sizeof(double));
+    o->lzInv = (double*)malloc(B * sizeof(double));
+    o->lzK = (int32_t*)calloc(B, sizeof(int32_t));
+    for (int64_t b = 0; b < B; ++b) o->lzR[b] = o->lzInv[b] = 1.0;
+  }
   return o;
+}
+/* weight of synapse e as the event-driven build delivers it */
+static double ora_lazy_w(const ora_sparse* o, int64_t e) {
+  if (!o->lazy || !o->plastic[e]) return o->w[e];
+  return clampd((o->w[e] + o->lzH[o->pre[e] / o->Nper] * o->sd[e]) - o->cacc[e], o->wmin, o->wmax);
+}
+/* re-basing pass of instance b with the advanced (H, r^k): s0 = clamp(s0 + H*sd' - C), sd' *= r^k, C = 0 */
+static void ora_lazy_rebase(ora_sparse* o, int64_t b, double H, double Rk) {
+  for (int64_t e = 0; e < o->E; ++e) {
+    if (!o->plastic[e] || o->pre[e] / o->Nper != b) continue;
+    o->w[e] = clampd((o->w[e] + H * o->sd[e]) - o->cacc[e], o->wmin, o->wmax);
+    o->sd[e] = o->sd[e] * Rk;
+    o->cacc[e] = 0.0;
+  }
+  o->lzH[b] = 0.0; o->lzR[b] = 1.0; o->lzInv[b] = 1.0; o->lzK[b] = 0;
+}
+/* what snn_get_array / snn_set_array do first in that mode: materialise (w, sd) */
+void ora_sparse_lazy_flush(ora_sparse* o) {
+  if (!o->lazy) return;
+  for (int64_t b = 0; b < o->N / o->Nper; ++b) ora_lazy_rebase(o, b, o->lzH[b], o->lzR[b]);
 }
 void ora_sparse_destroy(ora_sparse* o) {
   if (!o) return;
   free(o->rowptr); free(o->post); free(o->pre); free(o->delay); free(o->w); free(o->sd);
   free(o->plastic); free(o->colptr); free(o->in_syn); free(o->v); free(o->u); free(o->ho);
-  free(o->I); free(o->trace); free(o->spk); free(o->da); free(o);
+  free(o->I); free(o->trace); free(o->spk); free(o->da);
+  free(o->cacc); free(o->lzH); free(o->lzR); free(o->lzInv); free(o->lzK); free(o);
 }
 /* field ids follow include/snn_b200.h SNN_FIELD_*; trace returns the post-decay value the
  * reference holds between calls (new_net.jl:130). */
 void ora_sparse_get(ora_sparse* o, int which, double* out) {
   const int64_t N = o->N;
+  if (which == 4 || which == 5) ora_sparse_lazy_flush(o);
   switch (which) {
     case 0: memcpy(out, o->v, N * sizeof(double)); break;
     case 1: memcpy(out, o->u, N * sizeof(double)); break;
@@ -296,6 +333,7 @@ void ora_sparse_get(ora_sparse* o, int which, double* out) {
 }
 void ora_sparse_set(ora_sparse* o, int which, const double* in) {
   const int64_t N = o->N;
+  if (which == 4 || which == 5) ora_sparse_lazy_flush(o);
   switch (which) {
     case 0: memcpy(o->v, in, N * sizeof(double)); break;
     case 1: memcpy(o->u, in, N * sizeof(double)); break;
@@ -362,7 +400,7 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
       int64_t e = o->in_syn[q];
       int64_t ts = t - (o->delay[e] - 1);
       if (ts < 0) continue;
-      if (o->spk[(size_t)(ts % R) * N + o->pre[e]]) { acc += o->w[e]; n_ev++; }
+      if (o->spk[(size_t)(ts % R) * N + o->pre[e]]) { acc += ora_lazy_w(o, e); n_ev++; }
     }
     o->I[j] = acc;
   }
@@ -390,6 +428,12 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
     double pre_tr = tsp >= 0 ? o->trace[(size_t)(tsp % R) * N + i] : 0.0;
     double up = o->apost * pre_tr;
     double dn = o->apre * tr[j];
+    if (o->lazy) { /* the two additive accumulators; LTP and LTD are separate (unordered) reductions there */
+      const int64_t b = i / Nper;
+      if (ltp) { double d = up * o->lzInv[b]; o->sd[e] += d; o->cacc[e] += d * o->lzH[b]; }
+      if (ltd) { double d = (-dn) * o->lzInv[b]; o->sd[e] += d; o->cacc[e] += d * o->lzH[b]; }
+      continue;
+    }
     double x = o->sd[e];
     if (ltd && ltp) x = (o->variant_g || j <= i) ? (x + up) - dn : (x - dn) + up;
     else if (ltp) x = x + up;
@@ -399,11 +443,22 @@ int64_t ora_sparse_step(ora_sparse* o, const double* noise, const int32_t* force
   o->n_ltp_events += n_ltp;
   for (int64_t b = 0; b < N / Nper; ++b) o->da[b] *= o->da_decay;
   for (int64_t j = 0; j < N; ++j) o->ho[j] *= o->ttheta; /* net_res.jl:204 */
-  if (o->sd_decay_mode == 1) {
+  if (o->sd_decay_mode == 1 && !o->lazy) {
     #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < o->E; ++e) if (o->plastic[e]) o->sd[e] *= o->sd_decay;
   }
-  if (train) {
+  if (o->lazy && (train || o->sd_decay_mode == 1)) {
+    /* lazy_learn_kernel / lazy_commit_kernel: advance (H, r^k), re-base every M-th learn step or while da is high */
+    for (int64_t b = 0; b < N / Nper; ++b) {
+      double da = o->da[b];
+      double g = o->rate_mode == 0 ? (o->learn_base + da) : (o->rate_mode == 1 ? da : o->eta * da);
+      double Hn = train ? o->lzH[b] + g * o->lzR[b] : o->lzH[b];
+      double Rn = (o->sd_decay_mode == 1 || (train && o->sd_decay_mode == 0)) ? o->lzR[b] * o->sd_decay : o->lzR[b];
+      int Kn = o->lzK[b] + (train ? 1 : 0);
+      if (Kn >= o->lazy || (train && da > o->lazy_da)) ora_lazy_rebase(o, b, Hn, Rn);
+      else { o->lzH[b] = Hn; o->lzR[b] = Rn; o->lzInv[b] = 1.0 / Rn; o->lzK[b] = Kn; }
+    }
+  } else if (train) {
     #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < o->E; ++e) {
       if (!o->plastic[e]) continue;
