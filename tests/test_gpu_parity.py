@@ -442,8 +442,6 @@ def test_event_driven_learning_algebra(m, clamp, batched):
     assert len(sp) == 20
 
 
-@pytest.mark.skipif(__import__("os").environ.get("SNN_LAZY_CLAMP_TEST") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on a B200 (set SNN_LAZY_CLAMP_TEST=1)")
 def test_event_driven_learning_with_clamps_matches_lazy_oracle():
     """With the real bounds [0, 4] the event-driven build is an approximation of the reference's rule, so its
     checker is the oracle's own event-driven mode (oracle/snn_oracle.c `lazy`, pinned on the CPU against the
