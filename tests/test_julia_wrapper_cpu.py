@@ -46,3 +46,40 @@ def test_every_ccall_symbol_is_declared():
     called = set(re.findall(r"ccall\(\(:(\w+), LIB\)", src))
     assert called and called <= declared, called - declared
     assert {"snn_create", "snn_step", "snn_actor_episodes_env", "snn_partition_connect"} <= called
+
+
+def _split_top(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "{(":
+            depth += 1
+        elif ch in "})":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_ccall_signatures_have_the_prototypes_arity_and_pointer_shape():
+    src = open(os.path.join(ROOT, "julia", "RLSTDPB200.jl")).read()
+    hdr = " ".join(_strip_comments(open(os.path.join(ROOT, "include", "snn_b200.h")).read()).split())
+    protos = {m.group(1): _split_top(m.group(2)) for m in re.finditer(r"\b(snn_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", hdr)}
+    n = 0
+    for m in re.finditer(r"ccall\(\(:(\w+), LIB\),\s*(\w+),\s*\(([^()]*)\)", src):
+        name, ret, types = m.group(1), m.group(2), _split_top(m.group(3))
+        cargs = [a for a in protos[name] if a != "void"]
+        assert len(types) == len(cargs), (name, types, cargs)
+        for jt, ca in zip(types, cargs):
+            is_ptr_c = "*" in ca or ca.startswith("snn_exchange_fn")   # a function-pointer typedef
+            is_ptr_j = jt.startswith(("Ptr{", "Ref{")) or jt == "Cstring"
+            assert is_ptr_c == is_ptr_j, (name, jt, ca)
+            if not is_ptr_c:
+                assert CTYPE[ca.split()[0]] == jt, (name, jt, ca)
+        assert ret in ("Int32", "Cstring", "Int64"), (name, ret)
+        n += 1
+    assert n >= 15
