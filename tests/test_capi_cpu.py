@@ -104,3 +104,23 @@ def test_yaml_param_files_map_to_configs(tmp_path):
     bad.write_text("apost: 1.0\n")
     with pytest.raises(KeyError):
         params.izhikevich_config(params.load_params(str(bad)), layered=False)
+
+
+def test_ctypes_signatures_match_the_prototypes():
+    """rl_stdp_b200/_lib.py SYMBOLS against include/snn_b200.h: every declared function is bound, with the
+    prototype's number of arguments, pointers where the prototype has pointers and the right scalar widths."""
+    import ctypes as C
+    from rl_stdp_b200 import _lib as L
+    hdr = " ".join(re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "snn_b200.h")).read(), flags=re.S).split())
+    protos = {m.group(1): [a.strip() for a in m.group(2).split(",") if a.strip() != "void"]
+              for m in re.finditer(r"\b(snn_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", hdr)}
+    assert set(protos) == set(L.SYMBOLS), set(protos) ^ set(L.SYMBOLS)
+    scalar = {"int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double, "uint64_t": C.c_uint64}
+    for name, (ret, args) in L.SYMBOLS.items():
+        cargs = protos[name]
+        assert len(args) == len(cargs), (name, len(args), cargs)
+        for at, ca in zip(args, cargs):
+            if "*" in ca or ca.startswith("snn_exchange_fn"):
+                assert at is L._VP or hasattr(at, "contents") or issubclass(at, (C._Pointer, C._CFuncPtr, C.c_char_p)), (name, ca, at)
+            else:
+                assert at is scalar[ca.split()[0]], (name, ca, at)
