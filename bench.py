@@ -79,11 +79,16 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi sampled every 20 ms from before the warm-up; only the samples whose timestamp falls
+    inside [mark_begin(), mark_end()] — the timed region — are reported (a sampler started at the timed
+    region's first instant delivers its first line only after nvidia-smi has started up, which in a
+    multi-rank run was after the region had ended)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.path = index, None, f"/tmp/bench_clocks_{os.getpid()}.csv"
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -93,31 +98,57 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _ts(txt):
+        import datetime
+        try:
+            return datetime.datetime.strptime(txt.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
+        if self.t1 is not None:  # let the sampler deliver the lines of the region's last instants
+            time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, reasons, mx = [], set(), None
+        rows, mx = [], None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 7:
+                if len(f) < 8:
                     continue
-                sm.append(float(f[0])); mx = float(f[1])
-                for nme, val in zip(names, f[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nme)
+                try:
+                    rows.append((self._ts(f[0]), float(f[1]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
             os.remove(self.path)
         except Exception:
             pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t1 is not None
+                  and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        scope = "timed region"
+        if not inside and rows and self.t0 is not None:
+            # a region shorter than the sampling period: the nearest samples on either side of it
+            rows_t = [r for r in rows if r[0] is not None]
+            rows_t.sort(key=lambda r: abs(r[0] - 0.5 * (self.t0 + (self.t1 or self.t0))))
+            inside, scope = rows_t[:3], "nearest samples around the timed region"
+        if inside:
+            out = {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": mx,
+                   "reasons": sorted({n for r in inside for n in r[2]}), "samples": len(inside), "scope": scope}
         return out
 
 
@@ -129,11 +160,47 @@ def window_inputs(k_window: int, window_ms: int):
     return train, da
 
 
+def bench_config(args, world, partitioned=False):
+    """`config` of the JSON line — ONE function for the product arm and the reference arm, so that the
+    driver's same-config check compares like with like."""
+    wl = WORKLOADS[args.workload]
+    n, ne, fan, dmax = wl[:4]
+    n_inst = wl[4] if len(wl) > 4 else 1
+    cfg = {"workload": args.workload, "neurons": n * n_inst, "synapses": n * n_inst * fan, "max_delay_ms": dmax,
+           "instances_per_gpu": n_inst, "window_ms_per_step": args.window_ms, "learn_period_ms": LEARN_PERIOD,
+           "noise": "Philox4x32-10 keyed by (seed, step, neuron): the device generates it in the neuron kernel, the CPU arm replays the same stream",
+           "topology": "clustered (20 blocks, 80 % of the targets inside the own block)" if args.workload.startswith("c3")
+                       else "uniform fixed fan-out",
+           "instances": 1 if partitioned else world,
+           "sharding": ("one network, neurons partitioned over the ranks; per ms the spike bitmap is exchanged "
+                        + ("by NCCL all-gather from a host callback" if args.partition == "nccl" else
+                           "by peer stores over NVLink + device-side wait")) if partitioned
+                       else "one independent instance per GPU, no collective",
+           "l2": "working set ~4 GB per instance >> 126 MB L2 (no flush needed)"}
+    if getattr(args, "learn_lazy", 0):
+        cfg["learn_rule"] = f"EXPERIMENTAL event-driven, re-basing every {args.learn_lazy} learn steps (approximates the clamp)"
+    return cfg
+
+
+def synth_workload(args, seed, n_instances=None):
+    from rl_stdp_b200 import synth
+    wl = WORKLOADS[args.workload]
+    n, ne, fan, dmax = wl[:4]
+    n_inst = (wl[4] if len(wl) > 4 else 1) if n_instances is None else n_instances
+    if args.workload.startswith("c3"):  # MatrixCluster: block-clustered topology (SURVEY 8d C3)
+        parts = [synth.clustered(n, ne, fan, 20, 0.8, seed=seed + 1000 * b) for b in range(n_inst)]
+        rowptr = np.arange(n * n_inst + 1, dtype=np.int64) * fan
+        post = np.concatenate([p[1] + b * n for b, p in enumerate(parts)]).astype(np.int32)
+        w = np.concatenate([p[2] for p in parts]); delay = np.concatenate([p[3] for p in parts])
+        return rowptr, post, w, delay
+    return synth.fixed_fanout(n, ne, fan, dmax, seed=seed, n_instances=n_inst)
+
+
 def run_b200(args):
+    import hashlib
     import torch
     import torch.distributed as dist
     from rl_stdp_b200 import _lib as L
-    from rl_stdp_b200 import synth
     from rl_stdp_b200.network import SparseNetwork
 
     rank = int(os.environ.get("RANK", "0"))
@@ -148,32 +215,17 @@ def run_b200(args):
     n, ne, fan, dmax = wl[:4]
     n_inst = wl[4] if len(wl) > 4 else 1
     W = args.window_ms
-    t_build = time.perf_counter()
-    if args.partition and world > 1:
-        # ONE network, neuron-partitioned over the ranks, spike bitmap all-gathered per ms (NCCL)
-        from rl_stdp_b200.partition import PartitionedRank, TorchDistExchange, connect_dist, plan
-        rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9)
-        lo, hi = plan(n, world)[rank]
-        cb = TorchDistExchange().callback() if args.partition == "nccl" else None
-        net = PartitionedRank(n, ne, rowptr, post, w, delay, lo, hi, cb, dtype="f32",
-                              mode="fast", noise="philox", device=local, max_delay=dmax, noise_seed=10,
-                              learn_async=args.learn_async)
-        if cb is None:
-            connect_dist(net)  # in-library exchange: peer stores over NVLink, device-side wait
-        n_plastic = int(np.count_nonzero(np.repeat(np.arange(n), np.diff(rowptr))[net.local_index] < ne))
-    else:
-        rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9 + rank, n_instances=n_inst)
-        net = SparseNetwork(n, ne, rowptr, post, w, delay, n_instances=n_inst, dtype="f32", mode="fast", noise="philox",
-                            device=local, max_delay=dmax, noise_seed=10 + rank, exp_flags=args.exp_flags,
-                            graph=not args.no_graph, learn_async=args.learn_async, learn_blocks=args.learn_blocks, learn_tile_k=args.learn_tile_k, learn_stages=args.learn_stages, side_blocks=args.side_blocks,
-                            learn_lazy=args.learn_lazy, learn_lazy_da=args.learn_lazy_da)
-        n_plastic = int(rowptr[ne]) * n_inst
-    del post, w, delay
-    t_build = time.perf_counter() - t_build
     lib = L.load()
     stream = torch.cuda.Stream()  # the library launches on this stream, so torch events bracket its kernels
     torch.cuda.set_stream(stream)
-    lib.snn_set_stream(net._h, C.c_void_p(stream.cuda_stream))
+    only_partition = bool(args.partition) and world > 1
+    # N > 1: the headline stays instance sharding; the SAME invocation also times ONE network partitioned
+    # over the ranks (BASELINE config 5) and checks it spike for spike against a 1-GPU run of that network
+    with_partition_block = world > 1 and not only_partition and not args.no_partition_block and n_inst == 1
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    common = dict(dtype="f32", mode="fast", noise="philox", device=local, max_delay=dmax, learn_async=args.learn_async)
 
     def barrier():
         torch.cuda.synchronize()
@@ -181,35 +233,85 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also brings the network to its stationary firing regime)
-    kw = 0
-    # events around the learn pass (roofline of the dominant kernel) — not in partitioned runs, where the
-    # pass is 1/N of the work and the extra event nodes were seen to cost 20 % at 8 ranks
-    prof = False if (args.partition and world > 1) else 'learn'
-    for _ in range(args.warmup):
-        tr, da = window_inputs(kw, W)
-        net.run(W, None, tr, da_events=da, record=False, profile=prof)  # same graph as the timed region
-        kw += 1
+    def make_partitioned():
+        from rl_stdp_b200.partition import PartitionedRank, TorchDistExchange, connect_dist, plan
+        rowptr, post, w, delay = synth_workload(args, seed=9)
+        lo, hi = plan(n, world)[rank]
+        cb = TorchDistExchange().callback() if args.partition == "nccl" else None
+        pn = PartitionedRank(n, ne, rowptr, post, w, delay, lo, hi, cb, noise_seed=10, exp_flags=args.exp_flags, **common)
+        if cb is None:
+            connect_dist(pn)  # in-library exchange: peer stores over NVLink, device-side wait
+        npl = int(np.count_nonzero(np.repeat(np.arange(n), np.diff(rowptr))[pn.local_index] < ne))
+        lib.snn_set_stream(pn._h, C.c_void_p(stream.cuda_stream))
+        return pn, npl
+
+    t_build = time.perf_counter()
+    pnet = None
+    if only_partition:
+        net, n_plastic = make_partitioned()
+    else:
+        rowptr, post, w, delay = synth_workload(args, seed=9 + rank)
+        net = SparseNetwork(n, ne, rowptr, post, w, delay, n_instances=n_inst, noise_seed=10 + rank, exp_flags=args.exp_flags,
+                            graph=not args.no_graph, learn_blocks=args.learn_blocks, learn_tile_k=args.learn_tile_k,
+                            learn_stages=args.learn_stages, side_blocks=args.side_blocks, learn_lazy=args.learn_lazy,
+                            learn_lazy_da=args.learn_lazy_da, **common)
+        n_plastic = int(rowptr[ne]) * n_inst
+        del post, w, delay
+        lib.snn_set_stream(net._h, C.c_void_p(stream.cuda_stream))
+    t_build = time.perf_counter() - t_build
+
+    # ---- partition parity (N > 1): 100 ms with frozen weights from t = 0; every rank's spike record of the
+    # partitioned network must equal, bit for bit, the record of the same network on ONE GPU (rank 0's instance)
+    parity = None
+    if with_partition_block:
+        pnet, p_plastic = make_partitioned()
+        PM = 100
+        frozen = np.zeros(PM, np.uint8)
+        sp_p, _ = pnet.run(PM, None, frozen, record=True, spikes_cap=1 << 24)
+        digest = hashlib.sha1(b"".join(np.asarray(x, np.int32).tobytes() + b"|" for x in sp_p)).hexdigest()
+        n_sp = int(sum(len(x) for x in sp_p))
+        single = None
+        if rank == 0:
+            sp_1, _ = net.run(PM, None, frozen, record=True, spikes_cap=1 << 24)
+            single = hashlib.sha1(b"".join(np.asarray(x, np.int32).tobytes() + b"|" for x in sp_1)).hexdigest()
+        allp = [None] * world
+        dist.all_gather_object(allp, (digest, n_sp))
+        if rank == 0:
+            parity = {"ms": PM, "weights": "frozen (train flags 0), fp32 production mode", "spikes": n_sp,
+                      "ranks_agree": len({d for d, _ in allp}) == 1,
+                      "identical_to_single_gpu": all(d == single for d, _ in allp)}
+
+    def measure(net_, prof_, kw_, clock=None):
+        tot_ = dict(spikes=0, ev=0, ltp=0, learn_ms=0.0, neuron_ms=0.0, syn_ms=0.0, nl=0, nn=0, ns=0, npass=0)
+        for _ in range(args.warmup):  # also brings the network to its stationary firing regime
+            tr, da = window_inputs(kw_, W)
+            net_.run(W, None, tr, da_events=da, record=False, profile=prof_)  # same graph as the timed region
+            kw_ += 1
+        barrier()
+        if clock is not None:
+            clock.mark_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            tr, da = window_inputs(kw_, W)
+            _, st = net_.run(W, None, tr, da_events=da, record=False, profile=prof_)
+            kw_ += 1
+            tot_["spikes"] += st.n_spikes; tot_["ev"] += st.n_syn_events; tot_["ltp"] += st.n_ltp_events
+            tot_["learn_ms"] += st.learn_ms; tot_["neuron_ms"] += st.neuron_ms; tot_["syn_ms"] += st.synapse_ms
+            tot_["nl"] += st.learn_launches; tot_["nn"] += st.neuron_launches; tot_["ns"] += st.synapse_launches
+            tot_["npass"] += st.pass_launches
+        e1.record()
+        barrier()
+        if clock is not None:
+            clock.mark_end()
+        return tot_, e0.elapsed_time(e1), kw_
 
     # ---- timed region 1: inputs resident, no spike record -> `value`
-    sampler = ClockSampler(local)
-    sampler.start()
-    tot = dict(spikes=0, ev=0, ltp=0, learn_ms=0.0, neuron_ms=0.0, syn_ms=0.0, nl=0, nn=0, ns=0, npass=0)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        tr, da = window_inputs(kw, W)
-        _, st = net.run(W, None, tr, da_events=da, record=False, profile=prof)
-        kw += 1
-        tot["spikes"] += st.n_spikes; tot["ev"] += st.n_syn_events; tot["ltp"] += st.n_ltp_events
-        tot["learn_ms"] += st.learn_ms; tot["neuron_ms"] += st.neuron_ms; tot["syn_ms"] += st.synapse_ms
-        tot["nl"] += st.learn_launches; tot["nn"] += st.neuron_launches; tot["ns"] += st.synapse_launches
-        tot["npass"] += st.pass_launches
-    e1.record()
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    # events around the learn pass (roofline of the dominant kernel) — not in partitioned runs, where the
+    # pass is 1/N of the work and the extra event nodes were seen to cost 20 % at 8 ranks
+    prof = False if only_partition else 'learn'
+    tot, dev_ms, kw = measure(net, prof, 0, sampler if rank == 0 else None)
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed region 2: end to end through the C ABI with host buffers (spike record D2H)
     cap = int(max(1 << 20, 4 * tot["spikes"] / max(1, args.steps)))
@@ -234,13 +336,27 @@ def run_b200(args):
     # ---- diagnostics (outside the timed regions): per-kernel-class CUDA-event times with plain
     # stream-ordered launches, to show where a simulated millisecond goes
     diag = dict(learn_ms=0.0, neuron_ms=0.0, syn_ms=0.0, nl=0, nn=0, ns=0, total=0.0)
+    Wd = min(W, 250)
     for _ in range(2):
-        tr, da = window_inputs(kw, W)
-        _, st = net.run(W, None, tr, da_events=da, record=False, profile='kernels')
+        tr, da = window_inputs(kw, Wd)
+        _, st = net.run(Wd, None, tr, da_events=da, record=False, profile='kernels')
         kw += 1
         diag["learn_ms"] += st.learn_ms; diag["neuron_ms"] += st.neuron_ms; diag["syn_ms"] += st.synapse_ms
         diag["nl"] += st.learn_launches; diag["nn"] += st.neuron_launches; diag["ns"] += st.synapse_launches
         diag["total"] += st.device_ms
+
+    # ---- N > 1: the partitioned network, timed the same way (strong scaling of ONE network)
+    part = None
+    if with_partition_block:
+        psampler = ClockSampler(local)
+        if rank == 0:
+            psampler.start()
+        ptot, p_ms, _ = measure(pnet, False, 0, psampler if rank == 0 else None)
+        pclocks = psampler.stop() if rank == 0 else None
+        pv = torch.tensor([p_ms, float(ptot["ev"]), float(ptot["spikes"])], dtype=torch.float64, device="cuda")
+        pmx = pv.clone(); dist.all_reduce(pmx, op=dist.ReduceOp.MAX)
+        psm = pv.clone(); dist.all_reduce(psm, op=dist.ReduceOp.SUM)
+        part = dict(ms=float(pmx[0]), ev=float(psm[1]), spikes=float(pmx[2]), clocks=pclocks)
 
     vals = torch.tensor([dev_ms, e2e_s * 1e3, float(tot["ev"]), float(e2e_ev), float(tot["spikes"])],
                         dtype=torch.float64, device="cuda")
@@ -249,6 +365,8 @@ def run_b200(args):
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         dev_ms, e2e_ms = float(mx[0]), float(mx[1])
         ev_all, e2e_ev_all, spikes_all = float(sm[2]), float(sm[3]), float(sm[4])
+        if only_partition:  # every rank's spike counter sees the whole network
+            spikes_all = float(mx[4]) * world
     else:
         e2e_ms = e2e_s * 1e3
         ev_all, e2e_ev_all, spikes_all = float(tot["ev"]), float(e2e_ev), float(tot["spikes"])
@@ -261,24 +379,16 @@ def run_b200(args):
         learn_avg_ms = tot["learn_ms"] / max(1, tot["nl"])
         learn_gbs = learn_bytes / (learn_avg_ms * 1e-3) / 1e9 if learn_avg_ms > 0 else 0.0
         path_bytes = (sim_ms * n * n_inst * B_NEURON + tot["ev"] * B_EVENT + tot["ltp"] * B_LTP + tot["nl"] * learn_bytes)
+        traffic = learn_traffic(args.workload)
         line = {
             "metric": "synaptic events/s", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if (args.partition and world > 1) else "weak",
+            "scaling": "strong" if only_partition else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "neurons": n * n_inst, "synapses": int(rowptr[-1]), "max_delay_ms": dmax,
-                       "instances_per_gpu": n_inst,
-                       "window_ms_per_step": W, "learn_period_ms": LEARN_PERIOD,
-                       **({"learn_rule": f"EXPERIMENTAL event-driven, re-basing every {args.learn_lazy} learn steps (approximates the clamp)"} if args.learn_lazy else {}), "noise": "on-device Philox4x32-10",
-                       "instances": 1 if (args.partition and world > 1) else world,
-                       "sharding": ("one network, neurons partitioned over the ranks; per ms the spike bitmap is exchanged "
-                                    + ("by NCCL all-gather from a host callback" if args.partition == "nccl" else
-                                       "by peer stores over NVLink + device-side wait (in-graph)"))
-                                   if (args.partition and world > 1) else
-                                   "one independent instance per GPU, no collective",
-                       "l2": "working set ~4 GB per instance >> 126 MB L2 (no flush needed)"},
-            "sim_ms_per_wall_s": sim_ms * n_inst * (1 if (args.partition and world > 1) else world) / (dev_ms * 1e-3),
+            "config": bench_config(args, world, only_partition),
+            "sim_ms_per_wall_s": sim_ms * n_inst * (1 if only_partition else world) / (dev_ms * 1e-3),
             "x_realtime_per_instance": sim_ms / dev_ms,
+            "simulated_s_in_timed_region": sim_ms * 1e-3,
             "firing_rate_hz": spikes_all / world / (n * n_inst) / (sim_ms * 1e-3),
             "e2e": {"value": e2e_ev_all / (e2e_ms * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps,
@@ -288,7 +398,11 @@ def run_b200(args):
                          "kernel": ("learn_pass_tma_kernel<float> (asynchronous pass, timed live beside the step kernels)"
                                     if tot["npass"] else "learn_kernel<float>"),
                          "achieved": learn_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": learn_gbs / peak, "traffic": learn_traffic(args.workload), "peak_source": peak_src,
+                         "unit": "GB/s", "frac": learn_gbs / peak, "traffic": traffic,
+                         "traffic_source": (None if traffic is None else
+                                            "dram__bytes_read+write per launch from the committed ncu --set full capture "
+                                            "profiles/r1i_learn_pass_ncu_full.json (same kernel, same workload), not measured in this run"),
+                         "peak_source": peak_src,
                          "bytes_per_launch": learn_bytes, "avg_launch_ms": learn_avg_ms,
                          "share_of_step_time": tot["learn_ms"] / dev_ms if dev_ms else None},
             "roofline_path": {"algorithmic_bytes": path_bytes, "achieved": path_bytes / (dev_ms * 1e-3) / 1e9,
@@ -302,6 +416,17 @@ def run_b200(args):
             "learn_ms_in_timed_region": tot["learn_ms"],
             "clocks": clocks, "build_s": t_build,
         }
+        if part is not None:
+            x1 = sim_ms / dev_ms                 # the same network alone on one GPU, measured in this run (rank 0's instance)
+            xp = sim_ms / part["ms"]
+            line["partition"] = {
+                "what": "ONE network of this workload, neurons partitioned over the ranks (BASELINE config 5), timed like the headline",
+                "value": part["ev"] / (part["ms"] * 1e-3), "unit": "events/s", "ms_per_step": part["ms"] / args.steps,
+                "x_realtime": xp, "x_realtime_one_gpu_same_run": x1, "strong_speedup_vs_n1": xp / x1,
+                "strong_efficiency_vs_n1": xp / x1 / world,
+                "exchange": "peer stores of (bitmap word, step) pairs over NVLink/NVSwitch + device-side wait, fused into the neuron kernels",
+                "firing_rate_hz": part["spikes"] / n / (sim_ms * 1e-3), "clocks": part["clocks"]}
+            line["partition_parity"] = parity
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = (cpu_baseline_dense_c1(args.cpu_seconds) if args.workload == "c1_single"
                                     else cpu_baseline(args.cpu_seconds))
@@ -431,52 +556,74 @@ def cpu_baseline(budget_s: float = 12.0, n=50_000, ne=40_000, fan=100, dmax=20):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Julia original cannot run
-    here) on the host cores, same metric/unit/config, each step a bounded sample."""
+    """--impl reference: the reference's CPU algorithm (oracle port; the Julia original cannot run here:
+    no Julia in the image) on every host core, on the SAME network as the product arm — the full
+    workload, same topology seed, same Philox noise stream, same learn / dopamine schedule.  A step is a
+    bounded sample: --ref-ms-per-step simulated ms of that network (a product-arm step is a whole
+    window), after an untimed spin-up that takes the network out of its start-up transient so that
+    events per simulated ms are those of the stationary regime."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n, ne, fan, dmax = WORKLOADS[args.workload if args.workload != "c4_actors" else "c5_1M_100M"][:4]
+    wl = WORKLOADS[args.workload if args.workload != "c4_actors" else "c5_1M_100M"]
+    if args.workload == "c4_actors":
+        args.workload = "c5_1M_100M"
+    n, ne, fan, dmax = wl[:4]
+    n_inst = wl[4] if len(wl) > 4 else 1
     # the reference itself is single-threaded Julia; this arm gives its algorithm every host core
     # (OpenMP build of the same oracle sources, bit-identical results)
     os.environ.setdefault("ORACLE_OMP", "1")
     from oracle import py_oracle as po
-    from rl_stdp_b200 import synth
-    ns = min(n, 50_000)
-    nes = ns * ne // n
-    rowptr, post, w, delay = synth.fixed_fanout(ns, nes, fan, dmax, seed=9)
-    ora = po.Sparse(ns, nes, rowptr, post, w, delay, max_delay=dmax)
+    cores = po.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1: ask for the cores, then ask what we got
+    t_build = time.perf_counter()
+    rowptr, post, w, delay = synth_workload(args, seed=9)
+    ora = po.Sparse(n * n_inst, ne, rowptr, post, w, delay, max_delay=dmax, n_per_instance=n) if n_inst > 1 else \
+        po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax)
+    del post, w, delay
+    t_build = time.perf_counter() - t_build
     ms_per_step = max(1, args.ref_ms_per_step)
     t_abs = 0
+    ntot = n * n_inst
 
-    def one_step():
+    def one_ms():
         nonlocal t_abs
-        for _ in range(ms_per_step):
-            ora.step(po.philox_noise(10, t_abs, ns), (t_abs + 1) % LEARN_PERIOD == 0)
-            if (t_abs + 1) % DA_PERIOD == 0:
-                ora.add_da(0, 0.5)
-            t_abs += 1
+        sp = ora.step(po.philox_noise(10, t_abs, ntot), (t_abs + 1) % LEARN_PERIOD == 0)
+        if (t_abs + 1) % DA_PERIOD == 0:
+            for b in range(n_inst):
+                ora.add_da(b, 0.5)
+        t_abs += 1
+        return len(sp)
 
+    t_spin = time.perf_counter()
+    for _ in range(max(0, args.ref_spinup_ms)):
+        one_ms()
+    t_spin = time.perf_counter() - t_spin
     for _ in range(args.warmup):
-        one_step()
+        for _ in range(ms_per_step):
+            one_ms()
     ev0, _ = ora.counters()
+    spikes = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        one_step()
+        for _ in range(ms_per_step):
+            spikes += one_ms()
     dt = time.perf_counter() - t0
     ev1, _ = ora.counters()
     value = (ev1 - ev0) / dt
-    cores = po.omp_threads()
-    sample = (f"N={ns} neurons / {ns * fan} synapses sample of {args.workload}, {ms_per_step} simulated ms per step, "
-              f"fp64, {cores} OpenMP thread(s) over the independent loops of the step (the Julia reference itself is "
-              f"single-threaded)")
+    sim_ms = args.steps * ms_per_step
+    sample = (f"the full {args.workload} network ({ntot} neurons / {int(rowptr[-1])} synapses), {ms_per_step} simulated ms "
+              f"per step ({sim_ms} ms timed) after {args.ref_spinup_ms} ms of untimed spin-up, fp64, {cores} OpenMP "
+              f"thread(s) over the independent loops of the step (the Julia reference itself is single-threaded)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {"impl": "reference", "metric": "synaptic events/s", "value": value, "unit": "events/s",
-            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "neurons": n, "synapses": n * fan, "max_delay_ms": dmax,
-                       "sampled_as": sample},
-            "sim_ms_per_wall_s": args.steps * ms_per_step / dt,
+            "config": bench_config(args, world),
+            "sampled_as": sample,
+            "sim_ms_per_wall_s": sim_ms / dt,
+            "firing_rate_hz": spikes / ntot / (sim_ms * 1e-3),
+            "build_s": t_build, "spinup_s": t_spin,
             "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -489,9 +636,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5_1M_100M", choices=sorted(WORKLOADS))
-    ap.add_argument("--window-ms", type=int, default=250, help="simulated ms per snn_step() call (one bench step)")
+    ap.add_argument("--window-ms", type=int, default=500, help="simulated ms per snn_step() call (one bench step)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--ref-ms-per-step", type=int, default=20)
+    ap.add_argument("--ref-ms-per-step", type=int, default=4, help="--impl reference: simulated ms of the full network per step")
+    ap.add_argument("--ref-spinup-ms", type=int, default=120, help="--impl reference: untimed simulated ms before the warm-up steps")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exp-flags", type=int, default=0, help="snn_config.reserved[1] diagnostics (2 timeline, 4 serialise the learn pass, 512 LSU pass); 0 for reported numbers")
     ap.add_argument("--no-graph", action="store_true")
@@ -499,9 +647,11 @@ def main():
     ap.add_argument("--learn-lazy", type=int, default=0, help="EXPERIMENTAL event-driven learning: dense re-basing pass every M learn steps (0 = the reference's rule; not for reported numbers)")
     ap.add_argument("--learn-lazy-da", type=float, default=0.0, help="with --learn-lazy: re-base at every learn step while da exceeds this (0 = never)")
     ap.add_argument("--learn-tile-k", type=int, default=0, help="async learn pass: tile size in units of 1024 synapses (0 = 32)")
-    ap.add_argument("--learn-stages", type=int, default=0, help="async learn pass: TMA pipeline depth (0 = 6)")
+    ap.add_argument("--learn-stages", type=int, default=0, help="async learn pass: TMA pipeline depth (0 = 4)")
     ap.add_argument("--side-blocks", type=int, default=0, help="10*synapse + ltp kernel blocks per SM (0 = default)")
     ap.add_argument("--learn-blocks", type=int, default=0, help="async learn pass: blocks per SM (0 = default)")
+    ap.add_argument("--no-partition-block", action="store_true",
+                    help="N>1: skip the partitioned-network measurement that is otherwise added to the line")
     ap.add_argument("--partition", nargs="?", const="p2p", default=None, choices=["p2p", "nccl"],
                     help="N>1: ONE network neuron-partitioned over the ranks (strong scaling) instead of one instance "
                          "per rank; p2p = in-library exchange over peer memory, nccl = host callback + all-gather")

@@ -58,9 +58,21 @@ def build(force: bool = False) -> str:
 
 
 def omp_threads() -> int:
-    """Threads the loaded oracle library uses for ora_sparse_step (1 for the serial build)."""
-    lib()
-    return (os.cpu_count() or 1) if _OMP else 1
+    """Threads the loaded oracle library really uses for ora_sparse_step, asked of the OpenMP
+    runtime (1 for the serial build).  torchrun exports OMP_NUM_THREADS=1 to its workers, so the
+    host's core count says nothing about it."""
+    return int(lib().ora_omp_max_threads())
+
+
+def use_all_cores() -> int:
+    """bench.py --impl reference: give the OpenMP build every core this process may run on,
+    whatever OMP_NUM_THREADS the launcher exported.  Returns the thread count in use."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    lib().ora_omp_set_threads(n)
+    return omp_threads()
 
 
 _lib = None
@@ -71,6 +83,8 @@ def lib() -> C.CDLL:
     if _lib is None:
         L = C.CDLL(build())
         vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+        L.ora_omp_max_threads.restype = C.c_int
+        L.ora_omp_set_threads.argtypes = [C.c_int]
         L.ora_dense_create.restype = vp
         L.ora_dense_create.argtypes = [i64, i64, vp]
         L.ora_dense_destroy.argtypes = [vp]

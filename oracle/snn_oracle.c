@@ -25,6 +25,26 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* threads the OpenMP build really uses (torchrun exports OMP_NUM_THREADS=1 to its workers, so the
+ * count has to come from the runtime, not from the host's core count) */
+int ora_omp_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void ora_omp_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 /* ------------------------------------------------------------------ Philox4x32-10 */
 static inline void philox_round(uint32_t c[4], const uint32_t k[2]) {

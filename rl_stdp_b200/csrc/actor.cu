@@ -267,6 +267,9 @@ __device__ __forceinline__ double k_cos(double x) {
 }
 
 // CartPole-v1 step, restated (gym classic_control/cartpole.py, Euler integrator)
+// gym wraps both environments in a TimeLimit (max_episode_steps of CartPole-v1 / MountainCar-v0): an
+// episode ends there whatever n_decisions_max the caller passes
+constexpr int kCartPoleMaxSteps = 500, kMountainCarMaxSteps = 200;
 __device__ __forceinline__ int cartpole_step(double s[4], int action) {
   const double gravity = 9.8, masscart = 1.0, masspole = 0.1, length = 0.5, force_mag = 10.0, tau = 0.02;
   const double total_mass = DADD(masspole, masscart), polemass_length = DMUL(masspole, length);
@@ -318,7 +321,8 @@ template <int NS, int ENV>
 __global__ void __launch_bounds__(128)
 actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const double* __restrict__ state0,
                      const int32_t* __restrict__ tie_actions, int tie_stride, const int32_t* __restrict__ teach_actions,
-                     int n_decisions_max, int win_size, int train, double* __restrict__ rewards,
+                     int n_decisions_max, int win_size, int train, int32_t* __restrict__ tie_overflow,
+                     double* __restrict__ rewards,
                      int32_t* __restrict__ n_dec, int32_t* __restrict__ n_rand_out, double* __restrict__ state_out) {
   extern __shared__ double smem[];
   const unsigned FULL = 0xffffffffu;
@@ -396,6 +400,7 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
     if (ENV == 0) {
       action = (sl >= sr) ? 0 : 1;
       if (sl == sr) {  // :87-95
+        if (n_rand >= tie_stride) *tie_overflow = 1;  // the replayed rand(rng_action, 0:1) stream ran out
         action = n_rand < tie_stride ? tie_actions[(size_t)a * tie_stride + n_rand] : 0;
         tot_reward = DSUB(tot_reward, 0.9);
         ++n_rand;
@@ -405,7 +410,7 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
         const double inc = (action == teach_actions[(size_t)a * n_decisions_max + jdec]) ? 1.0 : -200.0;
         da = DADD(da, DMUL(inc, p.da_inc));
       }
-      done = cartpole_step(st, action);
+      done = cartpole_step(st, action) | (jdec + 1 >= kCartPoleMaxSteps);  // gym TimeLimit of CartPole-v1
       tot_reward = DADD(tot_reward, 1.0);
     } else {
       action = 0;  // argmax([sl, sm, sr]) - 1: the first maximum
@@ -418,13 +423,14 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         if (dif[i] == 0) {
+          if (n_rand >= tie_stride) *tie_overflow = 1;
           const int pick = n_rand < tie_stride ? tie_actions[(size_t)a * tie_stride + n_rand] : 0;
           action = pool[i][pick & 1];
           fac = 2.0;
           ++n_rand;
         }
       ++n_tot;
-      done = mountcar_step(st, action);
+      done = mountcar_step(st, action) | (jdec + 1 >= kMountainCarMaxSteps);  // gym TimeLimit of MountainCar-v0
       tot_reward = DADD(tot_reward, DMUL(-1.0, fac));  // :98
     }
     if (done) break;
@@ -444,11 +450,26 @@ __global__ void fill_d(double* a, int64_t n, double x) {
 
 }  // namespace
 
+// grow-only device buffer
+struct ActBuf {
+  void* ptr = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&ptr, bytes + bytes / 4 + 256);
+    if (e == cudaSuccess) cap = bytes + bytes / 4 + 256;
+    return e;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
 struct Actor::Impl {
   ActorDev d;
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ActBuf b_ma, b_s0, b_so, b_rw, b_tie, b_teach, b_nd;  // staging of episodes()
 };
 
 #define ACT_OK(expr)                                                       \
@@ -465,6 +486,8 @@ Actor::~Actor() {
   ActorDev& d = impl_->d;
   cudaSetDevice(impl_->device);
   cudaFree(d.v); cudaFree(d.ho); cudaFree(d.trace); cudaFree(d.e); cudaFree(d.de); cudaFree(d.da);
+  impl_->b_ma.release(); impl_->b_s0.release(); impl_->b_so.release(); impl_->b_rw.release();
+  impl_->b_tie.release(); impl_->b_teach.release(); impl_->b_nd.release();
   if (impl_->e0) cudaEventDestroy(impl_->e0);
   if (impl_->e1) cudaEventDestroy(impl_->e1);
   if (impl_->stream) cudaStreamDestroy(impl_->stream);
@@ -606,43 +629,54 @@ int Actor::episodes(int env, const double* matalpha, const double* state0, const
   const size_t nobs = env == SNN_ENV_CARTPOLE ? 4 : 2;
   ACT_OK(cudaSetDevice(impl_->device));
   const size_t A = (size_t)d.n_agents;
-  double *d_ma = nullptr, *d_s0 = nullptr, *d_rw = nullptr, *d_so = nullptr;
-  int32_t *d_tie = nullptr, *d_teach = nullptr, *d_nd = nullptr, *d_nr = nullptr;
+  // staging buffers live with the population (grow-only): a generation of an evolutionary run calls
+  // this once per episode batch, and eight cudaMalloc/cudaFree pairs per call were a third of the
+  // end-to-end time of config 4
+  Impl& m = *impl_;
+  ACT_OK(m.b_ma.reserve(A * d.arch[0] * nobs * sizeof(double)));
+  ACT_OK(m.b_s0.reserve(A * 4 * sizeof(double)));
+  ACT_OK(m.b_so.reserve(A * 4 * sizeof(double)));
+  ACT_OK(m.b_rw.reserve(A * sizeof(double)));
+  ACT_OK(m.b_tie.reserve(A * (size_t)tie_stride * sizeof(int32_t)));
+  if (teach_actions) ACT_OK(m.b_teach.reserve(A * (size_t)n_decisions_max * sizeof(int32_t)));
+  ACT_OK(m.b_nd.reserve((2 * A + 1) * sizeof(int32_t)));
+  double *d_ma = (double*)m.b_ma.ptr, *d_s0 = (double*)m.b_s0.ptr, *d_rw = (double*)m.b_rw.ptr, *d_so = (double*)m.b_so.ptr;
+  int32_t *d_tie = (int32_t*)m.b_tie.ptr, *d_teach = teach_actions ? (int32_t*)m.b_teach.ptr : nullptr;
+  int32_t *d_nd = (int32_t*)m.b_nd.ptr, *d_nr = d_nd + A, *d_ovf = d_nd + 2 * A;
   cudaStream_t s = impl_->stream;
-  cudaError_t e = cudaMalloc(&d_ma, A * d.arch[0] * nobs * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&d_s0, A * 4 * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&d_so, A * 4 * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&d_rw, A * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&d_tie, A * tie_stride * sizeof(int32_t));
-  if (e == cudaSuccess && teach_actions) e = cudaMalloc(&d_teach, A * n_decisions_max * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d_nd, A * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d_nr, A * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ma, matalpha, A * d.arch[0] * nobs * sizeof(double), cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_s0, state0, A * 4 * sizeof(double), cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_tie, tie_actions, A * tie_stride * sizeof(int32_t), cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess && teach_actions)
-    e = cudaMemcpyAsync(d_teach, teach_actions, A * n_decisions_max * sizeof(int32_t), cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) {
+  ACT_OK(cudaMemsetAsync(d_ovf, 0, sizeof(int32_t), s));
+  ACT_OK(cudaMemcpyAsync(d_ma, matalpha, A * d.arch[0] * nobs * sizeof(double), cudaMemcpyHostToDevice, s));
+  ACT_OK(cudaMemcpyAsync(d_s0, state0, A * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  ACT_OK(cudaMemcpyAsync(d_tie, tie_actions, A * (size_t)tie_stride * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  if (teach_actions)
+    ACT_OK(cudaMemcpyAsync(d_teach, teach_actions, A * (size_t)n_decisions_max * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  {
     const int warps = actor_warps(d), blocks = (int)((A + warps - 1) / warps);
     cudaEventRecord(impl_->e0, s);
 #define EPISODE_LAUNCH(NS, ENV)                                                                                      \
   actor_episode_kernel<NS, ENV><<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, tie_stride, d_teach, \
-                                                                                 n_decisions_max, win_size, train, d_rw, \
+                                                                                 n_decisions_max, win_size, train, d_ovf, d_rw, \
                                                                                  d_nd, d_nr, d_so)
     if (env == SNN_ENV_CARTPOLE) { if (d.n <= 32) EPISODE_LAUNCH(1, 0); else EPISODE_LAUNCH(2, 0); }
     else                         { if (d.n <= 32) EPISODE_LAUNCH(1, 1); else EPISODE_LAUNCH(2, 1); }
 #undef EPISODE_LAUNCH
     cudaEventRecord(impl_->e1, s);
-    e = cudaGetLastError();
+    ACT_OK(cudaGetLastError());
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(rewards, d_rw, A * sizeof(double), cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess && n_dec) e = cudaMemcpyAsync(n_dec, d_nd, A * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess && n_rand) e = cudaMemcpyAsync(n_rand, d_nr, A * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess && state_out) e = cudaMemcpyAsync(state_out, d_so, A * 4 * sizeof(double), cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  if (e == cudaSuccess && device_ms) { float ms = 0; cudaEventElapsedTime(&ms, impl_->e0, impl_->e1); *device_ms = ms; }
-  cudaFree(d_ma); cudaFree(d_s0); cudaFree(d_so); cudaFree(d_rw); cudaFree(d_tie); cudaFree(d_teach); cudaFree(d_nd); cudaFree(d_nr);
-  if (e != cudaSuccess) { err = std::string("actor episodes: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
+  int32_t overflow = 0;
+  ACT_OK(cudaMemcpyAsync(rewards, d_rw, A * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (n_dec) ACT_OK(cudaMemcpyAsync(n_dec, d_nd, A * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (n_rand) ACT_OK(cudaMemcpyAsync(n_rand, d_nr, A * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (state_out) ACT_OK(cudaMemcpyAsync(state_out, d_so, A * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  ACT_OK(cudaMemcpyAsync(&overflow, d_ovf, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  ACT_OK(cudaStreamSynchronize(s));
+  if (device_ms) { float ms = 0; cudaEventElapsedTime(&ms, impl_->e0, impl_->e1); *device_ms = ms; }
+  if (overflow) {
+    // the reference draws rand(rng_action, ...) at every tie (cartpole_fitness.jl:87-95, up to three per
+    // decision in mountcar_fitness.jl:83-93); an exhausted replay stream would silently diverge from it
+    err = "episodes: an agent met more ties than tie_stride replayed draws (MountainCar can take 3 per decision)";
+    return SNN_ERR_CAPACITY;
+  }
   return SNN_OK;
 }
 

@@ -1,6 +1,9 @@
 // capi.cu — the extern "C" boundary of libsnn_b200.so (declared in include/snn_b200.h).
 // Plain pointers and sizes only; every error becomes a status code + thread-local message.
 #include <string.h>
+#include <stdio.h>
+#include <time.h>
+#include <unistd.h>
 
 #include <memory>
 #include <string>
@@ -17,6 +20,27 @@ struct snn_net {
   snn_config cfg;
   std::unique_ptr<snn::IEngine> eng;
 };
+
+namespace snn {
+// 64 random bits drawn once per process (/dev/urandom; clock + pid + an address if that fails): tells two
+// processes with the same pid (different pid namespaces) apart when peers exchange raw device pointers
+uint64_t process_nonce() {
+  static const uint64_t nonce = [] {
+    uint64_t x = 0;
+    if (FILE* f = fopen("/dev/urandom", "rb")) {
+      if (fread(&x, sizeof(x), 1, f) != 1) x = 0;
+      fclose(f);
+    }
+    if (x == 0) {
+      struct timespec ts; clock_gettime(CLOCK_REALTIME, &ts);
+      x = (uint64_t)ts.tv_nsec * 0x9E3779B97F4A7C15ull ^ ((uint64_t)getpid() << 32) ^ (uint64_t)(uintptr_t)&ts ^ (uint64_t)ts.tv_sec;
+      if (x == 0) x = 1;
+    }
+    return x;
+  }();
+  return nonce;
+}
+}  // namespace snn
 
 namespace {
 thread_local std::string g_err;

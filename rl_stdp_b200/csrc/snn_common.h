@@ -58,8 +58,10 @@ struct PeerBlob {
   uint64_t raw_ring;               // device pointer of the exchange ring, valid inside the exporting process
   unsigned char ipc_ring[64];      // cudaIpcMemHandle_t of the exchange ring ((word, step) pairs)
   int32_t words_per_slot, ring;
-  unsigned char pad[96];
+  uint64_t proc_nonce;             // random per process: same pid AND same nonce <=> raw_ring is usable
+  unsigned char pad[88];
 };
+uint64_t process_nonce();          // capi.cu
 static_assert(sizeof(PeerBlob) == SNN_PEER_BLOB_BYTES, "PeerBlob must match SNN_PEER_BLOB_BYTES");
 
 struct StepArgs {

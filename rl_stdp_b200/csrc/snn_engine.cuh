@@ -1849,6 +1849,7 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaSetDevice(cfg_.device));
     memset(b, 0, sizeof(*b));
     b->magic = kPeerMagic; b->pid = (int32_t)getpid(); b->device = cfg_.device;
+    b->proc_nonce = process_nonce();
     b->raw_ring = (uint64_t)(uintptr_t)p_.ll;
     b->words_per_slot = p_.W; b->ring = p_.R;
     SNN_CUDA_OK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(b->ipc_ring), p_.ll));
@@ -1867,7 +1868,9 @@ class Engine : public IEngine {
         err = "peer blob of rank " + std::to_string(r) + " does not match this network (size / max_delay)"; return SNN_ERR_INVALID;
       }
       if (r == rank) { p.peer_ll[r] = p.ll; continue; }
-      if (b.pid == (int32_t)getpid()) {  // several handles in one process: plain pointers
+      // several handles in ONE process: plain pointers.  The pid alone does not identify a process (ranks in
+      // different containers / pid namespaces can share one), so the blob carries a per-process random nonce
+      if (b.pid == (int32_t)getpid() && b.proc_nonce == process_nonce()) {
         if (b.device != cfg_.device) {
           cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
           if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return SNN_ERR_CUDA; }
@@ -1948,6 +1951,7 @@ class Engine : public IEngine {
     cudaFree(p.cacc); cudaFree(p.lzH); cudaFree(p.lzK);
     cudaFree(const_cast<uint32_t*>(p.inst_lo));
     p.wsd = p.wsdX[0] = p.wsdX[1] = nullptr; p.dlog = nullptr; p.dsd = nullptr; p.log_cnt = nullptr;
+    p.cacc = nullptr; p.lzH = p.lzR = p.lzInv = nullptr; p.lzK = nullptr; p.lazy = 0;
     p.tile_done = nullptr; p.inst_lo = p.inst_hi = nullptr; p.log_regions = p.log_region_cap = p.n_tiles = 0;
   }
   void release() {

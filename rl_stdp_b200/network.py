@@ -79,7 +79,7 @@ class SparseNetwork:
         cfg.reserved[1] = exp_flags
         cfg.reserved[2] = learn_blocks   # asynchronous learn pass: blocks per SM (0 = default)
         cfg.reserved[3] = learn_tile_k   # tile of the asynchronous pass in units of 1024 synapses (0 = 32)
-        cfg.reserved[6] = learn_stages   # TMA pipeline depth of the asynchronous pass (0 = 6)
+        cfg.reserved[6] = learn_stages   # TMA pipeline depth of the asynchronous pass (0 = 4, kPassStages)
         cfg.reserved[7] = side_blocks    # 10*synapse + ltp blocks per SM (0 = default: occupancy limit / 4)
         cfg.reserved[5] = learn_log_cap  # total entries of the sd-update log (0 = by size)
         cfg.reserved[4] = learn_async    # 0 auto (large nets), 1 in-place pass only, 2 always asynchronous
