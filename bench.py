@@ -225,7 +225,8 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    common = dict(dtype="f32", mode="fast", noise="philox", device=local, max_delay=dmax, learn_async=args.learn_async)
+    common = dict(dtype="f32", mode="fast", noise="philox", device=local, max_delay=dmax, learn_async=args.learn_async,
+                  chain=args.chain, persistent=not args.no_persistent)
 
     def barrier():
         torch.cuda.synchronize()
@@ -643,6 +644,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exp-flags", type=int, default=0, help="snn_config.reserved[1] diagnostics (2 timeline, 4 serialise the learn pass, 512 LSU pass); 0 for reported numbers")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--chain", default=None, help="persistent chain footprints 'nthr,syn,ltp,ltp_thr,learn,learn_thr,stages' (sweeps; default: the library's)")
+    ap.add_argument("--no-persistent", action="store_true", help="captured CUDA graph of per-step kernels instead of the persistent chain")
     ap.add_argument("--learn-async", default="auto", choices=["auto", "off", "force"], help="learn pass beside the following steps (auto: large nets) or in place")
     ap.add_argument("--learn-lazy", type=int, default=0, help="EXPERIMENTAL event-driven learning: dense re-basing pass every M learn steps (0 = the reference's rule; not for reported numbers)")
     ap.add_argument("--learn-lazy-da", type=float, default=0.0, help="with --learn-lazy: re-base at every learn step while da exceeds this (0 = never)")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 2
+#define SNN_ABI_VERSION 3
 
 /* status codes */
 enum {
@@ -106,20 +106,8 @@ typedef struct snn_config {
                               pre trace of the PREVIOUS ms (STDP[pre,msec], :62-68: a presynaptic spike of
                               the same ms is not seen), all LTP before all LTD, the input current
                               accumulates in descending presynaptic id (:70-80 walks `firings` backwards) */
-  int32_t reserved[8];     /* tuning / A-B switches, 0 = default:
-                              [0] = 1 disables the CUDA-graph scheduler (plain launches)
-                              [1] diagnostics: 2 = kernel timeline for snn_debug_timeline, 4 = nothing overlaps
-                                  the asynchronous learn pass, 512 = register-staged pass instead of TMA
-                              [2] asynchronous learn pass: resident blocks per SM
-                              [4] learn pass: 0 auto (asynchronous on large nets), 1 always in place,
-                                  2 always asynchronous; 16+M = EXPERIMENTAL event-driven learning
-                                  (SNN_MODE_FAST only; an approximation of the reference's rule: the
-                                  clamp wmin <= w <= wmax is applied when a weight is read and at a
-                                  dense re-basing pass every M learn steps instead of at every learn
-                                  step; M = 1 is the reference's rule; not with snn_set_partition or synapse probes.
-                                  DESIGN.md section 11.1)
-                              [5] asynchronous learn pass: total entries of the sd-update log; with
-                                  [4] >= 16: re-base at every learn step while da > [5]/1000 (0 = never) */
+  int32_t reserved[8];     /* must be zero.  (ABI 2 carried tuning switches here as magic numbers; since ABI 3
+                              everything that is not part of the model is set BY NAME with snn_set_param.) */
 } snn_config;
 
 typedef struct snn_net snn_net;
@@ -199,6 +187,51 @@ int32_t snn_set_synapses_csr(snn_net* net, const int64_t* rowptr, const int32_t*
  * (new_net.jl:14-15, 86-91); single instance only. */
 int32_t snn_set_synapses_dense(snn_net* net, const double* s_colmajor,
                                const int64_t* connection_colmajor);
+
+/* The transposed storage of variant B: s[post,pre] and connection[post,pre], column-major N x N, "read by
+ * columns" (Old_net/new_net_col.jl:13-15, 93-99); single instance only. */
+int32_t snn_set_synapses_dense_col(snn_net* net, const double* s_colmajor,
+                                   const int64_t* connection_colmajor);
+
+/* Named parameters.
+ *  (1) The model's scalars, by their snn_config field name ("vthresh", "v_reset", "a_exc", "a_inh", "d_exc",
+ *      "d_inh", "trace_set", "trace_decay", "apost", "apre", "da_decay", "learn_base", "eta", "wmin", "wmax",
+ *      "sd_decay", "theta", "ttheta", "noise_amp", "noise_seed"): the reference keeps them as plain mutable
+ *      fields / Dict entries (net.param["..."], Modules/cfg.yml) that a script may change between two step!
+ *      calls; so may the caller here, between two windows.
+ *  (2) Everything that is NOT the model — any time unless marked [S] = only before the synapses are set:
+ *      "graph"                 1 (default) whole windows as device-side schedules; 0 plain launches per step
+ *      "persistent"            1 (default) production-mode windows run as the persistent chain (one resident
+ *                              kernel per role); 0 the captured CUDA graph of per-step kernels
+ *      "learn_async"       [S] 0 auto, 1 learn! always in place, 2 always the asynchronous double-buffered pass
+ *      "learn_log_cap"     [S] entries of the sd-update log of the asynchronous pass (0 = by size)
+ *      "learn_pass_blocks", "learn_pass_stages", "learn_pass_tile_k" [S]   asynchronous pass of the graph path
+ *      "synapse_blocks_per_sm", "ltp_blocks_per_sm" [S]                    side kernels of the graph path
+ *      "chain_neuron_threads", "chain_synapse_blocks", "chain_ltp_blocks", "chain_ltp_threads",
+ *      "chain_learn_blocks", "chain_learn_threads", "chain_learn_stages"   footprints of the chain's roles
+ *      "timeline"              1: kernels stamp %globaltimer for snn_debug_timeline (diagnostic)
+ *      "serialise_learn_pass", "neuron_blocks_256", "lsu_pass"             A/B switches (diagnostic)
+ *      "learn_lazy"        [S] M > 0: EXPERIMENTAL event-driven learning (SNN_MODE_FAST only) — an
+ *                              approximation of the reference's rule: the clamp wmin <= w <= wmax is applied
+ *                              when a weight is read and at a dense re-basing pass every M learn steps
+ *                              instead of at every learn step (M = 1 is the reference's rule; not with
+ *                              snn_set_partition or synapse probes)
+ *      "learn_lazy_da"     [S] with learn_lazy: re-base at every learn step while da exceeds this (0 = never)
+ *      read-only: "window_path" = how the last window ran (2 persistent chain, 1 captured graph, 0 plain launches)
+ * Unknown names are an error (SNN_ERR_INVALID). */
+int32_t snn_set_param(snn_net* net, const char* name, double value);
+int32_t snn_get_param(snn_net* net, const char* name, double* value);
+
+/* Checkpoint / resume of a run in flight (the reference itself only saves genomes,
+ * Modules/save_param.jl:4-47).  The blob holds everything the next window depends on: v, u, ho, da, (w, sd),
+ * the spike history the STDP traces derive from, and the axonal-delay ring (per-step spike lists and bitmaps
+ * of the last max_delay steps, the currents already pushed), plus the step counter.  It restores only into a
+ * handle created with the same snn_config and given the same synapses.  A restored run continues bit for
+ * bit (SNN_MODE_EXACT; in SNN_MODE_FAST up to the order of the atomic sums, as any two runs).
+ *   snn_checkpoint_bytes: size the blob needs right now (it depends on the spikes in flight). */
+int32_t snn_checkpoint_bytes(snn_net* net, int64_t* bytes);
+int32_t snn_checkpoint(snn_net* net, void* buf, int64_t bytes);
+int32_t snn_restore(snn_net* net, const void* buf, int64_t bytes);
 
 /* Run n_steps calls of step!(net[, input_spikes], train) (new_net.jl:146-161) on the device
  * with no host round trip.

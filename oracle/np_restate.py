@@ -7,6 +7,7 @@ arithmetic is IEEE and unfused, evaluated in the order written — the same cont
 broadcasts without @fastmath.
 
   NetA      Julia/Izhikevic_dastdp/Old_net/new_net.jl:4-161      (variant A)
+  NetB      Julia/Izhikevic_dastdp/Old_net/new_net_col.jl:4-161  (variant B: transposed storage)
   NetArch   Julia/Modules/Networks/net_arch.jl:8-281,316-379      (variants E and F)
   NetColSep Julia/Izhikevic_dastdp/Old_net/new_net_col_sep.jl     (variant C)
   NetRes    Julia/Modules/Networks/net_res.jl                     (variant D)
@@ -69,6 +70,72 @@ class NetA:
         self.sd *= 0.99
 
     def step(self, noise, train=False, input_spikes=None):            # :146-161
+        if input_spikes is not None:
+            self.input(input_spikes)
+        spiked = self.spike(noise)
+        if train:
+            self.learn()
+        return spiked
+
+
+class NetB:
+    """Variant B (new_net_col.jl): the same network stored transposed — connection, s and sd are indexed
+    [post, pre] ("WARNING read by columns", :13-15), propagation adds COLUMNS (:116-118), the STDP loop
+    updates the ROW of a spiker first (LTP of its incoming synapses) and then its COLUMN (LTD of its outgoing
+    ones) (:127-130), learn! works on the exc COLUMNS (:138-140).  `connection` is given as [pre, post], as
+    connect() draws it, and transposed here as :94 does."""
+
+    def __init__(self, n_neurons, n_exc, connection):
+        N = n_neurons
+        self.n_neurons, self.n_exc = N, n_exc
+        self.v = -65.0 * np.ones(N)                                   # :88
+        self.u = 0.2 * self.v                                         # :89
+        self.d = np.where(np.arange(1, N + 1) <= n_exc, 8.0, 2.0)     # :90
+        self.a = np.where(np.arange(1, N + 1) <= n_exc, 0.02, 0.1)    # :91
+        self.connection = np.array(connection, dtype=np.int64).T.copy()   # :93-94 transpose(connection)
+        self.exc = np.arange(0, n_exc)
+        self.inh = np.arange(n_exc, N)
+        self.s = np.zeros((N, N))
+        self.s[:, self.exc] = 1.0 * np.ones((N, n_exc))               # :97
+        self.s[:, self.inh] = -1.0 * np.ones((N, N - n_exc))          # :98
+        self.s *= self.connection                                     # :99
+        self.sd = np.zeros((N, N))
+        self.STDP = np.zeros(N)
+        self.I = np.zeros(0)
+        self.da = 0.0
+
+    def input(self, input_spikes):                                    # :106-108
+        self.v[input_spikes] = 40.0
+
+    def spike(self, noise):                                           # :111-135
+        self.I = np.array(noise, dtype=np.float64)                    # :113 recorded 13 .* (rand(N) .- 0.5)
+        spiked = np.flatnonzero(self.v > 30)                          # :114
+        self.v[spiked] = -65.0                                        # :115
+        self.u[spiked] += self.d[spiked]                              # :116
+        for neuron in spiked:                                         # :118-120
+            self.I += self.s[:, neuron]
+        v, u, I = self.v, self.u, self.I
+        self.v = v + 0.5 * ((0.04 * v + 5) * v + 140 - u + I)         # :122
+        v = self.v
+        self.v = v + 0.5 * ((0.04 * v + 5) * v + 140 - u + I)         # :123
+        self.u = u + self.a * (0.2 * self.v - u)                      # :124
+        self.STDP[spiked] = 0.1                                       # :125
+        for neuron in spiked:                                         # :127-130
+            self.sd[neuron, :] += 1.0 * self.STDP
+            self.sd[:, neuron] -= 1.5 * self.STDP
+        self.STDP *= 0.95                                             # :132
+        self.da *= 0.995                                              # :133
+        return spiked
+
+    def learn(self):                                                  # :137-144
+        e = self.exc
+        self.s[:, e] += (0.002 + self.da) * self.sd[:, e]
+        x = self.s[:, e]
+        self.s[:, e] = np.where(x > 4, 4.0, np.where(x < 0, 0.0, x))  # Base.clamp
+        self.s *= self.connection
+        self.sd *= 0.99
+
+    def step(self, noise, train=False, input_spikes=None):            # :148-163
         if input_spikes is not None:
             self.input(input_spikes)
         spiked = self.spike(noise)

@@ -96,6 +96,12 @@ SYMBOLS = {
     "snn_destroy": (C.c_int32, [_VP]),
     "snn_set_synapses_csr": (C.c_int32, [_VP, _VP, _VP, _VP, _VP]),
     "snn_set_synapses_dense": (C.c_int32, [_VP, _VP, _VP]),
+    "snn_set_synapses_dense_col": (C.c_int32, [_VP, _VP, _VP]),
+    "snn_set_param": (C.c_int32, [_VP, C.c_char_p, C.c_double]),
+    "snn_get_param": (C.c_int32, [_VP, C.c_char_p, C.POINTER(C.c_double)]),
+    "snn_checkpoint_bytes": (C.c_int32, [_VP, C.POINTER(C.c_int64)]),
+    "snn_checkpoint": (C.c_int32, [_VP, _VP, C.c_int64]),
+    "snn_restore": (C.c_int32, [_VP, _VP, C.c_int64]),
     "snn_step": (C.c_int32, [_VP, C.c_int32, _VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP, _VP, C.c_int64,
                              C.POINTER(SnnStepStats)]),
     "snn_step_ex": (C.c_int32, [_VP, C.POINTER(SnnStepIO)]),

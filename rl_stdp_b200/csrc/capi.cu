@@ -59,6 +59,8 @@ int validate(const snn_config& c, std::string& err) {
   if (c.noise_mode < SNN_NOISE_NONE || c.noise_mode > SNN_NOISE_PHILOX) { err = "bad noise_mode"; return SNN_ERR_INVALID; }
   if (c.sd_decay_mode < 0 || c.sd_decay_mode > 2 || c.rate_mode < 0 || c.rate_mode > 2) { err = "bad sd_decay_mode / rate_mode"; return SNN_ERR_INVALID; }
   if (!(c.wmin <= c.wmax)) { err = "wmin must be <= wmax"; return SNN_ERR_INVALID; }
+  for (int q = 0; q < 8; ++q)
+    if (c.reserved[q] != 0) { err = "snn_config.reserved must be zero (ABI 3: tuning switches are set by name with snn_set_param)"; return SNN_ERR_INVALID; }
   return SNN_OK;
 }
 }  // namespace
@@ -144,6 +146,22 @@ int32_t snn_set_synapses_dense(snn_net* net, const double* s, const int64_t* con
   return snn_set_synapses_csr(net, rowptr.data(), post.data(), w.data(), nullptr);
 }
 
+int32_t snn_set_synapses_dense_col(snn_net* net, const double* s, const int64_t* connection) {
+  if (!net || !s || !connection) return fail(SNN_ERR_INVALID, "null argument");
+  const int64_t N = net->cfg.n_neurons;
+  if (net->cfg.n_per_instance != N) return fail(SNN_ERR_INVALID, "dense synapses: single instance only");
+  if (net->cfg.max_delay != 1) return fail(SNN_ERR_INVALID, "dense synapses carry no delays: max_delay must be 1");
+  std::vector<int64_t> rowptr(N + 1, 0);
+  std::vector<int32_t> post;
+  std::vector<double> w;
+  for (int64_t i = 0; i < N; ++i) {       // presynaptic neuron = COLUMN i of the [post, pre] matrices
+    for (int64_t j = 0; j < N; ++j)
+      if (connection[j + N * i] != 0) { post.push_back((int32_t)j); w.push_back(s[j + N * i]); }
+    rowptr[i + 1] = (int64_t)post.size();
+  }
+  return snn_set_synapses_csr(net, rowptr.data(), post.data(), w.data(), nullptr);
+}
+
 int32_t snn_step(snn_net* net, int32_t n_steps, const double* noise, const uint8_t* train_flags,
                  const snn_force_event* force, int32_t n_force, const snn_da_event* da, int32_t n_da,
                  int32_t* spikes_out, int64_t* spike_offsets, int64_t spikes_cap, snn_step_stats* stats) {
@@ -209,6 +227,41 @@ int32_t snn_reset_v(snn_net* net) {
   if (!net) return fail(SNN_ERR_INVALID, "null net");
   std::string err;
   int rc = net->eng->reset_v(err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_set_param(snn_net* net, const char* name, double value) {
+  if (!net || !name) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->set_param(name, value, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_get_param(snn_net* net, const char* name, double* value) {
+  if (!net || !name || !value) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->get_param(name, value, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_checkpoint_bytes(snn_net* net, int64_t* bytes) {
+  if (!net || !bytes) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->checkpoint_bytes(bytes, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_checkpoint(snn_net* net, void* buf, int64_t bytes) {
+  if (!net || !buf) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->checkpoint(buf, bytes, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_restore(snn_net* net, const void* buf, int64_t bytes) {
+  if (!net || !buf) return fail(SNN_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = net->eng->restore(buf, bytes, err);
   return rc ? fail(rc, err) : SNN_OK;
 }
 

@@ -93,6 +93,11 @@ class IEngine {
   virtual int set_array(int field, const double* host, int64_t count, std::string& err) = 0;
   virtual int add_dopamine(int instance, double amount, std::string& err) = 0;
   virtual int reset_v(std::string& err) = 0;
+  virtual int checkpoint_bytes(int64_t* bytes, std::string& err) = 0;
+  virtual int checkpoint(void* buf, int64_t bytes, std::string& err) = 0;
+  virtual int restore(const void* buf, int64_t bytes, std::string& err) = 0;
+  virtual int set_param(const char* name, double value, std::string& err) = 0;
+  virtual int get_param(const char* name, double* value, std::string& err) = 0;
   virtual int set_partition(int64_t lo, int64_t hi, snn_exchange_fn fn, void* user, std::string& err) = 0;
   virtual int export_peer(PeerBlob* b, std::string& err) = 0;
   virtual int connect_peers(int rank, int world, const PeerBlob* blobs, std::string& err) = 0;

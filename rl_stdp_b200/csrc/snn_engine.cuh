@@ -43,6 +43,8 @@
 #include <unistd.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
+#include <stdio.h>
 
 #include <algorithm>
 #include <string>
@@ -98,6 +100,12 @@ __device__ __forceinline__ double philox_noise(uint64_t seed, int64_t t, int64_t
 }
 
 constexpr int kMaxSynBlocks = 148 * 16 * 2;
+constexpr int32_t kNever = -(1 << 30);  // "no spike yet" in hist / old_last
+// How far the neuron chain may run ahead of the slowest reader of spike history (ltp): neuron(m) waits for the
+// pushes of synapse(m-2), which waited for ltp(m-3).  Ring depth R = Dmax + 2*kLag + 1 and retire age
+// G = Dmax + kLag (+1 each for variant_g) make every slot a reader may scan valid and every older spike
+// already retired into old_last, whatever the interleaving inside that bound.
+constexpr int kLag = 3;
 constexpr int kMaxRanks = 8;
 
 // State of the asynchronous learn pass.  `state` packs (cur << 31) | frontier, frontier in units
@@ -124,7 +132,18 @@ struct DevNet {
   // neuron state
   T *v, *u, *ho;
   T* Iacc;           // [2][Nld]  Iacc[t&1] = currents consumed by the Euler update of step t
-  T* trace;          // [R][Nld]  trace after the set of that step (pre-decay)
+  // STDP traces are not stored: between two spikes of a neuron the reference's trace is the FIXED sequence
+  // set, set*decay, (set*decay)*decay, ... (new_net.jl:123,130), so the trace of neuron i after the set of step
+  // s is tseq[s - (last spike of i at or before s)], 0 before the first spike — bit for bit what the iterated
+  // multiplication gives.  State per neuron: the last two spike steps (one 8-byte word, rewritten only when
+  // the neuron spikes) and, for the rare neuron that spiked more than twice inside the delay window, the
+  // bitmap ring + the last spike that has left it.  (The dense trace ring this replaces cost 8 B per neuron
+  // and step in the neuron kernel, made LTP gather from an 88 MB array, and had to be replayed for every
+  // foreign neuron of a partitioned run.)
+  int2* hist;            // [Nld] (last, prev) spike step, kNever if none
+  int32_t* old_last;     // [Nld] last spike step <= t - G (retired from the bitmap ring G steps after it happened)
+  const T* tseq;         // [tseq_len] set * decay^n by iterated multiplication, up to its fixed point
+  int32_t tseq_len, G;   // G = retire age, see kLag
   uint32_t* bits;    // [R][W]    spike bitmap per step
   int32_t* spk_list; // [R][Nld]  spike list per step (unordered)
   int32_t* spk_cnt;  // [R]
@@ -173,7 +192,7 @@ struct DevNet {
   int64_t ho_from;
   int32_t threshold_ge, sd_decay_mode, rate_mode, plastic_ei, noise_mode, exact, homeostasis;
   int32_t ho_inh, variant_g;  // see snn_config
-  int32_t exp_flags;  // snn_config.reserved[1]: 2 = kernel timeline, 4 = nothing overlaps the learn pass, 8 = 256-thread neuron blocks, 512 = LSU pass
+  int32_t exp_flags;  // diagnostics (Options): 2 = kernel timeline, 4 = nothing overlaps the learn pass, 8 = 256-thread neuron blocks, 512 = LSU pass
   // neuron partition (multi-GPU): this rank integrates neurons [part_lo, part_hi)
   // and holds every synapse whose POST is in that range; spike bitmaps are exchanged per step
   int64_t part_lo, part_hi;
@@ -237,6 +256,38 @@ __device__ __forceinline__ void st4(double* p, const Vec4<double>& v) {
 __device__ __forceinline__ int wrap_slot(int s, int R) { return s >= R ? s - R : (s < 0 ? s + R : s); }
 
 // ---------------------------------------------------------------------------------------------
+// Spike history -> STDP trace (see DevNet::hist).  `t` is the step the calling kernel works on, `s` the
+// step whose trace is wanted (t - Dmax <= s <= t).  Two phases so that callers keep several gathers
+// in flight: hist_fetch issues the 8-byte load (L2: the kernel that writes hist runs concurrently),
+// trace_resolve finishes.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int2 hist_fetch(const int2* __restrict__ hist, uint32_t i) { return __ldcg(hist + i); }
+// more than two spikes of i after step s (the neuron chain is up to kLag steps ahead): walk the bitmap
+// ring back from s; anything older than the ring's guaranteed part has been retired into old_last
+// (arguments by value: a reference to the by-value kernel parameter DevNet would force the whole struct
+// into a local-memory copy in every kernel that can reach this call)
+static __device__ __noinline__ int32_t last_spike_slow(const uint32_t* __restrict__ bits, const int32_t* __restrict__ old_last,
+                                                       int R, int W, int G, uint32_t i, int32_t s, int32_t t) {
+  const int32_t x_lo = t - G + 1;
+  for (int32_t x = s; x >= x_lo && x >= 0; --x) {
+    const uint32_t word = __ldcg(bits + (size_t)(x % R) * W + (i >> 5));
+    if ((word >> (i & 31)) & 1u) return x;
+  }
+  return __ldcg(old_last + i);
+}
+template <typename T>
+__device__ __forceinline__ T trace_resolve(const DevNet<T>& p, const int2 h, uint32_t i, int32_t s, int32_t t) {
+  const int32_t ls = h.x <= s ? h.x : (h.y <= s ? h.y : last_spike_slow(p.bits, p.old_last, p.R, p.W, p.G, i, s, t));
+  if (ls == kNever) return (T)0;
+  const int32_t n = s - ls;
+  return __ldg(p.tseq + (n < p.tseq_len ? n : p.tseq_len - 1));
+}
+template <typename T>
+__device__ __forceinline__ T trace_at(const DevNet<T>& p, uint32_t i, int32_t s, int32_t t) {
+  return trace_resolve<T>(p, hist_fetch(p.hist, i), i, s, t);
+}
+
+// ---------------------------------------------------------------------------------------------
 // View of the (w, sd) storage while a learn pass may be in flight.  Read ONCE per kernel: a stale
 // (smaller) frontier is always safe — the synapse is then simply treated as not yet processed.
 // All accesses go to L2 (ld.cg / red): the L1 of this SM may not see another kernel's writes.
@@ -289,7 +340,7 @@ __device__ __forceinline__ T w_resolve(const DevNet<T>& p, const typename Real2<
                                        uint32_t inst, T c) {
   if (!(fly && plastic)) return p.lazy ? c : ws.x;  // non-plastic weights never change: both buffers hold them
   const T x = p.lazy ? Ops<T>::sub(Ops<T>::add(c, Ops<T>::mul(p.lzH[inst], ws.x)), ws.y)
-                     : Ops<T>::add(ws.x, Ops<T>::mul(p.lg[inst], ws.y));
+                     : Ops<T>::add(ws.x, Ops<T>::mul(__ldcg(p.lg + inst), ws.y));
   return x > p.wmax ? p.wmax : (x < p.wmin ? p.wmin : x);
 }
 // sd[e] += delta (production mode: unordered reductions).  A synapse the pass in flight has not
@@ -339,6 +390,18 @@ __device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, u
 // flight per warp and ran at 0.5 TB/s — profiles/r1a), one Philox4x32 call yields the four noise
 // values.  A warp covers 128 neurons = 4 bitmap words.  Arrays are padded to Nld.
 // ---------------------------------------------------------------------------------------------
+// The spikes of step t - G leave the part of the bitmap ring a reader may rely on: remember them per neuron
+// (detect(t) of every step, all threads of the neuron grid share the ~N*rate entries of that step's list).
+template <typename T>
+__device__ __forceinline__ void retire_spikes(const DevNet<T>& p, int64_t t, uint32_t gtid, uint32_t nth) {
+  const int64_t xr = t - p.G;
+  if (xr < 0) return;
+  const int rs = (int)(xr % p.R);
+  const int cnt = __ldcg(p.spk_cnt + rs);
+  const int32_t* __restrict__ rl = p.spk_list + (size_t)rs * p.Nld;
+  for (uint32_t q = gtid; q < (uint32_t)cnt; q += nth) p.old_last[__ldcg(rl + q)] = (int32_t)xr;
+}
+
 // `bid` / `nblk`: this block's index and the block count of the neuron part (the partitioned runs
 // launch it fused with remote_body in one grid)
 template <typename T, bool EULER, bool DETECT>
@@ -349,8 +412,6 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
   const int lane = threadIdx.x & 31;
   const int64_t t = cx->t0 + k;
   const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
-  T* __restrict__ tr = p.trace + (size_t)slot * p.Nld;
-  const T* __restrict__ trp = p.trace + (size_t)prev * p.Nld;
   uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
   int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.Nld;
   int32_t* __restrict__ rec_ids = cx->rec_ids;
@@ -358,6 +419,7 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
   // spike-record offset of this step = offset of the previous step + its (final) spike count
   int32_t rec_base = 0;
   const int n_prev = (k > 0 && (rec_ids || bid == 0)) ? p.spk_cnt[prev] : 0;
+  if (DETECT) retire_spikes<T>(p, t, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
   if (rec_ids && k > 0) {
     int64_t nxt = (int64_t)cx->rec_off[k - 1] + n_prev;
     rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
@@ -397,12 +459,9 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
   for (uint32_t q = q_lo + bid * blockDim.x + threadIdx.x; q < q_hi; q += nblk * blockDim.x) {
     const uint32_t j0 = q << 2;
     // ---- all loads first
-    Vec4<T> v = ld4(p.v + j0), u = ld4(p.u + j0), I, tp, ho;
+    Vec4<T> v = ld4(p.v + j0), u = ld4(p.u + j0), I, ho;
     if (EULER) I = ld4(I_prev + j0);
-    if (DETECT) {
-      tp = ld4(trp + j0);
-      if (p.homeostasis) ho = ld4(p.ho + j0);
-    }
+    if (DETECT && p.homeostasis) ho = ld4(p.ho + j0);
     const uint32_t l0 = p.B == 1 ? j0 : j0 % Nper;
     bool exc[4], act[4];
 #pragma unroll
@@ -456,6 +515,7 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
           if (s) {
             v.x[c] = p.v_reset;
             u.x[c] = O::add(u.x[c], exc[c] ? p.d_exc : p.d_inh);
+            p.hist[j0 + c] = make_int2((int32_t)t, __ldcg(p.hist + j0 + c).x);  // trace set (new_net.jl:123), see DevNet::hist
           }
         }
         if (p.homeostasis) {
@@ -465,10 +525,8 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
           if (s && (exc[c] || p.ho_inh) && (int64_t)l >= p.ho_from) h = O::add(h, p.theta);
           ho.x[c] = O::mul(h, p.ttheta);
         }
-        tp.x[c] = s ? p.trace_set : (t > 0 ? O::mul(tp.x[c], p.trace_decay) : (T)0);
         nib |= (s ? 1u : 0u) << c;
       }
-      st4(tr + j0, tp);
       if (p.homeostasis) st4(p.ho + j0, ho);
       // 8 lanes x 4 neurons = one 32-bit bitmap word
       unsigned word = nib << ((lane & 7) << 2);
@@ -568,23 +626,21 @@ __device__ __forceinline__ uint32_t ll_word(const DevNet<T>& p, int slot, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-// remote_kernel(k) — neuron-partitioned runs only.  After the spike bitmap of step k has been
-// all-gathered, every rank replays detect(k) for the neurons it does NOT own: trace set/decay
-// (the replicated pre-trace ring that LTP gathers from), spike-list append, spike record and the
-// delay-1 current push of remote spikers into local targets.  Same quad/warp mapping as
-// neuron_kernel; no v/u traffic (16 B/neuron).
+// remote_kernel(k) — neuron-partitioned runs only.  After the spike bitmap of step k has arrived from the
+// peers, every rank replays detect(k) for the neurons it does NOT own.  The work is O(spikes), not
+// O(neurons): one thread per FOREIGN BITMAP WORD (N/32 of them, ~4 % non-zero at C5) waits for the
+// word, keeps `bits` complete, and for every set bit appends to the spike list / record, rewrites the
+// neuron's spike history (the traces LTP reads are derived from it, see DevNet::hist) and pushes the
+// spiker's delay-1 synapses into local targets.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void remote_body(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t wait_peers,
                                             const uint32_t bid, const uint32_t nblk) {
-  typedef Ops<T> O;
   tl_begin(p.tl, 4, k);
   const bool from_ll = wait_peers != 0;
   const int lane = threadIdx.x & 31;
   const int64_t t = cx->t0 + k;
   const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
-  T* __restrict__ tr = p.trace + (size_t)slot * p.Nld;
-  const T* __restrict__ trp = p.trace + (size_t)prev * p.Nld;
   uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
   int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.Nld;
   int32_t* __restrict__ rec_ids = cx->rec_ids;
@@ -596,56 +652,59 @@ __device__ __forceinline__ void remote_body(const DevNet<T>& p, const WindowCtx<
   }
   T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;
   const WView<T> vw = wview(p);
-  // whole warps only: the last rank's range is padded up to Nld (padding neurons are inactive)
-  const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2);
-  const uint32_t nquad = (uint32_t)(p.Nld >> 2), n_remote = nquad - (q_hi - q_lo);
-  for (uint32_t r = bid * blockDim.x + threadIdx.x; r < n_remote; r += nblk * blockDim.x) {
-    const uint32_t q = r < q_lo ? r : r + (q_hi - q_lo);  // part bounds are multiples of 128: warps stay whole
-    const uint32_t j0 = q << 2;
-    Vec4<T> tp = ld4(trp + j0);
-    uint32_t word;
-    if (from_ll) {  // peer-to-peer exchange: wait for the owner's (word, step) pair, keep `bits` complete
-      word = ll_word<T>(p, slot, j0 >> 5, (uint32_t)(t + 1));
-      if ((lane & 7) == 0) bits[j0 >> 5] = word;
-    } else {
-      word = bits[j0 >> 5];
+  // partition bounds are multiples of 128 neurons = 4 words (the last rank's range is padded up to Nld)
+  const uint32_t w_lo = (uint32_t)(p.part_lo >> 5), w_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 5);
+  const uint32_t n_remote = (uint32_t)p.W - (w_hi - w_lo);
+  const uint32_t tag = (uint32_t)(t + 1);
+  for (uint32_t rb = bid * blockDim.x + (threadIdx.x & ~31u); rb < n_remote; rb += nblk * blockDim.x) {
+    const uint32_t r = rb + lane;
+    uint32_t word = 0, wi = 0;
+    if (r < n_remote) {
+      wi = r < w_lo ? r : r + (w_hi - w_lo);
+      if (from_ll) {  // peer-to-peer exchange: wait for the owner's (word, step) pair, keep `bits` complete
+        word = ll_word<T>(p, slot, wi, tag);
+        bits[wi] = word;
+      } else {
+        word = bits[wi];
+      }
     }
-    const unsigned nib = (word >> (j0 & 31)) & 0xFu;
+    const unsigned busy = __ballot_sync(0xffffffffu, word != 0u);
+    if (!busy) continue;
+    // list positions: warp-wide exclusive scan of the per-lane spike counts, one atomic per warp
+    const int cnt = __popc(word);
+    int incl = cnt;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const bool s = (nib >> c) & 1u;
-      tp.x[c] = s ? p.trace_set : (t > 0 ? O::mul(tp.x[c], p.trace_decay) : (T)0);
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
     }
-    st4(tr + j0, tp);
-    if (__any_sync(0xffffffffu, nib != 0)) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const bool s = (nib >> c) & 1u;
-        const unsigned m = __ballot_sync(0xffffffffu, s);
-        if (m) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&p.spk_cnt[slot], __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (s) {
-            const int pos = base + __popc(m & ((1u << lane) - 1u));
-            list[pos] = (int32_t)(j0 + c);
-            if (rec_ids && (int64_t)rec_base + pos < rec_cap) rec_ids[rec_base + pos] = (int32_t)(j0 + c);
-          }
-          if (!p.exact) {
-            unsigned mm = m;
-            while (mm) {
-              const int src = __ffs(mm) - 1; mm &= mm - 1;
-              const uint32_t i = __shfl_sync(0xffffffffu, j0, src) + c;
-              const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1)], s1 = p.seg[(size_t)i * (p.Dmax + 1) + 1];
-              const bool row_exc = i < (uint32_t)p.Ne;  // partitioned runs are single-instance
-              for (uint32_t e = s0 + lane; e < s1; e += 32) {
-                const uint32_t j = (uint32_t)p.post[e];
-                bool fly;
-                const typename DevNet<T>::T2 ws = w_fetch<T>(vw, e, row_exc, fly);
-                const T wc = c_fetch<T>(p, vw, e, fly);
-                atomicAdd(&I_now[j], w_resolve<T>(p, ws, fly, p.plastic_ei || j < (uint32_t)p.Ne, 0u, wc));
-              }
-            }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&p.spk_cnt[slot], total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    int pos = base + incl - cnt;
+    for (uint32_t wb = word; wb; wb &= wb - 1u) {
+      const uint32_t i = (wi << 5) + (uint32_t)(__ffs(wb) - 1);
+      list[pos] = (int32_t)i;
+      if (rec_ids && (int64_t)rec_base + pos < rec_cap) rec_ids[rec_base + pos] = (int32_t)i;
+      p.hist[i] = make_int2((int32_t)t, __ldcg(p.hist + i).x);
+      ++pos;
+    }
+    if (!p.exact) {
+      // delay-1 synapses of the remote spikers feed this very step's Euler update: warp-cooperative push
+      for (unsigned mm = busy; mm; mm &= mm - 1u) {
+        const int src = __ffs(mm) - 1;
+        const uint32_t wsrc = __shfl_sync(0xffffffffu, word, src), isrc = __shfl_sync(0xffffffffu, wi, src) << 5;
+        for (uint32_t wb = wsrc; wb; wb &= wb - 1u) {
+          const uint32_t i = isrc + (uint32_t)(__ffs(wb) - 1);
+          const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1)], s1 = p.seg[(size_t)i * (p.Dmax + 1) + 1];
+          const bool row_exc = i < (uint32_t)p.Ne;  // partitioned runs are single-instance
+          for (uint32_t e = s0 + lane; e < s1; e += 32) {
+            const uint32_t j = (uint32_t)p.post[e];
+            bool fly;
+            const typename DevNet<T>::T2 ws = w_fetch<T>(vw, e, row_exc, fly);
+            const T wc = c_fetch<T>(p, vw, e, fly);
+            atomicAdd(&I_now[j], w_resolve<T>(p, ws, fly, p.plastic_ei || j < (uint32_t)p.Ne, 0u, wc));
           }
         }
       }
@@ -745,8 +804,8 @@ gather_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
 // (delay-1 pushes of step-k spikers happen inside neuron_kernel(k).)
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool LTD, bool PUSHNEXT, bool ATOMIC>
-__global__ void __launch_bounds__(256)
-synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
+__device__ __forceinline__ void synapse_body(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2,
+                                             const uint32_t bid, const uint32_t nblk) {
   typedef Ops<T> O;
   __shared__ int cum[kMaxDelay + 2];
   __shared__ int slots[kMaxDelay + 1];
@@ -758,7 +817,7 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
   if (threadIdx.x < (unsigned)p.Dmax) {
     const int sl = wrap_slot(slot - (int)threadIdx.x, p.R);
     slots[threadIdx.x] = sl;
-    cum[threadIdx.x + 1] = p.spk_cnt[sl];
+    cum[threadIdx.x + 1] = __ldcg(p.spk_cnt + sl);
   }
   if (threadIdx.x == 0) blk_ev = 0ull;
   __syncthreads();
@@ -769,11 +828,11 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
   }
   __syncthreads();
   const int total = cum[p.Dmax];
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const uint32_t gtid = bid * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = nblk * blockDim.x;
   const uint32_t Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
   const size_t Nld = (size_t)p.Nld;
-  const T* __restrict__ tr_now = p.trace + (size_t)slot * Nld;
+  const int32_t t32 = (int32_t)t;
   const uint32_t* __restrict__ bits_now = p.bits + (size_t)slot * p.W;
   T* __restrict__ I_next = p.Iacc + (size_t)((t + 1) & 1) * Nld;
   unsigned long long n_ev = 0;
@@ -785,7 +844,7 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
     int a = 0;
     while (a + 1 < p.Dmax && cum[a + 1] <= (int)item) ++a;
     const int sl = slots[a];
-    const uint32_t i = (uint32_t)p.spk_list[(size_t)sl * Nld + (item - cum[a])];
+    const uint32_t i = (uint32_t)__ldcg(p.spk_list + (size_t)sl * Nld + (item - cum[a]));
     const uint32_t* __restrict__ sg = p.seg + (size_t)i * (p.Dmax + 1) + a;
     const uint32_t s0 = sg[0], s1 = sg[1];
     const uint32_t s2 = (PUSHNEXT && a + 1 < p.Dmax) ? sg[2] : s1;
@@ -794,7 +853,7 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
     const bool row_plastic = LTD && row_exc;
     // variant_g: the LTP term of a simultaneous post spike reads the pre trace of the step before
     const T pre_up = (row_plastic && !ATOMIC)
-                         ? O::mul(p.apost, p.trace[(size_t)(p.variant_g ? wrap_slot(sl - 1, p.R) : sl) * Nld + i]) : (T)0;
+                         ? O::mul(p.apost, trace_at<T>(p, i, t32 - a - (p.variant_g ? 1 : 0), t32)) : (T)0;
     if (LTD && gl == 0) n_ev += (s1 - s0);
     for (uint32_t e = (LTD ? s0 : s1) + gl; e < s2; e += G) {
       const uint32_t j = (uint32_t)p.post[e];
@@ -804,9 +863,9 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
         const T wc = c_fetch<T>(p, vw, e, fly);
         atomicAdd(&I_next[j], w_resolve<T>(p, ws, fly, p.plastic_ei || (j - ibase) < Ne, inst, wc));
       } else if (row_plastic && (p.plastic_ei || (j - ibase) < Ne)) {
-        const T dn = O::mul(p.apre, tr_now[j]);
+        const T dn = O::mul(p.apre, trace_at<T>(p, j, t32, t32));
         if (ATOMIC) {  // production: fire-and-forget reduction, LTP of this step comes from ltp_kernel
-          sd_add<T>(p, vw, e, -dn, blockIdx.x, inst);
+          sd_add<T>(p, vw, e, -dn, bid, inst);
           continue;
         }
         const bool jsp = (bits_now[j >> 5] >> (j & 31)) & 1u;
@@ -822,9 +881,14 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
     for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
     if ((threadIdx.x & 31) == 0 && n_ev) atomicAdd(&blk_ev, n_ev);
     __syncthreads();
-    if (threadIdx.x == 0 && blk_ev) p.blk_ev[blockIdx.x] += blk_ev;
+    if (threadIdx.x == 0 && blk_ev) p.blk_ev[bid] += blk_ev;
   }
   tl_end(p.tl, LTD ? 1 : 5, k);
+}
+template <typename T, bool LTD, bool PUSHNEXT, bool ATOMIC>
+__global__ void __launch_bounds__(256)
+synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
+  synapse_body<T, LTD, PUSHNEXT, ATOMIC>(p, cx, k, g_log2, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -835,17 +899,18 @@ synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int 
 // per lane.
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool ATOMIC>
-__global__ void __launch_bounds__(256)
-ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
+__device__ __forceinline__ void ltp_body(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2,
+                                         const uint32_t bid, const uint32_t nblk) {
   typedef Ops<T> O;
   __shared__ unsigned long long blk_ltp;
   tl_begin(p.tl, 2, k);
   const int slot = (cx->slot0 + k) % p.R;
-  const int n_now = p.spk_cnt[slot];
+  const int32_t t32 = (int32_t)(cx->t0 + k);
+  const int n_now = __ldcg(p.spk_cnt + slot);
   if (threadIdx.x == 0) blk_ltp = 0ull;
   __syncthreads();
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const uint32_t gtid = bid * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = nblk * blockDim.x;
   const size_t Nld = (size_t)p.Nld;
   const uint32_t G = 1u << g_log2;
   const uint32_t gl = gtid & (G - 1);
@@ -854,7 +919,7 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
   const WView<T> vw = wview(p);
   unsigned long long n_ltp = 0;
   for (uint32_t item = gtid >> g_log2; item < (uint32_t)n_now; item += ngroups) {
-    const int32_t j = list[item];
+    const int32_t j = __ldcg(list + item);
     const uint32_t inst = p.B == 1 ? 0u : (uint32_t)j / (uint32_t)p.Nper;
     const uint32_t c0 = p.colptr[j], c1 = c0 + p.col_npl[j];
     if (gl == 0) n_ltp += (c1 - c0);
@@ -867,27 +932,29 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
         pk[q] = ok[q] ? p.in_pre[kk] : 0u;
         e[q] = ok[q] ? p.in_syn[kk] : 0u;
       }
-      size_t toff[3];
+      // pre trace as seen at the synapse: of step t-(d-1) (DASTDP.jl:62-68; variant_g one step earlier, :65)
+      int2 hq[3];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const uint32_t i = pk[q] & kPreMask;
-        const int sl = wrap_slot(slot - (int)(pk[q] >> kPreBits), p.R);
-        toff[q] = (size_t)(p.variant_g ? wrap_slot(sl - 1, p.R) : sl) * Nld + i;  // DASTDP.jl:65 STDP[pre,msec]
         if (!ATOMIC && ok[q]) {
+          const int sl = wrap_slot(slot - (int)(pk[q] >> kPreBits), p.R);
           const uint32_t word = p.bits[(size_t)sl * p.W + (i >> 5)];
           ok[q] = !((word >> (i & 31)) & 1u);
         }
+        hq[q] = ok[q] ? hist_fetch(p.hist, i) : make_int2(kNever, kNever);
       }
       T trv[3], sdv[3];
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        trv[q] = ok[q] ? p.trace[toff[q]] : (T)0;
         sdv[q] = (!ATOMIC && ok[q]) ? vw.cur[e[q]].y : (T)0;
+        trv[q] = ok[q] ? trace_resolve<T>(p, hq[q], pk[q] & kPreMask, t32 - (int32_t)(pk[q] >> kPreBits) - (p.variant_g ? 1 : 0), t32)
+                       : (T)0;
       }
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         if (!ok[q]) continue;
-        if (ATOMIC) sd_add<T>(p, vw, e[q], O::mul(p.apost, trv[q]), p.log_ltp_base + blockIdx.x, inst);
+        if (ATOMIC) sd_add<T>(p, vw, e[q], O::mul(p.apost, trv[q]), p.log_ltp_base + bid, inst);
         else vw.cur[e[q]].y = O::add(sdv[q], O::mul(p.apost, trv[q]));
       }
     }
@@ -895,8 +962,13 @@ ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_lo
   for (int o = 16; o > 0; o >>= 1) n_ltp += __shfl_down_sync(0xffffffffu, n_ltp, o);
   if ((threadIdx.x & 31) == 0 && n_ltp) atomicAdd(&blk_ltp, n_ltp);
   __syncthreads();
-  if (threadIdx.x == 0 && blk_ltp) p.blk_ltp[blockIdx.x] += blk_ltp;
+  if (threadIdx.x == 0 && blk_ltp) p.blk_ltp[bid] += blk_ltp;
   tl_end(p.tl, 2, k);
+}
+template <typename T, bool ATOMIC>
+__global__ void __launch_bounds__(256)
+ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int g_log2) {
+  ltp_body<T, ATOMIC>(p, cx, k, g_log2, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1133,7 +1205,7 @@ __global__ void lazy_commit_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__
 // formed on the fly from the frozen buffer, its sd updates are logged.
 // ---------------------------------------------------------------------------------------------
 // learn_pass_kernel: the register-staged (LSU) version of the pass, kept as the A/B alternative of
-// learn_pass_tma_kernel (snn_config.reserved[1] & 512).  <= 64 registers: two resident blocks must
+// learn_pass_tma_kernel (snn_set_param "lsu_pass").  <= 64 registers: two resident blocks must
 // leave half of the SM's register file to the step kernels (at 128 registers two blocks owned the
 // whole file and nothing ran beside the pass).
 template <typename T>
@@ -1283,35 +1355,25 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 constexpr int kPassThreads = 256, kPassStages = 4, kPassMaxStages = 12;
 constexpr uint32_t kPassChunkBytes = 16384;
 
-template <typename T>
-__global__ void __launch_bounds__(kPassThreads)
-learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
+// one pass: blocks take tiles until the dispenser runs dry.  `q` = chunks consumed so far by this block (stage and
+// mbarrier parity continue across passes in the persistent learn role)
+template <typename T, int NT>
+__device__ __forceinline__ void learn_pass_tma_body(const DevNet<T>& p, int do_decay, const uint32_t S, uint64_t* mbar,
+                                                    uint32_t* s_tile, typename DevNet<T>::T2* const buf, uint32_t& q) {
   typedef typename DevNet<T>::T2 T2;
-  tl_begin(p.tl, 3, k);
-  extern __shared__ __align__(128) unsigned char pass_smem[];
-  __shared__ __align__(8) uint64_t mbar[kPassMaxStages];
-  const uint32_t S = (uint32_t)n_stages;
-  __shared__ uint32_t s_tile;
   constexpr uint32_t CH = kPassChunkBytes / sizeof(T2);  // synapses per chunk
-  T2* const buf = reinterpret_cast<T2*>(pass_smem);      // [kPassStages][CH]
   const uint32_t tid = threadIdx.x;
-  if (tid == 0) {
-    for (uint32_t s_ = 0; s_ < S; ++s_) mbar_init(&mbar[s_], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
   const uint64_t pol = l2_evict_first_policy();
   const uint32_t st0 = *reinterpret_cast<const volatile uint32_t*>(&p.lc->state);
   const uint32_t cur = st0 >> 31, curbit = st0 & 0x80000000u;
-  const uint32_t epoch = p.lc->epoch;
+  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(&p.lc->epoch);
   const T2* __restrict__ src = p.wsdX[cur ^ 1u];
   T2* __restrict__ dst = p.wsdX[cur];
   const uint32_t TS = p.tile_syn, U = TS >> 5;
-  uint32_t q = 0;  // chunks consumed so far by this block: stage = q % S, parity = (q / S) & 1
   for (;;) {
-    if (tid == 0) s_tile = atomicAdd(&p.lc->next_tile, 1u);
+    if (tid == 0) *s_tile = atomicAdd(&p.lc->next_tile, 1u);
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = *s_tile;
     __syncthreads();
     if (tile >= p.n_tiles) break;
     const int64_t a = (int64_t)tile * TS, z = a + TS;
@@ -1324,7 +1386,7 @@ learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
     for (; b < p.B && (int64_t)p.inst_lo[b] < z; ++b) {
       int64_t lo = max((int64_t)p.inst_lo[b], a), hi = min((int64_t)p.inst_hi[b], z);
       if (hi <= lo) continue;
-      const T g = p.lg[b];
+      const T g = __ldcg(p.lg + b);
       const int64_t r0 = (int64_t)b * p.Nper;
       auto one = [&](T2& ws, int64_t e) {
         if (!p.plastic_ei && ((int64_t)p.post[e] - r0) >= p.Ne) return;  // exc->inh: not plastic (net_res.jl:213-216)
@@ -1332,9 +1394,9 @@ learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
       };
       // bulk copies need 16-byte alignment: odd fp32 ends are done by hand
       if (sizeof(T2) == 8) {
-        if ((lo & 1) && tid == 0) { T2 ws = src[lo]; one(ws, lo); dst[lo] = ws; }
+        if ((lo & 1) && tid == 0) { T2 ws = __ldcg(src + lo); one(ws, lo); dst[lo] = ws; }
         lo = (lo + 1) & ~(int64_t)1;
-        if ((hi & 1) && hi > lo && tid == 1) { T2 ws = src[hi - 1]; one(ws, hi - 1); dst[hi - 1] = ws; }
+        if ((hi & 1) && hi > lo && tid == 1) { T2 ws = __ldcg(src + hi - 1); one(ws, hi - 1); dst[hi - 1] = ws; }
         hi &= ~(int64_t)1;
       }
       if (hi <= lo) continue;
@@ -1357,7 +1419,7 @@ learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
           // 16-byte shared-memory accesses: two synapses per thread and iteration (cnt is even)
           float4* const b4 = reinterpret_cast<float4*>(bs);
 #pragma unroll 4
-          for (uint32_t x = tid; x < (cnt >> 1); x += kPassThreads) {
+          for (uint32_t x = tid; x < (cnt >> 1); x += NT) {
             float4 r = b4[x];
             float2 s0 = make_float2(r.x, r.y), s1 = make_float2(r.z, r.w);
             one(s0, e0 + 2 * x);
@@ -1365,7 +1427,7 @@ learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
             b4[x] = make_float4(s0.x, s0.y, s1.x, s1.y);
           }
         } else {
-          for (uint32_t x = tid; x < cnt; x += kPassThreads) {
+          for (uint32_t x = tid; x < cnt; x += NT) {
             T2 ws = bs[x];
             one(ws, e0 + x);
             bs[x] = ws;
@@ -1415,6 +1477,24 @@ learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
       }
     }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPassThreads)
+learn_pass_tma_kernel(DevNet<T> p, int32_t k, int do_decay, int n_stages) {
+  typedef typename DevNet<T>::T2 T2;
+  tl_begin(p.tl, 3, k);
+  extern __shared__ __align__(128) unsigned char pass_smem[];
+  __shared__ __align__(8) uint64_t mbar[kPassMaxStages];
+  __shared__ uint32_t s_tile;
+  const uint32_t S = (uint32_t)n_stages;
+  if (threadIdx.x == 0) {
+    for (uint32_t s_ = 0; s_ < S; ++s_) mbar_init(&mbar[s_], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t q = 0;  // chunks consumed so far by this block: stage = q % S, parity = (q / S) & 1
+  learn_pass_tma_body<T, kPassThreads>(p, do_decay, S, mbar, &s_tile, reinterpret_cast<T2*>(pass_smem), q);
   tl_end(p.tl, 3, k);
 }
 
@@ -1422,9 +1502,9 @@ enum { kCtlBegin = 0, kCtlAll = 1 };
 // begin of a pass, by one block: g[b] from da as decayed by step k, flip cur, frontier = 0, new epoch
 template <typename T>
 __device__ __forceinline__ void learn_begin(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
-  const uint32_t st = p.lc->state;
+  const uint32_t st = *reinterpret_cast<const volatile uint32_t*>(&p.lc->state);
   const int64_t t = cx->t0 + k;
-  for (int b = threadIdx.x; b < p.B; b += blockDim.x) p.lg[b] = learn_rate<T>(p, p.da[(size_t)((t + 1) & 1) * p.B + b]);
+  for (int b = threadIdx.x; b < p.B; b += blockDim.x) p.lg[b] = learn_rate<T>(p, __ldcg(p.da + (size_t)((t + 1) & 1) * p.B + b));
   if (threadIdx.x == 0) {
     p.lc->state = ((st >> 31) ^ 1u) << 31;
     p.lc->epoch += 1u;
@@ -1478,7 +1558,665 @@ learn_replay_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k,
 template <typename T>
 __global__ void learn_spill_reset_kernel(DevNet<T> p) { p.lc->spilled = 0u; }
 
+// =============================================================================================
+// The persistent chain (production mode, one window = FOUR kernel launches).
+//
+// A window used to be a CUDA graph of ~4 kernels per simulated millisecond whose grids took turns on
+// the SMs (round-1 timeline: neuron start->start 20.5 us for a 15 us kernel; side kernels starting
+// 5-10 us after their dependencies were met because the neuron grid owned the register file).  Here
+// every role is ONE kernel that lives for the whole window, all four co-resident (sized on the host
+// from their register / shared-memory footprints), and steps are handed over through counters in
+// global memory (ChainCtl) instead of kernel boundaries:
+//
+//   chain_neuron_kernel   one block per SM; v and u of its neurons stay in SHARED MEMORY for the
+//                         whole window, so a step touches only Iacc (read + clear, L2-resident) and
+//                         the spike bookkeeping: 8 B per neuron and ms instead of 36.  The Philox
+//                         noise of the NEXT step is generated after the block has signalled the
+//                         current one — off the critical path, while the device-wide hand-off
+//                         (1.3 us on a B200, tools/barrier_probe.cu) is in flight.
+//   chain_synapse_kernel  LTD + next-step pushes of step k as soon as neuron(k) is complete
+//   chain_ltp_kernel      LTP of step k
+//   chain_learn_kernel    the asynchronous TMA pass of every learn step of the window (begin, tiles,
+//                         frontier = all, log replay), same double-buffer / frontier / log protocol
+//                         as the graph path
+//
+// Dependencies (the same as the graph path, as counters; `done` counters count BLOCKS, so "step k
+// complete" reads  counter >= blocks * (k + 1)):
+//   neuron(k)  : neuron(k-1) on every block [pushes of delay-1 synapses land in other blocks' Iacc],
+//                push phases 0..k-1 [Euler(k-1) consumes them], learn(k-1) begun if step k-1 learns
+//                [delay-1 pushes read w], ltp(k-kLag-1) [bounds the readers' lag, see kLag]
+//   synapse(k) : neuron(k); on a learn step the pushes for k+1 wait for learn(k) begun
+//   ltp(k)     : neuron(k)
+//   learn(k)   : LTD(k) and ltp(k) on every block; the previous pass complete and replayed
+// Every wait gives up after 2 s and raises ChainCtl::abort (the host then reports SNN_ERR_STATE):
+// a scheduling accident can cost a window, never hang the device.
+// Mutable data is read through L2 (ld.cg / volatile / acquire): nothing invalidates L1 inside a kernel.
+// =============================================================================================
+enum { kcNeuron = 0, kcPush = 1, kcLtd = 2, kcLtp = 3, kcBegun = 4, kcLearnBar = 5, kcAbort = 6, kcPassNs = 7, kcPassCnt = 8,
+       kcCounters = 9 };
+struct ChainCtl { uint32_t w[kcCounters * 32]; };  // counter c at w[c * 32]: one 128-byte line each
+struct ChainDims {
+  uint32_t NB, SB, PB, LB;   // blocks of the neuron / synapse / ltp / learn role
+  uint32_t qpb;              // quads (4 neurons) per neuron block, multiple of 32
+  int32_t n_learn;           // learn steps in this window
+  int32_t do_decay;          // sd *= sd_decay inside learn! (SNN_SD_DECAY_ON_LEARN)
+  int32_t g_arr_log2, g_ltp_log2, pass_stages;
+  int32_t thrN, thrP, thrL;  // threads per block of the neuron / ltp / learn role (synapse: 256)
+};
+// sched[0..n+1]: learn steps among steps < k ; sched[n+2 ..]: the learn steps themselves
+__device__ __forceinline__ int sched_before(const int32_t* __restrict__ sched, int k) { return sched[k]; }
+__device__ __forceinline__ bool sched_learn(const int32_t* __restrict__ sched, int k) { return sched[k + 1] != sched[k]; }
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* q) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
+  return v;
+}
+static __device__ __noinline__ bool chain_wait_slow(ChainCtl* c, int which, uint32_t target, uint32_t sleep_ns) {
+  const unsigned long long t0 = gtime_ns();
+  for (;;) {
+    if (ld_acquire_u32(&c->w[which * 32]) >= target) return true;
+    if (*reinterpret_cast<volatile uint32_t*>(&c->w[kcAbort * 32]) != 0u) return false;
+    if (gtime_ns() - t0 > 2000000000ull) { atomicExch(&c->w[kcAbort * 32], 1u + (uint32_t)which); return false; }
+    if (sleep_ns) __nanosleep(sleep_ns);
+  }
+}
+__device__ __forceinline__ bool chain_wait(ChainCtl* c, int which, uint32_t target, uint32_t sleep_ns) {
+  if (ld_acquire_u32(&c->w[which * 32]) >= target) return true;
+  return chain_wait_slow(c, which, target, sleep_ns);
+}
+// all threads of the block have finished their part (call after __syncthreads, from one thread)
+__device__ __forceinline__ void chain_arrive(ChainCtl* c, int which) {
+  __threadfence();
+  atomicAdd(&c->w[which * 32], 1u);
+}
+
+__device__ __forceinline__ Vec4<float> ld4cg(const float* p) {
+  float4 r = __ldcg(reinterpret_cast<const float4*>(p));
+  Vec4<float> o; o.x[0] = r.x; o.x[1] = r.y; o.x[2] = r.z; o.x[3] = r.w; return o;
+}
+__device__ __forceinline__ Vec4<double> ld4cg(const double* p) {
+  double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p + 2));
+  Vec4<double> o; o.x[0] = a.x; o.x[1] = a.y; o.x[2] = b.x; o.x[3] = b.y; return o;
+}
+
+constexpr int kChainNeuronThreads = 512, kChainLearnThreads = 128;
+
+// Delay-1 synapses of spiker i pushed warp-cooperatively into Iacc[t&1] — they feed the Euler update of this very
+// step (new_net.jl:116-121).  Weights of synapses the learn pass in flight has not reached are formed on the fly.
+template <typename T>
+__device__ __forceinline__ void chain_push_delay1(const DevNet<T>& p, const WView<T>& vw, const uint32_t i, const uint32_t lane,
+                                                  T* __restrict__ I_now) {
+  const uint32_t Ne = (uint32_t)p.Ne, Nper = (uint32_t)p.Nper;
+  const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1)], s1 = p.seg[(size_t)i * (p.Dmax + 1) + 1];
+  const uint32_t inst = p.B == 1 ? 0u : i / Nper, ibase = inst * Nper;
+  const bool row_exc = (i - ibase) < Ne;
+  for (uint32_t eb = s0 + lane; eb < s1; eb += 128) {  // four loads in flight per lane
+    int32_t pj[4]; typename DevNet<T>::T2 pw[4]; bool fly[4];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const uint32_t e = eb + 32 * q4;
+      pj[q4] = e < s1 ? p.post[e] : -1;
+      fly[q4] = false;
+      if (e < s1) pw[q4] = w_fetch<T>(vw, e, row_exc, fly[q4]);
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+      if (pj[q4] >= 0)
+        atomicAdd(&I_now[pj[q4]], w_resolve<T>(p, pw[q4], fly[q4], p.plastic_ei || ((uint32_t)pj[q4] - ibase) < Ne, inst, (T)0));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// chain_neuron_kernel: Euler(k-1) + detect(k) for k = 0..n over a block's own neurons (new_net.jl:111-114,
+// 120-123,130-131), state resident in shared memory: sv / su [4*qpb], sn [4*qpb] the noise of the next Euler.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kChainNeuronThreads, 2)
+chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl,
+                    const int32_t* __restrict__ sched, const ChainDims d) {
+  typedef Ops<T> O;
+  extern __shared__ __align__(16) unsigned char nsm_raw[];
+  __shared__ int s_ok;
+  __shared__ int s_nspk[2], s_base;  // spikers of this block in step k: s_nspk[k & 1] (the other one is being cleared)
+  T* const sv = reinterpret_cast<T*>(nsm_raw);
+  T* const su = sv + (size_t)4 * d.qpb;
+  T* const sn = su + (size_t)4 * d.qpb;
+  uint16_t* const s_spk = reinterpret_cast<uint16_t*>(sn + (size_t)4 * d.qpb);  // [4*qpb] this step's spikers (local ids)
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, bid = blockIdx.x, TN = blockDim.x;
+  const int n = cx->n_steps;
+  const int64_t t0 = cx->t0;
+  const uint32_t N = (uint32_t)p.N, Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
+  const uint32_t q_lo = (uint32_t)(p.part_lo >> 2), q_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2);
+  const uint32_t qb0 = q_lo + bid * d.qpb;
+  const uint32_t nq = qb0 < q_hi ? min(d.qpb, q_hi - qb0) : 0u;  // multiple of 32: warps stay whole
+  const bool philox = p.noise_mode == SNN_NOISE_PHILOX;
+  int32_t* __restrict__ rec_ids = cx->rec_ids;
+  const int64_t rec_cap = cx->rec_cap;
+
+  for (uint32_t ql = tid; ql < nq; ql += TN) {
+    st4(sv + 4 * ql, ld4(p.v + ((size_t)(qb0 + ql) << 2)));
+    st4(su + 4 * ql, ld4(p.u + ((size_t)(qb0 + ql) << 2)));
+  }
+  if (tid == 0) s_nspk[0] = s_nspk[1] = 0;
+  __syncthreads();
+  unsigned long long spikes_acc = 0;  // block 0, thread 0
+
+  for (int k = 0; k <= n; ++k) {
+    const bool euler = k > 0, detect = k < n;
+    if (tid == 0) {
+      bool ok = chain_wait(ctl, kcNeuron, d.NB * (uint32_t)k, 0);
+      if (ok && k >= 1) ok = chain_wait(ctl, kcPush, d.SB * (uint32_t)k, 0);
+      if (ok && k >= 1 && sched_learn(sched, k - 1)) ok = chain_wait(ctl, kcBegun, (uint32_t)sched_before(sched, k), 0);
+      if (ok && k > kLag) ok = chain_wait(ctl, kcLtp, d.PB * (uint32_t)(k - kLag), 0);
+      s_ok = ok ? 1 : 0;
+      s_nspk[(k + 1) & 1] = 0;  // last read in phase 3 of step k-1, which every thread has left
+    }
+    __syncthreads();
+    if (!s_ok) break;
+    tl_begin(p.tl, 0, k);
+    const int64_t t = t0 + k;
+    const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
+    uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
+    int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.Nld;
+    T* __restrict__ I_prev = p.Iacc + (size_t)((t - 1) & 1) * p.Nld;  // consumed by Euler(t-1)
+    T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;         // receives the pushes of step t
+    const T* __restrict__ noise_prev = (euler && cx->noise) ? cx->noise + (size_t)(k - 1) * p.N : nullptr;
+    int32_t rec_base = 0;
+    const int n_prev = (k > 0 && (rec_ids || bid == 0)) ? __ldcg(p.spk_cnt + prev) : 0;
+    if (rec_ids && k > 0) {
+      const int64_t nxt = (int64_t)__ldcg(cx->rec_off + (k - 1)) + n_prev;
+      rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
+    }
+    if (detect) retire_spikes<T>(p, t, bid * TN + tid, d.NB * TN);
+    WView<T> vw;
+    if (detect) vw = wview(p);
+    // dopamine (new_net.jl:131 da *= 0.995 ; newnet_DASTDP.jl:54-56 da += 0.5 after step!)
+    if (bid == 0) {
+      if (tid == 0) {
+        if (euler) {
+          spikes_acc += (unsigned long long)n_prev;
+          if (rec_ids) cx->rec_off[k] = rec_base;
+        }
+        if (detect) p.spk_cnt[wrap_slot(slot + 1, p.R)] = 0;  // next step's list (no reader is R-1 steps behind)
+      }
+      const T* __restrict__ din = p.da + (size_t)(t & 1) * p.B;
+      T* __restrict__ dout = p.da + (size_t)((t + 1) & 1) * p.B;
+      const bool evs = cx->ev_off && k > 0;
+      const int e0 = evs ? cx->ev_off[k - 1] : 0, e1 = evs ? cx->ev_off[k] : 0;
+      for (int b = tid; b < p.B; b += TN) {
+        T dv = __ldcg(din + b);
+        for (int q = e0; q < e1; ++q)
+          if (cx->ev_inst[q] == b) dv = O::add(dv, (T)cx->ev_amt[q]);
+        if (detect) dout[b] = O::mul(dv, p.da_decay);
+        else if (e1 > e0) p.da[(size_t)(t & 1) * p.B + b] = dv;  // window end: events only, in place
+      }
+    }
+
+    // ---- phase 1: total current of Euler(t-1) = noise + Iacc (new_net.jl:111,116-118), gathered into sn with every
+    // load of the thread in flight at once; Iacc is cleared for the pushes of step t+1.  (The same thread consumes the
+    // same quads in phase 2: no barrier in between.)
+    if (euler) {
+      for (uint32_t qr = tid; qr < nq; qr += 4 * TN) {
+        Vec4<T> Iq[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const uint32_t ql = qr + it * TN;
+          if (ql < nq) Iq[it] = ld4cg(I_prev + ((size_t)(qb0 + ql) << 2));
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const uint32_t ql = qr + it * TN;
+          if (ql >= nq) break;
+          const uint32_t j0 = (qb0 + ql) << 2;
+          Vec4<T> tot = Iq[it];
+          if (p.noise_mode == SNN_NOISE_REPLAY) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (j0 + c < N) tot.x[c] = O::add(noise_prev[j0 + c], tot.x[c]);
+          } else if (philox) {
+            const Vec4<T> nz = ld4(sn + 4 * ql);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tot.x[c] = O::add(nz.x[c], tot.x[c]);
+          }
+          st4(sn + 4 * ql, tot);
+          Vec4<T> z; z.x[0] = z.x[1] = z.x[2] = z.x[3] = (T)0;
+          st4(I_prev + j0, z);
+        }
+      }
+    }
+    // ---- phase 2: Euler(t-1) and detect(t) out of shared memory
+    for (uint32_t ql = tid; ql < nq; ql += TN) {  // warp-uniform trip count (nq and TN are multiples of 32)
+      const uint32_t q = qb0 + ql, j0 = q << 2;
+      Vec4<T> I;
+      if (euler) I = ld4(sn + 4 * ql);
+      Vec4<T> v = ld4(sv + 4 * ql), u = ld4(su + 4 * ql), ho;
+      if (detect && p.homeostasis) ho = ld4cg(p.ho + j0);
+      const uint32_t l0 = p.B == 1 ? j0 : j0 % Nper;
+      unsigned excm = 0, actm = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t l = l0 + c;
+        if (l >= Nper) l -= Nper;
+        excm |= (l < Ne ? 1u : 0u) << c;
+        actm |= (j0 + c < N ? 1u : 0u) << c;
+      }
+      if (euler) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (!((actm >> c) & 1u)) continue;
+          T vv = v.x[c];
+          // v = v + 0.5*((0.04*v+5)*v + 140 - u + I), twice (new_net.jl:120-121)
+#pragma unroll
+          for (int rep = 0; rep < 2; ++rep) {
+            T x = O::add(O::mul((T)0.04, vv), (T)5);
+            x = O::add(O::mul(x, vv), (T)140);
+            x = O::add(O::sub(x, u.x[c]), I.x[c]);
+            vv = O::add(vv, O::mul((T)0.5, x));
+          }
+          v.x[c] = vv;
+          u.x[c] = O::add(u.x[c], O::mul(((excm >> c) & 1u) ? p.a_exc : p.a_inh, O::sub(O::mul((T)0.2, vv), u.x[c])));  // :122
+        }
+      }
+      if (detect) {
+        unsigned nib = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          bool s = false;
+          if ((actm >> c) & 1u) {
+            const T x = p.homeostasis ? O::sub(v.x[c], ho.x[c]) : v.x[c];
+            s = p.threshold_ge ? (x >= p.vthresh) : (x > p.vthresh);
+            if (s) {
+              v.x[c] = p.v_reset;
+              u.x[c] = O::add(u.x[c], ((excm >> c) & 1u) ? p.d_exc : p.d_inh);
+            }
+          }
+          if (p.homeostasis) {
+            uint32_t l = l0 + c;
+            if (l >= Nper) l -= Nper;
+            T h = ho.x[c];
+            if (s && (((excm >> c) & 1u) || p.ho_inh) && (int64_t)l >= p.ho_from) h = O::add(h, p.theta);
+            ho.x[c] = O::mul(h, p.ttheta);
+          }
+          nib |= (s ? 1u : 0u) << c;
+        }
+        if (p.homeostasis) st4(p.ho + j0, ho);
+        st4(sv + 4 * ql, v);
+        st4(su + 4 * ql, u);
+        unsigned word = nib << ((lane & 7) << 2);  // 8 lanes x 4 neurons = one 32-bit bitmap word
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        if ((lane & 7) == 0) bits[j0 >> 5] = word;
+        // spikers (rare) only go on the block's list here: their global bookkeeping and delay-1 pushes are a chain
+        // of dependent memory round trips, done for all of them at once in phase 3
+        for (unsigned nb = nib; nb; nb &= nb - 1u) s_spk[atomicAdd(&s_nspk[k & 1], 1)] = (uint16_t)(4 * ql + (__ffs(nb) - 1));
+      } else {
+        st4(sv + 4 * ql, v);
+        st4(su + 4 * ql, u);
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: this block's spikers, all in flight together.  Thread 0 reserves the block's stretch of the global
+    // spike list while the warps push the spikers' delay-1 synapses; then list / record / spike history are written.
+    if (detect) {
+      const int nspk = s_nspk[k & 1];
+      if (nspk > 0) {
+        if (tid == 0) s_base = atomicAdd(&p.spk_cnt[slot], nspk);
+        for (int w = (int)(tid >> 5); w < nspk; w += (int)(TN >> 5))
+          chain_push_delay1<T>(p, vw, (qb0 << 2) + s_spk[w], lane, I_now);
+        __syncthreads();
+        const int base = s_base;
+        for (int w = (int)tid; w < nspk; w += (int)TN) {
+          const uint32_t j = (qb0 << 2) + s_spk[w];
+          list[base + w] = (int32_t)j;
+          if (rec_ids && (int64_t)rec_base + base + w < rec_cap) rec_ids[rec_base + base + w] = (int32_t)j;
+          p.hist[j] = make_int2((int32_t)t, __ldcg(p.hist + j).x);  // trace set (new_net.jl:123), see DevNet::hist
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0) chain_arrive(ctl, kcNeuron);
+    tl_end(p.tl, 0, k);
+    // ---- off the critical path: the noise Euler(k) will add, 13*(U-0.5) (new_net.jl:111)
+    if (detect && philox) {
+      for (uint32_t ql = tid; ql < nq; ql += TN) {
+        const uint32_t q = qb0 + ql;
+        const uint4 o = philox4x32_10(make_uint4(q, 0u, (uint32_t)t, (uint32_t)((uint64_t)t >> 32)),
+                                      make_uint2((uint32_t)p.noise_seed, (uint32_t)(p.noise_seed >> 32)));
+        Vec4<T> nz;
+        nz.x[0] = (T)philox_to_noise(o.x, p.noise_amp); nz.x[1] = (T)philox_to_noise(o.y, p.noise_amp);
+        nz.x[2] = (T)philox_to_noise(o.z, p.noise_amp); nz.x[3] = (T)philox_to_noise(o.w, p.noise_amp);
+        st4(sn + 4 * ql, nz);
+      }
+    }
+  }
+  __syncthreads();
+  if (bid == 0 && tid == 0) p.counters[0] += spikes_acc;
+  for (uint32_t ql = tid; ql < nq; ql += TN) {
+    st4(p.v + ((size_t)(qb0 + ql) << 2), ld4(sv + 4 * ql));
+    st4(p.u + ((size_t)(qb0 + ql) << 2), ld4(su + 4 * ql));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// synapse_wave (persistent chain, production mode): the same work as synapse_body — LTD on the delay-(a+1)
+// segment of every (age a, spiker) item, pushes of the adjacent delay-(a+2) segment into Iacc[(k+1)&1] — laid out
+// for memory-level parallelism instead of thread count.  A resident role has a fixed, small number of threads;
+// one group of lanes walking one item at a time made a step a serial chain of ~5 dependent DRAM round trips per
+// item (55-90 us per step at C5 while the learn pass keeps HBM busy).  Here a block takes a contiguous slice of
+// the step's items and
+//   stage A  one thread per item: spike-list entry -> its three segment bounds (all items' loads in flight at
+//            once), written to shared memory; block-wide scan of the segment lengths;
+//   stage B  one thread per SYNAPSE VISIT (balanced over the block whatever the row lengths), two visits per
+//            thread in flight: post id + weight, then the post neuron's spike history, then the reduction.
+// A step costs each block ~4 dependent round trips in total.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWaveItems = 512;
+struct WaveSmem {
+  int cum[kMaxDelay + 2];
+  int slots[kMaxDelay + 1];
+  uint32_t s0[kWaveItems], n1[kWaveItems], src[kWaveItems];
+  uint32_t off[kWaveItems + 1];
+  unsigned long long blk_ev;
+};
+
+template <typename T, bool LTD, bool PUSHNEXT>
+__device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k,
+                                             const uint32_t bid, const uint32_t nblk, WaveSmem& sm) {
+  typedef Ops<T> O;
+  tl_begin(p.tl, LTD ? 1 : 5, k);
+  const uint32_t tid = threadIdx.x, TB = blockDim.x, lane = tid & 31u;
+  const int64_t t = cx->t0 + k;
+  const int32_t t32 = (int32_t)t;
+  const int slot = (int)(((int64_t)cx->slot0 + k + p.R) % p.R);  // k may be -1 (window-start push)
+  if (tid < (uint32_t)p.Dmax) {
+    const int sl = wrap_slot(slot - (int)tid, p.R);
+    sm.slots[tid] = sl;
+    sm.cum[tid + 1] = __ldcg(p.spk_cnt + sl);
+  }
+  if (tid == 0) sm.blk_ev = 0ull;
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int a = 0; a < p.Dmax; ++a) { const int c = sm.cum[a + 1]; sm.cum[a] = acc; acc += c; }
+    sm.cum[p.Dmax] = acc;
+  }
+  __syncthreads();
+  const uint32_t total = (uint32_t)sm.cum[p.Dmax];
+  const uint32_t per = (total + nblk - 1) / nblk;
+  const uint32_t lo = min(total, bid * per), hi = min(total, lo + per);
+  const uint32_t Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
+  const size_t Nld = (size_t)p.Nld;
+  T* __restrict__ I_next = p.Iacc + (size_t)((t + 1) & 1) * Nld;
+  const WView<T> vw = wview(p);
+  unsigned long long n_ev = 0;
+  for (uint32_t r0 = lo; r0 < hi; r0 += kWaveItems) {
+    const uint32_t nitem = min((uint32_t)kWaveItems, hi - r0);
+    // ---- stage A: item -> (first synapse, LTD length, total length, spiker)
+    for (uint32_t x = tid; x < nitem; x += TB) {
+      const uint32_t item = r0 + x;
+      int a = 0;
+      while (a + 1 < p.Dmax && sm.cum[a + 1] <= (int)item) ++a;
+      const uint32_t i = (uint32_t)__ldcg(p.spk_list + (size_t)sm.slots[a] * Nld + (item - sm.cum[a]));
+      const uint32_t* __restrict__ sg = p.seg + (size_t)i * (p.Dmax + 1) + a;
+      const uint32_t g0 = sg[0], g1 = sg[1];
+      const uint32_t g2 = (PUSHNEXT && a + 1 < p.Dmax) ? sg[2] : g1;
+      const uint32_t ibase = p.B == 1 ? 0u : (i / Nper) * Nper;
+      const bool ltd_row = LTD && (i - ibase) < Ne;  // only excitatory rows are plastic: the others have no LTD visits
+      if (LTD) n_ev += (g1 - g0);
+      const uint32_t b0 = ltd_row ? g0 : g1;
+      sm.s0[x] = b0; sm.n1[x] = g1 - b0; sm.src[x] = i;
+      sm.off[x + 1] = g2 - b0;  // length; scanned below
+    }
+    __syncthreads();
+    if (tid < 32) {  // inclusive scan of off[1..nitem] by one warp, 16 consecutive items per lane
+      constexpr int PER = kWaveItems / 32;
+      const uint32_t b = lane * PER;
+      uint32_t acc = 0;
+#pragma unroll
+      for (int q = 0; q < PER; ++q) if (b + q < nitem) acc += sm.off[b + q + 1];
+      uint32_t inc = acc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += up;
+      }
+      uint32_t run = inc - acc;
+      if (lane == 0) sm.off[0] = 0u;
+#pragma unroll
+      for (int q = 0; q < PER; ++q)
+        if (b + q < nitem) { run += sm.off[b + q + 1]; sm.off[b + q + 1] = run; }
+    }
+    __syncthreads();
+    const uint32_t V = sm.off[nitem];
+    // ---- stage B: one thread per synapse visit, two in flight
+    for (uint32_t v0 = tid; v0 < V; v0 += 2 * TB) {
+      uint32_t e[2], j[2], inst[2], ibs[2]; bool ok[2], isl[2], pl[2], fly[2]; typename DevNet<T>::T2 ws[2]; int2 hq[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t v = v0 + u * TB;
+        ok[u] = v < V; isl[u] = false; pl[u] = false; fly[u] = false; e[u] = 0; j[u] = 0; inst[u] = 0; ibs[u] = 0;
+        if (!ok[u]) continue;
+        uint32_t a = 0, b = nitem;  // off[a] <= v < off[b]
+        while (b - a > 1) { const uint32_t m = (a + b) >> 1; if (sm.off[m] <= v) a = m; else b = m; }
+        const uint32_t rel = v - sm.off[a];
+        e[u] = sm.s0[a] + rel;
+        isl[u] = rel < sm.n1[a];             // inside the segment that arrives now (LTD), else a push for the next step
+        const uint32_t i = sm.src[a];
+        inst[u] = p.B == 1 ? 0u : i / Nper; ibs[u] = inst[u] * Nper;
+        j[u] = (uint32_t)p.post[e[u]];
+        if (!isl[u]) ws[u] = w_fetch<T>(vw, e[u], (i - ibs[u]) < Ne, fly[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        pl[u] = ok[u] && isl[u] && (p.plastic_ei || (j[u] - ibs[u]) < Ne);  // exc -> inh may be non-plastic (net_res.jl:213-216)
+        if (pl[u]) hq[u] = hist_fetch(p.hist, j[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        if (pl[u])             // arrives now: sd -= apre * trace_post(t)   (new_net.jl:127)
+          sd_add<T>(p, vw, e[u], -O::mul(p.apre, trace_resolve<T>(p, hq[u], j[u], t32, t32)), bid, inst[u]);
+        else if (!isl[u])      // arrives at k+1: I += w   (new_net.jl:116-118)
+          atomicAdd(&I_next[j[u]], w_resolve<T>(p, ws[u], fly[u], p.plastic_ei || (j[u] - ibs[u]) < Ne, inst[u], (T)0));
+      }
+    }
+    __syncthreads();
+  }
+  if (LTD) {
+    for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
+    if (lane == 0 && n_ev) atomicAdd(&sm.blk_ev, n_ev);
+    __syncthreads();
+    if (tid == 0 && sm.blk_ev) p.blk_ev[bid] += sm.blk_ev;
+  }
+  tl_end(p.tl, LTD ? 1 : 5, k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// chain_synapse_kernel: k = -1 (arrivals of window step 0 already in flight), then per step LTD + the pushes of
+// the next step; on a learn step the pushes wait until learn!(k) has begun (they must see its weights)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256, 5)
+chain_synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl,
+                     const int32_t* __restrict__ sched, const ChainDims d) {
+  __shared__ int s_ok;
+  __shared__ WaveSmem wsm;
+  const int n = cx->n_steps;
+  const uint32_t bid = blockIdx.x;
+  auto wait1 = [&](int which, uint32_t target) {
+    if (threadIdx.x == 0) s_ok = chain_wait(ctl, which, target, 40) ? 1 : 0;
+    __syncthreads();
+    const bool ok = s_ok != 0;
+    __syncthreads();
+    return ok;
+  };
+  auto arrive = [&](int which) {
+    __syncthreads();
+    if (threadIdx.x == 0) chain_arrive(ctl, which);
+  };
+  synapse_wave<T, false, true>(p, cx, -1, bid, d.SB, wsm);
+  arrive(kcPush);
+  for (int k = 0; k < n; ++k) {
+    if (!wait1(kcNeuron, d.NB * (uint32_t)(k + 1))) return;
+    const bool learn = sched_learn(sched, k), push_next = k + 1 < n;
+    if (push_next && !learn) {
+      synapse_wave<T, true, true>(p, cx, k, bid, d.SB, wsm);
+      arrive(kcLtd);
+      if (threadIdx.x == 0) atomicAdd(&ctl->w[kcPush * 32], 1u);  // ordered after the fence of the arrive above
+    } else {
+      synapse_wave<T, true, false>(p, cx, k, bid, d.SB, wsm);
+      arrive(kcLtd);
+      if (push_next) {
+        if (!wait1(kcBegun, (uint32_t)sched_before(sched, k) + 1u)) return;
+        synapse_wave<T, false, true>(p, cx, k, bid, d.SB, wsm);
+        arrive(kcPush);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 6)
+chain_ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl, const ChainDims d) {
+  __shared__ int s_ok;
+  const int n = cx->n_steps;
+  for (int k = 0; k < n; ++k) {
+    if (threadIdx.x == 0) s_ok = chain_wait(ctl, kcNeuron, d.NB * (uint32_t)(k + 1), 40) ? 1 : 0;
+    __syncthreads();
+    if (!s_ok) return;
+    ltp_body<T, true>(p, cx, k, d.g_ltp_log2, blockIdx.x, d.PB);
+    __syncthreads();
+    if (threadIdx.x == 0) chain_arrive(ctl, kcLtp);
+  }
+}
+
+// log replay of the pass that has just ended (all LB blocks, block-stride over the regions)
+template <typename T>
+__device__ __forceinline__ void chain_replay(const DevNet<T>& p, const uint32_t bid, const uint32_t nblk) {
+  typename DevNet<T>::T2* w = p.wsdX[*reinterpret_cast<const volatile uint32_t*>(&p.lc->state) >> 31];
+  for (uint32_t r = bid; r < p.log_regions; r += nblk) {
+    const uint32_t cnt = __ldcg(p.log_cnt + (size_t)r * kLogStride);
+    const uint32_t nn = cnt < p.log_region_cap ? cnt : p.log_region_cap;
+    const LogEntry<T>* __restrict__ lg = p.dlog + (size_t)r * p.log_region_cap;
+    for (uint32_t q = threadIdx.x; q < nn; q += blockDim.x) {
+      LogEntry<T> le;
+      le.e = __ldcg(&lg[q].e); le.d = __ldcg(&lg[q].d);
+      atomicAdd(&w[le.e].y, le.d);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && cnt) p.log_cnt[(size_t)r * kLogStride] = 0u;
+  }
+  if (*reinterpret_cast<const volatile uint32_t*>(&p.lc->spilled)) {
+    const int64_t tid = bid * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)nblk * blockDim.x;
+    for (int64_t e = tid; e < p.E; e += nth) {
+      const T dv = __ldcg(p.dsd + e);
+      if (dv != (T)0) { atomicAdd(&w[e].y, dv); p.dsd[e] = (T)0; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// chain_learn_kernel: learn!(k) (new_net.jl:135-142) of every learn step of the window, as the asynchronous
+// double-buffered TMA pass.  The role's own barrier (kcLearnBar, counts blocks) separates replay | begin |
+// tiles | frontier = all.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kChainLearnThreads)
+chain_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl,
+                   const int32_t* __restrict__ sched, const ChainDims d) {
+  typedef typename DevNet<T>::T2 T2;
+  extern __shared__ __align__(128) unsigned char pass_smem[];
+  __shared__ __align__(8) uint64_t mbar[kPassMaxStages];
+  __shared__ uint32_t s_tile;
+  __shared__ int s_ok;
+  const uint32_t S = (uint32_t)d.pass_stages, bid = blockIdx.x, LB = d.LB;
+  const int n = cx->n_steps;
+  if (threadIdx.x == 0) {
+    for (uint32_t s_ = 0; s_ < S; ++s_) mbar_init(&mbar[s_], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t q = 0, bar = 0;  // chunks consumed by this block ; barriers of the role passed so far
+  auto wait1 = [&](int which, uint32_t target) {
+    if (threadIdx.x == 0) s_ok = chain_wait(ctl, which, target, 100) ? 1 : 0;
+    __syncthreads();
+    const bool ok = s_ok != 0;
+    __syncthreads();
+    return ok;
+  };
+  auto role_barrier = [&]() {
+    __syncthreads();
+    ++bar;
+    if (threadIdx.x == 0) {
+      chain_arrive(ctl, kcLearnBar);
+      s_ok = chain_wait(ctl, kcLearnBar, LB * bar, 100) ? 1 : 0;
+    }
+    __syncthreads();
+    const bool ok = s_ok != 0;
+    __syncthreads();
+    return ok;
+  };
+  const int32_t* __restrict__ steps = sched + n + 2;
+  unsigned long long t_begin = 0;
+  for (int i = 0; i <= d.n_learn; ++i) {
+    const bool last = i == d.n_learn;           // window end: only the replay of the final pass
+    const int k = last ? n - 1 : steps[i];
+    // every sd update of the steps up to k has been issued (and none of step k+1 yet: they wait for `begun`)
+    if (!wait1(kcLtd, d.SB * (uint32_t)(k + 1))) return;
+    if (!wait1(kcLtp, d.PB * (uint32_t)(k + 1))) return;
+    if (i > 0) chain_replay<T>(p, bid, LB);
+    if (!role_barrier()) return;
+    if (last) {
+      if (bid == 0 && threadIdx.x == 0) p.lc->spilled = 0u;
+      break;
+    }
+    if (bid == 0) {
+      tl_begin(p.tl, 3, k);
+      learn_begin<T>(p, cx, k);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        t_begin = gtime_ns();
+        __threadfence();
+        atomicExch(&ctl->w[kcBegun * 32], (uint32_t)(i + 1));
+      }
+    }
+    if (!wait1(kcBegun, (uint32_t)(i + 1))) return;
+    learn_pass_tma_body<T, kChainLearnThreads>(p, d.do_decay, S, mbar, &s_tile, reinterpret_cast<T2*>(pass_smem), q);
+    if (!role_barrier()) return;
+    if (bid == 0 && threadIdx.x == 0) {
+      p.lc->state = (*reinterpret_cast<volatile uint32_t*>(&p.lc->state) & 0x80000000u) | kFrontAll;
+      __threadfence();
+      atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->w[kcPassNs * 32]), gtime_ns() - t_begin);
+      atomicAdd(&ctl->w[kcPassCnt * 32], 1u);
+    }
+    if (bid == 0) tl_end(p.tl, 3, k);
+  }
+}
+
 // ----------------------------------------------------------------------------- small helpers
+// set, set*decay, (set*decay)*decay, ... until the value no longer changes (0, a denormal, inf): out[0] = length,
+// out[1] = converged within cap.  seq == nullptr: count only.
+constexpr int32_t kTseqCap = 1 << 24;
+template <typename T>
+__global__ void tseq_build_kernel(T* seq, int32_t cap, T set, T decay, int32_t* out) {
+  T x = set;
+  int32_t n = 0, conv = 0;
+  while (n < cap) {
+    if (seq) seq[n] = x;
+    ++n;
+    const T y = Ops<T>::mul(x, decay);
+    if (y == x) { conv = 1; break; }
+    x = y;
+  }
+  out[0] = n; out[1] = conv;
+}
+// SNN_FIELD_TRACE: trace after the set of step s, times decay
+template <typename T>
+__global__ void trace_to_double_kernel(DevNet<T> p, int32_t s, double* __restrict__ out) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.N; j += (int64_t)gridDim.x * blockDim.x)
+    out[j] = (double)Ops<T>::mul(trace_at<T>(p, (uint32_t)j, s, s), p.trace_decay);
+}
 template <typename T>
 __global__ void init_state_kernel(DevNet<T> p) {
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p.Nld; j += (int64_t)gridDim.x * blockDim.x) {
@@ -1486,6 +2224,8 @@ __global__ void init_state_kernel(DevNet<T> p) {
     p.u[j] = Ops<T>::mul((T)0.2, p.v_reset);
   }
 }
+template <typename T>
+__global__ void add_scalar_kernel(T* a, T x) { *a = Ops<T>::add(*a, x); }
 template <typename T>
 __global__ void fill_kernel(T* a, int64_t n, T x) {
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) a[j] = x;
@@ -1533,6 +2273,21 @@ __global__ void probe_kernel(DevNet<T> p, const uint32_t* __restrict__ pos, int 
   out[((size_t)k * n + q) * 2 + 1] = (double)ws.y;
 }
 
+// Everything that is not part of the model: scheduling, footprints, diagnostics, the experimental learning mode.
+// Set by name through snn_set_param (the names are the quoted strings of Engine::set_param).
+struct Options {
+  int graph = 1;             // captured window graph / persistent chain (1) or plain stream-ordered launches (0)
+  int persistent = 1;        // persistent chain (1) or the captured graph (0) for production-mode windows
+  int learn_async = 0;       // 0 auto, 1 learn! always in place, 2 always the asynchronous double-buffered pass
+  int64_t learn_log_cap = 0; // asynchronous pass: total entries of the sd-update log (0 = by size)
+  int pass_blocks = 0, pass_tile_k = 0, pass_stages = 0;  // asynchronous pass of the graph path: blocks per SM, tile (K synapses), TMA stages
+  int syn_blocks = 0, ltp_blocks = 0;                     // graph path: side-kernel blocks per SM
+  int timeline = 0, serialise_pass = 0, neuron_blocks_256 = 0, lsu_pass = 0;  // diagnostics / A-B switches
+  int learn_lazy = 0;        // EXPERIMENTAL event-driven learning: dense re-basing every M learn steps (0 = the reference's rule)
+  double learn_lazy_da = 0;  //   ... and at every learn step while da exceeds this (0 = never)
+  int chain[7] = {0, 0, 0, 0, 0, 0, 0};  // persistent chain footprints, see Engine::chain_plan
+};
+
 // grow-only device buffer
 struct DevBuf {
   void* ptr = nullptr; size_t cap = 0;
@@ -1573,18 +2328,20 @@ class Engine : public IEngine {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device);
     n_sm_ = sms;
-    use_graph_ = cfg_.reserved[0] == 0;
     DevNet<T>& p = p_;
     memset(&p, 0, sizeof(p));
     p.N = cfg_.n_neurons; p.Nld = (p.N + 127) / 128 * 128; p.Nper = cfg_.n_per_instance; p.Ne = cfg_.n_exc;
     // ring: R-1 steps of history + the slot being prepared; variant_g reads one step further back
-    p.Dmax = cfg_.max_delay; p.R = p.Dmax + 2 + (cfg_.variant_g ? 1 : 0); p.B = (int32_t)(p.N / p.Nper); p.W = (int32_t)(p.Nld / 32);
+    // ring: see kLag; variant_g reads one step further back
+    p.Dmax = cfg_.max_delay; p.G = p.Dmax + kLag + (cfg_.variant_g ? 1 : 0); p.R = p.G + kLag + 1;
+    p.B = (int32_t)(p.N / p.Nper); p.W = (int32_t)(p.Nld / 32);
     const size_t N = (size_t)p.Nld;  // padded: vector accesses never leave the allocation
     SNN_CUDA_OK(cudaMalloc(&p.v, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.u, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.ho, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.Iacc, 2 * N * sizeof(T)));
-    SNN_CUDA_OK(cudaMalloc(&p.trace, (size_t)p.R * N * sizeof(T)));
+    SNN_CUDA_OK(cudaMalloc(&p.hist, N * sizeof(int2)));
+    SNN_CUDA_OK(cudaMalloc(&p.old_last, N * sizeof(int32_t)));
     SNN_CUDA_OK(cudaMalloc(&p.bits, (size_t)p.R * p.W * sizeof(uint32_t)));
     SNN_CUDA_OK(cudaMalloc(&p.spk_list, (size_t)p.R * N * sizeof(int32_t)));
     SNN_CUDA_OK(cudaMalloc(&p.spk_cnt, (size_t)p.R * sizeof(int32_t)));
@@ -1602,42 +2359,154 @@ class Engine : public IEngine {
       SNN_CUDA_OK(cudaMemcpyAsync(p.lc, &lc0, sizeof(lc0), cudaMemcpyHostToDevice, stream_));
       SNN_CUDA_OK(cudaStreamSynchronize(stream_));
     }
+    SNN_CUDA_OK(cudaMalloc(&d_chain_, sizeof(ChainCtl)));
+    SNN_CUDA_OK(cudaMallocHost(&h_chain_, sizeof(ChainCtl)));
+    memset(h_chain_, 0, sizeof(ChainCtl));
+    for (auto& e : chain_ev_) SNN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     SNN_CUDA_OK(cudaMalloc(&d_ctx_, sizeof(WindowCtx<T>)));
     SNN_CUDA_OK(cudaMallocHost(&h_ctx_, sizeof(WindowCtx<T>)));
     SNN_CUDA_OK(cudaMallocHost(&h_blk_, 2 * kMaxSynBlocks * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMemsetAsync(p.ho, 0, N * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.Iacc, 0, 2 * N * sizeof(T), stream_));
-    SNN_CUDA_OK(cudaMemsetAsync(p.trace, 0, (size_t)p.R * N * sizeof(T), stream_));
+    fill_kernel<int32_t><<<grid_for(2 * (int64_t)N), 256, 0, stream_>>>(reinterpret_cast<int32_t*>(p.hist), 2 * (int64_t)N, kNever);
+    fill_kernel<int32_t><<<grid_for((int64_t)N), 256, 0, stream_>>>(p.old_last, (int64_t)N, kNever);
     SNN_CUDA_OK(cudaMemsetAsync(p.bits, 0, (size_t)p.R * p.W * sizeof(uint32_t), stream_));
     SNN_CUDA_OK(cudaMalloc(&p.ll, (size_t)p.R * p.W * sizeof(uint2)));
     SNN_CUDA_OK(cudaMemsetAsync(p.ll, 0xFF, (size_t)p.R * p.W * sizeof(uint2), stream_));  // tag 0xffffffff: never a step
     SNN_CUDA_OK(cudaMemsetAsync(p.spk_cnt, 0, (size_t)p.R * sizeof(int32_t), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.da, 0, 2 * (size_t)p.B * sizeof(T), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(p.counters, 0, 4 * sizeof(unsigned long long), stream_));
-    p.vthresh = (T)cfg_.vthresh; p.v_reset = (T)cfg_.v_reset; p.a_exc = (T)cfg_.a_exc; p.a_inh = (T)cfg_.a_inh;
-    p.d_exc = (T)cfg_.d_exc; p.d_inh = (T)cfg_.d_inh; p.trace_set = (T)cfg_.trace_set;
-    p.trace_decay = (T)cfg_.trace_decay; p.apost = (T)cfg_.apost; p.apre = (T)cfg_.apre;
-    p.da_decay = (T)cfg_.da_decay; p.learn_base = (T)cfg_.learn_base; p.eta = (T)cfg_.eta;
-    p.wmin = (T)cfg_.wmin; p.wmax = (T)cfg_.wmax; p.sd_decay = (T)cfg_.sd_decay; p.theta = (T)cfg_.theta;
-    p.ttheta = (T)cfg_.ttheta; p.noise_amp = cfg_.noise_amp; p.noise_seed = cfg_.noise_seed;
+    load_model_scalars();
     p.ho_from = cfg_.ho_from; p.threshold_ge = cfg_.threshold_ge; p.sd_decay_mode = cfg_.sd_decay_mode;
     p.rate_mode = cfg_.rate_mode; p.plastic_ei = cfg_.plastic_ei; p.noise_mode = cfg_.noise_mode;
     p.exact = cfg_.mode == SNN_MODE_EXACT;
     p.ho_inh = cfg_.ho_inh; p.variant_g = cfg_.variant_g;
-    p.exp_flags = cfg_.reserved[1];
     p.part_lo = 0; p.part_hi = p.N;
     p.static_cur = -1;
-    if (cfg_.reserved[1] & 2) SNN_CUDA_OK(cudaMalloc(&p.tl, 2 * kTlClasses * kTlSteps * sizeof(unsigned long long)));
-    p.homeostasis = !(cfg_.theta == 0.0 && cfg_.ttheta == 1.0);
+    { const int rc = apply_options(err); if (rc) return rc; }
+    { const int rc = build_tseq(err); if (rc) return rc; }
     init_state_kernel<T><<<grid_for(p.Nld), 256, 0, stream_>>>(p);
     SNN_CUDA_OK(cudaGetLastError());
     SNN_CUDA_OK(cudaStreamSynchronize(stream_));
     return SNN_OK;
   }
 
+  // trace table: length first (one thread iterates to the fixed point of x -> x*decay), then the values
+  int build_tseq(std::string& err) {
+    DevNet<T>& p = p_;
+    int32_t* d_len = nullptr; int32_t h_len[2] = {0, 0};
+    SNN_CUDA_OK(cudaMalloc(&d_len, 2 * sizeof(int32_t)));
+    tseq_build_kernel<T><<<1, 1, 0, stream_>>>(nullptr, kTseqCap, p.trace_set, p.trace_decay, d_len);
+    SNN_CUDA_OK(cudaMemcpyAsync(h_len, d_len, sizeof(h_len), cudaMemcpyDeviceToHost, stream_));
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    if (!h_len[1]) {
+      cudaFree(d_len);
+      err = "trace_decay: set*decay^n does not reach a fixed point within 2^24 steps (use 0 <= trace_decay < 1, not within 1e-6 of 1)";
+      return SNN_ERR_INVALID;
+    }
+    T* seq = nullptr;
+    SNN_CUDA_OK(cudaMalloc(&seq, (size_t)h_len[0] * sizeof(T)));
+    tseq_build_kernel<T><<<1, 1, 0, stream_>>>(seq, h_len[0], p.trace_set, p.trace_decay, d_len);
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    cudaFree(d_len);
+    cudaFree(const_cast<T*>(p.tseq));
+    p.tseq = seq; p.tseq_len = h_len[0];
+    return SNN_OK;
+  }
+  int apply_options(std::string& err) {
+    DevNet<T>& p = p_;
+    use_graph_ = opt_.graph != 0;
+    p.exp_flags = (opt_.timeline ? 2 : 0) | (opt_.serialise_pass ? 4 : 0) | (opt_.neuron_blocks_256 ? 8 : 0) | (opt_.lsu_pass ? 512 : 0);
+    if (opt_.timeline && !p.tl) SNN_CUDA_OK(cudaMalloc(&p.tl, 2 * kTlClasses * kTlSteps * sizeof(unsigned long long)));
+    if (!opt_.timeline && p.tl) { cudaFree(p.tl); p.tl = nullptr; }
+    return SNN_OK;
+  }
+
+  // snn_set_param / snn_get_param: options by name; the model's scalars (snn_config fields) by their field name
+  int param_ref(const std::string& n, int** pi, int64_t** pl, double** pd, bool* structural) {
+    *pi = nullptr; *pl = nullptr; *pd = nullptr; *structural = false;
+    struct E { const char* name; int* i; bool st; };
+    const E ints[] = {
+        {"graph", &opt_.graph, false}, {"persistent", &opt_.persistent, false}, {"learn_async", &opt_.learn_async, true},
+        {"learn_pass_blocks", &opt_.pass_blocks, false}, {"learn_pass_tile_k", &opt_.pass_tile_k, true},
+        {"learn_pass_stages", &opt_.pass_stages, false}, {"synapse_blocks_per_sm", &opt_.syn_blocks, true},
+        {"ltp_blocks_per_sm", &opt_.ltp_blocks, true}, {"timeline", &opt_.timeline, false},
+        {"serialise_learn_pass", &opt_.serialise_pass, false}, {"neuron_blocks_256", &opt_.neuron_blocks_256, false},
+        {"lsu_pass", &opt_.lsu_pass, false}, {"learn_lazy", &opt_.learn_lazy, true},
+        {"chain_neuron_threads", &opt_.chain[0], false}, {"chain_synapse_blocks", &opt_.chain[1], false},
+        {"chain_ltp_blocks", &opt_.chain[2], false}, {"chain_ltp_threads", &opt_.chain[3], false},
+        {"chain_learn_blocks", &opt_.chain[4], false}, {"chain_learn_threads", &opt_.chain[5], false},
+        {"chain_learn_stages", &opt_.chain[6], false}};
+    for (const E& e : ints) if (n == e.name) { *pi = e.i; *structural = e.st; return 1; }
+    if (n == "learn_log_cap") { *pl = &opt_.learn_log_cap; *structural = true; return 1; }
+    if (n == "learn_lazy_da") { *pd = &opt_.learn_lazy_da; *structural = true; return 1; }
+    return 0;
+  }
+  double* model_ref(const std::string& n) {
+    struct E { const char* name; double* d; };
+    const E ds[] = {{"vthresh", &cfg_.vthresh}, {"v_reset", &cfg_.v_reset}, {"a_exc", &cfg_.a_exc}, {"a_inh", &cfg_.a_inh},
+                    {"d_exc", &cfg_.d_exc}, {"d_inh", &cfg_.d_inh}, {"trace_set", &cfg_.trace_set},
+                    {"trace_decay", &cfg_.trace_decay}, {"apost", &cfg_.apost}, {"apre", &cfg_.apre},
+                    {"da_decay", &cfg_.da_decay}, {"learn_base", &cfg_.learn_base}, {"eta", &cfg_.eta},
+                    {"wmin", &cfg_.wmin}, {"wmax", &cfg_.wmax}, {"sd_decay", &cfg_.sd_decay}, {"theta", &cfg_.theta},
+                    {"ttheta", &cfg_.ttheta}, {"noise_amp", &cfg_.noise_amp}};
+    for (const E& e : ds) if (n == e.name) return e.d;
+    return nullptr;
+  }
+  void load_model_scalars() {
+    DevNet<T>& p = p_;
+    p.vthresh = (T)cfg_.vthresh; p.v_reset = (T)cfg_.v_reset; p.a_exc = (T)cfg_.a_exc; p.a_inh = (T)cfg_.a_inh;
+    p.d_exc = (T)cfg_.d_exc; p.d_inh = (T)cfg_.d_inh; p.trace_set = (T)cfg_.trace_set;
+    p.trace_decay = (T)cfg_.trace_decay; p.apost = (T)cfg_.apost; p.apre = (T)cfg_.apre;
+    p.da_decay = (T)cfg_.da_decay; p.learn_base = (T)cfg_.learn_base; p.eta = (T)cfg_.eta;
+    p.wmin = (T)cfg_.wmin; p.wmax = (T)cfg_.wmax; p.sd_decay = (T)cfg_.sd_decay; p.theta = (T)cfg_.theta;
+    p.ttheta = (T)cfg_.ttheta; p.noise_amp = cfg_.noise_amp; p.noise_seed = cfg_.noise_seed;
+    p.homeostasis = !(cfg_.theta == 0.0 && cfg_.ttheta == 1.0);
+  }
+  int set_param(const char* name, double value, std::string& err) override {
+    if (!name) { err = "null parameter name"; return SNN_ERR_INVALID; }
+    SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    const std::string n(name);
+    int* pi; int64_t* pl; double* pd; bool structural;
+    if (param_ref(n, &pi, &pl, &pd, &structural)) {
+      if (structural && have_topo_) { err = "parameter '" + n + "' shapes the synapse storage: set it before the synapses"; return SNN_ERR_STATE; }
+      if (value < 0) { err = "parameter '" + n + "' must be >= 0"; return SNN_ERR_INVALID; }
+      if (pi) *pi = (int)value; else if (pl) *pl = (int64_t)value; else *pd = value;
+      drop_graph();
+      return apply_options(err);
+    }
+    if (n == "noise_seed") { cfg_.noise_seed = (uint64_t)value; load_model_scalars(); drop_graph(); return SNN_OK; }
+    if (double* d = model_ref(n)) {
+      // the reference's scalars are plain mutable fields / Dict entries (net.param["..."], cfg.yml): same here,
+      // between windows.  The values are baked into the captured window: it is captured again.
+      const double old = *d;
+      *d = value;
+      if (!(cfg_.wmin <= cfg_.wmax)) { *d = old; err = "wmin must be <= wmax"; return SNN_ERR_INVALID; }
+      load_model_scalars();
+      drop_graph();
+      if (n == "trace_set" || n == "trace_decay") {
+        const int rc = build_tseq(err);
+        if (rc) { *d = old; load_model_scalars(); build_tseq(err); return rc; }
+      }
+      return SNN_OK;
+    }
+    err = "unknown parameter '" + n + "'"; return SNN_ERR_INVALID;
+  }
+  int get_param(const char* name, double* value, std::string& err) override {
+    if (!name || !value) { err = "null argument"; return SNN_ERR_INVALID; }
+    const std::string n(name);
+    int* pi; int64_t* pl; double* pd; bool structural;
+    if (param_ref(n, &pi, &pl, &pd, &structural)) { *value = pi ? (double)*pi : (pl ? (double)*pl : *pd); return SNN_OK; }
+    if (n == "noise_seed") { *value = (double)cfg_.noise_seed; return SNN_OK; }
+    if (n == "window_path") { *value = last_window_chain_ ? 2.0 : (last_window_graph_ ? 1.0 : 0.0); return SNN_OK; }  // 2 chain, 1 graph, 0 plain launches
+    if (double* d = model_ref(n)) { *value = *d; return SNN_OK; }
+    err = "unknown parameter '" + n + "'"; return SNN_ERR_INVALID;
+  }
+
   int set_topology(Topo&& topo, const double* h_w, std::string& err) override {
     SNN_CUDA_OK(cudaSetDevice(cfg_.device));
     drop_graph();
+    { const int rc = apply_options(err); if (rc) return rc; }
     topo_.release();
     topo_ = topo;
     DevNet<T>& p = p_;
@@ -1665,17 +2534,17 @@ class Engine : public IEngine {
     n_plastic_ = 0;
     for (int b = 0; b < p.B; ++b) n_plastic_ += (int64_t)inst_hi_[b] - (int64_t)inst_lo_[b];
     // production mode: second (w, sd) buffer + update log for the asynchronous learn pass
-    // reserved[4] >= 16: event-driven learning, re-basing every reserved[4]-16 learn steps (and at every
-    // learn step while da > reserved[5]/1000 when that is > 0); production mode only
+    // "learn_lazy" = M > 0: event-driven learning, re-basing every M learn steps (and at every learn step while
+    // da > "learn_lazy_da" when that is > 0); production mode only
     p.lazy = 0;
-    if (cfg_.reserved[4] >= 16) {
-      if (p.exact) { err = "event-driven learning (reserved[4] >= 16) needs SNN_MODE_FAST"; return SNN_ERR_INVALID; }
+    if (opt_.learn_lazy > 0) {
+      if (p.exact) { err = "event-driven learning (learn_lazy) needs SNN_MODE_FAST"; return SNN_ERR_INVALID; }
       if (cfg_.sd_decay_mode == SNN_SD_DECAY_EVERY_STEP) {
         err = "event-driven learning does not support SNN_SD_DECAY_EVERY_STEP"; return SNN_ERR_INVALID;
       }
       if (n_plastic_ > 0) {
-        p.lazy = std::max(1, cfg_.reserved[4] - 16);
-        p.lazy_da = cfg_.reserved[5] > 0 ? (T)(cfg_.reserved[5] * 1e-3) : (T)1e30;
+        p.lazy = std::max(1, opt_.learn_lazy);
+        p.lazy_da = opt_.learn_lazy_da > 0 ? (T)opt_.learn_lazy_da : (T)1e30;
         SNN_CUDA_OK(cudaMalloc(&p.cacc, Ea * sizeof(T)));
         SNN_CUDA_OK(cudaMemsetAsync(p.cacc, 0, Ea * sizeof(T), stream_));
         SNN_CUDA_OK(cudaMalloc(&p.lzH, 3 * (size_t)p.B * sizeof(T)));
@@ -1688,13 +2557,13 @@ class Engine : public IEngine {
         SNN_CUDA_OK(cudaStreamSynchronize(stream_));
       }
     }
-    have_async_ = !p.lazy && !p.exact && use_graph_ && cfg_.reserved[4] != 1 && n_plastic_ > 0 &&
+    have_async_ = !p.lazy && !p.exact && opt_.learn_async != 1 && n_plastic_ > 0 &&
                   cfg_.sd_decay_mode != SNN_SD_DECAY_EVERY_STEP;
     if (have_async_) {
       SNN_CUDA_OK(cudaMalloc(&p.wsdX[1], Ea * sizeof(T2)));
       const Launch g = grids();
       p.log_regions = (uint32_t)(g.gA + g.gP); p.log_ltp_base = (uint32_t)g.gA;
-      const int64_t log_cap = cfg_.reserved[5] > 0 ? cfg_.reserved[5]
+      const int64_t log_cap = opt_.learn_log_cap > 0 ? opt_.learn_log_cap
                                                   : std::min<int64_t>(std::max<int64_t>(1 << 20, n_plastic_ / 8), 1ll << 28);
       p.log_region_cap = (uint32_t)std::max<int64_t>(1, log_cap / p.log_regions);
       SNN_CUDA_OK(cudaMalloc(&p.dlog, (size_t)p.log_regions * p.log_region_cap * sizeof(LogEntry<T>)));
@@ -1702,7 +2571,7 @@ class Engine : public IEngine {
       SNN_CUDA_OK(cudaMemsetAsync(p.log_cnt, 0, (size_t)p.log_regions * kLogStride * sizeof(uint32_t), stream_));
       SNN_CUDA_OK(cudaMalloc(&p.dsd, Ea * sizeof(T)));
       SNN_CUDA_OK(cudaMemsetAsync(p.dsd, 0, Ea * sizeof(T), stream_));
-      p.tile_syn = cfg_.reserved[3] > 0 ? (uint32_t)cfg_.reserved[3] * 1024u : kTileSyn;
+      p.tile_syn = opt_.pass_tile_k > 0 ? (uint32_t)opt_.pass_tile_k * 1024u : kTileSyn;
       p.n_tiles = (uint32_t)(((int64_t)inst_hi_[p.B - 1] + p.tile_syn - 1) / p.tile_syn);
       SNN_CUDA_OK(cudaMalloc(&p.tile_done, (size_t)std::max<uint32_t>(1, p.n_tiles) * sizeof(uint32_t)));
       SNN_CUDA_OK(cudaMemsetAsync(p.tile_done, 0, (size_t)std::max<uint32_t>(1, p.n_tiles) * sizeof(uint32_t), stream_));
@@ -1735,9 +2604,17 @@ class Engine : public IEngine {
       case SNN_FIELD_V: src = p.v; break;
       case SNN_FIELD_U: src = p.u; break;
       case SNN_FIELD_HO: src = p.ho; break;
-      case SNN_FIELD_TRACE:
-        if (t_ == 0) { if (count != p.N) { err = "count mismatch"; return SNN_ERR_INVALID; } std::fill(host, host + count, 0.0); return SNN_OK; }
-        src = p.trace + (size_t)slot_host(t_ - 1) * p.Nld; scale = cfg_.trace_decay; break;
+      case SNN_FIELD_TRACE: {
+        // the reference holds the post-decay value between calls (new_net.jl:130): trace after step t-1, times decay
+        if (count != p.N) { err = "count mismatch"; return SNN_ERR_INVALID; }
+        if (t_ == 0) { std::fill(host, host + count, 0.0); return SNN_OK; }
+        SNN_CUDA_OK(b_stage_.reserve(p.N * sizeof(double)));
+        double* d = b_stage_.as<double>();
+        trace_to_double_kernel<T><<<grid_for(p.N), 256, 0, stream_>>>(p, (int32_t)(t_ - 1), d);
+        SNN_CUDA_OK(cudaMemcpyAsync(host, d, p.N * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+        return SNN_OK;
+      }
       case SNN_FIELD_DA: src = p.da + (size_t)(t_ & 1) * p.B; n = p.B; break;
       case SNN_FIELD_I:
         if (!p.exact) { err = "FIELD_I is only kept in SNN_MODE_EXACT"; return SNN_ERR_INVALID; }
@@ -1747,12 +2624,11 @@ class Engine : public IEngine {
         if (count != p.E) { err = "count mismatch"; return SNN_ERR_INVALID; }
         if (p.E == 0) return SNN_OK;
         { const int rcf = lazy_to_api(err); if (rcf) return rcf; }
-        double* d = nullptr;
-        SNN_CUDA_OK(cudaMalloc(&d, p.E * sizeof(double)));
+        SNN_CUDA_OK(b_stage_.reserve(p.E * sizeof(double)));
+        double* d = b_stage_.as<double>();
         wsd_to_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(p.wsdX[cur_], topo_.perm, d, p.E, field == SNN_FIELD_W ? 0 : 1);
         cudaError_t e = cudaMemcpyAsync(host, d, p.E * sizeof(double), cudaMemcpyDeviceToHost, stream_);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
-        cudaFree(d);
         { const int rcf = lazy_from_api(err); if (rcf) return rcf; }
         if (e != cudaSuccess) { err = cudaGetErrorString(e); return SNN_ERR_CUDA; }
         return SNN_OK;
@@ -1760,13 +2636,13 @@ class Engine : public IEngine {
       default: err = "unknown field"; return SNN_ERR_INVALID;
     }
     if (count != n) { err = "count mismatch"; return SNN_ERR_INVALID; }
-    double* d = nullptr;
-    SNN_CUDA_OK(cudaMalloc(&d, n * sizeof(double)));
+    // persistent staging buffer: the closed-loop callers (reward / dopamine experiments) read a few scalars per
+    // window, and a cudaMalloc + cudaFree pair per call cost more than the window itself
+    SNN_CUDA_OK(b_stage_.reserve(n * sizeof(double)));
+    double* d = b_stage_.as<double>();
     to_double_kernel<T><<<grid_for(n), 256, 0, stream_>>>(src, d, n, scale);
-    cudaError_t e = cudaMemcpyAsync(host, d, n * sizeof(double), cudaMemcpyDeviceToHost, stream_);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
-    cudaFree(d);
-    if (e != cudaSuccess) { err = cudaGetErrorString(e); return SNN_ERR_CUDA; }
+    SNN_CUDA_OK(cudaMemcpyAsync(host, d, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
     return SNN_OK;
   }
 
@@ -1792,24 +2668,133 @@ class Engine : public IEngine {
       default: err = "field is not settable"; return SNN_ERR_INVALID;
     }
     if (count != n) { err = "count mismatch"; return SNN_ERR_INVALID; }
-    double* d = nullptr;
-    SNN_CUDA_OK(cudaMalloc(&d, n * sizeof(double)));
-    cudaError_t e = cudaMemcpyAsync(d, host, n * sizeof(double), cudaMemcpyHostToDevice, stream_);
+    SNN_CUDA_OK(b_stage_.reserve(n * sizeof(double)));
+    double* d = b_stage_.as<double>();
+    SNN_CUDA_OK(cudaMemcpyAsync(d, host, n * sizeof(double), cudaMemcpyHostToDevice, stream_));
     from_double_kernel<T><<<grid_for(n), 256, 0, stream_>>>(d, dst, n);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
-    cudaFree(d);
-    if (e != cudaSuccess) { err = cudaGetErrorString(e); return SNN_ERR_CUDA; }
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));  // `host` is pageable memory of the caller
     return SNN_OK;
   }
 
+  // net.da += amount between two step! calls (newnet_DASTDP.jl:54-56): one tiny kernel, stream-ordered with the
+  // windows, no host round trip (same rounding as the device type: da (T) + amount (T))
   int add_dopamine(int instance, double amount, std::string& err) override {
     if (instance < 0 || instance >= p_.B) { err = "instance out of range"; return SNN_ERR_INVALID; }
-    std::vector<double> da(p_.B);
-    int rc = get_array(SNN_FIELD_DA, da.data(), p_.B, err);
+    SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    add_scalar_kernel<T><<<1, 1, 0, stream_>>>(p_.da + (size_t)(t_ & 1) * p_.B + instance, (T)amount);
+    SNN_CUDA_OK(cudaGetLastError());
+    return SNN_OK;
+  }
+
+  // ---- checkpoint / resume: EVERYTHING a window depends on, delays in flight included — neuron state, dopamine,
+  // (w, sd), the spike history the traces derive from, and the delay ring (per-step spike lists + bitmaps + the
+  // currents already pushed).  The blob is only meaningful for a handle with the same configuration and synapses.
+  struct CkptHeader {
+    uint64_t magic; int32_t version, dtype;
+    int64_t N, Nld, E, t;
+    int32_t Dmax, R, B, W, cur, pad;
+    int64_t list_total;   // entries of the R spike lists, concatenated
+    uint64_t topo_sum;    // cheap fingerprint of the synapse layout (sum of post ids and segment table)
+  };
+  static constexpr uint64_t kCkptMagic = 0x534e4e434b503033ull;  // "SNNCKP03"
+  int64_t ckpt_bytes_for(int64_t list_total) const {
+    const DevNet<T>& p = p_;
+    const int64_t Nld = p.Nld;
+    return (int64_t)sizeof(CkptHeader) + Nld * (int64_t)sizeof(T) * 5                 // v, u, ho, Iacc[2]
+           + Nld * (int64_t)(sizeof(int2) + sizeof(int32_t))                           // hist, old_last
+           + (int64_t)p.R * p.W * (int64_t)sizeof(uint32_t) + (int64_t)p.R * (int64_t)sizeof(int32_t)  // bits, spk_cnt
+           + list_total * (int64_t)sizeof(int32_t) + 2 * (int64_t)p.B * (int64_t)sizeof(T)              // lists, da
+           + p.E * (int64_t)sizeof(typename DevNet<T>::T2);
+  }
+  int ckpt_counts(std::vector<int32_t>& cnt, int64_t& total, std::string& err) {
+    cnt.assign(p_.R, 0);
+    SNN_CUDA_OK(cudaMemcpyAsync(cnt.data(), p_.spk_cnt, (size_t)p_.R * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    total = 0;
+    for (int32_t c : cnt) total += c;
+    return SNN_OK;
+  }
+  uint64_t topo_fingerprint() const { return (uint64_t)p_.E * 0x9E3779B97F4A7C15ull ^ (uint64_t)p_.N * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)n_plastic_; }
+  int checkpoint_bytes(int64_t* bytes, std::string& err) override {
+    if (!have_topo_) { err = "synapses not set"; return SNN_ERR_STATE; }
+    SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    std::vector<int32_t> cnt; int64_t total = 0;
+    const int rc = ckpt_counts(cnt, total, err);
     if (rc) return rc;
-    // same rounding as the device type: da (T) + amount (T)
-    da[instance] = (double)((T)da[instance] + (T)amount);
-    return set_array(SNN_FIELD_DA, da.data(), p_.B, err);
+    *bytes = ckpt_bytes_for(total);
+    return SNN_OK;
+  }
+  int checkpoint(void* buf, int64_t bytes, std::string& err) override {
+    if (!have_topo_) { err = "synapses not set"; return SNN_ERR_STATE; }
+    SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    { const int rcf = lazy_to_api(err); if (rcf) return rcf; }
+    DevNet<T>& p = p_;
+    std::vector<int32_t> cnt; int64_t total = 0;
+    int rc = ckpt_counts(cnt, total, err);
+    if (rc) return rc;
+    if (bytes < ckpt_bytes_for(total)) { err = "checkpoint buffer too small (ask snn_checkpoint_bytes right before)"; return SNN_ERR_CAPACITY; }
+    unsigned char* o = static_cast<unsigned char*>(buf);
+    CkptHeader h; memset(&h, 0, sizeof(h));
+    h.magic = kCkptMagic; h.version = 3; h.dtype = cfg_.dtype; h.N = p.N; h.Nld = p.Nld; h.E = p.E; h.t = t_;
+    h.Dmax = p.Dmax; h.R = p.R; h.B = p.B; h.W = p.W; h.cur = cur_; h.list_total = total; h.topo_sum = topo_fingerprint();
+    memcpy(o, &h, sizeof(h)); o += sizeof(h);
+    auto put = [&](const void* d, size_t n) {
+      cudaError_t e = n ? cudaMemcpyAsync(o, d, n, cudaMemcpyDeviceToHost, stream_) : cudaSuccess;
+      o += n;
+      return e;
+    };
+    const size_t Nld = (size_t)p.Nld;
+    SNN_CUDA_OK(put(p.v, Nld * sizeof(T))); SNN_CUDA_OK(put(p.u, Nld * sizeof(T))); SNN_CUDA_OK(put(p.ho, Nld * sizeof(T)));
+    SNN_CUDA_OK(put(p.Iacc, 2 * Nld * sizeof(T)));
+    SNN_CUDA_OK(put(p.hist, Nld * sizeof(int2))); SNN_CUDA_OK(put(p.old_last, Nld * sizeof(int32_t)));
+    SNN_CUDA_OK(put(p.bits, (size_t)p.R * p.W * sizeof(uint32_t)));
+    memcpy(o, cnt.data(), (size_t)p.R * sizeof(int32_t)); o += (size_t)p.R * sizeof(int32_t);
+    for (int sl = 0; sl < p.R; ++sl) SNN_CUDA_OK(put(p.spk_list + (size_t)sl * Nld, (size_t)cnt[sl] * sizeof(int32_t)));
+    SNN_CUDA_OK(put(p.da, 2 * (size_t)p.B * sizeof(T)));
+    SNN_CUDA_OK(put(p.wsdX[cur_], (size_t)p.E * sizeof(typename DevNet<T>::T2)));
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    return lazy_from_api(err);
+  }
+  int restore(const void* buf, int64_t bytes, std::string& err) override {
+    if (!have_topo_) { err = "set the synapses (same topology) before snn_restore"; return SNN_ERR_STATE; }
+    SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    DevNet<T>& p = p_;
+    if (bytes < (int64_t)sizeof(CkptHeader)) { err = "not a checkpoint"; return SNN_ERR_INVALID; }
+    const unsigned char* in = static_cast<const unsigned char*>(buf);
+    CkptHeader h; memcpy(&h, in, sizeof(h)); in += sizeof(h);
+    if (h.magic != kCkptMagic || h.version != 3) { err = "not a checkpoint of this library version"; return SNN_ERR_INVALID; }
+    if (h.dtype != cfg_.dtype || h.N != p.N || h.Nld != p.Nld || h.E != p.E || h.Dmax != p.Dmax || h.R != p.R || h.B != p.B ||
+        h.W != p.W || h.topo_sum != topo_fingerprint()) {
+      err = "checkpoint belongs to a different network (dtype / size / delays / synapse count)"; return SNN_ERR_INVALID;
+    }
+    if (bytes < ckpt_bytes_for(h.list_total)) { err = "checkpoint truncated"; return SNN_ERR_INVALID; }
+    { const int rcf = lazy_to_api(err); if (rcf) return rcf; }
+    drop_graph();
+    auto get = [&](void* d, size_t n) {
+      cudaError_t e = n ? cudaMemcpyAsync(d, in, n, cudaMemcpyHostToDevice, stream_) : cudaSuccess;
+      in += n;
+      return e;
+    };
+    const size_t Nld = (size_t)p.Nld;
+    SNN_CUDA_OK(get(p.v, Nld * sizeof(T))); SNN_CUDA_OK(get(p.u, Nld * sizeof(T))); SNN_CUDA_OK(get(p.ho, Nld * sizeof(T)));
+    SNN_CUDA_OK(get(p.Iacc, 2 * Nld * sizeof(T)));
+    SNN_CUDA_OK(get(p.hist, Nld * sizeof(int2))); SNN_CUDA_OK(get(p.old_last, Nld * sizeof(int32_t)));
+    SNN_CUDA_OK(get(p.bits, (size_t)p.R * p.W * sizeof(uint32_t)));
+    std::vector<int32_t> cnt(p.R);
+    memcpy(cnt.data(), in, (size_t)p.R * sizeof(int32_t));
+    int64_t total = 0;
+    for (int32_t c : cnt) { if (c < 0 || c > p.Nld) { err = "checkpoint corrupt (spike-list length)"; return SNN_ERR_INVALID; } total += c; }
+    if (total != h.list_total) { err = "checkpoint corrupt (spike-list total)"; return SNN_ERR_INVALID; }
+    SNN_CUDA_OK(get(p.spk_cnt, (size_t)p.R * sizeof(int32_t)));
+    for (int sl = 0; sl < p.R; ++sl) SNN_CUDA_OK(get(p.spk_list + (size_t)sl * Nld, (size_t)cnt[sl] * sizeof(int32_t)));
+    SNN_CUDA_OK(get(p.da, 2 * (size_t)p.B * sizeof(T)));
+    const unsigned char* wsd_src = in;
+    SNN_CUDA_OK(get(p.wsdX[cur_], (size_t)p.E * sizeof(typename DevNet<T>::T2)));
+    if (p.wsdX[1] != p.wsdX[0])  // the other buffer holds the same weights (non-plastic ones are read from either)
+      SNN_CUDA_OK(cudaMemcpyAsync(p.wsdX[cur_ ^ 1], wsd_src, (size_t)p.E * sizeof(typename DevNet<T>::T2), cudaMemcpyHostToDevice, stream_));
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    t_ = h.t;
+    return lazy_from_api(err);
   }
 
   int reset_v(std::string& err) override {
@@ -1828,8 +2813,8 @@ class Engine : public IEngine {
     if (p_.B != 1) { err = "neuron partitioning applies to a single network instance"; return SNN_ERR_INVALID; }
     const bool whole = lo == 0 && hi == p_.N;
     if (t_ != 0) { err = "set the partition before the first step"; return SNN_ERR_STATE; }
-    if (!whole && (p_.lazy || cfg_.reserved[4] >= 16)) {
-      err = "event-driven learning (reserved[4] >= 16) has not been validated on neuron-partitioned runs"; return SNN_ERR_INVALID;
+    if (!whole && (p_.lazy || opt_.learn_lazy > 0)) {
+      err = "event-driven learning (learn_lazy) has not been validated on neuron-partitioned runs"; return SNN_ERR_INVALID;
     }
     drop_graph();
     p_.part_lo = lo; p_.part_hi = hi;
@@ -1838,7 +2823,7 @@ class Engine : public IEngine {
   }
 
   int get_timeline(unsigned long long* host, int64_t count, std::string& err) override {
-    if (!p_.tl) { err = "timeline recording is off (snn_config.reserved[1] & 2)"; return SNN_ERR_STATE; }
+    if (!p_.tl) { err = "timeline recording is off (snn_set_param \"timeline\" = 1 before the synapses are set)"; return SNN_ERR_STATE; }
     if (count != 2 * kTlClasses * kTlSteps) { err = "timeline count mismatch"; return SNN_ERR_INVALID; }
     SNN_CUDA_OK(cudaSetDevice(cfg_.device));
     SNN_CUDA_OK(cudaMemcpy(host, p_.tl, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -1919,8 +2904,8 @@ class Engine : public IEngine {
   int upload_wsd(const double* h, int comp, int zero_other, std::string& err) {
     DevNet<T>& p = p_;
     if (p.E == 0) return SNN_OK;
-    double* d = nullptr;
-    SNN_CUDA_OK(cudaMalloc(&d, p.E * sizeof(double)));
+    SNN_CUDA_OK(b_stage_.reserve(p.E * sizeof(double)));
+    double* d = b_stage_.as<double>();
     cudaError_t e = cudaMemcpyAsync(d, h, p.E * sizeof(double), cudaMemcpyHostToDevice, stream_);
     // weights go to both buffers (non-plastic ones are read from either); sd lives in the current one
     wsd_from_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(d, topo_.perm, p.wsdX[cur_], p.E, comp, zero_other);
@@ -1928,7 +2913,6 @@ class Engine : public IEngine {
       wsd_from_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(d, topo_.perm, p.wsdX[cur_ ^ 1], p.E, comp, zero_other);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
-    cudaFree(d);
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return SNN_ERR_CUDA; }
     return SNN_OK;
   }
@@ -1938,6 +2922,7 @@ class Engine : public IEngine {
     std::vector<cudaEvent_t> prof_events;  // event record nodes are baked into the graph
   };
   void drop_graph() {
+    chain_state_ = 0;  // topology / partition / stream changed: size the persistent chain again
     for (auto& g : graphs_) {
       if (g.exec) cudaGraphExecDestroy(g.exec);
       for (auto& e : g.prof_events) cudaEventDestroy(e);
@@ -1957,15 +2942,21 @@ class Engine : public IEngine {
   void release() {
     DevNet<T>& p = p_;
     drop_graph();
-    cudaFree(p.v); cudaFree(p.u); cudaFree(p.ho); cudaFree(p.Iacc); cudaFree(p.trace); cudaFree(p.bits);
+    cudaFree(p.v); cudaFree(p.u); cudaFree(p.ho); cudaFree(p.Iacc); cudaFree(p.hist); cudaFree(p.old_last);
+    cudaFree(const_cast<T*>(p.tseq)); cudaFree(p.bits);
     cudaFree(p.spk_list); cudaFree(p.spk_cnt); cudaFree(p.da); cudaFree(p.counters); cudaFree(p.blk_ev);
     cudaFree(p.blk_ltp); free_synapse_state(); cudaFree(d_ctx_); cudaFree(p.tl); cudaFree(p.lc); cudaFree(p.lg);
     close_peers();
     cudaFree(p.ll); cudaFree(p.xdone);
     if (h_ctx_) cudaFreeHost(h_ctx_);
     if (h_blk_) cudaFreeHost(h_blk_);
+    cudaFree(d_chain_); d_chain_ = nullptr;
+    if (h_chain_) cudaFreeHost(h_chain_);
+    h_chain_ = nullptr;
+    for (auto& e : chain_ev_) { if (e) cudaEventDestroy(e); e = nullptr; }
+    b_sched_.release();
     b_noise_.release(); b_noise64_.release(); b_ev_off_.release(); b_ev_inst_.release(); b_ev_amt_.release();
-    sort_scratch_.release(); b_probe_want_.release(); b_probe_pos_.release(); b_probe_out_.release();
+    sort_scratch_.release(); b_stage_.release(); b_probe_want_.release(); b_probe_pos_.release(); b_probe_out_.release();
     b_force_.release(); b_rec_.release(); b_rec_off_.release(); b_cur_idx_.release(); b_cur_val_.release();
     topo_.release();
     if (ev_begin_) cudaEventDestroy(ev_begin_);
@@ -2008,23 +2999,25 @@ class Engine : public IEngine {
   struct Launch {
     int gN, gA, gP, gR; dim3 gL;
   };
+  int gA_cap() { return grids().gA; }
+  int gP_cap() { return grids().gP; }
   Launch grids() {
     DevNet<T>& p = p_;
     Launch l;
     const int64_t local_quads = ((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2) - (p.part_lo >> 2);
     l.gN = (int)std::max<int64_t>(1, std::min<int64_t>((local_quads + 255) / 256, (int64_t)n_sm_ * 8));
-    l.gR = (int)std::max<int64_t>(1, std::min<int64_t>((p.Nld / 4 - local_quads + 255) / 256, (int64_t)n_sm_ * 8));
+    l.gR = (int)std::max<int64_t>(1, std::min<int64_t>(((p.Nld / 4 - local_quads) / 8 + 255) / 256, (int64_t)n_sm_ * 8));  // a thread per foreign bitmap word
     if (gA_ == 0) {
       int per_sm = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, synapse_kernel<T, true, true, true>, 256, 0);
-      // reserved[7]: side-kernel footprint, tens = synapse blocks per SM, units = ltp blocks per SM
+      // "synapse_blocks_per_sm" / "ltp_blocks_per_sm": footprint of the side kernels of the graph path
       // default 6 + 2: the side kernels are persistent (their blocks live as long as the kernel), so
       // whatever they hold is not available to the next neuron kernel when it becomes ready
-      const int syn_per_sm = cfg_.reserved[7] >= 10 ? cfg_.reserved[7] / 10 : 6;
+      const int syn_per_sm = opt_.syn_blocks > 0 ? opt_.syn_blocks : 6;
       gA_ = std::min(kMaxSynBlocks, n_sm_ * std::max(1, std::min(per_sm, syn_per_sm)));
     }
     l.gA = gA_;
-    l.gP = std::min(kMaxSynBlocks, n_sm_ * ((cfg_.reserved[7] % 10) > 0 ? cfg_.reserved[7] % 10 : 2));
+    l.gP = std::min(kMaxSynBlocks, n_sm_ * (opt_.ltp_blocks > 0 ? opt_.ltp_blocks : 2));
     int64_t plastic_per_inst = p.B ? (p.E / p.B) : 0;
     int gLx = (int)std::max<int64_t>(1, std::min<int64_t>((plastic_per_inst / 2 + 256 * 4 - 1) / (256 * 4),
                                                            std::max<int64_t>(1, (int64_t)n_sm_ * 8 / p.B)));
@@ -2066,8 +3059,12 @@ class Engine : public IEngine {
   int launch_graph(const StepArgs& a, bool prof, std::string& err);
   bool async_ok(const StepArgs& a) const;
   void launch_pass(cudaStream_t s4, int k, int do_decay, bool prof);
+  bool chain_plan(std::string* why);
+  bool chain_ok(const StepArgs& a);
+  int launch_chain(const StepArgs& a, std::string& err);
 
   snn_config cfg_;
+  Options opt_;
   DevNet<T> p_;
   Topo topo_;
   bool have_topo_ = false, use_graph_ = true;
@@ -2092,11 +3089,19 @@ class Engine : public IEngine {
   unsigned long long* h_blk_ = nullptr;
   DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_, b_cur_idx_, b_cur_val_;
   SortScratch sort_scratch_;
-  DevBuf b_probe_want_, b_probe_pos_, b_probe_out_;
+  DevBuf b_probe_want_, b_probe_pos_, b_probe_out_, b_stage_;
   std::vector<void*> ipc_opened_;
   snn_exchange_fn exchange_ = nullptr; void* exchange_user_ = nullptr; int exchange_failed_ = 0;
   const std::vector<cudaEvent_t>* graph_prof_events_ = nullptr;
   std::vector<CachedGraph> graphs_;  // a few (length, train pattern, profiling) variants
+  // persistent chain
+  ChainCtl* d_chain_ = nullptr; ChainCtl* h_chain_ = nullptr;
+  DevBuf b_sched_;
+  ChainDims chain_{};
+  int chain_state_ = 0;          // 0 = not planned yet, 1 = fits, -1 = does not fit (graph path)
+  size_t chain_smem_neuron_ = 0, chain_smem_learn_ = 0;
+  bool last_window_chain_ = false, last_window_graph_ = false;
+  cudaEvent_t chain_ev_[4] = {};
 };
 
 // Plain stream-ordered launches: exact mode, forced spikes, per-kernel profiling.
@@ -2193,7 +3198,7 @@ bool Engine<T>::async_ok(const StepArgs& a) const {
     last = k; ++n_learn;
   }
   if (n_learn == 0) return false;
-  if (cfg_.reserved[4] == 2) return true;               // forced (tests on small nets)
+  if (opt_.learn_async == 2) return true;               // forced (tests on small nets)
   return n_plastic_ * 2 * (int64_t)sizeof(typename DevNet<T>::T2) >= (32ll << 20);
 }
 
@@ -2202,14 +3207,14 @@ void Engine<T>::launch_pass(cudaStream_t s4, int k, int do_decay, bool prof) {
   DevNet<T>& p = p_;
   // persistent pass: LB blocks per SM stay resident for the whole pass and leave the other
   // thread slots to the step kernels (LB x 256 threads x 8 x 16 B in flight per SM)
-  const bool lsu = (cfg_.reserved[1] & 512) != 0;  // experiment 512: register-staged (LSU) pass instead of TMA
-  const int LB = cfg_.reserved[2] > 0 ? cfg_.reserved[2] : (lsu ? 2 : 3);
+  const bool lsu = opt_.lsu_pass != 0;  // experiment: register-staged (LSU) pass instead of TMA
+  const int LB = opt_.pass_blocks > 0 ? opt_.pass_blocks : (lsu ? 2 : 3);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm_ * LB, p.n_tiles));
   if (prof) prof_begin(2, s4, true);
   if (lsu) {
     learn_pass_kernel<T><<<grid, 256, 0, s4>>>(p, k, do_decay);
   } else {
-    const int S = cfg_.reserved[6] >= 2 && cfg_.reserved[6] <= kPassMaxStages ? cfg_.reserved[6] : kPassStages;
+    const int S = opt_.pass_stages >= 2 && opt_.pass_stages <= kPassMaxStages ? opt_.pass_stages : kPassStages;
     const size_t smem = (size_t)S * kPassChunkBytes;
     if (!pass_attr_set_) {  // per engine: the attribute belongs to the (function, device) pair
       cudaFuncSetAttribute(learn_pass_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2265,8 +3270,8 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
     bool s3_used = false, pass_open = false;
     cudaEvent_t evNk[2] = {dep_ev_[0], dep_ev_[11]};
     // neuron blocks of 64 threads (4 K registers each): they slip into an SM as soon as any side block
-    // retires instead of waiting for 16 K registers to come free (+0.8 %; reserved[1] & 8: 256 threads)
-    const int nbm = (cfg_.reserved[1] & 8) ? 1 : 4;
+    // retires instead of waiting for 16 K registers to come free (+0.8 %; "neuron_blocks_256": 256 threads)
+    const int nbm = opt_.neuron_blocks_256 ? 1 : 4;
     auto cap_neuron = [&](int k) {
       int dl, dd;
       const bool learn_prev = k >= 1 && wants_learn(a, k - 1, &dl, &dd);
@@ -2317,7 +3322,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
         ++last_pass_launches_;
         cudaEventRecord(evL, s4);
         launch_pass(s4, k, dd, prof);
-        if (cfg_.reserved[1] & 4) cudaEventRecord(evL, s4);  // experiment: nothing overlaps the pass
+        if (opt_.serialise_pass) cudaEventRecord(evL, s4);  // experiment: nothing overlaps the pass
         pass_open = true;
         if (push_next) {
           cudaStreamWaitEvent(s2, evL, 0);
@@ -2394,10 +3399,155 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
   return SNN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent chain, host side.  chain_plan sizes the four roles so that ALL their blocks are resident
+// at once (registers, shared memory, threads and block slots per SM, from the compiled kernels' own
+// attributes); if that cannot be had the window falls back to the captured graph.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+bool Engine<T>::chain_plan(std::string* why) {
+  if (chain_state_ != 0) return chain_state_ > 0;
+  chain_state_ = -1;
+  DevNet<T>& p = p_;
+  auto fail = [&](const char* m) { if (why) *why = m; return false; };
+  if (p.exact || !use_graph_ || !opt_.persistent || p.lazy) return fail("mode");
+  if (cfg_.sd_decay_mode == SNN_SD_DECAY_EVERY_STEP) return fail("sd decays every step");
+  if (p.n_ranks > 1 || exchange_ || !(p.part_lo == 0 && p.part_hi == p.N)) return fail("partitioned");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg_.device) != cudaSuccess) return fail("device properties");
+  const int64_t local_quads = ((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2) - (p.part_lo >> 2);
+  ChainDims d{};
+  d.NB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(n_sm_, (local_quads + 255) / 256));
+  d.qpb = (uint32_t)(((local_quads + d.NB - 1) / d.NB + 31) / 32 * 32);
+  d.NB = (uint32_t)((local_quads + d.qpb - 1) / d.qpb);  // no empty blocks
+  const size_t smem_n = (size_t)3 * 4 * d.qpb * sizeof(T) + (size_t)4 * d.qpb * sizeof(uint16_t);
+  // work-proportional block counts: small nets get small grids (every waiting block polls the counters)
+  const int64_t ev_guess = std::max<int64_t>(1, p.E / 64);  // synapse visits per step at ~1.5 % of the neurons firing
+  // role footprints per SM (defaults measured on C5; snn_set_param "chain_*" overrides them for sweeps)
+  int tune[7] = {256, 2, 1, 256, 2, 128, 3};
+  for (int q = 0; q < 7; ++q) if (opt_.chain[q] > 0) tune[q] = opt_.chain[q];
+  const int thrN = std::min(kChainNeuronThreads, std::max(32, tune[0] / 32 * 32));
+  int syn_per_sm = tune[1], ltp_per_sm = tune[2], learn_per_sm = tune[4];
+  const int thrP = std::min(256, std::max(32, tune[3] / 32 * 32)), thrL = kChainLearnThreads;  // (tune[5] is not used any more)
+  int S = std::min(kPassMaxStages, std::max(2, tune[6]));
+  size_t smem_l = (size_t)S * kPassChunkBytes;
+  cudaFuncAttributes fa[4];
+  if (cudaFuncGetAttributes(&fa[0], chain_neuron_kernel<T>) != cudaSuccess ||      // (also loads the functions now: a
+      cudaFuncGetAttributes(&fa[1], chain_synapse_kernel<T>) != cudaSuccess ||     // lazy module load in the middle of a
+      cudaFuncGetAttributes(&fa[2], chain_ltp_kernel<T>) != cudaSuccess ||         // window would wait for the spinning
+      cudaFuncGetAttributes(&fa[3], chain_learn_kernel<T>) != cudaSuccess) {       // kernels that wait for it)
+    cudaGetLastError();
+    return fail("kernel attributes");
+  }
+  if (smem_n + fa[0].sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) return fail("neuron state does not fit in shared memory");
+  auto fits = [&](int sp, int lp, int le) {
+    const int thr[4] = {thrN, 256, thrP, thrL};
+    const int cnt[4] = {1, sp, lp, n_plastic_ > 0 && have_async_ ? le : 0};
+    const size_t dyn[4] = {smem_n, 0, 0, smem_l};
+    size_t regs = 0, smem = 0; int threads = 0, blocks = 0;
+    for (int r = 0; r < 4; ++r) {
+      regs += (size_t)cnt[r] * (size_t)((fa[r].numRegs + 7) / 8 * 8) * thr[r];
+      smem += (size_t)cnt[r] * ((dyn[r] + fa[r].sharedSizeBytes + 1024 + 127) / 128 * 128);
+      threads += cnt[r] * thr[r]; blocks += cnt[r];
+    }
+    return regs + 4096 <= (size_t)prop.regsPerMultiprocessor && smem <= (size_t)prop.sharedMemPerMultiprocessor &&
+           threads <= prop.maxThreadsPerMultiProcessor && blocks <= 32;
+  };
+  while (!fits(syn_per_sm, ltp_per_sm, learn_per_sm)) {
+    if (S > 3) { --S; smem_l = (size_t)S * kPassChunkBytes; }
+    else if (learn_per_sm > 1) --learn_per_sm;
+    else if (syn_per_sm > 1) --syn_per_sm;
+    else return fail("the four roles do not fit on an SM together");
+  }
+  d.SB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm_ * syn_per_sm, (ev_guess + 255) / 256));
+  d.PB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm_ * ltp_per_sm, (ev_guess + 255) / 256));
+  d.LB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm_ * learn_per_sm, std::max<uint32_t>(1, p.n_tiles)));
+  if (d.SB > (uint32_t)gA_cap() || d.PB > (uint32_t)gP_cap()) return fail("log regions");
+  d.g_arr_log2 = g_arr_log2_; d.g_ltp_log2 = g_ltp_log2_; d.pass_stages = S;
+  d.thrN = thrN; d.thrP = thrP; d.thrL = thrL;
+  d.do_decay = cfg_.sd_decay_mode == SNN_SD_DECAY_ON_LEARN ? 1 : 0;
+  if (cudaFuncSetAttribute(chain_neuron_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n) != cudaSuccess ||
+      cudaFuncSetAttribute(chain_learn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess) {
+    cudaGetLastError();
+    return fail("shared-memory attribute");
+  }
+  // An SM's L1 / shared-memory split cannot change while a block is resident on it: if the first role to arrive
+  // configured it for its own (smaller) need, the blocks of a role that needs more would wait for the SM to
+  // drain — forever, since the resident role waits for them.  Every role asks for the maximum split up front.
+  cudaFuncSetAttribute(chain_neuron_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(chain_synapse_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(chain_ltp_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(chain_learn_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();
+  chain_ = d; chain_smem_neuron_ = smem_n; chain_smem_learn_ = smem_l;
+  chain_state_ = 1;
+  return true;
+}
+
+template <typename T>
+bool Engine<T>::chain_ok(const StepArgs& a) {
+  if (a.n_force > 0 || a.n_cur > 0 || a.n_probes > 0 || profiling_ == 1) return false;
+  if (!chain_plan(nullptr)) return false;
+  int dl, dd, last = -1000;
+  for (int k = 0; k < a.n_steps; ++k)
+    if (wants_learn(a, k, &dl, &dd)) {
+      if (!have_async_) return false;   // no second (w, sd) buffer: the in-place pass of the graph path
+      if (k - last < 2 && opt_.learn_async != 2) return false;  // learn! at every step: nothing to run beside the pass
+      last = k;
+    }
+  return true;
+}
+
+template <typename T>
+int Engine<T>::launch_chain(const StepArgs& a, std::string& err) {
+  DevNet<T> p = p_;
+  p.static_cur = -1;  // the (w, sd) view follows LearnCtl
+  const int n = a.n_steps;
+  std::vector<int32_t> sched(n + 2, 0), steps;
+  int dl, dd;
+  for (int k = 0; k < n; ++k) {
+    const bool learn = wants_learn(a, k, &dl, &dd);
+    sched[k + 1] = sched[k] + (learn ? 1 : 0);
+    if (learn) steps.push_back(k);
+  }
+  sched[n + 1] = sched[n];
+  sched.insert(sched.end(), steps.begin(), steps.end());
+  SNN_CUDA_OK(b_sched_.reserve(sched.size() * sizeof(int32_t)));
+  SNN_CUDA_OK(cudaMemcpyAsync(b_sched_.ptr, sched.data(), sched.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+  SNN_CUDA_OK(cudaMemsetAsync(d_chain_, 0, sizeof(ChainCtl), stream_));
+  ChainDims d = chain_;
+  d.n_learn = (int32_t)steps.size();
+  cudaStream_t s0 = stream_, sN = chain_stream_, s2 = side_stream_, s3 = side2_stream_, s4 = learn_stream_;
+  cudaEvent_t evFork = dep_ev_[9];
+  // the copy of the schedule comes from pageable memory: it has been staged before the call returns
+  SNN_CUDA_OK(cudaEventRecord(evFork, s0));
+  SNN_CUDA_OK(cudaStreamWaitEvent(sN, evFork, 0));
+  SNN_CUDA_OK(cudaStreamWaitEvent(s2, evFork, 0));
+  SNN_CUDA_OK(cudaStreamWaitEvent(s3, evFork, 0));
+  // the neuron role first: its blocks (one per SM) hand a step over among themselves and must all be resident
+  chain_neuron_kernel<T><<<d.NB, d.thrN, chain_smem_neuron_, sN>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
+  chain_synapse_kernel<T><<<d.SB, 256, 0, s2>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
+  chain_ltp_kernel<T><<<d.PB, d.thrP, 0, s3>>>(p, d_ctx_, d_chain_, d);
+  if (d.n_learn > 0) {
+    SNN_CUDA_OK(cudaStreamWaitEvent(s4, evFork, 0));
+    chain_learn_kernel<T><<<d.LB, d.thrL, chain_smem_learn_, s4>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
+    SNN_CUDA_OK(cudaEventRecord(chain_ev_[3], s4));
+    SNN_CUDA_OK(cudaStreamWaitEvent(s0, chain_ev_[3], 0));
+  }
+  SNN_CUDA_OK(cudaEventRecord(chain_ev_[0], sN));
+  SNN_CUDA_OK(cudaEventRecord(chain_ev_[1], s2));
+  SNN_CUDA_OK(cudaEventRecord(chain_ev_[2], s3));
+  for (int q = 0; q < 3; ++q) SNN_CUDA_OK(cudaStreamWaitEvent(s0, chain_ev_[q], 0));
+  SNN_CUDA_OK(cudaMemcpyAsync(h_chain_, d_chain_, sizeof(ChainCtl), cudaMemcpyDeviceToHost, s0));
+  last_pass_launches_ = d.n_learn > 0 ? 1 : 0;
+  return SNN_OK;
+}
+
 template <typename T>
 int Engine<T>::step(const StepArgs& a, std::string& err) {
   if (!have_topo_) { err = "snn_step before synapses were set"; return SNN_ERR_STATE; }
   if (a.n_steps <= 0) { err = "n_steps must be > 0"; return SNN_ERR_INVALID; }
+  if (t_ + a.n_steps >= (1ll << 30)) { err = "step counter would pass 2^30 (spike steps are kept as 32-bit values): ~12 days simulated"; return SNN_ERR_STATE; }
   if (cfg_.noise_mode == SNN_NOISE_REPLAY && !a.noise) { err = "noise_mode REPLAY needs a noise array"; return SNN_ERR_INVALID; }
   if (a.spikes_out && (!a.spike_offsets || a.spikes_cap <= 0 || a.spikes_cap > 0x7fffffff)) {
     err = "spikes_out needs spike_offsets and 0 < spikes_cap < 2^31"; return SNN_ERR_INVALID;
@@ -2518,7 +3668,12 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   const bool graphable = use_graph_ && !p.exact && a.n_force == 0 && a.n_cur == 0 && profiling_ != 1 && !exchange_ &&
                          a.n_probes == 0;
   last_pass_launches_ = 0;
-  if (graphable) {
+  const bool chained = graphable && chain_ok(a);
+  last_window_chain_ = chained; last_window_graph_ = graphable && !chained;
+  if (chained) {
+    int rc = launch_chain(a, err);
+    if (rc) return rc;
+  } else if (graphable) {
     int rc = launch_graph(a, profiling_ == 2, err);
     if (rc) return rc;
   } else {
@@ -2561,6 +3716,11 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   SNN_CUDA_OK(cudaEventRecord(ev_end_, stream_));
   SNN_CUDA_OK(cudaStreamSynchronize(stream_));
   cur_ = (int)(lc_h.state >> 31);
+  if (chained && h_chain_->w[kcAbort * 32]) {
+    err = "persistent chain: a hand-off timed out (role counter " + std::to_string((int)h_chain_->w[kcAbort * 32] - 1) +
+          "); the state of the network is undefined";
+    return SNN_ERR_STATE;
+  }
   if (xdone_h[1]) {
     cudaMemsetAsync(p.xdone, 0, 2 * sizeof(uint32_t), stream_);
     err = "peer exchange timed out: a rank of the partition did not publish its spikes"; return SNN_ERR_STATE;
@@ -2589,7 +3749,15 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
       else if (cls == 1) { s.synapse_ms += m; s.synapse_launches++; }
       else { s.learn_ms += m; s.learn_launches++; }
     }
-    if (graphable) {  // launches inside the graph (events exist only around learn, if at all)
+    if (chained) {  // one kernel per role; the passes are timed on the device (%globaltimer, begin -> frontier = all)
+      unsigned long long ns = 0;
+      memcpy(&ns, &h_chain_->w[kcPassNs * 32], sizeof(ns));
+      s.neuron_ms = s.synapse_ms = 0.f;
+      s.learn_ms = (float)((double)ns * 1e-6);
+      s.learn_launches = (int32_t)h_chain_->w[kcPassCnt * 32];
+      s.neuron_launches = 1; s.synapse_launches = 2;
+      s.reserved = last_pass_launches_;
+    } else if (graphable) {  // launches inside the graph (events exist only around learn, if at all)
       s.neuron_launches = n + 1; s.synapse_launches = 2 * n + 1;
       if (profiling_ != 2) {
         int nl = 0, dl, dd;

@@ -55,18 +55,35 @@ class SparseNetwork:
         lib = L.load()
         n_per = int(n_neurons)
         max_delay = int(params.pop("max_delay", int(delay.max()) if delay is not None and len(delay) else 1))
-        use_graph = bool(params.pop("graph", True))
+        # everything that is not the model goes through snn_set_param, by name (ABI 3)
+        opts = {}
+        if not bool(params.pop("graph", True)):
+            opts["graph"] = 0          # plain stream-ordered launches instead of whole-window schedules
+        if not bool(params.pop("persistent", True)):
+            opts["persistent"] = 0     # the captured CUDA graph of per-step kernels instead of the persistent chain
         exp_flags = int(params.pop("exp_flags", 0))
-        learn_async = {"auto": 0, "off": 1, "force": 2}[params.pop("learn_async", "auto")]
-        learn_log_cap = int(params.pop("learn_log_cap", 0))
+        for bit, name in ((2, "timeline"), (4, "serialise_learn_pass"), (8, "neuron_blocks_256"), (512, "lsu_pass")):
+            if exp_flags & bit:
+                opts[name] = 1
+        if exp_flags & 1024:
+            opts["persistent"] = 0
+        opts["learn_async"] = {"auto": 0, "off": 1, "force": 2}[params.pop("learn_async", "auto")]
+        opts["learn_log_cap"] = int(params.pop("learn_log_cap", 0))
         # opt-in, production mode only: event-driven learning, one dense re-basing pass
         # every `learn_lazy` learn steps (and at every learn step while da > learn_lazy_da, if given)
-        learn_lazy = int(params.pop("learn_lazy", 0))
-        learn_lazy_da = float(params.pop("learn_lazy_da", 0.0))
-        learn_tile_k = int(params.pop("learn_tile_k", 0))
-        learn_stages = int(params.pop("learn_stages", 0))
-        side_blocks = int(params.pop("side_blocks", 0))
-        learn_blocks = int(params.pop("learn_blocks", 0))
+        opts["learn_lazy"] = int(params.pop("learn_lazy", 0))
+        opts["learn_lazy_da"] = float(params.pop("learn_lazy_da", 0.0))
+        opts["learn_pass_tile_k"] = int(params.pop("learn_tile_k", 0))
+        opts["learn_pass_stages"] = int(params.pop("learn_stages", 0))
+        opts["learn_pass_blocks"] = int(params.pop("learn_blocks", 0))
+        side_blocks = int(params.pop("side_blocks", 0))  # 10*synapse + ltp blocks per SM of the graph path
+        opts["synapse_blocks_per_sm"], opts["ltp_blocks_per_sm"] = side_blocks // 10, side_blocks % 10
+        chain = params.pop("chain", None)  # "nthr,syn,ltp,ltp_thr,learn,learn_thr,stages" (sweeps)
+        if chain:
+            names = ("chain_neuron_threads", "chain_synapse_blocks", "chain_ltp_blocks", "chain_ltp_threads",
+                     "chain_learn_blocks", "chain_learn_threads", "chain_learn_stages")
+            for nme, v in zip(names, (chain.split(",") if isinstance(chain, str) else chain)):
+                opts[nme] = int(v)
         cfg = default_config(
             dtype=L.SNN_F64 if dtype == "f64" else L.SNN_F32,
             mode=L.SNN_MODE_EXACT if mode == "exact" else L.SNN_MODE_FAST,
@@ -74,23 +91,14 @@ class SparseNetwork:
             max_delay=max_delay,
             noise_mode={"none": L.SNN_NOISE_NONE, "replay": L.SNN_NOISE_REPLAY, "philox": L.SNN_NOISE_PHILOX}[noise],
             **params)
-        if not use_graph:
-            cfg.reserved[0] = 1  # plain stream-ordered launches instead of the captured window graph
-        cfg.reserved[1] = exp_flags
-        cfg.reserved[2] = learn_blocks   # asynchronous learn pass: blocks per SM (0 = default)
-        cfg.reserved[3] = learn_tile_k   # tile of the asynchronous pass in units of 1024 synapses (0 = 32)
-        cfg.reserved[6] = learn_stages   # TMA pipeline depth of the asynchronous pass (0 = 4, kPassStages)
-        cfg.reserved[7] = side_blocks    # 10*synapse + ltp blocks per SM (0 = default: occupancy limit / 4)
-        cfg.reserved[5] = learn_log_cap  # total entries of the sd-update log (0 = by size)
-        cfg.reserved[4] = learn_async    # 0 auto (large nets), 1 in-place pass only, 2 always asynchronous
-        if learn_lazy > 0:
-            cfg.reserved[4] = 16 + learn_lazy
-            cfg.reserved[5] = int(round(learn_lazy_da * 1000))
         self.cfg = cfg
         self.n_neurons = int(cfg.n_neurons)
         self.n_instances = int(n_instances)
         self._h = C.c_void_p()
         L.check(lib.snn_create(C.byref(cfg), C.byref(self._h)))
+        for name, v in opts.items():
+            if v or name in ("graph", "persistent"):   # the two switches are only in `opts` when they are turned OFF
+                self.set_param(name, v)
         rowptr = np.ascontiguousarray(rowptr, np.int64)
         post = np.ascontiguousarray(post, np.int32)
         w = np.ascontiguousarray(w, np.float64)
@@ -99,6 +107,27 @@ class SparseNetwork:
             raise ValueError("rowptr must have n_neurons+1 entries")
         L.check(lib.snn_set_synapses_csr(self._h, _ptr(rowptr), _ptr(post), _ptr(w), _ptr(delay)))
         self.n_synapses = int(lib.snn_n_synapses(self._h))
+
+    def set_param(self, name: str, value: float):
+        """snn_set_param: a model scalar by its snn_config field name, or a scheduling / diagnostic option."""
+        L.check(L.load().snn_set_param(self._h, name.encode(), float(value)))
+
+    def get_param(self, name: str) -> float:
+        v = C.c_double()
+        L.check(L.load().snn_get_param(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def checkpoint(self) -> bytes:
+        """Everything the next window depends on (delays in flight included), as one blob."""
+        lib = L.load()
+        n = C.c_int64()
+        L.check(lib.snn_checkpoint_bytes(self._h, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        L.check(lib.snn_checkpoint(self._h, buf, n.value))
+        return buf.raw
+
+    def restore(self, blob: bytes):
+        L.check(L.load().snn_restore(self._h, blob, len(blob)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:

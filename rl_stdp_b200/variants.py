@@ -4,6 +4,7 @@ Every variant is a configuration of libsnn_b200 (snn_config switches) plus a con
 the reference's dense matrices into CSR synapses; nothing here computes on the CPU.  Ids are
 0-based; every random quantity of the reference (connectivity, thalamic noise) is a recorded input.
 
+  NetworkCol     variant B  Julia/Izhikevic_dastdp/Old_net/new_net_col.jl:4-163 (transposed storage)
   NetworkColSep  variant C  Julia/Izhikevic_dastdp/Old_net/new_net_col_sep.jl:4-214
   NetworkRes     variant D  Julia/Modules/Networks/net_res.jl:6-251
   NetworkG       variant G  Julia/Izhikevic_dastdp/Old_net/DASTDP.jl:24-106 + Julia_DA_STDPv2.jl:71-96
@@ -31,6 +32,69 @@ class _DenseView:
         m = np.zeros((self.n_neurons, self.n_neurons))
         m[self._pre, self._post] = self._net.get(field)
         return m
+
+
+class NetworkCol:
+    """Variant B, `Network(n_neurons, connectivity, n_exc)` of new_net_col.jl:86-103: the network of variant A held
+    TRANSPOSED — `connection`, `s`, `sd` are [post, pre] ("read by columns", :13-15).  The caller hands the matrices
+    over exactly as that struct holds them (column-major [post, pre]) through snn_set_synapses_dense_col; `s[post, pre]`
+    / `sd[post, pre]` read them back in the same orientation.  `connection_pre_post` is what connect() draws (:28),
+    before the constructor transposes it (:94)."""
+
+    def __init__(self, n_neurons, n_exc, connection_pre_post, dtype="f64", mode="exact", device=0):
+        import ctypes as C
+        from .network import default_config
+        self.n_neurons, self.n_exc = int(n_neurons), int(n_exc)
+        N = self.n_neurons
+        conn_t = np.ascontiguousarray(np.asarray(connection_pre_post, np.int64).T)      # [post, pre], :94
+        s_t = np.zeros((N, N))
+        s_t[:, :n_exc] = 1.0                                                              # :97
+        s_t[:, n_exc:] = -1.0                                                             # :98
+        s_t *= conn_t                                                                     # :99
+        self.connection = conn_t
+        cfg = default_config(dtype=L.SNN_F64 if dtype == "f64" else L.SNN_F32,
+                             mode=L.SNN_MODE_EXACT if mode == "exact" else L.SNN_MODE_FAST, device=int(device),
+                             n_neurons=N, n_per_instance=N, n_exc=self.n_exc, max_delay=1, noise_mode=L.SNN_NOISE_REPLAY)
+        # SparseNetwork without its constructor: the handle is created here and fed the dense, transposed matrices
+        self._net = SparseNetwork.__new__(SparseNetwork)
+        self._net.cfg, self._net.n_neurons, self._net.n_instances = cfg, N, 1
+        self._net._h = C.c_void_p()
+        lib = L.load()
+        L.check(lib.snn_create(C.byref(cfg), C.byref(self._net._h)))
+        # column-major [post, pre] == the C-order bytes of the [pre, post] transpose
+        s_f = np.asfortranarray(s_t); c_f = np.asfortranarray(conn_t)
+        L.check(lib.snn_set_synapses_dense_col(self._net._h, s_f.ctypes.data_as(C.c_void_p), c_f.ctypes.data_as(C.c_void_p)))
+        self._net.n_synapses = int(lib.snn_n_synapses(self._net._h))
+        # the library's CSR order: ascending pre, then post
+        self._pre, self._post = np.nonzero(conn_t.T)
+
+    def step(self, noise, train=False, input_spikes=None):            # step! :148-163
+        force = None if input_spikes is None else [(0, int(j)) for j in input_spikes]
+        sp, _ = self._net.run(1, np.asarray(noise, np.float64).reshape(1, -1), [1 if train else 0], force=force)
+        return sp[0]
+
+    def run(self, noise, train, da_events=None, **kw):
+        return self._net.run(len(noise), noise, train, da_events=da_events, **kw)
+
+    def _dense_t(self, field):
+        m = np.zeros((self.n_neurons, self.n_neurons))
+        m[self._post, self._pre] = self._net.get(field)
+        return m
+
+    @property
+    def s(self): return self._dense_t(L.FIELD_W)       # [post, pre]
+    @property
+    def sd(self): return self._dense_t(L.FIELD_SD)     # [post, pre]; only plastic (exc pre) entries are maintained
+    @property
+    def v(self): return self._net.get(L.FIELD_V)
+    @property
+    def u(self): return self._net.get(L.FIELD_U)
+    @property
+    def STDP(self): return self._net.get(L.FIELD_TRACE)
+    @property
+    def da(self): return float(self._net.get(L.FIELD_DA)[0])
+    @da.setter
+    def da(self, x): self._net.set(L.FIELD_DA, [x])
 
 
 class NetworkColSep(_DenseView):

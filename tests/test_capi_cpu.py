@@ -25,7 +25,7 @@ def test_header_symbols_all_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/snn_b200.h but not exported"
     assert names == set(L.SYMBOLS), names ^ set(L.SYMBOLS)
-    assert lib.snn_abi_version() == 2
+    assert lib.snn_abi_version() == 3
 
 
 def test_config_struct_matches_header():

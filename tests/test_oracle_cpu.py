@@ -53,6 +53,39 @@ def test_dense_c_equals_numpy_equals_sparse():
     assert np.abs(A.sd).max() > 0 and np.abs(A.s - s0).max() > 0  # learning happened
 
 
+def test_variant_b_restatement_equals_variant_a_and_sparse_oracle():
+    """Variant B (new_net_col.jl:111-144) stores s / sd / connection transposed and walks the row of a spiker before
+    its column (:127-130).  Its literal restatement must give, bit for bit, the transpose of variant A's matrices and
+    the sparse oracle's values — the evidence (not just the argument) that the CSR engine covers B."""
+    N, Ne, T = 260, 200, 400
+    conn, noise = _drive_a(N, Ne, T, 5)
+    A = nr.NetA(N, Ne, conn)
+    B = nr.NetB(N, Ne, conn)
+    s0 = synth.variant_a_weights(N, Ne, conn)
+    rowptr, post, w = synth.dense_to_csr(s0, conn)
+    S = po.Sparse(N, Ne, rowptr, post, w)
+    assert np.array_equal(B.s, A.s.T) and np.array_equal(B.connection, A.connection.T)
+    total = 0
+    for t in range(T):
+        train = (t + 1) % 10 == 0
+        force = [3, 41] if t == 200 else None
+        a = A.step(noise[t], train, force)
+        b = B.step(noise[t], train, force)
+        c = S.step(noise[t], train, force)
+        assert np.array_equal(a, b) and np.array_equal(b, c), t
+        total += len(b)
+        if t in (90, 250):
+            A.da += 0.5; B.da += 0.5; S.add_da(0, 0.5)
+    assert total > 100
+    assert np.array_equal(B.s, A.s.T) and np.array_equal(B.sd, A.sd.T)
+    assert np.array_equal(B.v, A.v) and np.array_equal(B.u, A.u) and np.array_equal(B.STDP, A.STDP) and B.da == A.da
+    pre, pst = np.nonzero(conn)
+    exc = pre < Ne
+    assert np.array_equal(B.s[pst, pre], S.get(4))
+    assert np.array_equal(B.sd[pst, pre][exc], S.get(5)[exc])
+    assert np.abs(B.sd).max() > 0 and np.abs(B.s - s0.T).max() > 0  # learning happened
+
+
 def test_golden_variant_a():
     g = np.load(os.path.join(GOLD, "variant_a_n150_t300.npz"))
     N, Ne, T = int(g["N"]), int(g["Ne"]), int(g["T"])
