@@ -319,7 +319,7 @@ int32_t snn_set_profiling(snn_net* net, int32_t enable);
 /* Diagnostics (snn_config.reserved[1] & 2): %globaltimer stamps (ns) of the last window's kernels,
  * out[2][SNN_TL_CLASSES][SNN_TL_STEPS]: [0] = first block start, [1] = last block end; class
  * 0 neuron, 1 synapse, 2 ltp, 3 learn, 4 remote, 5 push-only synapse; index = window step + 1. */
-#define SNN_TL_CLASSES 6
+#define SNN_TL_CLASSES 16
 #define SNN_TL_STEPS 258
 int32_t snn_debug_timeline(snn_net* net, uint64_t* out, int64_t count);
 /* Use an externally owned CUDA stream (cudaStream_t) instead of the net's own. */

@@ -19,7 +19,7 @@ SNN_SD_DECAY_ON_LEARN, SNN_SD_DECAY_EVERY_STEP, SNN_SD_DECAY_NEVER = 0, 1, 2
 SNN_RATE_BASE_PLUS_DA, SNN_RATE_DA, SNN_RATE_ETA_DA = 0, 1, 2
 (FIELD_V, FIELD_U, FIELD_TRACE, FIELD_HO, FIELD_W, FIELD_SD, FIELD_DA, FIELD_I) = range(8)
 SNN_ERR_CAPACITY = -5
-SNN_TL_CLASSES, SNN_TL_STEPS = 6, 258
+SNN_TL_CLASSES, SNN_TL_STEPS = 16, 258
 SNN_PEER_BLOB_BYTES = 192
 
 

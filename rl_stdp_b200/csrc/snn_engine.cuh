@@ -149,6 +149,7 @@ struct DevNet {
   int32_t* spk_cnt;  // [R]
   T* da;             // [2][B]    da[t&1] = dopamine after the decay of step t-1
   // synapses (internal order: ascending pre, delay, caller position)
+  const uint2* seg01;    // [N] (first, end) of the delay-1 segment of every row: the 8 MB the neuron role needs of the 84 MB table
   const uint32_t* seg;   // [N][Dmax+1] delay-segment table
   const int32_t* post;   // [E]
   T2* wsd;               // = wsdX[0]; [E] (w, sd) interleaved: one 8-byte access serves propagate + LTD
@@ -210,8 +211,10 @@ struct DevNet {
   unsigned long long* tl;
 };
 
-// timeline classes: 0 neuron, 1 synapse, 2 ltp, 3 learn, 4 remote, 5 other
-constexpr int kTlSteps = 258, kTlClasses = 6;
+// timeline classes: 0 neuron, 1 synapse, 2 ltp, 3 learn, 4 remote, 5 push; phases of the persistent chain's roles:
+// 6 neuron wait, 7 currents (phase 1), 8 Euler + detect (phase 2), 9 spikers (phase 3), 10 noise of the next step,
+// 11 / 12 synapse wave stage A / B, 13 / 14 ltp wave stage A / B
+constexpr int kTlSteps = 258, kTlClasses = 16;
 __device__ __forceinline__ unsigned long long gtime_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -620,7 +623,7 @@ __device__ __forceinline__ uint32_t ll_word(const DevNet<T>& p, int slot, uint32
   for (;;) {
     asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(w), "=r"(g) : "l"(q) : "memory");
     if (g == tag) return w;
-    if (gtime_ns() - t_start > 4000000000ull) { p.xdone[1] = 1u; return 0u; }
+    if (gtime_ns() - t_start > 10000000000ull) { p.xdone[1] = 1u; return 0u; }
     __nanosleep(64);
   }
 }
@@ -647,7 +650,7 @@ __device__ __forceinline__ void remote_body(const DevNet<T>& p, const WindowCtx<
   const int64_t rec_cap = cx->rec_cap;
   int32_t rec_base = 0;
   if (rec_ids && k > 0) {
-    int64_t nxt = (int64_t)cx->rec_off[k - 1] + p.spk_cnt[prev];
+    int64_t nxt = (int64_t)__ldcg(cx->rec_off + (k - 1)) + __ldcg(p.spk_cnt + prev);
     rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
   }
   T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;
@@ -665,7 +668,7 @@ __device__ __forceinline__ void remote_body(const DevNet<T>& p, const WindowCtx<
         word = ll_word<T>(p, slot, wi, tag);
         bits[wi] = word;
       } else {
-        word = bits[wi];
+        word = __ldcg(bits + wi);
       }
     }
     const unsigned busy = __ballot_sync(0xffffffffu, word != 0u);
@@ -1588,15 +1591,15 @@ __global__ void learn_spill_reset_kernel(DevNet<T> p) { p.lc->spilled = 0u; }
 //   synapse(k) : neuron(k); on a learn step the pushes for k+1 wait for learn(k) begun
 //   ltp(k)     : neuron(k)
 //   learn(k)   : LTD(k) and ltp(k) on every block; the previous pass complete and replayed
-// Every wait gives up after 2 s and raises ChainCtl::abort (the host then reports SNN_ERR_STATE):
+// Every wait gives up after 10 s and raises ChainCtl::abort (the host then reports SNN_ERR_STATE):
 // a scheduling accident can cost a window, never hang the device.
 // Mutable data is read through L2 (ld.cg / volatile / acquire): nothing invalidates L1 inside a kernel.
 // =============================================================================================
 enum { kcNeuron = 0, kcPush = 1, kcLtd = 2, kcLtp = 3, kcBegun = 4, kcLearnBar = 5, kcAbort = 6, kcPassNs = 7, kcPassCnt = 8,
-       kcCounters = 9 };
+       kcRemote = 9, kcCounters = 10 };
 struct ChainCtl { uint32_t w[kcCounters * 32]; };  // counter c at w[c * 32]: one 128-byte line each
 struct ChainDims {
-  uint32_t NB, SB, PB, LB;   // blocks of the neuron / synapse / ltp / learn role
+  uint32_t NB, SB, PB, LB, RB;   // blocks of the neuron / synapse / ltp / learn / remote (partitioned runs) role
   uint32_t qpb;              // quads (4 neurons) per neuron block, multiple of 32
   int32_t n_learn;           // learn steps in this window
   int32_t do_decay;          // sd *= sd_decay inside learn! (SNN_SD_DECAY_ON_LEARN)
@@ -1617,7 +1620,7 @@ static __device__ __noinline__ bool chain_wait_slow(ChainCtl* c, int which, uint
   for (;;) {
     if (ld_acquire_u32(&c->w[which * 32]) >= target) return true;
     if (*reinterpret_cast<volatile uint32_t*>(&c->w[kcAbort * 32]) != 0u) return false;
-    if (gtime_ns() - t0 > 2000000000ull) { atomicExch(&c->w[kcAbort * 32], 1u + (uint32_t)which); return false; }
+    if (gtime_ns() - t0 > 10000000000ull) { atomicExch(&c->w[kcAbort * 32], 1u + (uint32_t)which); return false; }
     if (sleep_ns) __nanosleep(sleep_ns);
   }
 }
@@ -1640,7 +1643,7 @@ __device__ __forceinline__ Vec4<double> ld4cg(const double* p) {
   Vec4<double> o; o.x[0] = a.x; o.x[1] = a.y; o.x[2] = b.x; o.x[3] = b.y; return o;
 }
 
-constexpr int kChainNeuronThreads = 512, kChainLearnThreads = 128;
+constexpr int kChainNeuronThreads = 512, kChainLearnThreads = 128, kSpkWave = 256;
 
 // Delay-1 synapses of spiker i pushed warp-cooperatively into Iacc[t&1] — they feed the Euler update of this very
 // step (new_net.jl:116-121).  Weights of synapses the learn pass in flight has not reached are formed on the fly.
@@ -1671,14 +1674,17 @@ __device__ __forceinline__ void chain_push_delay1(const DevNet<T>& p, const WVie
 // chain_neuron_kernel: Euler(k-1) + detect(k) for k = 0..n over a block's own neurons (new_net.jl:111-114,
 // 120-123,130-131), state resident in shared memory: sv / su [4*qpb], sn [4*qpb] the noise of the next Euler.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kChainNeuronThreads, 2)
+// MINB: resident blocks per SM the register allocation is capped for (2: 64 registers, for blocks of <= 256
+// threads; 3: 40 registers with some spills, for 384-512 threads) — the role shares the SM with three others
+template <typename T, int MINB>
+__global__ void __launch_bounds__(kChainNeuronThreads, MINB)
 chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl,
                     const int32_t* __restrict__ sched, const ChainDims d) {
   typedef Ops<T> O;
   extern __shared__ __align__(16) unsigned char nsm_raw[];
   __shared__ int s_ok;
-  __shared__ int s_nspk[2], s_base;  // spikers of this block in step k: s_nspk[k & 1] (the other one is being cleared)
+  __shared__ int s_nspk[2], s_base;
+  __shared__ uint32_t s_ps0[kSpkWave], s_poff[kSpkWave + 1];  // spikers of this block in step k: s_nspk[k & 1] (the other one is being cleared)
   T* const sv = reinterpret_cast<T*>(nsm_raw);
   T* const su = sv + (size_t)4 * d.qpb;
   T* const sn = su + (size_t)4 * d.qpb;
@@ -1704,17 +1710,21 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
 
   for (int k = 0; k <= n; ++k) {
     const bool euler = k > 0, detect = k < n;
+    tl_begin(p.tl, 6, k);
     if (tid == 0) {
       bool ok = chain_wait(ctl, kcNeuron, d.NB * (uint32_t)k, 0);
       if (ok && k >= 1) ok = chain_wait(ctl, kcPush, d.SB * (uint32_t)k, 0);
       if (ok && k >= 1 && sched_learn(sched, k - 1)) ok = chain_wait(ctl, kcBegun, (uint32_t)sched_before(sched, k), 0);
       if (ok && k > kLag) ok = chain_wait(ctl, kcLtp, d.PB * (uint32_t)(k - kLag), 0);
+      if (ok && k >= 1 && d.RB) ok = chain_wait(ctl, kcRemote, d.RB * (uint32_t)k, 0);  // the peers' spikes of step k-1 pushed / listed
       s_ok = ok ? 1 : 0;
       s_nspk[(k + 1) & 1] = 0;  // last read in phase 3 of step k-1, which every thread has left
     }
     __syncthreads();
     if (!s_ok) break;
+    tl_end(p.tl, 6, k);
     tl_begin(p.tl, 0, k);
+    tl_begin(p.tl, 7, k);
     const int64_t t = t0 + k;
     const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
     uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
@@ -1784,6 +1794,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         }
       }
     }
+    if (p.tl) { __syncthreads(); tl_end(p.tl, 7, k); tl_begin(p.tl, 8, k); }
     // ---- phase 2: Euler(t-1) and detect(t) out of shared memory
     for (uint32_t ql = tid; ql < nq; ql += TN) {  // warp-uniform trip count (nq and TN are multiples of 32)
       const uint32_t q = qb0 + ql, j0 = q << 2;
@@ -1847,6 +1858,18 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         word |= __shfl_xor_sync(0xffffffffu, word, 2);
         word |= __shfl_xor_sync(0xffffffffu, word, 4);
         if ((lane & 7) == 0) bits[j0 >> 5] = word;
+        if (p.n_ranks > 1) {
+          // fused exchange (neuron-partitioned runs): a warp row owns 4 consecutive bitmap words = two 16-byte stores
+          // of (word, step tag) pairs into every peer's ring over NVLink
+          const unsigned w1 = __shfl_sync(0xffffffffu, word, 8), w2 = __shfl_sync(0xffffffffu, word, 16),
+                         w3 = __shfl_sync(0xffffffffu, word, 24);
+          if (lane < (uint32_t)p.n_ranks && lane != (uint32_t)p.rank) {
+            const uint32_t tag = (uint32_t)(t + 1);
+            uint4* dst = reinterpret_cast<uint4*>(p.peer_ll[lane] + (size_t)slot * p.W + (j0 >> 5));
+            dst[0] = make_uint4(word, tag, w1, tag);
+            dst[1] = make_uint4(w2, tag, w3, tag);
+          }
+        }
         // spikers (rare) only go on the block's list here: their global bookkeeping and delay-1 pushes are a chain
         // of dependent memory round trips, done for all of them at once in phase 3
         for (unsigned nb = nib; nb; nb &= nb - 1u) s_spk[atomicAdd(&s_nspk[k & 1], 1)] = (uint16_t)(4 * ql + (__ffs(nb) - 1));
@@ -1856,15 +1879,67 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
       }
     }
     __syncthreads();
-    // ---- phase 3: this block's spikers, all in flight together.  Thread 0 reserves the block's stretch of the global
-    // spike list while the warps push the spikers' delay-1 synapses; then list / record / spike history are written.
+    tl_end(p.tl, 8, k); tl_begin(p.tl, 9, k);
+    // ---- phase 3: this block's spikers, all in flight together (a chain of dependent memory round trips per
+    // spiker: done as a small wave — one thread per spiker fetches the bounds of its delay-1 segment, then one thread
+    // per SYNAPSE pushes it into Iacc[t&1]: it feeds the Euler update of this very step, new_net.jl:116-121).
+    // Thread 0 reserves the block's stretch of the global spike list meanwhile.
     if (detect) {
       const int nspk = s_nspk[k & 1];
       if (nspk > 0) {
         if (tid == 0) s_base = atomicAdd(&p.spk_cnt[slot], nspk);
-        for (int w = (int)(tid >> 5); w < nspk; w += (int)(TN >> 5))
-          chain_push_delay1<T>(p, vw, (qb0 << 2) + s_spk[w], lane, I_now);
-        __syncthreads();
+        for (int r0 = 0; r0 < nspk; r0 += kSpkWave) {
+          const int nr = min(kSpkWave, nspk - r0);
+          for (int x = (int)tid; x < nr; x += (int)TN) {
+            const uint2 sg = p.seg01[(qb0 << 2) + s_spk[r0 + x]];
+            s_ps0[x] = sg.x; s_poff[x + 1] = sg.y - sg.x;
+          }
+          __syncthreads();
+          if (tid < 32) {
+            constexpr int PER = kSpkWave / 32;
+            const int b0 = (int)lane * PER;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) if (b0 + q < nr) acc += s_poff[b0 + q + 1];
+            uint32_t inc = acc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+              if (lane >= (uint32_t)o) inc += up;
+            }
+            uint32_t run = inc - acc;
+            if (lane == 0) s_poff[0] = 0u;
+#pragma unroll
+            for (int q = 0; q < PER; ++q)
+              if (b0 + q < nr) { run += s_poff[b0 + q + 1]; s_poff[b0 + q + 1] = run; }
+          }
+          __syncthreads();
+          const uint32_t V = s_poff[nr];
+          for (uint32_t v0 = tid; v0 < V; v0 += 4 * TN) {
+            int32_t pj[4]; typename DevNet<T>::T2 pw[4]; bool fly[4]; uint32_t pi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t v = v0 + u * TN;
+              pj[u] = -1; fly[u] = false; pi[u] = 0;
+              if (v >= V) continue;
+              uint32_t a = 0, b = (uint32_t)nr;
+              while (b - a > 1) { const uint32_t m = (a + b) >> 1; if (s_poff[m] <= v) a = m; else b = m; }
+              const uint32_t e = s_ps0[a] + (v - s_poff[a]);
+              pi[u] = (qb0 << 2) + s_spk[r0 + a];
+              const uint32_t ib = p.B == 1 ? 0u : (pi[u] / Nper) * Nper;
+              pj[u] = p.post[e];
+              pw[u] = w_fetch<T>(vw, e, (pi[u] - ib) < Ne, fly[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (pj[u] < 0) continue;
+              const uint32_t inst = p.B == 1 ? 0u : pi[u] / Nper;
+              atomicAdd(&I_now[pj[u]],
+                        w_resolve<T>(p, pw[u], fly[u], p.plastic_ei || ((uint32_t)pj[u] - inst * Nper) < Ne, inst, (T)0));
+            }
+          }
+          __syncthreads();
+        }
         const int base = s_base;
         for (int w = (int)tid; w < nspk; w += (int)TN) {
           const uint32_t j = (qb0 << 2) + s_spk[w];
@@ -1875,8 +1950,10 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         __syncthreads();
       }
     }
+    tl_end(p.tl, 9, k);
     if (tid == 0) chain_arrive(ctl, kcNeuron);
     tl_end(p.tl, 0, k);
+    tl_begin(p.tl, 10, k);
     // ---- off the critical path: the noise Euler(k) will add, 13*(U-0.5) (new_net.jl:111)
     if (detect && philox) {
       for (uint32_t ql = tid; ql < nq; ql += TN) {
@@ -1889,6 +1966,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         st4(sn + 4 * ql, nz);
       }
     }
+    if (p.tl) { __syncthreads(); tl_end(p.tl, 10, k); }
   }
   __syncthreads();
   if (bid == 0 && tid == 0) p.counters[0] += spikes_acc;
@@ -1952,6 +2030,7 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
   unsigned long long n_ev = 0;
   for (uint32_t r0 = lo; r0 < hi; r0 += kWaveItems) {
     const uint32_t nitem = min((uint32_t)kWaveItems, hi - r0);
+    if (LTD) tl_begin(p.tl, 11, k);
     // ---- stage A: item -> (first synapse, LTD length, total length, spiker)
     for (uint32_t x = tid; x < nitem; x += TB) {
       const uint32_t item = r0 + x;
@@ -1989,6 +2068,7 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
     }
     __syncthreads();
     const uint32_t V = sm.off[nitem];
+    if (LTD) { tl_end(p.tl, 11, k); tl_begin(p.tl, 12, k); }
     // ---- stage B: one thread per synapse visit, two in flight
     for (uint32_t v0 = tid; v0 < V; v0 += 2 * TB) {
       uint32_t e[2], j[2], inst[2], ibs[2]; bool ok[2], isl[2], pl[2], fly[2]; typename DevNet<T>::T2 ws[2]; int2 hq[2];
@@ -2022,6 +2102,7 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
       }
     }
     __syncthreads();
+    if (LTD) tl_end(p.tl, 12, k);
   }
   if (LTD) {
     for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
@@ -2059,6 +2140,7 @@ chain_synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl*
   arrive(kcPush);
   for (int k = 0; k < n; ++k) {
     if (!wait1(kcNeuron, d.NB * (uint32_t)(k + 1))) return;
+    if (d.RB && !wait1(kcRemote, d.RB * (uint32_t)(k + 1))) return;  // partitioned: the step's spike list is complete
     const bool learn = sched_learn(sched, k), push_next = k + 1 < n;
     if (push_next && !learn) {
       synapse_wave<T, true, true>(p, cx, k, bid, d.SB, wsm);
@@ -2076,18 +2158,119 @@ chain_synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl*
   }
 }
 
+// ltp_wave (persistent chain): the work of ltp_body — for every neuron j that spiked at t, sd += apost * pre trace
+// as seen at the synapse over the plastic prefix of j's incoming list (new_net.jl:126, DASTDP.jl:62-68) — as a wave:
+// one thread per spiker fetches the bounds of its list, then one thread per INCOMING SYNAPSE, three in flight.
+template <typename T>
+__device__ __forceinline__ void ltp_wave(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k,
+                                         const uint32_t bid, const uint32_t nblk, WaveSmem& sm) {
+  typedef Ops<T> O;
+  tl_begin(p.tl, 2, k);
+  const uint32_t tid = threadIdx.x, TB = blockDim.x, lane = tid & 31u;
+  const int slot = (cx->slot0 + k) % p.R;
+  const int32_t t32 = (int32_t)(cx->t0 + k);
+  const uint32_t total = (uint32_t)__ldcg(p.spk_cnt + slot);
+  const uint32_t per = (total + nblk - 1) / nblk;
+  const uint32_t lo = min(total, bid * per), hi = min(total, lo + per);
+  const int32_t* __restrict__ list = p.spk_list + (size_t)slot * (size_t)p.Nld;
+  const WView<T> vw = wview(p);
+  unsigned long long n_ltp = 0;
+  if (tid == 0) sm.blk_ev = 0ull;
+  for (uint32_t r0 = lo; r0 < hi; r0 += kWaveItems) {
+    const uint32_t nitem = min((uint32_t)kWaveItems, hi - r0);
+    for (uint32_t x = tid; x < nitem; x += TB) {
+      const uint32_t j = (uint32_t)__ldcg(list + r0 + x);
+      const uint32_t c0 = p.colptr[j], npl = p.col_npl[j];
+      sm.s0[x] = c0; sm.src[x] = j; sm.off[x + 1] = npl;
+      n_ltp += npl;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      constexpr int PER = kWaveItems / 32;
+      const uint32_t b = lane * PER;
+      uint32_t acc = 0;
+#pragma unroll
+      for (int q = 0; q < PER; ++q) if (b + q < nitem) acc += sm.off[b + q + 1];
+      uint32_t inc = acc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += up;
+      }
+      uint32_t run = inc - acc;
+      if (lane == 0) sm.off[0] = 0u;
+#pragma unroll
+      for (int q = 0; q < PER; ++q)
+        if (b + q < nitem) { run += sm.off[b + q + 1]; sm.off[b + q + 1] = run; }
+    }
+    __syncthreads();
+    const uint32_t V = sm.off[nitem];
+    for (uint32_t v0 = tid; v0 < V; v0 += 3 * TB) {
+      uint32_t pk[3], e[3], inst[3]; bool ok[3]; int2 hq[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const uint32_t v = v0 + u * TB;
+        ok[u] = v < V; pk[u] = 0; e[u] = 0; inst[u] = 0;
+        if (!ok[u]) continue;
+        uint32_t a = 0, b = nitem;
+        while (b - a > 1) { const uint32_t m = (a + b) >> 1; if (sm.off[m] <= v) a = m; else b = m; }
+        const uint32_t kk = sm.s0[a] + (v - sm.off[a]);
+        inst[u] = p.B == 1 ? 0u : sm.src[a] / (uint32_t)p.Nper;
+        pk[u] = p.in_pre[kk];
+        e[u] = p.in_syn[kk];
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) if (ok[u]) hq[u] = hist_fetch(p.hist, pk[u] & kPreMask);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        if (!ok[u]) continue;
+        // pre trace as seen at the synapse: of step t-(d-1) (variant_g: one step earlier)
+        const T tr = trace_resolve<T>(p, hq[u], pk[u] & kPreMask, t32 - (int32_t)(pk[u] >> kPreBits) - (p.variant_g ? 1 : 0), t32);
+        sd_add<T>(p, vw, e[u], O::mul(p.apost, tr), p.log_ltp_base + bid, inst[u]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int o = 16; o > 0; o >>= 1) n_ltp += __shfl_down_sync(0xffffffffu, n_ltp, o);
+  if (lane == 0 && n_ltp) atomicAdd(&sm.blk_ev, n_ltp);
+  __syncthreads();
+  if (tid == 0 && sm.blk_ev) p.blk_ltp[bid] += sm.blk_ev;
+  tl_end(p.tl, 2, k);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256, 6)
 chain_ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl, const ChainDims d) {
   __shared__ int s_ok;
+  __shared__ WaveSmem wsm;
   const int n = cx->n_steps;
   for (int k = 0; k < n; ++k) {
-    if (threadIdx.x == 0) s_ok = chain_wait(ctl, kcNeuron, d.NB * (uint32_t)(k + 1), 40) ? 1 : 0;
+    if (threadIdx.x == 0)
+      s_ok = (chain_wait(ctl, kcNeuron, d.NB * (uint32_t)(k + 1), 40) &&
+              (!d.RB || chain_wait(ctl, kcRemote, d.RB * (uint32_t)(k + 1), 40))) ? 1 : 0;
     __syncthreads();
     if (!s_ok) return;
-    ltp_body<T, true>(p, cx, k, d.g_ltp_log2, blockIdx.x, d.PB);
+    ltp_wave<T>(p, cx, k, blockIdx.x, d.PB, wsm);
     __syncthreads();
     if (threadIdx.x == 0) chain_arrive(ctl, kcLtp);
+  }
+}
+
+// chain_remote_kernel (neuron-partitioned runs): replay of the peers' detection, step by step.  remote(k) may start
+// as soon as the local neuron role has finished step k-1 (Iacc[t&1] cleared, the step's list slot reset); it then
+// waits for the peers' (word, step) pairs themselves.
+template <typename T>
+__global__ void __launch_bounds__(256)
+chain_remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl, const ChainDims d) {
+  __shared__ int s_ok;
+  const int n = cx->n_steps;
+  for (int k = 0; k < n; ++k) {
+    if (threadIdx.x == 0) s_ok = chain_wait(ctl, kcNeuron, d.NB * (uint32_t)k, 0) ? 1 : 0;
+    __syncthreads();
+    if (!s_ok) return;
+    remote_body<T>(p, cx, k, 1, blockIdx.x, d.RB);
+    __syncthreads();
+    if (threadIdx.x == 0) chain_arrive(ctl, kcRemote);
   }
 }
 
@@ -2239,6 +2422,10 @@ __global__ void to_double_kernel(const T* __restrict__ in, double* __restrict__ 
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
     out[j] = scale == 1.0 ? (double)in[j] : (double)(Ops<T>::mul(in[j], (T)scale));
 }
+static __global__ void seg01_kernel(const uint32_t* __restrict__ seg, int64_t N, int stride, uint2* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = make_uint2(seg[i * stride], seg[i * stride + 1]);
+}
 // caller order <-> internal order through perm; comp 0 = w, 1 = sd
 template <typename T>
 __global__ void wsd_from_caller(const double* __restrict__ in, const uint32_t* __restrict__ perm,
@@ -2325,6 +2512,7 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaEventCreate(&ev_end_));
     for (auto& e : dep_ev_) SNN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     SNN_CUDA_OK(cudaStreamCreateWithPriority(&side2_stream_, cudaStreamNonBlocking, prio_mid));
+    SNN_CUDA_OK(cudaStreamCreateWithPriority(&remote_stream_, cudaStreamNonBlocking, prio_hi));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device);
     n_sm_ = sms;
@@ -2514,6 +2702,12 @@ class Engine : public IEngine {
     p.seg = topo_.seg; p.post = topo_.post; p.colptr = topo_.colptr; p.col_npl = topo_.col_npl;
     p.in_syn = topo_.in_syn; p.in_pre = topo_.in_pre;
     free_synapse_state();
+    {
+      uint2* s01 = nullptr;
+      SNN_CUDA_OK(cudaMalloc(&s01, (size_t)std::max<int64_t>(1, p.N) * sizeof(uint2)));
+      seg01_kernel<<<grid_for(p.N), 256, 0, stream_>>>(p.seg, p.N, p.Dmax + 1, s01);
+      p.seg01 = s01;
+    }
     const int64_t Ea = p.E > 0 ? p.E : 1;
     typedef typename DevNet<T>::T2 T2;
     SNN_CUDA_OK(cudaMalloc(&p.wsdX[0], Ea * sizeof(T2)));
@@ -2933,7 +3127,7 @@ class Engine : public IEngine {
     DevNet<T>& p = p_;
     if (p.wsdX[1] != p.wsdX[0]) cudaFree(p.wsdX[1]);
     cudaFree(p.wsdX[0]); cudaFree(p.dlog); cudaFree(p.dsd); cudaFree(p.log_cnt); cudaFree(p.tile_done);
-    cudaFree(p.cacc); cudaFree(p.lzH); cudaFree(p.lzK);
+    cudaFree(p.cacc); cudaFree(p.lzH); cudaFree(p.lzK); cudaFree(const_cast<uint2*>(p.seg01)); p.seg01 = nullptr;
     cudaFree(const_cast<uint32_t*>(p.inst_lo));
     p.wsd = p.wsdX[0] = p.wsdX[1] = nullptr; p.dlog = nullptr; p.dsd = nullptr; p.log_cnt = nullptr;
     p.cacc = nullptr; p.lzH = p.lzR = p.lzInv = nullptr; p.lzK = nullptr; p.lazy = 0;
@@ -2969,6 +3163,8 @@ class Engine : public IEngine {
     if (side2_stream_) cudaStreamDestroy(side2_stream_);
     if (chain_stream_) cudaStreamDestroy(chain_stream_);
     if (learn_stream_) cudaStreamDestroy(learn_stream_);
+    if (remote_stream_) cudaStreamDestroy(remote_stream_);
+    remote_stream_ = nullptr;
     side2_stream_ = chain_stream_ = learn_stream_ = nullptr;
     memset(&p, 0, sizeof(p));
     own_stream_ = side_stream_ = nullptr; ev_begin_ = ev_end_ = nullptr; d_ctx_ = nullptr; h_ctx_ = nullptr; h_blk_ = nullptr;
@@ -2999,6 +3195,7 @@ class Engine : public IEngine {
   struct Launch {
     int gN, gA, gP, gR; dim3 gL;
   };
+  cudaStream_t own_side_stream() { return remote_stream_; }
   int gA_cap() { return grids().gA; }
   int gP_cap() { return grids().gP; }
   Launch grids() {
@@ -3075,7 +3272,7 @@ class Engine : public IEngine {
   cudaStream_t own_stream_ = nullptr, side_stream_ = nullptr, stream_ = nullptr;
   cudaEvent_t ev_begin_ = nullptr, ev_end_ = nullptr;
   cudaEvent_t dep_ev_[16] = {};
-  cudaStream_t side2_stream_ = nullptr, chain_stream_ = nullptr, learn_stream_ = nullptr;
+  cudaStream_t side2_stream_ = nullptr, chain_stream_ = nullptr, learn_stream_ = nullptr, remote_stream_ = nullptr;
   // asynchronous learn pass
   bool have_async_ = false, pass_attr_set_ = false;
   int cur_ = 0;                  // host mirror of LearnCtl.state >> 31 (read back after every window)
@@ -3412,7 +3609,8 @@ bool Engine<T>::chain_plan(std::string* why) {
   auto fail = [&](const char* m) { if (why) *why = m; return false; };
   if (p.exact || !use_graph_ || !opt_.persistent || p.lazy) return fail("mode");
   if (cfg_.sd_decay_mode == SNN_SD_DECAY_EVERY_STEP) return fail("sd decays every step");
-  if (p.n_ranks > 1 || exchange_ || !(p.part_lo == 0 && p.part_hi == p.N)) return fail("partitioned");
+  const bool parted = !(p.part_lo == 0 && p.part_hi == p.N);
+  if (exchange_ || (parted && p.n_ranks < 2)) return fail("partitioned with a host-side exchange");
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg_.device) != cudaSuccess) return fail("device properties");
   const int64_t local_quads = ((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 2) - (p.part_lo >> 2);
@@ -3431,8 +3629,11 @@ bool Engine<T>::chain_plan(std::string* why) {
   const int thrP = std::min(256, std::max(32, tune[3] / 32 * 32)), thrL = kChainLearnThreads;  // (tune[5] is not used any more)
   int S = std::min(kPassMaxStages, std::max(2, tune[6]));
   size_t smem_l = (size_t)S * kPassChunkBytes;
-  cudaFuncAttributes fa[4];
-  if (cudaFuncGetAttributes(&fa[0], chain_neuron_kernel<T>) != cudaSuccess ||      // (also loads the functions now: a
+  cudaFuncAttributes fa[5];
+  memset(fa, 0, sizeof(fa));
+  if (parted && cudaFuncGetAttributes(&fa[4], chain_remote_kernel<T>) != cudaSuccess) { cudaGetLastError(); return fail("kernel attributes"); }
+  const bool lean = thrN > 256;  // the 40-register build of the neuron role
+  if (cudaFuncGetAttributes(&fa[0], lean ? chain_neuron_kernel<T, 3> : chain_neuron_kernel<T, 2>) != cudaSuccess ||  // (also loads the functions now: a
       cudaFuncGetAttributes(&fa[1], chain_synapse_kernel<T>) != cudaSuccess ||     // lazy module load in the middle of a
       cudaFuncGetAttributes(&fa[2], chain_ltp_kernel<T>) != cudaSuccess ||         // window would wait for the spinning
       cudaFuncGetAttributes(&fa[3], chain_learn_kernel<T>) != cudaSuccess) {       // kernels that wait for it)
@@ -3441,11 +3642,11 @@ bool Engine<T>::chain_plan(std::string* why) {
   }
   if (smem_n + fa[0].sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) return fail("neuron state does not fit in shared memory");
   auto fits = [&](int sp, int lp, int le) {
-    const int thr[4] = {thrN, 256, thrP, thrL};
-    const int cnt[4] = {1, sp, lp, n_plastic_ > 0 && have_async_ ? le : 0};
-    const size_t dyn[4] = {smem_n, 0, 0, smem_l};
+    const int thr[5] = {thrN, 256, thrP, thrL, 256};
+    const int cnt[5] = {1, sp, lp, n_plastic_ > 0 && have_async_ ? le : 0, parted ? 1 : 0};
+    const size_t dyn[5] = {smem_n, 0, 0, smem_l, 0};
     size_t regs = 0, smem = 0; int threads = 0, blocks = 0;
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 5; ++r) {
       regs += (size_t)cnt[r] * (size_t)((fa[r].numRegs + 7) / 8 * 8) * thr[r];
       smem += (size_t)cnt[r] * ((dyn[r] + fa[r].sharedSizeBytes + 1024 + 127) / 128 * 128);
       threads += cnt[r] * thr[r]; blocks += cnt[r];
@@ -3463,10 +3664,16 @@ bool Engine<T>::chain_plan(std::string* why) {
   d.PB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm_ * ltp_per_sm, (ev_guess + 255) / 256));
   d.LB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm_ * learn_per_sm, std::max<uint32_t>(1, p.n_tiles)));
   if (d.SB > (uint32_t)gA_cap() || d.PB > (uint32_t)gP_cap()) return fail("log regions");
+  d.RB = 0;
+  if (parted) {
+    const int64_t remote_words = p.W - local_quads / 8;
+    d.RB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(n_sm_, (remote_words + 255) / 256));
+    cudaFuncSetAttribute(chain_remote_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   d.g_arr_log2 = g_arr_log2_; d.g_ltp_log2 = g_ltp_log2_; d.pass_stages = S;
   d.thrN = thrN; d.thrP = thrP; d.thrL = thrL;
   d.do_decay = cfg_.sd_decay_mode == SNN_SD_DECAY_ON_LEARN ? 1 : 0;
-  if (cudaFuncSetAttribute(chain_neuron_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n) != cudaSuccess ||
+  if (cudaFuncSetAttribute(lean ? chain_neuron_kernel<T, 3> : chain_neuron_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n) != cudaSuccess ||
       cudaFuncSetAttribute(chain_learn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess) {
     cudaGetLastError();
     return fail("shared-memory attribute");
@@ -3474,7 +3681,7 @@ bool Engine<T>::chain_plan(std::string* why) {
   // An SM's L1 / shared-memory split cannot change while a block is resident on it: if the first role to arrive
   // configured it for its own (smaller) need, the blocks of a role that needs more would wait for the SM to
   // drain — forever, since the resident role waits for them.  Every role asks for the maximum split up front.
-  cudaFuncSetAttribute(chain_neuron_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(lean ? chain_neuron_kernel<T, 3> : chain_neuron_kernel<T, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(chain_synapse_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(chain_ltp_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(chain_learn_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -3525,9 +3732,16 @@ int Engine<T>::launch_chain(const StepArgs& a, std::string& err) {
   SNN_CUDA_OK(cudaStreamWaitEvent(s2, evFork, 0));
   SNN_CUDA_OK(cudaStreamWaitEvent(s3, evFork, 0));
   // the neuron role first: its blocks (one per SM) hand a step over among themselves and must all be resident
-  chain_neuron_kernel<T><<<d.NB, d.thrN, chain_smem_neuron_, sN>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
+  if (d.thrN > 256) chain_neuron_kernel<T, 3><<<d.NB, d.thrN, chain_smem_neuron_, sN>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
+  else chain_neuron_kernel<T, 2><<<d.NB, d.thrN, chain_smem_neuron_, sN>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
   chain_synapse_kernel<T><<<d.SB, 256, 0, s2>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
   chain_ltp_kernel<T><<<d.PB, d.thrP, 0, s3>>>(p, d_ctx_, d_chain_, d);
+  if (d.RB) {  // neuron-partitioned: the replay of the peers' detection (own stream: it spins on NVLink traffic)
+    SNN_CUDA_OK(cudaStreamWaitEvent(own_side_stream(), evFork, 0));
+    chain_remote_kernel<T><<<d.RB, 256, 0, own_side_stream()>>>(p, d_ctx_, d_chain_, d);
+    SNN_CUDA_OK(cudaEventRecord(dep_ev_[0], own_side_stream()));
+    SNN_CUDA_OK(cudaStreamWaitEvent(s0, dep_ev_[0], 0));
+  }
   if (d.n_learn > 0) {
     SNN_CUDA_OK(cudaStreamWaitEvent(s4, evFork, 0));
     chain_learn_kernel<T><<<d.LB, d.thrL, chain_smem_learn_, s4>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);

@@ -12,7 +12,7 @@ import bench
 from rl_stdp_b200 import _lib as L, synth
 from rl_stdp_b200.network import SparseNetwork
 
-CLS = ["neuron", "synapse", "ltp", "learn", "remote", "push"]
+CLS = ["neuron", "synapse", "ltp", "learn", "remote", "push", "n.wait", "n.cur", "n.euler", "n.spk", "n.noise", "s.A", "s.B", "l.A", "l.B", "-"]
 
 
 def main():
@@ -92,7 +92,7 @@ def main():
                   f"{ch[0]['start_us']:.0f}->{ch[-1]['end_us']:.0f} ({ch[-1]['end_us'] - ch[0]['start_us']:.0f} us, "
                   f"{len(ch)} steps, mean kernel {np.mean([c['end_us'] - c['start_us'] for c in ch]):.1f} us)")
     print("first 40 rows:")
-    for r in rows[:60]:
+    for r in [r for r in rows if 20 <= r["k"] <= 23 or 30 <= r["k"] <= 31]:
         print(f"  {r['cls']:8s} k={r['k']:3d}  {r['start_us']:9.2f} -> {r['end_us']:9.2f}  ({r['end_us'] - r['start_us']:7.2f})")
 
 
