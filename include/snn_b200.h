@@ -369,6 +369,9 @@ int32_t snn_actor_set_array(snn_actor* a, int32_t field, int32_t layer, const do
  * be NULL.  spike_masks [n_agents][n_steps]: bit j = neuron j spiked at that step, may be NULL. */
 int32_t snn_actor_window(snn_actor* a, int32_t n_steps, const double* intensity, int32_t train, int32_t critic,
                          int32_t reset_v, int32_t* counts, int32_t* spike_masks, double* device_ms);
+/* learn!(net) (critic = 0, net_arch.jl:213-220) or learn_critic!(net) (critic != 0, :222-235) on its own, for
+ * every agent: the scripts that call it outside step_LIF! (critic_sim.jl:107, Latencysim_rewardv0.jl:131). */
+int32_t snn_actor_learn(snn_actor* a, int32_t critic);
 /* play_episode (cartpole_fitness.jl:51-114) for every agent, environment on the device.
  * matalpha [n_agents][arch[1]*4] column-major, state0 [n_agents][4] (the env.reset() observation),
  * tie_actions [n_agents][n_decisions_max]: replayed rand(rng_action, 0:1) stream (:89),
@@ -397,6 +400,27 @@ int32_t snn_actor_episodes_env(snn_actor* a, int32_t env, const double* matalpha
                                const int32_t* tie_picks, int32_t tie_stride, int32_t n_decisions_max, int32_t win_size,
                                int32_t train, double* rewards, int32_t* n_decisions, int32_t* n_rand,
                                double* state_out, double* device_ms);
+
+/* ---------------------------------------------------------------------------------------------
+ * Grid-cell state encoders on the device (Julia/Modules/Gridcells): the distance tests of
+ *   input_spikes(obs, grid_cells::Array{HexGrid})      StateSpikeGaussGrid.jl:83-109
+ *   latency_spikes(obs, grid_cells, win_size)          StateSpikeGaussGrid.jl:111-139
+ * for a batch of observations.  The grids (HexGrid.jl, GridGenerator.jl: `grid.grid`, `grid.node_size`) are built
+ * by the caller and uploaded once: grid g has the nodes node_xy[2*node_off[g] .. 2*node_off[g+1]) as (x, y) pairs
+ * in the grid's own order (the encoder takes the FIRST node inside the radius, `filter(...)[1]`).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct snn_gridcode snn_gridcode;
+int32_t snn_gridcode_create(int32_t device, int32_t n_grids, const int64_t* node_off, const double* node_xy,
+                            const double* node_size, snn_gridcode** out);
+int32_t snn_gridcode_destroy(snn_gridcode* g);
+/* obs [n_obs][4] CartPole observations.  Neuron i (0-based) = grid i on (x, theta % pi), neuron n_grids + i =
+ * grid i on (x_dot, theta_dot), both scaled from [-15, 15] to the unit square (:85-89).
+ *   intensity_out [n_obs][2*n_grids] or NULL: 0.999999 * exp(-2 d / node_size) of the first node closer than
+ *     reach * node_size (reach 1.5 for input_spikes :95, 1.25 for latency_spikes :123), 0 where no node is;
+ *   slot_out [n_obs][2*n_grids] or NULL: the 0-based millisecond of the win_size window at which the neuron fires,
+ *     win_size - floor(win_size * intensity) - 1 (:131-134), -1 where it stays silent. */
+int32_t snn_gridcode_encode(snn_gridcode* g, const double* obs, int32_t n_obs, double reach, int32_t win_size,
+                            double* intensity_out, int32_t* slot_out);
 
 #ifdef __cplusplus
 }

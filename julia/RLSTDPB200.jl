@@ -12,8 +12,10 @@ module RLSTDPB200
 
 import Random
 
-export Network, step!, run_window!, add_dopamine!, reset_v!, weights, eligibility,
-       ActorPopulation, set_weights!, play_episodes
+export Network, NetworkCol, step!, run_window!, add_dopamine!, reset_v!, weights, eligibility,
+       set_param!, get_param, checkpoint, restore!,
+       ActorPopulation, set_weights!, play_episodes,
+       LayeredNetwork, step_LIF!, step_LIF_critic!, learn!, learn_critic!
 
 const LIB = get(ENV, "SNN_B200_LIB", joinpath(@__DIR__, "..", "rl_stdp_b200", "libsnn_b200.so"))
 
@@ -186,6 +188,65 @@ add_dopamine!(net::Network, x::Real; instance::Integer = 0) =
     check(ccall((:snn_add_dopamine, LIB), Int32, (Ptr{Cvoid}, Int32, Float64), net.handle, instance, x))
 reset_v!(net::Network) = check(ccall((:snn_reset_v, LIB), Int32, (Ptr{Cvoid},), net.handle))
 
+# ---- named parameters (ABI 3): the model's scalars by their field name (`net.param["apre"] = ...` of the reference's
+#      Dict-driven nets), scheduling / diagnostic switches ("persistent", "graph", "timeline", ...) — snn_b200.h
+set_param!(net::Network, name::AbstractString, value::Real) =
+    check(ccall((:snn_set_param, LIB), Int32, (Ptr{Cvoid}, Cstring, Float64), net.handle, name, value))
+function get_param(net::Network, name::AbstractString)
+    v = Ref{Float64}(0.0)
+    check(ccall((:snn_get_param, LIB), Int32, (Ptr{Cvoid}, Cstring, Ref{Float64}), net.handle, name, v))
+    v[]
+end
+
+# ---- checkpoint / resume with the axonal delays in flight (the reference only saves genomes, save_param.jl:4-47)
+function checkpoint(net::Network)
+    n = Ref{Int64}(0)
+    check(ccall((:snn_checkpoint_bytes, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), net.handle, n))
+    blob = zeros(UInt8, n[])
+    check(ccall((:snn_checkpoint, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int64), net.handle, blob, n[]))
+    blob
+end
+restore!(net::Network, blob::Vector{UInt8}) =
+    check(ccall((:snn_restore, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int64), net.handle, blob, length(blob)))
+
+"""
+    NetworkCol(n_neurons, connectivity, n_exc; connection)
+
+Variant B, `Network(n_neurons, connectivity, n_exc)` of Old_net/new_net_col.jl:86-103: `connection`, `s`, `sd` are
+held TRANSPOSED ([post, pre], "read by columns", :13-15).  `connection` is what `connect()` draws ([pre, post], :28);
+the constructor transposes it (:94) and hands the matrices to the library exactly as that struct holds them.
+Everything else (`step!`, `run_window!`, `net.da`, ...) is the `Network` API; `weights(net)` returns s[pre, post].
+"""
+function NetworkCol(n_neurons::Int64, connectivity::Float64, n_exc::Int64;
+                    connection::AbstractMatrix = (rand(n_neurons, n_neurons) .< connectivity),
+                    dtype::Symbol = :f64, mode::Symbol = :exact, device::Integer = 0)
+    conn = Matrix{Int64}(connection)
+    conn_t = Matrix{Int64}(transpose(conn))               # new_net_col.jl:94
+    s = zeros(n_neurons, n_neurons)                        # :95-99
+    s[:, 1:n_exc] .= 1.0
+    s[:, n_exc+1:end] .= -1.0
+    s .*= conn_t
+    cfg = SnnConfig()
+    check(ccall((:snn_config_default, LIB), Int32, (Ref{SnnConfig},), cfg))
+    cfg.dtype = dtype == :f64 ? 1 : 0
+    cfg.mode = mode == :exact ? 1 : 0
+    cfg.device = device
+    cfg.n_neurons = n_neurons; cfg.n_per_instance = n_neurons; cfg.n_exc = n_exc
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:snn_create, LIB), Int32, (Ref{SnnConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+    check(ccall((:snn_set_synapses_dense_col, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}), h[], s, conn_t))
+    rowptr = zeros(Int64, n_neurons + 1); post = Int32[]
+    for i in 1:n_neurons
+        for j in 1:n_neurons
+            conn[i, j] != 0 && push!(post, Int32(j - 1))
+        end
+        rowptr[i+1] = length(post)
+    end
+    net = Network(h[], n_neurons, n_exc, conn, rowptr, post, collect(1:n_exc), collect(n_exc+1:n_neurons))
+    finalizer(n -> (n.handle != C_NULL && ccall((:snn_destroy, LIB), Int32, (Ptr{Cvoid},), n.handle); n.handle = C_NULL), net)
+    return net
+end
+
 # ---- one network over several GPUs (one Julia process per GPU; include/snn_b200.h snn_partition_*)
 const PEER_BLOB_BYTES = 192
 
@@ -281,6 +342,77 @@ function play_episodes(pop::ActorPopulation, matalpha::Array{Float64,3}, state0:
                     rewards, nd, nr, so, ms))
     end
     return rewards, nd, nr
+end
+
+# ---- the layered LIF network as the reference's scripts hold it: ONE `Network(arch, param)` (net_arch.jl:98-128)
+#      with step_LIF! / step_LIF_critic! / learn! / learn_critic! of net_arch.jl:213-272 — a population of one.
+
+"`LayeredNetwork(arch, param)` stands for `Network(arch::Array{Int64}, param::Dict)` (net_arch.jl:98-128)."
+mutable struct LayeredNetwork
+    pop::ActorPopulation
+    arch::Vector{Int64}
+    param::Dict
+    n_exc::Int64
+    n_neurons::Int64
+end
+function LayeredNetwork(arch::Vector{Int64}, param::Dict = Dict(); device::Integer = 0)
+    pop = ActorPopulation(arch, param, 1; device = device)
+    n_exc = sum(arch)
+    LayeredNetwork(pop, arch, param, n_exc, n_exc + sum(arch[2:end-1]))
+end
+
+# one call of step_LIF!(net, input_spikes, train): `input_spikes` lists every input neuron once, as int_spikes
+# (PoissonStateSpike.jl:62-68) builds it — the form every script of the reference passes
+function lif_step(net::LayeredNetwork, input_spikes::Array{Tuple{Int64,Float64}}, train::Bool, critic::Bool)
+    a1 = net.arch[1]
+    @assert sort([t[1] for t in input_spikes]) == collect(1:a1) "input_spikes must list the neurons 1:arch[1] once each"
+    inten = zeros(Float64, a1)
+    for (i, x) in input_spikes
+        inten[i] = x
+    end
+    mask = zeros(Int32, 2)            # bit j of the 64-bit mask = neuron j+1 spiked
+    ms = Ref{Float64}(0.0)
+    GC.@preserve inten mask begin
+        check(ccall((:snn_actor_window, LIB), Int32,
+                    (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ref{Float64}),
+                    net.pop.handle, 1, inten, train ? 1 : 0, critic ? 1 : 0, 0, C_NULL, mask, ms))
+    end
+    bits = reinterpret(UInt32, mask[1])
+    [j + 1 for j in 0:min(31, net.n_neurons - 1) if (bits >> j) & 0x1 == 0x1]
+end
+
+"step_LIF!(net, input_spikes, train)  (net_arch.jl:256-263) -> spiked (1-based ids)"
+step_LIF!(net::LayeredNetwork, input_spikes::Array{Tuple{Int64,Float64}}, train::Bool = false) =
+    lif_step(net, input_spikes, train, false)
+"step_LIF_critic!(net, input_spikes, train)  (net_arch.jl:265-272)"
+step_LIF_critic!(net::LayeredNetwork, input_spikes::Array{Tuple{Int64,Float64}}, train::Bool = false) =
+    lif_step(net, input_spikes, train, true)
+"learn!(net)  (net_arch.jl:213-220): e[l] += da * de[l], clamped to [0, wmax]"
+learn!(net::LayeredNetwork) = check(ccall((:snn_actor_learn, LIB), Int32, (Ptr{Cvoid}, Int32), net.pop.handle, 0))
+"learn_critic!(net)  (net_arch.jl:222-235)"
+learn_critic!(net::LayeredNetwork) = check(ccall((:snn_actor_learn, LIB), Int32, (Ptr{Cvoid}, Int32), net.pop.handle, 1))
+
+# `net.da`, `net.v`, `net.ho`, `net.trace_e` read through; `net.da = x` / `net.da += x`, `net.v .= c` write through
+function actor_array(net::LayeredNetwork, field::Int32, n::Integer)
+    out = zeros(Float64, n)
+    check(ccall((:snn_actor_get_array, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64),
+                getfield(net, :pop).handle, field, 0, out, n))
+    out
+end
+function Base.getproperty(net::LayeredNetwork, f::Symbol)
+    f === :da && return actor_array(net, FIELD_DA, 1)[1]
+    f === :v && return actor_array(net, FIELD_V, getfield(net, :n_neurons))
+    f === :ho && return actor_array(net, FIELD_HO, getfield(net, :n_neurons))
+    f === :trace_e && return actor_array(net, FIELD_TRACE, getfield(net, :n_exc))
+    return getfield(net, f)
+end
+function Base.setproperty!(net::LayeredNetwork, f::Symbol, x)
+    if f === :da || f === :v
+        a = f === :da ? [Float64(x)] : Vector{Float64}(x)
+        return check(ccall((:snn_actor_set_array, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64),
+                           getfield(net, :pop).handle, f === :da ? FIELD_DA : FIELD_V, 0, a, length(a)))
+    end
+    return setfield!(net, f, x)
 end
 
 function default_tie_picks(env::Int32, n_steps::Integer, n_agents::Integer)

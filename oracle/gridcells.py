@@ -1,11 +1,11 @@
-"""Host-side mirror of the reference's grid-cell state encoders (second half):
+"""CHECKER of the device-side grid-cell encoders (rl_stdp_b200/csrc/gridcode.cu): a restatement of
 Julia/Modules/Gridcells/{HexGrid,GridGenerator,StateSpikeGaussGrid,StateSpikeGrid}.jl.
 
-They turn one CartPole observation into the `input_spikes` argument of `step!(net, input_spikes, train)`
-for the Izhikevich layered nets (net_res.jl / net_arch.jl variant E): a list of (neuron, intensity) pairs —
-`snn_current_event`s of `snn_step_ex` here (`LayeredNetwork` / `NetworkRes` take them as idx + intensity) —,
-a list of neuron ids (binary grids), or per-millisecond id lists (latency code).  The work is a few hundred
-distance tests per decision: it stays on the host, next to the environment.
+TEST INFRASTRUCTURE ONLY — nothing under rl_stdp_b200/ imports this.  It builds the grids the tests feed to the
+device (the product takes grids from its caller: in the reference's workflow GridGenerator.jl stays on the Julia
+side) and restates `input_spikes` / `latency_spikes` observation by observation.  `gauss` uses the oracle's
+written-out fdlibm exp (oracle/lif_oracle.c::ora_exp), the same IEEE operations as the device, so intensities
+compare bit for bit; against libm's exp it differs by at most one ulp (tests/test_gridcells_cpu.py).
 
 Not pinned by reference outputs: the only saved encoder output (CartPole/Heatmaps/disp_spikesGrid.jld) was made
 with grids drawn from an unseeded `rand()`.  `grid_gen()` itself IS reproducible: it calls `Random.seed!(0)`, and
@@ -17,7 +17,7 @@ import math
 
 import numpy as np
 
-from .julia_rng import DSFMT
+from rl_stdp_b200.julia_rng import DSFMT
 
 
 def ref_grid(hex_size: float) -> np.ndarray:
@@ -120,7 +120,8 @@ def grid_gen():
 
 def gauss(d, node_size):
     """StateSpikeGaussGrid.jl:9 (never reaches one: the latency code indexes with it)"""
-    return 0.999999 * math.exp(-2 * (d / node_size))
+    from . import py_oracle as po
+    return 0.999999 * po.exp_fdlibm(-2 * (d / node_size))
 
 
 def _first_close(grid, p, radius):
@@ -183,40 +184,3 @@ def binary_spikes(obs, cells_pos, cells_vel):
     """StateSpikeGrid.jl:6-30: ids of the grids with a node within one node_size of the state."""
     ids, _ = input_spikes(obs, cells_pos, cells_vel, reach=1.0)
     return ids
-
-
-# ---- DVS-style change encoder (Julia/Modules/DVS/StateSpikeDVSv2.jl) -------------------------------------
-# Third-party piece: Discretizers.jl `LinearDiscretizer` (unpinned in the reference).  Restated from its
-# published behaviour: nbins equal-width bins over [lo, hi], a value below / above the range falls into the
-# first / last bin, bin i covers [edge_i, edge_{i+1}) and the last bin includes its right edge.
-
-def lindisc(obs_low, obs_high, neurons=(200, 150, 100, 150)):
-    """lindisc :5-18: per observation component (lo, hi, nbins); velocities are binned over [-50, 50]."""
-    return [(float(obs_low[0]), float(obs_high[0]), int(neurons[0])), (-50.0, 50.0, int(neurons[1])),
-            (float(obs_low[2]), float(obs_high[2]), int(neurons[2])), (-50.0, 50.0, int(neurons[3]))]
-
-
-def _encode(disc, x):
-    lo, hi, n = disc
-    if x < lo:
-        return 1
-    if x >= hi:
-        return n
-    return min(n, int(math.floor((x - lo) / ((hi - lo) / n))) + 1)
-
-
-def dvs_spikes(obs, obs_pre, discs, neurons=(200, 150, 100, 150)):
-    """input_spikes :30-47: one spike per bin crossed between two observations — an 'up' population and a
-    'down' population of neurons[i] cells per component.  0-based ids, in the reference's push order."""
-    spikes = []
-    off = 0
-    for i in range(4):
-        a, b = _encode(discs[i], obs[i]), _encode(discs[i], obs_pre[i])
-        delta = a - b
-        for j in range(1, abs(delta) + 1):
-            if delta > 0:
-                spikes.append(a - j + 2 * off - 1)
-            else:
-                spikes.append(a + j + 2 * off + neurons[i] - 1)
-        off += neurons[i]
-    return np.array(spikes, np.int32)

@@ -424,3 +424,36 @@ double ora_play_episode_mountcar(ora_lay* o, const double* matalpha, const doubl
   if (state_out) { state_out[0] = st[0]; state_out[1] = st[1]; }
   return tot_reward;
 }
+
+/* exp(x) for |x| < 700: fdlibm e_exp.c (k = round(x / ln2), r = x - k*ln2 in two pieces, degree-5 rational kernel),
+ * written out operation by operation — the device encoders (rl_stdp_b200/csrc/gridcode.cu::exp_fdlibm) evaluate the
+ * same IEEE operations, so gauss() of StateSpikeGaussGrid.jl:9 compares bit for bit between checker and device. */
+double ora_exp(double x) {
+  const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00,
+               P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+               P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+  const double ax = x < 0 ? -x : x;
+  double hi = 0.0, lo = 0.0;
+  int k = 0;
+  if (ax > 0.34657359027997264) {
+    if (ax < 1.0397207708399179) {
+      if (x > 0) { hi = x - ln2HI; lo = ln2LO; k = 1; } else { hi = x + ln2HI; lo = -ln2LO; k = -1; }
+    } else {
+      k = (int)(invln2 * x + (x < 0 ? -0.5 : 0.5));
+      const double t = (double)k;
+      hi = x - t * ln2HI;
+      lo = t * ln2LO;
+    }
+    x = hi - lo;
+  } else if (ax < 3.725290298461914e-09) {
+    return 1.0 + x;
+  }
+  const double t = x * x;
+  const double c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  if (k == 0) return 1.0 - ((x * c) / (c - 2.0) - x);
+  const double y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
+  union { double d; long long i; } u;
+  u.d = y;
+  u.i += (long long)k << 52;
+  return u.d;
+}

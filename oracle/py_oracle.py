@@ -119,6 +119,7 @@ def lib() -> C.CDLL:
         L.ora_lay_spike_izh.restype = C.c_int
         L.ora_lay_spike_izh.argtypes = [vp, vp]
         L.ora_lay_learn.argtypes = [vp]
+        L.ora_lay_learn_critic.argtypes = [vp]
         L.ora_cartpole_step.restype = C.c_int
         L.ora_cartpole_step.argtypes = [vp, C.c_int]
         L.ora_norm_cartpole.argtypes = [vp, vp]
@@ -134,12 +135,19 @@ def lib() -> C.CDLL:
         L.ora_play_episode_mountcar.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         L.ora_kcos.restype = dbl
         L.ora_kcos.argtypes = [dbl]
+        L.ora_exp.restype = dbl
+        L.ora_exp.argtypes = [dbl]
         _lib = L
     return _lib
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def exp_fdlibm(x: float) -> float:
+    """exp as the device encoders evaluate it (oracle/lif_oracle.c::ora_exp)"""
+    return float(lib().ora_exp(float(x)))
 
 
 class DenseA:
@@ -289,6 +297,10 @@ class Layered:
         it = np.ascontiguousarray(intensity, np.float64)
         k = lib().ora_lay_step_lif(self._h, _p(idx), _p(it), len(idx), int(train), int(critic), _p(self._spk))
         return self._spk[:k].copy()
+
+    def learn(self, critic=False):
+        """learn!(net) / learn_critic!(net) on their own (net_arch.jl:213-235)"""
+        (lib().ora_lay_learn_critic if critic else lib().ora_lay_learn)(self._h)
 
     def step_izh(self, idx=None, intensity=None, train=False):
         if idx is not None:

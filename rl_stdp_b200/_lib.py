@@ -124,10 +124,15 @@ SYMBOLS = {
     "snn_actor_get_array": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
     "snn_actor_set_array": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64]),
     "snn_actor_window": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP]),
+    "snn_actor_learn": (C.c_int32, [_VP, C.c_int32]),
     "snn_actor_episodes": (C.c_int32, [_VP, _VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP,
                                        _VP]),
     "snn_actor_episodes_env": (C.c_int32, [_VP, C.c_int32, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                            _VP, _VP, _VP, _VP, _VP]),
+    # grid-cell encoders
+    "snn_gridcode_create": (C.c_int32, [C.c_int32, C.c_int32, _VP, _VP, _VP, C.POINTER(_VP)]),
+    "snn_gridcode_destroy": (C.c_int32, [_VP]),
+    "snn_gridcode_encode": (C.c_int32, [_VP, _VP, C.c_int32, C.c_double, C.c_int32, _VP, _VP]),
 }
 
 SNN_ENV_CARTPOLE, SNN_ENV_MOUNTAINCAR = 0, 1

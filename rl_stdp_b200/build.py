@@ -21,6 +21,7 @@ UNITS = [
     ("snn_f64.cu", ["-fmad=false"]),
     ("snn_build.cu", []),
     ("actor.cu", ["-fmad=false"]),
+    ("gridcode.cu", ["-fmad=false"]),
     ("capi.cu", []),
 ]
 HEADERS = ["snn_engine.cuh", "snn_common.h", "actor.h", os.path.join("..", "..", "include", "snn_b200.h")]

@@ -444,6 +444,29 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
   store_agent<NS>(p, a, lane, v, ho, da, se, sde, str);
 }
 
+// learn!(net) / learn_critic!(net) on their own (net_arch.jl:213-235), for every agent: e += g * de, clamp to
+// [0, wmax] (g = da, critic: eta*da), then for the critic the last div(arch[l],4) rows of the hidden e[l] <- winh
+__global__ void actor_learn_kernel(ActorDev p, int critic) {
+  const int a = blockIdx.x;
+  double* __restrict__ e = p.e + (size_t)a * p.w_tot;
+  const double* __restrict__ de = p.de + (size_t)a * p.w_tot;
+  const double g = critic ? DMUL(p.eta, p.da[a]) : p.da[a];
+  for (int q = threadIdx.x; q < p.w_tot; q += blockDim.x) {
+    const double x = DADD(e[q], DMUL(g, de[q]));
+    e[q] = x > p.wmax ? p.wmax : (x < 0.0 ? 0.0 : x);
+  }
+  if (critic) {
+    __syncthreads();
+    for (int l = 1; l < p.L - 1; ++l) {
+      const int n_inh = p.arch[l] / 4, nr = p.arch[l], nc = p.arch[l + 1];
+      for (int q = threadIdx.x; q < n_inh * nc; q += blockDim.x) {
+        const int i = nr - 1 - (q % n_inh), jj = q / n_inh;
+        e[p.woff[l] + i + nr * jj] = p.winh;
+      }
+    }
+  }
+}
+
 __global__ void fill_d(double* a, int64_t n, double x) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = x;
 }
@@ -580,6 +603,14 @@ static inline int actor_warps(const ActorDev& d) {
   return 1;
 }
 static inline size_t actor_smem(const ActorDev& d, int warps) { return (size_t)warps * (2 * d.w_tot + kActorTraceSlots) * sizeof(double); }
+
+int Actor::learn(int critic, std::string& err) {
+  ACT_OK(cudaSetDevice(impl_->device));
+  actor_learn_kernel<<<impl_->d.n_agents, 128, 0, impl_->stream>>>(impl_->d, critic);
+  ACT_OK(cudaGetLastError());
+  ACT_OK(cudaStreamSynchronize(impl_->stream));
+  return SNN_OK;
+}
 
 int Actor::window(int n_steps, const double* intensity, int train, int critic, int reset_v, int32_t* counts,
                   int32_t* spike_masks, double* device_ms, std::string& err) {

@@ -17,6 +17,7 @@ class Actor {
   int init(const snn_actor_config& cfg, std::string& err);
   int get_array(int field, int layer, double* host, int64_t count, std::string& err);
   int set_array(int field, int layer, const double* host, int64_t count, std::string& err);
+  int learn(int critic, std::string& err);
   int window(int n_steps, const double* intensity, int train, int critic, int reset_v, int32_t* counts,
              int32_t* spike_masks, double* device_ms, std::string& err);
   int episodes(int env, const double* matalpha, const double* state0, const int32_t* tie_actions, int tie_stride,

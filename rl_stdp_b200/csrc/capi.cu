@@ -45,6 +45,9 @@ uint64_t process_nonce() {
 namespace {
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
+}  // namespace
+namespace snn { int fail_with(int code, const std::string& msg) { return fail(code, msg); } }
+namespace {
 
 int validate(const snn_config& c, std::string& err) {
   if (c.struct_size != (int32_t)sizeof(snn_config)) { err = "snn_config.struct_size mismatch (ABI)"; return SNN_ERR_INVALID; }
@@ -355,6 +358,13 @@ int32_t snn_actor_window(snn_actor* a, int32_t n_steps, const double* intensity,
   if (!a) return fail(SNN_ERR_INVALID, "null actor");
   std::string err;
   int rc = a->impl.window(n_steps, intensity, train, critic, reset_v, counts, spike_masks, device_ms, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
+int32_t snn_actor_learn(snn_actor* a, int32_t critic) {
+  if (!a) return fail(SNN_ERR_INVALID, "null actor");
+  std::string err;
+  int rc = a->impl.learn(critic, err);
   return rc ? fail(rc, err) : SNN_OK;
 }
 

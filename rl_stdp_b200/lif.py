@@ -136,6 +136,10 @@ class ActorPopulation:
                                           _ptr(counts), _ptr(masks), C.byref(ms)))
         return counts, masks, ms.value
 
+    def learn(self, critic=False):
+        """learn!(net) / learn_critic!(net) on their own for every agent (net_arch.jl:213-235)."""
+        L.check(L.load().snn_actor_learn(self._h, int(critic)))
+
     def play_episodes(self, matalpha, state0, tie_actions=None, n_steps=200, win_size=40, train=False,
                       teach_actions=None, env="cartpole"):
         """play_episode for every agent, environment on the device.

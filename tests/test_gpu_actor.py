@@ -63,6 +63,34 @@ def test_decision_window_bitexact(train, critic):
     assert tot > 0
 
 
+@pytest.mark.parametrize("critic", [False, True])
+def test_learn_on_its_own_bitexact(critic):
+    """snn_actor_learn: learn!(net) / learn_critic!(net) called outside step_LIF!, as critic_sim.jl:107 does after a
+    window run with train = false — eligibility accumulates over the window, one weight update at its end."""
+    from rl_stdp_b200 import _lib as L
+    arch, A, T = [8, 8, 8], 9, 40
+    param = dict(theta=0.05, wei=0.3, wie=-0.2, apost=0.014, apre=0.019, ttrace=0.95, imin=0.9, eta=0.5, winh=-0.1)
+    pop, oras, rng = _mk(A, arch, 15, **param)
+    idx = np.arange(arch[0], dtype=np.int32)
+    inten = rng.random((A, arch[0])) * 1.2
+    da0 = rng.random(A) * 0.05
+    pop.set(L.FIELD_DA, da0)
+    pop.decision_window(inten, T, train=False, reset_v=True)
+    pop.learn(critic=critic)
+    moved = 0.0
+    for a, o in enumerate(oras):
+        o.da = da0[a]
+        o.v[:] = o.params["c"]
+        w0 = [o.e(l).copy() for l in range(len(arch) - 1)]
+        for _ in range(T):
+            o.step_lif(idx, inten[a], False, False)
+        o.learn(critic)
+        for l in range(len(arch) - 1):
+            assert np.array_equal(pop.weights(l)[a], o.e(l)), (a, l)
+            moved += np.abs(o.e(l) - w0[l]).sum()
+    assert moved > 0
+
+
 @pytest.mark.parametrize("arch", [[8, 8, 8, 8, 8], [12, 10, 6], [16, 16, 16]])
 def test_larger_actors_two_neurons_per_lane(arch):
     """Nets of 33..64 neurons (e.g. the [8,8,8,8,8] actors of CartPole/LIF_base): two neurons per lane.

@@ -1,11 +1,11 @@
-"""Host-side grid-cell encoders (rl_stdp_b200/gridcells.py, mirror of Julia/Modules/Gridcells/*.jl).
+"""The CHECKER of the device-side grid-cell encoders (oracle/gridcells.py, restatement of Julia/Modules/Gridcells/*.jl).
 No reference output pins them (DESIGN.md section 0, row f): structural properties, the reproducible part of
 grid_gen (Julia's seeded generator), and agreement with a literal loop-by-loop evaluation."""
 import math
 
 import numpy as np
 
-from rl_stdp_b200 import gridcells as gc
+from oracle import gridcells as gc
 
 OBS = [0.523324424, 0.323242424243, 0.4242424225, 0.224253525253]   # the scratch observation of StateSpikeGaussGrid.jl:157
 
@@ -104,25 +104,15 @@ def test_hex_modules_over_the_state_box():
     assert first == second
 
 
-def test_dvs_change_encoder():
-    discs = gc.lindisc([-4.8, -1e38, -0.418, -1e38], [4.8, 1e38, 0.418, 1e38])
-    assert discs[1] == (-50.0, 50.0, 150) and discs[0][2] == 200
-    same = gc.dvs_spikes(OBS, OBS, discs)
-    assert same.size == 0
-    # the cart moves right by three position bins (bin width 9.6 / 200 = 0.048): three 'up' cells of component 1
-    pre = list(OBS)
-    cur = list(OBS)
-    cur[0] = pre[0] + 3 * 0.048
-    up = gc.dvs_spikes(cur, pre, discs)
-    b = gc._encode(discs[0], cur[0])
-    assert up.tolist() == [b - 1 - 1, b - 2 - 1, b - 3 - 1]
-    down = gc.dvs_spikes(pre, cur, discs)
-    b0 = gc._encode(discs[0], pre[0])
-    assert down.tolist() == [b0 + 1 + 200 - 1, b0 + 2 + 200 - 1, b0 + 3 + 200 - 1]
-    # component offsets: 2 * (200), 2 * (200 + 150), ...
-    cur2 = list(OBS)
-    cur2[3] = OBS[3] + 100.0 / 150 * 1.5
-    ids = gc.dvs_spikes(cur2, OBS, discs)
-    assert ids.size >= 1 and np.all(ids >= 2 * (200 + 150 + 100)) and np.all(ids < 2 * (200 + 150 + 100) + 150)
-    # out-of-range values fall into the edge bins
-    assert gc._encode(discs[0], -100.0) == 1 and gc._encode(discs[0], 100.0) == 200
+def test_restated_exp_is_within_one_ulp_of_libm():
+    """gauss() uses the fdlibm exp written out in IEEE operations (oracle/lif_oracle.c::ora_exp; the device evaluates
+    the same ones): against libm it may differ in the last bit, never more, over the range the encoders use."""
+    from oracle import py_oracle as po
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([-rng.random(20000) * 4.0, rng.random(2000) * 4.0, [0.0, -1e-10, -0.3465, -0.3466, -1.0397, -1.0398]])
+    worst = 0.0
+    for x in xs:
+        a, b = po.exp_fdlibm(float(x)), math.exp(float(x))
+        worst = max(worst, abs(a - b) / math.ulp(b))
+    assert worst <= 1.0
+    assert po.exp_fdlibm(0.0) == 1.0
