@@ -46,6 +46,7 @@ WORKLOADS = {
     "c3_x64": (10_000, 8_000, 100, 1, 64),
     "tiny": (20_000, 16_000, 100, 20),
     "c4_actors": None,  # 4096 x LIF [8,8,8] CartPole actors, whole episodes on the device (per GPU: 4096/N)
+    "c2_teacher": None,  # BASELINE config 2: the Teacher loop (reward-driven dopamine, train = true), 256 learners per GPU
 }
 LEARN_PERIOD = int(os.environ.get("BENCH_LEARN_PERIOD", "10"))  # the reference learns every 10th ms (newnet_DASTDP.jl:48-51); the override is a diagnostic
 DA_PERIOD = 1000
@@ -226,7 +227,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     common = dict(dtype="f32", mode="fast", noise="philox", device=local, max_delay=dmax, learn_async=args.learn_async,
-                  chain=args.chain, persistent=not args.no_persistent)
+                  chain=args.chain, persistent=args.persistent, chain_lookahead=args.chain_lookahead, wave_kernels=not args.no_waves)
 
     def barrier():
         torch.cuda.synchronize()
@@ -437,8 +438,16 @@ def run_b200(args):
 
 
 def run_actors(args):
-    """Config 4: 4096 independent CartPole LIF actors (cartpole_fitness.jl play_episode), sharded by
-    instance over the ranks; a bench step = one full episode of every agent (<= 200 decisions x 40 ms)."""
+    """Configs 2 and 4, the LIF CartPole actor (Modules/Networks/net_arch.jl variant F), whole episodes on the device.
+
+    c4_actors  4096 independent actors (cartpole_fitness.jl play_episode, train = false), sharded by instance over
+               the ranks; a bench step = one full episode of every agent (<= 200 decisions x 40 ms).
+    c2_teacher BASELINE config 2: the Teacher loop (teacher_sim.jl:61-80,101-144) — train = true, after every
+               decision da += da_inc if the action matches the teacher's draw, -200 da_inc otherwise — run for 500
+               episodes (--steps) on 256 independent learners per GPU (seeds); a bench step = one episode of each.
+    The tie stream is the reference's default (`rng_seed = true`: every episode draws from a fresh
+    MersenneTwister(0)), so it is one shared 200-entry stream; per step the host uploads the start states (and,
+    c4: the population's observation matrices, which an evolution strategy rewrites every generation)."""
     import torch
     import torch.distributed as dist
     from rl_stdp_b200.lif import ActorPopulation, borne
@@ -447,18 +456,23 @@ def run_actors(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    arch, total = [8, 8, 8], 4096
+    teacher = args.workload == "c2_teacher"
+    arch, total = [8, 8, 8], (256 * world if teacher else 4096)
     A = total // world
     rng = np.random.Generator(np.random.Philox(key=4 + rank))
-    pop = ActorPopulation(arch, A, device=local)
+    pop = ActorPopulation(arch, A, device=local, **(dict(da_inc=0.0005) if teacher else {}))
     for l in range(2):
         pop.set_weights(l, np.clip(rng.standard_normal((A, 8, 8)) * 0.3 + 0.8, 0, 1.1))
     matalpha = borne(rng.random((A, 8, 4)) * 20 - 10, -1.0, 1.0)
 
     def episode():
         s0 = rng.random((A, 4)) * 0.1 - 0.05
-        ties = rng.integers(0, 2, size=(A, 200), dtype=np.int32)
-        return pop.play_episodes(matalpha, s0, ties, n_steps=200), s0.nbytes + ties.nbytes + matalpha.nbytes
+        if teacher:
+            teach = rng.integers(0, 2, size=(A, 200), dtype=np.int32)   # the teacher's rand(0:1), teacher_sim.jl:132
+            ties = rng.integers(0, 2, size=(A, 200), dtype=np.int32)
+            out = pop.play_episodes(matalpha, s0, ties, n_steps=200, train=True, teach_actions=teach)
+            return out, s0.nbytes + teach.nbytes + ties.nbytes + matalpha.nbytes
+        return pop.play_episodes(matalpha, s0, None, n_steps=200), s0.nbytes + matalpha.nbytes + 4 * 200
 
     for _ in range(args.warmup):
         episode()
@@ -466,10 +480,12 @@ def run_actors(args):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    dev_ms = 0.0; sim_ms = 0; h2d = 0
+    dev_ms = 0.0; sim_ms = 0; h2d = 0; first = last = None
     for _ in range(args.steps):
         out, nb = episode()
         dev_ms += out["device_ms"]; sim_ms += int(out["n_decisions"].sum()) * 40; h2d += nb
+        first = first if first is not None else float(out["rewards"].mean())
+        last = float(out["rewards"].mean())
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -482,14 +498,24 @@ def run_actors(args):
     else:
         wall_ms, sim_all = wall * 1e3, float(sim_ms)
     if rank == 0:
+        # bound of actor_episode_kernel: one warp per agent, fp64, the whole episode in registers / shared memory —
+        # neither HBM nor tensor cores; it is issue-latency bound (a dependent chain per LIF step), so what counts is
+        # how many of the SMs' warp slots the population fills
+        warp_slots = 148 * 64
         line = {"metric": "simulated agent-ms per wall-s", "value": sim_all / (dev_ms * 1e-3), "unit": "agent-ms/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "c4_actors", "agents": total, "arch": arch, "window_ms": 40, "max_decisions": 200,
-                           "env": "CartPole-v1 restated, on device"},
+                "higher_is_better": True, "scaling": "weak" if teacher else "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "agents": total, "arch": arch, "window_ms": 40, "max_decisions": 200,
+                           "env": "CartPole-v1 restated, on device",
+                           **({"train": "teacher dopamine after every decision (teacher_sim.jl:132-133), learn! every ms"}
+                              if teacher else {})},
                 "e2e": {"value": sim_all / (wall_ms * 1e-3), "unit": "agent-ms/s", "h2d_bytes_per_step": h2d // args.steps,
                         "d2h_bytes_per_step": A * (8 + 4 + 4 + 32)},
-                "gpu_launches": args.steps}
+                "gpu_launches": args.steps,
+                "occupancy": {"agents_per_gpu": A, "warps": A, "warp_slots_per_gpu": warp_slots, "fill": min(1.0, A / warp_slots),
+                              "bound": "issue latency of one warp per agent (no HBM traffic inside an episode)"},
+                "mean_reward_first_last_step": [first, last]}
         if world == 1 and not args.no_cpu:
             from oracle import py_oracle as po
             o = po.Layered(arch, "lif")
@@ -497,7 +523,11 @@ def run_actors(args):
                 o.e(l)[:, :] = np.clip(rng.standard_normal((8, 8)) * 0.3 + 0.8, 0, 1.1)
             t1 = time.perf_counter(); ms = 0
             while time.perf_counter() - t1 < min(args.cpu_seconds, 5.0):
-                _, nd, _, _ = o.play_episode(matalpha[0], rng.random(4) * 0.1 - 0.05, rng.integers(0, 2, 200), 200)
+                if teacher:
+                    _, nd, _, _ = o.play_episode(matalpha[0], rng.random(4) * 0.1 - 0.05, rng.integers(0, 2, 200), 200,
+                                                 train=True, teach_actions=rng.integers(0, 2, 200), da_inc=0.0005)
+                else:
+                    _, nd, _, _ = o.play_episode(matalpha[0], rng.random(4) * 0.1 - 0.05, rng.integers(0, 2, 200), 200)
                 ms += nd * 40
             dt = time.perf_counter() - t1
             line["cpu_baseline"] = {"value": ms / dt, "unit": "agent-ms/s", "cores": 1, "kind": "port",
@@ -566,9 +596,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload if args.workload != "c4_actors" else "c5_1M_100M"]
-    if args.workload == "c4_actors":
+    if args.workload in ("c4_actors", "c2_teacher"):
         args.workload = "c5_1M_100M"
+    wl = WORKLOADS[args.workload]
     n, ne, fan, dmax = wl[:4]
     n_inst = wl[4] if len(wl) > 4 else 1
     # the reference itself is single-threaded Julia; this arm gives its algorithm every host core
@@ -645,7 +675,9 @@ def main():
     ap.add_argument("--exp-flags", type=int, default=0, help="snn_config.reserved[1] diagnostics (2 timeline, 4 serialise the learn pass, 512 LSU pass); 0 for reported numbers")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--chain", default=None, help="persistent chain footprints 'nthr,syn,ltp,ltp_thr,learn,learn_thr,stages' (sweeps; default: the library's)")
-    ap.add_argument("--no-persistent", action="store_true", help="captured CUDA graph of per-step kernels instead of the persistent chain")
+    ap.add_argument("--chain-lookahead", type=int, default=0, help="persistent chain: steps of push lookahead (0 = default)")
+    ap.add_argument("--no-waves", action="store_true", help="captured graph: round 1's group-per-item side kernels instead of the waves")
+    ap.add_argument("--persistent", action="store_true", help="persistent chain of resident role kernels instead of the captured CUDA graph of per-step kernels")
     ap.add_argument("--learn-async", default="auto", choices=["auto", "off", "force"], help="learn pass beside the following steps (auto: large nets) or in place")
     ap.add_argument("--learn-lazy", type=int, default=0, help="EXPERIMENTAL event-driven learning: dense re-basing pass every M learn steps (0 = the reference's rule; not for reported numbers)")
     ap.add_argument("--learn-lazy-da", type=float, default=0.0, help="with --learn-lazy: re-base at every learn step while da exceeds this (0 = never)")
@@ -661,7 +693,7 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "c4_actors":
+    elif args.workload in ("c4_actors", "c2_teacher"):
         run_actors(args)
     else:
         run_b200(args)

@@ -201,8 +201,11 @@ int32_t snn_set_synapses_dense_col(snn_net* net, const double* s_colmajor,
  *      calls; so may the caller here, between two windows.
  *  (2) Everything that is NOT the model — any time unless marked [S] = only before the synapses are set:
  *      "graph"                 1 (default) whole windows as device-side schedules; 0 plain launches per step
- *      "persistent"            1 (default) production-mode windows run as the persistent chain (one resident
- *                              kernel per role); 0 the captured CUDA graph of per-step kernels
+ *      "persistent"            0 (default) production-mode windows run as a captured CUDA graph of per-step kernels;
+ *                              1 as the persistent chain: one resident kernel per role for the whole window, steps
+ *                              handed over through device-side counters (on one B200 the two
+ *                              are on par at 1M neurons, the graph is ahead on small nets)
+ *      "chain_lookahead"       persistent chain: steps of push lookahead, 1..3 (0 = default 2)
  *      "learn_async"       [S] 0 auto, 1 learn! always in place, 2 always the asynchronous double-buffered pass
  *      "learn_log_cap"     [S] entries of the sd-update log of the asynchronous pass (0 = by size)
  *      "learn_pass_blocks", "learn_pass_stages", "learn_pass_tile_k" [S]   asynchronous pass of the graph path
@@ -393,7 +396,11 @@ int32_t snn_actor_episodes(snn_actor* a, const double* matalpha, const double* s
  *                        every tied pair of pools draws `rand(rng_action, pool)` (:83-93) and the
  *                        decision then costs 2 instead of 1.
  * tie_picks [n_agents][tie_stride]: the replayed draw stream as 0-based indices into the
- * two-element pool (CartPole: the action itself); a MountainCar decision can consume three. */
+ * two-element pool (CartPole: the action itself); a MountainCar decision can consume three.
+ * tie_stride < 0: tie_picks is ONE stream of -tie_stride draws shared by all agents (the reference's default
+ * `rng_seed = true`: every episode draws from a fresh MersenneTwister(0), cartpole_fitness.jl:55).  An agent
+ * that meets more ties than the stream holds makes the call fail with SNN_ERR_CAPACITY.  An episode also ends at
+ * gym's TimeLimit (500 decisions CartPole-v1, 200 MountainCar-v0) whatever n_decisions_max says. */
 #define SNN_ENV_CARTPOLE 0
 #define SNN_ENV_MOUNTAINCAR 1
 int32_t snn_actor_episodes_env(snn_actor* a, int32_t env, const double* matalpha, const double* state0,

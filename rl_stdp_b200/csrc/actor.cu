@@ -320,7 +320,7 @@ __device__ __forceinline__ int mountcar_step(double s[4], int action) {
 template <int NS, int ENV>
 __global__ void __launch_bounds__(128)
 actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const double* __restrict__ state0,
-                     const int32_t* __restrict__ tie_actions, int tie_stride, const int32_t* __restrict__ teach_actions,
+                     const int32_t* __restrict__ tie_actions, int tie_stride, int tie_agent_stride, const int32_t* __restrict__ teach_actions,
                      int n_decisions_max, int win_size, int train, int32_t* __restrict__ tie_overflow,
                      double* __restrict__ rewards,
                      int32_t* __restrict__ n_dec, int32_t* __restrict__ n_rand_out, double* __restrict__ state_out) {
@@ -401,7 +401,7 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
       action = (sl >= sr) ? 0 : 1;
       if (sl == sr) {  // :87-95
         if (n_rand >= tie_stride) *tie_overflow = 1;  // the replayed rand(rng_action, 0:1) stream ran out
-        action = n_rand < tie_stride ? tie_actions[(size_t)a * tie_stride + n_rand] : 0;
+        action = n_rand < tie_stride ? tie_actions[(size_t)a * tie_agent_stride + n_rand] : 0;
         tot_reward = DSUB(tot_reward, 0.9);
         ++n_rand;
       }
@@ -424,7 +424,7 @@ actor_episode_kernel(ActorDev p, const double* __restrict__ matalpha, const doub
       for (int i = 0; i < 3; ++i)
         if (dif[i] == 0) {
           if (n_rand >= tie_stride) *tie_overflow = 1;
-          const int pick = n_rand < tie_stride ? tie_actions[(size_t)a * tie_stride + n_rand] : 0;
+          const int pick = n_rand < tie_stride ? tie_actions[(size_t)a * tie_agent_stride + n_rand] : 0;
           action = pool[i][pick & 1];
           fac = 2.0;
           ++n_rand;
@@ -650,6 +650,10 @@ int Actor::episodes(int env, const double* matalpha, const double* state0, const
                     const int32_t* teach_actions, int n_decisions_max, int win_size, int train, double* rewards,
                     int32_t* n_dec, int32_t* n_rand, double* state_out, double* device_ms, std::string& err) {
   ActorDev& d = impl_->d;
+  // tie_stride < 0: ONE stream of -tie_stride draws shared by all agents — the reference's default (`rng_seed = true`:
+  // every episode draws from a fresh MersenneTwister(0), cartpole_fitness.jl:55), 0.8 KB instead of 3.3 MB per call
+  const bool tie_shared = tie_stride < 0;
+  if (tie_shared) tie_stride = -tie_stride;
   if (!matalpha || !state0 || !tie_actions || !rewards || n_decisions_max <= 0 || win_size <= 0 || tie_stride <= 0) {
     err = "episodes: null argument / non-positive sizes"; return SNN_ERR_INVALID;
   }
@@ -668,7 +672,8 @@ int Actor::episodes(int env, const double* matalpha, const double* state0, const
   ACT_OK(m.b_s0.reserve(A * 4 * sizeof(double)));
   ACT_OK(m.b_so.reserve(A * 4 * sizeof(double)));
   ACT_OK(m.b_rw.reserve(A * sizeof(double)));
-  ACT_OK(m.b_tie.reserve(A * (size_t)tie_stride * sizeof(int32_t)));
+  const size_t tie_rows = tie_shared ? 1 : A;
+  ACT_OK(m.b_tie.reserve(tie_rows * (size_t)tie_stride * sizeof(int32_t)));
   if (teach_actions) ACT_OK(m.b_teach.reserve(A * (size_t)n_decisions_max * sizeof(int32_t)));
   ACT_OK(m.b_nd.reserve((2 * A + 1) * sizeof(int32_t)));
   double *d_ma = (double*)m.b_ma.ptr, *d_s0 = (double*)m.b_s0.ptr, *d_rw = (double*)m.b_rw.ptr, *d_so = (double*)m.b_so.ptr;
@@ -678,14 +683,14 @@ int Actor::episodes(int env, const double* matalpha, const double* state0, const
   ACT_OK(cudaMemsetAsync(d_ovf, 0, sizeof(int32_t), s));
   ACT_OK(cudaMemcpyAsync(d_ma, matalpha, A * d.arch[0] * nobs * sizeof(double), cudaMemcpyHostToDevice, s));
   ACT_OK(cudaMemcpyAsync(d_s0, state0, A * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
-  ACT_OK(cudaMemcpyAsync(d_tie, tie_actions, A * (size_t)tie_stride * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  ACT_OK(cudaMemcpyAsync(d_tie, tie_actions, tie_rows * (size_t)tie_stride * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   if (teach_actions)
     ACT_OK(cudaMemcpyAsync(d_teach, teach_actions, A * (size_t)n_decisions_max * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   {
     const int warps = actor_warps(d), blocks = (int)((A + warps - 1) / warps);
     cudaEventRecord(impl_->e0, s);
 #define EPISODE_LAUNCH(NS, ENV)                                                                                      \
-  actor_episode_kernel<NS, ENV><<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, tie_stride, d_teach, \
+  actor_episode_kernel<NS, ENV><<<blocks, warps * 32, actor_smem(d, warps), s>>>(d, d_ma, d_s0, d_tie, tie_stride, tie_shared ? 0 : tie_stride, d_teach, \
                                                                                  n_decisions_max, win_size, train, d_ovf, d_rw, \
                                                                                  d_nd, d_nr, d_so)
     if (env == SNN_ENV_CARTPOLE) { if (d.n <= 32) EPISODE_LAUNCH(1, 0); else EPISODE_LAUNCH(2, 0); }

@@ -76,6 +76,13 @@ template <> struct Ops<double> {
   static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
 };
 
+// x += v as a fire-and-forget reduction (red.global: no value comes back, the warp does not wait for L2).  Written as
+// PTX because inside the persistent kernels — loops around acquire loads and fences — nvcc keeps atomicAdd() with an
+// unused result as a RETURNING atomic (ATOMG), which stalls the issuing warp for a full L2 round trip per update.
+__device__ __forceinline__ void red_add(float* q, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add(double* q, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(q), "d"(v) : "memory"); }
+__device__ __forceinline__ void red_add(uint32_t* q, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(q), "r"(v) : "memory"); }
+
 // Philox4x32-10, identical to oracle/snn_oracle.c:ora_philox4x32.
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -106,6 +113,9 @@ constexpr int32_t kNever = -(1 << 30);  // "no spike yet" in hist / old_last
 // G = Dmax + kLag (+1 each for variant_g) make every slot a reader may scan valid and every older spike
 // already retired into old_last, whatever the interleaving inside that bound.
 constexpr int kLag = 3;
+// The persistent chain pushes currents up to kMaxLook steps ahead of their arrival (Engine::launch_chain): Iacc is a
+// ring of kIaccRing buffers there (the other schedulers use the first two, indexed by step parity).
+constexpr int kMaxLook = 3, kIaccRing = 4;
 constexpr int kMaxRanks = 8;
 
 // State of the asynchronous learn pass.  `state` packs (cur << 31) | frontier, frontier in units
@@ -131,7 +141,7 @@ struct DevNet {
   int32_t Dmax, R, B, W;        // R = Dmax+2 ring slots ; W = bitmap words per slot
   // neuron state
   T *v, *u, *ho;
-  T* Iacc;           // [2][Nld]  Iacc[t&1] = currents consumed by the Euler update of step t
+  T* Iacc;           // [kIaccRing][Nld]  Iacc[t&1] (chain: Iacc[t % ring]) = currents consumed by the Euler update of step t
   // STDP traces are not stored: between two spikes of a neuron the reference's trace is the FIXED sequence
   // set, set*decay, (set*decay)*decay, ... (new_net.jl:123,130), so the trace of neuron i after the set of step
   // s is tseq[s - (last spike of i at or before s)], 0 before the first spike — bit for bit what the iterated
@@ -149,7 +159,8 @@ struct DevNet {
   int32_t* spk_cnt;  // [R]
   T* da;             // [2][B]    da[t&1] = dopamine after the decay of step t-1
   // synapses (internal order: ascending pre, delay, caller position)
-  const uint2* seg01;    // [N] (first, end) of the delay-1 segment of every row: the 8 MB the neuron role needs of the 84 MB table
+  const uint4* segL;     // [N] bounds of the delay-1, -2 and -3 segments of every row (seg[i][0..3]): the 16 MB the neuron
+                         // role needs of the 84 MB table, L2-resident
   const uint32_t* seg;   // [N][Dmax+1] delay-segment table
   const int32_t* post;   // [E]
   T2* wsd;               // = wsdX[0]; [E] (w, sd) interleaved: one 8-byte access serves propagate + LTD
@@ -221,11 +232,12 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
   return t;
 }
 __device__ __forceinline__ void tl_begin(unsigned long long* tl, int cls, int k) {
-  if (tl && threadIdx.x == 0 && k + 1 >= 0 && k + 1 < kTlSteps) atomicMin(&tl[cls * kTlSteps + k + 1], gtime_ns());
+  if (tl && threadIdx.x == 0 && k + 1 >= 0 && k + 1 < kTlSteps)
+    asm volatile("red.global.min.u64 [%0], %1;" ::"l"(&tl[cls * kTlSteps + k + 1]), "l"(gtime_ns()) : "memory");
 }
 __device__ __forceinline__ void tl_end(unsigned long long* tl, int cls, int k) {
   if (tl && threadIdx.x == 0 && k + 1 >= 0 && k + 1 < kTlSteps)
-    atomicMax(&tl[kTlClasses * kTlSteps + cls * kTlSteps + k + 1], gtime_ns());
+    asm volatile("red.global.max.u64 [%0], %1;" ::"l"(&tl[kTlClasses * kTlSteps + cls * kTlSteps + k + 1]), "l"(gtime_ns()) : "memory");
 }
 
 // Per-window inputs/outputs.  Lives in device memory so that a captured graph never has to be
@@ -358,13 +370,13 @@ __device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, u
     if constexpr (sizeof(T) == 4) {
       asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(vw.cur + e), "f"(d), "f"(dh) : "memory");
     } else {
-      atomicAdd(&vw.cur[e].x, d);
-      atomicAdd(&vw.cur[e].y, dh);
+      red_add(&vw.cur[e].x, d);
+      red_add(&vw.cur[e].y, dh);
     }
     return;
   }
   if ((e >> 5) < vw.front) {
-    atomicAdd(&vw.cur[e].y, delta);
+    red_add(&vw.cur[e].y, delta);
     return;
   }
   namespace cg = cooperative_groups;
@@ -377,7 +389,7 @@ __device__ __forceinline__ void sd_add(const DevNet<T>& p, const WView<T>& vw, u
     LogEntry<T> le; le.e = e; le.d = delta;
     p.dlog[(size_t)region * p.log_region_cap + pos] = le;
   } else {
-    atomicAdd(&p.dsd[e], delta);
+    red_add(&p.dsd[e], delta);
     p.lc->spilled = 1u;
   }
 }
@@ -422,7 +434,6 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
   // spike-record offset of this step = offset of the previous step + its (final) spike count
   int32_t rec_base = 0;
   const int n_prev = (k > 0 && (rec_ids || bid == 0)) ? p.spk_cnt[prev] : 0;
-  if (DETECT) retire_spikes<T>(p, t, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
   if (rec_ids && k > 0) {
     int64_t nxt = (int64_t)cx->rec_off[k - 1] + n_prev;
     rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
@@ -587,7 +598,7 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
 #pragma unroll
                   for (int q4 = 0; q4 < 4; ++q4)
                     if (pj[q4] >= 0)
-                      atomicAdd(&I_now[pj[q4]],
+                      red_add(&I_now[pj[q4]],
                                 w_resolve<T>(p, pw[q4], fly[q4], p.plastic_ei || ((uint32_t)pj[q4] - ibase) < Ne, inst, pc[q4]));
                 }
               }
@@ -599,6 +610,8 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
     st4(p.v + j0, v);
     st4(p.u + j0, u);
   }
+  // (after the neurons: the list length it needs is a dependent load nobody should wait for up front)
+  if (DETECT) retire_spikes<T>(p, t, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
   if (p.tl) __syncthreads();  // timeline: stamp when the block's last warp (spike pushes) is done
   tl_end(p.tl, 0, k);
 }
@@ -638,7 +651,8 @@ __device__ __forceinline__ uint32_t ll_word(const DevNet<T>& p, int slot, uint32
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void remote_body(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k, int32_t wait_peers,
-                                            const uint32_t bid, const uint32_t nblk) {
+                                            const uint32_t bid, const uint32_t nblk, const int nd = 1, const int ring = 2) {
+  // nd / ring: the persistent chain pushes the delays 1..nd of a spiker here, into a ring of `ring` current buffers
   tl_begin(p.tl, 4, k);
   const bool from_ll = wait_peers != 0;
   const int lane = threadIdx.x & 31;
@@ -653,7 +667,6 @@ __device__ __forceinline__ void remote_body(const DevNet<T>& p, const WindowCtx<
     int64_t nxt = (int64_t)__ldcg(cx->rec_off + (k - 1)) + __ldcg(p.spk_cnt + prev);
     rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
   }
-  T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;
   const WView<T> vw = wview(p);
   // partition bounds are multiples of 128 neurons = 4 words (the last rank's range is padded up to Nld)
   const uint32_t w_lo = (uint32_t)(p.part_lo >> 5), w_hi = (uint32_t)((p.part_hi >= p.N ? p.Nld : p.part_hi) >> 5);
@@ -700,14 +713,17 @@ __device__ __forceinline__ void remote_body(const DevNet<T>& p, const WindowCtx<
         const uint32_t wsrc = __shfl_sync(0xffffffffu, word, src), isrc = __shfl_sync(0xffffffffu, wi, src) << 5;
         for (uint32_t wb = wsrc; wb; wb &= wb - 1u) {
           const uint32_t i = isrc + (uint32_t)(__ffs(wb) - 1);
-          const uint32_t s0 = p.seg[(size_t)i * (p.Dmax + 1)], s1 = p.seg[(size_t)i * (p.Dmax + 1) + 1];
+          const uint4 sg = p.segL[i];
+          const uint32_t s_end = nd == 1 ? sg.y : (nd == 2 ? sg.z : sg.w);
           const bool row_exc = i < (uint32_t)p.Ne;  // partitioned runs are single-instance
-          for (uint32_t e = s0 + lane; e < s1; e += 32) {
+          for (uint32_t e = sg.x + lane; e < s_end; e += 32) {
             const uint32_t j = (uint32_t)p.post[e];
             bool fly;
             const typename DevNet<T>::T2 ws = w_fetch<T>(vw, e, row_exc, fly);
             const T wc = c_fetch<T>(p, vw, e, fly);
-            atomicAdd(&I_now[j], w_resolve<T>(p, ws, fly, p.plastic_ei || j < (uint32_t)p.Ne, 0u, wc));
+            const uint32_t dl = (e >= sg.y ? 1u : 0u) + (e >= sg.z ? 1u : 0u);  // delay - 1
+            red_add(p.Iacc + (size_t)((t + dl) % ring) * p.Nld + j,
+                      w_resolve<T>(p, ws, fly, p.plastic_ei || j < (uint32_t)p.Ne, 0u, wc));
           }
         }
       }
@@ -864,7 +880,7 @@ __device__ __forceinline__ void synapse_body(const DevNet<T>& p, const WindowCtx
         bool fly;
         const typename DevNet<T>::T2 ws = w_fetch<T>(vw, e, row_exc, fly);
         const T wc = c_fetch<T>(p, vw, e, fly);
-        atomicAdd(&I_next[j], w_resolve<T>(p, ws, fly, p.plastic_ei || (j - ibase) < Ne, inst, wc));
+        red_add(&I_next[j], w_resolve<T>(p, ws, fly, p.plastic_ei || (j - ibase) < Ne, inst, wc));
       } else if (row_plastic && (p.plastic_ei || (j - ibase) < Ne)) {
         const T dn = O::mul(p.apre, trace_at<T>(p, j, t32, t32));
         if (ATOMIC) {  // production: fire-and-forget reduction, LTP of this step comes from ltp_kernel
@@ -1532,7 +1548,7 @@ learn_replay_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k,
     const LogEntry<T>* __restrict__ lg = p.dlog + (size_t)r * p.log_region_cap;
     for (uint32_t q = threadIdx.x; q < n; q += blockDim.x) {
       const LogEntry<T> le = lg[q];
-      atomicAdd(&w[le.e].y, le.d);
+      red_add(&w[le.e].y, le.d);
     }
     __syncthreads();
     if (threadIdx.x == 0 && cnt) p.log_cnt[(size_t)r * kLogStride] = 0u;
@@ -1541,7 +1557,7 @@ learn_replay_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k,
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = tid; e < p.E; e += nth) {
       const T d = p.dsd[e];
-      if (d != (T)0) { atomicAdd(&w[e].y, d); p.dsd[e] = (T)0; }
+      if (d != (T)0) { red_add(&w[e].y, d); p.dsd[e] = (T)0; }
     }
   }
   if (begin_next) {
@@ -1605,6 +1621,8 @@ struct ChainDims {
   int32_t do_decay;          // sd *= sd_decay inside learn! (SNN_SD_DECAY_ON_LEARN)
   int32_t g_arr_log2, g_ltp_log2, pass_stages;
   int32_t thrN, thrP, thrL;  // threads per block of the neuron / ltp / learn role (synapse: 256)
+  int32_t la, ring;          // push lookahead (1..kMaxLook) and Iacc ring depth (la + 1)
+  int32_t o_lo, o_hi, o_nd, o_need;  // offsets of the push schedule inside `sched`, see Engine::launch_chain
 };
 // sched[0..n+1]: learn steps among steps < k ; sched[n+2 ..]: the learn steps themselves
 __device__ __forceinline__ int sched_before(const int32_t* __restrict__ sched, int k) { return sched[k]; }
@@ -1631,7 +1649,7 @@ __device__ __forceinline__ bool chain_wait(ChainCtl* c, int which, uint32_t targ
 // all threads of the block have finished their part (call after __syncthreads, from one thread)
 __device__ __forceinline__ void chain_arrive(ChainCtl* c, int which) {
   __threadfence();
-  atomicAdd(&c->w[which * 32], 1u);
+  red_add(&c->w[which * 32], 1u);
 }
 
 __device__ __forceinline__ Vec4<float> ld4cg(const float* p) {
@@ -1666,7 +1684,7 @@ __device__ __forceinline__ void chain_push_delay1(const DevNet<T>& p, const WVie
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4)
       if (pj[q4] >= 0)
-        atomicAdd(&I_now[pj[q4]], w_resolve<T>(p, pw[q4], fly[q4], p.plastic_ei || ((uint32_t)pj[q4] - ibase) < Ne, inst, (T)0));
+        red_add(&I_now[pj[q4]], w_resolve<T>(p, pw[q4], fly[q4], p.plastic_ei || ((uint32_t)pj[q4] - ibase) < Ne, inst, (T)0));
   }
 }
 
@@ -1684,7 +1702,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
   extern __shared__ __align__(16) unsigned char nsm_raw[];
   __shared__ int s_ok;
   __shared__ int s_nspk[2], s_base;
-  __shared__ uint32_t s_ps0[kSpkWave], s_poff[kSpkWave + 1];  // spikers of this block in step k: s_nspk[k & 1] (the other one is being cleared)
+  __shared__ uint32_t s_ps0[kSpkWave], s_pb1[kSpkWave], s_pb2[kSpkWave], s_poff[kSpkWave + 1];  // spikers of this block in step k: s_nspk[k & 1] (the other one is being cleared)
   T* const sv = reinterpret_cast<T*>(nsm_raw);
   T* const su = sv + (size_t)4 * d.qpb;
   T* const sn = su + (size_t)4 * d.qpb;
@@ -1713,7 +1731,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
     tl_begin(p.tl, 6, k);
     if (tid == 0) {
       bool ok = chain_wait(ctl, kcNeuron, d.NB * (uint32_t)k, 0);
-      if (ok && k >= 1) ok = chain_wait(ctl, kcPush, d.SB * (uint32_t)k, 0);
+      if (ok && k >= 1) ok = chain_wait(ctl, kcPush, d.SB * (uint32_t)sched[d.o_need + k], 0);
       if (ok && k >= 1 && sched_learn(sched, k - 1)) ok = chain_wait(ctl, kcBegun, (uint32_t)sched_before(sched, k), 0);
       if (ok && k > kLag) ok = chain_wait(ctl, kcLtp, d.PB * (uint32_t)(k - kLag), 0);
       if (ok && k >= 1 && d.RB) ok = chain_wait(ctl, kcRemote, d.RB * (uint32_t)k, 0);  // the peers' spikes of step k-1 pushed / listed
@@ -1729,8 +1747,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
     const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
     uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
     int32_t* __restrict__ list = p.spk_list + (size_t)slot * p.Nld;
-    T* __restrict__ I_prev = p.Iacc + (size_t)((t - 1) & 1) * p.Nld;  // consumed by Euler(t-1)
-    T* __restrict__ I_now = p.Iacc + (size_t)(t & 1) * p.Nld;         // receives the pushes of step t
+    T* __restrict__ I_prev = p.Iacc + (size_t)((t + d.ring - 1) % d.ring) * p.Nld;  // consumed by Euler(t-1)
     const T* __restrict__ noise_prev = (euler && cx->noise) ? cx->noise + (size_t)(k - 1) * p.N : nullptr;
     int32_t rec_base = 0;
     const int n_prev = (k > 0 && (rec_ids || bid == 0)) ? __ldcg(p.spk_cnt + prev) : 0;
@@ -1882,17 +1899,20 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
     tl_end(p.tl, 8, k); tl_begin(p.tl, 9, k);
     // ---- phase 3: this block's spikers, all in flight together (a chain of dependent memory round trips per
     // spiker: done as a small wave — one thread per spiker fetches the bounds of its delay-1 segment, then one thread
-    // per SYNAPSE pushes it into Iacc[t&1]: it feeds the Euler update of this very step, new_net.jl:116-121).
+    // per SYNAPSE pushes it: delay 1 feeds the Euler update of this very step (new_net.jl:116-121), delays up to the
+    // lookahead the following ones).
     // Thread 0 reserves the block's stretch of the global spike list meanwhile.
     if (detect) {
       const int nspk = s_nspk[k & 1];
+      const int nd = sched[d.o_nd + k];  // delays 1..nd of this step's spikers are pushed here (the rest by the synapse role)
       if (nspk > 0) {
         if (tid == 0) s_base = atomicAdd(&p.spk_cnt[slot], nspk);
         for (int r0 = 0; r0 < nspk; r0 += kSpkWave) {
           const int nr = min(kSpkWave, nspk - r0);
           for (int x = (int)tid; x < nr; x += (int)TN) {
-            const uint2 sg = p.seg01[(qb0 << 2) + s_spk[r0 + x]];
-            s_ps0[x] = sg.x; s_poff[x + 1] = sg.y - sg.x;
+            const uint4 sg = p.segL[(qb0 << 2) + s_spk[r0 + x]];
+            s_ps0[x] = sg.x; s_pb1[x] = sg.y; s_pb2[x] = sg.z;
+            s_poff[x + 1] = (nd == 1 ? sg.y : (nd == 2 ? sg.z : sg.w)) - sg.x;
           }
           __syncthreads();
           if (tid < 32) {
@@ -1916,16 +1936,17 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
           __syncthreads();
           const uint32_t V = s_poff[nr];
           for (uint32_t v0 = tid; v0 < V; v0 += 4 * TN) {
-            int32_t pj[4]; typename DevNet<T>::T2 pw[4]; bool fly[4]; uint32_t pi[4];
+            int32_t pj[4]; typename DevNet<T>::T2 pw[4]; bool fly[4]; uint32_t pi[4], pd[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const uint32_t v = v0 + u * TN;
-              pj[u] = -1; fly[u] = false; pi[u] = 0;
+              pj[u] = -1; fly[u] = false; pi[u] = 0; pd[u] = 0;
               if (v >= V) continue;
               uint32_t a = 0, b = (uint32_t)nr;
               while (b - a > 1) { const uint32_t m = (a + b) >> 1; if (s_poff[m] <= v) a = m; else b = m; }
               const uint32_t e = s_ps0[a] + (v - s_poff[a]);
               pi[u] = (qb0 << 2) + s_spk[r0 + a];
+              pd[u] = (e >= s_pb1[a] ? 1u : 0u) + (e >= s_pb2[a] ? 1u : 0u);  // delay - 1 = steps until it arrives
               const uint32_t ib = p.B == 1 ? 0u : (pi[u] / Nper) * Nper;
               pj[u] = p.post[e];
               pw[u] = w_fetch<T>(vw, e, (pi[u] - ib) < Ne, fly[u]);
@@ -1934,7 +1955,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
             for (int u = 0; u < 4; ++u) {
               if (pj[u] < 0) continue;
               const uint32_t inst = p.B == 1 ? 0u : pi[u] / Nper;
-              atomicAdd(&I_now[pj[u]],
+              red_add(p.Iacc + (size_t)((t + pd[u]) % d.ring) * p.Nld + pj[u],
                         w_resolve<T>(p, pw[u], fly[u], p.plastic_ei || ((uint32_t)pj[u] - inst * Nper) < Ne, inst, (T)0));
             }
           }
@@ -1989,24 +2010,30 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
 //            thread in flight: post id + weight, then the post neuron's spike history, then the reduction.
 // A step costs each block ~4 dependent round trips in total.
 // ---------------------------------------------------------------------------------------------
-constexpr int kWaveItems = 512;
+constexpr int kWaveItems = 256;
 struct WaveSmem {
   int cum[kMaxDelay + 2];
   int slots[kMaxDelay + 1];
   uint32_t s0[kWaveItems], n1[kWaveItems], src[kWaveItems];
+  uint32_t pb[kWaveItems][kMaxLook + 1];  // synapse wave: bounds of the delay segments an item pushes
   uint32_t off[kWaveItems + 1];
   unsigned long long blk_ev;
 };
 
-template <typename T, bool LTD, bool PUSHNEXT>
-__device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k,
-                                             const uint32_t bid, const uint32_t nblk, WaveSmem& sm) {
+// r_lo..r_hi: the pushes of this call are the arrivals of steps k+r_lo .. k+r_hi (none if r_hi < r_lo), i.e. for an
+// item of age a the delay segments a+r_lo+1 .. a+r_hi+1, each into the ring buffer of its arrival step.
+template <typename T, bool LTD>
+__device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k, const int r_lo,
+                                             const int r_hi, const int ring, const uint32_t bid, const uint32_t nblk,
+                                             WaveSmem& sm) {
   typedef Ops<T> O;
   tl_begin(p.tl, LTD ? 1 : 5, k);
   const uint32_t tid = threadIdx.x, TB = blockDim.x, lane = tid & 31u;
   const int64_t t = cx->t0 + k;
   const int32_t t32 = (int32_t)t;
   const int slot = (int)(((int64_t)cx->slot0 + k + p.R) % p.R);  // k may be -1 (window-start push)
+  const bool push = r_hi >= r_lo;
+  const int nseg = push ? r_hi - r_lo + 1 : 0;                   // <= kMaxLook
   if (tid < (uint32_t)p.Dmax) {
     const int sl = wrap_slot(slot - (int)tid, p.R);
     sm.slots[tid] = sl;
@@ -2025,30 +2052,33 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
   const uint32_t lo = min(total, bid * per), hi = min(total, lo + per);
   const uint32_t Nper = (uint32_t)p.Nper, Ne = (uint32_t)p.Ne;
   const size_t Nld = (size_t)p.Nld;
-  T* __restrict__ I_next = p.Iacc + (size_t)((t + 1) & 1) * Nld;
   const WView<T> vw = wview(p);
   unsigned long long n_ev = 0;
   for (uint32_t r0 = lo; r0 < hi; r0 += kWaveItems) {
     const uint32_t nitem = min((uint32_t)kWaveItems, hi - r0);
     if (LTD) tl_begin(p.tl, 11, k);
-    // ---- stage A: item -> (first synapse, LTD length, total length, spiker)
+    // ---- stage A: item -> (LTD segment, push segments, spiker)
     for (uint32_t x = tid; x < nitem; x += TB) {
       const uint32_t item = r0 + x;
       int a = 0;
       while (a + 1 < p.Dmax && sm.cum[a + 1] <= (int)item) ++a;
       const uint32_t i = (uint32_t)__ldcg(p.spk_list + (size_t)sm.slots[a] * Nld + (item - sm.cum[a]));
-      const uint32_t* __restrict__ sg = p.seg + (size_t)i * (p.Dmax + 1) + a;
-      const uint32_t g0 = sg[0], g1 = sg[1];
-      const uint32_t g2 = (PUSHNEXT && a + 1 < p.Dmax) ? sg[2] : g1;
+      const uint32_t* __restrict__ sg = p.seg + (size_t)i * (p.Dmax + 1);
+      const uint32_t g0 = sg[a], g1 = sg[a + 1];
+      uint32_t pbv[kMaxLook + 1];
+#pragma unroll
+      for (int q = 0; q <= kMaxLook; ++q) pbv[q] = (push && q <= nseg) ? sg[min(a + r_lo + q, p.Dmax)] : g1;
       const uint32_t ibase = p.B == 1 ? 0u : (i / Nper) * Nper;
       const bool ltd_row = LTD && (i - ibase) < Ne;  // only excitatory rows are plastic: the others have no LTD visits
       if (LTD) n_ev += (g1 - g0);
       const uint32_t b0 = ltd_row ? g0 : g1;
       sm.s0[x] = b0; sm.n1[x] = g1 - b0; sm.src[x] = i;
-      sm.off[x + 1] = g2 - b0;  // length; scanned below
+#pragma unroll
+      for (int q = 0; q <= kMaxLook; ++q) sm.pb[x][q] = pbv[q];
+      sm.off[x + 1] = (g1 - b0) + (pbv[nseg] - pbv[0]);  // length; scanned below
     }
     __syncthreads();
-    if (tid < 32) {  // inclusive scan of off[1..nitem] by one warp, 16 consecutive items per lane
+    if (tid < 32) {  // inclusive scan of off[1..nitem] by one warp, consecutive items per lane
       constexpr int PER = kWaveItems / 32;
       const uint32_t b = lane * PER;
       uint32_t acc = 0;
@@ -2071,17 +2101,24 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
     if (LTD) { tl_end(p.tl, 11, k); tl_begin(p.tl, 12, k); }
     // ---- stage B: one thread per synapse visit, two in flight
     for (uint32_t v0 = tid; v0 < V; v0 += 2 * TB) {
-      uint32_t e[2], j[2], inst[2], ibs[2]; bool ok[2], isl[2], pl[2], fly[2]; typename DevNet<T>::T2 ws[2]; int2 hq[2];
+      uint32_t e[2], j[2], inst[2], ibs[2], ahead[2]; bool ok[2], isl[2], pl[2], fly[2]; typename DevNet<T>::T2 ws[2]; int2 hq[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const uint32_t v = v0 + u * TB;
-        ok[u] = v < V; isl[u] = false; pl[u] = false; fly[u] = false; e[u] = 0; j[u] = 0; inst[u] = 0; ibs[u] = 0;
+        ok[u] = v < V; isl[u] = false; pl[u] = false; fly[u] = false; e[u] = 0; j[u] = 0; inst[u] = 0; ibs[u] = 0; ahead[u] = 0;
         if (!ok[u]) continue;
         uint32_t a = 0, b = nitem;  // off[a] <= v < off[b]
         while (b - a > 1) { const uint32_t m = (a + b) >> 1; if (sm.off[m] <= v) a = m; else b = m; }
-        const uint32_t rel = v - sm.off[a];
-        e[u] = sm.s0[a] + rel;
-        isl[u] = rel < sm.n1[a];             // inside the segment that arrives now (LTD), else a push for the next step
+        const uint32_t rel = v - sm.off[a], n1 = sm.n1[a];
+        isl[u] = rel < n1;                   // inside the segment that arrives now (LTD), else a push for a later step
+        if (isl[u]) e[u] = sm.s0[a] + rel;
+        else {
+          e[u] = sm.pb[a][0] + (rel - n1);
+          uint32_t seg_i = 0;
+#pragma unroll
+          for (int q = 1; q < kMaxLook; ++q) seg_i += (q < nseg && e[u] >= sm.pb[a][q]) ? 1u : 0u;
+          ahead[u] = (uint32_t)r_lo + seg_i;  // arrives at step k + ahead
+        }
         const uint32_t i = sm.src[a];
         inst[u] = p.B == 1 ? 0u : i / Nper; ibs[u] = inst[u] * Nper;
         j[u] = (uint32_t)p.post[e[u]];
@@ -2097,8 +2134,9 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
         if (!ok[u]) continue;
         if (pl[u])             // arrives now: sd -= apre * trace_post(t)   (new_net.jl:127)
           sd_add<T>(p, vw, e[u], -O::mul(p.apre, trace_resolve<T>(p, hq[u], j[u], t32, t32)), bid, inst[u]);
-        else if (!isl[u])      // arrives at k+1: I += w   (new_net.jl:116-118)
-          atomicAdd(&I_next[j[u]], w_resolve<T>(p, ws[u], fly[u], p.plastic_ei || (j[u] - ibs[u]) < Ne, inst[u], (T)0));
+        else if (!isl[u])      // arrives later: I += w into the buffer of its arrival step   (new_net.jl:116-118)
+          red_add(p.Iacc + (size_t)((t + ahead[u]) % ring) * Nld + j[u],
+                    w_resolve<T>(p, ws[u], fly[u], p.plastic_ei || (j[u] - ibs[u]) < Ne, inst[u], (T)0));
       }
     }
     __syncthreads();
@@ -2111,6 +2149,14 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
     if (tid == 0 && sm.blk_ev) p.blk_ev[bid] += sm.blk_ev;
   }
   tl_end(p.tl, LTD ? 1 : 5, k);
+}
+
+// the waves as kernels of their own (captured-graph scheduler): one launch per step, as many blocks as the step has work for
+template <typename T, bool LTD>
+__global__ void __launch_bounds__(256)
+synapse_wave_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int r_lo, int r_hi) {
+  __shared__ WaveSmem wsm;
+  synapse_wave<T, LTD>(p, cx, k, r_lo, r_hi, 2, blockIdx.x, gridDim.x, wsm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2136,24 +2182,29 @@ chain_synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl*
     __syncthreads();
     if (threadIdx.x == 0) chain_arrive(ctl, which);
   };
-  synapse_wave<T, false, true>(p, cx, -1, bid, d.SB, wsm);
+  // push schedule (Engine::launch_chain): at step k the arrivals of steps lo[k]..hi[k] are pushed — one step of
+  // lookahead further than a step ago, everything up to the lookahead right after a learn step has begun
+  const int32_t* __restrict__ plo = sched + d.o_lo + 1;  // indexed by k = -1 .. n-1
+  const int32_t* __restrict__ phi = sched + d.o_hi + 1;
+  synapse_wave<T, false>(p, cx, -1, plo[-1] + 1, phi[-1] + 1, d.ring, bid, d.SB, wsm);  // spikes of earlier windows
   arrive(kcPush);
   for (int k = 0; k < n; ++k) {
     if (!wait1(kcNeuron, d.NB * (uint32_t)(k + 1))) return;
     if (d.RB && !wait1(kcRemote, d.RB * (uint32_t)(k + 1))) return;  // partitioned: the step's spike list is complete
-    const bool learn = sched_learn(sched, k), push_next = k + 1 < n;
-    if (push_next && !learn) {
-      synapse_wave<T, true, true>(p, cx, k, bid, d.SB, wsm);
+    const bool learn = sched_learn(sched, k);
+    const int r_lo = plo[k] - k, r_hi = phi[k] - k;
+    if (!learn) {
+      synapse_wave<T, true>(p, cx, k, r_lo, r_hi, d.ring, bid, d.SB, wsm);
       arrive(kcLtd);
-      if (threadIdx.x == 0) atomicAdd(&ctl->w[kcPush * 32], 1u);  // ordered after the fence of the arrive above
+      if (threadIdx.x == 0) red_add(&ctl->w[kcPush * 32], 1u);  // ordered after the fence of the arrive above
     } else {
-      synapse_wave<T, true, false>(p, cx, k, bid, d.SB, wsm);
+      synapse_wave<T, true>(p, cx, k, 1, 0, d.ring, bid, d.SB, wsm);  // LTD only: the pushes must see learn!(k)
       arrive(kcLtd);
-      if (push_next) {
+      if (r_hi >= r_lo) {
         if (!wait1(kcBegun, (uint32_t)sched_before(sched, k) + 1u)) return;
-        synapse_wave<T, false, true>(p, cx, k, bid, d.SB, wsm);
-        arrive(kcPush);
+        synapse_wave<T, false>(p, cx, k, r_lo, r_hi, d.ring, bid, d.SB, wsm);
       }
+      arrive(kcPush);
     }
   }
 }
@@ -2239,6 +2290,13 @@ __device__ __forceinline__ void ltp_wave(const DevNet<T>& p, const WindowCtx<T>*
 }
 
 template <typename T>
+__global__ void __launch_bounds__(256)
+ltp_wave_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
+  __shared__ WaveSmem wsm;
+  ltp_wave<T>(p, cx, k, blockIdx.x, gridDim.x, wsm);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256, 6)
 chain_ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl, const ChainDims d) {
   __shared__ int s_ok;
@@ -2261,14 +2319,15 @@ chain_ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __r
 // waits for the peers' (word, step) pairs themselves.
 template <typename T>
 __global__ void __launch_bounds__(256)
-chain_remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl, const ChainDims d) {
+chain_remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl,
+                    const int32_t* __restrict__ sched, const ChainDims d) {
   __shared__ int s_ok;
   const int n = cx->n_steps;
   for (int k = 0; k < n; ++k) {
     if (threadIdx.x == 0) s_ok = chain_wait(ctl, kcNeuron, d.NB * (uint32_t)k, 0) ? 1 : 0;
     __syncthreads();
     if (!s_ok) return;
-    remote_body<T>(p, cx, k, 1, blockIdx.x, d.RB);
+    remote_body<T>(p, cx, k, 1, blockIdx.x, d.RB, sched[d.o_nd + k], d.ring);
     __syncthreads();
     if (threadIdx.x == 0) chain_arrive(ctl, kcRemote);
   }
@@ -2285,7 +2344,7 @@ __device__ __forceinline__ void chain_replay(const DevNet<T>& p, const uint32_t 
     for (uint32_t q = threadIdx.x; q < nn; q += blockDim.x) {
       LogEntry<T> le;
       le.e = __ldcg(&lg[q].e); le.d = __ldcg(&lg[q].d);
-      atomicAdd(&w[le.e].y, le.d);
+      red_add(&w[le.e].y, le.d);
     }
     __syncthreads();
     if (threadIdx.x == 0 && cnt) p.log_cnt[(size_t)r * kLogStride] = 0u;
@@ -2294,7 +2353,7 @@ __device__ __forceinline__ void chain_replay(const DevNet<T>& p, const uint32_t 
     const int64_t tid = bid * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)nblk * blockDim.x;
     for (int64_t e = tid; e < p.E; e += nth) {
       const T dv = __ldcg(p.dsd + e);
-      if (dv != (T)0) { atomicAdd(&w[e].y, dv); p.dsd[e] = (T)0; }
+      if (dv != (T)0) { red_add(&w[e].y, dv); p.dsd[e] = (T)0; }
     }
   }
 }
@@ -2422,9 +2481,11 @@ __global__ void to_double_kernel(const T* __restrict__ in, double* __restrict__ 
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
     out[j] = scale == 1.0 ? (double)in[j] : (double)(Ops<T>::mul(in[j], (T)scale));
 }
-static __global__ void seg01_kernel(const uint32_t* __restrict__ seg, int64_t N, int stride, uint2* __restrict__ out) {
+static __global__ void segL_kernel(const uint32_t* __restrict__ seg, int64_t N, int Dmax, uint4* __restrict__ out) {
+  const int stride = Dmax + 1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = make_uint2(seg[i * stride], seg[i * stride + 1]);
+    out[i] = make_uint4(seg[i * stride], seg[i * stride + 1], seg[i * stride + (Dmax < 2 ? Dmax : 2)],
+                        seg[i * stride + (Dmax < 3 ? Dmax : 3)]);
 }
 // caller order <-> internal order through perm; comp 0 = w, 1 = sd
 template <typename T>
@@ -2464,7 +2525,8 @@ __global__ void probe_kernel(DevNet<T> p, const uint32_t* __restrict__ pos, int 
 // Set by name through snn_set_param (the names are the quoted strings of Engine::set_param).
 struct Options {
   int graph = 1;             // captured window graph / persistent chain (1) or plain stream-ordered launches (0)
-  int persistent = 1;        // persistent chain (1) or the captured graph (0) for production-mode windows
+  int persistent = 0;        // production-mode windows: the captured graph of per-step kernels (0, default) or the
+                             // persistent chain of four resident role kernels (1); DESIGN.md section 5 has the measurements
   int learn_async = 0;       // 0 auto, 1 learn! always in place, 2 always the asynchronous double-buffered pass
   int64_t learn_log_cap = 0; // asynchronous pass: total entries of the sd-update log (0 = by size)
   int pass_blocks = 0, pass_tile_k = 0, pass_stages = 0;  // asynchronous pass of the graph path: blocks per SM, tile (K synapses), TMA stages
@@ -2473,6 +2535,8 @@ struct Options {
   int learn_lazy = 0;        // EXPERIMENTAL event-driven learning: dense re-basing every M learn steps (0 = the reference's rule)
   double learn_lazy_da = 0;  //   ... and at every learn step while da exceeds this (0 = never)
   int chain[7] = {0, 0, 0, 0, 0, 0, 0};  // persistent chain footprints, see Engine::chain_plan
+  int chain_look = 0;        // persistent chain: steps of push lookahead (0 = default 2; 1..3)
+  int waves = 1;             // captured graph: load-balanced wave kernels for LTD / pushes / LTP (0: group-per-item kernels)
 };
 
 // grow-only device buffer
@@ -2527,7 +2591,7 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMalloc(&p.v, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.u, N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.ho, N * sizeof(T)));
-    SNN_CUDA_OK(cudaMalloc(&p.Iacc, 2 * N * sizeof(T)));
+    SNN_CUDA_OK(cudaMalloc(&p.Iacc, kIaccRing * N * sizeof(T)));
     SNN_CUDA_OK(cudaMalloc(&p.hist, N * sizeof(int2)));
     SNN_CUDA_OK(cudaMalloc(&p.old_last, N * sizeof(int32_t)));
     SNN_CUDA_OK(cudaMalloc(&p.bits, (size_t)p.R * p.W * sizeof(uint32_t)));
@@ -2555,7 +2619,7 @@ class Engine : public IEngine {
     SNN_CUDA_OK(cudaMallocHost(&h_ctx_, sizeof(WindowCtx<T>)));
     SNN_CUDA_OK(cudaMallocHost(&h_blk_, 2 * kMaxSynBlocks * sizeof(unsigned long long)));
     SNN_CUDA_OK(cudaMemsetAsync(p.ho, 0, N * sizeof(T), stream_));
-    SNN_CUDA_OK(cudaMemsetAsync(p.Iacc, 0, 2 * N * sizeof(T), stream_));
+    SNN_CUDA_OK(cudaMemsetAsync(p.Iacc, 0, kIaccRing * N * sizeof(T), stream_));
     fill_kernel<int32_t><<<grid_for(2 * (int64_t)N), 256, 0, stream_>>>(reinterpret_cast<int32_t*>(p.hist), 2 * (int64_t)N, kNever);
     fill_kernel<int32_t><<<grid_for((int64_t)N), 256, 0, stream_>>>(p.old_last, (int64_t)N, kNever);
     SNN_CUDA_OK(cudaMemsetAsync(p.bits, 0, (size_t)p.R * p.W * sizeof(uint32_t), stream_));
@@ -2573,6 +2637,7 @@ class Engine : public IEngine {
     p.static_cur = -1;
     { const int rc = apply_options(err); if (rc) return rc; }
     { const int rc = build_tseq(err); if (rc) return rc; }
+    (void)chain_kernel_info();  // now, while none of the chain's kernels can be running in this process
     init_state_kernel<T><<<grid_for(p.Nld), 256, 0, stream_>>>(p);
     SNN_CUDA_OK(cudaGetLastError());
     SNN_CUDA_OK(cudaStreamSynchronize(stream_));
@@ -2624,7 +2689,7 @@ class Engine : public IEngine {
         {"chain_neuron_threads", &opt_.chain[0], false}, {"chain_synapse_blocks", &opt_.chain[1], false},
         {"chain_ltp_blocks", &opt_.chain[2], false}, {"chain_ltp_threads", &opt_.chain[3], false},
         {"chain_learn_blocks", &opt_.chain[4], false}, {"chain_learn_threads", &opt_.chain[5], false},
-        {"chain_learn_stages", &opt_.chain[6], false}};
+        {"chain_learn_stages", &opt_.chain[6], false}, {"chain_lookahead", &opt_.chain_look, false}, {"wave_kernels", &opt_.waves, false}};
     for (const E& e : ints) if (n == e.name) { *pi = e.i; *structural = e.st; return 1; }
     if (n == "learn_log_cap") { *pl = &opt_.learn_log_cap; *structural = true; return 1; }
     if (n == "learn_lazy_da") { *pd = &opt_.learn_lazy_da; *structural = true; return 1; }
@@ -2703,10 +2768,10 @@ class Engine : public IEngine {
     p.in_syn = topo_.in_syn; p.in_pre = topo_.in_pre;
     free_synapse_state();
     {
-      uint2* s01 = nullptr;
-      SNN_CUDA_OK(cudaMalloc(&s01, (size_t)std::max<int64_t>(1, p.N) * sizeof(uint2)));
-      seg01_kernel<<<grid_for(p.N), 256, 0, stream_>>>(p.seg, p.N, p.Dmax + 1, s01);
-      p.seg01 = s01;
+      uint4* sl = nullptr;
+      SNN_CUDA_OK(cudaMalloc(&sl, (size_t)std::max<int64_t>(1, p.N) * sizeof(uint4)));
+      segL_kernel<<<grid_for(p.N), 256, 0, stream_>>>(p.seg, p.N, p.Dmax, sl);
+      p.segL = sl;
     }
     const int64_t Ea = p.E > 0 ? p.E : 1;
     typedef typename DevNet<T>::T2 T2;
@@ -3116,7 +3181,7 @@ class Engine : public IEngine {
     std::vector<cudaEvent_t> prof_events;  // event record nodes are baked into the graph
   };
   void drop_graph() {
-    chain_state_ = 0;  // topology / partition / stream changed: size the persistent chain again
+    chain_state_[0] = chain_state_[1] = 0;  // topology / partition / stream changed: size the persistent chain again
     for (auto& g : graphs_) {
       if (g.exec) cudaGraphExecDestroy(g.exec);
       for (auto& e : g.prof_events) cudaEventDestroy(e);
@@ -3127,7 +3192,7 @@ class Engine : public IEngine {
     DevNet<T>& p = p_;
     if (p.wsdX[1] != p.wsdX[0]) cudaFree(p.wsdX[1]);
     cudaFree(p.wsdX[0]); cudaFree(p.dlog); cudaFree(p.dsd); cudaFree(p.log_cnt); cudaFree(p.tile_done);
-    cudaFree(p.cacc); cudaFree(p.lzH); cudaFree(p.lzK); cudaFree(const_cast<uint2*>(p.seg01)); p.seg01 = nullptr;
+    cudaFree(p.cacc); cudaFree(p.lzH); cudaFree(p.lzK); cudaFree(const_cast<uint4*>(p.segL)); p.segL = nullptr;
     cudaFree(const_cast<uint32_t*>(p.inst_lo));
     p.wsd = p.wsdX[0] = p.wsdX[1] = nullptr; p.dlog = nullptr; p.dsd = nullptr; p.log_cnt = nullptr;
     p.cacc = nullptr; p.lzH = p.lzR = p.lzInv = nullptr; p.lzK = nullptr; p.lazy = 0;
@@ -3256,7 +3321,42 @@ class Engine : public IEngine {
   int launch_graph(const StepArgs& a, bool prof, std::string& err);
   bool async_ok(const StepArgs& a) const;
   void launch_pass(cudaStream_t s4, int k, int do_decay, bool prof);
-  bool chain_plan(std::string* why);
+  // Attributes of the chain's kernels, read and set ONCE per process and precision, before any of them runs: querying
+  // or changing a function's attributes loads it / may wait for the device, and a handle that does so while another
+  // handle's resident kernels are waiting for it (several ranks in one process) would deadlock the exchange.
+  struct ChainKernelInfo { bool ok = false; cudaFuncAttributes fa[6]; };
+  static const ChainKernelInfo& chain_kernel_info() {
+    static const ChainKernelInfo info = [] {
+      ChainKernelInfo k;
+      int dev = 0, optin = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      bool ok = cudaFuncGetAttributes(&k.fa[0], chain_neuron_kernel<T, 2>) == cudaSuccess &&
+                cudaFuncGetAttributes(&k.fa[1], chain_neuron_kernel<T, 3>) == cudaSuccess &&
+                cudaFuncGetAttributes(&k.fa[2], chain_synapse_kernel<T>) == cudaSuccess &&
+                cudaFuncGetAttributes(&k.fa[3], chain_ltp_kernel<T>) == cudaSuccess &&
+                cudaFuncGetAttributes(&k.fa[4], chain_learn_kernel<T>) == cudaSuccess &&
+                cudaFuncGetAttributes(&k.fa[5], chain_remote_kernel<T>) == cudaSuccess;
+      // An SM's L1 / shared-memory split cannot change while a block is resident on it: if the first role to arrive
+      // configured it for its own (smaller) need, the blocks of a role that needs more would wait for the SM to
+      // drain — forever, since the resident role waits for them.  Every role asks for the maximum split.
+      const int co = cudaSharedmemCarveoutMaxShared;
+      ok = ok && cudaFuncSetAttribute(chain_neuron_kernel<T, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, co) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(chain_neuron_kernel<T, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, co) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(chain_synapse_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, co) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(chain_ltp_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, co) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(chain_learn_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, co) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(chain_remote_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, co) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(chain_neuron_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)k.fa[0].sharedSizeBytes) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(chain_neuron_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)k.fa[1].sharedSizeBytes) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(chain_learn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPassMaxStages * (int)kPassChunkBytes) == cudaSuccess;
+      if (!ok) cudaGetLastError();
+      k.ok = ok;
+      return k;
+    }();
+    return info;
+  }
+  bool chain_plan(bool with_learn, std::string* why);
   bool chain_ok(const StepArgs& a);
   int launch_chain(const StepArgs& a, std::string& err);
 
@@ -3295,7 +3395,9 @@ class Engine : public IEngine {
   ChainCtl* d_chain_ = nullptr; ChainCtl* h_chain_ = nullptr;
   DevBuf b_sched_;
   ChainDims chain_{};
-  int chain_state_ = 0;          // 0 = not planned yet, 1 = fits, -1 = does not fit (graph path)
+  int chain_state_[2] = {0, 0};  // per plan (without / with the learn role): 0 = not planned yet, 1 = fits, -1 = does not fit
+  ChainDims chain_plans_[2] = {};
+  size_t chain_smem_[2][2] = {};
   size_t chain_smem_neuron_ = 0, chain_smem_learn_ = 0;
   bool last_window_chain_ = false, last_window_graph_ = false;
   cudaEvent_t chain_ev_[4] = {};
@@ -3462,7 +3564,17 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
     cudaEventRecord(evFork, s0);                    // fork point
     cudaStreamWaitEvent(sN, evFork, 0);
     cudaStreamWaitEvent(s2, evFork, 0);
-    synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, -1, g_arr_log2_);  // pushes for step 0
+    // side kernels: the load-balanced waves (default) or the group-per-item kernels ("wave_kernels" = 0)
+    const bool wv = opt_.waves != 0 && !p.lazy;  // (the event-driven mode forms weights from three arrays: old kernels)
+    auto syn = [&](cudaStream_t st, int k, bool ltd, bool push) {
+      if (wv) {
+        if (ltd) synapse_wave_kernel<T, true><<<g.gA, 256, 0, st>>>(p, d_ctx_, k, 1, push ? 1 : 0);
+        else synapse_wave_kernel<T, false><<<g.gA, 256, 0, st>>>(p, d_ctx_, k, 1, 1);
+      } else if (ltd && push) synapse_kernel<T, true, true, true><<<g.gA, 256, 0, st>>>(p, d_ctx_, k, g_arr_log2_);
+      else if (ltd) synapse_kernel<T, true, false, true><<<g.gA, 256, 0, st>>>(p, d_ctx_, k, g_arr_log2_);
+      else synapse_kernel<T, false, true, true><<<g.gA, 256, 0, st>>>(p, d_ctx_, k, g_arr_log2_);
+    };
+    syn(s2, -1, false, true);  // pushes for step 0
     cudaEventRecord(evPush(0), s2);
     bool s3_used = false, pass_open = false;
     cudaEvent_t evNk[2] = {dep_ev_[0], dep_ev_[11]};
@@ -3499,15 +3611,16 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
       cudaStreamWaitEvent(s2, evNk[k & 1], 0);
       if (learn_prev && !async) cudaStreamWaitEvent(s2, evL, 0);  // sd reductions must not race the in-place pass
       if (push_next && !learn) {
-        synapse_kernel<T, true, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
+        syn(s2, k, true, true);
         cudaEventRecord(evPush(k + 1), s2);
       } else {
-        synapse_kernel<T, true, false, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
+        syn(s2, k, true, false);
       }
       cudaEventRecord(evS(k), s2);
       // s3: ltp(k) [-> in-place learn(k)]
       cudaStreamWaitEvent(s3, evNk[k & 1], 0);
-      ltp_kernel<T, true><<<g.gP, 256, 0, s3>>>(p, d_ctx_, k, g_ltp_log2_);
+      if (wv) ltp_wave_kernel<T><<<g.gP, 256, 0, s3>>>(p, d_ctx_, k);
+      else ltp_kernel<T, true><<<g.gP, 256, 0, s3>>>(p, d_ctx_, k, g_ltp_log2_);
       s3_used = true;
       cudaEventRecord(evP(k), s3);
       if (learn && async) {
@@ -3523,7 +3636,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
         pass_open = true;
         if (push_next) {
           cudaStreamWaitEvent(s2, evL, 0);
-          synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
+          syn(s2, k, false, true);
           cudaEventRecord(evPush(k + 1), s2);
         }
       } else if (learn) {
@@ -3535,7 +3648,7 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
         cudaEventRecord(evL, s3);
         if (push_next) {
           cudaStreamWaitEvent(s2, evL, 0);
-          synapse_kernel<T, false, true, true><<<g.gA, 256, 0, s2>>>(p, d_ctx_, k, g_arr_log2_);
+          syn(s2, k, false, true);
           cudaEventRecord(evPush(k + 1), s2);
         }
         cudaEventRecord(evP(k), s3);
@@ -3602,9 +3715,11 @@ int Engine<T>::launch_graph(const StepArgs& a, bool prof, std::string& err) {
 // attributes); if that cannot be had the window falls back to the captured graph.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-bool Engine<T>::chain_plan(std::string* why) {
-  if (chain_state_ != 0) return chain_state_ > 0;
-  chain_state_ = -1;
+bool Engine<T>::chain_plan(bool with_learn, std::string* why) {
+  // two plans: windows without a learn step do not launch the learn role and need not make room for it
+  const int pi = with_learn ? 1 : 0;
+  if (chain_state_[pi] != 0) { chain_ = chain_plans_[pi]; chain_smem_neuron_ = chain_smem_[pi][0]; chain_smem_learn_ = chain_smem_[pi][1]; return chain_state_[pi] > 0; }
+  chain_state_[pi] = -1;
   DevNet<T>& p = p_;
   auto fail = [&](const char* m) { if (why) *why = m; return false; };
   if (p.exact || !use_graph_ || !opt_.persistent || p.lazy) return fail("mode");
@@ -3629,21 +3744,17 @@ bool Engine<T>::chain_plan(std::string* why) {
   const int thrP = std::min(256, std::max(32, tune[3] / 32 * 32)), thrL = kChainLearnThreads;  // (tune[5] is not used any more)
   int S = std::min(kPassMaxStages, std::max(2, tune[6]));
   size_t smem_l = (size_t)S * kPassChunkBytes;
-  cudaFuncAttributes fa[5];
-  memset(fa, 0, sizeof(fa));
-  if (parted && cudaFuncGetAttributes(&fa[4], chain_remote_kernel<T>) != cudaSuccess) { cudaGetLastError(); return fail("kernel attributes"); }
   const bool lean = thrN > 256;  // the 40-register build of the neuron role
-  if (cudaFuncGetAttributes(&fa[0], lean ? chain_neuron_kernel<T, 3> : chain_neuron_kernel<T, 2>) != cudaSuccess ||  // (also loads the functions now: a
-      cudaFuncGetAttributes(&fa[1], chain_synapse_kernel<T>) != cudaSuccess ||     // lazy module load in the middle of a
-      cudaFuncGetAttributes(&fa[2], chain_ltp_kernel<T>) != cudaSuccess ||         // window would wait for the spinning
-      cudaFuncGetAttributes(&fa[3], chain_learn_kernel<T>) != cudaSuccess) {       // kernels that wait for it)
-    cudaGetLastError();
-    return fail("kernel attributes");
+  cudaFuncAttributes fa[5];
+  {
+    const ChainKernelInfo& ki = chain_kernel_info();
+    if (!ki.ok) return fail("kernel attributes");
+    fa[0] = ki.fa[lean ? 1 : 0]; fa[1] = ki.fa[2]; fa[2] = ki.fa[3]; fa[3] = ki.fa[4]; fa[4] = ki.fa[5];
   }
   if (smem_n + fa[0].sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) return fail("neuron state does not fit in shared memory");
   auto fits = [&](int sp, int lp, int le) {
     const int thr[5] = {thrN, 256, thrP, thrL, 256};
-    const int cnt[5] = {1, sp, lp, n_plastic_ > 0 && have_async_ ? le : 0, parted ? 1 : 0};
+    const int cnt[5] = {1, sp, lp, with_learn ? le : 0, parted ? 1 : 0};
     const size_t dyn[5] = {smem_n, 0, 0, smem_l, 0};
     size_t regs = 0, smem = 0; int threads = 0, blocks = 0;
     for (int r = 0; r < 5; ++r) {
@@ -3668,41 +3779,30 @@ bool Engine<T>::chain_plan(std::string* why) {
   if (parted) {
     const int64_t remote_words = p.W - local_quads / 8;
     d.RB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(n_sm_, (remote_words + 255) / 256));
-    cudaFuncSetAttribute(chain_remote_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
   d.g_arr_log2 = g_arr_log2_; d.g_ltp_log2 = g_ltp_log2_; d.pass_stages = S;
   d.thrN = thrN; d.thrP = thrP; d.thrL = thrL;
+  d.la = std::min(kMaxLook, std::max(1, opt_.chain_look > 0 ? opt_.chain_look : 2));
+  d.ring = d.la + 1;
   d.do_decay = cfg_.sd_decay_mode == SNN_SD_DECAY_ON_LEARN ? 1 : 0;
-  if (cudaFuncSetAttribute(lean ? chain_neuron_kernel<T, 3> : chain_neuron_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n) != cudaSuccess ||
-      cudaFuncSetAttribute(chain_learn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess) {
-    cudaGetLastError();
-    return fail("shared-memory attribute");
-  }
-  // An SM's L1 / shared-memory split cannot change while a block is resident on it: if the first role to arrive
-  // configured it for its own (smaller) need, the blocks of a role that needs more would wait for the SM to
-  // drain — forever, since the resident role waits for them.  Every role asks for the maximum split up front.
-  cudaFuncSetAttribute(lean ? chain_neuron_kernel<T, 3> : chain_neuron_kernel<T, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(chain_synapse_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(chain_ltp_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(chain_learn_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaGetLastError();
   chain_ = d; chain_smem_neuron_ = smem_n; chain_smem_learn_ = smem_l;
-  chain_state_ = 1;
+  chain_plans_[pi] = d; chain_smem_[pi][0] = smem_n; chain_smem_[pi][1] = smem_l;
+  chain_state_[pi] = 1;
   return true;
 }
 
 template <typename T>
 bool Engine<T>::chain_ok(const StepArgs& a) {
   if (a.n_force > 0 || a.n_cur > 0 || a.n_probes > 0 || profiling_ == 1) return false;
-  if (!chain_plan(nullptr)) return false;
   int dl, dd, last = -1000;
+  bool any = false;
   for (int k = 0; k < a.n_steps; ++k)
     if (wants_learn(a, k, &dl, &dd)) {
       if (!have_async_) return false;   // no second (w, sd) buffer: the in-place pass of the graph path
       if (k - last < 2 && opt_.learn_async != 2) return false;  // learn! at every step: nothing to run beside the pass
-      last = k;
+      last = k; any = true;
     }
-  return true;
+  return chain_plan(any, nullptr);
 }
 
 template <typename T>
@@ -3719,10 +3819,46 @@ int Engine<T>::launch_chain(const StepArgs& a, std::string& err) {
   }
   sched[n + 1] = sched[n];
   sched.insert(sched.end(), steps.begin(), steps.end());
+  // ---- push schedule.  A current that arrives at step m is pushed into Iacc[m % ring] as early as the lookahead
+  // LA allows, but never before a learn! that precedes its arrival has begun (the weight applies at arrival time):
+  //   neuron(s), not a learn step : the spikers' own delays 1..nd[s]   (arrivals s .. s+nd-1)
+  //   synapse(k), not a learn step: arrival k+LA                        (one step further than synapse(k-1) got)
+  //   synapse(k), learn step / k=-1: arrivals k+1 .. k+LA, after learn!(k) has begun
+  // each clipped to the window and to the next learn step.  need[m] = push phases neuron(m) has to see complete
+  // before Euler(m-1): with LA = 2 the cycle neuron(k) -> synapse(k) -> neuron(k+3) spans three steps instead of two.
+  ChainDims d = chain_;
+  const int LA = d.la;
+  std::vector<char> is_learn(n + 1, 0);
+  for (int k : steps) is_learn[k] = 1;
+  std::vector<int> next_learn(n + 2, n);  // smallest learn step > k, for k = -1 .. n-1 (index k+1)
+  {
+    int nxt = n;
+    for (int k = n - 1; k >= -1; --k) { next_learn[k + 1] = nxt; if (k >= 0 && is_learn[k]) nxt = k; }
+  }
+  std::vector<int32_t> s_lo(n + 1), s_hi(n + 1), s_nd(std::max(1, n)), s_need(n + 1, 1);
+  for (int k = -1; k < n; ++k) {
+    const int nl = next_learn[k + 1];
+    int lo, hi;
+    if (k == -1 || is_learn[k]) { lo = k + 1; hi = std::min(std::min(k + LA, n - 1), nl); }
+    else { lo = hi = k + LA; if (hi > n - 1 || nl < hi) hi = lo - 1; }
+    s_lo[k + 1] = lo; s_hi[k + 1] = hi;
+    for (int m = lo; m <= hi; ++m) s_need[m + 1] = std::max(s_need[m + 1], k + 2);  // phases complete after synapse(k)
+  }
+  for (int k = 0; k < n; ++k) {
+    int nd = 1;
+    if (!is_learn[k])
+      for (int dd2 = 2; dd2 <= LA; ++dd2) { const int m = k + dd2 - 1; if (m <= n - 1 && next_learn[k + 1] >= m) nd = dd2; }
+    s_nd[k] = nd;
+  }
+  // (pushes into a ring buffer must also come after the Euler update that cleared it: they happen at synapse step
+  // >= m - LA = (m - ring) + 1, which waits for neuron(m - ring + 1), the one that consumed arrival m - ring)
+  d.o_lo = (int32_t)sched.size(); sched.insert(sched.end(), s_lo.begin(), s_lo.end());
+  d.o_hi = (int32_t)sched.size(); sched.insert(sched.end(), s_hi.begin(), s_hi.end());
+  d.o_nd = (int32_t)sched.size(); sched.insert(sched.end(), s_nd.begin(), s_nd.end());
+  d.o_need = (int32_t)sched.size(); sched.insert(sched.end(), s_need.begin(), s_need.end());
   SNN_CUDA_OK(b_sched_.reserve(sched.size() * sizeof(int32_t)));
   SNN_CUDA_OK(cudaMemcpyAsync(b_sched_.ptr, sched.data(), sched.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
   SNN_CUDA_OK(cudaMemsetAsync(d_chain_, 0, sizeof(ChainCtl), stream_));
-  ChainDims d = chain_;
   d.n_learn = (int32_t)steps.size();
   cudaStream_t s0 = stream_, sN = chain_stream_, s2 = side_stream_, s3 = side2_stream_, s4 = learn_stream_;
   cudaEvent_t evFork = dep_ev_[9];
@@ -3738,7 +3874,7 @@ int Engine<T>::launch_chain(const StepArgs& a, std::string& err) {
   chain_ltp_kernel<T><<<d.PB, d.thrP, 0, s3>>>(p, d_ctx_, d_chain_, d);
   if (d.RB) {  // neuron-partitioned: the replay of the peers' detection (own stream: it spins on NVLink traffic)
     SNN_CUDA_OK(cudaStreamWaitEvent(own_side_stream(), evFork, 0));
-    chain_remote_kernel<T><<<d.RB, 256, 0, own_side_stream()>>>(p, d_ctx_, d_chain_, d);
+    chain_remote_kernel<T><<<d.RB, 256, 0, own_side_stream()>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
     SNN_CUDA_OK(cudaEventRecord(dep_ev_[0], own_side_stream()));
     SNN_CUDA_OK(cudaStreamWaitEvent(s0, dep_ev_[0], 0));
   }

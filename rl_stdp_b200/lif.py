@@ -158,11 +158,19 @@ class ActorPopulation:
         ma = np.ascontiguousarray(np.transpose(ma, (0, 2, 1)).reshape(self.n_agents, -1))  # column-major
         s0 = np.zeros((self.n_agents, 4), np.float64)
         s0[:, :nobs] = np.asarray(state0, np.float64).reshape(self.n_agents, nobs)
+        shared = False
         if tie_actions is None:
+            # the reference's default: every episode of every agent draws from a fresh MersenneTwister(0) — one
+            # stream, shared (uploaded once per call, not once per agent)
             from .julia_rng import julia_mt_pick_bits
             k = n_steps * (1 if env_id == L.SNN_ENV_CARTPOLE else 3)
-            tie_actions = np.tile(np.asarray(julia_mt_pick_bits(0, k), np.int32), (self.n_agents, 1))
-        ta = np.ascontiguousarray(np.asarray(tie_actions, np.int32).reshape(self.n_agents, -1))
+            key = (env_id, k)
+            if getattr(self, "_mt0_key", None) != key:
+                self._mt0_key, self._mt0 = key, np.ascontiguousarray(julia_mt_pick_bits(0, k), np.int32).reshape(1, -1)
+            tie_actions, shared = self._mt0, teach_actions is None
+            if not shared:
+                tie_actions = np.tile(tie_actions, (self.n_agents, 1))
+        ta = np.ascontiguousarray(np.asarray(tie_actions, np.int32).reshape(1 if shared else self.n_agents, -1))
         if ta.shape[1] < n_steps:
             raise ValueError("tie_actions needs at least n_steps entries per agent")
         te = None if teach_actions is None else np.ascontiguousarray(
@@ -174,14 +182,15 @@ class ActorPopulation:
         nr = np.zeros(self.n_agents, np.int32)
         so = np.zeros((self.n_agents, 4), np.float64)
         ms = C.c_double(0.0)
-        if env_id == L.SNN_ENV_CARTPOLE and (te is not None or ta.shape[1] == n_steps):
+        if env_id == L.SNN_ENV_CARTPOLE and not shared and (te is not None or ta.shape[1] == n_steps):
             L.check(L.load().snn_actor_episodes(self._h, _ptr(ma), _ptr(s0), _ptr(ta), _ptr(te), int(n_steps),
                                                 int(win_size), int(train), _ptr(rewards), _ptr(nd), _ptr(nr),
                                                 _ptr(so), C.byref(ms)))
         else:
             if te is not None:
                 raise ValueError("teach_actions: CartPole only")
-            L.check(L.load().snn_actor_episodes_env(self._h, env_id, _ptr(ma), _ptr(s0), _ptr(ta), int(ta.shape[1]),
+            L.check(L.load().snn_actor_episodes_env(self._h, env_id, _ptr(ma), _ptr(s0), _ptr(ta),
+                                                    -int(ta.shape[1]) if shared else int(ta.shape[1]),
                                                     int(n_steps), int(win_size), int(train), _ptr(rewards),
                                                     _ptr(nd), _ptr(nr), _ptr(so), C.byref(ms)))
         return dict(rewards=rewards, n_decisions=nd, n_rand=nr, state=so[:, :nobs], device_ms=ms.value)

@@ -59,14 +59,12 @@ class SparseNetwork:
         opts = {}
         if not bool(params.pop("graph", True)):
             opts["graph"] = 0          # plain stream-ordered launches instead of whole-window schedules
-        if not bool(params.pop("persistent", True)):
-            opts["persistent"] = 0     # the captured CUDA graph of per-step kernels instead of the persistent chain
+        if bool(params.pop("persistent", False)):
+            opts["persistent"] = 1     # the persistent chain of resident role kernels instead of the captured CUDA graph
         exp_flags = int(params.pop("exp_flags", 0))
         for bit, name in ((2, "timeline"), (4, "serialise_learn_pass"), (8, "neuron_blocks_256"), (512, "lsu_pass")):
             if exp_flags & bit:
                 opts[name] = 1
-        if exp_flags & 1024:
-            opts["persistent"] = 0
         opts["learn_async"] = {"auto": 0, "off": 1, "force": 2}[params.pop("learn_async", "auto")]
         opts["learn_log_cap"] = int(params.pop("learn_log_cap", 0))
         # opt-in, production mode only: event-driven learning, one dense re-basing pass
@@ -78,6 +76,9 @@ class SparseNetwork:
         opts["learn_pass_blocks"] = int(params.pop("learn_blocks", 0))
         side_blocks = int(params.pop("side_blocks", 0))  # 10*synapse + ltp blocks per SM of the graph path
         opts["synapse_blocks_per_sm"], opts["ltp_blocks_per_sm"] = side_blocks // 10, side_blocks % 10
+        opts["chain_lookahead"] = int(params.pop("chain_lookahead", 0))  # 0 = the library's default
+        if not bool(params.pop("wave_kernels", True)):
+            opts["wave_kernels"] = 0   # group-per-item side kernels of round 1 instead of the load-balanced waves
         chain = params.pop("chain", None)  # "nthr,syn,ltp,ltp_thr,learn,learn_thr,stages" (sweeps)
         if chain:
             names = ("chain_neuron_threads", "chain_synapse_blocks", "chain_ltp_blocks", "chain_ltp_threads",
@@ -97,7 +98,7 @@ class SparseNetwork:
         self._h = C.c_void_p()
         L.check(lib.snn_create(C.byref(cfg), C.byref(self._h)))
         for name, v in opts.items():
-            if v or name in ("graph", "persistent"):   # the two switches are only in `opts` when they are turned OFF
+            if v or name in ("graph", "wave_kernels"):   # these two are only in `opts` when they are turned OFF
                 self.set_param(name, v)
         rowptr = np.ascontiguousarray(rowptr, np.int64)
         post = np.ascontiguousarray(post, np.int32)

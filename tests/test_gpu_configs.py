@@ -47,7 +47,7 @@ def test_c3_clustered_10k_fp64_exact_and_fp32_gates():
     assert rel_err(net.get(L.FIELD_W), ora.get(4)) <= 1e-9
     assert rel_err(net.get(L.FIELD_SD)[plastic], ora.get(5)[plastic]) <= 1e-9
     assert np.abs(ora.get(4)[plastic] - 1.0).max() > 1e-3
-    fast = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f32", mode="fast", max_delay=1)
+    fast = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f32", mode="fast", max_delay=1, persistent=True)
     fs, _ = fast.run(t, noise, train, da_events=da)
     assert fast.get_param("window_path") == 2          # the persistent chain
     nr, ng = sum(len(r) for r in ref), sum(len(s) for s in fs)
@@ -107,7 +107,7 @@ def test_full_size_c5_frozen_equals_openmp_oracle():
         ids, offs, v_ref = z["ids"], z["offs"], z["v"]
     rowptr, post, w, delay = synth.fixed_fanout(n, ne, fan, dmax, seed=9)
     net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="fast", noise="philox", max_delay=dmax,
-                        noise_seed=10)
+                        noise_seed=10, persistent=True)
     got, st = net.run(t, None, None, spikes_cap=1 << 22)
     assert net.get_param("window_path") == 2
     assert offs[-1] > 20_000                      # the network is out of its silent start-up phase
@@ -131,7 +131,8 @@ def test_fp32_production_statistics_10s():
     train = np.array([(k + 1) % 10 == 0 for k in range(t)], np.uint8)
     da = [(k, 0, 0.5) for k in range(999, t, 1000)]
     ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax)
-    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f32", mode="fast", max_delay=dmax, learn_async="force")
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f32", mode="fast", max_delay=dmax, learn_async="force",
+                        persistent=True)
     ref, got = [], []
     for lo in range(0, t, W):          # the noise is drawn window by window: 10 s x 2000 neurons would be 160 MB at once
         noise = synth.thalamic_noise(W, n, seed=1000 + lo)

@@ -337,15 +337,17 @@ def test_fast_scheduler_bitexact_with_frozen_weights(graph):
     assert np.array_equal(net.get(L.FIELD_TRACE), ora.get(2))
 
 
-@pytest.mark.parametrize("log_cap,batched", [(0, False), (4000, False), (0, True)])
-def test_fast_async_learn_matches_oracle(log_cap, batched):
+@pytest.mark.parametrize("log_cap,batched,persistent", [(0, False, False), (4000, False, False), (0, True, False),
+                                                        (0, False, True), (4000, False, True), (0, True, True)])
+def test_fast_async_learn_matches_oracle(log_cap, batched, persistent):
     """The asynchronous learn pass (production mode): learn!(k) streams beside steps k+1.. — pushes
     of not-yet-processed synapses form clamp(w + g*sd) on the fly from the frozen buffer, their sd
     updates are logged and replayed.  With real learning (base rate + dopamine) the fp64 production
     build must still reproduce the oracle: identical spikes while rounding noise has not flipped a
     threshold test, weights and sd to 1e-9 afterwards (atomic sums differ in the last bit only).
     log_cap = 4000 leaves one or two entries per log region, so most logged updates take the dense
-    spill path."""
+    spill path.  persistent: the same pass as the learn role of the persistent chain (four resident kernels, steps
+    handed over by device counters, currents pushed two steps ahead) instead of the captured graph."""
     from oracle import py_oracle as po
     from rl_stdp_b200 import synth
     from rl_stdp_b200.network import SparseNetwork
@@ -367,12 +369,13 @@ def test_fast_async_learn_matches_oracle(log_cap, batched):
                                       [(s, 0, a) for s, i, a in da_events if i == b]))
         oras.append(o)
     net = SparseNetwork(nper, ne, rowptr, post, w, delay, n_instances=B, dtype="f64", mode="fast", max_delay=dmax,
-                        learn_async="force", learn_log_cap=log_cap)
+                        learn_async="force", learn_log_cap=log_cap, persistent=persistent)
     got = []
     for lo in range(0, t, 100):
         sp, st = net.run(100, noise[lo:lo + 100], train[lo:lo + 100],
                          da_events=[(s - lo, i, a) for s, i, a in da_events if lo <= s < lo + 100])
         assert st.learn_launches == 10
+        assert net.get_param("window_path") == (2 if persistent else 1)
         got += sp
     for k in range(t):
         want = np.concatenate([refs[b][k] + b * nper for b in range(B)])

@@ -25,7 +25,9 @@ def main():
     ap.add_argument("--learn-async", default="auto")
     ap.add_argument("--learn-lazy", type=int, default=0, help="experimental event-driven learning (DESIGN 11.1)")
     ap.add_argument("--chain", default=None)
-    ap.add_argument("--no-persistent", action="store_true")
+    ap.add_argument("--chain-lookahead", type=int, default=0)
+    ap.add_argument("--persistent", action="store_true")
+    ap.add_argument("--no-waves", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.json"))
     a = ap.parse_args()
     wl = bench.WORKLOADS[a.workload]
@@ -47,7 +49,7 @@ def main():
     else:
         net = SparseNetwork(n, ne, rowptr, post, w, delay, n_instances=n_inst, dtype="f32", mode="fast", noise="philox",
                         max_delay=dmax, noise_seed=10, exp_flags=2 | a.exp_flags, learn_blocks=a.learn_blocks,
-                            learn_async=a.learn_async, learn_lazy=a.learn_lazy, chain=a.chain, persistent=not a.no_persistent)
+                            learn_async=a.learn_async, learn_lazy=a.learn_lazy, chain=a.chain, persistent=a.persistent, chain_lookahead=a.chain_lookahead, wave_kernels=not a.no_waves)
     W = a.window_ms
     for kw in range(a.warm):
         tr, da = bench.window_inputs(kw, W)
@@ -92,7 +94,7 @@ def main():
                   f"{ch[0]['start_us']:.0f}->{ch[-1]['end_us']:.0f} ({ch[-1]['end_us'] - ch[0]['start_us']:.0f} us, "
                   f"{len(ch)} steps, mean kernel {np.mean([c['end_us'] - c['start_us'] for c in ch]):.1f} us)")
     print("first 40 rows:")
-    for r in [r for r in rows if 20 <= r["k"] <= 23 or 30 <= r["k"] <= 31]:
+    for r in [r for r in rows if 26 <= r["k"] <= 31]:
         print(f"  {r['cls']:8s} k={r['k']:3d}  {r['start_us']:9.2f} -> {r['end_us']:9.2f}  ({r['end_us'] - r['start_us']:7.2f})")
 
 
