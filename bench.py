@@ -227,7 +227,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     common = dict(dtype="f32", mode="fast", noise="philox", device=local, max_delay=dmax, learn_async=args.learn_async,
-                  chain=args.chain, persistent=args.persistent, chain_lookahead=args.chain_lookahead, wave_kernels=not args.no_waves)
+                  chain=args.chain, persistent={'auto': None, 'chain': True, 'graph': False}[args.scheduler], chain_lookahead=args.chain_lookahead, wave_kernels=args.waves)
 
     def barrier():
         torch.cuda.synchronize()
@@ -676,8 +676,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--chain", default=None, help="persistent chain footprints 'nthr,syn,ltp,ltp_thr,learn,learn_thr,stages' (sweeps; default: the library's)")
     ap.add_argument("--chain-lookahead", type=int, default=0, help="persistent chain: steps of push lookahead (0 = default)")
-    ap.add_argument("--no-waves", action="store_true", help="captured graph: round 1's group-per-item side kernels instead of the waves")
-    ap.add_argument("--persistent", action="store_true", help="persistent chain of resident role kernels instead of the captured CUDA graph of per-step kernels")
+    ap.add_argument("--waves", action="store_true", help="captured graph: the chain's wave kernels instead of the group-per-item side kernels")
+    ap.add_argument("--scheduler", default="auto", choices=["auto", "chain", "graph"],
+                    help="production-mode windows: the library's automatic choice, the persistent chain of resident role kernels, or the captured CUDA graph of per-step kernels")
     ap.add_argument("--learn-async", default="auto", choices=["auto", "off", "force"], help="learn pass beside the following steps (auto: large nets) or in place")
     ap.add_argument("--learn-lazy", type=int, default=0, help="EXPERIMENTAL event-driven learning: dense re-basing pass every M learn steps (0 = the reference's rule; not for reported numbers)")
     ap.add_argument("--learn-lazy-da", type=float, default=0.0, help="with --learn-lazy: re-base at every learn step while da exceeds this (0 = never)")

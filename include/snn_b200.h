@@ -201,10 +201,12 @@ int32_t snn_set_synapses_dense_col(snn_net* net, const double* s_colmajor,
  *      calls; so may the caller here, between two windows.
  *  (2) Everything that is NOT the model — any time unless marked [S] = only before the synapses are set:
  *      "graph"                 1 (default) whole windows as device-side schedules; 0 plain launches per step
- *      "persistent"            0 (default) production-mode windows run as a captured CUDA graph of per-step kernels;
- *                              1 as the persistent chain: one resident kernel per role for the whole window, steps
- *                              handed over through device-side counters (on one B200 the two
- *                              are on par at 1M neurons, the graph is ahead on small nets)
+ *      "persistent"            how production-mode windows are scheduled: -1 (default) automatic; 0 a captured CUDA
+ *                              graph of per-step kernels; 1 the persistent chain — one resident kernel per role for
+ *                              the whole window, steps handed over through device-side counters.
+ *                              Automatic = the chain, except for batches of more than 256 instances and whenever a
+ *                              profiler (ncu, nsys, compute-sanitizer) or CUDA_LAUNCH_BLOCKING serialises kernels
+ *                              (resident roles cannot hand over to kernels that are not running)
  *      "chain_lookahead"       persistent chain: steps of push lookahead, 1..3 (0 = default 2)
  *      "learn_async"       [S] 0 auto, 1 learn! always in place, 2 always the asynchronous double-buffered pass
  *      "learn_log_cap"     [S] entries of the sd-update log of the asynchronous pass (0 = by size)

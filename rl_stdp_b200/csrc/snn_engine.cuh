@@ -1612,10 +1612,11 @@ __global__ void learn_spill_reset_kernel(DevNet<T> p) { p.lc->spilled = 0u; }
 // Mutable data is read through L2 (ld.cg / volatile / acquire): nothing invalidates L1 inside a kernel.
 // =============================================================================================
 enum { kcNeuron = 0, kcPush = 1, kcLtd = 2, kcLtp = 3, kcBegun = 4, kcLearnBar = 5, kcAbort = 6, kcPassNs = 7, kcPassCnt = 8,
-       kcRemote = 9, kcCounters = 10 };
+       kcRemote = 9, kcPush1 = 10, kcLtd1 = 11, kcCounters = 12 };  // kcPush1 / kcLtd1: the synapse role's second step group
 struct ChainCtl { uint32_t w[kcCounters * 32]; };  // counter c at w[c * 32]: one 128-byte line each
 struct ChainDims {
   uint32_t NB, SB, PB, LB, RB;   // blocks of the neuron / synapse / ltp / learn / remote (partitioned runs) role
+  uint32_t SG, SBg[2];           // the synapse role works in SG (1 or 2) groups of SBg[g] blocks; group k & 1 takes step k
   uint32_t qpb;              // quads (4 neurons) per neuron block, multiple of 32
   int32_t n_learn;           // learn steps in this window
   int32_t do_decay;          // sd *= sd_decay inside learn! (SNN_SD_DECAY_ON_LEARN)
@@ -1646,6 +1647,44 @@ __device__ __forceinline__ bool chain_wait(ChainCtl* c, int which, uint32_t targ
   if (ld_acquire_u32(&c->w[which * 32]) >= target) return true;
   return chain_wait_slow(c, which, target, sleep_ns);
 }
+// Several conditions at once: ALL the counters are loaded before the first one is looked at (one L2 round trip for
+// the lot — waiting for them one after the other cost the neuron role three to four round trips per step), then a
+// single acquire fence.  target 0 = nothing to wait for.
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* q) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
+  return v;
+}
+template <int N>
+__device__ __forceinline__ bool chain_wait_all(ChainCtl* c, const int (&which)[N], const uint32_t (&target)[N], uint32_t sleep_ns) {
+  unsigned long long t0 = 0;
+  for (;;) {
+    uint32_t v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = target[i] ? ld_relaxed_u32(&c->w[which[i] * 32]) : 0u;
+    bool ok = true;
+    int first_bad = 0;
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) if (v[i] < target[i]) { ok = false; first_bad = which[i]; }
+    if (ok) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); return true; }
+    if (*reinterpret_cast<volatile uint32_t*>(&c->w[kcAbort * 32]) != 0u) return false;
+    if (!t0) t0 = gtime_ns();
+    else if (gtime_ns() - t0 > 10000000000ull) { atomicExch(&c->w[kcAbort * 32], 1u + (uint32_t)first_bad); return false; }
+    if (sleep_ns) __nanosleep(sleep_ns);
+  }
+}
+// phases of the synapse role's group g among the steps -1 .. k_last (group k & 1 takes step k; one group: all of them)
+__device__ __forceinline__ uint32_t syn_phases(const ChainDims& d, int g, int k_last) {
+  if (d.SG == 1) return g == 0 ? (uint32_t)(k_last + 2) : 0u;
+  if (g == 1) return (uint32_t)((k_last + 1) / 2 + 1);        // -1, 1, 3, ...
+  return k_last >= 0 ? (uint32_t)(k_last / 2 + 1) : 0u;       // 0, 2, 4, ...
+}
+// LTD phases (steps 0 .. k) of group g
+__device__ __forceinline__ uint32_t syn_ltd_phases(const ChainDims& d, int g, int k) {
+  if (d.SG == 1) return g == 0 ? (uint32_t)(k + 1) : 0u;
+  return g == 0 ? (uint32_t)(k / 2 + 1) : (uint32_t)((k + 1) / 2);
+}
+
 // all threads of the block have finished their part (call after __syncthreads, from one thread)
 __device__ __forceinline__ void chain_arrive(ChainCtl* c, int which) {
   __threadfence();
@@ -1730,12 +1769,17 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
     const bool euler = k > 0, detect = k < n;
     tl_begin(p.tl, 6, k);
     if (tid == 0) {
-      bool ok = chain_wait(ctl, kcNeuron, d.NB * (uint32_t)k, 0);
-      if (ok && k >= 1) ok = chain_wait(ctl, kcPush, d.SB * (uint32_t)sched[d.o_need + k], 0);
-      if (ok && k >= 1 && sched_learn(sched, k - 1)) ok = chain_wait(ctl, kcBegun, (uint32_t)sched_before(sched, k), 0);
-      if (ok && k > kLag) ok = chain_wait(ctl, kcLtp, d.PB * (uint32_t)(k - kLag), 0);
-      if (ok && k >= 1 && d.RB) ok = chain_wait(ctl, kcRemote, d.RB * (uint32_t)k, 0);  // the peers' spikes of step k-1 pushed / listed
-      s_ok = ok ? 1 : 0;
+      // neuron(k-1) on every block | the push phases Euler(k-1) consumes | learn!(k-1) begun | ltp not more than kLag
+      // steps behind | (partitioned) the peers' spikes of step k-1 pushed and listed
+      const int kl = k >= 1 ? sched[d.o_need + k] - 2 : -2;  // last push phase needed
+      const int which[6] = {kcNeuron, kcPush, kcPush1, kcBegun, kcLtp, kcRemote};
+      const uint32_t target[6] = {d.NB * (uint32_t)k,
+                                  kl >= -1 ? d.SBg[0] * syn_phases(d, 0, kl) : 0u,
+                                  kl >= -1 ? d.SBg[1] * syn_phases(d, 1, kl) : 0u,
+                                  (k >= 1 && sched_learn(sched, k - 1)) ? (uint32_t)sched_before(sched, k) : 0u,
+                                  k > kLag ? d.PB * (uint32_t)(k - kLag) : 0u,
+                                  (k >= 1 && d.RB) ? d.RB * (uint32_t)k : 0u};
+      s_ok = chain_wait_all<6>(ctl, which, target, 0) ? 1 : 0;
       s_nspk[(k + 1) & 1] = 0;  // last read in phase 3 of step k-1, which every thread has left
     }
     __syncthreads();
@@ -1755,7 +1799,9 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
       const int64_t nxt = (int64_t)__ldcg(cx->rec_off + (k - 1)) + n_prev;
       rec_base = (int32_t)(nxt < rec_cap ? nxt : rec_cap);
     }
-    if (detect) retire_spikes<T>(p, t, bid * TN + tid, d.NB * TN);
+    // (retire_spikes: after phase 2 — its list length is a dependent load nobody should wait for up front)
+    const int64_t xr = t - p.G;
+    const int retire_cnt = (detect && xr >= 0) ? __ldcg(p.spk_cnt + (int)(xr % p.R)) : 0;
     WView<T> vw;
     if (detect) vw = wview(p);
     // dopamine (new_net.jl:131 da *= 0.995 ; newnet_DASTDP.jl:54-56 da += 0.5 after step!)
@@ -1895,6 +1941,10 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         st4(su + 4 * ql, u);
       }
     }
+    if (retire_cnt > 0) {  // the spikes of step t - G leave the part of the bitmap ring a reader may rely on
+      const int32_t* __restrict__ rl = p.spk_list + (size_t)(xr % p.R) * p.Nld;
+      for (uint32_t q = bid * TN + tid; q < (uint32_t)retire_cnt; q += d.NB * TN) p.old_last[__ldcg(rl + q)] = (int32_t)xr;
+    }
     __syncthreads();
     tl_end(p.tl, 8, k); tl_begin(p.tl, 9, k);
     // ---- phase 3: this block's spikers, all in flight together (a chain of dependent memory round trips per
@@ -1907,6 +1957,8 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
       const int nd = sched[d.o_nd + k];  // delays 1..nd of this step's spikers are pushed here (the rest by the synapse role)
       if (nspk > 0) {
         if (tid == 0) s_base = atomicAdd(&p.spk_cnt[slot], nspk);
+        // previous spike of this thread's spiker(s), for the history word written at the end: in flight during the pushes
+        const int32_t h_prev = (int)tid < nspk ? __ldcg(p.hist + ((qb0 << 2) + s_spk[tid])).x : 0;
         for (int r0 = 0; r0 < nspk; r0 += kSpkWave) {
           const int nr = min(kSpkWave, nspk - r0);
           for (int x = (int)tid; x < nr; x += (int)TN) {
@@ -1966,7 +2018,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
           const uint32_t j = (qb0 << 2) + s_spk[w];
           list[base + w] = (int32_t)j;
           if (rec_ids && (int64_t)rec_base + base + w < rec_cap) rec_ids[rec_base + base + w] = (int32_t)j;
-          p.hist[j] = make_int2((int32_t)t, __ldcg(p.hist + j).x);  // trace set (new_net.jl:123), see DevNet::hist
+          p.hist[j] = make_int2((int32_t)t, w == (int)tid ? h_prev : __ldcg(p.hist + j).x);  // trace set (new_net.jl:123)
         }
         __syncthreads();
       }
@@ -2025,7 +2077,9 @@ struct WaveSmem {
 template <typename T, bool LTD>
 __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k, const int r_lo,
                                              const int r_hi, const int ring, const uint32_t bid, const uint32_t nblk,
-                                             WaveSmem& sm) {
+                                             const uint32_t region, WaveSmem& sm) {
+  // bid / nblk: this block's share of the step's items; region: its private sd-update log (unique per block);
+  // sm.blk_ev accumulates the delivered events over the calls (the caller zeroes it first and stores it last)
   typedef Ops<T> O;
   tl_begin(p.tl, LTD ? 1 : 5, k);
   const uint32_t tid = threadIdx.x, TB = blockDim.x, lane = tid & 31u;
@@ -2039,7 +2093,6 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
     sm.slots[tid] = sl;
     sm.cum[tid + 1] = __ldcg(p.spk_cnt + sl);
   }
-  if (tid == 0) sm.blk_ev = 0ull;
   __syncthreads();
   if (tid == 0) {
     int acc = 0;
@@ -2065,9 +2118,12 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
       const uint32_t i = (uint32_t)__ldcg(p.spk_list + (size_t)sm.slots[a] * Nld + (item - sm.cum[a]));
       const uint32_t* __restrict__ sg = p.seg + (size_t)i * (p.Dmax + 1);
       const uint32_t g0 = sg[a], g1 = sg[a + 1];
-      uint32_t pbv[kMaxLook + 1];
+      uint32_t pbv[kMaxLook + 1], p_end = g1;  // (no run-time index into pbv: it would live in local memory)
 #pragma unroll
-      for (int q = 0; q <= kMaxLook; ++q) pbv[q] = (push && q <= nseg) ? sg[min(a + r_lo + q, p.Dmax)] : g1;
+      for (int q = 0; q <= kMaxLook; ++q) {
+        pbv[q] = (push && q <= nseg) ? sg[min(a + r_lo + q, p.Dmax)] : g1;
+        if (q == nseg) p_end = pbv[q];
+      }
       const uint32_t ibase = p.B == 1 ? 0u : (i / Nper) * Nper;
       const bool ltd_row = LTD && (i - ibase) < Ne;  // only excitatory rows are plastic: the others have no LTD visits
       if (LTD) n_ev += (g1 - g0);
@@ -2075,7 +2131,7 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
       sm.s0[x] = b0; sm.n1[x] = g1 - b0; sm.src[x] = i;
 #pragma unroll
       for (int q = 0; q <= kMaxLook; ++q) sm.pb[x][q] = pbv[q];
-      sm.off[x + 1] = (g1 - b0) + (pbv[nseg] - pbv[0]);  // length; scanned below
+      sm.off[x + 1] = (g1 - b0) + (push ? p_end - pbv[0] : 0u);  // length; scanned below
     }
     __syncthreads();
     if (tid < 32) {  // inclusive scan of off[1..nitem] by one warp, consecutive items per lane
@@ -2133,7 +2189,7 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
       for (int u = 0; u < 2; ++u) {
         if (!ok[u]) continue;
         if (pl[u])             // arrives now: sd -= apre * trace_post(t)   (new_net.jl:127)
-          sd_add<T>(p, vw, e[u], -O::mul(p.apre, trace_resolve<T>(p, hq[u], j[u], t32, t32)), bid, inst[u]);
+          sd_add<T>(p, vw, e[u], -O::mul(p.apre, trace_resolve<T>(p, hq[u], j[u], t32, t32)), region, inst[u]);
         else if (!isl[u])      // arrives later: I += w into the buffer of its arrival step   (new_net.jl:116-118)
           red_add(p.Iacc + (size_t)((t + ahead[u]) % ring) * Nld + j[u],
                     w_resolve<T>(p, ws[u], fly[u], p.plastic_ei || (j[u] - ibs[u]) < Ne, inst[u], (T)0));
@@ -2145,8 +2201,6 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
   if (LTD) {
     for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
     if (lane == 0 && n_ev) atomicAdd(&sm.blk_ev, n_ev);
-    __syncthreads();
-    if (tid == 0 && sm.blk_ev) p.blk_ev[bid] += sm.blk_ev;
   }
   tl_end(p.tl, LTD ? 1 : 5, k);
 }
@@ -2156,7 +2210,10 @@ template <typename T, bool LTD>
 __global__ void __launch_bounds__(256)
 synapse_wave_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k, int r_lo, int r_hi) {
   __shared__ WaveSmem wsm;
-  synapse_wave<T, LTD>(p, cx, k, r_lo, r_hi, 2, blockIdx.x, gridDim.x, wsm);
+  if (threadIdx.x == 0) wsm.blk_ev = 0ull;
+  synapse_wave<T, LTD>(p, cx, k, r_lo, r_hi, 2, blockIdx.x, gridDim.x, blockIdx.x, wsm);
+  __syncthreads();
+  if (threadIdx.x == 0 && wsm.blk_ev) p.blk_ev[blockIdx.x] += wsm.blk_ev;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2170,43 +2227,52 @@ chain_synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl*
   __shared__ int s_ok;
   __shared__ WaveSmem wsm;
   const int n = cx->n_steps;
-  const uint32_t bid = blockIdx.x;
-  auto wait1 = [&](int which, uint32_t target) {
-    if (threadIdx.x == 0) s_ok = chain_wait(ctl, which, target, 40) ? 1 : 0;
-    __syncthreads();
-    const bool ok = s_ok != 0;
-    __syncthreads();
-    return ok;
-  };
+  // two groups of blocks take alternate steps (group k & 1 takes step k): a step is a chain of dependent memory
+  // round trips that neither group can shorten, but two steps in flight double the role's throughput
+  const uint32_t grp = d.SG == 2 ? (blockIdx.x & 1u) : 0u;
+  // (no run-time index into d.SBg: the whole by-value ChainDims would be copied to local memory)
+  const uint32_t bid = d.SG == 2 ? (blockIdx.x >> 1) : blockIdx.x, nblk = grp ? d.SBg[1] : d.SBg[0], region = blockIdx.x;
+  const int cPush = grp ? kcPush1 : kcPush, cLtd = grp ? kcLtd1 : kcLtd;
   auto arrive = [&](int which) {
     __syncthreads();
     if (threadIdx.x == 0) chain_arrive(ctl, which);
   };
+  if (threadIdx.x == 0) wsm.blk_ev = 0ull;
   // push schedule (Engine::launch_chain): at step k the arrivals of steps lo[k]..hi[k] are pushed — one step of
   // lookahead further than a step ago, everything up to the lookahead right after a learn step has begun
   const int32_t* __restrict__ plo = sched + d.o_lo + 1;  // indexed by k = -1 .. n-1
   const int32_t* __restrict__ phi = sched + d.o_hi + 1;
-  synapse_wave<T, false>(p, cx, -1, plo[-1] + 1, phi[-1] + 1, d.ring, bid, d.SB, wsm);  // spikes of earlier windows
-  arrive(kcPush);
-  for (int k = 0; k < n; ++k) {
-    if (!wait1(kcNeuron, d.NB * (uint32_t)(k + 1))) return;
-    if (d.RB && !wait1(kcRemote, d.RB * (uint32_t)(k + 1))) return;  // partitioned: the step's spike list is complete
-    const bool learn = sched_learn(sched, k);
+  for (int k = -1; k < n; ++k) {
+    if (d.SG == 2 && (uint32_t)(k & 1) != grp) continue;
+    const bool learn = k >= 0 && sched_learn(sched, k);
     const int r_lo = plo[k] - k, r_hi = phi[k] - k;
-    if (!learn) {
-      synapse_wave<T, true>(p, cx, k, r_lo, r_hi, d.ring, bid, d.SB, wsm);
-      arrive(kcLtd);
-      if (threadIdx.x == 0) red_add(&ctl->w[kcPush * 32], 1u);  // ordered after the fence of the arrive above
-    } else {
-      synapse_wave<T, true>(p, cx, k, 1, 0, d.ring, bid, d.SB, wsm);  // LTD only: the pushes must see learn!(k)
-      arrive(kcLtd);
-      if (r_hi >= r_lo) {
-        if (!wait1(kcBegun, (uint32_t)sched_before(sched, k) + 1u)) return;
-        synapse_wave<T, false>(p, cx, k, r_lo, r_hi, d.ring, bid, d.SB, wsm);
+    if (k >= 0) {
+      if (threadIdx.x == 0) {  // neuron(k) on every block; partitioned: the step's spike list complete
+        const int which[2] = {kcNeuron, kcRemote};
+        const uint32_t target[2] = {d.NB * (uint32_t)(k + 1), d.RB * (uint32_t)(k + 1)};
+        s_ok = chain_wait_all<2>(ctl, which, target, 40) ? 1 : 0;
       }
-      arrive(kcPush);
+      __syncthreads();
+      if (!s_ok) break;
+    }
+    // (each instantiation of the wave appears once: four inlined copies cost 200 bytes of spills per thread)
+    if (k >= 0) {  // LTD of the arrivals of step k, fused with the look-ahead pushes unless this is a learn step
+      synapse_wave<T, true>(p, cx, k, learn ? 1 : r_lo, learn ? 0 : r_hi, d.ring, bid, nblk, region, wsm);
+      arrive(cLtd);
+      if (!learn && threadIdx.x == 0) red_add(&ctl->w[cPush * 32], 1u);  // ordered after the fence of the arrive above
+    }
+    if (k < 0 || learn) {  // spikes of earlier windows / the pushes that must see learn!(k)
+      if (learn && r_hi >= r_lo) {
+        if (threadIdx.x == 0) s_ok = chain_wait(ctl, kcBegun, (uint32_t)sched_before(sched, k) + 1u, 40) ? 1 : 0;
+        __syncthreads();
+        if (!s_ok) break;
+      }
+      if (r_hi >= r_lo) synapse_wave<T, false>(p, cx, k, r_lo, r_hi, d.ring, bid, nblk, region, wsm);
+      arrive(cPush);
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0 && wsm.blk_ev) p.blk_ev[blockIdx.x] += wsm.blk_ev;
 }
 
 // ltp_wave (persistent chain): the work of ltp_body — for every neuron j that spiked at t, sd += apost * pre trace
@@ -2226,7 +2292,6 @@ __device__ __forceinline__ void ltp_wave(const DevNet<T>& p, const WindowCtx<T>*
   const int32_t* __restrict__ list = p.spk_list + (size_t)slot * (size_t)p.Nld;
   const WView<T> vw = wview(p);
   unsigned long long n_ltp = 0;
-  if (tid == 0) sm.blk_ev = 0ull;
   for (uint32_t r0 = lo; r0 < hi; r0 += kWaveItems) {
     const uint32_t nitem = min((uint32_t)kWaveItems, hi - r0);
     for (uint32_t x = tid; x < nitem; x += TB) {
@@ -2283,9 +2348,7 @@ __device__ __forceinline__ void ltp_wave(const DevNet<T>& p, const WindowCtx<T>*
     __syncthreads();
   }
   for (int o = 16; o > 0; o >>= 1) n_ltp += __shfl_down_sync(0xffffffffu, n_ltp, o);
-  if (lane == 0 && n_ltp) atomicAdd(&sm.blk_ev, n_ltp);
-  __syncthreads();
-  if (tid == 0 && sm.blk_ev) p.blk_ltp[bid] += sm.blk_ev;
+  if (lane == 0 && n_ltp) atomicAdd(&sm.blk_ev, n_ltp);  // (accumulates over the calls; the caller stores it)
   tl_end(p.tl, 2, k);
 }
 
@@ -2293,7 +2356,11 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 ltp_wave_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
   __shared__ WaveSmem wsm;
+  if (threadIdx.x == 0) wsm.blk_ev = 0ull;
+  __syncthreads();
   ltp_wave<T>(p, cx, k, blockIdx.x, gridDim.x, wsm);
+  __syncthreads();
+  if (threadIdx.x == 0 && wsm.blk_ev) p.blk_ltp[blockIdx.x] += wsm.blk_ev;
 }
 
 template <typename T>
@@ -2302,16 +2369,21 @@ chain_ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __r
   __shared__ int s_ok;
   __shared__ WaveSmem wsm;
   const int n = cx->n_steps;
+  if (threadIdx.x == 0) wsm.blk_ev = 0ull;
   for (int k = 0; k < n; ++k) {
-    if (threadIdx.x == 0)
-      s_ok = (chain_wait(ctl, kcNeuron, d.NB * (uint32_t)(k + 1), 40) &&
-              (!d.RB || chain_wait(ctl, kcRemote, d.RB * (uint32_t)(k + 1), 40))) ? 1 : 0;
+    if (threadIdx.x == 0) {
+      const int which[2] = {kcNeuron, kcRemote};
+      const uint32_t target[2] = {d.NB * (uint32_t)(k + 1), d.RB * (uint32_t)(k + 1)};
+      s_ok = chain_wait_all<2>(ctl, which, target, 40) ? 1 : 0;
+    }
     __syncthreads();
-    if (!s_ok) return;
+    if (!s_ok) break;
     ltp_wave<T>(p, cx, k, blockIdx.x, d.PB, wsm);
     __syncthreads();
     if (threadIdx.x == 0) chain_arrive(ctl, kcLtp);
   }
+  __syncthreads();
+  if (threadIdx.x == 0 && wsm.blk_ev) p.blk_ltp[blockIdx.x] += wsm.blk_ev;
 }
 
 // chain_remote_kernel (neuron-partitioned runs): replay of the peers' detection, step by step.  remote(k) may start
@@ -2335,19 +2407,33 @@ chain_remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
 
 // log replay of the pass that has just ended (all LB blocks, block-stride over the regions)
 template <typename T>
-__device__ __forceinline__ void chain_replay(const DevNet<T>& p, const uint32_t bid, const uint32_t nblk) {
+__device__ __forceinline__ void chain_replay(const DevNet<T>& p, const ChainDims& d, const uint32_t bid, const uint32_t nblk) {
   typename DevNet<T>::T2* w = p.wsdX[*reinterpret_cast<const volatile uint32_t*>(&p.lc->state) >> 31];
-  for (uint32_t r = bid; r < p.log_regions; r += nblk) {
-    const uint32_t cnt = __ldcg(p.log_cnt + (size_t)r * kLogStride);
-    const uint32_t nn = cnt < p.log_region_cap ? cnt : p.log_region_cap;
-    const LogEntry<T>* __restrict__ lg = p.dlog + (size_t)r * p.log_region_cap;
-    for (uint32_t q = threadIdx.x; q < nn; q += blockDim.x) {
-      LogEntry<T> le;
-      le.e = __ldcg(&lg[q].e); le.d = __ldcg(&lg[q].d);
-      red_add(&w[le.e].y, le.d);
+  // only the regions the chain's blocks write: [0, SB) synapse role, [log_ltp_base, log_ltp_base + PB) ltp role.  This
+  // block's share is looked at all at once (one round trip for the counts), then the non-empty ones are replayed.
+  __shared__ uint32_t s_cnt[256];
+  const uint32_t n_reg = d.SB + d.PB, TB = min(blockDim.x, 256u);
+  // block b replays the regions b, b + nblk, b + 2 nblk, ... (the work stays spread over all blocks); thread x looks
+  // at the count of the x-th of them, so a block sees all its counts after one round trip
+  for (uint32_t base = bid; base < n_reg; base += nblk * TB) {
+    const uint32_t mine = base + threadIdx.x * nblk;
+    if (threadIdx.x < TB)
+      s_cnt[threadIdx.x] = mine < n_reg ? __ldcg(p.log_cnt + (size_t)(mine < d.SB ? mine : p.log_ltp_base + (mine - d.SB)) * kLogStride) : 0u;
+    __syncthreads();
+    for (uint32_t x = 0; x < TB && base + x * nblk < n_reg; ++x) {
+      const uint32_t cnt = s_cnt[x];
+      if (!cnt) continue;
+      const uint32_t rr = base + x * nblk, r = rr < d.SB ? rr : p.log_ltp_base + (rr - d.SB);
+      const uint32_t nn = cnt < p.log_region_cap ? cnt : p.log_region_cap;
+      const LogEntry<T>* __restrict__ lg = p.dlog + (size_t)r * p.log_region_cap;
+      for (uint32_t q = threadIdx.x; q < nn; q += blockDim.x) {
+        LogEntry<T> le;
+        le.e = __ldcg(&lg[q].e); le.d = __ldcg(&lg[q].d);
+        red_add(&w[le.e].y, le.d);
+      }
+      if (threadIdx.x == 0) p.log_cnt[(size_t)r * kLogStride] = 0u;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && cnt) p.log_cnt[(size_t)r * kLogStride] = 0u;
   }
   if (*reinterpret_cast<const volatile uint32_t*>(&p.lc->spilled)) {
     const int64_t tid = bid * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)nblk * blockDim.x;
@@ -2405,9 +2491,15 @@ chain_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* _
     const bool last = i == d.n_learn;           // window end: only the replay of the final pass
     const int k = last ? n - 1 : steps[i];
     // every sd update of the steps up to k has been issued (and none of step k+1 yet: they wait for `begun`)
-    if (!wait1(kcLtd, d.SB * (uint32_t)(k + 1))) return;
-    if (!wait1(kcLtp, d.PB * (uint32_t)(k + 1))) return;
-    if (i > 0) chain_replay<T>(p, bid, LB);
+    if (threadIdx.x == 0) {
+      const int which[3] = {kcLtd, kcLtd1, kcLtp};
+      const uint32_t target[3] = {d.SBg[0] * syn_ltd_phases(d, 0, k), d.SBg[1] * syn_ltd_phases(d, 1, k), d.PB * (uint32_t)(k + 1)};
+      s_ok = chain_wait_all<3>(ctl, which, target, 100) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    __syncthreads();
+    if (i > 0) chain_replay<T>(p, d, bid, LB);
     if (!role_barrier()) return;
     if (last) {
       if (bid == 0 && threadIdx.x == 0) p.lc->spilled = 0u;
@@ -2525,8 +2617,10 @@ __global__ void probe_kernel(DevNet<T> p, const uint32_t* __restrict__ pos, int 
 // Set by name through snn_set_param (the names are the quoted strings of Engine::set_param).
 struct Options {
   int graph = 1;             // captured window graph / persistent chain (1) or plain stream-ordered launches (0)
-  int persistent = 0;        // production-mode windows: the captured graph of per-step kernels (0, default) or the
-                             // persistent chain of four resident role kernels (1); DESIGN.md section 5 has the measurements
+  int persistent = -1;       // production-mode windows: -1 auto (the persistent chain of resident role kernels unless the
+                             // batch has more than 256 instances), 0 the captured graph of per-step kernels, 1 the chain.
+                             // DESIGN.md section 5 has the measurements.  Under a profiler / CUDA_LAUNCH_BLOCKING the chain is
+                             // never used: serialised kernels cannot hand steps over to each other.
   int learn_async = 0;       // 0 auto, 1 learn! always in place, 2 always the asynchronous double-buffered pass
   int64_t learn_log_cap = 0; // asynchronous pass: total entries of the sd-update log (0 = by size)
   int pass_blocks = 0, pass_tile_k = 0, pass_stages = 0;  // asynchronous pass of the graph path: blocks per SM, tile (K synapses), TMA stages
@@ -2536,18 +2630,23 @@ struct Options {
   double learn_lazy_da = 0;  //   ... and at every learn step while da exceeds this (0 = never)
   int chain[7] = {0, 0, 0, 0, 0, 0, 0};  // persistent chain footprints, see Engine::chain_plan
   int chain_look = 0;        // persistent chain: steps of push lookahead (0 = default 2; 1..3)
-  int waves = 1;             // captured graph: load-balanced wave kernels for LTD / pushes / LTP (0: group-per-item kernels)
+  int chain_groups = 0;      // persistent chain: 2 = the synapse role works on alternate steps in two block groups
+  int waves = 0;             // captured graph: 1 = the chain's load-balanced wave kernels for LTD / pushes / LTP instead of the
+                             // group-per-item kernels (measured slower as kernels of their own: 19.9x vs 21.0x real time on C5)
 };
 
 // grow-only device buffer
 struct DevBuf {
   void* ptr = nullptr; size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
+  // stream-ordered allocation (cudaMallocAsync / cudaFreeAsync on `s`): cudaMalloc and cudaFree wait for the whole
+  // device, and a handle that grows a staging buffer while the resident kernels of ANOTHER handle of the process wait
+  // for its spikes (several ranks in one process) would never get its turn
+  cudaError_t reserve(size_t bytes, cudaStream_t s) {
     if (bytes <= cap) return cudaSuccess;
-    if (ptr) cudaFree(ptr);
+    if (ptr) cudaFreeAsync(ptr, s);
     ptr = nullptr; cap = 0;
     size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e = cudaMalloc(&ptr, want);
+    cudaError_t e = cudaMallocAsync(&ptr, want, s);
     if (e == cudaSuccess) cap = want;
     return e;
   }
@@ -2689,7 +2788,7 @@ class Engine : public IEngine {
         {"chain_neuron_threads", &opt_.chain[0], false}, {"chain_synapse_blocks", &opt_.chain[1], false},
         {"chain_ltp_blocks", &opt_.chain[2], false}, {"chain_ltp_threads", &opt_.chain[3], false},
         {"chain_learn_blocks", &opt_.chain[4], false}, {"chain_learn_threads", &opt_.chain[5], false},
-        {"chain_learn_stages", &opt_.chain[6], false}, {"chain_lookahead", &opt_.chain_look, false}, {"wave_kernels", &opt_.waves, false}};
+        {"chain_learn_stages", &opt_.chain[6], false}, {"chain_lookahead", &opt_.chain_look, false}, {"wave_kernels", &opt_.waves, false}, {"chain_synapse_groups", &opt_.chain_groups, false}};
     for (const E& e : ints) if (n == e.name) { *pi = e.i; *structural = e.st; return 1; }
     if (n == "learn_log_cap") { *pl = &opt_.learn_log_cap; *structural = true; return 1; }
     if (n == "learn_lazy_da") { *pd = &opt_.learn_lazy_da; *structural = true; return 1; }
@@ -2723,7 +2822,7 @@ class Engine : public IEngine {
     int* pi; int64_t* pl; double* pd; bool structural;
     if (param_ref(n, &pi, &pl, &pd, &structural)) {
       if (structural && have_topo_) { err = "parameter '" + n + "' shapes the synapse storage: set it before the synapses"; return SNN_ERR_STATE; }
-      if (value < 0) { err = "parameter '" + n + "' must be >= 0"; return SNN_ERR_INVALID; }
+      if (value < 0 && n != "persistent") { err = "parameter '" + n + "' must be >= 0"; return SNN_ERR_INVALID; }
       if (pi) *pi = (int)value; else if (pl) *pl = (int64_t)value; else *pd = value;
       drop_graph();
       return apply_options(err);
@@ -2867,7 +2966,7 @@ class Engine : public IEngine {
         // the reference holds the post-decay value between calls (new_net.jl:130): trace after step t-1, times decay
         if (count != p.N) { err = "count mismatch"; return SNN_ERR_INVALID; }
         if (t_ == 0) { std::fill(host, host + count, 0.0); return SNN_OK; }
-        SNN_CUDA_OK(b_stage_.reserve(p.N * sizeof(double)));
+        SNN_CUDA_OK(b_stage_.reserve(p.N * sizeof(double), stream_));
         double* d = b_stage_.as<double>();
         trace_to_double_kernel<T><<<grid_for(p.N), 256, 0, stream_>>>(p, (int32_t)(t_ - 1), d);
         SNN_CUDA_OK(cudaMemcpyAsync(host, d, p.N * sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -2883,7 +2982,7 @@ class Engine : public IEngine {
         if (count != p.E) { err = "count mismatch"; return SNN_ERR_INVALID; }
         if (p.E == 0) return SNN_OK;
         { const int rcf = lazy_to_api(err); if (rcf) return rcf; }
-        SNN_CUDA_OK(b_stage_.reserve(p.E * sizeof(double)));
+        SNN_CUDA_OK(b_stage_.reserve(p.E * sizeof(double), stream_));
         double* d = b_stage_.as<double>();
         wsd_to_caller<T><<<grid_for(p.E), 256, 0, stream_>>>(p.wsdX[cur_], topo_.perm, d, p.E, field == SNN_FIELD_W ? 0 : 1);
         cudaError_t e = cudaMemcpyAsync(host, d, p.E * sizeof(double), cudaMemcpyDeviceToHost, stream_);
@@ -2897,7 +2996,7 @@ class Engine : public IEngine {
     if (count != n) { err = "count mismatch"; return SNN_ERR_INVALID; }
     // persistent staging buffer: the closed-loop callers (reward / dopamine experiments) read a few scalars per
     // window, and a cudaMalloc + cudaFree pair per call cost more than the window itself
-    SNN_CUDA_OK(b_stage_.reserve(n * sizeof(double)));
+    SNN_CUDA_OK(b_stage_.reserve(n * sizeof(double), stream_));
     double* d = b_stage_.as<double>();
     to_double_kernel<T><<<grid_for(n), 256, 0, stream_>>>(src, d, n, scale);
     SNN_CUDA_OK(cudaMemcpyAsync(host, d, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -2927,7 +3026,7 @@ class Engine : public IEngine {
       default: err = "field is not settable"; return SNN_ERR_INVALID;
     }
     if (count != n) { err = "count mismatch"; return SNN_ERR_INVALID; }
-    SNN_CUDA_OK(b_stage_.reserve(n * sizeof(double)));
+    SNN_CUDA_OK(b_stage_.reserve(n * sizeof(double), stream_));
     double* d = b_stage_.as<double>();
     SNN_CUDA_OK(cudaMemcpyAsync(d, host, n * sizeof(double), cudaMemcpyHostToDevice, stream_));
     from_double_kernel<T><<<grid_for(n), 256, 0, stream_>>>(d, dst, n);
@@ -3163,7 +3262,7 @@ class Engine : public IEngine {
   int upload_wsd(const double* h, int comp, int zero_other, std::string& err) {
     DevNet<T>& p = p_;
     if (p.E == 0) return SNN_OK;
-    SNN_CUDA_OK(b_stage_.reserve(p.E * sizeof(double)));
+    SNN_CUDA_OK(b_stage_.reserve(p.E * sizeof(double), stream_));
     double* d = b_stage_.as<double>();
     cudaError_t e = cudaMemcpyAsync(d, h, p.E * sizeof(double), cudaMemcpyHostToDevice, stream_);
     // weights go to both buffers (non-plastic ones are read from either); sd lives in the current one
@@ -3355,6 +3454,15 @@ class Engine : public IEngine {
       return k;
     }();
     return info;
+  }
+  // ncu / nsys / compute-sanitizer inject themselves through these variables; CUDA_LAUNCH_BLOCKING makes launches synchronous
+  static bool kernels_are_serialised() {
+    static const bool s = [] {
+      const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
+      return (lb && lb[0] == '1') || getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
+             getenv("NVTX_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE");
+    }();
+    return s;
   }
   bool chain_plan(bool with_learn, std::string* why);
   bool chain_ok(const StepArgs& a);
@@ -3722,7 +3830,9 @@ bool Engine<T>::chain_plan(bool with_learn, std::string* why) {
   chain_state_[pi] = -1;
   DevNet<T>& p = p_;
   auto fail = [&](const char* m) { if (why) *why = m; return false; };
-  if (p.exact || !use_graph_ || !opt_.persistent || p.lazy) return fail("mode");
+  if (p.exact || !use_graph_ || opt_.persistent == 0 || p.lazy) return fail("mode");
+  if (opt_.persistent < 0 && p.B > 256) return fail("auto: large batches of small instances run faster as the captured graph");
+  if (kernels_are_serialised()) return fail("a profiler or CUDA_LAUNCH_BLOCKING serialises kernels: resident roles could not hand over");
   if (cfg_.sd_decay_mode == SNN_SD_DECAY_EVERY_STEP) return fail("sd decays every step");
   const bool parted = !(p.part_lo == 0 && p.part_hi == p.N);
   if (exchange_ || (parted && p.n_ranks < 2)) return fail("partitioned with a host-side exchange");
@@ -3775,6 +3885,10 @@ bool Engine<T>::chain_plan(bool with_learn, std::string* why) {
   d.PB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm_ * ltp_per_sm, (ev_guess + 255) / 256));
   d.LB = (uint32_t)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm_ * learn_per_sm, std::max<uint32_t>(1, p.n_tiles)));
   if (d.SB > (uint32_t)gA_cap() || d.PB > (uint32_t)gP_cap()) return fail("log regions");
+  // two step groups were measured slower on C5 (22.7x vs 24.4x real time: a step with half the blocks takes twice as
+  // long, and the pushes right after a learn step are on the neuron role's critical path): one group unless asked
+  d.SG = (opt_.chain_groups == 2 && d.SB >= 2) ? 2u : 1u;
+  d.SBg[0] = d.SG == 2 ? (d.SB + 1) / 2 : d.SB; d.SBg[1] = d.SG == 2 ? d.SB / 2 : 0u;
   d.RB = 0;
   if (parted) {
     const int64_t remote_words = p.W - local_quads / 8;
@@ -3856,7 +3970,7 @@ int Engine<T>::launch_chain(const StepArgs& a, std::string& err) {
   d.o_hi = (int32_t)sched.size(); sched.insert(sched.end(), s_hi.begin(), s_hi.end());
   d.o_nd = (int32_t)sched.size(); sched.insert(sched.end(), s_nd.begin(), s_nd.end());
   d.o_need = (int32_t)sched.size(); sched.insert(sched.end(), s_need.begin(), s_need.end());
-  SNN_CUDA_OK(b_sched_.reserve(sched.size() * sizeof(int32_t)));
+  SNN_CUDA_OK(b_sched_.reserve(sched.size() * sizeof(int32_t), stream_));
   SNN_CUDA_OK(cudaMemcpyAsync(b_sched_.ptr, sched.data(), sched.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
   SNN_CUDA_OK(cudaMemsetAsync(d_chain_, 0, sizeof(ChainCtl), stream_));
   d.n_learn = (int32_t)steps.size();
@@ -3957,38 +4071,38 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
   cx.t0 = t_; cx.slot0 = slot_host(t_); cx.n_steps = n;
   if (cfg_.noise_mode == SNN_NOISE_REPLAY) {
     const size_t cnt = (size_t)n * N;
-    SNN_CUDA_OK(b_noise_.reserve(cnt * sizeof(T)));
+    SNN_CUDA_OK(b_noise_.reserve(cnt * sizeof(T), stream_));
     if (sizeof(T) == 8) {
       SNN_CUDA_OK(cudaMemcpyAsync(b_noise_.ptr, a.noise, cnt * sizeof(double), cudaMemcpyHostToDevice, stream_));
     } else {
-      SNN_CUDA_OK(b_noise64_.reserve(cnt * sizeof(double)));
+      SNN_CUDA_OK(b_noise64_.reserve(cnt * sizeof(double), stream_));
       SNN_CUDA_OK(cudaMemcpyAsync(b_noise64_.ptr, a.noise, cnt * sizeof(double), cudaMemcpyHostToDevice, stream_));
       from_double_kernel<T><<<grid_for((int64_t)cnt), 256, 0, stream_>>>(b_noise64_.as<double>(), b_noise_.as<T>(), (int64_t)cnt);
     }
     cx.noise = b_noise_.as<T>();
   }
   if (a.n_da > 0) {
-    SNN_CUDA_OK(b_ev_off_.reserve((n + 1) * sizeof(int32_t)));
-    SNN_CUDA_OK(b_ev_inst_.reserve(a.n_da * sizeof(int32_t)));
-    SNN_CUDA_OK(b_ev_amt_.reserve(a.n_da * sizeof(double)));
+    SNN_CUDA_OK(b_ev_off_.reserve((n + 1) * sizeof(int32_t), stream_));
+    SNN_CUDA_OK(b_ev_inst_.reserve(a.n_da * sizeof(int32_t), stream_));
+    SNN_CUDA_OK(b_ev_amt_.reserve(a.n_da * sizeof(double), stream_));
     SNN_CUDA_OK(cudaMemcpyAsync(b_ev_off_.ptr, ev_off.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
     SNN_CUDA_OK(cudaMemcpyAsync(b_ev_inst_.ptr, ev_inst.data(), a.n_da * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
     SNN_CUDA_OK(cudaMemcpyAsync(b_ev_amt_.ptr, ev_amt.data(), a.n_da * sizeof(double), cudaMemcpyHostToDevice, stream_));
     cx.ev_off = b_ev_off_.as<int32_t>(); cx.ev_inst = b_ev_inst_.as<int32_t>(); cx.ev_amt = b_ev_amt_.as<double>();
   }
   if (a.n_force > 0) {
-    SNN_CUDA_OK(b_force_.reserve(a.n_force * sizeof(int32_t)));
+    SNN_CUDA_OK(b_force_.reserve(a.n_force * sizeof(int32_t), stream_));
     SNN_CUDA_OK(cudaMemcpyAsync(b_force_.ptr, force_ids.data(), a.n_force * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
   }
   if (a.n_cur > 0) {
-    SNN_CUDA_OK(b_cur_idx_.reserve(a.n_cur * sizeof(int32_t)));
-    SNN_CUDA_OK(b_cur_val_.reserve(a.n_cur * sizeof(double)));
+    SNN_CUDA_OK(b_cur_idx_.reserve(a.n_cur * sizeof(int32_t), stream_));
+    SNN_CUDA_OK(b_cur_val_.reserve(a.n_cur * sizeof(double), stream_));
     SNN_CUDA_OK(cudaMemcpyAsync(b_cur_idx_.ptr, cur_ids.data(), a.n_cur * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
     SNN_CUDA_OK(cudaMemcpyAsync(b_cur_val_.ptr, cur_val.data(), a.n_cur * sizeof(double), cudaMemcpyHostToDevice, stream_));
   }
   if (a.spikes_out) {
-    SNN_CUDA_OK(b_rec_.reserve(a.spikes_cap * sizeof(int32_t)));
-    SNN_CUDA_OK(b_rec_off_.reserve((n + 1) * sizeof(int32_t)));
+    SNN_CUDA_OK(b_rec_.reserve(a.spikes_cap * sizeof(int32_t), stream_));
+    SNN_CUDA_OK(b_rec_off_.reserve((n + 1) * sizeof(int32_t), stream_));
     SNN_CUDA_OK(cudaMemsetAsync(b_rec_off_.ptr, 0, (n + 1) * sizeof(int32_t), stream_));
     cx.rec_ids = b_rec_.as<int32_t>(); cx.rec_off = b_rec_off_.as<int32_t>(); cx.rec_cap = a.spikes_cap;
   }
@@ -4008,9 +4122,9 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     if (a.n_probes > 4096 || !a.probe_syn || !a.probe_out) { err = "probes: 1..4096 synapse indices and an output buffer"; return SNN_ERR_INVALID; }
     for (int q = 0; q < a.n_probes; ++q)
       if (a.probe_syn[q] < 0 || a.probe_syn[q] >= p.E) { err = "probe synapse index out of range"; return SNN_ERR_INVALID; }
-    SNN_CUDA_OK(b_probe_want_.reserve(a.n_probes * sizeof(int64_t)));
-    SNN_CUDA_OK(b_probe_pos_.reserve(a.n_probes * sizeof(uint32_t)));
-    SNN_CUDA_OK(b_probe_out_.reserve((size_t)n * a.n_probes * 2 * sizeof(double)));
+    SNN_CUDA_OK(b_probe_want_.reserve(a.n_probes * sizeof(int64_t), stream_));
+    SNN_CUDA_OK(b_probe_pos_.reserve(a.n_probes * sizeof(uint32_t), stream_));
+    SNN_CUDA_OK(b_probe_out_.reserve((size_t)n * a.n_probes * 2 * sizeof(double), stream_));
     SNN_CUDA_OK(cudaMemcpyAsync(b_probe_want_.ptr, a.probe_syn, a.n_probes * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
     probe_locate_kernel<<<grid_for(p.E), 256, 0, stream_>>>(topo_.perm, p.E, b_probe_want_.as<int64_t>(), a.n_probes,
                                                             b_probe_pos_.as<uint32_t>());

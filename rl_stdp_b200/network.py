@@ -59,8 +59,9 @@ class SparseNetwork:
         opts = {}
         if not bool(params.pop("graph", True)):
             opts["graph"] = 0          # plain stream-ordered launches instead of whole-window schedules
-        if bool(params.pop("persistent", False)):
-            opts["persistent"] = 1     # the persistent chain of resident role kernels instead of the captured CUDA graph
+        persistent = params.pop("persistent", None)   # None: the library's automatic choice
+        if persistent is not None:
+            opts["persistent"] = 1 if persistent else 0   # the persistent chain of resident role kernels / the captured graph
         exp_flags = int(params.pop("exp_flags", 0))
         for bit, name in ((2, "timeline"), (4, "serialise_learn_pass"), (8, "neuron_blocks_256"), (512, "lsu_pass")):
             if exp_flags & bit:
@@ -77,8 +78,8 @@ class SparseNetwork:
         side_blocks = int(params.pop("side_blocks", 0))  # 10*synapse + ltp blocks per SM of the graph path
         opts["synapse_blocks_per_sm"], opts["ltp_blocks_per_sm"] = side_blocks // 10, side_blocks % 10
         opts["chain_lookahead"] = int(params.pop("chain_lookahead", 0))  # 0 = the library's default
-        if not bool(params.pop("wave_kernels", True)):
-            opts["wave_kernels"] = 0   # group-per-item side kernels of round 1 instead of the load-balanced waves
+        if bool(params.pop("wave_kernels", False)):
+            opts["wave_kernels"] = 1   # captured graph: the chain's load-balanced waves instead of the group-per-item side kernels
         chain = params.pop("chain", None)  # "nthr,syn,ltp,ltp_thr,learn,learn_thr,stages" (sweeps)
         if chain:
             names = ("chain_neuron_threads", "chain_synapse_blocks", "chain_ltp_blocks", "chain_ltp_threads",
@@ -98,7 +99,7 @@ class SparseNetwork:
         self._h = C.c_void_p()
         L.check(lib.snn_create(C.byref(cfg), C.byref(self._h)))
         for name, v in opts.items():
-            if v or name in ("graph", "wave_kernels"):   # these two are only in `opts` when they are turned OFF
+            if v or name in ("graph", "persistent"):   # these two are only in `opts` when they were given
                 self.set_param(name, v)
         rowptr = np.ascontiguousarray(rowptr, np.int64)
         post = np.ascontiguousarray(post, np.int32)

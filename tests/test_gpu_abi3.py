@@ -100,7 +100,7 @@ def test_named_parameters():
     L = _L()
     n, ne, dmax, rowptr, post, w, delay = _delay_net(seed=41, n=800, ne=640, fan=30, dmax=4)
     net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="fast", max_delay=dmax)
-    assert net.get_param("apre") == 1.5 and net.get_param("persistent") == 0 and net.get_param("graph") == 1
+    assert net.get_param("apre") == 1.5 and net.get_param("persistent") == -1 and net.get_param("graph") == 1
     with pytest.raises(L.SnnError):
         net.set_param("no_such_parameter", 1)
     with pytest.raises(L.SnnError):
@@ -139,7 +139,7 @@ def test_three_schedulers_same_spikes():
     noise = synth.thalamic_noise(T, n, seed=52)
     ora = po.Sparse(n, ne, rowptr, post, w, delay, max_delay=dmax)
     ref = run_oracle_sparse(ora, noise, np.zeros(T, np.uint8), [])
-    for kw, path in ((dict(persistent=True), 2), (dict(), 1), (dict(graph=False), 0)):
+    for kw, path in ((dict(persistent=True), 2), (dict(persistent=False), 1), (dict(graph=False), 0), (dict(), 2)):
         net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="fast", max_delay=dmax, **kw)
         got = []
         for lo in range(0, T, 80):

@@ -174,10 +174,13 @@ def test_p3_batch_equals_singles_gpu(seed, B):
 
 @pytest.mark.gpu
 @GPU
-@given(seed=st.integers(0, 10_000), world=st.sampled_from([2, 3, 4]), mode=st.sampled_from(["exact", "fast", "chain"]))
+@given(seed=st.integers(0, 10_000), world=st.sampled_from([2, 3, 4]), mode=st.sampled_from(["exact", "chain"]))
 def test_p4_partition_equals_single_gpu(seed, world, mode):
     """G handles of one process on one GPU, peer-to-peer exchange (plain device pointers) — the same kernels the
-    multi-GPU runs use; production mode with frozen weights, exact mode with learning."""
+    multi-GPU runs use; production mode (persistent chain with its remote role) with frozen weights, exact mode with
+    learning.  (The captured-graph scheduler is not run this way: a rank that instantiates its graph while the
+    kernels of its peers in the SAME process spin for it stalls them; one process per rank — the deployment, and
+    test_partition_p2p_ipc_two_processes_one_gpu — has no such coupling.)"""
     from rl_stdp_b200.partition import PartitionedRank, connect_local, plan, run_local_ranks
     kw = dict(persistent=True) if mode == "chain" else {}   # "chain": production mode on the persistent chain (remote role)
     mode = "fast" if mode == "chain" else mode

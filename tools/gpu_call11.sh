@@ -1,0 +1,22 @@
+#!/bin/bash
+mkdir -p gpurun_out
+SECONDS=0
+timeout 1200 python -m pytest tests/test_properties.py tests/test_gpu_parity.py tests/test_gpu_gridcode.py tests/test_gpu_actor.py tests/test_gpu_partition.py -m gpu -q > gpurun_out/r2k_pytest.txt 2>&1
+echo "pytest rc=$? ${SECONDS}s"; tail -15 gpurun_out/r2k_pytest.txt
+show() { python - "$1" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], {k:round(d[k],3) if isinstance(d[k],float) else d[k] for k in ('value','ms_per_step','x_realtime_per_instance')}, 'learn frac %.3f avg %.3f ms'%(d['roofline']['frac'], d['roofline']['avg_launch_ms']), 'path %.3f'%d['roofline_path']['frac'], 'e2e %.3g'%d['e2e']['value'])
+except Exception as e:
+    print(sys.argv[1], 'parse failed', e); print(open(sys.argv[1].replace('.json','.err')).read()[-1500:])
+PY
+}
+for v in "" "--persistent" "--persistent --chain 384,2,1,256,2,128,3" "--persistent --chain 512,2,1,128,2,128,3" "--persistent --chain 256,3,1,128,2,128,3" "--persistent --chain 256,2,1,256,1,128,6" "--persistent --chain 256,2,2,128,2,128,3" "--persistent --chain-lookahead 3"; do
+  f="gpurun_out/r2k_bench_c5$(echo $v | tr -d ' ').json"
+  timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu --window-ms 250 $v > "$f" 2> "${f%.json}.err"; show "$f"
+done
+for wl in c1_x1024 c3_x64; do for v in "" "--persistent"; do
+  f="gpurun_out/r2k_bench_${wl}$(echo $v | tr -d ' ').json"
+  timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu --window-ms 250 --workload $wl $v > "$f" 2> "${f%.json}.err"; show "$f"
+done; done

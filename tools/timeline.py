@@ -26,8 +26,8 @@ def main():
     ap.add_argument("--learn-lazy", type=int, default=0, help="experimental event-driven learning (DESIGN 11.1)")
     ap.add_argument("--chain", default=None)
     ap.add_argument("--chain-lookahead", type=int, default=0)
-    ap.add_argument("--persistent", action="store_true")
-    ap.add_argument("--no-waves", action="store_true")
+    ap.add_argument("--scheduler", default="auto", choices=["auto", "chain", "graph"])
+    ap.add_argument("--waves", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.json"))
     a = ap.parse_args()
     wl = bench.WORKLOADS[a.workload]
@@ -49,7 +49,7 @@ def main():
     else:
         net = SparseNetwork(n, ne, rowptr, post, w, delay, n_instances=n_inst, dtype="f32", mode="fast", noise="philox",
                         max_delay=dmax, noise_seed=10, exp_flags=2 | a.exp_flags, learn_blocks=a.learn_blocks,
-                            learn_async=a.learn_async, learn_lazy=a.learn_lazy, chain=a.chain, persistent=a.persistent, chain_lookahead=a.chain_lookahead, wave_kernels=not a.no_waves)
+                            learn_async=a.learn_async, learn_lazy=a.learn_lazy, chain=a.chain, persistent={'auto': None, 'chain': True, 'graph': False}[a.scheduler], chain_lookahead=a.chain_lookahead, wave_kernels=a.waves)
     W = a.window_ms
     for kw in range(a.warm):
         tr, da = bench.window_inputs(kw, W)
