@@ -240,6 +240,15 @@ __device__ __forceinline__ void tl_end(unsigned long long* tl, int cls, int k) {
     asm volatile("red.global.max.u64 [%0], %1;" ::"l"(&tl[kTlClasses * kTlSteps + cls * kTlSteps + k + 1]), "l"(gtime_ns()) : "memory");
 }
 
+__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+// timeline diagnostics of the persistent chain: which SM hosts how many blocks of a role (end half of class `cls`,
+// indexed by SM), and how long the neuron block of every SM needs for two chosen steps (class 15: begin half = step
+// kTlProbeA, end half = step kTlProbeB)
+constexpr int kTlProbeA = 27, kTlProbeB = 33;
+__device__ __forceinline__ void tl_count_sm(unsigned long long* tl, int cls) {
+  if (tl && threadIdx.x == 0 && smid() < (uint32_t)kTlSteps) atomicAdd(&tl[kTlClasses * kTlSteps + cls * kTlSteps + smid()], 1ull);
+}
+
 // Per-window inputs/outputs.  Lives in device memory so that a captured graph never has to be
 // re-parameterised: kernels receive (net, ctx pointer, k) and derive everything else.
 template <typename T>
@@ -1787,6 +1796,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
     tl_end(p.tl, 6, k);
     tl_begin(p.tl, 0, k);
     tl_begin(p.tl, 7, k);
+    const unsigned long long t_step0 = (p.tl && (k == kTlProbeA || k == kTlProbeB)) ? gtime_ns() : 0ull;
     const int64_t t = t0 + k;
     const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
     uint32_t* __restrict__ bits = p.bits + (size_t)slot * p.W;
@@ -2024,6 +2034,8 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
       }
     }
     tl_end(p.tl, 9, k);
+    if (t_step0 && tid == 0 && smid() < (uint32_t)kTlSteps)
+      p.tl[(k == kTlProbeA ? 0 : kTlClasses * kTlSteps) + 15 * kTlSteps + smid()] = gtime_ns() - t_step0;
     if (tid == 0) chain_arrive(ctl, kcNeuron);
     tl_end(p.tl, 0, k);
     tl_begin(p.tl, 10, k);
@@ -2229,6 +2241,7 @@ chain_synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl*
   const int n = cx->n_steps;
   // two groups of blocks take alternate steps (group k & 1 takes step k): a step is a chain of dependent memory
   // round trips that neither group can shorten, but two steps in flight double the role's throughput
+  tl_count_sm(p.tl, 13);
   const uint32_t grp = d.SG == 2 ? (blockIdx.x & 1u) : 0u;
   // (no run-time index into d.SBg: the whole by-value ChainDims would be copied to local memory)
   const uint32_t bid = d.SG == 2 ? (blockIdx.x >> 1) : blockIdx.x, nblk = grp ? d.SBg[1] : d.SBg[0], region = blockIdx.x;
@@ -2396,7 +2409,13 @@ chain_remote_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
   __shared__ int s_ok;
   const int n = cx->n_steps;
   for (int k = 0; k < n; ++k) {
-    if (threadIdx.x == 0) s_ok = chain_wait(ctl, kcNeuron, d.NB * (uint32_t)k, 0) ? 1 : 0;
+    if (threadIdx.x == 0) {
+      // neuron(k-1) on every block (Iacc cleared, the step's list slot reset) and remote(k-1) on every block (the
+      // spike record's offset of step k is the final count of step k-1)
+      const int which[2] = {kcNeuron, kcRemote};
+      const uint32_t target[2] = {d.NB * (uint32_t)k, d.RB * (uint32_t)k};
+      s_ok = chain_wait_all<2>(ctl, which, target, 0) ? 1 : 0;
+    }
     __syncthreads();
     if (!s_ok) return;
     remote_body<T>(p, cx, k, 1, blockIdx.x, d.RB, sched[d.o_nd + k], d.ring);
@@ -2460,6 +2479,7 @@ chain_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* _
   __shared__ int s_ok;
   const uint32_t S = (uint32_t)d.pass_stages, bid = blockIdx.x, LB = d.LB;
   const int n = cx->n_steps;
+  tl_count_sm(p.tl, 14);
   if (threadIdx.x == 0) {
     for (uint32_t s_ = 0; s_ < S; ++s_) mbar_init(&mbar[s_], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -65,6 +65,7 @@ def main():
     L.check(L.load().snn_debug_timeline(net._h, buf.ctypes.data_as(C.c_void_p), buf.size))
     tl = buf.reshape(2, K, S)
     valid = tl[1] > 0
+    valid[13:16, :] = False   # classes 13-15 carry per-SM diagnostics of the chain, not (begin, end) stamps
     t0 = int(tl[0][valid].min())
     rows = []
     for c in range(K):
@@ -72,6 +73,21 @@ def main():
             if valid[c, k]:
                 rows.append({"cls": CLS[c], "k": k - 1, "start_us": (int(tl[0, c, k]) - t0) / 1e3,
                              "end_us": (int(tl[1, c, k]) - t0) / 1e3})
+    # persistent chain: blocks of the synapse / learn role per SM and the neuron block's duration of two probe steps
+    if int(tl[1, 13].sum()) > 0:
+        syn, lrn = tl[1, 13].astype(np.int64), tl[1, 14].astype(np.int64)
+        da, db = tl[0, 15].astype(np.float64), tl[1, 15].astype(np.float64)
+        da[tl[0, 15] == np.uint64(0xFFFFFFFFFFFFFFFF)] = np.nan
+        sms = [i for i in range(S) if syn[i] or lrn[i] or not np.isnan(da[i])]
+        print("per SM: synapse blocks, learn blocks, neuron-block time of step 27 / 33 (us)")
+        import collections
+        grp = collections.defaultdict(list)
+        for i in sms:
+            grp[(int(syn[i]), int(lrn[i]))].append((da[i] / 1e3, db[i] / 1e3))
+        for key in sorted(grp):
+            v = np.array(grp[key])
+            print(f"  syn={key[0]} learn={key[1]}: {len(v):3d} SMs  step27 mean {np.nanmean(v[:,0]):6.1f} max {np.nanmax(v[:,0]):6.1f}   step33 mean {np.nanmean(v[:,1]):6.1f} max {np.nanmax(v[:,1]):6.1f}")
+        valid[13:16, :] = False
     rows.sort(key=lambda r: r["start_us"])
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump({"workload": a.workload, "window_ms": W, "device_ms": st.device_ms, "rows": rows}, open(a.out, "w"))
