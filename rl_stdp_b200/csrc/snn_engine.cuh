@@ -1774,9 +1774,16 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
   __syncthreads();
   unsigned long long spikes_acc = 0;  // block 0, thread 0
 
+  const T k_a_exc = p.a_exc, k_a_inh = p.a_inh, k_d_exc = p.d_exc, k_d_inh = p.d_inh, k_vthresh = p.vthresh, k_v_reset = p.v_reset;
+  const bool k_thr_ge = p.threshold_ge != 0, k_homeo = p.homeostasis != 0;
+  // timeline = 2: the phase classes 6-12 are stamped by ONE block (the middle one) — a block's own step, not the
+  // first-begin / last-end envelope over all blocks; 11 / 12 then are the two halves of this role's spiker wave
+  const bool solo = (p.exp_flags & 1024) != 0;
+  unsigned long long* const tq = (!solo || bid == d.NB / 2) ? p.tl : nullptr;
+  unsigned long long* const ts = solo ? tq : nullptr;
   for (int k = 0; k <= n; ++k) {
     const bool euler = k > 0, detect = k < n;
-    tl_begin(p.tl, 6, k);
+    tl_begin(tq, 6, k);
     if (tid == 0) {
       // neuron(k-1) on every block | the push phases Euler(k-1) consumes | learn!(k-1) begun | ltp not more than kLag
       // steps behind | (partitioned) the peers' spikes of step k-1 pushed and listed
@@ -1793,9 +1800,9 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
     }
     __syncthreads();
     if (!s_ok) break;
-    tl_end(p.tl, 6, k);
+    tl_end(tq, 6, k);
     tl_begin(p.tl, 0, k);
-    tl_begin(p.tl, 7, k);
+    tl_begin(tq, 7, k);
     const unsigned long long t_step0 = (p.tl && (k == kTlProbeA || k == kTlProbeB)) ? gtime_ns() : 0ull;
     const int64_t t = t0 + k;
     const int slot = (cx->slot0 + k) % p.R, prev = wrap_slot(slot - 1, p.R);
@@ -1867,14 +1874,12 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         }
       }
     }
-    if (p.tl) { __syncthreads(); tl_end(p.tl, 7, k); tl_begin(p.tl, 8, k); }
+    if (p.tl) { __syncthreads(); tl_end(tq, 7, k); tl_begin(tq, 8, k); }
     // ---- phase 2: Euler(t-1) and detect(t) out of shared memory
     for (uint32_t ql = tid; ql < nq; ql += TN) {  // warp-uniform trip count (nq and TN are multiples of 32)
       const uint32_t q = qb0 + ql, j0 = q << 2;
-      Vec4<T> I;
-      if (euler) I = ld4(sn + 4 * ql);
       Vec4<T> v = ld4(sv + 4 * ql), u = ld4(su + 4 * ql), ho;
-      if (detect && p.homeostasis) ho = ld4cg(p.ho + j0);
+      if (detect && k_homeo) ho = ld4cg(p.ho + j0);
       const uint32_t l0 = p.B == 1 ? j0 : j0 % Nper;
       unsigned excm = 0, actm = 0;
 #pragma unroll
@@ -1884,10 +1889,13 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         excm |= (l < Ne ? 1u : 0u) << c;
         actm |= (j0 + c < N ? 1u : 0u) << c;
       }
+      // the four neurons of a quad are four independent dependency chains: selects instead of branches, so that the
+      // compiler interleaves them (a block has few warps: the role is bound by instruction latency, not by issue slots)
       if (euler) {
+        const Vec4<T> I = ld4(sn + 4 * ql);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          if (!((actm >> c) & 1u)) continue;
+          const bool act = (actm >> c) & 1u, exc = (excm >> c) & 1u;
           T vv = v.x[c];
           // v = v + 0.5*((0.04*v+5)*v + 140 - u + I), twice (new_net.jl:120-121)
 #pragma unroll
@@ -1897,33 +1905,31 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
             x = O::add(O::sub(x, u.x[c]), I.x[c]);
             vv = O::add(vv, O::mul((T)0.5, x));
           }
-          v.x[c] = vv;
-          u.x[c] = O::add(u.x[c], O::mul(((excm >> c) & 1u) ? p.a_exc : p.a_inh, O::sub(O::mul((T)0.2, vv), u.x[c])));  // :122
+          const T un = O::add(u.x[c], O::mul(exc ? k_a_exc : k_a_inh, O::sub(O::mul((T)0.2, vv), u.x[c])));  // :122
+          v.x[c] = act ? vv : v.x[c];
+          u.x[c] = act ? un : u.x[c];
         }
       }
       if (detect) {
         unsigned nib = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          bool s = false;
-          if ((actm >> c) & 1u) {
-            const T x = p.homeostasis ? O::sub(v.x[c], ho.x[c]) : v.x[c];
-            s = p.threshold_ge ? (x >= p.vthresh) : (x > p.vthresh);
-            if (s) {
-              v.x[c] = p.v_reset;
-              u.x[c] = O::add(u.x[c], ((excm >> c) & 1u) ? p.d_exc : p.d_inh);
-            }
-          }
-          if (p.homeostasis) {
+          const bool act = (actm >> c) & 1u, exc = (excm >> c) & 1u;
+          const T x = k_homeo ? O::sub(v.x[c], ho.x[c]) : v.x[c];
+          const bool s = act && (k_thr_ge ? (x >= k_vthresh) : (x > k_vthresh));
+          const T ur = O::add(u.x[c], exc ? k_d_exc : k_d_inh);
+          v.x[c] = s ? k_v_reset : v.x[c];
+          u.x[c] = s ? ur : u.x[c];
+          if (k_homeo) {
             uint32_t l = l0 + c;
             if (l >= Nper) l -= Nper;
             T h = ho.x[c];
-            if (s && (((excm >> c) & 1u) || p.ho_inh) && (int64_t)l >= p.ho_from) h = O::add(h, p.theta);
+            if (s && (exc || p.ho_inh) && (int64_t)l >= p.ho_from) h = O::add(h, p.theta);
             ho.x[c] = O::mul(h, p.ttheta);
           }
           nib |= (s ? 1u : 0u) << c;
         }
-        if (p.homeostasis) st4(p.ho + j0, ho);
+        if (k_homeo) st4(p.ho + j0, ho);
         st4(sv + 4 * ql, v);
         st4(su + 4 * ql, u);
         unsigned word = nib << ((lane & 7) << 2);  // 8 lanes x 4 neurons = one 32-bit bitmap word
@@ -1951,12 +1957,14 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         st4(su + 4 * ql, u);
       }
     }
+    if (ts) { __syncthreads(); tl_end(ts, 8, k); tl_begin(ts, 5, k); }  // (solo timeline: class 5 = retire + block barrier)
     if (retire_cnt > 0) {  // the spikes of step t - G leave the part of the bitmap ring a reader may rely on
       const int32_t* __restrict__ rl = p.spk_list + (size_t)(xr % p.R) * p.Nld;
       for (uint32_t q = bid * TN + tid; q < (uint32_t)retire_cnt; q += d.NB * TN) p.old_last[__ldcg(rl + q)] = (int32_t)xr;
     }
     __syncthreads();
-    tl_end(p.tl, 8, k); tl_begin(p.tl, 9, k);
+    if (ts) tl_end(ts, 5, k); else tl_end(tq, 8, k);
+    tl_begin(tq, 9, k);
     // ---- phase 3: this block's spikers, all in flight together (a chain of dependent memory round trips per
     // spiker: done as a small wave — one thread per spiker fetches the bounds of its delay-1 segment, then one thread
     // per SYNAPSE pushes it: delay 1 feeds the Euler update of this very step (new_net.jl:116-121), delays up to the
@@ -1971,6 +1979,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         const int32_t h_prev = (int)tid < nspk ? __ldcg(p.hist + ((qb0 << 2) + s_spk[tid])).x : 0;
         for (int r0 = 0; r0 < nspk; r0 += kSpkWave) {
           const int nr = min(kSpkWave, nspk - r0);
+          tl_begin(ts, 11, k);
           for (int x = (int)tid; x < nr; x += (int)TN) {
             const uint4 sg = p.segL[(qb0 << 2) + s_spk[r0 + x]];
             s_ps0[x] = sg.x; s_pb1[x] = sg.y; s_pb2[x] = sg.z;
@@ -1997,6 +2006,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
           }
           __syncthreads();
           const uint32_t V = s_poff[nr];
+          tl_end(ts, 11, k); tl_begin(ts, 12, k);
           for (uint32_t v0 = tid; v0 < V; v0 += 4 * TN) {
             int32_t pj[4]; typename DevNet<T>::T2 pw[4]; bool fly[4]; uint32_t pi[4], pd[4];
 #pragma unroll
@@ -2022,6 +2032,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
             }
           }
           __syncthreads();
+          tl_end(ts, 12, k);
         }
         const int base = s_base;
         for (int w = (int)tid; w < nspk; w += (int)TN) {
@@ -2033,12 +2044,14 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         __syncthreads();
       }
     }
-    tl_end(p.tl, 9, k);
+    tl_end(tq, 9, k);
     if (t_step0 && tid == 0 && smid() < (uint32_t)kTlSteps)
       p.tl[(k == kTlProbeA ? 0 : kTlClasses * kTlSteps) + 15 * kTlSteps + smid()] = gtime_ns() - t_step0;
+    tl_begin(ts, 4, k);  // (solo timeline: class 4 = the fence + counter update of the hand-over)
     if (tid == 0) chain_arrive(ctl, kcNeuron);
+    tl_end(ts, 4, k);
     tl_end(p.tl, 0, k);
-    tl_begin(p.tl, 10, k);
+    tl_begin(tq, 10, k);
     // ---- off the critical path: the noise Euler(k) will add, 13*(U-0.5) (new_net.jl:111)
     if (detect && philox) {
       for (uint32_t ql = tid; ql < nq; ql += TN) {
@@ -2051,7 +2064,7 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
         st4(sn + 4 * ql, nz);
       }
     }
-    if (p.tl) { __syncthreads(); tl_end(p.tl, 10, k); }
+    if (p.tl) { __syncthreads(); tl_end(tq, 10, k); }
   }
   __syncthreads();
   if (bid == 0 && tid == 0) p.counters[0] += spikes_acc;
@@ -2121,7 +2134,7 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
   unsigned long long n_ev = 0;
   for (uint32_t r0 = lo; r0 < hi; r0 += kWaveItems) {
     const uint32_t nitem = min((uint32_t)kWaveItems, hi - r0);
-    if (LTD) tl_begin(p.tl, 11, k);
+    if (LTD && !(p.exp_flags & 1024)) tl_begin(p.tl, 11, k);
     // ---- stage A: item -> (LTD segment, push segments, spiker)
     for (uint32_t x = tid; x < nitem; x += TB) {
       const uint32_t item = r0 + x;
@@ -2166,7 +2179,7 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
     }
     __syncthreads();
     const uint32_t V = sm.off[nitem];
-    if (LTD) { tl_end(p.tl, 11, k); tl_begin(p.tl, 12, k); }
+    if (LTD && !(p.exp_flags & 1024)) { tl_end(p.tl, 11, k); tl_begin(p.tl, 12, k); }
     // ---- stage B: one thread per synapse visit, two in flight
     for (uint32_t v0 = tid; v0 < V; v0 += 2 * TB) {
       uint32_t e[2], j[2], inst[2], ibs[2], ahead[2]; bool ok[2], isl[2], pl[2], fly[2]; typename DevNet<T>::T2 ws[2]; int2 hq[2];
@@ -2208,7 +2221,7 @@ __device__ __forceinline__ void synapse_wave(const DevNet<T>& p, const WindowCtx
       }
     }
     __syncthreads();
-    if (LTD) tl_end(p.tl, 12, k);
+    if (LTD && !(p.exp_flags & 1024)) tl_end(p.tl, 12, k);
   }
   if (LTD) {
     for (int o = 16; o > 0; o >>= 1) n_ev += __shfl_down_sync(0xffffffffu, n_ev, o);
@@ -2445,10 +2458,18 @@ __device__ __forceinline__ void chain_replay(const DevNet<T>& p, const ChainDims
       const uint32_t rr = base + x * nblk, r = rr < d.SB ? rr : p.log_ltp_base + (rr - d.SB);
       const uint32_t nn = cnt < p.log_region_cap ? cnt : p.log_region_cap;
       const LogEntry<T>* __restrict__ lg = p.dlog + (size_t)r * p.log_region_cap;
-      for (uint32_t q = threadIdx.x; q < nn; q += blockDim.x) {
-        LogEntry<T> le;
-        le.e = __ldcg(&lg[q].e); le.d = __ldcg(&lg[q].d);
-        red_add(&w[le.e].y, le.d);
+      // four entries of a thread in flight at once (an entry at a time made the replay a chain of ~15 dependent
+      // round trips per region: 33 us per learn period at C5)
+      for (uint32_t q0 = threadIdx.x; q0 < nn; q0 += 4 * blockDim.x) {
+        LogEntry<T> le[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t q = q0 + u * blockDim.x;
+          if (q < nn) { le[u].e = __ldcg(&lg[q].e); le[u].d = __ldcg(&lg[q].d); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (q0 + u * blockDim.x < nn) red_add(&w[le[u].e].y, le[u].d);
       }
       if (threadIdx.x == 0) p.log_cnt[(size_t)r * kLogStride] = 0u;
     }
@@ -2469,7 +2490,7 @@ __device__ __forceinline__ void chain_replay(const DevNet<T>& p, const ChainDims
 // tiles | frontier = all.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kChainLearnThreads)
+__global__ void __launch_bounds__(kChainLearnThreads, 12)  // <= 40 registers: two blocks per SM fit beside the other roles
 chain_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __restrict__ ctl,
                    const int32_t* __restrict__ sched, const ChainDims d) {
   typedef typename DevNet<T>::T2 T2;
@@ -2545,6 +2566,32 @@ chain_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* _
       atomicAdd(&ctl->w[kcPassCnt * 32], 1u);
     }
     if (bid == 0) tl_end(p.tl, 3, k);
+    // ---- early replay.  The sd updates logged while the pass was in flight are folded in NOW, in the idle time
+    // before the next learn step, instead of on its critical path (the replay sat between the last LTD / LTP of a
+    // learn step and `begun`: ~20 us of every learn period at C5 during which the neuron role waits).  Only waves
+    // that took their view of the frontier before it read `all` can still append: those of the steps whose neuron
+    // role had completed when every block of this role knows the frontier is published.
+    if (!role_barrier()) return;
+    {
+      __shared__ uint32_t s_done;
+      if (threadIdx.x == 0) s_done = min(ld_acquire_u32(&ctl->w[kcNeuron * 32]) / d.NB, (uint32_t)n);  // steps 0 .. s_done-1
+      __syncthreads();
+      const int sd_ = (int)s_done;
+      if (sd_ >= 1) {
+        if (threadIdx.x == 0) {
+          const int which[3] = {kcLtd, kcLtd1, kcLtp};
+          const uint32_t target[3] = {d.SBg[0] * syn_ltd_phases(d, 0, sd_ - 1), d.SBg[1] * syn_ltd_phases(d, 1, sd_ - 1), d.PB * (uint32_t)sd_};
+          s_ok = chain_wait_all<3>(ctl, which, target, 100) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_ok) return;
+        __syncthreads();
+      }
+      unsigned long long* const t4 = (p.exp_flags & 1024) ? nullptr : p.tl;  // (timeline class 4 on one GPU: the early replay)
+      tl_begin(t4, 4, k);
+      chain_replay<T>(p, d, bid, LB);
+      tl_end(t4, 4, k);
+    }
   }
 }
 
@@ -2788,7 +2835,7 @@ class Engine : public IEngine {
   int apply_options(std::string& err) {
     DevNet<T>& p = p_;
     use_graph_ = opt_.graph != 0;
-    p.exp_flags = (opt_.timeline ? 2 : 0) | (opt_.serialise_pass ? 4 : 0) | (opt_.neuron_blocks_256 ? 8 : 0) | (opt_.lsu_pass ? 512 : 0);
+    p.exp_flags = (opt_.timeline ? 2 : 0) | (opt_.timeline == 2 ? 1024 : 0) | (opt_.serialise_pass ? 4 : 0) | (opt_.neuron_blocks_256 ? 8 : 0) | (opt_.lsu_pass ? 512 : 0);
     if (opt_.timeline && !p.tl) SNN_CUDA_OK(cudaMalloc(&p.tl, 2 * kTlClasses * kTlSteps * sizeof(unsigned long long)));
     if (!opt_.timeline && p.tl) { cudaFree(p.tl); p.tl = nullptr; }
     return SNN_OK;
@@ -3874,7 +3921,7 @@ bool Engine<T>::chain_plan(bool with_learn, std::string* why) {
   const int thrP = std::min(256, std::max(32, tune[3] / 32 * 32)), thrL = kChainLearnThreads;  // (tune[5] is not used any more)
   int S = std::min(kPassMaxStages, std::max(2, tune[6]));
   size_t smem_l = (size_t)S * kPassChunkBytes;
-  const bool lean = thrN > 256;  // the 40-register build of the neuron role
+  const bool lean = thrN > 256 && tune[5] != 64;  // the 40-register build of the neuron role ("chain_learn_threads" = 64: sweeps of the 64-register build with more threads)
   cudaFuncAttributes fa[5];
   {
     const ChainKernelInfo& ki = chain_kernel_info();
@@ -4002,7 +4049,7 @@ int Engine<T>::launch_chain(const StepArgs& a, std::string& err) {
   SNN_CUDA_OK(cudaStreamWaitEvent(s2, evFork, 0));
   SNN_CUDA_OK(cudaStreamWaitEvent(s3, evFork, 0));
   // the neuron role first: its blocks (one per SM) hand a step over among themselves and must all be resident
-  if (d.thrN > 256) chain_neuron_kernel<T, 3><<<d.NB, d.thrN, chain_smem_neuron_, sN>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
+  if (d.thrN > 256 && opt_.chain[5] != 64) chain_neuron_kernel<T, 3><<<d.NB, d.thrN, chain_smem_neuron_, sN>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
   else chain_neuron_kernel<T, 2><<<d.NB, d.thrN, chain_smem_neuron_, sN>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
   chain_synapse_kernel<T><<<d.SB, 256, 0, s2>>>(p, d_ctx_, d_chain_, b_sched_.as<int32_t>(), d);
   chain_ltp_kernel<T><<<d.PB, d.thrP, 0, s3>>>(p, d_ctx_, d_chain_, d);

@@ -66,6 +66,8 @@ class SparseNetwork:
         for bit, name in ((2, "timeline"), (4, "serialise_learn_pass"), (8, "neuron_blocks_256"), (512, "lsu_pass")):
             if exp_flags & bit:
                 opts[name] = 1
+        if exp_flags & 1024:
+            opts["timeline"] = 2       # chain phases stamped by one block of the role, not the envelope over all blocks
         opts["learn_async"] = {"auto": 0, "off": 1, "force": 2}[params.pop("learn_async", "auto")]
         opts["learn_log_cap"] = int(params.pop("learn_log_cap", 0))
         # opt-in, production mode only: event-driven learning, one dense re-basing pass

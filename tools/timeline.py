@@ -28,8 +28,11 @@ def main():
     ap.add_argument("--chain-lookahead", type=int, default=0)
     ap.add_argument("--scheduler", default="auto", choices=["auto", "chain", "graph"])
     ap.add_argument("--waves", action="store_true")
+    ap.add_argument("--solo", action="store_true", help="chain phases (classes 6-12) of ONE neuron block instead of the envelope over all")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.json"))
     a = ap.parse_args()
+    if a.solo:
+        a.exp_flags |= 1024
     wl = bench.WORKLOADS[a.workload]
     n, ne, fan, dmax = wl[:4]
     n_inst = wl[4] if len(wl) > 4 else 1
