@@ -511,8 +511,7 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
         st4(I_prev + j0, z);
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (!act[c]) continue;
+      for (int c = 0; c < 4; ++c) {  // selects, no branches: four independent dependency chains the compiler interleaves
         T vv = v.x[c];
         // v = v + 0.5*((0.04*v+5)*v + 140 - u + I), twice (new_net.jl:120-121)
 #pragma unroll
@@ -522,9 +521,10 @@ __device__ __forceinline__ void neuron_body(const DevNet<T>& p, const WindowCtx<
           x = O::add(O::sub(x, u.x[c]), I.x[c]);
           vv = O::add(vv, O::mul((T)0.5, x));
         }
-        v.x[c] = vv;
         // u = u + a*(0.2*v - u) (new_net.jl:122)
-        u.x[c] = O::add(u.x[c], O::mul(exc[c] ? p.a_exc : p.a_inh, O::sub(O::mul((T)0.2, vv), u.x[c])));
+        const T un = O::add(u.x[c], O::mul(exc[c] ? p.a_exc : p.a_inh, O::sub(O::mul((T)0.2, vv), u.x[c])));
+        v.x[c] = act[c] ? vv : v.x[c];
+        u.x[c] = act[c] ? un : u.x[c];
       }
     }
     if (DETECT) {
@@ -1843,36 +1843,20 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
       }
     }
 
-    // ---- phase 1: total current of Euler(t-1) = noise + Iacc (new_net.jl:111,116-118), gathered into sn with every
-    // load of the thread in flight at once; Iacc is cleared for the pushes of step t+1.  (The same thread consumes the
-    // same quads in phase 2: no barrier in between.)
+    // ---- phase 1: the Iacc quads of this block, global -> shared memory (sn) as asynchronous 16-byte copies: every
+    // quad of a thread is in flight at once and none of them occupies a register (the register version had to go in
+    // two batches of four — twice the L2 latency under the learn pass's traffic — and a batch of eight spilled).
+    // A thread waits for its own copies only and consumes the same quads in phase 2: no barrier in between.
     if (euler) {
-      for (uint32_t qr = tid; qr < nq; qr += 4 * TN) {
-        Vec4<T> Iq[4];
+      for (uint32_t ql = tid; ql < nq; ql += TN) {
+        const T* src = I_prev + ((size_t)(qb0 + ql) << 2);
+        const uint32_t dst = smem_u32(sn + 4 * ql);
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const uint32_t ql = qr + it * TN;
-          if (ql < nq) Iq[it] = ld4cg(I_prev + ((size_t)(qb0 + ql) << 2));
-        }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const uint32_t ql = qr + it * TN;
-          if (ql >= nq) break;
-          const uint32_t j0 = (qb0 + ql) << 2;
-          Vec4<T> tot = Iq[it];
-          if (p.noise_mode == SNN_NOISE_REPLAY) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) if (j0 + c < N) tot.x[c] = O::add(noise_prev[j0 + c], tot.x[c]);
-          } else if (philox) {
-            const Vec4<T> nz = ld4(sn + 4 * ql);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tot.x[c] = O::add(nz.x[c], tot.x[c]);
-          }
-          st4(sn + 4 * ql, tot);
-          Vec4<T> z; z.x[0] = z.x[1] = z.x[2] = z.x[3] = (T)0;
-          st4(I_prev + j0, z);
-        }
+        for (uint32_t o = 0; o < 4 * sizeof(T); o += 16)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(reinterpret_cast<const char*>(src) + o) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     if (p.tl) { __syncthreads(); tl_end(tq, 7, k); tl_begin(tq, 8, k); }
     // ---- phase 2: Euler(t-1) and detect(t) out of shared memory
@@ -1892,7 +1876,25 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
       // the four neurons of a quad are four independent dependency chains: selects instead of branches, so that the
       // compiler interleaves them (a block has few warps: the role is bound by instruction latency, not by issue slots)
       if (euler) {
-        const Vec4<T> I = ld4(sn + 4 * ql);
+        // total current of Euler(t-1) = noise + Iacc (new_net.jl:111,116-118); Iacc is cleared for the pushes that
+        // arrive `ring` steps later
+        Vec4<T> I = ld4(sn + 4 * ql);
+        if (p.noise_mode == SNN_NOISE_REPLAY) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (j0 + c < N) I.x[c] = O::add(noise_prev[j0 + c], I.x[c]);
+        } else if (philox) {  // 13*(U-0.5) (new_net.jl:111): a counter-based draw keyed by (seed, step, quad)
+          const int64_t tp = t - 1;
+          const uint4 o = philox4x32_10(make_uint4(q, 0u, (uint32_t)tp, (uint32_t)((uint64_t)tp >> 32)),
+                                        make_uint2((uint32_t)p.noise_seed, (uint32_t)(p.noise_seed >> 32)));
+          I.x[0] = O::add((T)philox_to_noise(o.x, p.noise_amp), I.x[0]);
+          I.x[1] = O::add((T)philox_to_noise(o.y, p.noise_amp), I.x[1]);
+          I.x[2] = O::add((T)philox_to_noise(o.z, p.noise_amp), I.x[2]);
+          I.x[3] = O::add((T)philox_to_noise(o.w, p.noise_amp), I.x[3]);
+        }
+        {
+          Vec4<T> z; z.x[0] = z.x[1] = z.x[2] = z.x[3] = (T)0;
+          st4(I_prev + j0, z);
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const bool act = (actm >> c) & 1u, exc = (excm >> c) & 1u;
@@ -2051,20 +2053,6 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
     if (tid == 0) chain_arrive(ctl, kcNeuron);
     tl_end(ts, 4, k);
     tl_end(p.tl, 0, k);
-    tl_begin(tq, 10, k);
-    // ---- off the critical path: the noise Euler(k) will add, 13*(U-0.5) (new_net.jl:111)
-    if (detect && philox) {
-      for (uint32_t ql = tid; ql < nq; ql += TN) {
-        const uint32_t q = qb0 + ql;
-        const uint4 o = philox4x32_10(make_uint4(q, 0u, (uint32_t)t, (uint32_t)((uint64_t)t >> 32)),
-                                      make_uint2((uint32_t)p.noise_seed, (uint32_t)(p.noise_seed >> 32)));
-        Vec4<T> nz;
-        nz.x[0] = (T)philox_to_noise(o.x, p.noise_amp); nz.x[1] = (T)philox_to_noise(o.y, p.noise_amp);
-        nz.x[2] = (T)philox_to_noise(o.z, p.noise_amp); nz.x[3] = (T)philox_to_noise(o.w, p.noise_amp);
-        st4(sn + 4 * ql, nz);
-      }
-    }
-    if (p.tl) { __syncthreads(); tl_end(tq, 10, k); }
   }
   __syncthreads();
   if (bid == 0 && tid == 0) p.counters[0] += spikes_acc;
@@ -2540,8 +2528,12 @@ chain_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* _
     __syncthreads();
     if (!s_ok) return;
     __syncthreads();
-    if (i > 0) chain_replay<T>(p, d, bid, LB);
-    if (!role_barrier()) return;
+    // (i > 0: the log is empty — the early replay below has folded it in and was followed by the role's barrier, and
+    // nothing is appended between `frontier = all` and the next `begun`)
+    if (i == 0) {
+      chain_replay<T>(p, d, bid, LB);  // whatever an earlier window's scheduler may have left
+      if (!role_barrier()) return;
+    }
     if (last) {
       if (bid == 0 && threadIdx.x == 0) p.lc->spilled = 0u;
       break;
@@ -2591,6 +2583,7 @@ chain_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* _
       tl_begin(t4, 4, k);
       chain_replay<T>(p, d, bid, LB);
       tl_end(t4, 4, k);
+      if (!role_barrier()) return;  // every block's share is in before the next learn! flips the buffers
     }
   }
 }
@@ -3914,7 +3907,7 @@ bool Engine<T>::chain_plan(bool with_learn, std::string* why) {
   // work-proportional block counts: small nets get small grids (every waiting block polls the counters)
   const int64_t ev_guess = std::max<int64_t>(1, p.E / 64);  // synapse visits per step at ~1.5 % of the neurons firing
   // role footprints per SM (defaults measured on C5; snn_set_param "chain_*" overrides them for sweeps)
-  int tune[7] = {256, 2, 1, 256, 2, 128, 3};
+  int tune[7] = {256, 2, 1, 128, 2, 128, 3};
   for (int q = 0; q < 7; ++q) if (opt_.chain[q] > 0) tune[q] = opt_.chain[q];
   const int thrN = std::min(kChainNeuronThreads, std::max(32, tune[0] / 32 * 32));
   int syn_per_sm = tune[1], ltp_per_sm = tune[2], learn_per_sm = tune[4];
