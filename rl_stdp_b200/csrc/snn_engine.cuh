@@ -1598,15 +1598,16 @@ __global__ void learn_spill_reset_kernel(DevNet<T> p) { p.lc->spilled = 0u; }
 //
 //   chain_neuron_kernel   one block per SM; v and u of its neurons stay in SHARED MEMORY for the
 //                         whole window, so a step touches only Iacc (read + clear, L2-resident) and
-//                         the spike bookkeeping: 8 B per neuron and ms instead of 36.  The Philox
-//                         noise of the NEXT step is generated after the block has signalled the
-//                         current one — off the critical path, while the device-wide hand-off
-//                         (1.3 us on a B200, tools/barrier_probe.cu) is in flight.
+//                         the spike bookkeeping: 8 B per neuron and ms instead of 36.  Iacc is staged
+//                         into shared memory with cp.async (every quad of a thread in flight, no
+//                         registers), the Philox draw is formed inside the Euler loop, and the four
+//                         neurons of a quad are written as selects so that their dependency chains
+//                         interleave (a block has 8 warps: the role is bound by latency, not issue).
 //   chain_synapse_kernel  LTD + next-step pushes of step k as soon as neuron(k) is complete
 //   chain_ltp_kernel      LTP of step k
 //   chain_learn_kernel    the asynchronous TMA pass of every learn step of the window (begin, tiles,
-//                         frontier = all, log replay), same double-buffer / frontier / log protocol
-//                         as the graph path
+//                         frontier = all, early replay of the log), same double-buffer / frontier /
+//                         log protocol as the graph path
 //
 // Dependencies (the same as the graph path, as counters; `done` counters count BLOCKS, so "step k
 // complete" reads  counter >= blocks * (k + 1)):
@@ -1738,7 +1739,7 @@ __device__ __forceinline__ void chain_push_delay1(const DevNet<T>& p, const WVie
 
 // ---------------------------------------------------------------------------------------------
 // chain_neuron_kernel: Euler(k-1) + detect(k) for k = 0..n over a block's own neurons (new_net.jl:111-114,
-// 120-123,130-131), state resident in shared memory: sv / su [4*qpb], sn [4*qpb] the noise of the next Euler.
+// 120-123,130-131), state resident in shared memory: sv / su [4*qpb], sn [4*qpb] the currents of this Euler.
 // ---------------------------------------------------------------------------------------------
 // MINB: resident blocks per SM the register allocation is capped for (2: 64 registers, for blocks of <= 256
 // threads; 3: 40 registers with some spills, for 384-512 threads) — the role shares the SM with three others

@@ -61,12 +61,20 @@ def main():
         import torch.distributed as dist
         dist.barrier()
         if rank != 0:
+            # every rank keeps its raw stamps (absolute %globaltimer ns: the GPUs of a box share the time base closely
+            # enough to line the ranks up to a few us) next to rank 0's report
+            S, K = L.SNN_TL_STEPS, L.SNN_TL_CLASSES
+            buf = np.zeros(2 * K * S, np.uint64)
+            L.check(L.load().snn_debug_timeline(net._h, buf.ctypes.data_as(C.c_void_p), buf.size))
+            np.save(a.out.replace(".json", f"_rank{rank}.npy"), buf.reshape(2, K, S))
             dist.destroy_process_group()
             return
     S, K = L.SNN_TL_STEPS, L.SNN_TL_CLASSES
     buf = np.zeros(2 * K * S, np.uint64)
     L.check(L.load().snn_debug_timeline(net._h, buf.ctypes.data_as(C.c_void_p), buf.size))
     tl = buf.reshape(2, K, S)
+    if world > 1:
+        np.save(a.out.replace(".json", "_rank0.npy"), tl)
     valid = tl[1] > 0
     valid[13:16, :] = False   # classes 13-15 carry per-SM diagnostics of the chain, not (begin, end) stamps
     t0 = int(tl[0][valid].min())
