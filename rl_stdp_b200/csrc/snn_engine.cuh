@@ -1546,6 +1546,44 @@ __global__ void learn_ctl_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ c
   else if (threadIdx.x == 0) p.lc->state = (p.lc->state & 0x80000000u) | kFrontAll;
 }
 
+__device__ __forceinline__ Vec4<float> ld4cg(const float* p) {
+  float4 r = __ldcg(reinterpret_cast<const float4*>(p));
+  Vec4<float> o; o.x[0] = r.x; o.x[1] = r.y; o.x[2] = r.z; o.x[3] = r.w; return o;
+}
+__device__ __forceinline__ Vec4<double> ld4cg(const double* p) {
+  double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p + 2));
+  Vec4<double> o; o.x[0] = a.x; o.x[1] = a.y; o.x[2] = b.x; o.x[3] = b.y; return o;
+}
+
+// Dense spill of the update log (a region was full): dsd holds a few thousand non-zeros among E entries.  16-byte
+// loads, four of them in flight per thread (an entry at a time made the scan a chain of E / threads dependent round
+// trips: 360 us for the 12.5 M synapses of an 8-way partition, on the critical path of every learn period).
+template <typename T>
+static __device__ __noinline__ void spill_merge(T* __restrict__ dsd, typename Real2<T>::type* __restrict__ w, const int64_t E,
+                                                const int64_t tid, const int64_t nth) {
+  const int64_t n4 = E >> 2;
+  for (int64_t q0 = tid; q0 < n4; q0 += 4 * nth) {
+    Vec4<T> d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t q = q0 + u * nth;
+      if (q < n4) d[u] = ld4cg(dsd + (q << 2));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t q = q0 + u * nth;
+      if (q >= n4) break;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (d[u].x[c] != (T)0) { red_add(&w[(q << 2) + c].y, d[u].x[c]); dsd[(q << 2) + c] = (T)0; }
+    }
+  }
+  for (int64_t e = (n4 << 2) + tid; e < E; e += nth) {
+    const T dv = __ldcg(dsd + e);
+    if (dv != (T)0) { red_add(&w[e].y, dv); dsd[e] = (T)0; }
+  }
+}
+
 // one block per log region (block-stride); empties the regions it replays
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -1562,13 +1600,8 @@ learn_replay_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k,
     __syncthreads();
     if (threadIdx.x == 0 && cnt) p.log_cnt[(size_t)r * kLogStride] = 0u;
   }
-  if (p.lc->spilled) {
-    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = tid; e < p.E; e += nth) {
-      const T d = p.dsd[e];
-      if (d != (T)0) { red_add(&w[e].y, d); p.dsd[e] = (T)0; }
-    }
-  }
+  if (p.lc->spilled)
+    spill_merge<T>(p.dsd, w, p.E, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
   if (begin_next) {
     // the last block to finish begins the next pass: one node less on the learn step's critical path
     __shared__ int s_last;
@@ -1701,14 +1734,6 @@ __device__ __forceinline__ void chain_arrive(ChainCtl* c, int which) {
   red_add(&c->w[which * 32], 1u);
 }
 
-__device__ __forceinline__ Vec4<float> ld4cg(const float* p) {
-  float4 r = __ldcg(reinterpret_cast<const float4*>(p));
-  Vec4<float> o; o.x[0] = r.x; o.x[1] = r.y; o.x[2] = r.z; o.x[3] = r.w; return o;
-}
-__device__ __forceinline__ Vec4<double> ld4cg(const double* p) {
-  double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p + 2));
-  Vec4<double> o; o.x[0] = a.x; o.x[1] = a.y; o.x[2] = b.x; o.x[3] = b.y; return o;
-}
 
 constexpr int kChainNeuronThreads = 512, kChainLearnThreads = 128, kSpkWave = 256;
 
@@ -2272,7 +2297,9 @@ chain_synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl*
     }
     // (each instantiation of the wave appears once: four inlined copies cost 200 bytes of spills per thread)
     if (k >= 0) {  // LTD of the arrivals of step k, fused with the look-ahead pushes unless this is a learn step
-      synapse_wave<T, true>(p, cx, k, learn ? 1 : r_lo, learn ? 0 : r_hi, d.ring, bid, nblk, region, wsm);
+      // (the log region rotates with the step: a block whose slice of the items carries most of the plastic visits —
+      // in a partition the local spikers sit together in the list — does not fill one region on its own)
+      synapse_wave<T, true>(p, cx, k, learn ? 1 : r_lo, learn ? 0 : r_hi, d.ring, bid, nblk, (region + (uint32_t)k) % d.SB, wsm);
       arrive(cLtd);
       if (!learn && threadIdx.x == 0) red_add(&ctl->w[cPush * 32], 1u);  // ordered after the fence of the arrive above
     }
@@ -2295,7 +2322,8 @@ chain_synapse_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl*
 // one thread per spiker fetches the bounds of its list, then one thread per INCOMING SYNAPSE, three in flight.
 template <typename T>
 __device__ __forceinline__ void ltp_wave(const DevNet<T>& p, const WindowCtx<T>* __restrict__ cx, int32_t k,
-                                         const uint32_t bid, const uint32_t nblk, WaveSmem& sm) {
+                                         const uint32_t bid, const uint32_t nblk, const uint32_t region, WaveSmem& sm) {
+  // region: the sd-update log region this block appends to in this step (one block per region and step)
   typedef Ops<T> O;
   tl_begin(p.tl, 2, k);
   const uint32_t tid = threadIdx.x, TB = blockDim.x, lane = tid & 31u;
@@ -2357,7 +2385,7 @@ __device__ __forceinline__ void ltp_wave(const DevNet<T>& p, const WindowCtx<T>*
         if (!ok[u]) continue;
         // pre trace as seen at the synapse: of step t-(d-1) (variant_g: one step earlier)
         const T tr = trace_resolve<T>(p, hq[u], pk[u] & kPreMask, t32 - (int32_t)(pk[u] >> kPreBits) - (p.variant_g ? 1 : 0), t32);
-        sd_add<T>(p, vw, e[u], O::mul(p.apost, tr), p.log_ltp_base + bid, inst[u]);
+        sd_add<T>(p, vw, e[u], O::mul(p.apost, tr), region, inst[u]);
       }
     }
     __syncthreads();
@@ -2373,7 +2401,7 @@ ltp_wave_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, int32_t k) {
   __shared__ WaveSmem wsm;
   if (threadIdx.x == 0) wsm.blk_ev = 0ull;
   __syncthreads();
-  ltp_wave<T>(p, cx, k, blockIdx.x, gridDim.x, wsm);
+  ltp_wave<T>(p, cx, k, blockIdx.x, gridDim.x, p.log_ltp_base + blockIdx.x, wsm);
   __syncthreads();
   if (threadIdx.x == 0 && wsm.blk_ev) p.blk_ltp[blockIdx.x] += wsm.blk_ev;
 }
@@ -2393,7 +2421,7 @@ chain_ltp_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* __r
     }
     __syncthreads();
     if (!s_ok) break;
-    ltp_wave<T>(p, cx, k, blockIdx.x, d.PB, wsm);
+    ltp_wave<T>(p, cx, k, blockIdx.x, d.PB, p.log_ltp_base + (blockIdx.x + (uint32_t)k) % d.PB, wsm);
     __syncthreads();
     if (threadIdx.x == 0) chain_arrive(ctl, kcLtp);
   }
@@ -2465,6 +2493,8 @@ __device__ __forceinline__ void chain_replay(const DevNet<T>& p, const ChainDims
     __syncthreads();
   }
   if (*reinterpret_cast<const volatile uint32_t*>(&p.lc->spilled)) {
+    // (the plain loop, not spill_merge: a call in this role costs the 40-register learn kernel spills in its hot
+    // loops; a spill is rare — the log holds >= 4 M entries and the regions rotate with the step)
     const int64_t tid = bid * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)nblk * blockDim.x;
     for (int64_t e = tid; e < p.E; e += nth) {
       const T dv = __ldcg(p.dsd + e);
@@ -2983,7 +3013,7 @@ class Engine : public IEngine {
       const Launch g = grids();
       p.log_regions = (uint32_t)(g.gA + g.gP); p.log_ltp_base = (uint32_t)g.gA;
       const int64_t log_cap = opt_.learn_log_cap > 0 ? opt_.learn_log_cap
-                                                  : std::min<int64_t>(std::max<int64_t>(1 << 20, n_plastic_ / 8), 1ll << 28);
+                                                  : std::min<int64_t>(std::max<int64_t>(1 << 22, n_plastic_ / 8), 1ll << 28);
       p.log_region_cap = (uint32_t)std::max<int64_t>(1, log_cap / p.log_regions);
       SNN_CUDA_OK(cudaMalloc(&p.dlog, (size_t)p.log_regions * p.log_region_cap * sizeof(LogEntry<T>)));
       SNN_CUDA_OK(cudaMalloc(&p.log_cnt, (size_t)p.log_regions * kLogStride * sizeof(uint32_t)));

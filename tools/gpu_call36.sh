@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=$(nvidia-smi -L | wc -l)
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/r2E_bench_c5_${N}gpu.json 2> gpurun_out/r2E_bench_c5_${N}gpu.err
+echo "bench N=$N rc=$?"
+python - gpurun_out/r2E_bench_c5_${N}gpu.json <<'PY'
+import json,sys
+try:
+    d=json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith('{')][-1])
+    p=d.get('partition') or {}
+    print({k:d[k] for k in ('value','ms_per_step','x_realtime_per_instance','n_gpus')}, {k:p.get(k) for k in ('value','x_realtime','strong_speedup_vs_n1')}, d.get('partition_parity'))
+except Exception as e:
+    print('parse failed', e); print(open(sys.argv[1].replace('.json','.err')).read()[-3000:])
+PY
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 tools/timeline.py --window-ms 100 --out gpurun_out/r2E_timeline_${N}gpu.json > gpurun_out/r2E_timeline_${N}gpu.txt 2>&1; head -24 gpurun_out/r2E_timeline_${N}gpu.txt | grep -v "^\*\|^$\|Setting OMP" | head -22
