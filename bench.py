@@ -58,15 +58,26 @@ B_LEARN = 16       # per plastic synapse per learn pass
 
 
 def learn_traffic(workload):
-    """DRAM bytes per learn_kernel launch from the committed `ncu --set full` capture (same workload)."""
+    """DRAM bytes per learn-pass launch from the committed `ncu --set full` capture (same kernel, same workload):
+    (bytes, file) or (None, None)."""
     if workload != "c5_1M_100M":
-        return None
+        return None, None
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1i_learn_pass_ncu_full.json")))
-        v = [(float(x["dram__bytes_read.sum"]) + float(x["dram__bytes_write.sum"])) * 1e6 for x in d["launches"]]
-        return sum(v) / len(v)
+        name = "r2_step_kernels_ncu_full.json"
+        rows = json.load(open(os.path.join(ROOT, "profiles", name)))
+        v = [(float(x["dram__bytes_read.sum"].split()[0]) + float(x["dram__bytes_write.sum"].split()[0])) * 1e6
+             for x in rows if "learn_pass_tma_kernel" in x["Kernel Name"]]
+        if v:
+            return sum(v) / len(v), name
     except Exception:
-        return None
+        pass
+    try:
+        name = "r1i_learn_pass_ncu_full.json"
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        v = [(float(x["dram__bytes_read.sum"]) + float(x["dram__bytes_write.sum"])) * 1e6 for x in d["launches"]]
+        return sum(v) / len(v), name
+    except Exception:
+        return None, None
 
 
 def peaks():
@@ -226,7 +237,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    common = dict(dtype="f32", mode="fast", noise="philox", device=local, max_delay=dmax, learn_async=args.learn_async,
+    common = dict(dtype=args.dtype, mode="fast", noise="philox", device=local, max_delay=dmax, learn_async=args.learn_async,
                   chain=args.chain, persistent={'auto': None, 'chain': True, 'graph': False}[args.scheduler], chain_lookahead=args.chain_lookahead, wave_kernels=args.waves)
 
     def barrier():
@@ -377,16 +388,19 @@ def run_b200(args):
         peak, peak_src = peaks()
         sim_ms = args.steps * W
         value = ev_all / (dev_ms * 1e-3)
-        learn_bytes = B_LEARN * n_plastic
+        fpw = 2 if args.dtype == "f64" else 1   # every floating-point quantity doubles; indices and bitmaps do not (path-level bytes below: upper bound for f64)
+        learn_bytes = B_LEARN * fpw * n_plastic
         learn_avg_ms = tot["learn_ms"] / max(1, tot["nl"])
         learn_gbs = learn_bytes / (learn_avg_ms * 1e-3) / 1e9 if learn_avg_ms > 0 else 0.0
-        path_bytes = (sim_ms * n * n_inst * B_NEURON + tot["ev"] * B_EVENT + tot["ltp"] * B_LTP + tot["nl"] * learn_bytes)
-        traffic = learn_traffic(args.workload)
+        path_bytes = (fpw * (sim_ms * n * n_inst * B_NEURON + tot["ev"] * B_EVENT + tot["ltp"] * B_LTP) + tot["nl"] * learn_bytes)
+        traffic, traffic_file = learn_traffic(args.workload)
+        if args.dtype != "f32":
+            traffic = traffic_file = None   # the capture is of the fp32 kernel
         line = {
             "metric": "synaptic events/s", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if only_partition else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": bench_config(args, world, only_partition),
             "sim_ms_per_wall_s": sim_ms * n_inst * (1 if only_partition else world) / (dev_ms * 1e-3),
             "x_realtime_per_instance": sim_ms / dev_ms,
@@ -397,13 +411,13 @@ def run_b200(args):
                     "note": "snn_step() with host buffers: train flags + dopamine events in, sorted spike record out"},
             "gpu_launches": (tot["npass"] if tot["npass"] else tot["nl"]) + tot["nn"] + tot["ns"],
             "roofline": {"bound": "hbm",
-                         "kernel": ("learn_pass_tma_kernel<float> (asynchronous pass, timed live beside the step kernels)"
-                                    if tot["npass"] else "learn_kernel<float>"),
+                         "kernel": ("learn_pass_tma_kernel<%s> (asynchronous pass, timed live beside the step kernels)"
+                                    if tot["npass"] else "learn_kernel<%s>") % ("double" if args.dtype == "f64" else "float"),
                          "achieved": learn_gbs, "peak": peak,
                          "unit": "GB/s", "frac": learn_gbs / peak, "traffic": traffic,
                          "traffic_source": (None if traffic is None else
                                             "dram__bytes_read+write per launch from the committed ncu --set full capture "
-                                            "profiles/r1i_learn_pass_ncu_full.json (same kernel, same workload), not measured in this run"),
+                                            "profiles/%s (same kernel, same workload, fp32), not measured in this run" % traffic_file),
                          "peak_source": peak_src,
                          "bytes_per_launch": learn_bytes, "avg_launch_ms": learn_avg_ms,
                          "share_of_step_time": tot["learn_ms"] / dev_ms if dev_ms else None},
@@ -667,6 +681,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5_1M_100M", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="arithmetic type of the production path (f64: the fp64 build of the same kernels, non-contracted arithmetic; not the headline)")
     ap.add_argument("--window-ms", type=int, default=500, help="simulated ms per snn_step() call (one bench step)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-ms-per-step", type=int, default=4, help="--impl reference: simulated ms of the full network per step")

@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if verbose and out:
                     print(out)
     if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-lcudart"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-lcudart", "-ldl"]
         run(cmd)
     return LIB
 

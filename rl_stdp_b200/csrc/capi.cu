@@ -9,8 +9,18 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost a pointer test unless a tool (nsys, ncu --nvtx) is attached
+
 #include "actor.h"
 #include "snn_common.h"
+
+namespace {
+// one NVTX range per entry point that launches device work: a timeline shows which API call a kernel belongs to
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
 
 struct snn_actor {
   snn::Actor impl;
@@ -124,6 +134,7 @@ int32_t snn_set_synapses_csr(snn_net* net, const int64_t* rowptr, const int32_t*
   const int64_t E = rowptr[net->cfg.n_neurons];
   if (E > 0 && (!post || !w)) return fail(SNN_ERR_INVALID, "null post / w");
   std::string err;
+  NvtxRange nv("snn_set_synapses_csr");
   cudaSetDevice(net->cfg.device);
   snn::Topo topo;
   int rc = snn::build_topology(net->cfg, rowptr, post, delay, &topo, net->eng->stream(), err);
@@ -176,6 +187,7 @@ int32_t snn_step(snn_net* net, int32_t n_steps, const double* noise, const uint8
   a.da = da; a.n_da = n_da; a.spikes_out = spikes_out; a.spike_offsets = spike_offsets; a.spikes_cap = spikes_cap;
   a.stats = stats;
   std::string err;
+  NvtxRange nv("snn_step");
   int rc = net->eng->step(a, err);
   if (rc) return fail(rc, err);
   return SNN_OK;
@@ -194,6 +206,7 @@ int32_t snn_step_ex(snn_net* net, const snn_step_io* io) {
   a.probe_syn = io->probe_syn; a.n_probes = io->n_probes; a.probe_out = io->probe_out;
   if (io->n_probes < 0) return fail(SNN_ERR_INVALID, "n_probes < 0");
   std::string err;
+  NvtxRange nv("snn_step_ex");
   int rc = net->eng->step(a, err);
   return rc ? fail(rc, err) : SNN_OK;
 }
@@ -357,6 +370,7 @@ int32_t snn_actor_window(snn_actor* a, int32_t n_steps, const double* intensity,
                          int32_t reset_v, int32_t* counts, int32_t* spike_masks, double* device_ms) {
   if (!a) return fail(SNN_ERR_INVALID, "null actor");
   std::string err;
+  NvtxRange nv("snn_actor_window");
   int rc = a->impl.window(n_steps, intensity, train, critic, reset_v, counts, spike_masks, device_ms, err);
   return rc ? fail(rc, err) : SNN_OK;
 }
@@ -364,6 +378,7 @@ int32_t snn_actor_window(snn_actor* a, int32_t n_steps, const double* intensity,
 int32_t snn_actor_learn(snn_actor* a, int32_t critic) {
   if (!a) return fail(SNN_ERR_INVALID, "null actor");
   std::string err;
+  NvtxRange nv("snn_actor_learn");
   int rc = a->impl.learn(critic, err);
   return rc ? fail(rc, err) : SNN_OK;
 }
@@ -374,6 +389,7 @@ int32_t snn_actor_episodes(snn_actor* a, const double* matalpha, const double* s
                            double* device_ms) {
   if (!a) return fail(SNN_ERR_INVALID, "null actor");
   std::string err;
+  NvtxRange nv("snn_actor_episodes");
   int rc = a->impl.episodes(SNN_ENV_CARTPOLE, matalpha, state0, tie_actions, n_decisions_max, teach_actions,
                             n_decisions_max, win_size, train, rewards, n_decisions, n_rand, state_out, device_ms, err);
   return rc ? fail(rc, err) : SNN_OK;
@@ -385,6 +401,7 @@ int32_t snn_actor_episodes_env(snn_actor* a, int32_t env, const double* matalpha
                                double* state_out, double* device_ms) {
   if (!a) return fail(SNN_ERR_INVALID, "null actor");
   std::string err;
+  NvtxRange nv("snn_actor_episodes_env");
   int rc = a->impl.episodes(env, matalpha, state0, tie_picks, tie_stride, nullptr, n_decisions_max, win_size, train,
                             rewards, n_decisions, n_rand, state_out, device_ms, err);
   return rc ? fail(rc, err) : SNN_OK;
