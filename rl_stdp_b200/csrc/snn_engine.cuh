@@ -2670,6 +2670,31 @@ static __global__ void segL_kernel(const uint32_t* __restrict__ seg, int64_t N, 
     out[i] = make_uint4(seg[i * stride], seg[i * stride + 1], seg[i * stride + (Dmax < 2 ? Dmax : 2)],
                         seg[i * stride + (Dmax < 3 ? Dmax : 3)]);
 }
+// The spike record of a window: every step's ids are appended in arrival order (atomics); the API returns them
+// ascending inside a step.  One block per step sorts its segment in shared memory (bitonic network, padded to a power
+// of two) — a step of C5 has ~1 300 spikes; segments longer than kRecSortMax go through the library sort instead.
+constexpr int kRecSortMax = 8192, kRecSortThreads = 1024;
+static __global__ void __launch_bounds__(kRecSortThreads)
+record_sort_kernel(int32_t* __restrict__ rec, const int32_t* __restrict__ off) {
+  __shared__ int32_t s_key[kRecSortMax];
+  const int32_t lo = off[blockIdx.x], len = off[blockIdx.x + 1] - lo;
+  if (len <= 1 || len > kRecSortMax) return;
+  int P = 2;
+  while (P < len) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += kRecSortThreads) s_key[i] = i < len ? rec[lo + i] : 0x7fffffff;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int c = threadIdx.x; c < (P >> 1); c += kRecSortThreads) {
+        const int i = ((c / stride) * stride << 1) + (c % stride), j = i + stride;  // comparator (i, j)
+        const bool up = (i & size) == 0;
+        const int32_t a = s_key[i], b = s_key[j];
+        if ((a > b) == up) { s_key[i] = b; s_key[j] = a; }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < len; i += kRecSortThreads) rec[lo + i] = s_key[i];
+}
 // caller order <-> internal order through perm; comp 0 = w, 1 = sd
 template <typename T>
 __global__ void wsd_from_caller(const double* __restrict__ in, const uint32_t* __restrict__ perm,
@@ -3987,7 +4012,7 @@ bool Engine<T>::chain_plan(bool with_learn, std::string* why) {
   }
   d.g_arr_log2 = g_arr_log2_; d.g_ltp_log2 = g_ltp_log2_; d.pass_stages = S;
   d.thrN = thrN; d.thrP = thrP; d.thrL = thrL;
-  d.la = std::min(kMaxLook, std::max(1, opt_.chain_look > 0 ? opt_.chain_look : 2));
+  d.la = std::min(kMaxLook, std::max(1, opt_.chain_look > 0 ? opt_.chain_look : 1));
   d.ring = d.la + 1;
   d.do_decay = cfg_.sd_decay_mode == SNN_SD_DECAY_ON_LEARN ? 1 : 0;
   chain_ = d; chain_smem_neuron_ = smem_n; chain_smem_learn_ = smem_l;
@@ -4253,8 +4278,14 @@ int Engine<T>::step(const StepArgs& a, std::string& err) {
     SNN_CUDA_OK(cudaMemcpyAsync(h_off.data(), b_rec_off_.ptr, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     SNN_CUDA_OK(cudaStreamSynchronize(stream_));
     const int64_t total = h_off[n];
-    int src = sort_segments(b_rec_.as<int32_t>(), total, b_rec_off_.as<int32_t>(), n, stream_, &sort_scratch_, err);
-    if (src) return src;
+    int32_t longest = 0;
+    for (int k = 0; k < n; ++k) longest = std::max(longest, h_off[k + 1] - h_off[k]);
+    if (longest <= kRecSortMax) {
+      if (longest > 1) record_sort_kernel<<<n, kRecSortThreads, 0, stream_>>>(b_rec_.as<int32_t>(), b_rec_off_.as<int32_t>());
+    } else {  // a step with more spikes than a block sorts in shared memory (a burst): the library's segmented sort
+      int src = sort_segments(b_rec_.as<int32_t>(), total, b_rec_off_.as<int32_t>(), n, stream_, &sort_scratch_, err);
+      if (src) return src;
+    }
     if (total > 0) SNN_CUDA_OK(cudaMemcpyAsync(a.spikes_out, b_rec_.ptr, total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
     for (int k = 0; k <= n; ++k) a.spike_offsets[k] = h_off[k];
   }
