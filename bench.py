@@ -420,6 +420,10 @@ def run_b200(args):
                                             "profiles/%s (same kernel, same workload, fp32), not measured in this run" % traffic_file),
                          "peak_source": peak_src,
                          "bytes_per_launch": learn_bytes, "avg_launch_ms": learn_avg_ms,
+                         "note": ("timed live: the pass shares HBM with the step roles that run beside it for its whole "
+                                  "duration (persistent chain); the same kernel alone streams the same bytes in 198 us "
+                                  "= 0.99 of the measured peak (ncu, profiles/r2_step_kernels_ncu_full.json); "
+                                  "roofline_path is the whole step path against the same peak"),
                          "share_of_step_time": tot["learn_ms"] / dev_ms if dev_ms else None},
             "roofline_path": {"algorithmic_bytes": path_bytes, "achieved": path_bytes / (dev_ms * 1e-3) / 1e9,
                               "unit": "GB/s", "frac": path_bytes / (dev_ms * 1e-3) / 1e9 / peak},
@@ -689,7 +693,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exp-flags", type=int, default=0, help="snn_config.reserved[1] diagnostics (2 timeline, 4 serialise the learn pass, 512 LSU pass); 0 for reported numbers")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--chain", default=None, help="persistent chain footprints 'nthr,syn,ltp,ltp_thr,learn,learn_thr,stages' (sweeps; default: the library's)")
+    ap.add_argument("--chain", default=None, help="persistent chain footprints 'nthr,syn,ltp,ltp_thr,learn,neuron_regs,stages' (sweeps; default: the library's)")
     ap.add_argument("--chain-lookahead", type=int, default=0, help="persistent chain: steps of push lookahead (0 = default)")
     ap.add_argument("--waves", action="store_true", help="captured graph: the chain's wave kernels instead of the group-per-item side kernels")
     ap.add_argument("--scheduler", default="auto", choices=["auto", "chain", "graph"],

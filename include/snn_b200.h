@@ -213,7 +213,7 @@ int32_t snn_set_synapses_dense_col(snn_net* net, const double* s_colmajor,
  *      "learn_pass_blocks", "learn_pass_stages", "learn_pass_tile_k" [S]   asynchronous pass of the graph path
  *      "synapse_blocks_per_sm", "ltp_blocks_per_sm" [S]                    side kernels of the graph path
  *      "chain_neuron_threads", "chain_synapse_blocks", "chain_ltp_blocks", "chain_ltp_threads",
- *      "chain_learn_blocks", "chain_learn_threads", "chain_learn_stages"   footprints of the chain's roles
+ *      "chain_learn_blocks", "chain_neuron_registers", "chain_learn_stages"   footprints of the chain's roles (sweeps)
  *      "timeline"              1: kernels stamp %globaltimer for snn_debug_timeline (diagnostic); 2: the chain's phase
  *                              classes are stamped by one block of the neuron role instead of the envelope over all
  *      "serialise_learn_pass", "neuron_blocks_256", "lsu_pass"             A/B switches (diagnostic)

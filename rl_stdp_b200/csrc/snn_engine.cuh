@@ -2903,7 +2903,7 @@ class Engine : public IEngine {
         {"lsu_pass", &opt_.lsu_pass, false}, {"learn_lazy", &opt_.learn_lazy, true},
         {"chain_neuron_threads", &opt_.chain[0], false}, {"chain_synapse_blocks", &opt_.chain[1], false},
         {"chain_ltp_blocks", &opt_.chain[2], false}, {"chain_ltp_threads", &opt_.chain[3], false},
-        {"chain_learn_blocks", &opt_.chain[4], false}, {"chain_learn_threads", &opt_.chain[5], false},
+        {"chain_learn_blocks", &opt_.chain[4], false}, {"chain_neuron_registers", &opt_.chain[5], false},
         {"chain_learn_stages", &opt_.chain[6], false}, {"chain_lookahead", &opt_.chain_look, false}, {"wave_kernels", &opt_.waves, false}, {"chain_synapse_groups", &opt_.chain_groups, false}};
     for (const E& e : ints) if (n == e.name) { *pi = e.i; *structural = e.st; return 1; }
     if (n == "learn_log_cap") { *pl = &opt_.learn_log_cap; *structural = true; return 1; }
@@ -3963,14 +3963,14 @@ bool Engine<T>::chain_plan(bool with_learn, std::string* why) {
   // work-proportional block counts: small nets get small grids (every waiting block polls the counters)
   const int64_t ev_guess = std::max<int64_t>(1, p.E / 64);  // synapse visits per step at ~1.5 % of the neurons firing
   // role footprints per SM (defaults measured on C5; snn_set_param "chain_*" overrides them for sweeps)
-  int tune[7] = {256, 2, 1, 128, 2, 128, 3};
+  int tune[7] = {256, 2, 1, 128, 2, 0, 3};
   for (int q = 0; q < 7; ++q) if (opt_.chain[q] > 0) tune[q] = opt_.chain[q];
   const int thrN = std::min(kChainNeuronThreads, std::max(32, tune[0] / 32 * 32));
   int syn_per_sm = tune[1], ltp_per_sm = tune[2], learn_per_sm = tune[4];
-  const int thrP = std::min(256, std::max(32, tune[3] / 32 * 32)), thrL = kChainLearnThreads;  // (tune[5] is not used any more)
+  const int thrP = std::min(256, std::max(32, tune[3] / 32 * 32)), thrL = kChainLearnThreads;
   int S = std::min(kPassMaxStages, std::max(2, tune[6]));
   size_t smem_l = (size_t)S * kPassChunkBytes;
-  const bool lean = thrN > 256 && tune[5] != 64;  // the 40-register build of the neuron role ("chain_learn_threads" = 64: sweeps of the 64-register build with more threads)
+  const bool lean = thrN > 256 && tune[5] != 64;  // more than 256 threads: the 40-register build of the neuron role, unless "chain_neuron_registers" = 64 (sweeps)
   cudaFuncAttributes fa[5];
   {
     const ChainKernelInfo& ki = chain_kernel_info();

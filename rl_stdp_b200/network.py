@@ -82,10 +82,10 @@ class SparseNetwork:
         opts["chain_lookahead"] = int(params.pop("chain_lookahead", 0))  # 0 = the library's default
         if bool(params.pop("wave_kernels", False)):
             opts["wave_kernels"] = 1   # captured graph: the chain's load-balanced waves instead of the group-per-item side kernels
-        chain = params.pop("chain", None)  # "nthr,syn,ltp,ltp_thr,learn,learn_thr,stages" (sweeps)
+        chain = params.pop("chain", None)  # "nthr,syn,ltp,ltp_thr,learn,neuron_regs,stages" (sweeps; 0 = default)
         if chain:
             names = ("chain_neuron_threads", "chain_synapse_blocks", "chain_ltp_blocks", "chain_ltp_threads",
-                     "chain_learn_blocks", "chain_learn_threads", "chain_learn_stages")
+                     "chain_learn_blocks", "chain_neuron_registers", "chain_learn_stages")
             for nme, v in zip(names, (chain.split(",") if isinstance(chain, str) else chain)):
                 opts[nme] = int(v)
         cfg = default_config(
