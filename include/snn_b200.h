@@ -204,10 +204,10 @@ int32_t snn_set_synapses_dense_col(snn_net* net, const double* s_colmajor,
  *      "persistent"            how production-mode windows are scheduled: -1 (default) automatic; 0 a captured CUDA
  *                              graph of per-step kernels; 1 the persistent chain — one resident kernel per role for
  *                              the whole window, steps handed over through device-side counters.
- *                              Automatic = the chain, except for batches of more than 256 instances and whenever a
+ *                              Automatic = the chain, except whenever a
  *                              profiler (ncu, nsys, compute-sanitizer) or CUDA_LAUNCH_BLOCKING serialises kernels
  *                              (resident roles cannot hand over to kernels that are not running)
- *      "chain_lookahead"       persistent chain: steps of push lookahead, 1..3 (0 = default 1)
+ *      "chain_lookahead"       persistent chain: steps of push lookahead, 1..2 (0 = default 1)
  *      "learn_async"       [S] 0 auto, 1 learn! always in place, 2 always the asynchronous double-buffered pass
  *      "learn_log_cap"     [S] entries of the sd-update log of the asynchronous pass (0 = by size)
  *      "learn_pass_blocks", "learn_pass_stages", "learn_pass_tile_k" [S]   asynchronous pass of the graph path

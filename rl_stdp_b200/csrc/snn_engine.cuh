@@ -115,7 +115,7 @@ constexpr int32_t kNever = -(1 << 30);  // "no spike yet" in hist / old_last
 constexpr int kLag = 3;
 // The persistent chain pushes currents up to kMaxLook steps ahead of their arrival (Engine::launch_chain): Iacc is a
 // ring of kIaccRing buffers there (the other schedulers use the first two, indexed by step parity).
-constexpr int kMaxLook = 3, kIaccRing = 4;
+constexpr int kMaxLook = 2, kIaccRing = 4;  // (a lookahead of 3 was measured 3 % slower than 1; every step of it costs 1 KB of shared memory per wave block)
 constexpr int kMaxRanks = 8;
 
 // State of the asynchronous learn pass.  `state` packs (cur << 31) | frontier, frontier in units
@@ -1735,7 +1735,7 @@ __device__ __forceinline__ void chain_arrive(ChainCtl* c, int which) {
 }
 
 
-constexpr int kChainNeuronThreads = 512, kChainLearnThreads = 128, kSpkWave = 256;
+constexpr int kChainNeuronThreads = 512, kChainLearnThreads = 128, kSpkWave = 128;
 
 // Delay-1 synapses of spiker i pushed warp-cooperatively into Iacc[t&1] — they feed the Euler update of this very
 // step (new_net.jl:116-121).  Weights of synapses the learn pass in flight has not reached are formed on the fly.
@@ -3947,7 +3947,6 @@ bool Engine<T>::chain_plan(bool with_learn, std::string* why) {
   DevNet<T>& p = p_;
   auto fail = [&](const char* m) { if (why) *why = m; return false; };
   if (p.exact || !use_graph_ || opt_.persistent == 0 || p.lazy) return fail("mode");
-  if (opt_.persistent < 0 && p.B > 256) return fail("auto: large batches of small instances run faster as the captured graph");
   if (kernels_are_serialised()) return fail("a profiler or CUDA_LAUNCH_BLOCKING serialises kernels: resident roles could not hand over");
   if (cfg_.sd_decay_mode == SNN_SD_DECAY_EVERY_STEP) return fail("sd decays every step");
   const bool parted = !(p.part_lo == 0 && p.part_hi == p.N);
@@ -3992,7 +3991,7 @@ bool Engine<T>::chain_plan(bool with_learn, std::string* why) {
            threads <= prop.maxThreadsPerMultiProcessor && blocks <= 32;
   };
   while (!fits(syn_per_sm, ltp_per_sm, learn_per_sm)) {
-    if (S > 3) { --S; smem_l = (size_t)S * kPassChunkBytes; }
+    if (S > 2) { --S; smem_l = (size_t)S * kPassChunkBytes; }  // two blocks of two stages stream faster than one block of three (c1_x1024: 375 against 421 us per pass)
     else if (learn_per_sm > 1) --learn_per_sm;
     else if (syn_per_sm > 1) --syn_per_sm;
     else return fail("the four roles do not fit on an SM together");
