@@ -2075,9 +2075,9 @@ chain_neuron_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* 
     tl_end(tq, 9, k);
     if (t_step0 && tid == 0 && smid() < (uint32_t)kTlSteps)
       p.tl[(k == kTlProbeA ? 0 : kTlClasses * kTlSteps) + 15 * kTlSteps + smid()] = gtime_ns() - t_step0;
-    tl_begin(ts, 4, k);  // (solo timeline: class 4 = the fence + counter update of the hand-over)
+    tl_begin(ts, 10, k);  // (solo timeline: class 10 = the fence + counter update of the hand-over)
     if (tid == 0) chain_arrive(ctl, kcNeuron);
-    tl_end(ts, 4, k);
+    tl_end(ts, 10, k);
     tl_end(p.tl, 0, k);
   }
   __syncthreads();
@@ -2610,7 +2610,8 @@ chain_learn_kernel(DevNet<T> p, const WindowCtx<T>* __restrict__ cx, ChainCtl* _
         if (!s_ok) return;
         __syncthreads();
       }
-      unsigned long long* const t4 = (p.exp_flags & 1024) ? nullptr : p.tl;  // (timeline class 4 on one GPU: the early replay)
+      // (timeline class 4 on one GPU: the early replay — the envelope over the role's blocks, or block 0's own with timeline = 2)
+      unsigned long long* const t4 = ((p.exp_flags & 1024) && bid != 0) ? nullptr : p.tl;
       tl_begin(t4, 4, k);
       chain_replay<T>(p, d, bid, LB);
       tl_end(t4, 4, k);

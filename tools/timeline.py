@@ -12,7 +12,7 @@ import bench
 from rl_stdp_b200 import _lib as L, synth
 from rl_stdp_b200.network import SparseNetwork
 
-CLS = ["neuron", "synapse", "ltp", "learn", "remote", "push", "n.wait", "n.cur", "n.euler", "n.spk", "n.noise", "s.A", "s.B", "l.A", "l.B", "-"]
+CLS = ["neuron", "synapse", "ltp", "learn", "remote/replay", "push", "n.wait", "n.cur", "n.euler", "n.spk", "n.fence", "s.A", "s.B", "l.A", "l.B", "-"]
 
 
 def main():
