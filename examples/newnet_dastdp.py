@@ -53,22 +53,27 @@ def main():
         base = win * W                                                    # absolute ms of step 0 is base + 1
         da = [(t - base - 1, 0, 0.5) for t in sorted(rew) if base < t <= base + W]   # `if time in rew` :54: once per ms
         noise = 13.0 * (noise_rng.random((W, N)) - 0.5) if exact else None
-        spikes, _ = net.run(W, noise, train, da_events=da)
-        for k, sp in enumerate(spikes):                                   # reward!(...) :24-34
-            t = base + k + 1
-            if n1 in sp:
+        (ids, offs), _ = net.run(W, noise, train, da_events=da, raw=True)
+        # reward!(...) :24-34 — only the steps in which n1 or n2 fired are looked at (the record is (ids, offsets))
+        hits = np.flatnonzero((ids == n1) | (ids == n2))
+        # (ms, 0 for n1 / 1 for n2): step k is ms base + k + 1; inside one ms n1 is looked at first, as in the script
+        for t, is_n2 in sorted((base + int(np.searchsorted(offs, h, side="right")), int(ids[h] != n1)) for h in hits):
+            if not is_n2:
                 n1f.append(t)
-            if n2 in sp:
+            else:
                 n2f.append(t)
                 if t - n1f[-1] < interval and n2f[-1] > n1f[-1]:
                     tr = t + 1000 + int(rng.integers(1, 2001))
                     rew[tr] = rew.get(tr, 0) + 1
                     n_rewards += 1
-        wv, sd = net.get(L.FIELD_W), net.get(L.FIELD_SD)                  # shist[...] :57-60
-        shist.append(((base + W) / 1000.0, wv[e_target], sd[e_target], wv.mean()))
-        if (win + 1) % (600 * 1000 // W) == 0 or win + 1 == a.seconds * 1000 // W:
+        wt, sdt = net.get_synapses([e_target])                            # shist[...] :57-60: the target synapse only
+        last = win + 1 == a.seconds * 1000 // W
+        report = (win + 1) % (600 * 1000 // W) == 0 or last
+        mean_s = float(net.get(L.FIELD_W).mean()) if report or (win + 1) % 100 == 0 else float("nan")  # every 10 s
+        shist.append(((base + W) / 1000.0, wt[0], sdt[0], mean_s))
+        if report:
             el = time.perf_counter() - t0
-            print(f"t = {(base + W) / 1000:7.1f} s  s[n1,n2] = {wv[e_target]:.4f}  sd = {sd[e_target]:+.4f}  mean s = {wv.mean():.4f}  "
+            print(f"t = {(base + W) / 1000:7.1f} s  s[n1,n2] = {wt[0]:.4f}  sd = {sdt[0]:+.4f}  mean s = {mean_s:.4f}  "
                   f"rewards = {n_rewards}  ({(base + W) / 1000 / el:.1f} simulated s per wall s)", flush=True)
     el = time.perf_counter() - t0
     print(f"{a.seconds} simulated s in {el:.1f} wall s ({a.seconds / el:.1f} x real time, mode {a.mode}); "

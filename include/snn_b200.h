@@ -287,6 +287,10 @@ int32_t snn_reset_v(snn_net* net);
  * always float64 regardless of dtype; count = number of elements. */
 int32_t snn_get_array(snn_net* net, int32_t field, double* host, int64_t count);
 int32_t snn_set_array(snn_net* net, int32_t field, const double* host, int64_t count);
+/* `shist[time,:] = [net.s[n1,syn], net.sd[n1,syn]]` (newnet_DASTDP.jl:57-60): (w, sd) of n (1..4096) synapses, by
+ * their index in the CSR arrays passed to snn_set_synapses_*; either output may be NULL.  A gather of n elements
+ * instead of two E-element copies; the positions of the last query are remembered.  Not with "learn_lazy". */
+int32_t snn_get_synapses(snn_net* net, const int64_t* idx, int32_t n, double* w, double* sd);
 
 int64_t snn_n_synapses(const snn_net* net);
 int64_t snn_step_index(const snn_net* net);

@@ -12,7 +12,7 @@ module RLSTDPB200
 
 import Random
 
-export Network, NetworkCol, step!, run_window!, add_dopamine!, reset_v!, weights, eligibility,
+export Network, NetworkCol, step!, run_window!, add_dopamine!, reset_v!, weights, eligibility, get_synapses,
        set_param!, get_param, checkpoint, restore!,
        ActorPopulation, set_weights!, play_episodes,
        LayeredNetwork, step_LIF!, step_LIF_critic!, learn!, learn_critic!
@@ -109,6 +109,14 @@ function get_array(net::Network, field::Int32, n::Integer)
     out = zeros(Float64, n)
     check(ccall((:snn_get_array, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), net.handle, field, out, n))
     out
+end
+"""`(net.s[n1, syn], net.sd[n1, syn])` (newnet_DASTDP.jl:57-60) for a few synapses: `idx` are 0-based positions in the CSR
+order the net was built with; a gather of `length(idx)` elements instead of two E-element copies."""
+function get_synapses(net::Network, idx::Vector{Int64})
+    w = zeros(Float64, length(idx)); sd = zeros(Float64, length(idx))
+    check(ccall((:snn_get_synapses, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Int32, Ptr{Float64}, Ptr{Float64}),
+                net.handle, idx, Int32(length(idx)), w, sd))
+    (w, sd)
 end
 set_array!(net::Network, field::Int32, a::Vector{Float64}) =
     check(ccall((:snn_set_array, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), net.handle, field, a, length(a)))

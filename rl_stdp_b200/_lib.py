@@ -108,6 +108,7 @@ SYMBOLS = {
     "snn_add_dopamine": (C.c_int32, [_VP, C.c_int32, C.c_double]),
     "snn_reset_v": (C.c_int32, [_VP]),
     "snn_get_array": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int64]),
+    "snn_get_synapses": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP]),
     "snn_set_array": (C.c_int32, [_VP, C.c_int32, _VP, C.c_int64]),
     "snn_n_synapses": (C.c_int64, [_VP]),
     "snn_step_index": (C.c_int64, [_VP]),

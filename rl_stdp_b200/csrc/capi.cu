@@ -288,6 +288,13 @@ int32_t snn_get_array(snn_net* net, int32_t field, double* host, int64_t count) 
   return rc ? fail(rc, err) : SNN_OK;
 }
 
+int32_t snn_get_synapses(snn_net* net, const int64_t* idx, int32_t n, double* w, double* sd) {
+  if (!net) return fail(SNN_ERR_INVALID, "null net");
+  std::string err;
+  int rc = net->eng->get_synapses(idx, n, w, sd, err);
+  return rc ? fail(rc, err) : SNN_OK;
+}
+
 int32_t snn_set_array(snn_net* net, int32_t field, const double* host, int64_t count) {
   if (!net || !host) return fail(SNN_ERR_INVALID, "null argument");
   std::string err;

@@ -91,6 +91,7 @@ class IEngine {
   virtual int step(const StepArgs& a, std::string& err) = 0;
   virtual int get_array(int field, double* host, int64_t count, std::string& err) = 0;
   virtual int set_array(int field, const double* host, int64_t count, std::string& err) = 0;
+  virtual int get_synapses(const int64_t* idx, int32_t n, double* w, double* sd, std::string& err) = 0;
   virtual int add_dopamine(int instance, double amount, std::string& err) = 0;
   virtual int reset_v(std::string& err) = 0;
   virtual int checkpoint_bytes(int64_t* bytes, std::string& err) = 0;

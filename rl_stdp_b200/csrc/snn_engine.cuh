@@ -2721,6 +2721,16 @@ static __global__ void probe_locate_kernel(const uint32_t* __restrict__ perm, in
     for (int q = 0; q < n; ++q) if (want[q] == c) pos[q] = (uint32_t)e;
   }
 }
+// (w, sd) of a few chosen synapses, read between two windows (snn_get_synapses)
+template <typename T>
+__global__ void gather_syn_kernel(const typename Real2<T>::type* __restrict__ wsd, const uint32_t* __restrict__ pos, int n,
+                                  double* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const typename Real2<T>::type ws = wsd[pos[q]];
+  out[2 * q] = (double)ws.x;
+  out[2 * q + 1] = (double)ws.y;
+}
 template <typename T>
 __global__ void probe_kernel(DevNet<T> p, const uint32_t* __restrict__ pos, int n, double* __restrict__ out, int32_t k) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -3066,6 +3076,7 @@ class Engine : public IEngine {
     g_arr_log2_ = pick_group(mean_row / p.Dmax);
     g_ltp_log2_ = pick_group(mean_row);
     have_topo_ = true;
+    syn_want_.clear();  // positions cached by snn_get_synapses belong to the previous synapse order
     return SNN_OK;
   }
 
@@ -3118,6 +3129,33 @@ class Engine : public IEngine {
     to_double_kernel<T><<<grid_for(n), 256, 0, stream_>>>(src, d, n, scale);
     SNN_CUDA_OK(cudaMemcpyAsync(host, d, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    return SNN_OK;
+  }
+
+  // `net.s[n1, syn]`, `net.sd[n1, syn]` (newnet_DASTDP.jl:57-60): a few synapses by their index in the caller's CSR
+  // order, without the 2 x E-element round trip of get_array.  The positions of the last query are remembered: the
+  // reference reads the same synapses every 100 ms.
+  int get_synapses(const int64_t* idx, int32_t n, double* w, double* sd, std::string& err) override {
+    if (!have_topo_) { err = "synapses not set"; return SNN_ERR_STATE; }
+    if (n < 1 || n > 4096 || !idx || (!w && !sd)) { err = "get_synapses: 1..4096 indices and at least one output"; return SNN_ERR_INVALID; }
+    if (p_.lazy) { err = "get_synapses is not available with event-driven learning (use snn_get_array)"; return SNN_ERR_INVALID; }
+    for (int q = 0; q < n; ++q)
+      if (idx[q] < 0 || idx[q] >= p_.E) { err = "synapse index out of range"; return SNN_ERR_INVALID; }
+    SNN_CUDA_OK(cudaSetDevice(cfg_.device));
+    SNN_CUDA_OK(b_syn_pos_.reserve(n * sizeof(uint32_t), stream_));
+    SNN_CUDA_OK(b_stage_.reserve((size_t)n * 2 * sizeof(double) + n * sizeof(int64_t), stream_));
+    double* d_out = b_stage_.as<double>();
+    if (syn_want_.size() != (size_t)n || !std::equal(syn_want_.begin(), syn_want_.end(), idx)) {
+      int64_t* d_want = reinterpret_cast<int64_t*>(d_out + 2 * (size_t)n);
+      SNN_CUDA_OK(cudaMemcpyAsync(d_want, idx, n * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+      probe_locate_kernel<<<grid_for(p_.E), 256, 0, stream_>>>(topo_.perm, p_.E, d_want, n, b_syn_pos_.as<uint32_t>());
+      syn_want_.assign(idx, idx + n);
+    }
+    gather_syn_kernel<T><<<(n + 63) / 64, 64, 0, stream_>>>(p_.wsdX[cur_], b_syn_pos_.as<uint32_t>(), n, d_out);
+    std::vector<double> h(2 * (size_t)n);
+    SNN_CUDA_OK(cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    SNN_CUDA_OK(cudaStreamSynchronize(stream_));
+    for (int q = 0; q < n; ++q) { if (w) w[q] = h[2 * q]; if (sd) sd[q] = h[2 * q + 1]; }
     return SNN_OK;
   }
 
@@ -3431,7 +3469,7 @@ class Engine : public IEngine {
     for (auto& e : chain_ev_) { if (e) cudaEventDestroy(e); e = nullptr; }
     b_sched_.release();
     b_noise_.release(); b_noise64_.release(); b_ev_off_.release(); b_ev_inst_.release(); b_ev_amt_.release();
-    sort_scratch_.release(); b_stage_.release(); b_probe_want_.release(); b_probe_pos_.release(); b_probe_out_.release();
+    sort_scratch_.release(); b_stage_.release(); b_probe_want_.release(); b_probe_pos_.release(); b_probe_out_.release(); b_syn_pos_.release(); syn_want_.clear();
     b_force_.release(); b_rec_.release(); b_rec_off_.release(); b_cur_idx_.release(); b_cur_val_.release();
     topo_.release();
     if (ev_begin_) cudaEventDestroy(ev_begin_);
@@ -3611,7 +3649,8 @@ class Engine : public IEngine {
   unsigned long long* h_blk_ = nullptr;
   DevBuf b_noise_, b_noise64_, b_ev_off_, b_ev_inst_, b_ev_amt_, b_force_, b_rec_, b_rec_off_, b_cur_idx_, b_cur_val_;
   SortScratch sort_scratch_;
-  DevBuf b_probe_want_, b_probe_pos_, b_probe_out_, b_stage_;
+  DevBuf b_probe_want_, b_probe_pos_, b_probe_out_, b_stage_, b_syn_pos_;
+  std::vector<int64_t> syn_want_;  // the synapses b_syn_pos_ holds the internal positions of (snn_get_synapses)
   std::vector<void*> ipc_opened_;
   snn_exchange_fn exchange_ = nullptr; void* exchange_user_ = nullptr; int exchange_failed_ = 0;
   const std::vector<cudaEvent_t>* graph_prof_events_ = nullptr;

@@ -146,12 +146,13 @@ class SparseNetwork:
 
     # -- step!(net[, input_spikes], train) for a whole window
     def run(self, n_steps, noise=None, train=None, da_events=None, force=None, record=True,
-            spikes_cap=None, profile=False, currents=None, probes=None):
+            spikes_cap=None, profile=False, currents=None, probes=None, raw=False):
         """Runs n_steps milliseconds on the device.  noise: [n_steps, n_neurons] float64 or None;
         train: bool array [n_steps] (learn! after that step); da_events: [(step, instance,
         amount)]; force: [(step, neuron)]; currents: [(step, neuron, current)] (injected-current
         input!); probes: synapse indices (caller's CSR order) whose (w, sd) is recorded after every step
-        into self.last_probes [n_steps, n_probes, 2].  Returns (list of ascending spike-id arrays, stats)."""
+        into self.last_probes [n_steps, n_probes, 2].  Returns (list of ascending spike-id arrays, stats); with
+        raw=True the record as the C ABI returns it, (ids [n_spikes], offsets [n_steps + 1]), instead of the list."""
         lib = L.load()
         n_steps = int(n_steps)
         if noise is not None:
@@ -209,7 +210,9 @@ class SparseNetwork:
         stats = StepStats(st.n_spikes, st.n_syn_events, st.n_ltp_events, st.device_ms, st.learn_ms, st.neuron_ms,
                           st.synapse_ms, st.learn_launches, st.neuron_launches, st.synapse_launches, st.reserved)
         spikes = None
-        if record:
+        if record and raw:
+            spikes = (out[:offs[n_steps]], offs)
+        elif record:
             spikes = [out[offs[k]:offs[k + 1]].copy() for k in range(n_steps)]
         if probe_out is not None:
             self.last_probes = probe_out  # [n_steps, n_probes, (w, sd)] after every step
@@ -221,6 +224,14 @@ class SparseNetwork:
         out = np.zeros(n, np.float64)
         L.check(L.load().snn_get_array(self._h, field, _ptr(out), n))
         return out
+
+    def get_synapses(self, idx):
+        """(w, sd) of the synapses `idx` (positions in the CSR arrays the net was built from) — `net.s[n1, syn]`,
+        `net.sd[n1, syn]` of newnet_DASTDP.jl:57-60 without copying all E of them."""
+        idx = np.ascontiguousarray(idx, np.int64)
+        w, sd = np.zeros(idx.size, np.float64), np.zeros(idx.size, np.float64)
+        L.check(L.load().snn_get_synapses(self._h, _ptr(idx), idx.size, _ptr(w), _ptr(sd)))
+        return w, sd
 
     def set(self, field, arr):
         a = np.ascontiguousarray(arr, np.float64)

@@ -173,3 +173,30 @@ def test_spike_record_is_ascending_for_sparse_steps_and_bursts():
     for k in range(T):
         assert np.all(np.diff(got[k]) > 0), k
         assert np.array_equal(got[k], ref[k]), k
+
+
+def test_get_synapses_matches_get_array():
+    """snn_get_synapses (the reference's `net.s[n1, syn]`, `net.sd[n1, syn]` reads) against the full arrays, before and
+    after learning, with a repeated and a changed index set; error paths."""
+    from rl_stdp_b200 import synth
+    from rl_stdp_b200.network import SparseNetwork
+    L = _L()
+    n, ne, dmax, rowptr, post, w, delay = _delay_net(seed=71, n=1500, ne=1200, fan=40, dmax=5)
+    net = SparseNetwork(n, ne, rowptr, post, w, delay, dtype="f64", mode="fast", max_delay=dmax)
+    E = len(post)
+    rng = np.random.default_rng(72)
+    idx = rng.choice(E, 300, replace=False)
+    gw, gsd = net.get_synapses(idx)
+    assert np.array_equal(gw, np.asarray(w, np.float64)[idx]) and not gsd.any()
+    noise = synth.thalamic_noise(120, n, seed=73)
+    train = np.array([(k + 1) % 10 == 0 for k in range(120)], np.uint8)
+    net.run(120, noise, train, da_events=[(30, 0, 0.5)], record=False)
+    W, SD = net.get(L.FIELD_W), net.get(L.FIELD_SD)
+    for ix in (idx, idx, idx[::-1].copy(), np.array([0, E - 1])):   # same set twice (cached positions), then others
+        gw, gsd = net.get_synapses(ix)
+        assert np.array_equal(gw, W[ix]) and np.array_equal(gsd, SD[ix])
+    assert np.abs(SD).sum() > 0
+    with pytest.raises(RuntimeError):
+        net.get_synapses([E])
+    with pytest.raises(RuntimeError):
+        net.get_synapses(np.zeros(5000, np.int64))
