@@ -222,9 +222,10 @@ struct DevNet {
   unsigned long long* tl;
 };
 
-// timeline classes: 0 neuron, 1 synapse, 2 ltp, 3 learn, 4 remote, 5 push; phases of the persistent chain's roles:
-// 6 neuron wait, 7 currents (phase 1), 8 Euler + detect (phase 2), 9 spikers (phase 3), 10 noise of the next step,
-// 11 / 12 synapse wave stage A / B, 13 / 14 ltp wave stage A / B
+// timeline classes: 0 neuron, 1 synapse, 2 ltp, 3 learn, 4 remote (one GPU: the learn role's early replay), 5 push; phases
+// of the persistent chain's roles: 6 neuron wait, 7 currents (phase 1), 8 Euler + detect (phase 2), 9 spikers (phase 3),
+// 10 the fence + signal of the hand-over (timeline = 2 only; 5 then is retire + block barrier),
+// 11 / 12 synapse wave stage A / B (timeline = 2: the two halves of the neuron role's spiker wave), 13 - 15 per-SM diagnostics
 constexpr int kTlSteps = 258, kTlClasses = 16;
 __device__ __forceinline__ unsigned long long gtime_ns() {
   unsigned long long t;
