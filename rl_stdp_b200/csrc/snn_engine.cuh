@@ -1731,7 +1731,9 @@ __device__ __forceinline__ uint32_t syn_ltd_phases(const ChainDims& d, int g, in
 
 // all threads of the block have finished their part (call after __syncthreads, from one thread)
 __device__ __forceinline__ void chain_arrive(ChainCtl* c, int which) {
-  __threadfence();
+  // release: an acq_rel fence, not __threadfence() — that one is a sequentially consistent fence (MEMBAR.SC), which
+  // the hand-off does not need and which waits longer under the learn pass's traffic
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
   red_add(&c->w[which * 32], 1u);
 }
 
